@@ -1,0 +1,155 @@
+/* nwb.h - C ABI of the B200-native NAO whole-body validity / planning core.
+ *
+ * Drop-in boundary for the data-parallel hot path of burgetf/nao_wholebody_planning.  Every entry
+ * point names the reference interface it replaces (file:line relative to the reference checkout):
+ *   RP  = rrt_connect_planner/src/rrt_planner.cpp
+ *   RPh = rrt_connect_planner/include/rrt_connect_planner/rrt_planner.h
+ *   LP  = rrt_connect_planner/src/local_planner.cpp
+ *   SCG = rrt_connect_planner/src/stable_config_generator.cpp
+ *   NCK = rrt_connect_planner/src/nao_constraint_kinematics.cpp
+ *   NPC = rrt_connect_planner/src/nao_planner_control.cpp
+ *
+ * Conventions
+ *   - A configuration is NWB_NJ = 21 doubles in the planner's joint order (RP:2003-2023), row-major.
+ *   - Plain pointers and sizes only; the caller owns every buffer, the library owns nwb_ctx / nwb_tree.
+ *   - Every function returns 0 (NWB_OK) or a negative NWB_E_* code; nothing exits or throws across
+ *     the ABI (the reference calls exit(1) on I/O errors, SCG:205,218, RP:1440).
+ *   - A context is bound to one CUDA device and one stream and is not re-entrant (the reference's
+ *     planner objects are not either: RPh:137-138); use one context per GPU / per host thread.
+ *   - `*_dev` variants take device pointers on the context's device and only enqueue work on the
+ *     context's stream (no host synchronisation); call nwb_ctx_synchronize() to wait.
+ *   - There is no CPU fallback: without a usable CUDA device nwb_ctx_create fails with NWB_E_CUDA.
+ */
+#ifndef NWB_H_
+#define NWB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NWB_NJ 21          /* joints per configuration (RP:2001-2023)                       */
+#define NWB_NFRAMES 29     /* link frames returned by nwb_fk_batch (models/nao_h25_rfoot)  */
+#define NWB_ABI_VERSION 1
+
+/* error codes */
+#define NWB_OK 0
+#define NWB_E_INVALID (-1)   /* bad argument (NULL, negative size, wrong length: NPC:242 has no check) */
+#define NWB_E_CUDA (-2)      /* CUDA runtime error; text in nwb_last_error()                   */
+#define NWB_E_NOMEM (-3)
+#define NWB_E_IO (-4)
+#define NWB_E_STATE (-5)     /* call sequence error (e.g. solve before start/goal are set)     */
+
+/* enum Status { ADVANCED, REACHED, TRAPPED }  (RPh:46) - same numeric values */
+#define NWB_ADVANCED 0
+#define NWB_REACHED 1
+#define NWB_TRAPPED 2
+
+/* reason bits written by the validity operators */
+#define NWB_REASON_COLLISION 1u   /* some enabled link pair / scene box in contact (RP:1257)   */
+#define NWB_REASON_UNSTABLE 2u    /* projected COM not strictly inside the support hull (RP:1275) */
+
+/* Reference quirks that change results.  A set bit reproduces the shipped
+ * behaviour, a clear bit the evidently intended one. */
+#define NWB_QUIRK_DB_KEEPS_INFEASIBLE 1u  /* C1  SCG:452-456 inverted test in the database branch   */
+#define NWB_QUIRK_SIGNED_FOOT_ERROR 2u    /* C2  LP:283-297 signed max of the position error        */
+#define NWB_QUIRK_DB_INDEX_FLOOR 4u       /* C3  RP:319-320 floor(U(0,n-1)): last row never drawn   */
+#define NWB_QUIRKS_DEFAULT (NWB_QUIRK_SIGNED_FOOT_ERROR | NWB_QUIRK_DB_INDEX_FLOOR)
+
+/* collision-pair set selector */
+#define NWB_PAIRS_GROUP 0   /* isFeasible: group "whole_body_rfoot" filter, 108 pairs (RP:1250-1257) */
+#define NWB_PAIRS_ALL 1     /* isPathValid: whole robot, 109 pairs (RP:1876)                        */
+
+/* element type of device-resident configurations for the *_dev variants */
+#define NWB_F64 0
+#define NWB_F32 1
+
+typedef struct nwb_ctx nwb_ctx;
+
+/* Planner parameters: the private-namespace ROS parameters of NPC:20-51 /
+ * planning_config/planning_parameters.yaml plus the constants hard-coded in the sources. */
+typedef struct nwb_params {
+  int32_t device;              /* CUDA device ordinal                                          */
+  int32_t quirks;              /* NWB_QUIRK_* bit mask                                          */
+  int32_t srdf_trim;           /* 1: trim stray blanks in SRDF link names (srdfdom), SRDF:230,236,301 */
+  int32_t scale_origin;        /* support-polygon scaling about 1: vertex centroid, 0: sole origin */
+  double scale_sp;             /* planning_parameters.yaml:3 (0.8); RP:105-109                  */
+  double ds_tolerance;         /* LP:293 (0.01 m)                                               */
+  double ik_eps;               /* LP:182, NCK:127 (1e-3)                                        */
+  int32_t ik_maxiter;          /* LP:182, NCK:127 (100)                                         */
+  int32_t scg_max_samples;     /* planning_parameters.yaml:6 (5000)                             */
+  int32_t scg_max_ik_iterations; /* planning_parameters.yaml:7 (5)                              */
+  int32_t planner_max_iterations; /* planning_parameters.yaml:11 (8000)                         */
+  double planner_step_factor;  /* planning_parameters.yaml:10 (0.1)                             */
+  double pinv_eps;             /* KDL ChainIkSolverVel_pinv default (1e-5)                      */
+  int32_t shortcut_waypoints;  /* RP:1396 (100)                                                 */
+  int32_t shortcut_max_rounds; /* RP:1856 (500)                                                 */
+} nwb_params;
+
+/* Fill `p` with the reference defaults. */
+int nwb_params_default(nwb_params* p);
+
+/* Library / ABI version (NWB_ABI_VERSION of the built library). */
+int nwb_abi_version(void);
+
+/* Context = robot model + planning scene + parameters on one device.
+ * Replaces the construction in NAO_PLANNER_CONTROL (NPC:87-104): PlanningScene from the robot
+ * model, StableConfigGenerator / RRT_Planner with scale_sp.  The scene starts empty, as in NPC:90-92. */
+int nwb_ctx_create(const nwb_params* params, nwb_ctx** out);
+void nwb_ctx_destroy(nwb_ctx* ctx);
+const char* nwb_last_error(const nwb_ctx* ctx);   /* ctx may be NULL: last create error */
+int nwb_ctx_synchronize(nwb_ctx* ctx);
+/* RRT_Planner::scale_support_polygon (RP:105-109) / StableConfigGenerator ctor (SCG:63). */
+int nwb_scale_support_polygon(nwb_ctx* ctx, double scale_sp);
+/* Joint limits of the 21 planner joints (read from the RobotModel in RP:64-72). */
+int nwb_get_joint_limits(const nwb_ctx* ctx, double* min_out /*[21]*/, double* max_out /*[21]*/);
+/* Raw CUDA stream handle (cudaStream_t) of the context, for callers that enqueue around it. */
+void* nwb_ctx_stream(nwb_ctx* ctx);
+
+/* Batched state validity: collision-free AND statically stable, both tests always evaluated
+ * (RRT_Planner::isConfigValid RP:701-745 -> isFeasible RP:1219-1287; identical copy SCG:77-159).
+ *   q      [n][21]  configurations (host)
+ *   valid  [n]      1 = feasible
+ *   reason [n]      NWB_REASON_* bits, may be NULL
+ *   margins[n][2]   {min proxy separation, signed distance COM -> support-hull boundary} in metres,
+ *                   > 0 = free / stable; may be NULL (then the cheaper kernel variant runs)
+ */
+int nwb_is_feasible_batch(nwb_ctx* ctx, const double* q, int64_t n, uint8_t* valid, uint8_t* reason,
+                          float* margins);
+/* Same, device-resident.  q_dev is [n][21] of `dtype` (NWB_F64 | NWB_F32). */
+int nwb_is_feasible_batch_dev(nwb_ctx* ctx, const void* q_dev, int dtype, int64_t n,
+                              uint8_t* valid_dev, uint8_t* reason_dev, float* margins_dev);
+
+/* Collision-only validity over the whole robot, the predicate PlanningScene::isPathValid applies to
+ * every way-point (RP:1876,1905; the stability predicate is never registered: RP:233). */
+int nwb_is_state_colliding_batch(nwb_ctx* ctx, const double* q, int64_t n, uint8_t* colliding,
+                                 float* min_separation /* [n], may be NULL */);
+
+/* Forward kinematics of the whole body rooted at r_sole + centre of mass
+ * (MoveIt RobotState FK, called RP:715-720; hrl_kinematics computeCOM, called RP:1275).
+ *   link_poses [n][NWB_NFRAMES][12]  rows of [R | p] (3x4, row-major) in the r_sole frame, may be NULL
+ *   com        [n][3]                may be NULL
+ * Computed in fp32 on the device and widened; agrees with the fp64 oracle to 1e-5 m. */
+int nwb_fk_batch(nwb_ctx* ctx, const double* q, int64_t n, double* link_poses, double* com);
+/* Name of link frame `i` (0 <= i < NWB_NFRAMES), e.g. "l_sole"; NULL if out of range. */
+const char* nwb_frame_name(int i);
+
+/* Pinned host memory helpers: buffers from here make the host<->device copies of the batch
+ * operators run at full PCIe speed. */
+void* nwb_host_alloc(size_t bytes);
+void nwb_host_free(void* p);
+
+/* FP32-pipe micro-benchmark: dependent FFMA chains on every SM; returns achieved TFLOP/s.
+ * Used as the measured roofline denominator for the FP32-bound kernels. */
+int nwb_ffma_peak(nwb_ctx* ctx, int iters, double* tflops_out, double* ms_out);
+
+/* Device time of the most recent batch operator on this context (CUDA events on the context's
+ * stream around the kernel launches only), in milliseconds; and the number of kernels launched. */
+int nwb_last_kernel_ms(nwb_ctx* ctx, double* ms_out, int64_t* launches_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NWB_H_ */

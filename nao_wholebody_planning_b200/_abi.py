@@ -1,0 +1,107 @@
+"""ctypes view of include/nwb.h (the C ABI) and loader of the in-tree CUDA library.
+
+The product path has no CPU fallback: if libnwb.so is missing or cannot be loaded the import of
+any operator fails loudly with instructions to build it (`python -c "import __graft_entry__ as g; g.build()"`).
+"""
+import ctypes as C
+import os
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+LIB_PATH = PKG_DIR / "libnwb.so"
+
+NJ = 21
+NFRAMES = 29
+ADVANCED, REACHED, TRAPPED = 0, 1, 2
+REASON_COLLISION, REASON_UNSTABLE = 1, 2
+QUIRK_DB_KEEPS_INFEASIBLE, QUIRK_SIGNED_FOOT_ERROR, QUIRK_DB_INDEX_FLOOR = 1, 2, 4
+PAIRS_GROUP, PAIRS_ALL = 0, 1
+F64, F32 = 0, 1
+
+
+class NwbParams(C.Structure):
+    """struct nwb_params (include/nwb.h)."""
+    _fields_ = [
+        ("device", C.c_int32),
+        ("quirks", C.c_int32),
+        ("srdf_trim", C.c_int32),
+        ("scale_origin", C.c_int32),
+        ("scale_sp", C.c_double),
+        ("ds_tolerance", C.c_double),
+        ("ik_eps", C.c_double),
+        ("ik_maxiter", C.c_int32),
+        ("scg_max_samples", C.c_int32),
+        ("scg_max_ik_iterations", C.c_int32),
+        ("planner_max_iterations", C.c_int32),
+        ("planner_step_factor", C.c_double),
+        ("pinv_eps", C.c_double),
+        ("shortcut_waypoints", C.c_int32),
+        ("shortcut_max_rounds", C.c_int32),
+    ]
+
+
+def default_params(**over):
+    """Reference defaults (planning_config/planning_parameters.yaml, hard-coded constants)."""
+    p = NwbParams(device=0, quirks=QUIRK_SIGNED_FOOT_ERROR | QUIRK_DB_INDEX_FLOOR, srdf_trim=1, scale_origin=1,
+                  scale_sp=0.8, ds_tolerance=0.01, ik_eps=1e-3, ik_maxiter=100, scg_max_samples=5000,
+                  scg_max_ik_iterations=5, planner_max_iterations=8000, planner_step_factor=0.1, pinv_eps=1e-5,
+                  shortcut_waypoints=100, shortcut_max_rounds=500)
+    for k, v in over.items():
+        if not hasattr(p, k):
+            raise AttributeError(k)
+        setattr(p, k, v)
+    return p
+
+
+class NwbError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library(path=None):
+    """Load libnwb.so (built in-tree by __graft_entry__.build()).  Never falls back to a CPU path."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = Path(path or os.environ.get("NWB_LIB", LIB_PATH))
+    if not p.exists():
+        raise NwbError(
+            f"{p} not found: the CUDA library is not built. Run `python -c \"import __graft_entry__ as g; g.build()\"` "
+            "from the repo root. There is no CPU fallback.")
+    lib = C.CDLL(str(p))
+    _declare(lib)
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _declare(lib):
+    vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    pd, pu8, pf, pi32 = C.POINTER(C.c_double), C.POINTER(C.c_uint8), C.POINTER(C.c_float), C.POINTER(C.c_int32)
+    sigs = {
+        "nwb_params_default": (C.c_int, [C.POINTER(NwbParams)]),
+        "nwb_abi_version": (C.c_int, []),
+        "nwb_ctx_create": (C.c_int, [C.POINTER(NwbParams), C.POINTER(vp)]),
+        "nwb_ctx_destroy": (None, [vp]),
+        "nwb_last_error": (C.c_char_p, [vp]),
+        "nwb_ctx_synchronize": (C.c_int, [vp]),
+        "nwb_scale_support_polygon": (C.c_int, [vp, dbl]),
+        "nwb_get_joint_limits": (C.c_int, [vp, pd, pd]),
+        "nwb_ctx_stream": (vp, [vp]),
+        "nwb_is_feasible_batch": (C.c_int, [vp, vp, i64, vp, vp, vp]),
+        "nwb_is_feasible_batch_dev": (C.c_int, [vp, vp, C.c_int, i64, vp, vp, vp]),
+        "nwb_is_state_colliding_batch": (C.c_int, [vp, vp, i64, vp, vp]),
+        "nwb_fk_batch": (C.c_int, [vp, vp, i64, vp, vp]),
+        "nwb_frame_name": (C.c_char_p, [C.c_int]),
+        "nwb_host_alloc": (vp, [C.c_size_t]),
+        "nwb_host_free": (None, [vp]),
+        "nwb_ffma_peak": (C.c_int, [vp, C.c_int, pd, pd]),
+        "nwb_last_kernel_ms": (C.c_int, [vp, pd, C.POINTER(i64)]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(lib, name)  # AttributeError here = header/library mismatch: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    lib._nwb_sigs = sigs

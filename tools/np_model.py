@@ -145,6 +145,8 @@ def seg_seg_dist(p1, q1, p2, q2):
     with np.errstate(divide="ignore", invalid="ignore"):
         s = np.where(denom > eps, np.clip((b * f - c * e) / np.where(denom > eps, denom, 1), 0, 1), 0.0)
         t = np.where(e > eps, (b * s + f) / np.where(e > eps, e, 1), 0.0)
+        # second segment degenerate (sphere): closest point of the first segment to that point
+        s = np.where((e <= eps) & (a > eps), np.clip(-c / np.where(a > eps, a, 1), 0, 1), s)
         s = np.where(t < 0, np.where(a > eps, np.clip(-c / np.where(a > eps, a, 1), 0, 1), 0.0), s)
         s = np.where(t > 1, np.where(a > eps, np.clip((b - c) / np.where(a > eps, a, 1), 0, 1), 0.0), s)
         t = np.clip(t, 0, 1)
