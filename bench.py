@@ -1,0 +1,311 @@
+#!/usr/bin/env python3
+"""bench.py - headline benchmark: validated configurations / second (FK + COM + collision).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload (BASELINE.json configs[1], SURVEY.md section 8d "V1/S0"): B = 1 048 576 uniformly random NAO
+whole-body configurations per GPU (seed 20121001 + rank), scene S0 (the empty scene the shipped
+planner actually checks), right-foot support, support polygon scale 0.8.  One step = one pass of
+the validity hot path over the batch (FK + COM-in-support-polygon + 108 self-collision pairs, both
+tests always evaluated, one kernel launch).
+
+  value   device-timed throughput with the batch resident in HBM in the reference API's layout
+          ([n][21] float64, 176 MB > the 126 MB L2, so no inter-iteration reuse)
+  e2e     the same metric through the C-ABI call nwb_is_feasible_batch with pinned HOST buffers:
+          H2D of the configurations and D2H of the verdicts inside the timed region
+  roofline  FP32-pipe: algorithmic flops (profiles/roofline.json, frozen by tools/count_flops.cpp)
+            / mean kernel duration (CUDA events on the launching stream) vs the FFMA peak measured
+            live by nwb_ffma_peak in this same process
+  cpu_baseline  the CPU oracle (a port: the reference cannot be built here) on a bounded sample,
+            one thread, on this box's host cores
+
+Multi-GPU: the batch shards by index, no data-path collective; each step ends with an NCCL
+all_gather of the 1 B/config verdicts (north_star: "NCCL over NVLink used only to gather results").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+for p in (str(ROOT), str(ROOT / "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+B_PER_GPU = 1 << 20
+SEED = 20121001
+METRIC = "validated_configs_per_sec"
+UNIT = "configs/s"
+WORKLOAD = "V1/S0: 1,048,576 uniform random NAO configs per GPU vs the scenario scene (empty), right-foot support, scale_sp 0.8"
+
+
+def load_json(path, default=None):
+    try:
+        return json.loads(Path(path).read_text())
+    except Exception:
+        return default
+
+
+def make_batch(n, seed):
+    import oracle_lib as OL   # input generator only (joint limits + PCG64 stream of SURVEY.md 8d)
+    return OL.uniform_configs(n, seed=seed)
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(q, seconds=12.0, threads=1):
+    """Time the CPU oracle on a bounded prefix of the same batch (about `seconds` of CPU work)."""
+    import oracle_lib as OL
+    orc = OL.Oracle()
+    probe = 20000
+    t0 = time.perf_counter()
+    orc.is_feasible(q[:probe], threads=threads)
+    rate = probe / (time.perf_counter() - t0)
+    n = int(min(len(q), max(probe, rate * seconds)))
+    t0 = time.perf_counter()
+    valid, _, _ = orc.is_feasible(q[:n], threads=threads)
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"first {n} configurations of the same batch, {dt:.1f} s, oracle/ (fp64 C++ restatement; "
+                      f"the reference itself needs ROS/MoveIt/FCL/KDL and cannot be built here)"}, valid, n
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path (oracle port), all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    import oracle_lib as OL
+    orc = OL.Oracle()
+    threads = max(1, orc.threads)
+    q = make_batch(B_PER_GPU, SEED)
+    # size the per-step sample so the whole run stays within a few minutes
+    t0 = time.perf_counter()
+    orc.is_feasible(q[:50000], threads=threads)
+    rate = 50000 / (time.perf_counter() - t0)
+    budget_s = 150.0 / max(1, args.steps + args.warmup)
+    n = int(min(B_PER_GPU, max(50000, rate * min(budget_s, 20.0))))
+    for _ in range(args.warmup):
+        orc.is_feasible(q[:n], threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.is_feasible(q[:n], threads=threads)
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    sample = f"first {n} configurations of the batch per step, {threads} host threads"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample_per_step": n},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batch", type=int, default=B_PER_GPU, help="configurations per GPU (default = the headline size)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import nao_wholebody_planning_b200 as nwb
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    n = args.batch
+    q_host = make_batch(n, SEED + rank)
+    ctx = nwb.Context(device=local_rank)
+    stream = torch.cuda.Stream(device=dev)
+    ctx.set_stream(stream.cuda_stream)          # the library launches on this torch stream
+
+    with torch.cuda.stream(stream):
+        q_dev = torch.from_numpy(q_host).to(dev)                       # [n,21] f64, resident in HBM
+        valid = torch.empty(n, dtype=torch.uint8, device=dev)
+        reason = torch.empty(n, dtype=torch.uint8, device=dev)
+        gathered = torch.empty(n * world, dtype=torch.uint8, device=dev) if world > 1 else None
+    stream.synchronize()
+
+    def step():
+        ctx.is_feasible_dev(q_dev.data_ptr(), nwb.F64, n, valid.data_ptr(), reason.data_ptr())
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, valid)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # measured FP32 peak (roofline denominator), before the timed region
+    ffma_tflops = max(ctx.ffma_peak(8192)[0] for _ in range(3))
+
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            step()
+        barrier()
+        clocks = ClockSampler(local_rank)
+        clocks.start()
+        time.sleep(0.25)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+        barrier()
+        ev[0].record(stream)
+        for k in range(args.steps):
+            step()
+            ev[k + 1].record(stream)
+        barrier()
+        # keep the GPU busy a little longer so the clock sampler sees the loaded state
+        t_end = time.time() + 0.6
+        while time.time() < t_end:
+            step()
+        torch.cuda.synchronize(dev)
+        clk = clocks.stop()
+    total_ms = ev[0].elapsed_time(ev[-1])
+    step_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    value = n * world * args.steps / (total_ms * 1e-3)
+
+    # kernel-only duration (one launch per step): events bracket exactly the kernel when N = 1
+    kern_ms = float(np.mean(step_ms)) if world == 1 else None
+    if world > 1:
+        # time the kernel alone on this rank for the roofline figure
+        with torch.cuda.stream(stream):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(args.steps):
+                ctx.is_feasible_dev(q_dev.data_ptr(), nwb.F64, n, valid.data_ptr(), reason.data_ptr())
+            e1.record(stream)
+            torch.cuda.synchronize(dev)
+            kern_ms = e0.elapsed_time(e1) / args.steps
+
+    # ---- end to end through the C ABI with pinned host buffers ------------------------------------
+    ctx.set_stream(None)
+    pin_q = nwb.PinnedArray((n, nwb.NJ), np.float64)
+    pin_v = nwb.PinnedArray((n,), np.uint8)
+    pin_q.array[:] = q_host
+    for _ in range(2):
+        ctx.is_feasible_host_buffers(pin_q.ptr, n, pin_v.ptr)
+    barrier()
+    e2e_steps = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ctx.is_feasible_host_buffers(pin_q.ptr, n, pin_v.ptr)
+    torch.cuda.synchronize(dev)
+    e2e_dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_dt = float(t.item())
+    e2e_value = n * world * e2e_steps / e2e_dt
+    e2e_valid = pin_v.array.copy()
+    assert (e2e_valid == valid.cpu().numpy()).all(), "host-buffer path and device path disagree"
+
+    if rank == 0:
+        rf = load_json(ROOT / "profiles" / "roofline.json", {})
+        flops_cfg = rf.get("validity_S0_flops_per_config")
+        peaks = load_json(ROOT / "MEASURED_PEAKS.json", {})
+        ncu = load_json(ROOT / "profiles" / "validity_ncu_summary.json", {})
+        achieved = flops_cfg * n / (kern_ms * 1e-3) / 1e12 if flops_cfg else None
+        roofline = {"bound": "fp32", "kernel": "nwb::validity_kernel<double,false,false>",
+                    "achieved": achieved, "peak": ffma_tflops, "unit": "TFLOP/s",
+                    "frac": (achieved / ffma_tflops) if achieved else None,
+                    "peak_source": "nwb_ffma_peak measured live in this run (MEASURED_PEAKS.json has no FP32 figure; nominal 74.4)",
+                    "flops_per_config": flops_cfg, "kernel_ms": kern_ms,
+                    "traffic": ncu.get("dram_bytes_per_launch"),
+                    "hbm_view": {"achieved_gbs": n * 170 / (kern_ms * 1e-3) / 1e9, "peak_gbs": peaks.get("hbm_gbs"),
+                                 "note": "170 B/config (168 in, 2 out): far from the HBM bound, as designed"}}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "batch_per_gpu": n, "input_layout": "[n][21] float64 resident in HBM",
+                           "l2_policy": "inputs (176 MB per GPU) larger than L2 (126 MB)",
+                           "parallelism": f"shard{world}" if world > 1 else "single",
+                           "valid_fraction": float(valid.float().mean().item())},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * nwb.NJ * 8, "d2h_bytes_per_step": n,
+                        "steps": e2e_steps, "api": "nwb_is_feasible_batch (pinned host buffers)"},
+                "gpu_launches": args.steps, "clocks": clk, "roofline": roofline}
+        if not args.no_cpu_baseline:
+            cb, cpu_valid, cn = cpu_baseline(q_host)
+            line["cpu_baseline"] = cb
+            mism = int((cpu_valid != e2e_valid[:cn]).sum())
+            line["config"]["oracle_mismatches_in_cpu_sample"] = mism      # boundary-band configurations
+        print(json.dumps(line))
+    pin_q.free()
+    pin_v.free()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -30,6 +30,12 @@
 extern "C" {
 #endif
 
+#if defined(__GNUC__)
+#define NWB_API __attribute__((visibility("default")))
+#else
+#define NWB_API
+#endif
+
 #define NWB_NJ 21          /* joints per configuration (RP:2001-2023)                       */
 #define NWB_NFRAMES 29     /* link frames returned by nwb_fk_batch (models/nao_h25_rfoot)  */
 #define NWB_ABI_VERSION 1
@@ -89,24 +95,35 @@ typedef struct nwb_params {
 } nwb_params;
 
 /* Fill `p` with the reference defaults. */
-int nwb_params_default(nwb_params* p);
+NWB_API int nwb_params_default(nwb_params* p);
 
 /* Library / ABI version (NWB_ABI_VERSION of the built library). */
-int nwb_abi_version(void);
+NWB_API int nwb_abi_version(void);
 
 /* Context = robot model + planning scene + parameters on one device.
  * Replaces the construction in NAO_PLANNER_CONTROL (NPC:87-104): PlanningScene from the robot
  * model, StableConfigGenerator / RRT_Planner with scale_sp.  The scene starts empty, as in NPC:90-92. */
-int nwb_ctx_create(const nwb_params* params, nwb_ctx** out);
-void nwb_ctx_destroy(nwb_ctx* ctx);
-const char* nwb_last_error(const nwb_ctx* ctx);   /* ctx may be NULL: last create error */
-int nwb_ctx_synchronize(nwb_ctx* ctx);
+NWB_API int nwb_ctx_create(const nwb_params* params, nwb_ctx** out);
+NWB_API void nwb_ctx_destroy(nwb_ctx* ctx);
+NWB_API const char* nwb_last_error(const nwb_ctx* ctx);   /* ctx may be NULL: last create error */
+NWB_API int nwb_ctx_synchronize(nwb_ctx* ctx);
 /* RRT_Planner::scale_support_polygon (RP:105-109) / StableConfigGenerator ctor (SCG:63). */
-int nwb_scale_support_polygon(nwb_ctx* ctx, double scale_sp);
+NWB_API int nwb_scale_support_polygon(nwb_ctx* ctx, double scale_sp);
 /* Joint limits of the 21 planner joints (read from the RobotModel in RP:64-72). */
-int nwb_get_joint_limits(const nwb_ctx* ctx, double* min_out /*[21]*/, double* max_out /*[21]*/);
+NWB_API int nwb_get_joint_limits(const nwb_ctx* ctx, double* min_out /*[21]*/, double* max_out /*[21]*/);
 /* Raw CUDA stream handle (cudaStream_t) of the context, for callers that enqueue around it. */
-void* nwb_ctx_stream(nwb_ctx* ctx);
+NWB_API void* nwb_ctx_stream(nwb_ctx* ctx);
+/* Make the context launch on a caller-owned stream (cudaStream_t; NULL restores the context's own).
+ * Lets a host framework order these kernels with its own work and time them with its own events. */
+NWB_API int nwb_ctx_set_stream(nwb_ctx* ctx, void* cuda_stream);
+
+/* Planning scene: oriented boxes in the r_sole frame (moveit_msgs/CollisionObject BOX primitives as
+ * the examples insert them: planning_example_simulation.cpp:310-357, initScene.cpp:120-158; all
+ * commented out in the shipped node, so the default scene is empty like NPC:90-92).
+ *   center[3], size[3] = full extents, rot[9] = row-major rotation (NULL = axis aligned). */
+NWB_API int nwb_scene_clear(nwb_ctx* ctx);
+NWB_API int nwb_scene_add_box(nwb_ctx* ctx, const double* center, const double* size, const double* rot);
+NWB_API int nwb_scene_num_boxes(const nwb_ctx* ctx);
 
 /* Batched state validity: collision-free AND statically stable, both tests always evaluated
  * (RRT_Planner::isConfigValid RP:701-745 -> isFeasible RP:1219-1287; identical copy SCG:77-159).
@@ -116,15 +133,15 @@ void* nwb_ctx_stream(nwb_ctx* ctx);
  *   margins[n][2]   {min proxy separation, signed distance COM -> support-hull boundary} in metres,
  *                   > 0 = free / stable; may be NULL (then the cheaper kernel variant runs)
  */
-int nwb_is_feasible_batch(nwb_ctx* ctx, const double* q, int64_t n, uint8_t* valid, uint8_t* reason,
+NWB_API int nwb_is_feasible_batch(nwb_ctx* ctx, const double* q, int64_t n, uint8_t* valid, uint8_t* reason,
                           float* margins);
 /* Same, device-resident.  q_dev is [n][21] of `dtype` (NWB_F64 | NWB_F32). */
-int nwb_is_feasible_batch_dev(nwb_ctx* ctx, const void* q_dev, int dtype, int64_t n,
+NWB_API int nwb_is_feasible_batch_dev(nwb_ctx* ctx, const void* q_dev, int dtype, int64_t n,
                               uint8_t* valid_dev, uint8_t* reason_dev, float* margins_dev);
 
 /* Collision-only validity over the whole robot, the predicate PlanningScene::isPathValid applies to
  * every way-point (RP:1876,1905; the stability predicate is never registered: RP:233). */
-int nwb_is_state_colliding_batch(nwb_ctx* ctx, const double* q, int64_t n, uint8_t* colliding,
+NWB_API int nwb_is_state_colliding_batch(nwb_ctx* ctx, const double* q, int64_t n, uint8_t* colliding,
                                  float* min_separation /* [n], may be NULL */);
 
 /* Forward kinematics of the whole body rooted at r_sole + centre of mass
@@ -132,22 +149,22 @@ int nwb_is_state_colliding_batch(nwb_ctx* ctx, const double* q, int64_t n, uint8
  *   link_poses [n][NWB_NFRAMES][12]  rows of [R | p] (3x4, row-major) in the r_sole frame, may be NULL
  *   com        [n][3]                may be NULL
  * Computed in fp32 on the device and widened; agrees with the fp64 oracle to 1e-5 m. */
-int nwb_fk_batch(nwb_ctx* ctx, const double* q, int64_t n, double* link_poses, double* com);
+NWB_API int nwb_fk_batch(nwb_ctx* ctx, const double* q, int64_t n, double* link_poses, double* com);
 /* Name of link frame `i` (0 <= i < NWB_NFRAMES), e.g. "l_sole"; NULL if out of range. */
-const char* nwb_frame_name(int i);
+NWB_API const char* nwb_frame_name(int i);
 
 /* Pinned host memory helpers: buffers from here make the host<->device copies of the batch
  * operators run at full PCIe speed. */
-void* nwb_host_alloc(size_t bytes);
-void nwb_host_free(void* p);
+NWB_API void* nwb_host_alloc(size_t bytes);
+NWB_API void nwb_host_free(void* p);
 
 /* FP32-pipe micro-benchmark: dependent FFMA chains on every SM; returns achieved TFLOP/s.
  * Used as the measured roofline denominator for the FP32-bound kernels. */
-int nwb_ffma_peak(nwb_ctx* ctx, int iters, double* tflops_out, double* ms_out);
+NWB_API int nwb_ffma_peak(nwb_ctx* ctx, int iters, double* tflops_out, double* ms_out);
 
 /* Device time of the most recent batch operator on this context (CUDA events on the context's
  * stream around the kernel launches only), in milliseconds; and the number of kernels launched. */
-int nwb_last_kernel_ms(nwb_ctx* ctx, double* ms_out, int64_t* launches_out);
+NWB_API int nwb_last_kernel_ms(nwb_ctx* ctx, double* ms_out, int64_t* launches_out);
 
 #ifdef __cplusplus
 }

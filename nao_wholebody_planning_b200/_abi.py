@@ -90,6 +90,10 @@ def _declare(lib):
         "nwb_scale_support_polygon": (C.c_int, [vp, dbl]),
         "nwb_get_joint_limits": (C.c_int, [vp, pd, pd]),
         "nwb_ctx_stream": (vp, [vp]),
+        "nwb_ctx_set_stream": (C.c_int, [vp, vp]),
+        "nwb_scene_clear": (C.c_int, [vp]),
+        "nwb_scene_add_box": (C.c_int, [vp, pd, pd, pd]),
+        "nwb_scene_num_boxes": (C.c_int, [vp]),
         "nwb_is_feasible_batch": (C.c_int, [vp, vp, i64, vp, vp, vp]),
         "nwb_is_feasible_batch_dev": (C.c_int, [vp, vp, C.c_int, i64, vp, vp, vp]),
         "nwb_is_state_colliding_batch": (C.c_int, [vp, vp, i64, vp, vp]),

@@ -1,0 +1,162 @@
+"""Thin Python handle over the C ABI (include/nwb.h) for tests and benchmarks.
+
+All compute happens in libnwb.so (C++ host code + CUDA kernels); this module only marshals NumPy
+arrays / raw device pointers.  Method names follow the reference's operator surface:
+  isFeasible            RRT_Planner::isFeasible            rrt_planner.h:73
+  scale_support_polygon RRT_Planner::scale_support_polygon rrt_planner.h:65
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi
+from ._abi import NJ, NFRAMES, NwbError, default_params, load_library
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """nwb_ctx: robot model + planning scene + parameters on one CUDA device."""
+
+    def __init__(self, params=None, **overrides):
+        self.lib = load_library()
+        self.params = params or default_params(**overrides)
+        h = C.c_void_p()
+        rc = self.lib.nwb_ctx_create(C.byref(self.params), C.byref(h))
+        if rc != 0:
+            raise NwbError(f"nwb_ctx_create failed ({rc}): {self.lib.nwb_last_error(None).decode()}")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.nwb_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise NwbError(f"{what} failed ({rc}): {self.lib.nwb_last_error(self.h).decode()}")
+
+    # ---- parameters -----------------------------------------------------------------------------
+    def scale_support_polygon(self, scale_sp):
+        self._check(self.lib.nwb_scale_support_polygon(self.h, float(scale_sp)), "nwb_scale_support_polygon")
+
+    def joint_limits(self):
+        lo, hi = np.empty(NJ), np.empty(NJ)
+        self._check(self.lib.nwb_get_joint_limits(self.h, lo.ctypes.data_as(C.POINTER(C.c_double)),
+                                                  hi.ctypes.data_as(C.POINTER(C.c_double))), "nwb_get_joint_limits")
+        return lo, hi
+
+    def synchronize(self):
+        self._check(self.lib.nwb_ctx_synchronize(self.h), "nwb_ctx_synchronize")
+
+    @property
+    def stream(self):
+        return self.lib.nwb_ctx_stream(self.h)
+
+    def set_stream(self, cuda_stream):
+        """Launch on a caller-owned cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); None restores."""
+        self._check(self.lib.nwb_ctx_set_stream(self.h, cuda_stream), "nwb_ctx_set_stream")
+
+    # ---- planning scene -------------------------------------------------------------------------
+    def scene_clear(self):
+        self._check(self.lib.nwb_scene_clear(self.h), "nwb_scene_clear")
+
+    def scene_add_box(self, center, size, rot=None):
+        pd = C.POINTER(C.c_double)
+        c = np.ascontiguousarray(center, dtype=np.float64)
+        s = np.ascontiguousarray(size, dtype=np.float64)
+        r = None if rot is None else np.ascontiguousarray(rot, dtype=np.float64).reshape(9)
+        self._check(self.lib.nwb_scene_add_box(self.h, c.ctypes.data_as(pd), s.ctypes.data_as(pd),
+                                               None if r is None else r.ctypes.data_as(pd)), "nwb_scene_add_box")
+
+    def scene_add_boxes(self, boxes15):
+        """rows of [cx,cy,cz, sx,sy,sz, R row-major] (tests/oracle_lib.scene_boxes layout)."""
+        for b in np.asarray(boxes15, dtype=np.float64).reshape(-1, 15):
+            self.scene_add_box(b[0:3], b[3:6], b[6:15])
+
+    @property
+    def num_boxes(self):
+        return self.lib.nwb_scene_num_boxes(self.h)
+
+    # ---- validity -------------------------------------------------------------------------------
+    def isFeasible(self, q, want_reason=True, want_margins=False):
+        """Batched RRT_Planner::isFeasible.  q [n,21] float64 (host).  Returns (valid, reason, margins)."""
+        q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, NJ)
+        n = len(q)
+        valid = np.empty(n, np.uint8)
+        reason = np.empty(n, np.uint8) if want_reason else None
+        margins = np.empty((n, 2), np.float32) if want_margins else None
+        self._check(self.lib.nwb_is_feasible_batch(self.h, _p(q), n, _p(valid), _p(reason), _p(margins)),
+                    "nwb_is_feasible_batch")
+        return valid, reason, margins
+
+    def is_feasible_host_buffers(self, q_ptr, n, valid_ptr, reason_ptr=None, margins_ptr=None):
+        """Raw-pointer form (pinned buffers from host_alloc) used by the end-to-end benchmark."""
+        self._check(self.lib.nwb_is_feasible_batch(self.h, q_ptr, n, valid_ptr, reason_ptr, margins_ptr),
+                    "nwb_is_feasible_batch")
+
+    def is_feasible_dev(self, q_dev, dtype, n, valid_dev, reason_dev=None, margins_dev=None):
+        """Device-pointer form: only enqueues on the context's stream."""
+        self._check(self.lib.nwb_is_feasible_batch_dev(self.h, q_dev, dtype, n, valid_dev, reason_dev, margins_dev),
+                    "nwb_is_feasible_batch_dev")
+
+    def is_state_colliding(self, q, want_separation=False):
+        q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, NJ)
+        n = len(q)
+        col = np.empty(n, np.uint8)
+        sep = np.empty(n, np.float32) if want_separation else None
+        self._check(self.lib.nwb_is_state_colliding_batch(self.h, _p(q), n, _p(col), _p(sep)),
+                    "nwb_is_state_colliding_batch")
+        return col, sep
+
+    def fk(self, q, want_poses=True, want_com=True):
+        q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, NJ)
+        n = len(q)
+        poses = np.empty((n, NFRAMES, 3, 4)) if want_poses else None
+        com = np.empty((n, 3)) if want_com else None
+        self._check(self.lib.nwb_fk_batch(self.h, _p(q), n, _p(poses), _p(com)), "nwb_fk_batch")
+        return poses, com
+
+    # ---- measurement ----------------------------------------------------------------------------
+    def ffma_peak(self, iters=4096):
+        t, ms = C.c_double(0), C.c_double(0)
+        self._check(self.lib.nwb_ffma_peak(self.h, iters, C.byref(t), C.byref(ms)), "nwb_ffma_peak")
+        return t.value, ms.value
+
+    def last_kernel_ms(self):
+        ms, n = C.c_double(0), C.c_int64(0)
+        self._check(self.lib.nwb_last_kernel_ms(self.h, C.byref(ms), C.byref(n)), "nwb_last_kernel_ms")
+        return ms.value, n.value
+
+
+class PinnedArray:
+    """NumPy view over nwb_host_alloc memory (page-locked)."""
+
+    def __init__(self, shape, dtype):
+        self.lib = load_library()
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self.ptr = self.lib.nwb_host_alloc(max(self.nbytes, 1))
+        if not self.ptr:
+            raise NwbError("nwb_host_alloc failed")
+        buf = (C.c_char * max(self.nbytes, 1)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            self.lib.nwb_host_free(self.ptr)
+            self.ptr = None

@@ -1,0 +1,20 @@
+#!/bin/bash
+# Builds libnwb.so in-tree for sm_100a (called by __graft_entry__.build()).
+set -euo pipefail
+cd "$(dirname "$0")"
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+OUT=../libnwb.so
+FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -fvisibility=hidden
+       --expt-relaxed-constexpr -cudart static -Xptxas -v)
+SRCS=(validity.cu nwb_abi.cu)
+OBJS=()
+mkdir -p build
+for s in "${SRCS[@]}"; do
+  o=build/${s%.cu}.o
+  if [ ! -f "$o" ] || [ "$s" -nt "$o" ] || [ -n "$(find . -maxdepth 1 \( -name '*.h' -o -name '*.cuh' \) -newer "$o")" ] || [ ../../include/nwb.h -nt "$o" ]; then
+    "$NVCC" "${FLAGS[@]}" -c "$s" -o "$o" 2> "build/${s%.cu}.ptxas.log" || { cat "build/${s%.cu}.ptxas.log"; exit 1; }
+  fi
+  OBJS+=("$o")
+done
+"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -cudart static -o "$OUT" "${OBJS[@]}"
+echo "built $OUT"

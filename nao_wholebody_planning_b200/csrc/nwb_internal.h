@@ -1,0 +1,89 @@
+// nwb_internal.h - host-side context and kernel launcher prototypes (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/nwb.h"
+#include "nao_model_gen.h"
+
+namespace nwb {
+
+constexpr int kMaxPairs = 112;
+constexpr int kMaxRuns = 48;
+constexpr int kMaxBoxes = 16;
+
+// One collision pair inside a run: B's point-table slot and constants.
+struct PairEntry {
+  int off_b;     // float slot of B's first point
+  float e;       // |b_B - a_B|^2
+  float inv_e;   // 1/e (0 for spheres)
+  float rsum;    // r_A + r_B
+};
+// Pairs sharing the same first proxy A, so A is loaded from the point table once.
+struct PairRun {
+  int off_a;
+  float a;       // |b_A - a_A|^2
+  float inv_a;
+  int first;     // index of the first PairEntry
+  int count;
+};
+struct SceneBox {   // oriented box in the r_sole frame
+  float c[3];
+  float h[3];      // half extents
+  float r[9];      // row-major rotation, columns = box axes
+};
+struct EnvLink {    // a robot proxy tested against the scene boxes
+  int off;
+  float inv_a;     // 1/|b-a|^2, 0 for spheres
+  float radius;
+  int is_sphere;
+};
+
+// Passed to the kernels by value (__grid_constant__): lives in the constant bank, per launch,
+// so contexts with different parameters never share global state.
+struct ValidityTables {
+  float foot_right[nwbm::kFootN][2];   // scaled right-foot polygon, r_sole frame
+  float foot_left[nwbm::kFootN][2];    // scaled left-foot polygon, l_sole frame
+  int n_runs_cc, n_runs_cs, n_runs_ss; // runs are stored in this order
+  int n_boxes, n_env_links;
+  PairRun runs[kMaxRuns];
+  PairEntry entries[kMaxPairs];
+  SceneBox boxes[kMaxBoxes];
+  EnvLink env_links[nwbm::kNumGeom];
+};
+
+struct Ctx {
+  nwb_params params;
+  int device = 0;
+  cudaStream_t stream = nullptr;      // stream the operators launch on (own_stream unless overridden)
+  cudaStream_t own_stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t copy_stream = nullptr;                     // second stream: H2D copies overlap the kernels
+  cudaEvent_t in_done[2] = {nullptr, nullptr}, k_done[2] = {nullptr, nullptr};
+  std::string err;
+  std::vector<SceneBox> boxes;
+  ValidityTables tab_group;   // isFeasible pair set
+  ValidityTables tab_all;     // isPathValid pair set
+  // scratch device buffers for the host-pointer entry points (grown on demand)
+  void* d_in = nullptr; size_t d_in_bytes = 0;
+  void* d_out = nullptr; size_t d_out_bytes = 0;
+  void* h_stage = nullptr; size_t h_stage_bytes = 0;   // pinned staging for pageable callers
+  double last_ms = 0;
+  int64_t last_launches = 0;
+  int sm_count = 0;
+};
+
+void build_tables(Ctx* ctx);
+
+// kernel launchers (validity.cu).  q is [n][21] of float or double on the device.
+cudaError_t launch_validity(const ValidityTables& tab, const void* q, int dtype, int64_t n, uint8_t* valid,
+                            uint8_t* reason, float* margins, bool collision_only, cudaStream_t stream);
+cudaError_t launch_fk(const void* q, int dtype, int64_t n, double* poses, double* com, cudaStream_t stream);
+cudaError_t launch_ffma_peak(int sm_count, int iters, float* sink, cudaStream_t stream, double* flops_out);
+
+}  // namespace nwb
+
+struct nwb_ctx : nwb::Ctx {};

@@ -1,0 +1,177 @@
+// validity.cu - fused batched state validity for sm_100a.
+//
+// One configuration per thread.  Replaces, for a whole batch at once, what the reference does per
+// state in RRT_Planner::isConfigValid -> isFeasible (rrt_connect_planner/src/rrt_planner.cpp:701-745,
+// 1219-1287; copy at stable_config_generator.cpp:77-159):
+//   MoveIt RobotState FK over the robot tree        -> straight-line FK walk, frames in registers
+//   hrl_kinematics computeCOM + isPoseStable        -> COM accumulated during the walk; support test
+//                                                      as an incremental angular wedge (no hull build)
+//   PlanningScene::checkCollision (FCL, SRDF ACM)   -> capsule/sphere proxies, enabled-pair runs
+//                                                      from the constant bank, world points staged in
+//                                                      shared memory ([slot][thread], conflict-free)
+// Both tests are always evaluated (the reference has no early exit: rrt_planner.cpp:1257-1286); the
+// roofline figure is quoted for this full evaluation.  FP32 pipe bound: no dense contraction here,
+// so no tensor cores (BASELINE.json north_star).
+#include <cuda_runtime.h>
+
+#include "validity_core.cuh"
+
+namespace nwb {
+
+constexpr int NT = 128;                                 // threads (= configurations) per block
+constexpr int kSmemFloats = nwbm::kPointFloats * NT;    // 111 * 128 * 4 B = 56.8 KB
+
+// Point table of one configuration inside the block's shared memory: [slot][thread].
+struct SmemStore {
+  float* base;   // shared memory, already offset by threadIdx.x
+  __device__ __forceinline__ void put(int slot, float v) { base[slot * NT] = v; }
+  __device__ __forceinline__ float get(int slot) const { return base[slot * NT]; }
+};
+
+// Writes every frame and the full COM to global memory (nwb_fk_batch).
+struct FkVisitor {
+  double* poses;   // [29][12] of this configuration, or nullptr
+  float com[3];
+  template <int ID>
+  __device__ __forceinline__ void frame(const XF<float>& F) {
+    using M = nwbm::FrameMass<ID>;
+    if constexpr (M::has) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        com[k] += float(M::w) * F.p[k] + float(M::wx) * F.r[3 * k] + float(M::wy) * F.r[3 * k + 1] + float(M::wz) * F.r[3 * k + 2];
+    }
+    if (poses) {
+      double* o = poses + ID * 12;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        o[4 * r + 0] = F.r[3 * r + 0]; o[4 * r + 1] = F.r[3 * r + 1]; o[4 * r + 2] = F.r[3 * r + 2];
+        o[4 * r + 3] = F.p[r];
+      }
+    }
+  }
+};
+
+// ---- the validity kernel ------------------------------------------------------------------------
+//   MARGINS        also produce {min separation, signed hull distance} (sqrt per pair + gift wrapping)
+//   COLLISION_ONLY skip COM / support (isPathValid way-points)
+template <typename QT, bool MARGINS, bool COLLISION_ONLY>
+__global__ void __launch_bounds__(NT, 3)
+validity_kernel(const __grid_constant__ ValidityTables tab, const QT* __restrict__ q, int64_t n,
+                uint8_t* __restrict__ valid, uint8_t* __restrict__ reason, float* __restrict__ margins) {
+  extern __shared__ float smem[];
+  const int tid = threadIdx.x;
+  const int64_t base = (int64_t)blockIdx.x * NT;
+  const int64_t i = base + tid;
+  const int nvalid = (int)min((int64_t)NT, n - base);
+
+  // stage this block's configurations: coalesced global read, fp32 in shared, AoS order
+  for (int e = tid; e < nvalid * NWB_NJ; e += NT) smem[e] = (float)q[base * NWB_NJ + e];
+  __syncthreads();
+  float qv[NWB_NJ];
+  const int row = tid < nvalid ? tid : 0;     // idle lanes recompute row 0 (keeps the warp converged)
+#pragma unroll
+  for (int j = 0; j < NWB_NJ; ++j) qv[j] = smem[row * NWB_NJ + j];   // stride 21 words: conflict-free
+  __syncthreads();                            // staging area is reused as the point table below
+
+  SmemStore st{smem + tid};
+  float min_sep = 0.f, hull_margin = 0.f;
+  const ValidityResult res = evaluate_config<float, SmemStore, MARGINS, COLLISION_ONLY>(tab, qv, st, &min_sep, &hull_margin);
+
+  if (i < n) {
+    unsigned rs = (res.hit ? NWB_REASON_COLLISION : 0u) | (res.stable ? 0u : NWB_REASON_UNSTABLE);
+    if (valid) valid[i] = COLLISION_ONLY ? (uint8_t)res.hit : (uint8_t)(rs == 0u);
+    if (reason) reason[i] = (uint8_t)rs;
+    if constexpr (MARGINS) {
+      if (margins) {
+        if constexpr (COLLISION_ONLY) margins[i] = min_sep;
+        else { margins[2 * i] = min_sep; margins[2 * i + 1] = hull_margin; }
+      }
+    }
+  }
+}
+
+template <typename QT, bool MARGINS, bool COLLISION_ONLY>
+static cudaError_t launch_one(const ValidityTables& tab, const void* q, int64_t n, uint8_t* valid, uint8_t* reason,
+                              float* margins, cudaStream_t stream) {
+  auto kern = validity_kernel<QT, MARGINS, COLLISION_ONLY>;
+  static bool configured = false;   // per instantiation
+  const size_t smem = kSmemFloats * sizeof(float);
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int64_t blocks = (n + NT - 1) / NT;
+  kern<<<(unsigned)blocks, NT, smem, stream>>>(tab, (const QT*)q, n, valid, reason, margins);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_validity(const ValidityTables& tab, const void* q, int dtype, int64_t n, uint8_t* valid,
+                            uint8_t* reason, float* margins, bool collision_only, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  const bool m = margins != nullptr;
+  if (dtype == NWB_F64) {
+    if (collision_only) return m ? launch_one<double, true, true>(tab, q, n, valid, reason, margins, stream)
+                                 : launch_one<double, false, true>(tab, q, n, valid, reason, margins, stream);
+    return m ? launch_one<double, true, false>(tab, q, n, valid, reason, margins, stream)
+             : launch_one<double, false, false>(tab, q, n, valid, reason, margins, stream);
+  }
+  if (collision_only) return m ? launch_one<float, true, true>(tab, q, n, valid, reason, margins, stream)
+                               : launch_one<float, false, true>(tab, q, n, valid, reason, margins, stream);
+  return m ? launch_one<float, true, false>(tab, q, n, valid, reason, margins, stream)
+           : launch_one<float, false, false>(tab, q, n, valid, reason, margins, stream);
+}
+
+// ---- FK kernel (nwb_fk_batch): every frame + COM, one configuration per thread ----------------
+template <typename QT>
+__global__ void __launch_bounds__(128)
+fk_kernel(const QT* __restrict__ q, int64_t n, double* __restrict__ poses, double* __restrict__ com) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float qv[NWB_NJ];
+#pragma unroll
+  for (int j = 0; j < NWB_NJ; ++j) qv[j] = (float)q[i * NWB_NJ + j];
+  FkVisitor V;
+  V.poses = poses ? poses + (size_t)i * nwbm::kNumFrames * 12 : nullptr;
+  V.com[0] = V.com[1] = V.com[2] = 0.f;
+  { NWB_MODEL_FK_WALK(float, XF<float>, qv, V) }
+  if (com) {
+    com[3 * i + 0] = V.com[0];
+    com[3 * i + 1] = V.com[1];
+    com[3 * i + 2] = V.com[2];
+  }
+}
+
+cudaError_t launch_fk(const void* q, int dtype, int64_t n, double* poses, double* com, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  unsigned blocks = (unsigned)((n + 127) / 128);
+  if (dtype == NWB_F64) fk_kernel<double><<<blocks, 128, 0, stream>>>((const double*)q, n, poses, com);
+  else fk_kernel<float><<<blocks, 128, 0, stream>>>((const float*)q, n, poses, com);
+  return cudaGetLastError();
+}
+
+// ---- FP32 pipe micro-benchmark: 8 independent FFMA chains per thread ----------------------------
+__global__ void __launch_bounds__(256)
+ffma_peak_kernel(int iters, float* sink) {
+  float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f,
+        a6 = a0 + 6.f, a7 = a0 + 7.f;
+  const float m = 0.999f + blockIdx.x * 1e-9f, c = 1e-3f;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+      a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+    }
+  }
+  float s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (s == 123.456f) sink[0] = s;   // never true; keeps the chains alive
+}
+
+cudaError_t launch_ffma_peak(int sm_count, int iters, float* sink, cudaStream_t stream, double* flops_out) {
+  const int blocks = sm_count * 8, threads = 256;   // 2048 threads / SM resident
+  ffma_peak_kernel<<<blocks, threads, 0, stream>>>(iters, sink);
+  if (flops_out) *flops_out = 2.0 * 8 * 16 * (double)iters * blocks * threads;
+  return cudaGetLastError();
+}
+
+}  // namespace nwb

@@ -1,0 +1,247 @@
+// validity_core.cuh - per-configuration validity evaluation, generic over the scalar type T and the
+// storage policy of the proxy point table.
+//
+// On the device T = float and the point table lives in shared memory ([slot][thread]); on the host
+// tools/count_flops.cu instantiates the very same code with a flop-counting scalar to freeze the
+// algorithmic flops per configuration used by the roofline (profiles/roofline.json).
+#pragma once
+#include "nwb_internal.h"
+#include "nwb_math.cuh"
+
+namespace nwb {
+
+// Visitor of the generated FK walk: stores proxy world points, accumulates the COM (x,y) and
+// remembers the left-sole frame.
+template <class T, class Store, bool WANT_COM>
+struct ValidityVisitor {
+  Store& st;
+  T comx, comy;
+  XF<T> lsole;
+  NWB_HD explicit ValidityVisitor(Store& s) : st(s), comx(T(0)), comy(T(0)) {}
+
+  template <int ID>
+  NWB_HD void frame(const XF<T>& F) {
+    using M = nwbm::FrameMass<ID>;
+    if constexpr (M::has && WANT_COM) {
+      comx += T(float(M::w)) * F.p[0];
+      comy += T(float(M::w)) * F.p[1];
+      if constexpr (M::wx != 0) { comx += T(float(M::wx)) * F.r[0]; comy += T(float(M::wx)) * F.r[3]; }
+      if constexpr (M::wy != 0) { comx += T(float(M::wy)) * F.r[1]; comy += T(float(M::wy)) * F.r[4]; }
+      if constexpr (M::wz != 0) { comx += T(float(M::wz)) * F.r[2]; comy += T(float(M::wz)) * F.r[5]; }
+    }
+    using P = nwbm::FrameProxy<ID>;
+    if constexpr (P::has) {
+      put<P::slot, (P::ax != 0), (P::ay != 0), (P::az != 0)>(F, T(float(P::ax)), T(float(P::ay)), T(float(P::az)));
+      if constexpr (!P::sphere)
+        put<P::slot + 3, (P::bx != 0), (P::by != 0), (P::bz != 0)>(F, T(float(P::bx)), T(float(P::by)), T(float(P::bz)));
+    }
+    if constexpr (ID == nwbm::kFrameLSole) lsole = F;
+  }
+  template <int SLOT, bool UX, bool UY, bool UZ>
+  NWB_HD void put(const XF<T>& F, T x, T y, T z) {
+    T wx = F.p[0], wy = F.p[1], wz = F.p[2];
+    if constexpr (UX) { wx += F.r[0] * x; wy += F.r[3] * x; wz += F.r[6] * x; }
+    if constexpr (UY) { wx += F.r[1] * y; wy += F.r[4] * y; wz += F.r[7] * y; }
+    if constexpr (UZ) { wx += F.r[2] * z; wy += F.r[5] * z; wz += F.r[8] * z; }
+    st.put(SLOT + 0, wx);
+    st.put(SLOT + 1, wy);
+    st.put(SLOT + 2, wz);
+  }
+};
+
+template <class T, class Store>
+NWB_HD void load3(const Store& st, int slot, T* o) {
+  o[0] = st.get(slot + 0);
+  o[1] = st.get(slot + 1);
+  o[2] = st.get(slot + 2);
+}
+
+// ---- exact squared distance segment (A + tD, t in [0,1]) -> box, in the box frame ---------------
+// phi(t) = sum_k excess_k(t) * D_k is half the derivative of the convex piecewise-quadratic
+// f(t) = sum_k excess_k(t)^2; it is non-decreasing and piecewise linear with break points at the
+// (<= 6) face crossings.  Bracket its root between the break points, then interpolate linearly.
+template <class T>
+NWB_HD T box_excess(T x, T h) { return x - nwb_min(nwb_max(x, -h), h); }
+template <class T>
+NWB_HD T box_phi(const T* A, const T* D, const T* H, T t) {
+  T s = T(0);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) s += box_excess(A[k] + t * D[k], H[k]) * D[k];
+  return s;
+}
+template <class T>
+NWB_HD T box_f(const T* A, const T* D, const T* H, T t) {
+  T s = T(0);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    T e = box_excess(A[k] + t * D[k], H[k]);
+    s += e * e;
+  }
+  return s;
+}
+template <class T>
+NWB_HD T seg_box_dist2(const T* A, const T* D, const T* H) {
+  T lo = T(0), hi = T(1);
+  const T p0 = box_phi(A, D, H, T(0)), p1 = box_phi(A, D, H, T(1));
+  T plo = p0, phi = p1;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    T inv = nwb_sel(D[k] != T(0), T(1) / D[k], T(0));
+#pragma unroll
+    for (int sg = 0; sg < 2; ++sg) {
+      T face = sg ? H[k] : -H[k];
+      T t = nwb_sat((face - A[k]) * inv);
+      T p = box_phi(A, D, H, t);
+      bool below = (p <= T(0)) && (t >= lo);
+      bool above = (p >= T(0)) && (t <= hi);
+      lo = nwb_sel(below, t, lo); plo = nwb_sel(below, p, plo);
+      hi = nwb_sel(above, t, hi); phi = nwb_sel(above, p, phi);
+    }
+  }
+  T den = phi - plo;
+  T t = nwb_sel(den > T(0), lo + (hi - lo) * nwb_sat(-plo / den), lo);
+  t = nwb_sel(p0 >= T(0), T(0), t);     // already moving away at the start
+  t = nwb_sel(p1 <= T(0), T(1), t);     // still approaching at the end
+  return box_f(A, D, H, t);
+}
+
+struct ValidityResult {
+  bool hit;        // some enabled pair / scene box in contact
+  bool stable;
+};
+
+// Evaluate one configuration.  q = 21 joint values.  MARGINS: also min separation / hull distance.
+template <class T, class Store, bool MARGINS, bool COLLISION_ONLY>
+NWB_HD ValidityResult evaluate_config(const ValidityTables& tab, const T* q, Store& st, T* min_sep_out, T* hull_out) {
+  ValidityVisitor<T, Store, !COLLISION_ONLY> V(st);
+  { NWB_MODEL_FK_WALK(T, XF<T>, q, V) }
+
+  // ---- static stability: projected COM strictly inside hull(right foot U left foot) ------------
+  bool stable = true;
+  T hull_margin = T(0);
+  if constexpr (!COLLISION_ONLY) {
+    const XF<T>& L = V.lsole;
+    if constexpr (!MARGINS) {
+      Wedge<T> w;
+      w.init(T(tab.foot_right[0][0]) - V.comx, T(tab.foot_right[0][1]) - V.comy);
+#pragma unroll
+      for (int k = 1; k < nwbm::kFootN; ++k) w.add(T(tab.foot_right[k][0]) - V.comx, T(tab.foot_right[k][1]) - V.comy);
+#pragma unroll
+      for (int k = 0; k < nwbm::kFootN; ++k) {
+        T x = T(tab.foot_left[k][0]), y = T(tab.foot_left[k][1]);
+        T wx = L.p[0] + L.r[0] * x + L.r[1] * y;
+        T wy = L.p[1] + L.r[3] * x + L.r[4] * y;
+        w.add(wx - V.comx, wy - V.comy);
+      }
+      stable = w.surrounded;
+    } else {
+      T px[2 * nwbm::kFootN], py[2 * nwbm::kFootN];
+#pragma unroll
+      for (int k = 0; k < nwbm::kFootN; ++k) {
+        px[k] = T(tab.foot_right[k][0]);
+        py[k] = T(tab.foot_right[k][1]);
+        T x = T(tab.foot_left[k][0]), y = T(tab.foot_left[k][1]);
+        px[nwbm::kFootN + k] = L.p[0] + L.r[0] * x + L.r[1] * y;
+        py[nwbm::kFootN + k] = L.p[1] + L.r[3] * x + L.r[4] * y;
+      }
+      hull_margin = hull_signed_distance<T, 2 * nwbm::kFootN>(px, py, V.comx, V.comy);
+      stable = hull_margin > T(0);
+    }
+  }
+
+  // ---- self collision over the enabled-pair runs -------------------------------------------------
+  bool hit = false;
+  T min_sep = T(1e30f);
+  auto account = [&](T d2, T rsum) {
+    if constexpr (MARGINS) min_sep = nwb_min(min_sep, nwb_sqrt(d2) - rsum);
+    else hit = hit || (d2 < rsum * rsum);
+  };
+  int r = 0;
+  for (; r < tab.n_runs_cc; ++r) {               // capsule - capsule
+    const PairRun& run = tab.runs[r];
+    T pa[3], qa[3], d1[3];
+    load3(st, run.off_a, pa);
+    load3(st, run.off_a + 3, qa);
+    d1[0] = qa[0] - pa[0]; d1[1] = qa[1] - pa[1]; d1[2] = qa[2] - pa[2];
+    const int cnt = run.count, first = run.first;
+    const T a = T(run.a), inv_a = T(run.inv_a);
+#pragma unroll 2
+    for (int k = 0; k < cnt; ++k) {
+      const PairEntry& pe = tab.entries[first + k];
+      T pb[3], qb[3], d2[3];
+      load3(st, pe.off_b, pb);
+      load3(st, pe.off_b + 3, qb);
+      d2[0] = qb[0] - pb[0]; d2[1] = qb[1] - pb[1]; d2[2] = qb[2] - pb[2];
+      account(seg_seg_dist2(pa, d1, a, inv_a, pb, d2, T(pe.e), T(pe.inv_e)), T(pe.rsum));
+    }
+  }
+  for (; r < tab.n_runs_cc + tab.n_runs_cs; ++r) {   // capsule - sphere
+    const PairRun& run = tab.runs[r];
+    T pa[3], qa[3], d1[3];
+    load3(st, run.off_a, pa);
+    load3(st, run.off_a + 3, qa);
+    d1[0] = qa[0] - pa[0]; d1[1] = qa[1] - pa[1]; d1[2] = qa[2] - pa[2];
+    const int cnt = run.count, first = run.first;
+    const T inv_a = T(run.inv_a);
+#pragma unroll 2
+    for (int k = 0; k < cnt; ++k) {
+      const PairEntry& pe = tab.entries[first + k];
+      T pb[3];
+      load3(st, pe.off_b, pb);
+      account(seg_point_dist2(pa, d1, inv_a, pb), T(pe.rsum));
+    }
+  }
+  for (; r < tab.n_runs_cc + tab.n_runs_cs + tab.n_runs_ss; ++r) {   // sphere - sphere
+    const PairRun& run = tab.runs[r];
+    T pa[3];
+    load3(st, run.off_a, pa);
+    const int cnt = run.count, first = run.first;
+#pragma unroll 2
+    for (int k = 0; k < cnt; ++k) {
+      const PairEntry& pe = tab.entries[first + k];
+      T pb[3];
+      load3(st, pe.off_b, pb);
+      account(point_point_dist2(pa, pb), T(pe.rsum));
+    }
+  }
+
+  // ---- environment: robot proxies against the scene boxes ---------------------------------------
+  for (int b = 0; b < tab.n_boxes; ++b) {
+    const SceneBox& bx = tab.boxes[b];
+    T H[3] = {T(bx.h[0]), T(bx.h[1]), T(bx.h[2])};
+    for (int l = 0; l < tab.n_env_links; ++l) {
+      const EnvLink& el = tab.env_links[l];
+      T pa[3], A[3];
+      load3(st, el.off, pa);
+      T rx = pa[0] - T(bx.c[0]), ry = pa[1] - T(bx.c[1]), rz = pa[2] - T(bx.c[2]);
+      A[0] = T(bx.r[0]) * rx + T(bx.r[3]) * ry + T(bx.r[6]) * rz;      // R^T (a - c)
+      A[1] = T(bx.r[1]) * rx + T(bx.r[4]) * ry + T(bx.r[7]) * rz;
+      A[2] = T(bx.r[2]) * rx + T(bx.r[5]) * ry + T(bx.r[8]) * rz;
+      T d2;
+      if (el.is_sphere) {                                              // table driven: warp-uniform
+        T ex = box_excess(A[0], H[0]), ey = box_excess(A[1], H[1]), ez = box_excess(A[2], H[2]);
+        d2 = ex * ex + ey * ey + ez * ez;
+      } else {
+        T qa[3], D[3];
+        load3(st, el.off + 3, qa);
+        T dx = qa[0] - pa[0], dy = qa[1] - pa[1], dz = qa[2] - pa[2];
+        D[0] = T(bx.r[0]) * dx + T(bx.r[3]) * dy + T(bx.r[6]) * dz;
+        D[1] = T(bx.r[1]) * dx + T(bx.r[4]) * dy + T(bx.r[7]) * dz;
+        D[2] = T(bx.r[2]) * dx + T(bx.r[5]) * dy + T(bx.r[8]) * dz;
+        d2 = seg_box_dist2(A, D, H);
+      }
+      account(d2, T(el.radius));
+    }
+  }
+  if constexpr (MARGINS) {
+    hit = min_sep < T(0);
+    if (min_sep_out) *min_sep_out = min_sep;
+    if (hull_out) *hull_out = hull_margin;
+  }
+  ValidityResult res;
+  res.hit = hit;
+  res.stable = stable;
+  return res;
+}
+
+}  // namespace nwb

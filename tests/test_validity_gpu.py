@@ -1,0 +1,190 @@
+"""GPU parity: the CUDA validity / FK operators (through the C ABI) against the CPU oracle.
+
+Bar (BASELINE.json north_star): validity booleans bit-exact except for configurations within
+1e-5 m of a contact or support-polygon boundary (counted and reported); link poses within 1e-5 m.
+"""
+import numpy as np
+import pytest
+
+import nao_wholebody_planning_b200 as nwb
+import oracle_lib as OL
+
+pytestmark = pytest.mark.gpu
+BAND = 1e-5          # metres, stated by north_star
+POSE_TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = nwb.Context()
+    yield c
+    c.close()
+
+
+def check_validity(ctx, oracle, q, tag, params=None):
+    o_valid, o_reason, o_marg = oracle.is_feasible(q, params=params, threads=oracle.threads)
+    band = (np.abs(o_marg) < BAND).any(1)
+    for want_margins in (False, True):
+        valid, reason, marg = ctx.isFeasible(q, want_margins=want_margins)
+        bad = (valid != o_valid) & ~band
+        assert bad.sum() == 0, f"{tag}: {bad.sum()} validity mismatches outside the band (margins={want_margins})"
+        badr = (reason != o_reason) & ~band
+        assert badr.sum() == 0, f"{tag}: {badr.sum()} reason mismatches outside the band"
+        if want_margins:
+            # separation margin: same definition on both sides
+            assert np.abs(marg[:, 0] - o_marg[:, 0]).max() < 2e-6, tag
+            # hull margin: same definition (line distance inside, hull distance outside)
+            assert np.abs(marg[:, 1] - o_marg[:, 1]).max() < 2e-6, tag
+    print(f"{tag}: n={len(q)} valid={o_valid.mean():.4f} collision={(o_reason & 1).mean():.4f} "
+          f"unstable={((o_reason & 2) != 0).mean():.4f} in-band={int(band.sum())}")
+    return band.sum()
+
+
+def test_V1_uniform_random_configs(ctx, oracle):
+    check_validity(ctx, oracle, OL.uniform_configs(20000, seed=20121001), "V1")
+
+
+def test_V1b_lhipyawpitch_zero(ctx, oracle):
+    check_validity(ctx, oracle, OL.uniform_configs(20000, seed=20121001, lhyp_zero=True), "V1b")
+
+
+def test_V1d_noisy_database_rows_near_the_boundary(ctx, oracle):
+    check_validity(ctx, oracle, OL.noisy_db_configs(20000), "V1d")
+
+
+def test_golden_rows(ctx, oracle):
+    q = OL.golden_valid_rows()
+    valid, reason, _ = ctx.isFeasible(q)
+    assert (reason & 1).sum() == 0                      # E12 one-sided gate, on the GPU path
+    check_validity(ctx, oracle, q, "golden")
+
+
+def test_ragged_sizes_and_empty(ctx, oracle):
+    for n in (0, 1, 2, 31, 127, 128, 129, 1000, 4097):
+        q = OL.noisy_db_configs(max(n, 1), seed=n + 1)[:n]
+        valid, reason, _ = ctx.isFeasible(q)
+        assert valid.shape == (n,)
+        if n:
+            o_valid, o_reason, o_marg = oracle.is_feasible(q)
+            band = (np.abs(o_marg) < BAND).any(1)
+            assert ((valid == o_valid) | band).all()
+
+
+def test_joint_limit_extremes(ctx, oracle):
+    lo, hi = OL.joint_limits()
+    rng = np.random.default_rng(3)
+    q = np.where(rng.random((4096, nwb.NJ)) < 0.5, lo, hi)   # every joint at one of its limits
+    check_validity(ctx, oracle, q, "corners")
+
+
+def test_scale_support_polygon(oracle):
+    q = OL.noisy_db_configs(8000, seed=9)
+    for scale in (1.0, 0.5):
+        with nwb.Context(scale_sp=scale) as c:
+            check_validity(c, oracle, q, f"scale{scale}", params=OL.default_params(scale_sp=scale))
+    with nwb.Context() as c:
+        c.scale_support_polygon(0.6)
+        check_validity(c, oracle, q, "rescaled", params=OL.default_params(scale_sp=0.6))
+    with nwb.Context(scale_origin=0) as c:
+        check_validity(c, oracle, q, "sole-origin", params=OL.default_params(scale_origin=0))
+
+
+def test_srdf_notrim_pair_set(oracle):
+    q = OL.uniform_configs(8000, seed=5)
+    with nwb.Context(srdf_trim=0) as c:
+        check_validity(c, oracle, q, "notrim", params=OL.default_params(srdf_trim=0))
+
+
+def test_state_colliding_whole_robot(ctx, oracle):
+    q = OL.uniform_configs(10000, seed=21)
+    o_col, o_sep = oracle.is_state_colliding(q, group_only=False)
+    col, sep = ctx.is_state_colliding(q, want_separation=True)
+    band = np.abs(o_sep) < BAND
+    assert ((col == o_col) | band).all()
+    assert np.abs(sep - o_sep).max() < 2e-6
+    col2, _ = ctx.is_state_colliding(q)
+    assert ((col2 == o_col) | band).all()
+
+
+def test_link_poses_and_com(ctx, oracle):
+    q = np.concatenate([OL.uniform_configs(3000, seed=4), OL.golden_db()])
+    poses, com = ctx.fk(q)
+    o_poses, o_com = oracle.fk(q)
+    assert np.abs(poses - o_poses).max() < POSE_TOL
+    assert np.abs(com - o_com).max() < POSE_TOL
+    # left sole of the shipped database rows sits at (0, 0.1, 0) (E1, through the GPU path)
+    lsole = poses[-463:, 28, :, 3]
+    assert np.abs(lsole - [0, 0.1, 0]).max() < 1.1e-3
+
+
+def test_full_size_properties(ctx):
+    """BASELINE size (1M): size-independent properties - determinism, batch-split invariance,
+    valid == (reason == 0)."""
+    q = OL.uniform_configs(1 << 20, seed=20121001)
+    v1, r1, _ = ctx.isFeasible(q)
+    v2, r2, _ = ctx.isFeasible(q)
+    assert (v1 == v2).all() and (r1 == r2).all()
+    assert ((r1 == 0) == (v1 == 1)).all()
+    parts = [ctx.isFeasible(q[a:b])[0] for a, b in ((0, 300001), (300001, 777777), (777777, 1 << 20))]
+    assert (np.concatenate(parts) == v1).all()
+    perm = np.random.default_rng(0).permutation(len(q))[:100000]
+    vp, _, _ = ctx.isFeasible(q[perm])
+    assert (vp == v1[perm]).all()
+    assert 0.05 < v1.mean() < 0.3
+
+
+def test_device_pointer_variant_f32_and_f64(ctx, oracle):
+    import torch
+    q = OL.noisy_db_configs(50000, seed=13)
+    o_valid, _, o_marg = oracle.is_feasible(q, threads=oracle.threads)
+    band = (np.abs(o_marg) < 1e-4).any(1)      # f32 inputs are rounded: widen the band for that variant
+    for dtype, code in ((torch.float64, nwb.F64), (torch.float32, nwb.F32)):
+        qd = torch.tensor(q, dtype=dtype, device="cuda")
+        valid = torch.empty(len(q), dtype=torch.uint8, device="cuda")
+        reason = torch.empty(len(q), dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        ctx.is_feasible_dev(qd.data_ptr(), code, len(q), valid.data_ptr(), reason.data_ptr())
+        ctx.synchronize()
+        v = valid.cpu().numpy()
+        assert ((v == o_valid) | band).all()
+        ms, launches = ctx.last_kernel_ms()
+        assert launches == 1 and ms > 0
+
+
+@pytest.mark.parametrize("scene", ["S1", "S2", "S3"])
+def test_environment_boxes(oracle, scene):
+    """Scene boxes of SURVEY.md Appendix D (shelf, table, drawer + beam): capsule/sphere vs box."""
+    boxes = OL.scene_boxes(scene)
+    q = np.concatenate([OL.uniform_configs(6000, seed=31), OL.noisy_db_configs(6000, seed=32)])
+    o_valid, o_reason, o_marg = oracle.is_feasible(q, boxes=boxes, threads=oracle.threads)
+    o_free, _, o_marg0 = oracle.is_feasible(q, threads=oracle.threads)
+    assert ((o_reason & 1) != 0).sum() > ((_ & 1) != 0).sum()          # the scene adds collisions
+    band = (np.abs(o_marg) < BAND).any(1)
+    with nwb.Context() as c:
+        c.scene_add_boxes(boxes)
+        assert c.num_boxes == len(boxes)
+        for want_margins in (False, True):
+            valid, reason, marg = c.isFeasible(q, want_margins=want_margins)
+            assert (((valid == o_valid) & (reason == o_reason)) | band).all(), scene
+            if want_margins:
+                assert np.abs(marg[:, 0] - o_marg[:, 0]).max() < 3e-6
+        col, sep = c.is_state_colliding(q, want_separation=True)
+        o_col, o_sep = oracle.is_state_colliding(q, boxes=boxes, group_only=False)
+        assert ((col == o_col) | (np.abs(o_sep) < BAND)).all()
+        c.scene_clear()
+        valid, _, _ = c.isFeasible(q)
+        assert ((valid == o_free) | (np.abs(o_marg0) < BAND).any(1)).all()
+
+
+def test_rotated_box(oracle):
+    ang = 0.6
+    R = [np.cos(ang), -np.sin(ang), 0, np.sin(ang), np.cos(ang), 0, 0, 0, 1]
+    boxes = np.array([[0.2, 0.05, 0.25, 0.2, 0.1, 0.3] + R])
+    q = OL.uniform_configs(8000, seed=33)
+    o_valid, o_reason, o_marg = oracle.is_feasible(q, boxes=boxes, threads=oracle.threads)
+    band = (np.abs(o_marg) < BAND).any(1)
+    with nwb.Context() as c:
+        c.scene_add_boxes(boxes)
+        valid, reason, marg = c.isFeasible(q, want_margins=True)
+        assert (((valid == o_valid) & (reason == o_reason)) | band).all()
+        assert np.abs(marg[:, 0] - o_marg[:, 0]).max() < 3e-6
