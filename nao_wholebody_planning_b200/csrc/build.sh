@@ -5,7 +5,7 @@ cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 OUT=../libnwb.so
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -fvisibility=hidden
-       --expt-relaxed-constexpr -cudart static -Xptxas -v)
+       --expt-relaxed-constexpr -cudart static -Xptxas -v -DNWB_FAST_SINCOS ${NWB_EXTRA_FLAGS:-})
 SRCS=(validity.cu nwb_abi.cu)
 OBJS=()
 mkdir -p build

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 
@@ -119,6 +120,7 @@ int nwb_ctx_create(const nwb_params* params, nwb_ctx** out) {
     nwb_ctx_destroy(ctx);
     return NWB_E_CUDA;
   }
+  ctx->force_table_pairs = getenv("NWB_FORCE_TABLE_PAIRS") != nullptr;
   build_tables(ctx);
   *out = ctx;
   return NWB_OK;
@@ -214,7 +216,7 @@ void nwb_host_free(void* p) {
 static int feasible_dev(nwb_ctx* ctx, const ValidityTables& tab, const void* q, int dtype, int64_t n, uint8_t* valid,
                         uint8_t* reason, float* margins, bool collision_only) {
   NWB_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-  NWB_CUDA(ctx, launch_validity(tab, q, dtype, n, valid, reason, margins, collision_only, ctx->stream));
+  NWB_CUDA(ctx, launch_validity(tab, q, dtype, n, valid, reason, margins, collision_only, ctx->params.srdf_trim != 0 && !ctx->force_table_pairs, ctx->stream));
   NWB_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->last_launches = n > 0 ? 1 : 0;
   ctx->last_ms = -1;   // resolved lazily by nwb_last_kernel_ms
@@ -266,7 +268,7 @@ static int feasible_host(nwb_ctx* ctx, const ValidityTables& tab, const double* 
     NWB_CUDA(ctx, cudaEventRecord(in_done[s], copy_stream));
     NWB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, in_done[s], 0));
     NWB_CUDA(ctx, launch_validity(tab, din, NWB_F64, cn, d_valid, reason ? d_reason : nullptr, margins ? d_marg : nullptr,
-                                  collision_only, ctx->stream));
+                                  collision_only, ctx->params.srdf_trim != 0 && !ctx->force_table_pairs, ctx->stream));
     ++launches;
     NWB_CUDA(ctx, cudaMemcpyAsync(valid + off, d_valid, (size_t)cn, cudaMemcpyDeviceToHost, ctx->stream));
     if (reason) NWB_CUDA(ctx, cudaMemcpyAsync(reason + off, d_reason, (size_t)cn, cudaMemcpyDeviceToHost, ctx->stream));

@@ -74,13 +74,14 @@ struct Ctx {
   double last_ms = 0;
   int64_t last_launches = 0;
   int sm_count = 0;
+  bool force_table_pairs = false;   // NWB_FORCE_TABLE_PAIRS=1: use the table-driven pair loops (A/B measurements)
 };
 
 void build_tables(Ctx* ctx);
 
 // kernel launchers (validity.cu).  q is [n][21] of float or double on the device.
 cudaError_t launch_validity(const ValidityTables& tab, const void* q, int dtype, int64_t n, uint8_t* valid,
-                            uint8_t* reason, float* margins, bool collision_only, cudaStream_t stream);
+                            uint8_t* reason, float* margins, bool collision_only, bool static_pairs, cudaStream_t stream);
 cudaError_t launch_fk(const void* q, int dtype, int64_t n, double* poses, double* com, cudaStream_t stream);
 cudaError_t launch_ffma_peak(int sm_count, int iters, float* sink, cudaStream_t stream, double* flops_out);
 

@@ -18,7 +18,9 @@ namespace nwb {
 
 // ---- scalar helpers (overloaded for float / double; a counting type provides its own) --------
 NWB_HD void nwb_sincos(float a, float& s, float& c) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(NWB_FAST_SINCOS)
+  s = __sinf(a); c = __cosf(a);
+#elif defined(__CUDA_ARCH__)
   sincosf(a, &s, &c);
 #else
   s = sinf(a); c = cosf(a);
@@ -49,6 +51,16 @@ NWB_HD float nwb_abs(float a) { return fabsf(a); }
 NWB_HD double nwb_abs(double a) { return fabs(a); }
 template <class T>
 NWB_HD T nwb_sel(bool c, T a, T b) { return c ? a : b; }
+// a / b where 2 ulp are enough (interpolation parameters that get clamped to [0,1] anyway):
+// one MUFU.RCP + one FMUL on the device instead of the IEEE division sequence.
+NWB_HD float nwb_div_fast(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fdividef(a, b);
+#else
+  return a / b;
+#endif
+}
+NWB_HD double nwb_div_fast(double a, double b) { return a / b; }
 
 // ---- rigid transform: rotation (row-major r[3*row+col]) + translation, in the r_sole frame ----
 template <class T>
@@ -124,7 +136,10 @@ NWB_HD void nwb_xf_point(const XF<T>& f, T x, T y, T z, T& ox, T& oy, T& oz) {
 
 // ---- closest squared distance between two segments, lengths known at compile time -------------
 // Segment A = pa + s*d1, B = pb + t*d2.  a = |d1|^2, e = |d2|^2 (link constants), inv_a = 1/a,
-// inv_e = 1/e.  Branch-free form of Ericson's ClosestPtSegmentSegment.
+// inv_e = 1/e (0 for a degenerate segment = sphere centre).
+// Branch-free: unconstrained optimum for s (clamped), best t for that s (clamped), then the best s
+// for that t (clamped).  The last step reproduces both end-point cases of Ericson's
+// ClosestPtSegmentSegment and leaves an interior optimum unchanged, without any select.
 template <class T>
 NWB_HD T seg_seg_dist2(const T* pa, const T* d1, T a, T inv_a, const T* pb, const T* d2, T e, T inv_e) {
   T rx = pa[0] - pb[0], ry = pa[1] - pb[1], rz = pa[2] - pb[2];
@@ -132,12 +147,9 @@ NWB_HD T seg_seg_dist2(const T* pa, const T* d1, T a, T inv_a, const T* pb, cons
   T c = d1[0] * rx + d1[1] * ry + d1[2] * rz;
   T b = d1[0] * d2[0] + d1[1] * d2[1] + d1[2] * d2[2];
   T denom = a * e - b * b;
-  T s = nwb_sel(denom > T(1e-12), nwb_sat((b * f - c * e) / denom), T(0));
-  T t = (b * s + f) * inv_e;
-  T s_lo = nwb_sat(-c * inv_a);
-  T s_hi = nwb_sat((b - c) * inv_a);
-  s = nwb_sel(t < T(0), s_lo, nwb_sel(t > T(1), s_hi, s));
-  t = nwb_sat(t);
+  T s = nwb_sel(denom > T(1e-12), nwb_sat(nwb_div_fast(b * f - c * e, denom)), T(0));
+  T t = nwb_sat((b * s + f) * inv_e);
+  s = nwb_sat((b * t - c) * inv_a);
   T vx = rx + d1[0] * s - d2[0] * t;
   T vy = ry + d1[1] * s - d2[1] * t;
   T vz = rz + d1[2] * s - d2[2] * t;

@@ -28,6 +28,14 @@ struct SmemStore {
   __device__ __forceinline__ float get(int slot) const { return base[slot * NT]; }
 };
 
+// Point table in registers: only valid where every slot index is a compile-time constant (the
+// compiled-in pair list); no shared memory, occupancy is set by registers alone.
+struct RegStore {
+  float v[nwbm::kPointFloats];
+  __device__ __forceinline__ void put(int slot, float x) { v[slot] = x; }
+  __device__ __forceinline__ float get(int slot) const { return v[slot]; }
+};
+
 // Writes every frame and the full COM to global memory (nwb_fk_batch).
 struct FkVisitor {
   double* poses;   // [29][12] of this configuration, or nullptr
@@ -54,7 +62,7 @@ struct FkVisitor {
 // ---- the validity kernel ------------------------------------------------------------------------
 //   MARGINS        also produce {min separation, signed hull distance} (sqrt per pair + gift wrapping)
 //   COLLISION_ONLY skip COM / support (isPathValid way-points)
-template <typename QT, bool MARGINS, bool COLLISION_ONLY>
+template <typename QT, bool MARGINS, bool COLLISION_ONLY, int PAIRS>
 __global__ void __launch_bounds__(NT, 3)
 validity_kernel(const __grid_constant__ ValidityTables tab, const QT* __restrict__ q, int64_t n,
                 uint8_t* __restrict__ valid, uint8_t* __restrict__ reason, float* __restrict__ margins) {
@@ -71,11 +79,17 @@ validity_kernel(const __grid_constant__ ValidityTables tab, const QT* __restrict
   const int row = tid < nvalid ? tid : 0;     // idle lanes recompute row 0 (keeps the warp converged)
 #pragma unroll
   for (int j = 0; j < NWB_NJ; ++j) qv[j] = smem[row * NWB_NJ + j];   // stride 21 words: conflict-free
-  __syncthreads();                            // staging area is reused as the point table below
+  if constexpr (PAIRS == PAIRS_TABLE) __syncthreads();   // staging area is reused as the point table below
 
-  SmemStore st{smem + tid};
   float min_sep = 0.f, hull_margin = 0.f;
-  const ValidityResult res = evaluate_config<float, SmemStore, MARGINS, COLLISION_ONLY>(tab, qv, st, &min_sep, &hull_margin);
+  ValidityResult res;
+  if constexpr (PAIRS == PAIRS_TABLE) {
+    SmemStore st{smem + tid};
+    res = evaluate_config<float, SmemStore, MARGINS, COLLISION_ONLY, PAIRS>(tab, qv, st, &min_sep, &hull_margin);
+  } else {
+    RegStore st;
+    res = evaluate_config<float, RegStore, MARGINS, COLLISION_ONLY, PAIRS>(tab, qv, st, &min_sep, &hull_margin);
+  }
 
   if (i < n) {
     unsigned rs = (res.hit ? NWB_REASON_COLLISION : 0u) | (res.stable ? 0u : NWB_REASON_UNSTABLE);
@@ -90,12 +104,12 @@ validity_kernel(const __grid_constant__ ValidityTables tab, const QT* __restrict
   }
 }
 
-template <typename QT, bool MARGINS, bool COLLISION_ONLY>
+template <typename QT, bool MARGINS, bool COLLISION_ONLY, int PAIRS>
 static cudaError_t launch_one(const ValidityTables& tab, const void* q, int64_t n, uint8_t* valid, uint8_t* reason,
                               float* margins, cudaStream_t stream) {
-  auto kern = validity_kernel<QT, MARGINS, COLLISION_ONLY>;
+  auto kern = validity_kernel<QT, MARGINS, COLLISION_ONLY, PAIRS>;
   static bool configured = false;   // per instantiation
-  const size_t smem = kSmemFloats * sizeof(float);
+  const size_t smem = (PAIRS == PAIRS_TABLE ? kSmemFloats : NT * NWB_NJ) * sizeof(float);
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -106,20 +120,27 @@ static cudaError_t launch_one(const ValidityTables& tab, const void* q, int64_t 
   return cudaGetLastError();
 }
 
+template <typename QT, bool COLLISION_ONLY>
+static cudaError_t launch_qt(const ValidityTables& tab, const void* q, int64_t n, uint8_t* valid, uint8_t* reason,
+                             float* margins, bool static_pairs, cudaStream_t stream) {
+  constexpr int kStatic = COLLISION_ONLY ? PAIRS_STATIC_ALL : PAIRS_STATIC_GROUP;
+  if (static_pairs)
+    return margins ? launch_one<QT, true, COLLISION_ONLY, kStatic>(tab, q, n, valid, reason, margins, stream)
+                   : launch_one<QT, false, COLLISION_ONLY, kStatic>(tab, q, n, valid, reason, margins, stream);
+  return margins ? launch_one<QT, true, COLLISION_ONLY, PAIRS_TABLE>(tab, q, n, valid, reason, margins, stream)
+                 : launch_one<QT, false, COLLISION_ONLY, PAIRS_TABLE>(tab, q, n, valid, reason, margins, stream);
+}
+
+// static_pairs: the context uses the default SRDF reading, so the compiled-in pair list applies
+// (group set for isFeasible, whole-robot set for the collision-only predicate).
 cudaError_t launch_validity(const ValidityTables& tab, const void* q, int dtype, int64_t n, uint8_t* valid,
-                            uint8_t* reason, float* margins, bool collision_only, cudaStream_t stream) {
+                            uint8_t* reason, float* margins, bool collision_only, bool static_pairs, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
-  const bool m = margins != nullptr;
-  if (dtype == NWB_F64) {
-    if (collision_only) return m ? launch_one<double, true, true>(tab, q, n, valid, reason, margins, stream)
-                                 : launch_one<double, false, true>(tab, q, n, valid, reason, margins, stream);
-    return m ? launch_one<double, true, false>(tab, q, n, valid, reason, margins, stream)
-             : launch_one<double, false, false>(tab, q, n, valid, reason, margins, stream);
-  }
-  if (collision_only) return m ? launch_one<float, true, true>(tab, q, n, valid, reason, margins, stream)
-                               : launch_one<float, false, true>(tab, q, n, valid, reason, margins, stream);
-  return m ? launch_one<float, true, false>(tab, q, n, valid, reason, margins, stream)
-           : launch_one<float, false, false>(tab, q, n, valid, reason, margins, stream);
+  if (dtype == NWB_F64)
+    return collision_only ? launch_qt<double, true>(tab, q, n, valid, reason, margins, static_pairs, stream)
+                          : launch_qt<double, false>(tab, q, n, valid, reason, margins, static_pairs, stream);
+  return collision_only ? launch_qt<float, true>(tab, q, n, valid, reason, margins, static_pairs, stream)
+                        : launch_qt<float, false>(tab, q, n, valid, reason, margins, static_pairs, stream);
 }
 
 // ---- FK kernel (nwb_fk_batch): every frame + COM, one configuration per thread ----------------

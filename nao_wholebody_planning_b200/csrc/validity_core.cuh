@@ -110,8 +110,12 @@ struct ValidityResult {
   bool stable;
 };
 
+// Pair-set selector: the default SRDF reading is compiled in (every slot, length and radius an
+// immediate, loops fully unrolled); any other reading walks the runtime tables.
+enum PairMode { PAIRS_TABLE = 0, PAIRS_STATIC_GROUP = 1, PAIRS_STATIC_ALL = 2 };
+
 // Evaluate one configuration.  q = 21 joint values.  MARGINS: also min separation / hull distance.
-template <class T, class Store, bool MARGINS, bool COLLISION_ONLY>
+template <class T, class Store, bool MARGINS, bool COLLISION_ONLY, int PAIRS = PAIRS_TABLE>
 NWB_HD ValidityResult evaluate_config(const ValidityTables& tab, const T* q, Store& st, T* min_sep_out, T* hull_out) {
   ValidityVisitor<T, Store, !COLLISION_ONLY> V(st);
   { NWB_MODEL_FK_WALK(T, XF<T>, q, V) }
@@ -156,81 +160,132 @@ NWB_HD ValidityResult evaluate_config(const ValidityTables& tab, const T* q, Sto
     if constexpr (MARGINS) min_sep = nwb_min(min_sep, nwb_sqrt(d2) - rsum);
     else hit = hit || (d2 < rsum * rsum);
   };
-  int r = 0;
-  for (; r < tab.n_runs_cc; ++r) {               // capsule - capsule
-    const PairRun& run = tab.runs[r];
-    T pa[3], qa[3], d1[3];
-    load3(st, run.off_a, pa);
-    load3(st, run.off_a + 3, qa);
-    d1[0] = qa[0] - pa[0]; d1[1] = qa[1] - pa[1]; d1[2] = qa[2] - pa[2];
-    const int cnt = run.count, first = run.first;
-    const T a = T(run.a), inv_a = T(run.inv_a);
-#pragma unroll 2
-    for (int k = 0; k < cnt; ++k) {
-      const PairEntry& pe = tab.entries[first + k];
-      T pb[3], qb[3], d2[3];
-      load3(st, pe.off_b, pb);
-      load3(st, pe.off_b + 3, qb);
-      d2[0] = qb[0] - pb[0]; d2[1] = qb[1] - pb[1]; d2[2] = qb[2] - pb[2];
-      account(seg_seg_dist2(pa, d1, a, inv_a, pb, d2, T(pe.e), T(pe.inv_e)), T(pe.rsum));
+  auto account2 = [&](T d2, T rsum, T rsum2) {   // (rA+rB)^2 known at compile time
+    if constexpr (MARGINS) min_sep = nwb_min(min_sep, nwb_sqrt(d2) - rsum);
+    else hit = hit || (d2 < rsum2);
+  };
+  (void)account2;
+  if constexpr (PAIRS == PAIRS_TABLE) {
+    int r = 0;
+    for (; r < tab.n_runs_cc; ++r) {               // capsule - capsule
+      const PairRun& run = tab.runs[r];
+      T pa[3], qa[3], d1[3];
+      load3(st, run.off_a, pa);
+      load3(st, run.off_a + 3, qa);
+      d1[0] = qa[0] - pa[0]; d1[1] = qa[1] - pa[1]; d1[2] = qa[2] - pa[2];
+      const int cnt = run.count, first = run.first;
+      const T a = T(run.a), inv_a = T(run.inv_a);
+  #pragma unroll 2
+      for (int k = 0; k < cnt; ++k) {
+        const PairEntry& pe = tab.entries[first + k];
+        T pb[3], qb[3], d2[3];
+        load3(st, pe.off_b, pb);
+        load3(st, pe.off_b + 3, qb);
+        d2[0] = qb[0] - pb[0]; d2[1] = qb[1] - pb[1]; d2[2] = qb[2] - pb[2];
+        account(seg_seg_dist2(pa, d1, a, inv_a, pb, d2, T(pe.e), T(pe.inv_e)), T(pe.rsum));
+      }
     }
-  }
-  for (; r < tab.n_runs_cc + tab.n_runs_cs; ++r) {   // capsule - sphere
-    const PairRun& run = tab.runs[r];
-    T pa[3], qa[3], d1[3];
-    load3(st, run.off_a, pa);
-    load3(st, run.off_a + 3, qa);
-    d1[0] = qa[0] - pa[0]; d1[1] = qa[1] - pa[1]; d1[2] = qa[2] - pa[2];
-    const int cnt = run.count, first = run.first;
-    const T inv_a = T(run.inv_a);
-#pragma unroll 2
-    for (int k = 0; k < cnt; ++k) {
-      const PairEntry& pe = tab.entries[first + k];
-      T pb[3];
-      load3(st, pe.off_b, pb);
-      account(seg_point_dist2(pa, d1, inv_a, pb), T(pe.rsum));
+    for (; r < tab.n_runs_cc + tab.n_runs_cs; ++r) {   // capsule - sphere
+      const PairRun& run = tab.runs[r];
+      T pa[3], qa[3], d1[3];
+      load3(st, run.off_a, pa);
+      load3(st, run.off_a + 3, qa);
+      d1[0] = qa[0] - pa[0]; d1[1] = qa[1] - pa[1]; d1[2] = qa[2] - pa[2];
+      const int cnt = run.count, first = run.first;
+      const T inv_a = T(run.inv_a);
+  #pragma unroll 2
+      for (int k = 0; k < cnt; ++k) {
+        const PairEntry& pe = tab.entries[first + k];
+        T pb[3];
+        load3(st, pe.off_b, pb);
+        account(seg_point_dist2(pa, d1, inv_a, pb), T(pe.rsum));
+      }
     }
-  }
-  for (; r < tab.n_runs_cc + tab.n_runs_cs + tab.n_runs_ss; ++r) {   // sphere - sphere
-    const PairRun& run = tab.runs[r];
-    T pa[3];
-    load3(st, run.off_a, pa);
-    const int cnt = run.count, first = run.first;
-#pragma unroll 2
-    for (int k = 0; k < cnt; ++k) {
-      const PairEntry& pe = tab.entries[first + k];
-      T pb[3];
-      load3(st, pe.off_b, pb);
-      account(point_point_dist2(pa, pb), T(pe.rsum));
+    for (; r < tab.n_runs_cc + tab.n_runs_cs + tab.n_runs_ss; ++r) {   // sphere - sphere
+      const PairRun& run = tab.runs[r];
+      T pa[3];
+      load3(st, run.off_a, pa);
+      const int cnt = run.count, first = run.first;
+  #pragma unroll 2
+      for (int k = 0; k < cnt; ++k) {
+        const PairEntry& pe = tab.entries[first + k];
+        T pb[3];
+        load3(st, pe.off_b, pb);
+        account(point_point_dist2(pa, pb), T(pe.rsum));
+      }
     }
+  } else {
+#define NWB_X_CC(SA, LA, ILA, SB, LB, ILB, RS, RS2)                                        \
+    {                                                                                        \
+      T pa[3], qa[3], d1[3], pb[3], qb[3], d2[3];                                            \
+      load3(st, SA, pa); load3(st, SA + 3, qa); load3(st, SB, pb); load3(st, SB + 3, qb);    \
+      d1[0] = qa[0] - pa[0]; d1[1] = qa[1] - pa[1]; d1[2] = qa[2] - pa[2];                   \
+      d2[0] = qb[0] - pb[0]; d2[1] = qb[1] - pb[1]; d2[2] = qb[2] - pb[2];                   \
+      account2(seg_seg_dist2(pa, d1, T(LA), T(ILA), pb, d2, T(LB), T(ILB)), T(RS), T(RS2)); \
+    }
+#define NWB_X_CS(SA, LA, ILA, SB, LB, ILB, RS, RS2)                                        \
+    {                                                                                        \
+      T pa[3], qa[3], d1[3], pb[3];                                                          \
+      load3(st, SA, pa); load3(st, SA + 3, qa); load3(st, SB, pb);                           \
+      d1[0] = qa[0] - pa[0]; d1[1] = qa[1] - pa[1]; d1[2] = qa[2] - pa[2];                   \
+      account2(seg_point_dist2(pa, d1, T(ILA), pb), T(RS), T(RS2));                          \
+    }
+#define NWB_X_SS(SA, LA, ILA, SB, LB, ILB, RS, RS2)                                        \
+    {                                                                                        \
+      T pa[3], pb[3];                                                                        \
+      load3(st, SA, pa); load3(st, SB, pb);                                                  \
+      account2(point_point_dist2(pa, pb), T(RS), T(RS2));                                    \
+    }
+    if constexpr (PAIRS == PAIRS_STATIC_GROUP) {
+      NWB_PAIRS_CC_GROUP(NWB_X_CC)
+      NWB_PAIRS_CS_GROUP(NWB_X_CS)
+      NWB_PAIRS_SS_GROUP(NWB_X_SS)
+    } else {
+      NWB_PAIRS_CC_ALL(NWB_X_CC)
+      NWB_PAIRS_CS_ALL(NWB_X_CS)
+      NWB_PAIRS_SS_ALL(NWB_X_SS)
+    }
+#undef NWB_X_CC
+#undef NWB_X_CS
+#undef NWB_X_SS
   }
 
   // ---- environment: robot proxies against the scene boxes ---------------------------------------
   for (int b = 0; b < tab.n_boxes; ++b) {
     const SceneBox& bx = tab.boxes[b];
-    T H[3] = {T(bx.h[0]), T(bx.h[1]), T(bx.h[2])};
-    for (int l = 0; l < tab.n_env_links; ++l) {
-      const EnvLink& el = tab.env_links[l];
+    const T H[3] = {T(bx.h[0]), T(bx.h[1]), T(bx.h[2])};
+    auto env_link = [&](int off, bool is_sphere, T radius) {
       T pa[3], A[3];
-      load3(st, el.off, pa);
+      load3(st, off, pa);
       T rx = pa[0] - T(bx.c[0]), ry = pa[1] - T(bx.c[1]), rz = pa[2] - T(bx.c[2]);
       A[0] = T(bx.r[0]) * rx + T(bx.r[3]) * ry + T(bx.r[6]) * rz;      // R^T (a - c)
       A[1] = T(bx.r[1]) * rx + T(bx.r[4]) * ry + T(bx.r[7]) * rz;
       A[2] = T(bx.r[2]) * rx + T(bx.r[5]) * ry + T(bx.r[8]) * rz;
       T d2;
-      if (el.is_sphere) {                                              // table driven: warp-uniform
+      if (is_sphere) {                                                 // table / compile-time: warp-uniform
         T ex = box_excess(A[0], H[0]), ey = box_excess(A[1], H[1]), ez = box_excess(A[2], H[2]);
         d2 = ex * ex + ey * ey + ez * ez;
       } else {
         T qa[3], D[3];
-        load3(st, el.off + 3, qa);
+        load3(st, off + 3, qa);
         T dx = qa[0] - pa[0], dy = qa[1] - pa[1], dz = qa[2] - pa[2];
         D[0] = T(bx.r[0]) * dx + T(bx.r[3]) * dy + T(bx.r[6]) * dz;
         D[1] = T(bx.r[1]) * dx + T(bx.r[4]) * dy + T(bx.r[7]) * dz;
         D[2] = T(bx.r[2]) * dx + T(bx.r[5]) * dy + T(bx.r[8]) * dz;
         d2 = seg_box_dist2(A, D, H);
       }
-      account(d2, T(el.radius));
+      account(d2, radius);
+    };
+    if constexpr (PAIRS == PAIRS_TABLE) {
+      for (int l = 0; l < tab.n_env_links; ++l) {
+        const EnvLink& el = tab.env_links[l];
+        env_link(el.off, el.is_sphere != 0, T(el.radius));
+      }
+    } else {
+#define NWB_X_ENV(SLOT, SPHERE, R) env_link(SLOT, SPHERE, T(R));
+      if constexpr (PAIRS == PAIRS_STATIC_GROUP) { NWB_ENV_LINKS_GROUP(NWB_X_ENV) }
+      else { NWB_ENV_LINKS_ALL(NWB_X_ENV) }
+#undef NWB_X_ENV
     }
   }
   if constexpr (MARGINS) {

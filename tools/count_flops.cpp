@@ -40,6 +40,7 @@ inline Counted nwb_sqrt(Counted x) { ++Counted::flops; return Counted(std::sqrt(
 inline Counted nwb_min(Counted a, Counted b) { ++Counted::flops; return Counted(std::fmin(a.v, b.v)); }
 inline Counted nwb_max(Counted a, Counted b) { ++Counted::flops; return Counted(std::fmax(a.v, b.v)); }
 inline Counted nwb_abs(Counted a) { return Counted(std::fabs(a.v)); }
+inline Counted nwb_div_fast(Counted a, Counted b) { ++Counted::flops; return Counted(a.v / b.v); }
 }  // namespace nwb
 
 #include "../nao_wholebody_planning_b200/csrc/nwb_tables.h"
@@ -72,7 +73,7 @@ static std::vector<SceneBox> shelf_scene() {   // S1 of SURVEY.md Appendix D
   return v;
 }
 
-template <bool MARGINS, bool COLLISION_ONLY>
+template <bool MARGINS, bool COLLISION_ONLY, int PAIRS = PAIRS_TABLE>
 static double count(const ValidityTables& tab, int samples) {
   std::mt19937_64 rng(20121001);
   std::uniform_real_distribution<double> U(0, 1);
@@ -83,7 +84,7 @@ static double count(const ValidityTables& tab, int samples) {
     ArrayStore st;
     Counted ms, hm;
     Counted::flops = 0;
-    evaluate_config<Counted, ArrayStore, MARGINS, COLLISION_ONLY>(tab, q, st, &ms, &hm);
+    evaluate_config<Counted, ArrayStore, MARGINS, COLLISION_ONLY, PAIRS>(tab, q, st, &ms, &hm);
     total += Counted::flops;
   }
   return (double)total / samples;
@@ -105,7 +106,10 @@ int main() {
   printf(" \"convention\": \"add/sub/mul/div/sqrt/min/max/saturate/compare = 1 flop, sincos = 2, FMA = 2; selects free\",\n");
   printf(" \"source\": \"tools/count_flops.cpp: csrc/validity_core.cuh instantiated with a counting scalar, mean over %d uniform configs\",\n", N);
   printf(" \"pairs\": {\"capsule_capsule\": %d, \"capsule_sphere\": %d, \"sphere_sphere\": %d},\n", ncc, ncs, nss);
+  // the table-driven form computes each capsule direction once per run = the minimal algorithm;
+  // the compiled-in pair list is the same arithmetic after common-subexpression elimination
   printf(" \"validity_S0_flops_per_config\": %.1f,\n", count<false, false>(s0g, N));
+  printf(" \"validity_S0_static_pairs_as_written\": %.1f,\n", count<false, false, PAIRS_STATIC_GROUP>(s0g, N));
   printf(" \"validity_S0_margins_flops_per_config\": %.1f,\n", count<true, false>(s0g, N));
   printf(" \"collision_only_S0_all_pairs_flops_per_config\": %.1f,\n", count<false, true>(s0a, N));
   printf(" \"validity_S1_shelf_flops_per_config\": %.1f,\n", count<false, false>(s1g, N));
