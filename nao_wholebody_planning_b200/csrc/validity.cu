@@ -14,11 +14,20 @@
 // so no tensor cores (BASELINE.json north_star).
 #include <cuda_runtime.h>
 
+#include <algorithm>
+#include <cstdlib>
+
 #include "validity_core.cuh"
 
 namespace nwb {
 
-constexpr int NT = 128;                                 // threads (= configurations) per block
+#ifndef NWB_NT
+#define NWB_NT 128
+#endif
+#ifndef NWB_MINB
+#define NWB_MINB 3
+#endif
+constexpr int NT = NWB_NT;                              // threads (= configurations) per block
 constexpr int kSmemFloats = nwbm::kPointFloats * NT;    // 111 * 128 * 4 B = 56.8 KB
 
 // Point table of one configuration inside the block's shared memory: [slot][thread].
@@ -63,7 +72,7 @@ struct FkVisitor {
 //   MARGINS        also produce {min separation, signed hull distance} (sqrt per pair + gift wrapping)
 //   COLLISION_ONLY skip COM / support (isPathValid way-points)
 template <typename QT, bool MARGINS, bool COLLISION_ONLY, int PAIRS>
-__global__ void __launch_bounds__(NT, 3)
+__global__ void __launch_bounds__(NT, NWB_MINB)
 validity_kernel(const __grid_constant__ ValidityTables tab, const QT* __restrict__ q, int64_t n,
                 uint8_t* __restrict__ valid, uint8_t* __restrict__ reason, float* __restrict__ margins) {
   extern __shared__ float smem[];
@@ -104,6 +113,134 @@ validity_kernel(const __grid_constant__ ValidityTables tab, const QT* __restrict
   }
 }
 
+// ---- persistent variant: one resident CTA per SM slot, input tiles streamed by TMA bulk copies --
+// The batch is cut into tiles of PT configurations (PT*21 contiguous elements).  One elected thread
+// issues cp.async.bulk (UBLKCP) for tile k+1 into the other half of a double buffer while all
+// threads evaluate tile k; completion is signalled through an mbarrier (complete_tx).  This removes
+// the load->barrier->compute bubble at the start of every block of the plain kernel.
+#ifndef NWB_PT
+#define NWB_PT 256
+#endif
+#ifndef NWB_PMINB
+#define NWB_PMINB 2
+#endif
+constexpr int PT = NWB_PT;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <typename QT, bool MARGINS, bool COLLISION_ONLY, int PAIRS>
+__global__ void __launch_bounds__(PT, NWB_PMINB)
+validity_persistent_kernel(const __grid_constant__ ValidityTables tab, const QT* __restrict__ q, int64_t n,
+                           uint8_t* __restrict__ valid, uint8_t* __restrict__ reason, float* __restrict__ margins) {
+  static_assert(PAIRS != PAIRS_TABLE, "the persistent kernel keeps the point table in registers");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr uint32_t kTileBytes = PT * NWB_NJ * sizeof(QT);
+  QT* buf[2] = {reinterpret_cast<QT*>(smem_raw), reinterpret_cast<QT*>(smem_raw + kTileBytes)};
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + 2 * kTileBytes);
+  const int tid = threadIdx.x;
+  const int64_t full_tiles = n / PT;
+
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  int64_t tile = blockIdx.x;
+  if (tid == 0 && tile < full_tiles) {
+    mbar_expect_tx(&bar[0], kTileBytes);
+    bulk_g2s(buf[0], q + tile * PT * NWB_NJ, kTileBytes, &bar[0]);
+  }
+  uint32_t phase[2] = {0u, 0u};
+  const int64_t tiles = (n + PT - 1) / PT;           // the last tile may be ragged (< PT rows)
+  for (int it = 0; tile < tiles; tile += gridDim.x, ++it) {
+    const int b = it & 1;
+    const int64_t next = tile + gridDim.x;
+    if (tid == 0 && next < full_tiles) {               // buffer b^1 was drained before the last barrier
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(&bar[b ^ 1], kTileBytes);
+      bulk_g2s(buf[b ^ 1], q + next * PT * NWB_NJ, kTileBytes, &bar[b ^ 1]);
+    }
+    const int64_t i = tile * PT + tid;
+    float qv[NWB_NJ];
+    if (tile < full_tiles) {                           // block-uniform
+      mbar_wait(&bar[b], phase[b]);
+      phase[b] ^= 1u;
+#pragma unroll
+      for (int j = 0; j < NWB_NJ; ++j) qv[j] = (float)buf[b][tid * NWB_NJ + j];
+    } else {                                           // ragged tail: straight from global memory
+      const int64_t row = i < n ? i : n - 1;
+#pragma unroll
+      for (int j = 0; j < NWB_NJ; ++j) qv[j] = (float)q[row * NWB_NJ + j];
+    }
+    __syncthreads();                                   // everyone has its row: buffer b may be refilled
+
+    float min_sep = 0.f, hull_margin = 0.f;
+    RegStore st;
+    const ValidityResult res = evaluate_config<float, RegStore, MARGINS, COLLISION_ONLY, PAIRS>(tab, qv, st, &min_sep, &hull_margin);
+    if (i < n) {
+      const unsigned rs = (res.hit ? NWB_REASON_COLLISION : 0u) | (res.stable ? 0u : NWB_REASON_UNSTABLE);
+      if (valid) valid[i] = COLLISION_ONLY ? (uint8_t)res.hit : (uint8_t)(rs == 0u);
+      if (reason) reason[i] = (uint8_t)rs;
+      if constexpr (MARGINS) {
+        if (margins) {
+          if constexpr (COLLISION_ONLY) margins[i] = min_sep;
+          else { margins[2 * i] = min_sep; margins[2 * i + 1] = hull_margin; }
+        }
+      }
+    }
+  }
+}
+
+static int g_sm_count = 0;
+
+template <typename QT, bool MARGINS, bool COLLISION_ONLY, int PAIRS>
+static cudaError_t launch_persistent(const ValidityTables& tab, const void* q, int64_t n, uint8_t* valid, uint8_t* reason,
+                                     float* margins, cudaStream_t stream) {
+  auto kern = validity_persistent_kernel<QT, MARGINS, COLLISION_ONLY, PAIRS>;
+  static int blocks_per_sm = 0;   // per instantiation
+  const size_t smem = 2 * (size_t)PT * NWB_NJ * sizeof(QT) + 16;
+  if (!blocks_per_sm) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, PT, smem);
+    if (e != cudaSuccess) return e;
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
+    if (!g_sm_count) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    }
+  }
+  const int64_t tiles = (n + PT - 1) / PT;
+  const int64_t grid = std::min<int64_t>(tiles, (int64_t)g_sm_count * blocks_per_sm);
+  kern<<<(unsigned)grid, PT, smem, stream>>>(tab, (const QT*)q, n, valid, reason, margins);
+  return cudaGetLastError();
+}
+
 template <typename QT, bool MARGINS, bool COLLISION_ONLY, int PAIRS>
 static cudaError_t launch_one(const ValidityTables& tab, const void* q, int64_t n, uint8_t* valid, uint8_t* reason,
                               float* margins, cudaStream_t stream) {
@@ -124,6 +261,10 @@ template <typename QT, bool COLLISION_ONLY>
 static cudaError_t launch_qt(const ValidityTables& tab, const void* q, int64_t n, uint8_t* valid, uint8_t* reason,
                              float* margins, bool static_pairs, cudaStream_t stream) {
   constexpr int kStatic = COLLISION_ONLY ? PAIRS_STATIC_ALL : PAIRS_STATIC_GROUP;
+  // TMA bulk copies need 16-byte aligned sources; every tile offset is a multiple of 16 bytes
+  if (static_pairs && (reinterpret_cast<uintptr_t>(q) & 15) == 0 && !getenv("NWB_NO_PERSISTENT"))
+    return margins ? launch_persistent<QT, true, COLLISION_ONLY, kStatic>(tab, q, n, valid, reason, margins, stream)
+                   : launch_persistent<QT, false, COLLISION_ONLY, kStatic>(tab, q, n, valid, reason, margins, stream);
   if (static_pairs)
     return margins ? launch_one<QT, true, COLLISION_ONLY, kStatic>(tab, q, n, valid, reason, margins, stream)
                    : launch_one<QT, false, COLLISION_ONLY, kStatic>(tab, q, n, valid, reason, margins, stream);
