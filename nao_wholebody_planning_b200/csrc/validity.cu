@@ -91,7 +91,7 @@ validity_kernel(const __grid_constant__ ValidityTables tab, const QT* __restrict
   if constexpr (PAIRS == PAIRS_TABLE) __syncthreads();   // staging area is reused as the point table below
 
   float min_sep = 0.f, hull_margin = 0.f;
-  ValidityResult res;
+  ValidityResult<float> res;
   if constexpr (PAIRS == PAIRS_TABLE) {
     SmemStore st{smem + tid};
     res = evaluate_config<float, SmemStore, MARGINS, COLLISION_ONLY, PAIRS>(tab, qv, st, &min_sep, &hull_margin);
@@ -200,7 +200,7 @@ validity_persistent_kernel(const __grid_constant__ ValidityTables tab, const QT*
 
     float min_sep = 0.f, hull_margin = 0.f;
     RegStore st;
-    const ValidityResult res = evaluate_config<float, RegStore, MARGINS, COLLISION_ONLY, PAIRS>(tab, qv, st, &min_sep, &hull_margin);
+    const ValidityResult<float> res = evaluate_config<float, RegStore, MARGINS, COLLISION_ONLY, PAIRS>(tab, qv, st, &min_sep, &hull_margin);
     if (i < n) {
       const unsigned rs = (res.hit ? NWB_REASON_COLLISION : 0u) | (res.stable ? 0u : NWB_REASON_UNSTABLE);
       if (valid) valid[i] = COLLISION_ONLY ? (uint8_t)res.hit : (uint8_t)(rs == 0u);
@@ -214,6 +214,90 @@ validity_persistent_kernel(const __grid_constant__ ValidityTables tab, const QT*
     }
   }
 }
+
+#ifdef NWB_ENABLE_PACKED   // measured slower than the scalar persistent kernel as compiled (experiments)
+// ---- packed variant: TWO configurations per thread on FFMA2/FADD2/FMUL2 ------------------------
+// Every arithmetic value is a float2 (lane x = configuration 2t, lane y = 2t+1) issued as one packed
+// instruction, so the FMA pipe does the same work in half the dispatch slots and the freed slots
+// carry the compare / select / clamp instructions (ALU pipe, two dispatch cycles each on sm_100).
+// The point table holds float2 per slot in shared memory: [slot][thread], 8-byte accesses,
+// conflict-free.  No margins (the gift-wrapping hull has a data-dependent trip count).
+#ifndef NWB_P2T
+#define NWB_P2T 128            // threads per block = 256 configurations per tile
+#endif
+#ifndef NWB_P2MINB
+#define NWB_P2MINB 2
+#endif
+constexpr int P2T = NWB_P2T;
+
+struct SmemStore2 {
+  float2* base;   // shared memory, already offset by threadIdx.x
+  __device__ __forceinline__ void put(int slot, F2 v) { base[slot * P2T] = v.v; }
+  __device__ __forceinline__ F2 get(int slot) const { return f2(base[slot * P2T]); }
+};
+
+template <typename QT, bool COLLISION_ONLY, int PAIRS>
+__global__ void __launch_bounds__(P2T, NWB_P2MINB)
+validity_packed_kernel(const __grid_constant__ ValidityTables tab, const QT* __restrict__ q, int64_t n,
+                       uint8_t* __restrict__ valid, uint8_t* __restrict__ reason) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* stage = reinterpret_cast<float*>(smem_raw);           // [2*P2T][21] floats, aliased by the point table
+  float2* table = reinterpret_cast<float2*>(smem_raw);         // [kPointFloats][P2T] float2
+  const int tid = threadIdx.x;
+  constexpr int TILE = 2 * P2T;
+  const int64_t base = (int64_t)blockIdx.x * TILE;
+  const int nvalid = (int)min((int64_t)TILE, n - base);
+
+  for (int e = tid; e < nvalid * NWB_NJ; e += P2T) stage[e] = (float)q[base * NWB_NJ + e];
+  __syncthreads();
+  // thread t owns rows 2t and 2t+1 (adjacent outputs -> one 2-byte store); idle lanes reuse row 0
+  const int r0 = (2 * tid < nvalid) ? 2 * tid : 0, r1 = (2 * tid + 1 < nvalid) ? 2 * tid + 1 : 0;
+  F2 qv[NWB_NJ];
+#pragma unroll
+  for (int j = 0; j < NWB_NJ; ++j) qv[j] = F2(stage[r0 * NWB_NJ + j], stage[r1 * NWB_NJ + j]);
+  __syncthreads();                                             // the staging area becomes the point table
+
+  SmemStore2 st{table + tid};
+  const ValidityResult<F2> res = evaluate_config<F2, SmemStore2, false, COLLISION_ONLY, PAIRS>(tab, qv, st, nullptr, nullptr);
+
+  const int64_t i0 = base + 2 * tid;
+  const unsigned rs0 = (res.hit.x ? NWB_REASON_COLLISION : 0u) | (res.stable.x ? 0u : NWB_REASON_UNSTABLE);
+  const unsigned rs1 = (res.hit.y ? NWB_REASON_COLLISION : 0u) | (res.stable.y ? 0u : NWB_REASON_UNSTABLE);
+  const unsigned v0 = COLLISION_ONLY ? (unsigned)res.hit.x : (unsigned)(rs0 == 0u);
+  const unsigned v1 = COLLISION_ONLY ? (unsigned)res.hit.y : (unsigned)(rs1 == 0u);
+  if (i0 + 1 < n && ((reinterpret_cast<uintptr_t>(valid) | reinterpret_cast<uintptr_t>(reason)) & 1) == 0) {
+    if (valid) *reinterpret_cast<uint16_t*>(valid + i0) = (uint16_t)(v0 | (v1 << 8));
+    if (reason) *reinterpret_cast<uint16_t*>(reason + i0) = (uint16_t)(rs0 | (rs1 << 8));
+  } else {
+    if (i0 < n) {
+      if (valid) valid[i0] = (uint8_t)v0;
+      if (reason) reason[i0] = (uint8_t)rs0;
+    }
+    if (i0 + 1 < n) {
+      if (valid) valid[i0 + 1] = (uint8_t)v1;
+      if (reason) reason[i0 + 1] = (uint8_t)rs1;
+    }
+  }
+}
+
+template <typename QT, bool COLLISION_ONLY, int PAIRS>
+static cudaError_t launch_packed(const ValidityTables& tab, const void* q, int64_t n, uint8_t* valid, uint8_t* reason,
+                                 cudaStream_t stream) {
+  auto kern = validity_packed_kernel<QT, COLLISION_ONLY, PAIRS>;
+  static bool configured = false;
+  const size_t smem = (size_t)nwbm::kPointFloats * P2T * sizeof(float2);
+  static_assert((size_t)nwbm::kPointFloats * sizeof(float2) >= 2 * NWB_NJ * sizeof(float), "staging must fit in the table");
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int64_t blocks = (n + 2 * P2T - 1) / (2 * P2T);
+  kern<<<(unsigned)blocks, P2T, smem, stream>>>(tab, (const QT*)q, n, valid, reason);
+  return cudaGetLastError();
+}
+
+#endif  // NWB_ENABLE_PACKED
 
 static int g_sm_count = 0;
 
@@ -261,6 +345,10 @@ template <typename QT, bool COLLISION_ONLY>
 static cudaError_t launch_qt(const ValidityTables& tab, const void* q, int64_t n, uint8_t* valid, uint8_t* reason,
                              float* margins, bool static_pairs, cudaStream_t stream) {
   constexpr int kStatic = COLLISION_ONLY ? PAIRS_STATIC_ALL : PAIRS_STATIC_GROUP;
+#ifdef NWB_ENABLE_PACKED
+  if (static_pairs && !margins && getenv("NWB_PACKED"))
+    return launch_packed<QT, COLLISION_ONLY, kStatic>(tab, q, n, valid, reason, stream);
+#endif
   // TMA bulk copies need 16-byte aligned sources; every tile offset is a multiple of 16 bytes
   if (static_pairs && (reinterpret_cast<uintptr_t>(q) & 15) == 0 && !getenv("NWB_NO_PERSISTENT"))
     return margins ? launch_persistent<QT, true, COLLISION_ONLY, kStatic>(tab, q, n, valid, reason, margins, stream)

@@ -1,9 +1,11 @@
 // validity_core.cuh - per-configuration validity evaluation, generic over the scalar type T and the
 // storage policy of the proxy point table.
 //
-// On the device T = float and the point table lives in shared memory ([slot][thread]); on the host
-// tools/count_flops.cu instantiates the very same code with a flop-counting scalar to freeze the
-// algorithmic flops per configuration used by the roofline (profiles/roofline.json).
+// Device instantiations: T = float (one configuration per thread, point table in registers or
+// shared memory) and T = F2 (two configurations per thread on the packed FP32 instructions, point
+// table in shared memory).  Host instantiation: tools/count_flops.cpp runs the very same code with
+// a flop-counting scalar to freeze the algorithmic flops per configuration used by the roofline
+// (profiles/roofline.json).
 #pragma once
 #include "nwb_internal.h"
 #include "nwb_math.cuh"
@@ -17,17 +19,17 @@ struct ValidityVisitor {
   Store& st;
   T comx, comy;
   XF<T> lsole;
-  NWB_HD explicit ValidityVisitor(Store& s) : st(s), comx(T(0)), comy(T(0)) {}
+  NWB_HD explicit ValidityVisitor(Store& s) : st(s), comx(T(0.f)), comy(T(0.f)) {}
 
   template <int ID>
   NWB_HD void frame(const XF<T>& F) {
     using M = nwbm::FrameMass<ID>;
     if constexpr (M::has && WANT_COM) {
-      comx += T(float(M::w)) * F.p[0];
-      comy += T(float(M::w)) * F.p[1];
-      if constexpr (M::wx != 0) { comx += T(float(M::wx)) * F.r[0]; comy += T(float(M::wx)) * F.r[3]; }
-      if constexpr (M::wy != 0) { comx += T(float(M::wy)) * F.r[1]; comy += T(float(M::wy)) * F.r[4]; }
-      if constexpr (M::wz != 0) { comx += T(float(M::wz)) * F.r[2]; comy += T(float(M::wz)) * F.r[5]; }
+      comx = nwb_fma(T(float(M::w)), F.p[0], comx);
+      comy = nwb_fma(T(float(M::w)), F.p[1], comy);
+      if constexpr (M::wx != 0) { comx = nwb_fma(T(float(M::wx)), F.r[0], comx); comy = nwb_fma(T(float(M::wx)), F.r[3], comy); }
+      if constexpr (M::wy != 0) { comx = nwb_fma(T(float(M::wy)), F.r[1], comx); comy = nwb_fma(T(float(M::wy)), F.r[4], comy); }
+      if constexpr (M::wz != 0) { comx = nwb_fma(T(float(M::wz)), F.r[2], comx); comy = nwb_fma(T(float(M::wz)), F.r[5], comy); }
     }
     using P = nwbm::FrameProxy<ID>;
     if constexpr (P::has) {
@@ -40,9 +42,9 @@ struct ValidityVisitor {
   template <int SLOT, bool UX, bool UY, bool UZ>
   NWB_HD void put(const XF<T>& F, T x, T y, T z) {
     T wx = F.p[0], wy = F.p[1], wz = F.p[2];
-    if constexpr (UX) { wx += F.r[0] * x; wy += F.r[3] * x; wz += F.r[6] * x; }
-    if constexpr (UY) { wx += F.r[1] * y; wy += F.r[4] * y; wz += F.r[7] * y; }
-    if constexpr (UZ) { wx += F.r[2] * z; wy += F.r[5] * z; wz += F.r[8] * z; }
+    if constexpr (UX) { wx = nwb_fma(F.r[0], x, wx); wy = nwb_fma(F.r[3], x, wy); wz = nwb_fma(F.r[6], x, wz); }
+    if constexpr (UY) { wx = nwb_fma(F.r[1], y, wx); wy = nwb_fma(F.r[4], y, wy); wz = nwb_fma(F.r[7], y, wz); }
+    if constexpr (UZ) { wx = nwb_fma(F.r[2], z, wx); wy = nwb_fma(F.r[5], z, wy); wz = nwb_fma(F.r[8], z, wz); }
     st.put(SLOT + 0, wx);
     st.put(SLOT + 1, wy);
     st.put(SLOT + 2, wz);
@@ -64,65 +66,68 @@ template <class T>
 NWB_HD T box_excess(T x, T h) { return x - nwb_min(nwb_max(x, -h), h); }
 template <class T>
 NWB_HD T box_phi(const T* A, const T* D, const T* H, T t) {
-  T s = T(0);
+  T s = T(0.f);
 #pragma unroll
-  for (int k = 0; k < 3; ++k) s += box_excess(A[k] + t * D[k], H[k]) * D[k];
+  for (int k = 0; k < 3; ++k) s = nwb_fma(box_excess(nwb_fma(t, D[k], A[k]), H[k]), D[k], s);
   return s;
 }
 template <class T>
 NWB_HD T box_f(const T* A, const T* D, const T* H, T t) {
-  T s = T(0);
+  T s = T(0.f);
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    T e = box_excess(A[k] + t * D[k], H[k]);
-    s += e * e;
+    T e = box_excess(nwb_fma(t, D[k], A[k]), H[k]);
+    s = nwb_fma(e, e, s);
   }
   return s;
 }
 template <class T>
 NWB_HD T seg_box_dist2(const T* A, const T* D, const T* H) {
-  T lo = T(0), hi = T(1);
-  const T p0 = box_phi(A, D, H, T(0)), p1 = box_phi(A, D, H, T(1));
+  T lo = T(0.f), hi = T(1.f);
+  const T p0 = box_phi(A, D, H, T(0.f)), p1 = box_phi(A, D, H, T(1.f));
   T plo = p0, phi = p1;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    T inv = nwb_sel(D[k] != T(0), T(1) / D[k], T(0));
+    T inv = nwb_sel(D[k] != T(0.f), T(1.f) / D[k], T(0.f));
 #pragma unroll
     for (int sg = 0; sg < 2; ++sg) {
       T face = sg ? H[k] : -H[k];
-      T t = nwb_sat((face - A[k]) * inv);
+      T t = nwb_mul_sat(face - A[k], inv);
       T p = box_phi(A, D, H, t);
-      bool below = (p <= T(0)) && (t >= lo);
-      bool above = (p >= T(0)) && (t <= hi);
+      auto below = nwb_and(p <= T(0.f), t >= lo);
+      auto above = nwb_and(p >= T(0.f), t <= hi);
       lo = nwb_sel(below, t, lo); plo = nwb_sel(below, p, plo);
       hi = nwb_sel(above, t, hi); phi = nwb_sel(above, p, phi);
     }
   }
   T den = phi - plo;
-  T t = nwb_sel(den > T(0), lo + (hi - lo) * nwb_sat(-plo / den), lo);
-  t = nwb_sel(p0 >= T(0), T(0), t);     // already moving away at the start
-  t = nwb_sel(p1 <= T(0), T(1), t);     // still approaching at the end
+  T t = nwb_sel(den > T(0.f), nwb_fma(hi - lo, nwb_sat(nwb_div_fast(-plo, den)), lo), lo);
+  t = nwb_sel(p0 >= T(0.f), T(0.f), t);     // already moving away at the start
+  t = nwb_sel(p1 <= T(0.f), T(1.f), t);     // still approaching at the end
   return box_f(A, D, H, t);
 }
 
+template <class T>
 struct ValidityResult {
-  bool hit;        // some enabled pair / scene box in contact
-  bool stable;
+  typename mask_of<T>::type hit;      // some enabled pair / scene box in contact
+  typename mask_of<T>::type stable;
 };
 
 // Pair-set selector: the default SRDF reading is compiled in (every slot, length and radius an
 // immediate, loops fully unrolled); any other reading walks the runtime tables.
 enum PairMode { PAIRS_TABLE = 0, PAIRS_STATIC_GROUP = 1, PAIRS_STATIC_ALL = 2 };
 
-// Evaluate one configuration.  q = 21 joint values.  MARGINS: also min separation / hull distance.
+// Evaluate one configuration (or one lane-pair of configurations).  q = 21 joint values.
+// MARGINS: also min separation / hull distance (one-lane scalars only).
 template <class T, class Store, bool MARGINS, bool COLLISION_ONLY, int PAIRS = PAIRS_TABLE>
-NWB_HD ValidityResult evaluate_config(const ValidityTables& tab, const T* q, Store& st, T* min_sep_out, T* hull_out) {
+NWB_HD ValidityResult<T> evaluate_config(const ValidityTables& tab, const T* q, Store& st, T* min_sep_out, T* hull_out) {
+  using M = typename mask_of<T>::type;
   ValidityVisitor<T, Store, !COLLISION_ONLY> V(st);
   { NWB_MODEL_FK_WALK(T, XF<T>, q, V) }
 
   // ---- static stability: projected COM strictly inside hull(right foot U left foot) ------------
-  bool stable = true;
-  T hull_margin = T(0);
+  M stable = nwb_mask<M>(true);
+  T hull_margin = T(0.f);
   if constexpr (!COLLISION_ONLY) {
     const XF<T>& L = V.lsole;
     if constexpr (!MARGINS) {
@@ -130,12 +135,12 @@ NWB_HD ValidityResult evaluate_config(const ValidityTables& tab, const T* q, Sto
       w.init(T(tab.foot_right[0][0]) - V.comx, T(tab.foot_right[0][1]) - V.comy);
 #pragma unroll
       for (int k = 1; k < nwbm::kFootN; ++k) w.add(T(tab.foot_right[k][0]) - V.comx, T(tab.foot_right[k][1]) - V.comy);
+      // left-foot vertices relative to the COM: (L.p - com) + L.R * v
+      const T ox = L.p[0] - V.comx, oy = L.p[1] - V.comy;
 #pragma unroll
       for (int k = 0; k < nwbm::kFootN; ++k) {
         T x = T(tab.foot_left[k][0]), y = T(tab.foot_left[k][1]);
-        T wx = L.p[0] + L.r[0] * x + L.r[1] * y;
-        T wy = L.p[1] + L.r[3] * x + L.r[4] * y;
-        w.add(wx - V.comx, wy - V.comy);
+        w.add(nwb_fma(L.r[1], y, nwb_fma(L.r[0], x, ox)), nwb_fma(L.r[4], y, nwb_fma(L.r[3], x, oy)));
       }
       stable = w.surrounded;
     } else {
@@ -145,24 +150,24 @@ NWB_HD ValidityResult evaluate_config(const ValidityTables& tab, const T* q, Sto
         px[k] = T(tab.foot_right[k][0]);
         py[k] = T(tab.foot_right[k][1]);
         T x = T(tab.foot_left[k][0]), y = T(tab.foot_left[k][1]);
-        px[nwbm::kFootN + k] = L.p[0] + L.r[0] * x + L.r[1] * y;
-        py[nwbm::kFootN + k] = L.p[1] + L.r[3] * x + L.r[4] * y;
+        px[nwbm::kFootN + k] = nwb_fma(L.r[1], y, nwb_fma(L.r[0], x, L.p[0]));
+        py[nwbm::kFootN + k] = nwb_fma(L.r[4], y, nwb_fma(L.r[3], x, L.p[1]));
       }
       hull_margin = hull_signed_distance<T, 2 * nwbm::kFootN>(px, py, V.comx, V.comy);
-      stable = hull_margin > T(0);
+      stable = (hull_margin > T(0.f));
     }
   }
 
-  // ---- self collision over the enabled-pair runs -------------------------------------------------
-  bool hit = false;
+  // ---- self collision over the enabled pairs -----------------------------------------------------
+  M hit = nwb_mask<M>(false);
   T min_sep = T(1e30f);
   auto account = [&](T d2, T rsum) {
     if constexpr (MARGINS) min_sep = nwb_min(min_sep, nwb_sqrt(d2) - rsum);
-    else hit = hit || (d2 < rsum * rsum);
+    else hit = nwb_or(hit, d2 < rsum * rsum);
   };
   auto account2 = [&](T d2, T rsum, T rsum2) {   // (rA+rB)^2 known at compile time
     if constexpr (MARGINS) min_sep = nwb_min(min_sep, nwb_sqrt(d2) - rsum);
-    else hit = hit || (d2 < rsum2);
+    else hit = nwb_or(hit, d2 < rsum2);
   };
   (void)account2;
   if constexpr (PAIRS == PAIRS_TABLE) {
@@ -175,7 +180,7 @@ NWB_HD ValidityResult evaluate_config(const ValidityTables& tab, const T* q, Sto
       d1[0] = qa[0] - pa[0]; d1[1] = qa[1] - pa[1]; d1[2] = qa[2] - pa[2];
       const int cnt = run.count, first = run.first;
       const T a = T(run.a), inv_a = T(run.inv_a);
-  #pragma unroll 2
+#pragma unroll 2
       for (int k = 0; k < cnt; ++k) {
         const PairEntry& pe = tab.entries[first + k];
         T pb[3], qb[3], d2[3];
@@ -193,7 +198,7 @@ NWB_HD ValidityResult evaluate_config(const ValidityTables& tab, const T* q, Sto
       d1[0] = qa[0] - pa[0]; d1[1] = qa[1] - pa[1]; d1[2] = qa[2] - pa[2];
       const int cnt = run.count, first = run.first;
       const T inv_a = T(run.inv_a);
-  #pragma unroll 2
+#pragma unroll 2
       for (int k = 0; k < cnt; ++k) {
         const PairEntry& pe = tab.entries[first + k];
         T pb[3];
@@ -206,7 +211,7 @@ NWB_HD ValidityResult evaluate_config(const ValidityTables& tab, const T* q, Sto
       T pa[3];
       load3(st, run.off_a, pa);
       const int cnt = run.count, first = run.first;
-  #pragma unroll 2
+#pragma unroll 2
       for (int k = 0; k < cnt; ++k) {
         const PairEntry& pe = tab.entries[first + k];
         T pb[3];
@@ -258,20 +263,20 @@ NWB_HD ValidityResult evaluate_config(const ValidityTables& tab, const T* q, Sto
       T pa[3], A[3];
       load3(st, off, pa);
       T rx = pa[0] - T(bx.c[0]), ry = pa[1] - T(bx.c[1]), rz = pa[2] - T(bx.c[2]);
-      A[0] = T(bx.r[0]) * rx + T(bx.r[3]) * ry + T(bx.r[6]) * rz;      // R^T (a - c)
-      A[1] = T(bx.r[1]) * rx + T(bx.r[4]) * ry + T(bx.r[7]) * rz;
-      A[2] = T(bx.r[2]) * rx + T(bx.r[5]) * ry + T(bx.r[8]) * rz;
+      A[0] = nwb_fma(T(bx.r[6]), rz, nwb_fma(T(bx.r[3]), ry, T(bx.r[0]) * rx));      // R^T (a - c)
+      A[1] = nwb_fma(T(bx.r[7]), rz, nwb_fma(T(bx.r[4]), ry, T(bx.r[1]) * rx));
+      A[2] = nwb_fma(T(bx.r[8]), rz, nwb_fma(T(bx.r[5]), ry, T(bx.r[2]) * rx));
       T d2;
       if (is_sphere) {                                                 // table / compile-time: warp-uniform
         T ex = box_excess(A[0], H[0]), ey = box_excess(A[1], H[1]), ez = box_excess(A[2], H[2]);
-        d2 = ex * ex + ey * ey + ez * ez;
+        d2 = nwb_fma(ez, ez, nwb_fma(ey, ey, ex * ex));
       } else {
         T qa[3], D[3];
         load3(st, off + 3, qa);
         T dx = qa[0] - pa[0], dy = qa[1] - pa[1], dz = qa[2] - pa[2];
-        D[0] = T(bx.r[0]) * dx + T(bx.r[3]) * dy + T(bx.r[6]) * dz;
-        D[1] = T(bx.r[1]) * dx + T(bx.r[4]) * dy + T(bx.r[7]) * dz;
-        D[2] = T(bx.r[2]) * dx + T(bx.r[5]) * dy + T(bx.r[8]) * dz;
+        D[0] = nwb_fma(T(bx.r[6]), dz, nwb_fma(T(bx.r[3]), dy, T(bx.r[0]) * dx));
+        D[1] = nwb_fma(T(bx.r[7]), dz, nwb_fma(T(bx.r[4]), dy, T(bx.r[1]) * dx));
+        D[2] = nwb_fma(T(bx.r[8]), dz, nwb_fma(T(bx.r[5]), dy, T(bx.r[2]) * dx));
         d2 = seg_box_dist2(A, D, H);
       }
       account(d2, radius);
@@ -289,11 +294,11 @@ NWB_HD ValidityResult evaluate_config(const ValidityTables& tab, const T* q, Sto
     }
   }
   if constexpr (MARGINS) {
-    hit = min_sep < T(0);
+    hit = (min_sep < T(0.f));
     if (min_sep_out) *min_sep_out = min_sep;
     if (hull_out) *hull_out = hull_margin;
   }
-  ValidityResult res;
+  ValidityResult<T> res;
   res.hit = hit;
   res.stable = stable;
   return res;

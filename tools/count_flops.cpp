@@ -39,7 +39,9 @@ inline Counted nwb_sat(Counted x) { ++Counted::flops; return Counted(x.v < 0 ? 0
 inline Counted nwb_sqrt(Counted x) { ++Counted::flops; return Counted(std::sqrt(x.v)); }
 inline Counted nwb_min(Counted a, Counted b) { ++Counted::flops; return Counted(std::fmin(a.v, b.v)); }
 inline Counted nwb_max(Counted a, Counted b) { ++Counted::flops; return Counted(std::fmax(a.v, b.v)); }
-inline Counted nwb_abs(Counted a) { return Counted(std::fabs(a.v)); }
+inline Counted nwb_fma(Counted a, Counted b, Counted c) { Counted::flops += 2; return Counted(a.v * b.v + c.v); }
+inline Counted nwb_mul_sat(Counted a, Counted b) { Counted::flops += 2; double x = a.v * b.v; return Counted(x < 0 ? 0.0 : (x > 1 ? 1.0 : x)); }
+inline Counted nwb_sel(bool c, Counted a, Counted b) { return c ? a : b; }
 inline Counted nwb_div_fast(Counted a, Counted b) { ++Counted::flops; return Counted(a.v / b.v); }
 }  // namespace nwb
 
