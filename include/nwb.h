@@ -153,6 +153,78 @@ NWB_API int nwb_fk_batch(nwb_ctx* ctx, const double* q, int64_t n, double* link_
 /* Name of link frame `i` (0 <= i < NWB_NFRAMES), e.g. "l_sole"; NULL if out of range. */
 NWB_API const char* nwb_frame_name(int i);
 
+/* ---- tree + nearest neighbour ------------------------------------------------------------------
+ * Device-resident replacement of struct Node / struct Tree (RPh:30-46).  A node is its configuration
+ * plus predecessor_index; its index is its insertion position (RRT_Planner::addConfigtoTree, RP:749-783).
+ * The library owns the nwb_tree; it belongs to the context it was created on. */
+typedef struct nwb_tree nwb_tree;
+NWB_API int nwb_tree_create(nwb_ctx* ctx, int64_t capacity_hint, nwb_tree** out);
+NWB_API void nwb_tree_destroy(nwb_tree* tree);
+NWB_API int nwb_tree_clear(nwb_tree* tree);                      /* RP:1110-1114: nodes.clear()            */
+NWB_API int64_t nwb_tree_size(const nwb_tree* tree);             /* Tree::num_nodes                        */
+/* Append n nodes (q [n][21], predecessor [n] or NULL = -1); indices continue from nwb_tree_size(). */
+NWB_API int nwb_tree_add(nwb_tree* tree, const double* q, const int32_t* predecessor, int64_t n);
+NWB_API int nwb_tree_add_dev(nwb_tree* tree, const double* q_dev, const int32_t* predecessor_dev, int64_t n);
+/* Read back nodes [first, first+n): configurations and/or predecessors (either may be NULL). */
+NWB_API int nwb_tree_get(nwb_tree* tree, int64_t first, int64_t n, double* q_out, int32_t* predecessor_out);
+/* RRT_Planner::findNearestNeighbour (RP:336-419) for nq query configurations against one tree:
+ * idx[k] = argmin_i sqrt(sum_j (q_k[j] - node_i[j])^2), first strict minimum (lowest index on ties),
+ * -1 if no node is closer than 10000.0 (RP:347); dist[k] = that distance (may be NULL).
+ * Exact: candidates are re-evaluated in double with the reference's rounding sequence. */
+NWB_API int nwb_nearest_neighbour_batch(nwb_tree* tree, const double* q, int64_t nq, int32_t* idx, double* dist);
+NWB_API int nwb_nearest_neighbour_batch_dev(nwb_tree* tree, const double* q_dev, int64_t nq, int32_t* idx_dev,
+                                            double* dist_dev);
+
+/* ---- local planner operators ---------------------------------------------------------------------
+ * weights: the 21 joint weights of RRT_Planner::setJointWeights (RP:307-311), NULL = all 1.0 (RP:76-78).
+ * step:    max_step_size of solveQuery (planner_step_factor, 0.1). */
+
+/* generate_q_new (RP:424-494) followed by enforce_DS_Constraints (RP:498-593), combined the way
+ * extendTree does (RP:807-818): status[i] = NWB_TRAPPED if the projection failed (joint limits or
+ * left-leg IK), else NWB_ADVANCED if the left leg was re-solved, else generate_q_new's status.
+ * q_out[i] is written only when status[i] != NWB_TRAPPED.  ds_status (may be NULL) = the
+ * enforce_DS_Constraints result on its own. */
+NWB_API int nwb_steer_project_batch(nwb_ctx* ctx, const double* q_near, const double* q_target, int64_t n,
+                                    const double* weights, double step, double* q_out, int32_t* status,
+                                    int32_t* ds_status);
+
+/* The connectTree walk (RP:926-1031) for n_edges independent edges: from q_start[e] step towards
+ * q_connect[e] (steer -> project -> isConfigValid -> append, each step starting from the projected
+ * previous node, RP:1004) until NWB_REACHED or NWB_TRAPPED.  nodes_out [n_edges][max_steps][21]
+ * receives the appended nodes, n_added[e] their count; status[e] = -1 if max_steps ran out first. */
+NWB_API int nwb_connect_batch(nwb_ctx* ctx, const double* q_start, const double* q_connect, int64_t n_edges,
+                              const double* weights, double step, int32_t max_steps, double* nodes_out,
+                              int32_t* n_added, int32_t* status);
+
+/* interpolateWaypoints (RP:1677-1774: k intermediate + 2 end states) + PlanningScene::isPathValid
+ * (RP:1876,1905: every way-point collision-free over the whole robot, no stability predicate) for
+ * n_edges candidate edges qa[e] -> qb[e].  ok[e] = 1 if valid; first_bad[e] (may be NULL) = index of
+ * the first colliding way-point or -1. */
+NWB_API int nwb_is_path_valid_batch(nwb_ctx* ctx, const double* qa, const double* qb, int64_t n_edges, int32_t k,
+                                    uint8_t* ok, int32_t* first_bad);
+
+/* StableConfigGenerator::sample_stable_configs, database branch (SCG:278-480), for the sample indices
+ * [first, first + count): uniform sample within the joint limits (LHipYawPitch = 0), hip FK, left-leg
+ * IK (NCK:71-197), validity; kept rows (quirk C1 selects which) are returned in ascending sample
+ * index.  The random stream is counter based (Philox4x32-10 keyed by `seed`, counter = sample index),
+ * so the accepted set does not depend on how the index range is split over calls or GPUs.
+ *   rows_out [cap][21], index_out [cap] (may be NULL), *n_out = number accepted (may exceed cap: then
+ *   only the first cap rows in index order ... are returned and the call reports NWB_E_NOMEM),
+ *   stage_out [count] (may be NULL): 0 = IK failed, 1 = infeasible, 2 = feasible. */
+NWB_API int nwb_sample_stable_configs(nwb_ctx* ctx, uint64_t seed, uint64_t first, int64_t count, int32_t max_ik_iter,
+                                      double* rows_out, int64_t cap, int64_t* n_out, uint64_t* index_out,
+                                      uint8_t* stage_out);
+/* Device-resident form for throughput runs: rows in arrival order (not sorted), *n_out_dev is an
+ * unsigned 64-bit counter the caller zeroes. */
+NWB_API int nwb_sample_stable_configs_dev(nwb_ctx* ctx, uint64_t seed, uint64_t first, int64_t count,
+                                          int32_t max_ik_iter, double* rows_dev, uint64_t* index_dev, int64_t cap,
+                                          unsigned long long* n_out_dev, uint8_t* stage_dev);
+NWB_API int nwb_is_path_valid_batch_dev(nwb_ctx* ctx, const double* qa_dev, const double* qb_dev, int64_t n_edges,
+                                        int32_t k, uint8_t* ok_dev, int32_t* first_bad_dev);
+NWB_API int nwb_steer_project_batch_dev(nwb_ctx* ctx, const double* q_near_dev, const double* q_target_dev, int64_t n,
+                                        const double* weights, double step, double* q_out_dev, int32_t* status_dev,
+                                        int32_t* ds_status_dev);
+
 /* Pinned host memory helpers: buffers from here make the host<->device copies of the batch
  * operators run at full PCIe speed. */
 NWB_API void* nwb_host_alloc(size_t bytes);

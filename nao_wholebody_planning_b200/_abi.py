@@ -99,6 +99,22 @@ def _declare(lib):
         "nwb_is_state_colliding_batch": (C.c_int, [vp, vp, i64, vp, vp]),
         "nwb_fk_batch": (C.c_int, [vp, vp, i64, vp, vp]),
         "nwb_frame_name": (C.c_char_p, [C.c_int]),
+        "nwb_tree_create": (C.c_int, [vp, i64, C.POINTER(vp)]),
+        "nwb_tree_destroy": (None, [vp]),
+        "nwb_tree_clear": (C.c_int, [vp]),
+        "nwb_tree_size": (i64, [vp]),
+        "nwb_tree_add": (C.c_int, [vp, vp, vp, i64]),
+        "nwb_tree_add_dev": (C.c_int, [vp, vp, vp, i64]),
+        "nwb_tree_get": (C.c_int, [vp, i64, i64, vp, vp]),
+        "nwb_nearest_neighbour_batch": (C.c_int, [vp, vp, i64, vp, vp]),
+        "nwb_nearest_neighbour_batch_dev": (C.c_int, [vp, vp, i64, vp, vp]),
+        "nwb_steer_project_batch": (C.c_int, [vp, vp, vp, i64, vp, dbl, vp, vp, vp]),
+        "nwb_steer_project_batch_dev": (C.c_int, [vp, vp, vp, i64, vp, dbl, vp, vp, vp]),
+        "nwb_connect_batch": (C.c_int, [vp, vp, vp, i64, vp, dbl, i32, vp, vp, vp]),
+        "nwb_is_path_valid_batch": (C.c_int, [vp, vp, vp, i64, i32, vp, vp]),
+        "nwb_is_path_valid_batch_dev": (C.c_int, [vp, vp, vp, i64, i32, vp, vp]),
+        "nwb_sample_stable_configs": (C.c_int, [vp, C.c_uint64, C.c_uint64, i64, i32, vp, i64, C.POINTER(i64), vp, vp]),
+        "nwb_sample_stable_configs_dev": (C.c_int, [vp, C.c_uint64, C.c_uint64, i64, i32, vp, vp, i64, vp, vp]),
         "nwb_host_alloc": (vp, [C.c_size_t]),
         "nwb_host_free": (None, [vp]),
         "nwb_ffma_peak": (C.c_int, [vp, C.c_int, pd, pd]),

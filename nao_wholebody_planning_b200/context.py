@@ -131,6 +131,59 @@ class Context:
         self._check(self.lib.nwb_fk_batch(self.h, _p(q), n, _p(poses), _p(com)), "nwb_fk_batch")
         return poses, com
 
+    # ---- local planner operators ----------------------------------------------------------------
+    @staticmethod
+    def _weights(w):
+        return None if w is None else np.ascontiguousarray(w, dtype=np.float64).reshape(NJ)
+
+    def steer_project(self, q_near, q_target, weights=None, step=0.1):
+        """generate_q_new + enforce_DS_Constraints (rrt_planner.cpp:424-593) -> (q_out, status, ds_status)."""
+        q_near = np.ascontiguousarray(q_near, dtype=np.float64).reshape(-1, NJ)
+        q_target = np.ascontiguousarray(q_target, dtype=np.float64).reshape(-1, NJ)
+        n = len(q_near)
+        w = self._weights(weights)
+        out = np.full((n, NJ), np.nan)
+        st = np.empty(n, np.int32)
+        ds = np.empty(n, np.int32)
+        self._check(self.lib.nwb_steer_project_batch(self.h, _p(q_near), _p(q_target), n, _p(w), float(step), _p(out), _p(st),
+                                                     _p(ds)), "nwb_steer_project_batch")
+        return out, st, ds
+
+    def connect(self, q_start, q_connect, weights=None, step=0.1, max_steps=128):
+        """connectTree edge walks (rrt_planner.cpp:926-1031) -> (nodes [n,max_steps,21], n_added, status)."""
+        q_start = np.ascontiguousarray(q_start, dtype=np.float64).reshape(-1, NJ)
+        q_connect = np.ascontiguousarray(q_connect, dtype=np.float64).reshape(-1, NJ)
+        n = len(q_start)
+        w = self._weights(weights)
+        nodes = np.full((n, max_steps, NJ), np.nan)
+        added = np.empty(n, np.int32)
+        st = np.empty(n, np.int32)
+        self._check(self.lib.nwb_connect_batch(self.h, _p(q_start), _p(q_connect), n, _p(w), float(step), int(max_steps),
+                                               _p(nodes), _p(added), _p(st)), "nwb_connect_batch")
+        return nodes, added, st
+
+    def isPathValid(self, qa, qb, k=100):
+        """interpolateWaypoints + PlanningScene::isPathValid (rrt_planner.cpp:1876) -> (ok, first_bad)."""
+        qa = np.ascontiguousarray(qa, dtype=np.float64).reshape(-1, NJ)
+        qb = np.ascontiguousarray(qb, dtype=np.float64).reshape(-1, NJ)
+        n = len(qa)
+        ok = np.empty(n, np.uint8)
+        fb = np.empty(n, np.int32)
+        self._check(self.lib.nwb_is_path_valid_batch(self.h, _p(qa), _p(qb), n, int(k), _p(ok), _p(fb)),
+                    "nwb_is_path_valid_batch")
+        return ok, fb
+
+    def sample_stable_configs(self, seed, first, count, max_ik_iter=5, cap=None, want_stage=True):
+        """sample_stable_configs database branch (stable_config_generator.cpp:278-480) -> (rows, index, stage)."""
+        cap = count if cap is None else cap
+        rows = np.empty((cap, NJ))
+        idx = np.empty(cap, np.uint64)
+        stage = np.empty(count, np.uint8) if want_stage else None
+        n = C.c_int64(0)
+        self._check(self.lib.nwb_sample_stable_configs(self.h, int(seed), int(first), int(count), int(max_ik_iter), _p(rows),
+                                                       int(cap), C.byref(n), _p(idx), _p(stage)), "nwb_sample_stable_configs")
+        return rows[:n.value].copy(), idx[:n.value].copy(), stage
+
     # ---- measurement ----------------------------------------------------------------------------
     def ffma_peak(self, iters=4096):
         t, ms = C.c_double(0), C.c_double(0)
@@ -141,6 +194,56 @@ class Context:
         ms, n = C.c_double(0), C.c_int64(0)
         self._check(self.lib.nwb_last_kernel_ms(self.h, C.byref(ms), C.byref(n)), "nwb_last_kernel_ms")
         return ms.value, n.value
+
+
+class Tree:
+    """nwb_tree: device-resident RRT tree (struct Tree, rrt_planner.h:38-44) with the nearest-neighbour scan."""
+
+    def __init__(self, ctx, capacity_hint=1024):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        h = C.c_void_p()
+        ctx._check(self.lib.nwb_tree_create(ctx.h, int(capacity_hint), C.byref(h)), "nwb_tree_create")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.nwb_tree_destroy(self.h)
+            self.h = None
+
+    def __len__(self):
+        return int(self.lib.nwb_tree_size(self.h))
+
+    def clear(self):
+        self.ctx._check(self.lib.nwb_tree_clear(self.h), "nwb_tree_clear")
+
+    def add(self, q, predecessor=None):
+        q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, NJ)
+        p = None if predecessor is None else np.ascontiguousarray(predecessor, dtype=np.int32)
+        self.ctx._check(self.lib.nwb_tree_add(self.h, _p(q), _p(p), len(q)), "nwb_tree_add")
+
+    def add_dev(self, q_dev, n, predecessor_dev=None):
+        self.ctx._check(self.lib.nwb_tree_add_dev(self.h, q_dev, predecessor_dev, n), "nwb_tree_add_dev")
+
+    def get(self, first=0, n=None):
+        n = len(self) - first if n is None else n
+        q = np.empty((n, NJ))
+        p = np.empty(n, np.int32)
+        self.ctx._check(self.lib.nwb_tree_get(self.h, first, n, _p(q), _p(p)), "nwb_tree_get")
+        return q, p
+
+    def findNearestNeighbour(self, q):
+        """RRT_Planner::findNearestNeighbour for a batch of queries: (idx int32 [nq], dist float64 [nq])."""
+        q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, NJ)
+        idx = np.empty(len(q), np.int32)
+        dist = np.empty(len(q))
+        self.ctx._check(self.lib.nwb_nearest_neighbour_batch(self.h, _p(q), len(q), _p(idx), _p(dist)),
+                        "nwb_nearest_neighbour_batch")
+        return idx, dist
+
+    def nearest_dev(self, q_dev, nq, idx_dev, dist_dev=None):
+        self.ctx._check(self.lib.nwb_nearest_neighbour_batch_dev(self.h, q_dev, nq, idx_dev, dist_dev),
+                        "nwb_nearest_neighbour_batch_dev")
 
 
 class PinnedArray:

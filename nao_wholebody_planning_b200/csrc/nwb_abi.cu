@@ -132,6 +132,7 @@ void nwb_ctx_destroy(nwb_ctx* ctx) {
   if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
   if (ctx->d_in) cudaFree(ctx->d_in);
   if (ctx->d_out) cudaFree(ctx->d_out);
+  if (ctx->d_plan) cudaFree(ctx->d_plan);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);

@@ -71,6 +71,7 @@ struct Ctx {
   void* d_in = nullptr; size_t d_in_bytes = 0;
   void* d_out = nullptr; size_t d_out_bytes = 0;
   void* h_stage = nullptr; size_t h_stage_bytes = 0;   // pinned staging for pageable callers
+  void* d_plan = nullptr; size_t d_plan_bytes = 0;     // scratch of the planner operators
   double last_ms = 0;
   int64_t last_launches = 0;
   int sm_count = 0;
@@ -84,6 +85,19 @@ cudaError_t launch_validity(const ValidityTables& tab, const void* q, int dtype,
                             uint8_t* reason, float* margins, bool collision_only, bool static_pairs, cudaStream_t stream);
 cudaError_t launch_fk(const void* q, int dtype, int64_t n, double* poses, double* com, cudaStream_t stream);
 cudaError_t launch_ffma_peak(int sm_count, int iters, float* sink, cudaStream_t stream, double* flops_out);
+
+// planner kernels (planner_kernels.cu); all pointers are device pointers
+struct PlanConst;
+cudaError_t launch_steer_project(const PlanConst& pc, const double* q_near, const double* q_target, int64_t n, double* q_out,
+                                 int32_t* status, int32_t* ds_status, int32_t* iters, cudaStream_t s);
+cudaError_t launch_connect(const PlanConst& pc, const ValidityTables& tab, bool static_pairs, const double* q_start,
+                           const double* q_connect, int64_t n_edges, int max_steps, double* nodes_out, int32_t* n_added,
+                           int32_t* status, cudaStream_t s);
+cudaError_t launch_edge_check(const ValidityTables& tab, bool static_pairs, const double* qa, const double* qb, int64_t n_edges,
+                              int k, uint8_t* ok, int32_t* first_bad, cudaStream_t s);
+cudaError_t launch_sample(const PlanConst& pc, const ValidityTables& tab, bool static_pairs, uint64_t seed, uint64_t first,
+                          int64_t count, int max_ik_iter, double* rows, uint64_t* row_index, int64_t cap,
+                          unsigned long long* n_out, uint8_t* stage_out, cudaStream_t s);
 
 }  // namespace nwb
 

@@ -1,0 +1,254 @@
+// planner_abi.cu - extern "C" entry points of the local-planner operators (include/nwb.h).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "nwb_internal.h"
+#include "planner_core.cuh"
+
+using namespace nwb;
+
+namespace {
+#define P_CUDA(ctx, call)                                                      \
+  do {                                                                         \
+    cudaError_t e_ = (call);                                                   \
+    if (e_ != cudaSuccess) {                                                   \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_);         \
+      return NWB_E_CUDA;                                                       \
+    }                                                                          \
+  } while (0)
+
+int bad(nwb_ctx* ctx, const char* msg) {
+  if (ctx) ctx->err = msg;
+  return NWB_E_INVALID;
+}
+
+// bump allocator over one device scratch buffer, 256-byte aligned sections
+struct Arena {
+  nwb_ctx* ctx;
+  size_t off = 0;
+  std::vector<size_t> sizes;
+  explicit Arena(nwb_ctx* c) : ctx(c) {}
+  size_t add(size_t bytes) {
+    size_t o = off;
+    off += (bytes + 255) & ~(size_t)255;
+    return o;
+  }
+  int commit() {
+    if (off <= ctx->d_plan_bytes) return NWB_OK;
+    if (ctx->d_plan) cudaFree(ctx->d_plan);
+    ctx->d_plan = nullptr;
+    ctx->d_plan_bytes = 0;
+    size_t cap = std::max(off, (size_t)1 << 20);
+    cudaError_t e = cudaMalloc(&ctx->d_plan, cap);
+    if (e != cudaSuccess) {
+      ctx->err = std::string("cudaMalloc(scratch): ") + cudaGetErrorString(e);
+      return NWB_E_CUDA;
+    }
+    ctx->d_plan_bytes = cap;
+    return NWB_OK;
+  }
+  template <class T>
+  T* at(size_t o) const { return reinterpret_cast<T*>(static_cast<char*>(ctx->d_plan) + o); }
+};
+
+bool static_pairs(const nwb_ctx* ctx) { return ctx->params.srdf_trim != 0 && !ctx->force_table_pairs; }
+}  // namespace
+
+namespace nwb {
+void make_plan_const(const nwb_ctx* ctx, const double* weights, double step, PlanConst& pc) {
+  for (int j = 0; j < NWB_NJ; ++j) {
+    pc.jmin[j] = nwbm::kJointMin[j];
+    pc.jmax[j] = nwbm::kJointMax[j];
+    pc.weights[j] = weights ? weights[j] : 1.0;
+  }
+  pc.step = step;
+  pc.ds_tolerance = ctx->params.ds_tolerance;
+  pc.ik_eps = ctx->params.ik_eps;
+  pc.pinv_eps = ctx->params.pinv_eps;
+  pc.ik_maxiter = ctx->params.ik_maxiter;
+  pc.quirks = (unsigned)ctx->params.quirks;
+}
+}  // namespace nwb
+
+extern "C" {
+
+int nwb_steer_project_batch_dev(nwb_ctx* ctx, const double* q_near, const double* q_target, int64_t n, const double* weights,
+                                double step, double* q_out, int32_t* status, int32_t* ds_status) {
+  if (!ctx) return NWB_E_INVALID;
+  if (n < 0 || (n > 0 && (!q_near || !q_target || !q_out || !status))) return bad(ctx, "nwb_steer_project_batch_dev: bad argument");
+  P_CUDA(ctx, cudaSetDevice(ctx->device));
+  PlanConst pc;
+  make_plan_const(ctx, weights, step, pc);
+  P_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  P_CUDA(ctx, launch_steer_project(pc, q_near, q_target, n, q_out, status, ds_status, nullptr, ctx->stream));
+  P_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  ctx->last_ms = -1;
+  ctx->last_launches = n > 0;
+  return NWB_OK;
+}
+
+int nwb_steer_project_batch(nwb_ctx* ctx, const double* q_near, const double* q_target, int64_t n, const double* weights,
+                            double step, double* q_out, int32_t* status, int32_t* ds_status) {
+  if (!ctx) return NWB_E_INVALID;
+  if (n < 0 || (n > 0 && (!q_near || !q_target || !q_out || !status))) return bad(ctx, "nwb_steer_project_batch: bad argument");
+  if (n == 0) return NWB_OK;
+  P_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t qb = sizeof(double) * NWB_NJ * n, ib = sizeof(int32_t) * n;
+  Arena A(ctx);
+  size_t o_near = A.add(qb), o_tgt = A.add(qb), o_out = A.add(qb), o_st = A.add(ib), o_ds = A.add(ib);
+  int rc = A.commit();
+  if (rc != NWB_OK) return rc;
+  cudaStream_t s = ctx->stream;
+  P_CUDA(ctx, cudaMemcpyAsync(A.at<double>(o_near), q_near, qb, cudaMemcpyHostToDevice, s));
+  P_CUDA(ctx, cudaMemcpyAsync(A.at<double>(o_tgt), q_target, qb, cudaMemcpyHostToDevice, s));
+  // rows of TRAPPED entries are left untouched on the host: copy the caller's buffer in first
+  P_CUDA(ctx, cudaMemcpyAsync(A.at<double>(o_out), q_out, qb, cudaMemcpyHostToDevice, s));
+  rc = nwb_steer_project_batch_dev(ctx, A.at<double>(o_near), A.at<double>(o_tgt), n, weights, step, A.at<double>(o_out),
+                                   A.at<int32_t>(o_st), A.at<int32_t>(o_ds));
+  if (rc != NWB_OK) return rc;
+  P_CUDA(ctx, cudaMemcpyAsync(q_out, A.at<double>(o_out), qb, cudaMemcpyDeviceToHost, s));
+  P_CUDA(ctx, cudaMemcpyAsync(status, A.at<int32_t>(o_st), ib, cudaMemcpyDeviceToHost, s));
+  if (ds_status) P_CUDA(ctx, cudaMemcpyAsync(ds_status, A.at<int32_t>(o_ds), ib, cudaMemcpyDeviceToHost, s));
+  P_CUDA(ctx, cudaStreamSynchronize(s));
+  return NWB_OK;
+}
+
+int nwb_connect_batch(nwb_ctx* ctx, const double* q_start, const double* q_connect, int64_t n_edges, const double* weights,
+                      double step, int32_t max_steps, double* nodes_out, int32_t* n_added, int32_t* status) {
+  if (!ctx) return NWB_E_INVALID;
+  if (n_edges < 0 || max_steps <= 0 || (n_edges > 0 && (!q_start || !q_connect || !nodes_out || !n_added || !status)))
+    return bad(ctx, "nwb_connect_batch: bad argument");
+  if (n_edges == 0) return NWB_OK;
+  P_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t qb = sizeof(double) * NWB_NJ * n_edges, nb = qb * max_steps, ib = sizeof(int32_t) * n_edges;
+  Arena A(ctx);
+  size_t o_s = A.add(qb), o_c = A.add(qb), o_n = A.add(nb), o_a = A.add(ib), o_st = A.add(ib);
+  int rc = A.commit();
+  if (rc != NWB_OK) return rc;
+  cudaStream_t s = ctx->stream;
+  PlanConst pc;
+  make_plan_const(ctx, weights, step, pc);
+  P_CUDA(ctx, cudaMemcpyAsync(A.at<double>(o_s), q_start, qb, cudaMemcpyHostToDevice, s));
+  P_CUDA(ctx, cudaMemcpyAsync(A.at<double>(o_c), q_connect, qb, cudaMemcpyHostToDevice, s));
+  P_CUDA(ctx, launch_connect(pc, ctx->tab_group, static_pairs(ctx), A.at<double>(o_s), A.at<double>(o_c), n_edges, max_steps,
+                             A.at<double>(o_n), A.at<int32_t>(o_a), A.at<int32_t>(o_st), s));
+  P_CUDA(ctx, cudaMemcpyAsync(nodes_out, A.at<double>(o_n), nb, cudaMemcpyDeviceToHost, s));
+  P_CUDA(ctx, cudaMemcpyAsync(n_added, A.at<int32_t>(o_a), ib, cudaMemcpyDeviceToHost, s));
+  P_CUDA(ctx, cudaMemcpyAsync(status, A.at<int32_t>(o_st), ib, cudaMemcpyDeviceToHost, s));
+  P_CUDA(ctx, cudaStreamSynchronize(s));
+  ctx->last_launches = 1;
+  return NWB_OK;
+}
+
+int nwb_is_path_valid_batch_dev(nwb_ctx* ctx, const double* qa, const double* qb, int64_t n_edges, int32_t k, uint8_t* ok,
+                                int32_t* first_bad) {
+  if (!ctx) return NWB_E_INVALID;
+  if (n_edges < 0 || k < 0 || (n_edges > 0 && (!qa || !qb || !first_bad))) return bad(ctx, "nwb_is_path_valid_batch_dev: bad argument");
+  P_CUDA(ctx, cudaSetDevice(ctx->device));
+  P_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  P_CUDA(ctx, launch_edge_check(ctx->tab_all, static_pairs(ctx), qa, qb, n_edges, k, ok, first_bad, ctx->stream));
+  P_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  ctx->last_ms = -1;
+  ctx->last_launches = n_edges > 0 ? 2 : 0;
+  return NWB_OK;
+}
+
+int nwb_is_path_valid_batch(nwb_ctx* ctx, const double* qa, const double* qb, int64_t n_edges, int32_t k, uint8_t* ok,
+                            int32_t* first_bad) {
+  if (!ctx) return NWB_E_INVALID;
+  if (n_edges < 0 || k < 0 || (n_edges > 0 && (!qa || !qb || !ok))) return bad(ctx, "nwb_is_path_valid_batch: bad argument");
+  if (n_edges == 0) return NWB_OK;
+  P_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t qbytes = sizeof(double) * NWB_NJ * n_edges;
+  Arena A(ctx);
+  size_t o_a = A.add(qbytes), o_b = A.add(qbytes), o_ok = A.add(n_edges), o_fb = A.add(sizeof(int32_t) * n_edges);
+  int rc = A.commit();
+  if (rc != NWB_OK) return rc;
+  cudaStream_t s = ctx->stream;
+  P_CUDA(ctx, cudaMemcpyAsync(A.at<double>(o_a), qa, qbytes, cudaMemcpyHostToDevice, s));
+  P_CUDA(ctx, cudaMemcpyAsync(A.at<double>(o_b), qb, qbytes, cudaMemcpyHostToDevice, s));
+  rc = nwb_is_path_valid_batch_dev(ctx, A.at<double>(o_a), A.at<double>(o_b), n_edges, k, A.at<uint8_t>(o_ok), A.at<int32_t>(o_fb));
+  if (rc != NWB_OK) return rc;
+  P_CUDA(ctx, cudaMemcpyAsync(ok, A.at<uint8_t>(o_ok), n_edges, cudaMemcpyDeviceToHost, s));
+  if (first_bad) P_CUDA(ctx, cudaMemcpyAsync(first_bad, A.at<int32_t>(o_fb), sizeof(int32_t) * n_edges, cudaMemcpyDeviceToHost, s));
+  P_CUDA(ctx, cudaStreamSynchronize(s));
+  return NWB_OK;
+}
+
+int nwb_sample_stable_configs_dev(nwb_ctx* ctx, uint64_t seed, uint64_t first, int64_t count, int32_t max_ik_iter,
+                                  double* rows, uint64_t* index, int64_t cap, unsigned long long* n_out, uint8_t* stage) {
+  if (!ctx) return NWB_E_INVALID;
+  if (count < 0 || cap < 0 || (count > 0 && (!rows || !index || !n_out))) return bad(ctx, "nwb_sample_stable_configs_dev: bad argument");
+  P_CUDA(ctx, cudaSetDevice(ctx->device));
+  PlanConst pc;
+  make_plan_const(ctx, nullptr, ctx->params.planner_step_factor, pc);
+  P_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  P_CUDA(ctx, launch_sample(pc, ctx->tab_group, static_pairs(ctx), seed, first, count, max_ik_iter, rows, index, cap, n_out, stage,
+                            ctx->stream));
+  P_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  ctx->last_ms = -1;
+  ctx->last_launches = count > 0;
+  return NWB_OK;
+}
+
+int nwb_sample_stable_configs(nwb_ctx* ctx, uint64_t seed, uint64_t first, int64_t count, int32_t max_ik_iter, double* rows_out,
+                              int64_t cap, int64_t* n_out, uint64_t* index_out, uint8_t* stage_out) {
+  if (!ctx) return NWB_E_INVALID;
+  if (count < 0 || cap < 0 || !n_out || (cap > 0 && !rows_out)) return bad(ctx, "nwb_sample_stable_configs: bad argument");
+  *n_out = 0;
+  if (count == 0) return NWB_OK;
+  P_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  const int64_t chunk = std::min<int64_t>(count, (int64_t)1 << 20);
+  Arena A(ctx);
+  size_t o_rows = A.add(sizeof(double) * NWB_NJ * chunk), o_idx = A.add(sizeof(uint64_t) * chunk), o_n = A.add(8),
+         o_stage = A.add(chunk);
+  int rc = A.commit();
+  if (rc != NWB_OK) return rc;
+  std::vector<double> rows;
+  std::vector<uint64_t> idx;
+  int64_t launches = 0;
+  for (int64_t off = 0; off < count; off += chunk) {
+    const int64_t cn = std::min(chunk, count - off);
+    P_CUDA(ctx, cudaMemsetAsync(A.at<char>(o_n), 0, 8, s));
+    rc = nwb_sample_stable_configs_dev(ctx, seed, first + (uint64_t)off, cn, max_ik_iter, A.at<double>(o_rows), A.at<uint64_t>(o_idx),
+                                       cn, A.at<unsigned long long>(o_n), stage_out ? A.at<uint8_t>(o_stage) : nullptr);
+    if (rc != NWB_OK) return rc;
+    ++launches;
+    unsigned long long got = 0;
+    P_CUDA(ctx, cudaMemcpyAsync(&got, A.at<char>(o_n), 8, cudaMemcpyDeviceToHost, s));
+    if (stage_out) P_CUDA(ctx, cudaMemcpyAsync(stage_out + off, A.at<uint8_t>(o_stage), cn, cudaMemcpyDeviceToHost, s));
+    P_CUDA(ctx, cudaStreamSynchronize(s));
+    const size_t base = idx.size();
+    rows.resize((base + got) * NWB_NJ);
+    idx.resize(base + got);
+    if (got) {
+      P_CUDA(ctx, cudaMemcpyAsync(rows.data() + base * NWB_NJ, A.at<double>(o_rows), sizeof(double) * NWB_NJ * got, cudaMemcpyDeviceToHost, s));
+      P_CUDA(ctx, cudaMemcpyAsync(idx.data() + base, A.at<uint64_t>(o_idx), sizeof(uint64_t) * got, cudaMemcpyDeviceToHost, s));
+      P_CUDA(ctx, cudaStreamSynchronize(s));
+    }
+  }
+  // arrival order is not deterministic: restore ascending sample index (the order the reference's
+  // serial loop writes its file in, SCG:463-468)
+  std::vector<size_t> order(idx.size());
+  std::iota(order.begin(), order.end(), (size_t)0);
+  std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return idx[a] < idx[b]; });
+  *n_out = (int64_t)idx.size();
+  const int64_t m = std::min<int64_t>(cap, (int64_t)idx.size());
+  for (int64_t r = 0; r < m; ++r) {
+    std::memcpy(rows_out + r * NWB_NJ, rows.data() + order[r] * NWB_NJ, sizeof(double) * NWB_NJ);
+    if (index_out) index_out[r] = idx[order[r]];
+  }
+  ctx->last_launches = launches;
+  if ((int64_t)idx.size() > cap) {
+    ctx->err = "nwb_sample_stable_configs: more rows accepted than the output capacity";
+    return NWB_E_NOMEM;
+  }
+  return NWB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,339 @@
+// planner_core.cuh - per-thread (fp64) device functions of the local planner: steering, joint limits,
+// double-support check and the left-leg Newton-Raphson / pseudo-inverse IK.
+//
+// Reference functions replaced (file:line relative to the reference checkout):
+//   RRT_Planner::generate_q_new            rrt_connect_planner/src/rrt_planner.cpp:424-494
+//   RRT_Planner::enforce_DS_Constraints    rrt_connect_planner/src/rrt_planner.cpp:498-593
+//   LocalPlanner::checkJointLimits         rrt_connect_planner/src/local_planner.cpp:305-371
+//   LocalPlanner::checkLeftLegPose         rrt_connect_planner/src/local_planner.cpp:244-299
+//   LocalPlanner::getHipPose / getDesiredLeftLegPose / computeLeftLegIK   local_planner.cpp:59-236
+//   ConstraintKinematics::getHipPose / computeLeftLegIK / joint_limits_respected
+//                                          rrt_connect_planner/src/nao_constraint_kinematics.cpp:71-197,512-608
+// and the orocos-KDL solvers those construct (ChainFkSolverPos_recursive, ChainJntToJacSolver,
+// ChainIkSolverVel_pinv eps 1e-5, ChainIkSolverPos_NR maxiter 100 eps 1e-3).
+//
+// Double precision on purpose: B200 keeps a full-rate FP64 pipe, the NR iteration count depends on
+// comparisons against 1e-3 / 1e-5 thresholds, and running it in fp64 makes the device take the same
+// branch as the CPU path except within ~1e-12 of a threshold.  The leg chains are compiled in
+// (local_planner.cpp:18-47): RotX/RotY joints with z- or y- offsets, so FK and the Jacobian are
+// closed-form products of planar rotations instead of generic segment walks.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/nwb.h"
+#include "nao_model_gen.h"
+
+namespace nwb {
+
+struct PlanConst {            // passed by value to the planner kernels
+  double jmin[NWB_NJ], jmax[NWB_NJ];
+  double weights[NWB_NJ];
+  double step;
+  double ds_tolerance, ik_eps, pinv_eps;
+  int ik_maxiter;
+  unsigned quirks;
+};
+
+struct D3 {
+  double x, y, z;
+};
+struct DFrame {               // rotation row-major + translation
+  double r[9];
+  D3 p;
+};
+
+__device__ __forceinline__ D3 d3(double x, double y, double z) { return D3{x, y, z}; }
+__device__ __forceinline__ D3 operator+(D3 a, D3 b) { return d3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ D3 operator-(D3 a, D3 b) { return d3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ D3 cross(D3 a, D3 b) { return d3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+__device__ __forceinline__ D3 rmul(const double* r, D3 v) {
+  return d3(r[0] * v.x + r[1] * v.y + r[2] * v.z, r[3] * v.x + r[4] * v.y + r[5] * v.z, r[6] * v.x + r[7] * v.y + r[8] * v.z);
+}
+__device__ __forceinline__ D3 col(const double* r, int c) { return d3(r[c], r[3 + c], r[6 + c]); }
+
+__device__ __forceinline__ void dframe_identity(DFrame& f) {
+  f.r[0] = 1; f.r[1] = 0; f.r[2] = 0; f.r[3] = 0; f.r[4] = 1; f.r[5] = 0; f.r[6] = 0; f.r[7] = 0; f.r[8] = 1;
+  f.p = d3(0, 0, 0);
+}
+// f.R <- f.R * RotX(a) / RotY(a)  (KDL::Rotation::RotX/RotY)
+__device__ __forceinline__ void drotx(DFrame& f, double a) {
+  double s, c;
+  sincos(a, &s, &c);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    double u = f.r[3 * k + 1], v = f.r[3 * k + 2];
+    f.r[3 * k + 1] = c * u + s * v;
+    f.r[3 * k + 2] = c * v - s * u;
+  }
+}
+__device__ __forceinline__ void droty(DFrame& f, double a) {
+  double s, c;
+  sincos(a, &s, &c);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    double u = f.r[3 * k + 0], v = f.r[3 * k + 2];
+    f.r[3 * k + 0] = c * u - s * v;
+    f.r[3 * k + 2] = s * u + c * v;
+  }
+}
+__device__ __forceinline__ void dtrans(DFrame& f, double x, double y, double z) { f.p = f.p + rmul(f.r, d3(x, y, z)); }
+
+// chain_right_leg_ (sole -> hip), local_planner.cpp:18-23.  legs5 = (-RAnkleRoll, -RAnklePitch, -RKneePitch, -RHipPitch, -RHipRoll)
+__device__ __forceinline__ void right_leg_fk(const double* legs5, DFrame& f) {
+  dframe_identity(f);
+  f.p = d3(0, 0, 0.04519);
+  drotx(f, legs5[0]);
+  droty(f, legs5[1]); dtrans(f, 0, 0, 0.1029);
+  droty(f, legs5[2]); dtrans(f, 0, 0, 0.1);
+  droty(f, legs5[3]);
+  drotx(f, legs5[4]); dtrans(f, 0, 0.05, 0);
+}
+
+// chain_left_leg_ (hip -> sole), local_planner.cpp:26-31, appended to `f`; optionally records the
+// joint origins / axes (base frame of `f`'s parent) for the Jacobian.
+__device__ __forceinline__ void left_leg_fk(const double* ll5, DFrame& f, D3* origin, D3* axis) {
+  dtrans(f, 0, 0.05, 0);
+  if (origin) { origin[0] = f.p; axis[0] = col(f.r, 0); }
+  drotx(f, ll5[0]);
+  if (origin) { origin[1] = f.p; axis[1] = col(f.r, 1); }
+  droty(f, ll5[1]); dtrans(f, 0, 0, -0.1);
+  if (origin) { origin[2] = f.p; axis[2] = col(f.r, 1); }
+  droty(f, ll5[2]); dtrans(f, 0, 0, -0.1029);
+  if (origin) { origin[3] = f.p; axis[3] = col(f.r, 1); }
+  droty(f, ll5[3]);
+  if (origin) { origin[4] = f.p; axis[4] = col(f.r, 0); }
+  drotx(f, ll5[4]); dtrans(f, 0, 0, -0.04519);
+}
+
+// KDL::Rotation::GetRot of R = A^T B (rotation vector axis*angle; GetRotAngle with epsilon 1e-6)
+__device__ __forceinline__ D3 rot_vector(const double* R) {
+  const double eps = 1e-6;
+  double ca = (R[0] + R[4] + R[8] - 1) / 2.0;
+  double t = eps * eps / 2.0;
+  if (ca > 1 - t) return d3(0, 0, 0);
+  if (ca < -1 + t) {
+    double x = sqrt((R[0] + 1.0) / 2), y = sqrt((R[4] + 1.0) / 2), z = sqrt((R[8] + 1.0) / 2);
+    if (R[2] < 0) x = -x;
+    if (R[7] < 0) y = -y;
+    if (x * y * R[1] < 0) x = -x;
+    const double pi = 3.14159265358979323846;
+    return d3(x * pi, y * pi, z * pi);
+  }
+  double ax = R[7] - R[5], ay = R[2] - R[6], az = R[3] - R[1];
+  double mod = sqrt(ax * ax + ay * ay + az * az);
+  double angle = atan2(mod / 2, ca);
+  return d3(ax / mod * angle, ay / mod * angle, az / mod * angle);
+}
+
+// KDL::diff(F_a, F_b) = (p_b - p_a, R_a * rotvec(R_a^T R_b))
+__device__ __forceinline__ void frame_diff(const DFrame& a, const DFrame& b, double* tw) {
+  double rel[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) rel[3 * i + j] = a.r[i] * b.r[j] + a.r[3 + i] * b.r[3 + j] + a.r[6 + i] * b.r[6 + j];
+  D3 w = rmul(a.r, rot_vector(rel));
+  tw[0] = b.p.x - a.p.x; tw[1] = b.p.y - a.p.y; tw[2] = b.p.z - a.p.z;
+  tw[3] = w.x; tw[4] = w.y; tw[5] = w.z;
+}
+
+// qdot = pinv(J) * twist with singular values below eps zeroed (ChainIkSolverVel_pinv).
+// J is 6x5 (column i = (a_i x (p_tip - o_i), a_i)).  One-sided Jacobi SVD, W = J V = U S.
+static __device__ __noinline__ void pinv_solve(double (*W)[5], const double* tw, double eps, double* qdot) {
+  double V[5][5];
+#pragma unroll
+  for (int i = 0; i < 5; ++i)
+#pragma unroll
+    for (int j = 0; j < 5; ++j) V[i][j] = (i == j) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = 0;
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int q = p + 1; q < 5; ++q) {
+        double alpha = 0, beta = 0, gamma = 0;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+          alpha += W[r][p] * W[r][p];
+          beta += W[r][q] * W[r][q];
+          gamma += W[r][p] * W[r][q];
+        }
+        if (gamma != 0.0) {
+          off = fmax(off, fabs(gamma) / sqrt(alpha * beta + 1e-300));
+          double zeta = (beta - alpha) / (2 * gamma);
+          double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1 + zeta * zeta));
+          double c = 1 / sqrt(1 + t * t), s = c * t;
+#pragma unroll
+          for (int r = 0; r < 6; ++r) {
+            double wp = W[r][p], wq = W[r][q];
+            W[r][p] = c * wp - s * wq;
+            W[r][q] = s * wp + c * wq;
+          }
+#pragma unroll
+          for (int r = 0; r < 5; ++r) {
+            double vp = V[r][p], vq = V[r][q];
+            V[r][p] = c * vp - s * vq;
+            V[r][q] = s * vp + c * vq;
+          }
+        }
+      }
+    if (off < 1e-15) break;
+  }
+  // tmp_i = (u_i . tw) / s_i  with u_i = W[:,i]/s_i  ->  (W[:,i] . tw) / s_i^2 ; zero if s_i < eps
+  double tmp[5];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    double n2 = 0, dotv = 0;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      n2 += W[r][i] * W[r][i];
+      dotv += W[r][i] * tw[r];
+    }
+    double sv = sqrt(n2);
+    tmp[i] = (sv < eps) ? 0.0 : (dotv / sv) * (1.0 / sv);
+  }
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    double s = 0;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) s += V[i][j] * tmp[j];
+    qdot[i] = s;
+  }
+}
+
+// ChainIkSolverPos_NR::CartToJnt on the left-leg chain (base = hip frame).  The update is applied
+// BEFORE the convergence test.  Returns true on convergence; q holds the result.
+__device__ __forceinline__ bool left_leg_ik_nr(const DFrame& target, double* q /*[5] in: seed*/, int maxiter, double eps,
+                                               double pinv_eps, int* iters_out) {
+  int i;
+  for (i = 0; i < maxiter; ++i) {
+    DFrame f;
+    dframe_identity(f);
+    D3 o[5], a[5];
+    left_leg_fk(q, f, o, a);
+    double tw[6];
+    frame_diff(f, target, tw);
+    double W[6][5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      D3 v = cross(a[k], f.p - o[k]);
+      W[0][k] = v.x; W[1][k] = v.y; W[2][k] = v.z;
+      W[3][k] = a[k].x; W[4][k] = a[k].y; W[5][k] = a[k].z;
+    }
+    double dq[5];
+    pinv_solve(W, tw, pinv_eps, dq);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) q[k] += dq[k];
+    bool conv = true;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) conv = conv && (eps > tw[k]) && (tw[k] > -eps);
+    if (conv) break;
+  }
+  if (iters_out) *iters_out = (i < maxiter) ? i + 1 : maxiter;
+  return i != maxiter;
+}
+
+// target = (R^T, R^T ((0,0.1,0) - p_hip))   (getDesiredLeftLegPose, local_planner.cpp:59-110)
+__device__ __forceinline__ void desired_left_leg_pose(const DFrame& hip, DFrame& t) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) t.r[3 * i + j] = hip.r[3 * j + i];
+  const double fx = nwbm::kLeftSoleTarget[0], fy = nwbm::kLeftSoleTarget[1], fz = nwbm::kLeftSoleTarget[2];
+  double o[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    double tmp = -t.r[3 * i] * hip.p.x - t.r[3 * i + 1] * hip.p.y - t.r[3 * i + 2] * hip.p.z;
+    double tmp2 = t.r[3 * i] * fx + t.r[3 * i + 1] * fy + t.r[3 * i + 2] * fz;
+    o[i] = tmp + tmp2;
+  }
+  t.p = d3(o[0], o[1], o[2]);
+}
+
+// strict joint-limit test (checkJointLimits / joint_limits_respected); swapped bounds tolerated
+__device__ __forceinline__ bool limits_ok(const double* q, const double* mn, const double* mx, int n) {
+  bool ok = true;
+  for (int i = 0; i < n; ++i) {
+    double lo = fmin(mn[i], mx[i]), hi = fmax(mn[i], mx[i]);
+    if (mn[i] != mx[i]) ok = ok && (q[i] > lo) && (q[i] < hi);
+  }
+  return ok;
+}
+
+// RRT_Planner::generate_q_new.  Returns NWB_ADVANCED or NWB_REACHED.
+__device__ __forceinline__ int generate_q_new(const double* q_near, const double* q_rand, const PlanConst& pc, double* q_new) {
+  double d[NWB_NJ], sum = 0;
+  for (int i = 0; i < NWB_NJ; ++i) {
+    d[i] = q_rand[i] - q_near[i];
+    sum = __dadd_rn(sum, __dmul_rn(d[i], d[i]));
+  }
+  double norm = sqrt(sum);
+  double inc[NWB_NJ], sum_inc = 0;
+  for (int j = 0; j < NWB_NJ; ++j) {
+    double dir = d[j] / norm;
+    inc[j] = __dmul_rn(pc.step, __dmul_rn(dir, pc.weights[j]));
+    sum_inc = __dadd_rn(sum_inc, __dmul_rn(inc[j], inc[j]));
+  }
+  double norm_inc = sqrt(sum_inc);
+  if (norm_inc < norm) {
+    for (int i = 0; i < NWB_NJ; ++i) q_new[i] = q_near[i] + inc[i];
+    return NWB_ADVANCED;
+  }
+  for (int i = 0; i < NWB_NJ; ++i) q_new[i] = q_rand[i];
+  return NWB_REACHED;
+}
+
+// RRT_Planner::enforce_DS_Constraints.  q is modified in place (left leg) when the IK is needed.
+// Returns NWB_REACHED (already in double support), NWB_ADVANCED (left leg re-solved), NWB_TRAPPED.
+__device__ __forceinline__ int enforce_ds_constraints(double* q, const PlanConst& pc, int* iters_out) {
+  if (iters_out) *iters_out = 0;
+  if (!limits_ok(q, pc.jmin, pc.jmax, NWB_NJ)) return NWB_TRAPPED;
+  double rl[5], ll[5];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    rl[i] = -q[i];
+    ll[i] = q[16 + i];
+  }
+  DFrame hip;
+  right_leg_fk(rl, hip);
+  // checkLeftLegPose: FK of the 10-joint legs chain, signed error (quirk C2) or absolute error
+  DFrame foot = hip;
+  left_leg_fk(ll, foot, nullptr, nullptr);
+  const double des[3] = {nwbm::kLeftSoleTarget[0], nwbm::kLeftSoleTarget[1], nwbm::kLeftSoleTarget[2]};
+  const double act[3] = {foot.p.x, foot.p.y, foot.p.z};
+  double max_err = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    double e = des[i] - act[i];
+    if (!(pc.quirks & NWB_QUIRK_SIGNED_FOOT_ERROR)) e = fabs(e);
+    if (e > max_err) max_err = e;
+  }
+  if (!(max_err > pc.ds_tolerance)) return NWB_REACHED;
+  DFrame target;
+  desired_left_leg_pose(hip, target);
+  if (!left_leg_ik_nr(target, ll, pc.ik_maxiter, pc.ik_eps, pc.pinv_eps, iters_out)) return NWB_TRAPPED;
+  if (!limits_ok(ll, pc.jmin + 16, pc.jmax + 16, 5)) return NWB_TRAPPED;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) q[16 + i] = ll[i];
+  return NWB_ADVANCED;
+}
+
+// ---- Philox4x32-10 counter-based stream (DESIGN.md "random streams") ---------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t* out) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+constexpr uint32_t kStreamSampler = 1, kStreamPlanner = 2;
+__device__ __forceinline__ double u01(uint32_t x) { return ((double)x + 0.5) * (1.0 / 4294967296.0); }
+
+}  // namespace nwb

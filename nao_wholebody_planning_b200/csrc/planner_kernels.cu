@@ -1,0 +1,224 @@
+// planner_kernels.cu - batched local-planner operators for sm_100a:
+//   steer_project   generate_q_new -> enforce_DS_Constraints         (RP:424-494, 498-593)
+//   connect         the connectTree edge walk, one thread per edge   (RP:926-1031)
+//   edge_check      interpolateWaypoints + isPathValid               (RP:1677-1774, 1876, 1905)
+//   sample          sample_stable_configs, database branch           (SCG:278-480)
+// RP = rrt_connect_planner/src/rrt_planner.cpp, SCG = .../stable_config_generator.cpp.
+// The per-thread building blocks live in planner_core.cuh (fp64 IK) and validity_core.cuh (fp32
+// validity); these kernels only lay the work out: one unit (edge step chain, way-point, sample) per
+// thread, coalesced output, no inter-thread communication except the per-edge "first bad way-point"
+// minimum and the compaction counter of the sampler.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <climits>
+#include <cstdlib>
+
+#include "planner_core.cuh"
+#include "validity_core.cuh"
+
+namespace nwb {
+
+// Point table of one configuration in thread-private storage: registers when every slot is a
+// compile-time constant (compiled-in pair list), local memory under the table-driven pair list.
+struct LocalStore {
+  float v[nwbm::kPointFloats];
+  __device__ __forceinline__ void put(int slot, float x) { v[slot] = x; }
+  __device__ __forceinline__ float get(int slot) const { return v[slot]; }
+};
+
+template <bool COLLISION_ONLY, bool STATIC>
+__device__ __forceinline__ ValidityResult<float> eval_one(const ValidityTables& tab, const double* q) {
+  float qf[NWB_NJ];
+#pragma unroll
+  for (int j = 0; j < NWB_NJ; ++j) qf[j] = (float)q[j];
+  LocalStore st;
+  constexpr int P = STATIC ? (COLLISION_ONLY ? PAIRS_STATIC_ALL : PAIRS_STATIC_GROUP) : PAIRS_TABLE;
+  return evaluate_config<float, LocalStore, false, COLLISION_ONLY, P>(tab, qf, st, nullptr, nullptr);
+}
+
+// ---- steer + project ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+steer_project_kernel(const __grid_constant__ PlanConst pc, const double* __restrict__ q_near, const double* __restrict__ q_target,
+                     int64_t n, double* __restrict__ q_out, int32_t* __restrict__ status, int32_t* __restrict__ ds_status,
+                     int32_t* __restrict__ iters) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double a[NWB_NJ], b[NWB_NJ], q[NWB_NJ];
+  for (int j = 0; j < NWB_NJ; ++j) {
+    a[j] = q_near[i * NWB_NJ + j];
+    b[j] = q_target[i * NWB_NJ + j];
+  }
+  int st = generate_q_new(a, b, pc, q);
+  int it = 0;
+  int ds = enforce_ds_constraints(q, pc, &it);
+  if (ds_status) ds_status[i] = ds;
+  if (iters) iters[i] = it;
+  if (ds == NWB_TRAPPED) {
+    status[i] = NWB_TRAPPED;
+    return;
+  }
+  if (ds == NWB_ADVANCED) st = NWB_ADVANCED;
+  status[i] = st;
+  for (int j = 0; j < NWB_NJ; ++j) q_out[i * NWB_NJ + j] = q[j];
+}
+
+// ---- connect: one thread walks one edge -------------------------------------------------------------
+// From q_start repeat {generate_q_new -> enforce_DS -> isConfigValid -> append} until REACHED or
+// TRAPPED; step k+1 starts from the PROJECTED node of step k (RP:1004), so the walk is serial by
+// construction and the parallelism is across edges.
+template <bool STATIC>
+__global__ void __launch_bounds__(64)
+connect_kernel(const __grid_constant__ PlanConst pc, const __grid_constant__ ValidityTables tab,
+               const double* __restrict__ q_start, const double* __restrict__ q_connect, int64_t n_edges, int max_steps,
+               double* __restrict__ nodes_out /*[n_edges][max_steps][21]*/, int32_t* __restrict__ n_added,
+               int32_t* __restrict__ status) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  double cur[NWB_NJ], tgt[NWB_NJ], q[NWB_NJ];
+  for (int j = 0; j < NWB_NJ; ++j) {
+    cur[j] = q_start[e * NWB_NJ + j];
+    tgt[j] = q_connect[e * NWB_NJ + j];
+  }
+  int state = NWB_ADVANCED, added = 0;
+  while (state == NWB_ADVANCED && added < max_steps) {
+    state = generate_q_new(cur, tgt, pc, q);
+    int ds = enforce_ds_constraints(q, pc, nullptr);
+    if (ds == NWB_TRAPPED) { state = NWB_TRAPPED; break; }
+    if (ds == NWB_ADVANCED) state = NWB_ADVANCED;
+    ValidityResult<float> r = eval_one<false, STATIC>(tab, q);
+    if (r.hit || !r.stable) { state = NWB_TRAPPED; break; }
+    double* o = nodes_out + ((size_t)e * max_steps + added) * NWB_NJ;
+    for (int j = 0; j < NWB_NJ; ++j) {
+      o[j] = q[j];
+      cur[j] = q[j];
+    }
+    ++added;
+  }
+  n_added[e] = added;
+  status[e] = (state == NWB_ADVANCED) ? -1 : state;     // -1: step budget exhausted before REACHED / TRAPPED
+}
+
+// ---- edge check: (edge, way-point) -> collision-only validity ------------------------------------------
+template <bool STATIC>
+__global__ void __launch_bounds__(128)
+edge_check_kernel(const __grid_constant__ ValidityTables tab, const double* __restrict__ qa, const double* __restrict__ qb,
+                  int64_t n_edges, int k, int32_t* __restrict__ first_bad) {
+  const int wp = k + 2;
+  int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = gid < n_edges * wp;
+  if (!active) gid = 0;
+  const int64_t e = gid / wp;
+  const int n = (int)(gid - e * wp);
+  double q[NWB_NJ];
+  for (int j = 0; j < NWB_NJ; ++j) {
+    double a = qa[e * NWB_NJ + j], b = qb[e * NWB_NJ + j];
+    double sw = (b - a) / (k + 1);                         // RP:1758
+    q[j] = (n == 0) ? a : __dadd_rn(a, __dmul_rn(sw, (double)n));   // RP:1763, 1771
+  }
+  ValidityResult<float> r = eval_one<true, STATIC>(tab, q);
+  if (active && r.hit) atomicMin(first_bad + e, n);
+}
+
+__global__ void edge_finish_kernel(int32_t* __restrict__ first_bad, int64_t n_edges, uint8_t* __restrict__ ok) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  int fb = first_bad[e];
+  bool good = fb == 0x7f7f7f7f;                 // the memset pattern of launch_edge_check: no way-point collided
+  if (ok) ok[e] = good;
+  first_bad[e] = good ? -1 : fb;
+}
+
+// ---- stable-configuration sampler ------------------------------------------------------------------------
+// Sample i draws its 21 joints from Philox(seed; counter = (i, slot/4, stream)), so the accepted set
+// is independent of how [first, first+count) is partitioned over launches, streams or GPUs.
+template <bool STATIC>
+__global__ void __launch_bounds__(64)
+sample_kernel(const __grid_constant__ PlanConst pc, const __grid_constant__ ValidityTables tab, uint64_t seed, uint64_t first,
+              int64_t count, int max_ik_iter, double* __restrict__ rows /*[cap][21]*/, uint64_t* __restrict__ row_index,
+              int64_t cap, unsigned long long* __restrict__ n_out, uint8_t* __restrict__ stage_out) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  const uint64_t i = first + (uint64_t)t;
+  double q[NWB_NJ];
+#pragma unroll 1
+  for (int blk = 0; blk < (NWB_NJ + 3) / 4; ++blk) {
+    uint32_t r[4];
+    philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), (uint32_t)blk, kStreamSampler, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    for (int l = 0; l < 4; ++l) {
+      int j = 4 * blk + l;
+      if (j < NWB_NJ) q[j] = __dadd_rn(__dmul_rn(pc.jmax[j] - pc.jmin[j], u01(r[l])), pc.jmin[j]);   // uniformReal(lo, hi)
+    }
+  }
+  q[15] = 0.0;                                           // SCG:291
+  double rl[5], ll[5];
+  for (int m = 0; m < 5; ++m) rl[m] = -q[m];             // SCG:307-313
+  DFrame hip, target;
+  right_leg_fk(rl, hip);
+  desired_left_leg_pose(hip, target);
+  uint8_t stage = 0;
+  bool solved = false;
+  for (int attempt = 0; attempt < max_ik_iter && !solved; ++attempt) {   // identical attempts (quirk C5)
+    for (int m = 0; m < 5; ++m) ll[m] = -rl[m];          // NCK:150 seed
+    if (left_leg_ik_nr(target, ll, pc.ik_maxiter, pc.ik_eps, pc.pinv_eps, nullptr)) solved = limits_ok(ll, pc.jmin + 16, pc.jmax + 16, 5);
+    if (!solved && attempt == 0 && max_ik_iter > 1) break;   // every further attempt repeats the same arithmetic
+  }
+  if (solved) {
+    for (int m = 0; m < 5; ++m) q[16 + m] = ll[m];
+    ValidityResult<float> r = eval_one<false, STATIC>(tab, q);
+    const bool feasible = !r.hit && r.stable;
+    stage = feasible ? 2 : 1;
+    const bool keep = (pc.quirks & NWB_QUIRK_DB_KEEPS_INFEASIBLE) ? !feasible : feasible;   // SCG:452-456
+    if (keep) {
+      unsigned long long slot = atomicAdd(n_out, 1ull);
+      if ((int64_t)slot < cap) {
+        for (int j = 0; j < NWB_NJ; ++j) rows[slot * NWB_NJ + j] = q[j];
+        row_index[slot] = i;
+      }
+    }
+  }
+  if (stage_out) stage_out[t] = stage;
+}
+
+// ---- launchers -------------------------------------------------------------------------------------------------
+cudaError_t launch_steer_project(const PlanConst& pc, const double* q_near, const double* q_target, int64_t n, double* q_out,
+                                 int32_t* status, int32_t* ds_status, int32_t* iters, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  steer_project_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(pc, q_near, q_target, n, q_out, status, ds_status, iters);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_connect(const PlanConst& pc, const ValidityTables& tab, bool static_pairs, const double* q_start,
+                           const double* q_connect, int64_t n_edges, int max_steps, double* nodes_out, int32_t* n_added,
+                           int32_t* status, cudaStream_t s) {
+  if (n_edges <= 0) return cudaSuccess;
+  unsigned blocks = (unsigned)((n_edges + 63) / 64);
+  if (static_pairs) connect_kernel<true><<<blocks, 64, 0, s>>>(pc, tab, q_start, q_connect, n_edges, max_steps, nodes_out, n_added, status);
+  else connect_kernel<false><<<blocks, 64, 0, s>>>(pc, tab, q_start, q_connect, n_edges, max_steps, nodes_out, n_added, status);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_edge_check(const ValidityTables& tab, bool static_pairs, const double* qa, const double* qb, int64_t n_edges,
+                              int k, uint8_t* ok, int32_t* first_bad, cudaStream_t s) {
+  if (n_edges <= 0) return cudaSuccess;
+  cudaError_t e = cudaMemsetAsync(first_bad, 0x7f, sizeof(int32_t) * n_edges, s);   // 0x7f7f7f7f > any way-point index
+  if (e != cudaSuccess) return e;
+  const int64_t total = n_edges * (k + 2);
+  unsigned blocks = (unsigned)((total + 127) / 128);
+  if (static_pairs) edge_check_kernel<true><<<blocks, 128, 0, s>>>(tab, qa, qb, n_edges, k, first_bad);
+  else edge_check_kernel<false><<<blocks, 128, 0, s>>>(tab, qa, qb, n_edges, k, first_bad);
+  edge_finish_kernel<<<(unsigned)((n_edges + 127) / 128), 128, 0, s>>>(first_bad, n_edges, ok);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sample(const PlanConst& pc, const ValidityTables& tab, bool static_pairs, uint64_t seed, uint64_t first,
+                          int64_t count, int max_ik_iter, double* rows, uint64_t* row_index, int64_t cap,
+                          unsigned long long* n_out, uint8_t* stage_out, cudaStream_t s) {
+  if (count <= 0) return cudaSuccess;
+  unsigned blocks = (unsigned)((count + 63) / 64);
+  if (static_pairs) sample_kernel<true><<<blocks, 64, 0, s>>>(pc, tab, seed, first, count, max_ik_iter, rows, row_index, cap, n_out, stage_out);
+  else sample_kernel<false><<<blocks, 64, 0, s>>>(pc, tab, seed, first, count, max_ik_iter, rows, row_index, cap, n_out, stage_out);
+  return cudaGetLastError();
+}
+
+}  // namespace nwb
