@@ -225,6 +225,43 @@ NWB_API int nwb_steer_project_batch_dev(nwb_ctx* ctx, const double* q_near_dev, 
                                         const double* weights, double step, double* q_out_dev, int32_t* status_dev,
                                         int32_t* ds_status_dev);
 
+/* ---- RRT-Connect driver --------------------------------------------------------------------------
+ * Result of one planning query (the response fields of Compute_Motion_Plan.srv:16-29 that come out
+ * of RRT_Planner::solveQuery, plus what writePath needs to rebuild the path). */
+typedef struct nwb_plan_result {
+  int32_t start_valid;          /* RRT_Planner::setStartGoalConfigs, RP:241-246                    */
+  int32_t goal_valid;           /* RP:260-265                                                       */
+  int32_t success;              /* a path was found (REACHED), RP:1087 / RP:1147                    */
+  int32_t iterations;           /* solveQuery loop iterations used (RP:1067)                        */
+  int32_t num_nodes_generated;  /* T_start.num_nodes + T_goal.num_nodes (RP:1108)                   */
+  int32_t nodes_start;
+  int32_t nodes_goal;
+  int32_t connector;            /* 1: goal tree connected to start tree, 2: the reverse (RP:1101,1161) */
+  int32_t bridge_other;         /* q_near.index in the connecting tree (RP:1320,1325)               */
+  int32_t raw_path_len;         /* way-points of the raw solution path (RP:1383-1391)               */
+} nwb_plan_result;
+
+/* RRT_Planner::setStartGoalConfigs + solveQuery (RP:227-302, 1039-1212) + the path extraction of
+ * writePath (RP:1303-1392) for nq independent queries advanced in lock step on the device.
+ *   starts, goals [nq][21]; db [n_db][21] = the stable-configuration database (load_DS_database,
+ *   RP:121-191); weights [21] or NULL; seeds [nq]: query k draws its database row of iteration i
+ *   from Philox4x32-10(seed_k; i) (RRT_Planner::getRandomStableConfig RP:316-332 with an injected
+ *   stream; quirk C3 selects floor(U*(n-1)) or floor(U*n)); max_iter, step: solveQuery arguments
+ *   (8000, 0.1); tree_capacity: nodes per tree (0 = 4096).
+ *   results [nq]; raw_paths [nq][raw_path_capacity][21] (may be NULL) receives each raw path. */
+NWB_API int nwb_solve_query_batch(nwb_ctx* ctx, const double* starts, const double* goals, int64_t nq, const double* db,
+                                  int32_t n_db, const double* weights, const uint64_t* seeds, int32_t max_iter, double step,
+                                  int32_t tree_capacity, nwb_plan_result* results, double* raw_paths,
+                                  int32_t raw_path_capacity);
+/* RRT_Planner::path_shortcutter, way-point selection (RP:1830-1951): returns the number of way-points
+ * written to out (<= cap), -100 if the 500-round budget ran out, or an NWB_E_* code.  Every round's
+ * candidate edges are checked in one batch of nwb_is_path_valid_batch. */
+NWB_API int nwb_shortcut_path(nwb_ctx* ctx, const double* raw, int32_t n_raw, double* out, int32_t cap,
+                              int32_t* edges_checked);
+/* RRT_Planner::interpolateShortPathWaypoints (RP:1956-1994): k points per segment; returns the row
+ * count (n_path-1)*(k+1)+1 (rows beyond cap are not written). */
+NWB_API int nwb_interpolate_path(const double* path, int32_t n_path, int32_t k, double* out, int32_t cap);
+
 /* Pinned host memory helpers: buffers from here make the host<->device copies of the batch
  * operators run at full PCIe speed. */
 NWB_API void* nwb_host_alloc(size_t bytes);

@@ -40,6 +40,12 @@ class NwbParams(C.Structure):
     ]
 
 
+class NwbPlanResult(C.Structure):
+    """struct nwb_plan_result (include/nwb.h)."""
+    _fields_ = [(n, C.c_int32) for n in ("start_valid", "goal_valid", "success", "iterations", "num_nodes_generated",
+                                         "nodes_start", "nodes_goal", "connector", "bridge_other", "raw_path_len")]
+
+
 def default_params(**over):
     """Reference defaults (planning_config/planning_parameters.yaml, hard-coded constants)."""
     p = NwbParams(device=0, quirks=QUIRK_SIGNED_FOOT_ERROR | QUIRK_DB_INDEX_FLOOR, srdf_trim=1, scale_origin=1,
@@ -115,6 +121,9 @@ def _declare(lib):
         "nwb_is_path_valid_batch_dev": (C.c_int, [vp, vp, vp, i64, i32, vp, vp]),
         "nwb_sample_stable_configs": (C.c_int, [vp, C.c_uint64, C.c_uint64, i64, i32, vp, i64, C.POINTER(i64), vp, vp]),
         "nwb_sample_stable_configs_dev": (C.c_int, [vp, C.c_uint64, C.c_uint64, i64, i32, vp, vp, i64, vp, vp]),
+        "nwb_solve_query_batch": (C.c_int, [vp, vp, vp, i64, vp, i32, vp, vp, i32, dbl, i32, vp, vp, i32]),
+        "nwb_shortcut_path": (C.c_int, [vp, vp, i32, vp, i32, vp]),
+        "nwb_interpolate_path": (C.c_int, [vp, i32, i32, vp, i32]),
         "nwb_host_alloc": (vp, [C.c_size_t]),
         "nwb_host_free": (None, [vp]),
         "nwb_ffma_peak": (C.c_int, [vp, C.c_int, pd, pd]),

@@ -184,6 +184,45 @@ class Context:
                                                        int(cap), C.byref(n), _p(idx), _p(stage)), "nwb_sample_stable_configs")
         return rows[:n.value].copy(), idx[:n.value].copy(), stage
 
+    # ---- RRT-Connect driver ---------------------------------------------------------------------
+    def solveQuery(self, starts, goals, db, seeds, weights=None, max_iter=8000, step=0.1, tree_capacity=4096,
+                   raw_path_capacity=1024):
+        """setStartGoalConfigs + solveQuery + raw path extraction for a batch of queries.
+        Returns (list of result dicts, list of raw paths [len,21])."""
+        starts = np.ascontiguousarray(starts, dtype=np.float64).reshape(-1, NJ)
+        goals = np.ascontiguousarray(goals, dtype=np.float64).reshape(-1, NJ)
+        db = np.ascontiguousarray(db, dtype=np.float64).reshape(-1, NJ)
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint64)
+        nq = len(starts)
+        w = self._weights(weights)
+        res = (_abi.NwbPlanResult * nq)()
+        raw = np.full((nq, raw_path_capacity, NJ), np.nan)
+        self._check(self.lib.nwb_solve_query_batch(self.h, _p(starts), _p(goals), nq, _p(db), len(db), _p(w), _p(seeds),
+                                                   int(max_iter), float(step), int(tree_capacity), C.byref(res), _p(raw),
+                                                   int(raw_path_capacity)), "nwb_solve_query_batch")
+        out = [{n: getattr(r, n) for n, _ in _abi.NwbPlanResult._fields_} for r in res]
+        paths = [raw[k, :min(out[k]["raw_path_len"], raw_path_capacity)].copy() for k in range(nq)]
+        return out, paths
+
+    def shortcut_path(self, raw):
+        raw = np.ascontiguousarray(raw, dtype=np.float64).reshape(-1, NJ)
+        out = np.empty((len(raw) + 4, NJ))
+        edges = C.c_int32(0)
+        n = self.lib.nwb_shortcut_path(self.h, _p(raw), len(raw), _p(out), len(out), C.byref(edges))
+        if n == -100:
+            return None, edges.value
+        if n < 0:
+            self._check(n, "nwb_shortcut_path")
+        return out[:n].copy(), edges.value
+
+    def interpolate_path(self, path, k):
+        path = np.ascontiguousarray(path, dtype=np.float64).reshape(-1, NJ)
+        cap = (len(path) - 1) * (k + 1) + 1
+        out = np.empty((cap, NJ))
+        n = self.lib.nwb_interpolate_path(_p(path), len(path), int(k), _p(out), cap)
+        assert n == cap
+        return out
+
     # ---- measurement ----------------------------------------------------------------------------
     def ffma_peak(self, iters=4096):
         t, ms = C.c_double(0), C.c_double(0)

@@ -1,0 +1,110 @@
+"""GPU parity: the RRT-Connect driver, shortcutter and path interpolation against the CPU oracle
+under the same injected random stream (seeded Philox)."""
+import numpy as np
+import pytest
+
+import nao_wholebody_planning_b200 as nwb
+import oracle_lib as OL
+
+pytestmark = pytest.mark.gpu
+W_APPROACH = np.ones(21)
+W_APPROACH[15] = 0.0
+
+
+def queries(n, seed):
+    rng = np.random.default_rng(seed)
+    db = OL.golden_db()
+    sol = OL.load_dat(OL.GOLDEN / "solutions" / "solution_path_first.dat")
+    starts = np.tile(sol[0], (n, 1))                      # crouched init pose (EXE:323-343)
+    goals = db[rng.integers(0, len(db), n)]
+    starts[n // 2:] = db[rng.integers(0, len(db), n - n // 2)]
+    return starts, goals, db
+
+
+def compare(ctx, oracle, starts, goals, db, seeds, boxes=None, max_iter=300):
+    res, paths = ctx.solveQuery(starts, goals, db, seeds, W_APPROACH, max_iter=max_iter, step=0.1)
+    n_same = 0
+    for k in range(len(starts)):
+        oraw, ost = oracle.solve_query(starts[k], goals[k], db, W_APPROACH, int(seeds[k]), max_iter=max_iter, step=0.1, boxes=boxes)
+        same = (res[k]["success"] == ost["success"] and res[k]["iterations"] == ost["iterations"] and
+                res[k]["num_nodes_generated"] == ost["num_nodes"] and len(paths[k]) == len(oraw))
+        if same and len(oraw):
+            same = np.abs(paths[k] - oraw).max() < 1e-7
+        n_same += same
+    return res, paths, n_same
+
+
+def test_solve_query_batch_matches_oracle_empty_scene(oracle):
+    starts, goals, db = queries(48, 1)
+    seeds = np.arange(20121100, 20121100 + 48, dtype=np.uint64)
+    with nwb.Context() as ctx:
+        res, paths, n_same = compare(ctx, oracle, starts, goals, db, seeds)
+    assert n_same == 48                                           # identical trees, iterations and raw paths
+    # ~3 % of the shipped rows are unstable under the authored mass table: those queries are rejected
+    # by setStartGoalConfigs on both sides; every other query is solved
+    assert all(bool(r["success"]) == bool(r["start_valid"] and r["goal_valid"]) for r in res)
+    assert sum(r["success"] for r in res) >= 40
+    for k, p in enumerate(paths):
+        if res[k]["success"]:
+            assert np.allclose(p[0], starts[k]) and np.allclose(p[-1], goals[k])
+
+
+def test_solve_query_with_obstacles_needs_several_iterations(oracle):
+    boxes = OL.scene_boxes("S3")                                  # beam + cabinet in front of the robot
+    starts, goals, db = queries(32, 2)
+    with nwb.Context() as ctx:
+        ctx.scene_add_boxes(boxes)
+        v_s, _, _ = ctx.isFeasible(starts)
+        v_g, _, _ = ctx.isFeasible(goals)
+        seeds = np.arange(7, 7 + 32, dtype=np.uint64)
+        res, paths, n_same = compare(ctx, oracle, starts, goals, db, seeds, boxes=boxes)
+    # a boundary-band validity flip makes a query diverge from the oracle: tolerate a couple
+    assert n_same >= 30, n_same
+    for k, r in enumerate(res):
+        assert r["start_valid"] == v_s[k] and r["goal_valid"] == v_g[k]
+        if not (v_s[k] and v_g[k]):
+            assert not r["success"] and r["iterations"] == 0
+    assert max(r["iterations"] for r in res) > 1
+
+
+def test_invalid_start_is_rejected(oracle):
+    db = OL.golden_db()
+    bad = OL.uniform_configs(200, seed=3)
+    valid, _, _ = oracle.is_feasible(bad)
+    bad = bad[valid == 0][:4]
+    with nwb.Context() as ctx:
+        res, paths = ctx.solveQuery(bad, db[:4], db, np.arange(4, dtype=np.uint64), W_APPROACH, max_iter=10)
+    assert all(not r["success"] and not r["start_valid"] and r["iterations"] == 0 for r in res)
+
+
+def test_quirk_c3_index_floor(oracle):
+    with nwb.Context(quirks=nwb._abi.QUIRK_SIGNED_FOOT_ERROR) as ctx:        # C3 off: floor(U*n)
+        starts, goals, db = queries(8, 4)
+        seeds = np.arange(100, 108, dtype=np.uint64)
+        res, paths = ctx.solveQuery(starts, goals, db, seeds, W_APPROACH, max_iter=50)
+    p = OL.default_params(quirks=nwb._abi.QUIRK_SIGNED_FOOT_ERROR)
+    for k in range(8):
+        oraw, ost = oracle.solve_query(starts[k], goals[k], db, W_APPROACH, int(seeds[k]), max_iter=50, params=p)
+        assert res[k]["iterations"] == ost["iterations"] and len(paths[k]) == len(oraw)
+
+
+def test_shortcutter_and_interpolation_match_oracle(oracle):
+    boxes = OL.scene_boxes("S3")
+    starts, goals, db = queries(12, 5)
+    with nwb.Context() as ctx:
+        ctx.scene_add_boxes(boxes)
+        res, paths = ctx.solveQuery(starts, goals, db, np.arange(12, dtype=np.uint64) + 50, W_APPROACH, max_iter=300)
+        n_checked = 0
+        for k, raw in enumerate(paths):
+            if not res[k]["success"]:
+                continue
+            short, edges = ctx.shortcut_path(raw)
+            oshort, oedges = oracle.shortcut_path(raw, boxes=boxes)
+            assert (short is None) == (oshort is None)
+            if short is not None:
+                assert len(short) == len(oshort) and np.abs(short - oshort).max() == 0 and edges == oedges
+                dense = ctx.interpolate_path(short, 100)
+                assert np.abs(dense - oracle.interpolate_short_path(short, 100)).max() < 1e-15
+                assert len(dense) == (len(short) - 1) * 101 + 1
+                n_checked += 1
+        assert n_checked >= 6
