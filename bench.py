@@ -102,7 +102,7 @@ class ClockSampler:
 
 
 def cpu_baseline(q, seconds=12.0, threads=1):
-    """Time the CPU oracle on a bounded prefix of the same batch (about `seconds` of CPU work)."""
+    """Time the CPU oracle on a bounded sample of the same batch (about `seconds` of CPU work)."""
     import oracle_lib as OL
     orc = OL.Oracle()
     probe = 20000
@@ -110,12 +110,15 @@ def cpu_baseline(q, seconds=12.0, threads=1):
     orc.is_feasible(q[:probe], threads=threads)
     rate = probe / (time.perf_counter() - t0)
     n = int(min(len(q), max(probe, rate * seconds)))
+    done, dt, valid = 0, 0.0, None
     t0 = time.perf_counter()
-    valid, _, _ = orc.is_feasible(q[:n], threads=threads)
-    dt = time.perf_counter() - t0
-    return {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"first {n} configurations of the same batch, {dt:.1f} s, oracle/ (fp64 C++ restatement; "
-                      f"the reference itself needs ROS/MoveIt/FCL/KDL and cannot be built here)"}, valid, n
+    while dt < seconds * 0.8:                      # whole passes over the first n configurations
+        valid, _, _ = orc.is_feasible(q[:n], threads=threads)
+        done += n
+        dt = time.perf_counter() - t0
+    return {"value": done / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{done // n} pass(es) over the first {n} configurations of the same batch, {dt:.1f} s, oracle/ "
+                      f"(fp64 C++ restatement; the reference itself needs ROS/MoveIt/FCL/KDL and cannot be built here)"}, valid, n
 
 
 def run_reference(args, rank, world):
@@ -189,15 +192,33 @@ def main():
 
     with torch.cuda.stream(stream):
         q_dev = torch.from_numpy(q_host).to(dev)                       # [n,21] f64, resident in HBM
-        valid = torch.empty(n, dtype=torch.uint8, device=dev)
+        valid2 = [torch.empty(n, dtype=torch.uint8, device=dev) for _ in range(2)]   # double-buffered verdicts
         reason = torch.empty(n, dtype=torch.uint8, device=dev)
-        gathered = torch.empty(n * world, dtype=torch.uint8, device=dev) if world > 1 else None
+        gathered = [torch.empty(n * world, dtype=torch.uint8, device=dev) for _ in range(2)] if world > 1 else None
     stream.synchronize()
+    valid = valid2[0]
+    comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
+    pending = [None, None]
+    step_no = [0]
 
     def step():
-        ctx.is_feasible_dev(q_dev.data_ptr(), nwb.F64, n, valid.data_ptr(), reason.data_ptr())
+        """One pass of the hot path over this rank's shard; at N > 1 the 1 B/config verdicts are then
+        all-gathered over NCCL on a side stream, overlapping the next step's kernel (the verdict buffer
+        is double-buffered; a buffer is reused only after its gather completed)."""
+        b = step_no[0] & 1
+        step_no[0] += 1
+        if world > 1 and pending[b] is not None:
+            stream.wait_event(pending[b])                # gather that read valid2[b] two steps ago is done
+        ctx.is_feasible_dev(q_dev.data_ptr(), nwb.F64, n, valid2[b].data_ptr(), reason.data_ptr())
         if world > 1:
-            dist.all_gather_into_tensor(gathered, valid)
+            done = torch.cuda.Event()
+            done.record(stream)
+            with torch.cuda.stream(comm_stream):
+                comm_stream.wait_event(done)
+                dist.all_gather_into_tensor(gathered[b], valid2[b])
+                ev = torch.cuda.Event()
+                ev.record(comm_stream)
+            pending[b] = ev
 
     def barrier():
         if world > 1:
@@ -219,6 +240,10 @@ def main():
         ev[0].record(stream)
         for k in range(args.steps):
             step()
+            if k == args.steps - 1:                     # the timed region ends when the last gather has landed
+                for e in pending:
+                    if e is not None:
+                        stream.wait_event(e)
             ev[k + 1].record(stream)
         barrier()
         # keep the GPU busy a little longer so the clock sampler sees the loaded state
@@ -243,7 +268,7 @@ def main():
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             for _ in range(args.steps):
-                ctx.is_feasible_dev(q_dev.data_ptr(), nwb.F64, n, valid.data_ptr(), reason.data_ptr())
+                ctx.is_feasible_dev(q_dev.data_ptr(), nwb.F64, n, valid2[0].data_ptr(), reason.data_ptr())
             e1.record(stream)
             torch.cuda.synchronize(dev)
             kern_ms = e0.elapsed_time(e1) / args.steps
