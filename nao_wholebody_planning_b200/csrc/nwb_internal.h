@@ -74,6 +74,7 @@ struct Ctx {
   void* d_plan = nullptr; size_t d_plan_bytes = 0;     // scratch of the planner operators
   double last_ms = 0;
   int64_t last_launches = 0;
+  int64_t last_nn_passes = 0;        // passes over the node array of the last nearest-neighbour call
   int sm_count = 0;
   bool force_table_pairs = false;   // NWB_FORCE_TABLE_PAIRS=1: use the table-driven pair loops (A/B measurements)
 };

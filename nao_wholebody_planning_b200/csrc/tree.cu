@@ -27,7 +27,6 @@
 namespace nwb {
 
 constexpr int NN_THREADS = 256;
-constexpr int NN_QT = 4;          // queries per pass over the nodes (registers: 4 x {best, idx, threshold})
 
 __global__ void tree_append_kernel(const double* __restrict__ src, const int32_t* __restrict__ pred_src, int64_t n,
                                    float* __restrict__ soa, double* __restrict__ aos, int32_t* __restrict__ pred,
@@ -48,67 +47,212 @@ __device__ __forceinline__ bool lex_less(double da, int ia, double db, int ib) {
   return (da < db) || (da == db && (unsigned)ia < (unsigned)ib);
 }
 
-// one pass over the nodes for NN_QT queries; writes one (dist, idx) partial per (query, block)
-__global__ void __launch_bounds__(NN_THREADS)
+// fp32 error bound of the scan: if node m has the smallest fp32 squared distance s_m, the exactly
+// nearest node w satisfies s_w <= s_m + 2 e(s_m) with e(s) = 1.2e-5 sqrt(s) + 3e-6 s + 1e-10: inputs
+// rounded to fp32 (|q| <= pi per joint: 2 * 2^-24 * pi * sqrt(21) * d) plus 21 fma roundings (relative
+// 21 * 2^-24 of s).  Only nodes under that bound are re-evaluated exactly.
+__device__ __forceinline__ float nn_candidate_bound(float m) {
+  return (m + 2.4e-5f * sqrtf(m) + 6e-6f * m + 2e-10f) * (1.0f + 1e-6f);
+}
+
+// ---- TMA bulk-copy helpers (cp.async.bulk 1-D, completion on an mbarrier) -------------------------
+__device__ __forceinline__ uint32_t nn_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void nn_mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(nn_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void nn_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(nn_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void nn_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "NNWAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra NNDONE_%=;\n"
+      "bra NNWAIT_%=;\n"
+      "NNDONE_%=:\n"
+      "}\n" ::"r"(nn_smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void nn_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(nn_smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(nn_smem_u32(bar))
+               : "memory");
+}
+
+constexpr int NN_TILE = 512;      // nodes per tile: 21 rows x 2 KB = 43 KB per stage
+constexpr int NN_STAGES = 4;      // 172 KB of shared memory: one persistent CTA per SM
+
+// one pass over the nodes for NN_QT queries; writes one (dist, idx) partial per (query, block).
+// Persistent CTAs (one per SM) stream the 21 SoA rows of their tiles through a 4-stage shared-memory
+// ring with TMA bulk copies (UBLKCP, mbarrier complete_tx), so ~130 KB of loads are in flight per SM
+// while the threads compute on the stage that has landed.  Per tile the block first agrees on the
+// running fp32 minimum per query (warp shuffle + shared atomicMin on the float bits), then only the
+// nodes within the error bound of that minimum take the exact fp64 path.
+template <int QT>
+__global__ void __launch_bounds__(NN_THREADS, 1)
 nn_scan_kernel(const float* __restrict__ soa, const double* __restrict__ aos, int64_t cap, int64_t N,
                const double* __restrict__ q, int64_t nq, double* __restrict__ part_d, int32_t* __restrict__ part_i) {
-  __shared__ double qd[NN_QT][NWB_NJ];
-  __shared__ float qf[NN_QT][NWB_NJ];
-  __shared__ double red_d[NN_QT][NN_THREADS / 32];
-  __shared__ int red_i[NN_QT][NN_THREADS / 32];
+  extern __shared__ __align__(128) unsigned char nn_smem[];
+  float* ring = reinterpret_cast<float*>(nn_smem);                           // [NN_STAGES][21][NN_TILE]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(nn_smem + sizeof(float) * NN_STAGES * NWB_NJ * NN_TILE);
+  __shared__ double qd[QT][NWB_NJ];
+  __shared__ float qf[QT][NWB_NJ];
+  __shared__ unsigned run_min[QT];                    // running fp32 minimum of the block (float bits, s >= 0)
+  __shared__ double red_d[QT][NN_THREADS / 32];
+  __shared__ int red_i[QT][NN_THREADS / 32];
+  __shared__ int overflow;                            // some thread saw more than two candidates for a query
   const int tid = threadIdx.x;
-  const int64_t q0 = (int64_t)blockIdx.y * NN_QT;
-  for (int e = tid; e < NN_QT * NWB_NJ; e += NN_THREADS) {
+  const int64_t q0 = (int64_t)blockIdx.y * QT;
+  for (int e = tid; e < QT * NWB_NJ; e += NN_THREADS) {
     int k = e / NWB_NJ, j = e % NWB_NJ;
     double v = (q0 + k < nq) ? q[(q0 + k) * NWB_NJ + j] : 0.0;
     qd[k][j] = v;
     qf[k][j] = (float)v;
   }
+  if (tid < QT) run_min[tid] = 0x7f7fffffu;           // FLT_MAX
+  if (tid == 0) {
+    overflow = 0;
+    for (int sg = 0; sg < NN_STAGES; ++sg) nn_mbar_init(&bars[sg], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
 
-  double best[NN_QT];
-  int besti[NN_QT];
-  float thr[NN_QT];
+  const int64_t tiles = (N + NN_TILE - 1) / NN_TILE;
+  auto issue = [&](int64_t tile, int stage) {          // thread 0: 21 row copies of one tile
+    const int64_t n0 = tile * NN_TILE;
+    const int64_t cnt = min((int64_t)NN_TILE, ((N - n0) + 3) & ~(int64_t)3);   // rows are padded to 64 nodes
+    const uint32_t bytes = (uint32_t)(cnt * sizeof(float));
+    nn_mbar_expect_tx(&bars[stage], bytes * NWB_NJ);
+    float* dst = ring + (size_t)stage * NWB_NJ * NN_TILE;
+    for (int j = 0; j < NWB_NJ; ++j) nn_bulk_g2s(dst + j * NN_TILE, soa + (int64_t)j * cap + n0, bytes, &bars[stage]);
+  };
+  if (tid == 0)
+    for (int sg = 0; sg < NN_STAGES; ++sg) {
+      const int64_t t = (int64_t)blockIdx.x + (int64_t)sg * gridDim.x;
+      if (t < tiles) issue(t, sg);
+    }
+
+  // Each thread keeps its two best fp32 candidates per query; the exact fp64 evaluation is deferred
+  // to the end of the scan so that no tile waits on the long-latency exact path.
+  float cs[QT][2];
+  int ci[QT][2];
+  bool ovf = false;
 #pragma unroll
-  for (int k = 0; k < NN_QT; ++k) {
-    best[k] = 10000.0;       // RP:347
-    besti[k] = -1;
-    thr[k] = 3.0e38f;
+  for (int k = 0; k < QT; ++k) {
+    cs[k][0] = cs[k][1] = 3.0e38f;
+    ci[k][0] = ci[k][1] = -1;
   }
-  for (int64_t node = (int64_t)blockIdx.x * NN_THREADS + tid; node < N; node += (int64_t)gridDim.x * NN_THREADS) {
-    float x[NWB_NJ];
+  uint32_t phase = 0;
+  int stage = 0;
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    nn_mbar_wait(&bars[stage], phase);
+    const float* x = ring + (size_t)stage * NWB_NJ * NN_TILE;
+    const int64_t n0 = tile * NN_TILE;
+    float s[QT][2];
 #pragma unroll
-    for (int j = 0; j < NWB_NJ; ++j) x[j] = __ldg(soa + (int64_t)j * cap + node);   // 21 loads in flight
+    for (int k = 0; k < QT; ++k) s[k][0] = s[k][1] = 0.f;
 #pragma unroll
-    for (int k = 0; k < NN_QT; ++k) {
-      float s = 0.f;
+    for (int j = 0; j < NWB_NJ; ++j) {
+      const float x0 = x[j * NN_TILE + tid], x1 = x[j * NN_TILE + tid + NN_THREADS];
 #pragma unroll
-      for (int j = 0; j < NWB_NJ; ++j) {
-        float d = qf[k][j] - x[j];
-        s = fmaf(d, d, s);
-      }
-      if (s <= thr[k]) {     // rare: within the fp32 error bound of this thread's running minimum
-        double sum = 0.0;
-        const double* row = aos + node * NWB_NJ;
-        for (int j = 0; j < NWB_NJ; ++j) {
-          double d = __dsub_rn(qd[k][j], row[j]);
-          sum = __dadd_rn(sum, __dmul_rn(d, d));      // RP:369: separately rounded multiply and add
-        }
-        double dn = sqrt(sum);                        // RP:373
-        if (dn < best[k]) {                           // RP:377 strict
-          best[k] = dn;
-          besti[k] = (int)node;
-        }
-        // any node whose exact distance can still be < best has fp32 s below this bound
-        double b = best[k];
-        thr[k] = __double2float_ru((b * b + 1.2e-5 * b + 1e-10) * (1.0 + 1e-6));
+      for (int k = 0; k < QT; ++k) {
+        const float c = qf[k][j];
+        const float d0 = c - x0, d1 = c - x1;
+        s[k][0] = fmaf(d0, d0, s[k][0]);
+        s[k][1] = fmaf(d1, d1, s[k][1]);
       }
     }
+    const bool live0 = n0 + tid < N, live1 = n0 + tid + NN_THREADS < N;
+#pragma unroll
+    for (int k = 0; k < QT; ++k) {
+      if (!live0) s[k][0] = 3.0e38f;
+      if (!live1) s[k][1] = 3.0e38f;
+      float m = fminf(s[k][0], s[k][1]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if ((tid & 31) == 0) atomicMin(&run_min[k], __float_as_uint(m));
+    }
+    __syncthreads();                                    // the stage is consumed and run_min is current
+    if (tid == 0) {                                     // refill this stage with the tile NN_STAGES rounds ahead
+      const int64_t nt = tile + (int64_t)NN_STAGES * gridDim.x;
+      if (nt < tiles) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue(nt, stage);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < QT; ++k) {
+      const float bound = nn_candidate_bound(__uint_as_float(run_min[k]));
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const float v = s[k][u];
+        if (v <= bound) {                               // candidate (nodes arrive in ascending index per thread)
+          const int node = (int)(n0 + tid + u * NN_THREADS);
+          if (v < cs[k][0]) { cs[k][1] = cs[k][0]; ci[k][1] = ci[k][0]; cs[k][0] = v; ci[k][0] = node; }
+          else if (v < cs[k][1]) { cs[k][1] = v; ci[k][1] = node; }
+          else ovf = true;                              // a third candidate: resolved by the exact rescan below
+        }
+      }
+    }
+    if (++stage == NN_STAGES) { stage = 0; phase ^= 1u; }
+  }
+  if (ovf) overflow = 1;
+  __syncthreads();
+
+  double best[QT];
+  int besti[QT];
+#pragma unroll
+  for (int k = 0; k < QT; ++k) {
+    best[k] = 10000.0;       // RP:347
+    besti[k] = -1;
+  }
+  auto exact = [&](int k, int64_t node) {               // the reference's arithmetic: RP:361-377
+    const double* row = aos + node * NWB_NJ;
+    double r[NWB_NJ];
+#pragma unroll
+    for (int j = 0; j < NWB_NJ; ++j) r[j] = row[j];     // all 21 loads in flight
+    double sum = 0.0;
+#pragma unroll
+    for (int j = 0; j < NWB_NJ; ++j) {
+      double d = __dsub_rn(qd[k][j], r[j]);
+      sum = __dadd_rn(sum, __dmul_rn(d, d));            // separately rounded multiply and add
+    }
+    double dn = sqrt(sum);
+    if (dn < best[k] || (dn == best[k] && (unsigned)node < (unsigned)besti[k])) {   // first strict minimum in index order
+      best[k] = dn;
+      besti[k] = (int)node;
+    }
+  };
+  if (!overflow) {
+#pragma unroll
+    for (int k = 0; k < QT; ++k) {
+      const float bound = nn_candidate_bound(__uint_as_float(run_min[k]));
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+        if (ci[k][u] >= 0 && cs[k][u] <= bound) exact(k, ci[k][u]);
+    }
+  } else {
+    // pathological input (three or more near-ties in one thread): rescan this block's tiles from global
+    // memory and take the exact path for every node under the final bound
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x)
+      for (int u = 0; u < 2; ++u) {
+        const int64_t node = tile * NN_TILE + tid + u * NN_THREADS;
+        if (node >= N) continue;
+        for (int k = 0; k < QT; ++k) {
+          float sv = 0.f;
+          for (int j = 0; j < NWB_NJ; ++j) {
+            float d = qf[k][j] - soa[(int64_t)j * cap + node];
+            sv = fmaf(d, d, sv);
+          }
+          if (sv <= nn_candidate_bound(__uint_as_float(run_min[k]))) exact(k, node);
+        }
+      }
   }
   // block reduction per query
   const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
-  for (int k = 0; k < NN_QT; ++k) {
+  for (int k = 0; k < QT; ++k) {
     double d = best[k];
     int i = besti[k];
 #pragma unroll
@@ -120,7 +264,7 @@ nn_scan_kernel(const float* __restrict__ soa, const double* __restrict__ aos, in
     if (lane == 0) { red_d[k][warp] = d; red_i[k][warp] = i; }
   }
   __syncthreads();
-  if (tid < NN_QT) {
+  if (tid < QT) {
     double d = red_d[tid][0];
     int i = red_i[tid][0];
     for (int w = 1; w < NN_THREADS / 32; ++w)
@@ -213,8 +357,8 @@ int stage_reserve(nwb_tree* t, size_t bytes) {
 }
 
 int nn_grid_blocks(const nwb_tree* t) {
-  int64_t want = (t->size + NN_THREADS - 1) / NN_THREADS;
-  int64_t cap = (int64_t)t->ctx->sm_count * 8;     // 8 resident blocks of 256 threads per SM
+  int64_t want = (t->size + NN_TILE - 1) / NN_TILE;
+  int64_t cap = (int64_t)t->ctx->sm_count;                             // persistent: one CTA per SM
   return (int)std::max<int64_t>(1, std::min(want, cap));
 }
 
@@ -232,19 +376,33 @@ int nn_launch(nwb_tree* t, const double* q_dev, int64_t nq, int32_t* idx_dev, do
     t->part_cap = need;
   }
   cudaStream_t s = t->ctx->stream;
+  constexpr size_t kNnSmem = sizeof(float) * NN_STAGES * NWB_NJ * NN_TILE + 8 * NN_STAGES;
+  static bool configured = false;
+  if (!configured) {
+    TREE_CUDA(t, cudaFuncSetAttribute(nn_scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNnSmem));
+    TREE_CUDA(t, cudaFuncSetAttribute(nn_scan_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNnSmem));
+    configured = true;
+  }
   TREE_CUDA(t, cudaEventRecord(t->ctx->ev0, s));
-  const int64_t qtiles = (nq + NN_QT - 1) / NN_QT;
+  // one query (the RRT loop): minimum arithmetic per tile; batches: 8 queries share each pass over the nodes
+  const int QT = nq == 1 ? 1 : 8;
+  const int64_t qtiles = (nq + QT - 1) / QT;
   for (int64_t y0 = 0; y0 < qtiles; y0 += 65535) {       // gridDim.y limit
     const int64_t ny = std::min<int64_t>(65535, qtiles - y0);
-    const int64_t qoff = y0 * NN_QT;
-    nn_scan_kernel<<<dim3(nb, (unsigned)ny), NN_THREADS, 0, s>>>(t->soa, t->aos, t->cap, t->size, q_dev + qoff * NWB_NJ,
-                                                                  nq - qoff, t->part_d + qoff * nb, t->part_i + qoff * nb);
+    const int64_t qoff = y0 * QT;
+    if (QT == 1)
+      nn_scan_kernel<1><<<dim3(nb, (unsigned)ny), NN_THREADS, kNnSmem, s>>>(t->soa, t->aos, t->cap, t->size, q_dev + qoff * NWB_NJ,
+                                                                            nq - qoff, t->part_d + qoff * nb, t->part_i + qoff * nb);
+    else
+      nn_scan_kernel<8><<<dim3(nb, (unsigned)ny), NN_THREADS, kNnSmem, s>>>(t->soa, t->aos, t->cap, t->size, q_dev + qoff * NWB_NJ,
+                                                                            nq - qoff, t->part_d + qoff * nb, t->part_i + qoff * nb);
   }
   nn_final_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, s>>>(t->part_d, t->part_i, nb, nq, idx_dev, dist_dev);
   TREE_CUDA(t, cudaGetLastError());
   TREE_CUDA(t, cudaEventRecord(t->ctx->ev1, s));
   t->ctx->last_ms = -1;
   t->ctx->last_launches = (qtiles + 65534) / 65535 + 1;
+  t->ctx->last_nn_passes = qtiles;
   return NWB_OK;
 }
 }  // namespace
