@@ -196,7 +196,7 @@ def main():
     for scene in ("S0", "S3"):
         c2 = nwb.Context()
         c2.scene_add_boxes(OL.scene_boxes(scene))
-        c2.solveQuery(starts[:8], goals[:8], db, seeds[:8], w, max_iter=500)        # warm-up
+        c2.solveQuery(starts, goals, db, seeds, w, max_iter=500)                   # warm-up (allocates the forest)
         t0 = time.perf_counter()
         res, paths = c2.solveQuery(starts, goals, db, seeds, w, max_iter=500, step=0.1)
         dt = time.perf_counter() - t0

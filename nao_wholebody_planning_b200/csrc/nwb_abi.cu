@@ -133,6 +133,9 @@ void nwb_ctx_destroy(nwb_ctx* ctx) {
   if (ctx->d_in) cudaFree(ctx->d_in);
   if (ctx->d_out) cudaFree(ctx->d_out);
   if (ctx->d_plan) cudaFree(ctx->d_plan);
+  if (ctx->d_forest) cudaFree(ctx->d_forest);
+  if (ctx->d_rrt) cudaFree(ctx->d_rrt);
+  if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);

@@ -72,6 +72,9 @@ struct Ctx {
   void* d_out = nullptr; size_t d_out_bytes = 0;
   void* h_stage = nullptr; size_t h_stage_bytes = 0;   // pinned staging for pageable callers
   void* d_plan = nullptr; size_t d_plan_bytes = 0;     // scratch of the planner operators
+  void* d_forest = nullptr; size_t d_forest_bytes = 0; // pooled forest of the RRT driver (grow-only)
+  void* d_rrt = nullptr; size_t d_rrt_bytes = 0;       // control state / staging of the RRT driver (grow-only)
+  int32_t* h_flag = nullptr;                           // pinned word the RRT driver polls
   double last_ms = 0;
   int64_t last_launches = 0;
   int64_t last_nn_passes = 0;        // passes over the node array of the last nearest-neighbour call
@@ -87,8 +90,37 @@ cudaError_t launch_validity(const ValidityTables& tab, const void* q, int dtype,
 cudaError_t launch_fk(const void* q, int dtype, int64_t n, double* poses, double* com, cudaStream_t stream);
 cudaError_t launch_ffma_peak(int sm_count, int iters, float* sink, cudaStream_t stream, double* flops_out);
 
+// Pooled forest of the RRT driver: 2 trees per query, fixed capacity each (device pointers).
+//   soa float [T][21][cap] | aos double [T][cap][21] | pred int32 [T][cap] | size int32 [T]
+struct ForestView {
+  float* soa;
+  double* aos;
+  int32_t* pred;
+  int32_t* size;
+  int64_t cap;
+};
+// Per-query control state of the lock-step RRT-Connect driver (device arrays of length nq).
+struct RrtState {
+  uint8_t* active;      // query still searching
+  uint8_t* swap;        // 0: extend the start tree this iteration, 1: the goal tree (RP:1073,1136)
+  uint8_t* walking;     // the extend step succeeded: the other tree runs connectTree this iteration
+  int32_t* iterations;
+  int32_t* success;
+  int32_t* connector;   // 1: goal tree connected to start tree, 2: the reverse (RP:1101,1161)
+  int32_t* bridge;      // q_near.index of the connecting walk (RP:1000-1001)
+  int32_t* tree_a;      // tree extended this iteration
+  int32_t* tree_b;      // tree that tries to connect
+  int32_t* idx_b;       // nearest neighbour of q_connect in tree_b
+  double* q_connect;    // node just added to tree_a
+  double* cstart;       // configuration of that nearest neighbour
+  int32_t* n_active;    // [1]
+  int32_t* overflow;    // [1] a tree outgrew its capacity
+};
+
 // planner kernels (planner_kernels.cu); all pointers are device pointers
 struct PlanConst;
+cudaError_t launch_connect_forest(const PlanConst& pc, const ValidityTables& tab, bool static_pairs, ForestView F, RrtState S,
+                                  int nq, cudaStream_t s);
 cudaError_t launch_steer_project(const PlanConst& pc, const double* q_near, const double* q_target, int64_t n, double* q_out,
                                  int32_t* status, int32_t* ds_status, int32_t* iters, cudaStream_t s);
 cudaError_t launch_connect(const PlanConst& pc, const ValidityTables& tab, bool static_pairs, const double* q_start,

@@ -99,6 +99,66 @@ connect_kernel(const __grid_constant__ PlanConst pc, const __grid_constant__ Val
   status[e] = (state == NWB_ADVANCED) ? -1 : state;     // -1: step budget exhausted before REACHED / TRAPPED
 }
 
+// ---- connect inside the pooled forest (RRT driver): one thread per query --------------------------------
+// Same walk as connect_kernel, but the nodes go straight into tree_b of the query's forest slot and the
+// end-of-iteration bookkeeping (success / connector / bridge node, tree swap, active count) happens on
+// the device, so the host never has to synchronise inside an RRT iteration.
+template <bool STATIC>
+__global__ void __launch_bounds__(32)
+connect_forest_kernel(const __grid_constant__ PlanConst pc, const __grid_constant__ ValidityTables tab, ForestView F, RrtState S,
+                      int nq) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nq || !S.active[k]) return;
+  if (S.walking[k]) {
+    const int t = S.tree_b[k];
+    float* soa = F.soa + (size_t)t * NWB_NJ * F.cap;
+    double* aos = F.aos + (size_t)t * F.cap * NWB_NJ;
+    int32_t* pred = F.pred + (size_t)t * F.cap;
+    int size = F.size[t];
+    double cur[NWB_NJ], tgt[NWB_NJ], q[NWB_NJ];
+    for (int j = 0; j < NWB_NJ; ++j) {
+      cur[j] = S.cstart[(size_t)k * NWB_NJ + j];
+      tgt[j] = S.q_connect[(size_t)k * NWB_NJ + j];
+    }
+    int cur_idx = S.idx_b[k];
+    int state = NWB_ADVANCED;
+    while (state == NWB_ADVANCED) {
+      state = generate_q_new(cur, tgt, pc, q);
+      int ds = enforce_ds_constraints(q, pc, nullptr);
+      if (ds == NWB_TRAPPED) { state = NWB_TRAPPED; break; }
+      if (ds == NWB_ADVANCED) state = NWB_ADVANCED;
+      ValidityResult<float> r = eval_one<false, STATIC>(tab, q);
+      if (r.hit || !r.stable) { state = NWB_TRAPPED; break; }
+      if (size >= F.cap) {                       // tree full: give the query up and report it
+        atomicExch(S.overflow, 1);
+        state = -1;
+        break;
+      }
+      for (int j = 0; j < NWB_NJ; ++j) {         // addConfigtoTree (RP:749-783)
+        aos[(size_t)size * NWB_NJ + j] = q[j];
+        soa[(size_t)j * F.cap + size] = (float)q[j];
+      }
+      pred[size] = cur_idx;
+      if (state == NWB_REACHED) {
+        S.bridge[k] = cur_idx;                   // q_near = current_q_near (RP:1000-1001)
+      } else {
+        cur_idx = size;                          // current_q_near = tree.nodes.back() (RP:1004)
+        for (int j = 0; j < NWB_NJ; ++j) cur[j] = q[j];
+      }
+      ++size;
+    }
+    F.size[t] = size;
+    if (state == NWB_REACHED || state == -1) {
+      S.success[k] = state == NWB_REACHED;
+      S.connector[k] = S.swap[k] ? 2 : 1;
+      S.active[k] = 0;
+      atomicSub(S.n_active, 1);
+      return;
+    }
+  }
+  S.swap[k] ^= 1;                                // trees swap every iteration regardless of outcome (RP:1125-1192)
+}
+
 // ---- edge check: (edge, way-point) -> collision-only validity ------------------------------------------
 template <bool STATIC>
 __global__ void __launch_bounds__(128)
@@ -195,6 +255,15 @@ cudaError_t launch_connect(const PlanConst& pc, const ValidityTables& tab, bool 
   unsigned blocks = (unsigned)((n_edges + 63) / 64);
   if (static_pairs) connect_kernel<true><<<blocks, 64, 0, s>>>(pc, tab, q_start, q_connect, n_edges, max_steps, nodes_out, n_added, status);
   else connect_kernel<false><<<blocks, 64, 0, s>>>(pc, tab, q_start, q_connect, n_edges, max_steps, nodes_out, n_added, status);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_connect_forest(const PlanConst& pc, const ValidityTables& tab, bool static_pairs, ForestView F, RrtState S,
+                                  int nq, cudaStream_t s) {
+  if (nq <= 0) return cudaSuccess;
+  unsigned blocks = (unsigned)((nq + 31) / 32);
+  if (static_pairs) connect_forest_kernel<true><<<blocks, 32, 0, s>>>(pc, tab, F, S, nq);
+  else connect_forest_kernel<false><<<blocks, 32, 0, s>>>(pc, tab, F, S, nq);
   return cudaGetLastError();
 }
 

@@ -7,9 +7,10 @@
 // query is one pass of
 //     random DB row -> nearest neighbour -> steer -> double-support projection -> validity -> append
 //     -> nearest neighbour in the other tree -> connect walk -> append -> swap
-// where each arrow is one kernel over all queries.  The host only keeps the control flow (which
-// queries are active, which tree is which); every distance, IK step and validity test runs on the
-// device.  A single query is the nq = 1 case (latency bound: RRT-Connect is serial by construction,
+// where each arrow is one kernel over all queries.  The control state (which queries are active,
+// which tree extends, success / bridge nodes) lives on the device too, so an iteration is seven
+// kernel launches with NO host synchronisation; the host only reads the active-query count every
+// few iterations.  A single query is the nq = 1 case (latency bound: RRT-Connect is serial by construction,
 // SURVEY.md section 8e "a single RRT query: replicas only").
 //
 // Trees live in one pooled forest (2 trees per query, fixed capacity each):
@@ -26,23 +27,17 @@
 namespace nwb {
 void make_plan_const(const nwb_ctx* ctx, const double* weights, double step, PlanConst& pc);
 
-struct ForestView {
-  float* soa;
-  double* aos;
-  int32_t* pred;
-  int32_t* size;
-  int64_t cap;
-};
-
 __device__ __forceinline__ bool lex_less2(double da, int ia, double db, int ib) {
   return (da < db) || (da == db && (unsigned)ia < (unsigned)ib);
 }
 
-// q_rand[k] = DB row floor(U * (n-1)) (quirk C3) or floor(U * n); U = Philox(seed_k; iteration)
-__global__ void rrt_random_rows_kernel(const double* __restrict__ db, int n_db, const uint64_t* __restrict__ seeds, int iteration,
-                                       unsigned quirks, int nq, double* __restrict__ q_rand) {
+// start of iteration `iteration` for every active query: which tree extends (RP:1073,1136), and
+// q_rand[k] = DB row floor(U * (n-1)) (quirk C3) or floor(U * n) with U = Philox(seed_k; iteration)
+// (getRandomStableConfig, RP:316-332, with the injected stream)
+__global__ void rrt_begin_kernel(const double* __restrict__ db, int n_db, const uint64_t* __restrict__ seeds, int iteration,
+                                 unsigned quirks, int nq, RrtState S, double* __restrict__ q_rand) {
   int k = blockIdx.x;
-  if (k >= nq) return;
+  if (k >= nq || !S.active[k]) return;
   __shared__ int row;
   if (threadIdx.x == 0) {
     uint32_t r[4];
@@ -50,6 +45,11 @@ __global__ void rrt_random_rows_kernel(const double* __restrict__ db, int n_db, 
     philox4x32_10((uint32_t)iteration, 0u, 0u, kStreamPlanner, (uint32_t)s, (uint32_t)(s >> 32), r);
     double u = u01(r[0]);
     row = (quirks & NWB_QUIRK_DB_INDEX_FLOOR) ? (int)floor(0.0 + (double)(n_db - 1 - 0) * u) : (int)floor((double)n_db * u);
+    const int sw = S.swap[k];
+    S.tree_a[k] = 2 * k + sw;
+    S.tree_b[k] = 2 * k + 1 - sw;
+    S.iterations[k] = iteration + 1;
+    S.walking[k] = 0;
   }
   __syncthreads();
   if (threadIdx.x < NWB_NJ) q_rand[k * NWB_NJ + threadIdx.x] = db[(size_t)row * NWB_NJ + threadIdx.x];
@@ -147,16 +147,35 @@ __global__ void forest_append_kernel(ForestView F, const int32_t* __restrict__ t
   }
 }
 
-// after steer/project + validity: decide which queries extend (RP:846-870) and set up the connect edges
-__global__ void rrt_extend_commit_kernel(const int32_t* __restrict__ status, const uint8_t* __restrict__ valid,
-                                         const uint8_t* __restrict__ active, int nq, int32_t* __restrict__ ext_state,
-                                         int32_t* __restrict__ ext_count) {
-  int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= nq) return;
-  int st = NWB_TRAPPED;
-  if (active[k] && status[k] != NWB_TRAPPED && valid[k]) st = status[k];
-  ext_state[k] = st;
-  ext_count[k] = (st != NWB_TRAPPED) ? 1 : 0;
+// after steer/project + validity: extendTree's decision (RP:846-870).  A surviving q_new is appended to
+// tree_a (predecessor = its nearest neighbour) and becomes q_connect of this iteration's connectTree.
+__global__ void rrt_extend_commit_kernel(ForestView F, RrtState S, const int32_t* __restrict__ status, const uint8_t* __restrict__ valid,
+                                         const int32_t* __restrict__ idx_a, const double* __restrict__ q_new, int nq) {
+  const int k = blockIdx.x;
+  if (k >= nq || !S.active[k]) return;
+  if (status[k] == NWB_TRAPPED || !valid[k]) return;        // walking stays 0: only the swap happens this iteration
+  const int t = S.tree_a[k];
+  const int base = F.size[t];
+  if (base >= F.cap) {
+    if (threadIdx.x == 0) {
+      atomicExch(S.overflow, 1);
+      S.active[k] = 0;
+      atomicSub(S.n_active, 1);
+    }
+    return;
+  }
+  if (threadIdx.x < NWB_NJ) {
+    const double v = q_new[(size_t)k * NWB_NJ + threadIdx.x];
+    F.aos[((size_t)t * F.cap + base) * NWB_NJ + threadIdx.x] = v;
+    F.soa[(size_t)t * NWB_NJ * F.cap + (size_t)threadIdx.x * F.cap + base] = (float)v;
+    S.q_connect[(size_t)k * NWB_NJ + threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    F.pred[(size_t)t * F.cap + base] = idx_a[k];
+    F.size[t] = base + 1;
+    S.walking[k] = 1;
+  }
 }
 
 }  // namespace nwb
@@ -197,187 +216,139 @@ int nwb_solve_query_batch(nwb_ctx* ctx, const double* starts, const double* goal
   cudaStream_t s = ctx->stream;
   const int Q = (int)nq, T = 2 * Q;
   const int64_t C = tree_capacity > 0 ? tree_capacity : 4096;
-  const int max_steps = 64;                                // connect nodes per launch; longer walks continue in another round
   const bool sp = ctx->params.srdf_trim != 0 && !ctx->force_table_pairs;
   PlanConst pc;
   make_plan_const(ctx, weights, step, pc);
 
-  DevBuf b_soa, b_aos, b_pred, b_size, b_db, b_seeds, b_qrand, b_near, b_qnew, b_status, b_valid, b_active, b_tree_a, b_tree_b,
-      b_idx_a, b_idx_b, b_ext_state, b_ext_count, b_first, b_overflow, b_chain, b_nadd, b_cstat, b_cstart, b_pfirst, b_sg;
+  // one device allocation for the forest, one for everything else
   const size_t qbytes = sizeof(double) * NWB_NJ * Q;
-  R_CUDA(ctx, b_soa.alloc(sizeof(float) * NWB_NJ * C * T));
-  R_CUDA(ctx, b_aos.alloc(sizeof(double) * NWB_NJ * C * T));
-  R_CUDA(ctx, b_pred.alloc(sizeof(int32_t) * C * T));
-  R_CUDA(ctx, b_size.alloc(sizeof(int32_t) * T));
-  R_CUDA(ctx, b_db.alloc(sizeof(double) * NWB_NJ * n_db));
-  R_CUDA(ctx, b_seeds.alloc(sizeof(uint64_t) * Q));
-  R_CUDA(ctx, b_qrand.alloc(qbytes));
-  R_CUDA(ctx, b_near.alloc(qbytes));
-  R_CUDA(ctx, b_qnew.alloc(qbytes));
-  R_CUDA(ctx, b_cstart.alloc(qbytes));
-  R_CUDA(ctx, b_status.alloc(sizeof(int32_t) * Q));
-  R_CUDA(ctx, b_valid.alloc(2 * (size_t)Q));
-  R_CUDA(ctx, b_active.alloc(Q));
-  R_CUDA(ctx, b_tree_a.alloc(sizeof(int32_t) * Q));
-  R_CUDA(ctx, b_tree_b.alloc(sizeof(int32_t) * Q));
-  R_CUDA(ctx, b_idx_a.alloc(sizeof(int32_t) * Q));
-  R_CUDA(ctx, b_idx_b.alloc(sizeof(int32_t) * Q));
-  R_CUDA(ctx, b_ext_state.alloc(sizeof(int32_t) * Q));
-  R_CUDA(ctx, b_ext_count.alloc(sizeof(int32_t) * Q));
-  R_CUDA(ctx, b_first.alloc(sizeof(int32_t) * Q));
-  R_CUDA(ctx, b_overflow.alloc(sizeof(int32_t)));
-  R_CUDA(ctx, b_chain.alloc(qbytes * max_steps));
-  R_CUDA(ctx, b_nadd.alloc(sizeof(int32_t) * Q));
-  R_CUDA(ctx, b_cstat.alloc(sizeof(int32_t) * Q));
-  R_CUDA(ctx, b_pfirst.alloc(sizeof(int32_t) * Q));
-  R_CUDA(ctx, b_sg.alloc(2 * qbytes));
-  ForestView F{b_soa.as<float>(), b_aos.as<double>(), b_pred.as<int32_t>(), b_size.as<int32_t>(), C};
+  auto grow = [&](void** buf, size_t* have, size_t need) -> cudaError_t {
+    if (*have >= need) return cudaSuccess;
+    if (*buf) cudaFree(*buf);
+    *buf = nullptr;
+    *have = 0;
+    cudaError_t e = cudaMalloc(buf, need);
+    if (e == cudaSuccess) *have = need;
+    return e;
+  };
+  const size_t soa_b = sizeof(float) * NWB_NJ * C * T, aos_b = sizeof(double) * NWB_NJ * C * T, pred_b = sizeof(int32_t) * C * T;
+  R_CUDA(ctx, grow(&ctx->d_forest, &ctx->d_forest_bytes, soa_b + aos_b + pred_b + 256));
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  const size_t o_size = carve(sizeof(int32_t) * T), o_db = carve(sizeof(double) * NWB_NJ * n_db), o_seeds = carve(sizeof(uint64_t) * Q),
+               o_sg = carve(2 * qbytes), o_qrand = carve(qbytes), o_near = carve(qbytes), o_qnew = carve(qbytes),
+               o_qconn = carve(qbytes), o_cstart = carve(qbytes), o_status = carve(sizeof(int32_t) * Q), o_valid = carve(2 * (size_t)Q),
+               o_active = carve(Q), o_swap = carve(Q), o_walk = carve(Q), o_iter = carve(sizeof(int32_t) * Q),
+               o_succ = carve(sizeof(int32_t) * Q), o_conn = carve(sizeof(int32_t) * Q), o_bridge = carve(sizeof(int32_t) * Q),
+               o_ta = carve(sizeof(int32_t) * Q), o_tb = carve(sizeof(int32_t) * Q), o_ia = carve(sizeof(int32_t) * Q),
+               o_ib = carve(sizeof(int32_t) * Q), o_cnt = carve(sizeof(int32_t) * T), o_roots = carve(sizeof(int32_t) * T),
+               o_zero = carve(sizeof(int32_t) * T), o_nact = carve(16), o_ovf = carve(16);
+  R_CUDA(ctx, grow(&ctx->d_rrt, &ctx->d_rrt_bytes, off));
+  R_CUDA(ctx, cudaMemsetAsync(ctx->d_rrt, 0, off, s));           // inactive slots still flow through the kernels: keep them finite
+  char* M = static_cast<char*>(ctx->d_rrt);
+  char* FB = static_cast<char*>(ctx->d_forest);
+  ForestView F{reinterpret_cast<float*>(FB), reinterpret_cast<double*>(FB + ((soa_b + 255) & ~(size_t)255)),
+               reinterpret_cast<int32_t*>(FB + ((soa_b + 255) & ~(size_t)255) + aos_b), reinterpret_cast<int32_t*>(M + o_size), C};
+  RrtState S;
+  S.active = reinterpret_cast<uint8_t*>(M + o_active);
+  S.swap = reinterpret_cast<uint8_t*>(M + o_swap);
+  S.walking = reinterpret_cast<uint8_t*>(M + o_walk);
+  S.iterations = reinterpret_cast<int32_t*>(M + o_iter);
+  S.success = reinterpret_cast<int32_t*>(M + o_succ);
+  S.connector = reinterpret_cast<int32_t*>(M + o_conn);
+  S.bridge = reinterpret_cast<int32_t*>(M + o_bridge);
+  S.tree_a = reinterpret_cast<int32_t*>(M + o_ta);
+  S.tree_b = reinterpret_cast<int32_t*>(M + o_tb);
+  S.idx_b = reinterpret_cast<int32_t*>(M + o_ib);
+  S.q_connect = reinterpret_cast<double*>(M + o_qconn);
+  S.cstart = reinterpret_cast<double*>(M + o_cstart);
+  S.n_active = reinterpret_cast<int32_t*>(M + o_nact);
+  S.overflow = reinterpret_cast<int32_t*>(M + o_ovf);
+  double* d_db = reinterpret_cast<double*>(M + o_db);
+  uint64_t* d_seeds = reinterpret_cast<uint64_t*>(M + o_seeds);
+  double* d_sg = reinterpret_cast<double*>(M + o_sg);
+  double* d_qrand = reinterpret_cast<double*>(M + o_qrand);
+  double* d_near = reinterpret_cast<double*>(M + o_near);
+  double* d_qnew = reinterpret_cast<double*>(M + o_qnew);
+  int32_t* d_status = reinterpret_cast<int32_t*>(M + o_status);
+  uint8_t* d_valid = reinterpret_cast<uint8_t*>(M + o_valid);
+  int32_t* d_idx_a = reinterpret_cast<int32_t*>(M + o_ia);
 
-  R_CUDA(ctx, cudaMemsetAsync(b_size.p, 0, sizeof(int32_t) * T, s));
-  R_CUDA(ctx, cudaMemsetAsync(b_near.p, 0, qbytes, s));       // inactive slots still flow through the kernels: keep them finite
-  R_CUDA(ctx, cudaMemsetAsync(b_qnew.p, 0, qbytes, s));
-  R_CUDA(ctx, cudaMemsetAsync(b_cstart.p, 0, qbytes, s));
-  R_CUDA(ctx, cudaMemsetAsync(b_qrand.p, 0, qbytes, s));
-  R_CUDA(ctx, cudaMemsetAsync(b_overflow.p, 0, sizeof(int32_t), s));
-  R_CUDA(ctx, cudaMemcpyAsync(b_db.p, db, sizeof(double) * NWB_NJ * n_db, cudaMemcpyHostToDevice, s));
-  R_CUDA(ctx, cudaMemcpyAsync(b_seeds.p, seeds, sizeof(uint64_t) * Q, cudaMemcpyHostToDevice, s));
-  R_CUDA(ctx, cudaMemcpyAsync(b_sg.p, starts, qbytes, cudaMemcpyHostToDevice, s));
-  R_CUDA(ctx, cudaMemcpyAsync(b_sg.as<char>() + qbytes, goals, qbytes, cudaMemcpyHostToDevice, s));
+  R_CUDA(ctx, cudaMemcpyAsync(d_db, db, sizeof(double) * NWB_NJ * n_db, cudaMemcpyHostToDevice, s));
+  R_CUDA(ctx, cudaMemcpyAsync(d_seeds, seeds, sizeof(uint64_t) * Q, cudaMemcpyHostToDevice, s));
+  R_CUDA(ctx, cudaMemcpyAsync(d_sg, starts, qbytes, cudaMemcpyHostToDevice, s));
+  R_CUDA(ctx, cudaMemcpyAsync(reinterpret_cast<char*>(d_sg) + qbytes, goals, qbytes, cudaMemcpyHostToDevice, s));
 
   // setStartGoalConfigs (RP:227-302): both roots must be valid, else the query fails immediately
-  R_CUDA(ctx, launch_validity(ctx->tab_group, b_sg.p, NWB_F64, 2 * (int64_t)Q, b_valid.as<uint8_t>(), nullptr, nullptr, false, sp, s));
+  R_CUDA(ctx, launch_validity(ctx->tab_group, d_sg, NWB_F64, 2 * (int64_t)Q, d_valid, nullptr, nullptr, false, sp, s));
   std::vector<uint8_t> root_valid(2 * (size_t)Q);
-  R_CUDA(ctx, cudaMemcpyAsync(root_valid.data(), b_valid.p, 2 * (size_t)Q, cudaMemcpyDeviceToHost, s));
+  R_CUDA(ctx, cudaMemcpyAsync(root_valid.data(), d_valid, 2 * (size_t)Q, cudaMemcpyDeviceToHost, s));
   R_CUDA(ctx, cudaStreamSynchronize(s));
-
-  std::vector<uint8_t> active(Q);
-  std::vector<int32_t> tree_a(Q), tree_b(Q), ones(Q, 1), minus1(Q, -1), roots(T);
-  std::vector<int> swap_flag(Q, 0);
   int64_t launches = 1;
+  std::vector<uint8_t> active(Q);
+  std::vector<int32_t> roots(T), cnt(T);
+  int32_t n_active = 0;
   for (int k = 0; k < Q; ++k) {
     std::memset(&results[k], 0, sizeof(nwb_plan_result));
     results[k].start_valid = root_valid[k];
     results[k].goal_valid = root_valid[Q + k];
     active[k] = root_valid[k] && root_valid[Q + k];
-    roots[k] = 2 * k;                    // start tree of query k
-    roots[Q + k] = 2 * k + 1;            // goal tree
+    n_active += active[k];
+    roots[k] = 2 * k;                    // start tree of query k <- starts[k]
+    roots[Q + k] = 2 * k + 1;            // goal tree            <- goals[k]
+    cnt[k] = cnt[Q + k] = active[k] ? 1 : 0;
   }
-  {  // insert the roots: tree 2k <- start_k, tree 2k+1 <- goal_k (index 0, predecessor 0: RP:236-258)
-    DevBuf b_roots, b_cnt, b_zero;
-    R_CUDA(ctx, b_roots.alloc(sizeof(int32_t) * T));
-    R_CUDA(ctx, b_cnt.alloc(sizeof(int32_t) * T));
-    R_CUDA(ctx, b_zero.alloc(sizeof(int32_t) * T));
-    std::vector<int32_t> cnt(T), zero(T, 0);
-    for (int k = 0; k < Q; ++k) cnt[k] = cnt[Q + k] = active[k] ? 1 : 0;
-    R_CUDA(ctx, cudaMemcpyAsync(b_roots.p, roots.data(), sizeof(int32_t) * T, cudaMemcpyHostToDevice, s));
-    R_CUDA(ctx, cudaMemcpyAsync(b_cnt.p, cnt.data(), sizeof(int32_t) * T, cudaMemcpyHostToDevice, s));
-    R_CUDA(ctx, cudaMemcpyAsync(b_zero.p, zero.data(), sizeof(int32_t) * T, cudaMemcpyHostToDevice, s));
-    forest_append_kernel<<<T, 32, 0, s>>>(F, b_roots.as<int32_t>(), b_sg.as<double>(), 1, b_cnt.as<int32_t>(), b_zero.as<int32_t>(), T,
-                                          nullptr, b_overflow.as<int32_t>());
-    R_CUDA(ctx, cudaGetLastError());
-    R_CUDA(ctx, cudaStreamSynchronize(s));
-    ++launches;
-  }
+  // insert the roots (index 0, predecessor 0: RP:236-258)
+  R_CUDA(ctx, cudaMemcpyAsync(M + o_roots, roots.data(), sizeof(int32_t) * T, cudaMemcpyHostToDevice, s));
+  R_CUDA(ctx, cudaMemcpyAsync(M + o_cnt, cnt.data(), sizeof(int32_t) * T, cudaMemcpyHostToDevice, s));
+  R_CUDA(ctx, cudaMemcpyAsync(S.active, active.data(), Q, cudaMemcpyHostToDevice, s));
+  R_CUDA(ctx, cudaMemcpyAsync(S.n_active, &n_active, sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  forest_append_kernel<<<T, 32, 0, s>>>(F, reinterpret_cast<int32_t*>(M + o_roots), d_sg, 1, reinterpret_cast<int32_t*>(M + o_cnt),
+                                        reinterpret_cast<int32_t*>(M + o_zero), T, nullptr, S.overflow);
+  R_CUDA(ctx, cudaGetLastError());
+  ++launches;
 
-  std::vector<int32_t> h_ext(Q), h_cstat(Q), h_nadd(Q), h_idx_b(Q), h_first(Q), h_pfirst(Q), walk_added(Q), walk_near(Q);
-  std::vector<uint8_t> walking(Q);
-  int n_active = 0;
-  for (int k = 0; k < Q; ++k) n_active += active[k];
-
-  for (int it = 0; it < max_iter && n_active > 0; ++it) {
-    for (int k = 0; k < Q; ++k) {
-      tree_a[k] = 2 * k + swap_flag[k];
-      tree_b[k] = 2 * k + 1 - swap_flag[k];
-      if (active[k]) results[k].iterations = it + 1;
+  // ---- solveQuery main loop (RP:1067-1198): no host synchronisation inside an iteration -----------------
+  if (!ctx->h_flag) R_CUDA(ctx, cudaMallocHost(&ctx->h_flag, 64));
+  int32_t* h_flag = ctx->h_flag;                               // pinned: remaining active queries
+  *h_flag = n_active;
+  int check_every = 1, since_check = 0;
+  for (int it = 0; it < max_iter && *h_flag > 0; ++it) {
+    rrt_begin_kernel<<<Q, 32, 0, s>>>(d_db, n_db, d_seeds, it, pc.quirks, Q, S, d_qrand);
+    // extendTree (RP:787-884)
+    forest_nn_kernel<<<Q, 128, 0, s>>>(F, S.tree_a, S.active, d_qrand, Q, d_idx_a, d_near);
+    cudaError_t e = launch_steer_project(pc, d_near, d_qrand, Q, d_qnew, d_status, nullptr, nullptr, s);
+    if (e == cudaSuccess) e = launch_validity(ctx->tab_group, d_qnew, NWB_F64, Q, d_valid, nullptr, nullptr, false, sp, s);
+    rrt_extend_commit_kernel<<<Q, 32, 0, s>>>(F, S, d_status, d_valid, d_idx_a, d_qnew, Q);
+    // connectTree (RP:890-1034) for the queries that extended, then the swap
+    forest_nn_kernel<<<Q, 128, 0, s>>>(F, S.tree_b, S.walking, S.q_connect, Q, S.idx_b, S.cstart);
+    if (e == cudaSuccess) e = launch_connect_forest(pc, ctx->tab_group, sp, F, S, Q, s);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      ctx->err = std::string("nwb_solve_query_batch: ") + cudaGetErrorString(e);
+      return NWB_E_CUDA;
     }
-    R_CUDA(ctx, cudaMemcpyAsync(b_active.p, active.data(), Q, cudaMemcpyHostToDevice, s));
-    R_CUDA(ctx, cudaMemcpyAsync(b_tree_a.p, tree_a.data(), sizeof(int32_t) * Q, cudaMemcpyHostToDevice, s));
-    R_CUDA(ctx, cudaMemcpyAsync(b_tree_b.p, tree_b.data(), sizeof(int32_t) * Q, cudaMemcpyHostToDevice, s));
-    // ---- extendTree (RP:787-884) -----------------------------------------------------------------
-    rrt_random_rows_kernel<<<Q, 32, 0, s>>>(b_db.as<double>(), n_db, b_seeds.as<uint64_t>(), it, pc.quirks, Q, b_qrand.as<double>());
-    forest_nn_kernel<<<Q, 128, 0, s>>>(F, b_tree_a.as<int32_t>(), b_active.as<uint8_t>(), b_qrand.as<double>(), Q, b_idx_a.as<int32_t>(),
-                                       b_near.as<double>());
-    R_CUDA(ctx, launch_steer_project(pc, b_near.as<double>(), b_qrand.as<double>(), Q, b_qnew.as<double>(), b_status.as<int32_t>(),
-                                     nullptr, nullptr, s));
-    R_CUDA(ctx, launch_validity(ctx->tab_group, b_qnew.p, NWB_F64, Q, b_valid.as<uint8_t>(), nullptr, nullptr, false, sp, s));
-    rrt_extend_commit_kernel<<<(Q + 127) / 128, 128, 0, s>>>(b_status.as<int32_t>(), b_valid.as<uint8_t>(), b_active.as<uint8_t>(), Q,
-                                                             b_ext_state.as<int32_t>(), b_ext_count.as<int32_t>());
-    forest_append_kernel<<<Q, 32, 0, s>>>(F, b_tree_a.as<int32_t>(), b_qnew.as<double>(), 1, b_ext_count.as<int32_t>(),
-                                          b_idx_a.as<int32_t>(), Q, b_first.as<int32_t>(), b_overflow.as<int32_t>());
-    launches += 6;
-    R_CUDA(ctx, cudaMemcpyAsync(h_ext.data(), b_ext_state.p, sizeof(int32_t) * Q, cudaMemcpyDeviceToHost, s));
-    R_CUDA(ctx, cudaStreamSynchronize(s));
-    // ---- connectTree (RP:890-1034) for the queries that extended ---------------------------------------
-    int n_walk = 0;
-    for (int k = 0; k < Q; ++k) {
-      walking[k] = active[k] && h_ext[k] != NWB_TRAPPED;
-      n_walk += walking[k];
-      walk_added[k] = 0;
-    }
-    if (n_walk > 0) {
-      R_CUDA(ctx, cudaMemcpyAsync(b_active.p, walking.data(), Q, cudaMemcpyHostToDevice, s));
-      // q_connect = the node just appended to Ta = q_new; nearest neighbour in Tb is the walk's first node
-      forest_nn_kernel<<<Q, 128, 0, s>>>(F, b_tree_b.as<int32_t>(), b_active.as<uint8_t>(), b_qnew.as<double>(), Q, b_idx_b.as<int32_t>(),
-                                         b_cstart.as<double>());
-      R_CUDA(ctx, cudaMemcpyAsync(h_idx_b.data(), b_idx_b.p, sizeof(int32_t) * Q, cudaMemcpyDeviceToHost, s));
-      R_CUDA(ctx, cudaStreamSynchronize(s));
-      ++launches;
-      for (int k = 0; k < Q; ++k) {
-        h_pfirst[k] = h_idx_b[k];
-        walk_near[k] = h_idx_b[k];
-      }
-      while (n_walk > 0) {
-        // only the still-walking edges take steps: mask the others by making them zero-length REACHED... simpler:
-        // run every edge slot; results of non-walking slots are ignored and never appended (count forced to 0)
-        R_CUDA(ctx, launch_connect(pc, ctx->tab_group, sp, b_cstart.as<double>(), b_qnew.as<double>(), Q, max_steps, b_chain.as<double>(),
-                                   b_nadd.as<int32_t>(), b_cstat.as<int32_t>(), s));
-        R_CUDA(ctx, cudaMemcpyAsync(h_nadd.data(), b_nadd.p, sizeof(int32_t) * Q, cudaMemcpyDeviceToHost, s));
-        R_CUDA(ctx, cudaMemcpyAsync(h_cstat.data(), b_cstat.p, sizeof(int32_t) * Q, cudaMemcpyDeviceToHost, s));
-        R_CUDA(ctx, cudaStreamSynchronize(s));
-        for (int k = 0; k < Q; ++k)
-          if (!walking[k]) h_nadd[k] = 0;
-        R_CUDA(ctx, cudaMemcpyAsync(b_nadd.p, h_nadd.data(), sizeof(int32_t) * Q, cudaMemcpyHostToDevice, s));
-        R_CUDA(ctx, cudaMemcpyAsync(b_pfirst.p, h_pfirst.data(), sizeof(int32_t) * Q, cudaMemcpyHostToDevice, s));
-        forest_append_kernel<<<Q, 32, 0, s>>>(F, b_tree_b.as<int32_t>(), b_chain.as<double>(), max_steps, b_nadd.as<int32_t>(),
-                                              b_pfirst.as<int32_t>(), Q, b_first.as<int32_t>(), b_overflow.as<int32_t>());
-        R_CUDA(ctx, cudaMemcpyAsync(h_first.data(), b_first.p, sizeof(int32_t) * Q, cudaMemcpyDeviceToHost, s));
-        R_CUDA(ctx, cudaStreamSynchronize(s));
-        launches += 2;
-        n_walk = 0;
-        for (int k = 0; k < Q; ++k) {
-          if (!walking[k]) continue;
-          const int n = h_nadd[k];
-          // q_near of writePath (RP:1000-1001): the node the REACHED step started from
-          if (n >= 2) walk_near[k] = h_first[k] + n - 2;
-          else if (n == 1 && walk_added[k] > 0) walk_near[k] = h_pfirst[k];
-          walk_added[k] += n;
-          if (h_cstat[k] == -1) {          // budget exhausted: continue from the last appended node
-            h_pfirst[k] = h_first[k] + n - 1;
-            R_CUDA(ctx, cudaMemcpyAsync(b_cstart.as<double>() + (size_t)k * NWB_NJ,
-                                        b_chain.as<double>() + ((size_t)k * max_steps + n - 1) * NWB_NJ, sizeof(double) * NWB_NJ,
-                                        cudaMemcpyDeviceToDevice, s));
-            ++n_walk;
-          } else {
-            walking[k] = 0;
-            if (h_cstat[k] == NWB_REACHED) {
-              results[k].success = 1;
-              results[k].connector = swap_flag[k] ? 2 : 1;      // 1: goal tree connected to start tree (RP:1101)
-              results[k].bridge_other = walk_near[k];
-              active[k] = 0;
-              --n_active;
-            }
-          }
-        }
+    launches += 7;
+    if (++since_check >= check_every || it + 1 == max_iter) {  // look at the active count now and then
+      since_check = 0;
+      check_every = std::min(16, check_every * 2);
+      cudaMemcpyAsync(h_flag, S.n_active, sizeof(int32_t), cudaMemcpyDeviceToHost, s);
+      e = cudaStreamSynchronize(s);
+      if (e != cudaSuccess) {
+          ctx->err = std::string("nwb_solve_query_batch: ") + cudaGetErrorString(e);
+        return NWB_E_CUDA;
       }
     }
-    for (int k = 0; k < Q; ++k)
-      if (active[k]) swap_flag[k] ^= 1;         // trees swap every iteration regardless of outcome (RP:1125-1192)
   }
 
   int32_t overflow = 0;
-  std::vector<int32_t> sizes(T);
-  R_CUDA(ctx, cudaMemcpyAsync(&overflow, b_overflow.p, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-  R_CUDA(ctx, cudaMemcpyAsync(sizes.data(), b_size.p, sizeof(int32_t) * T, cudaMemcpyDeviceToHost, s));
+  std::vector<int32_t> sizes(T), h_iter(Q), h_succ(Q), h_conn(Q), h_bridge(Q);
+  R_CUDA(ctx, cudaMemcpyAsync(&overflow, S.overflow, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  R_CUDA(ctx, cudaMemcpyAsync(sizes.data(), F.size, sizeof(int32_t) * T, cudaMemcpyDeviceToHost, s));
+  R_CUDA(ctx, cudaMemcpyAsync(h_iter.data(), S.iterations, sizeof(int32_t) * Q, cudaMemcpyDeviceToHost, s));
+  R_CUDA(ctx, cudaMemcpyAsync(h_succ.data(), S.success, sizeof(int32_t) * Q, cudaMemcpyDeviceToHost, s));
+  R_CUDA(ctx, cudaMemcpyAsync(h_conn.data(), S.connector, sizeof(int32_t) * Q, cudaMemcpyDeviceToHost, s));
+  R_CUDA(ctx, cudaMemcpyAsync(h_bridge.data(), S.bridge, sizeof(int32_t) * Q, cudaMemcpyDeviceToHost, s));
   R_CUDA(ctx, cudaStreamSynchronize(s));
 
   // ---- writePath, path extraction part (RP:1303-1392) -------------------------------------------------------
@@ -385,6 +356,10 @@ int nwb_solve_query_batch(nwb_ctx* ctx, const double* starts, const double* goal
   std::vector<int32_t> pred;
   for (int k = 0; k < Q; ++k) {
     nwb_plan_result& r = results[k];
+    r.iterations = h_iter[k];
+    r.success = h_succ[k];
+    r.connector = r.success ? h_conn[k] : 0;
+    r.bridge_other = r.success ? h_bridge[k] : 0;
     r.nodes_start = sizes[2 * k];
     r.nodes_goal = sizes[2 * k + 1];
     r.num_nodes_generated = r.success ? r.nodes_start + r.nodes_goal : 0;   // RP:1045: stays 0 unless a path is found
