@@ -262,6 +262,23 @@ NWB_API int nwb_shortcut_path(nwb_ctx* ctx, const double* raw, int32_t n_raw, do
  * count (n_path-1)*(k+1)+1 (rows beyond cap are not written). */
 NWB_API int nwb_interpolate_path(const double* path, int32_t n_path, int32_t k, double* out, int32_t cap);
 
+/* ---- multi-GPU result gather without a collective --------------------------------------------------
+ * Independent validity batches shard over the GPUs of one box with no data-path exchange; only the
+ * 1 B/config verdicts have to reach every rank.  Instead of a separate all-gather, the validity
+ * kernel itself stores each verdict into the gathered array of every rank through peer-mapped
+ * memory (NVLink 5 / NVSwitch).  One process per GPU: every rank allocates its gathered array with
+ * nwb_dev_alloc, exports it (nwb_ipc_export, 64-byte handle, exchanged by the host framework),
+ * imports the others (nwb_ipc_import) and registers the n_ranks base pointers (own one included, in
+ * rank order) with nwb_set_gather_peers; from then on nwb_is_feasible_batch_dev also writes
+ * verdict i to gathered[r][my_offset + i] on every rank r.  A rank may read its gathered array after
+ * its own stream and a cross-rank barrier have completed.  n_ranks = 0 switches the fused gather off. */
+NWB_API int nwb_dev_alloc(nwb_ctx* ctx, size_t bytes, void** out);
+NWB_API int nwb_dev_free(nwb_ctx* ctx, void* p);
+NWB_API int nwb_ipc_export(nwb_ctx* ctx, void* dev_ptr, unsigned char* handle64);
+NWB_API int nwb_ipc_import(nwb_ctx* ctx, const unsigned char* handle64, void** out);
+NWB_API int nwb_ipc_close(nwb_ctx* ctx, void* p);
+NWB_API int nwb_set_gather_peers(nwb_ctx* ctx, void* const* gathered, int32_t n_ranks, int64_t my_offset);
+
 /* Pinned host memory helpers: buffers from here make the host<->device copies of the batch
  * operators run at full PCIe speed. */
 NWB_API void* nwb_host_alloc(size_t bytes);

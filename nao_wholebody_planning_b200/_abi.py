@@ -124,6 +124,12 @@ def _declare(lib):
         "nwb_solve_query_batch": (C.c_int, [vp, vp, vp, i64, vp, i32, vp, vp, i32, dbl, i32, vp, vp, i32]),
         "nwb_shortcut_path": (C.c_int, [vp, vp, i32, vp, i32, vp]),
         "nwb_interpolate_path": (C.c_int, [vp, i32, i32, vp, i32]),
+        "nwb_dev_alloc": (C.c_int, [vp, C.c_size_t, C.POINTER(vp)]),
+        "nwb_dev_free": (C.c_int, [vp, vp]),
+        "nwb_ipc_export": (C.c_int, [vp, vp, vp]),
+        "nwb_ipc_import": (C.c_int, [vp, vp, C.POINTER(vp)]),
+        "nwb_ipc_close": (C.c_int, [vp, vp]),
+        "nwb_set_gather_peers": (C.c_int, [vp, C.POINTER(vp), i32, i64]),
         "nwb_host_alloc": (vp, [C.c_size_t]),
         "nwb_host_free": (None, [vp]),
         "nwb_ffma_peak": (C.c_int, [vp, C.c_int, pd, pd]),

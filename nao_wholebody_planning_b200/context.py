@@ -223,6 +223,34 @@ class Context:
         assert n == cap
         return out
 
+    # ---- multi-GPU fused gather ------------------------------------------------------------------
+    def dev_alloc(self, nbytes):
+        p = C.c_void_p()
+        self._check(self.lib.nwb_dev_alloc(self.h, int(nbytes), C.byref(p)), "nwb_dev_alloc")
+        return p.value
+
+    def dev_free(self, ptr):
+        self._check(self.lib.nwb_dev_free(self.h, ptr), "nwb_dev_free")
+
+    def ipc_export(self, ptr):
+        buf = (C.c_ubyte * 64)()
+        self._check(self.lib.nwb_ipc_export(self.h, ptr, buf), "nwb_ipc_export")
+        return bytes(buf)
+
+    def ipc_import(self, handle):
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+        p = C.c_void_p()
+        self._check(self.lib.nwb_ipc_import(self.h, buf, C.byref(p)), "nwb_ipc_import")
+        return p.value
+
+    def ipc_close(self, ptr):
+        self._check(self.lib.nwb_ipc_close(self.h, ptr), "nwb_ipc_close")
+
+    def set_gather_peers(self, ptrs, my_offset):
+        """ptrs: gathered-array base pointer of every rank, in rank order ([] switches the fused gather off)."""
+        arr = (C.c_void_p * max(len(ptrs), 1))(*ptrs)
+        self._check(self.lib.nwb_set_gather_peers(self.h, arr, len(ptrs), int(my_offset)), "nwb_set_gather_peers")
+
     # ---- measurement ----------------------------------------------------------------------------
     def ffma_peak(self, iters=4096):
         t, ms = C.c_double(0), C.c_double(0)

@@ -220,7 +220,8 @@ void nwb_host_free(void* p) {
 static int feasible_dev(nwb_ctx* ctx, const ValidityTables& tab, const void* q, int dtype, int64_t n, uint8_t* valid,
                         uint8_t* reason, float* margins, bool collision_only) {
   NWB_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-  NWB_CUDA(ctx, launch_validity(tab, q, dtype, n, valid, reason, margins, collision_only, ctx->params.srdf_trim != 0 && !ctx->force_table_pairs, ctx->stream));
+  const GatherPeers* gp = (!collision_only && ctx->gather.n > 0) ? &ctx->gather : nullptr;
+  NWB_CUDA(ctx, launch_validity(tab, q, dtype, n, valid, reason, margins, collision_only, ctx->params.srdf_trim != 0 && !ctx->force_table_pairs, ctx->stream, gp));
   NWB_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->last_launches = n > 0 ? 1 : 0;
   ctx->last_ms = -1;   // resolved lazily by nwb_last_kernel_ms
@@ -323,6 +324,52 @@ int nwb_fk_batch(nwb_ctx* ctx, const double* q, int64_t n, double* link_poses, d
     NWB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }
   ctx->last_launches = launches;
+  return NWB_OK;
+}
+
+// ---- multi-GPU: peer-mapped result gather ------------------------------------------------------------
+int nwb_dev_alloc(nwb_ctx* ctx, size_t bytes, void** out) {
+  if (!ctx || !out) return NWB_E_INVALID;
+  NWB_CUDA(ctx, cudaSetDevice(ctx->device));
+  NWB_CUDA(ctx, cudaMalloc(out, bytes ? bytes : 1));
+  return NWB_OK;
+}
+int nwb_dev_free(nwb_ctx* ctx, void* p) {
+  if (!ctx) return NWB_E_INVALID;
+  NWB_CUDA(ctx, cudaSetDevice(ctx->device));
+  NWB_CUDA(ctx, cudaFree(p));
+  return NWB_OK;
+}
+int nwb_ipc_export(nwb_ctx* ctx, void* dev_ptr, unsigned char* handle64) {
+  if (!ctx || !dev_ptr || !handle64) return NWB_E_INVALID;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  NWB_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  NWB_CUDA(ctx, cudaIpcGetMemHandle(&h, dev_ptr));
+  std::memcpy(handle64, &h, 64);
+  return NWB_OK;
+}
+int nwb_ipc_import(nwb_ctx* ctx, const unsigned char* handle64, void** out) {
+  if (!ctx || !handle64 || !out) return NWB_E_INVALID;
+  NWB_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle64, 64);
+  NWB_CUDA(ctx, cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+  return NWB_OK;
+}
+int nwb_ipc_close(nwb_ctx* ctx, void* p) {
+  if (!ctx) return NWB_E_INVALID;
+  NWB_CUDA(ctx, cudaSetDevice(ctx->device));
+  NWB_CUDA(ctx, cudaIpcCloseMemHandle(p));
+  return NWB_OK;
+}
+int nwb_set_gather_peers(nwb_ctx* ctx, void* const* gathered, int32_t n_ranks, int64_t my_offset) {
+  if (!ctx || n_ranks < 0 || n_ranks > 8 || (n_ranks > 0 && !gathered) || my_offset < 0)
+    return fail(ctx, NWB_E_INVALID, "nwb_set_gather_peers: bad argument (at most 8 ranks)");
+  ctx->gather = GatherPeers{};
+  for (int r = 0; r < n_ranks; ++r) ctx->gather.ptr[r] = static_cast<uint8_t*>(gathered[r]);
+  ctx->gather.n = n_ranks;
+  ctx->gather.offset = my_offset;
   return NWB_OK;
 }
 

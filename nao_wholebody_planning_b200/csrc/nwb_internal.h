@@ -55,8 +55,17 @@ struct ValidityTables {
   EnvLink env_links[nwbm::kNumGeom];
 };
 
+// Fused result gather: besides its own verdict array, the validity kernel stores each verdict into
+// the gathered array of every rank (peer memory over NVLink / NVSwitch, mapped through CUDA IPC).
+struct GatherPeers {
+  uint8_t* ptr[8];     // base of each rank's gathered array (own rank included)
+  int n;               // 0 = no fused gather
+  int64_t offset;      // this rank's first element inside the gathered arrays
+};
+
 struct Ctx {
   nwb_params params;
+  GatherPeers gather{};
   int device = 0;
   cudaStream_t stream = nullptr;      // stream the operators launch on (own_stream unless overridden)
   cudaStream_t own_stream = nullptr;
@@ -86,7 +95,8 @@ void build_tables(Ctx* ctx);
 
 // kernel launchers (validity.cu).  q is [n][21] of float or double on the device.
 cudaError_t launch_validity(const ValidityTables& tab, const void* q, int dtype, int64_t n, uint8_t* valid,
-                            uint8_t* reason, float* margins, bool collision_only, bool static_pairs, cudaStream_t stream);
+                            uint8_t* reason, float* margins, bool collision_only, bool static_pairs, cudaStream_t stream,
+                            const GatherPeers* gather = nullptr);
 cudaError_t launch_fk(const void* q, int dtype, int64_t n, double* poses, double* com, cudaStream_t stream);
 cudaError_t launch_ffma_peak(int sm_count, int iters, float* sink, cudaStream_t stream, double* flops_out);
 

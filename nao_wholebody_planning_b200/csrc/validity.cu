@@ -152,8 +152,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 
 template <typename QT, bool MARGINS, bool COLLISION_ONLY, int PAIRS>
 __global__ void __launch_bounds__(PT, NWB_PMINB)
-validity_persistent_kernel(const __grid_constant__ ValidityTables tab, const QT* __restrict__ q, int64_t n,
-                           uint8_t* __restrict__ valid, uint8_t* __restrict__ reason, float* __restrict__ margins) {
+validity_persistent_kernel(const __grid_constant__ ValidityTables tab, const __grid_constant__ GatherPeers gp,
+                           const QT* __restrict__ q, int64_t n, uint8_t* __restrict__ valid, uint8_t* __restrict__ reason,
+                           float* __restrict__ margins) {
   static_assert(PAIRS != PAIRS_TABLE, "the persistent kernel keeps the point table in registers");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr uint32_t kTileBytes = PT * NWB_NJ * sizeof(QT);
@@ -203,8 +204,12 @@ validity_persistent_kernel(const __grid_constant__ ValidityTables tab, const QT*
     const ValidityResult<float> res = evaluate_config<float, RegStore, MARGINS, COLLISION_ONLY, PAIRS>(tab, qv, st, &min_sep, &hull_margin);
     if (i < n) {
       const unsigned rs = (res.hit ? NWB_REASON_COLLISION : 0u) | (res.stable ? 0u : NWB_REASON_UNSTABLE);
-      if (valid) valid[i] = COLLISION_ONLY ? (uint8_t)res.hit : (uint8_t)(rs == 0u);
+      const uint8_t v = COLLISION_ONLY ? (uint8_t)res.hit : (uint8_t)(rs == 0u);
+      if (valid) valid[i] = v;
       if (reason) reason[i] = (uint8_t)rs;
+      // fused gather: the verdict goes straight into every rank's gathered array (posted NVLink
+      // stores; a warp writes 32 contiguous bytes = one sector per peer)
+      for (int p = 0; p < gp.n; ++p) gp.ptr[p][gp.offset + i] = v;
       if constexpr (MARGINS) {
         if (margins) {
           if constexpr (COLLISION_ONLY) margins[i] = min_sep;
@@ -302,8 +307,8 @@ static cudaError_t launch_packed(const ValidityTables& tab, const void* q, int64
 static int g_sm_count = 0;
 
 template <typename QT, bool MARGINS, bool COLLISION_ONLY, int PAIRS>
-static cudaError_t launch_persistent(const ValidityTables& tab, const void* q, int64_t n, uint8_t* valid, uint8_t* reason,
-                                     float* margins, cudaStream_t stream) {
+static cudaError_t launch_persistent(const ValidityTables& tab, const GatherPeers& gp, const void* q, int64_t n, uint8_t* valid,
+                                     uint8_t* reason, float* margins, cudaStream_t stream) {
   auto kern = validity_persistent_kernel<QT, MARGINS, COLLISION_ONLY, PAIRS>;
   static int blocks_per_sm = 0;   // per instantiation
   const size_t smem = 2 * (size_t)PT * NWB_NJ * sizeof(QT) + 16;
@@ -320,8 +325,11 @@ static cudaError_t launch_persistent(const ValidityTables& tab, const void* q, i
     }
   }
   const int64_t tiles = (n + PT - 1) / PT;
-  const int64_t grid = std::min<int64_t>(tiles, (int64_t)g_sm_count * blocks_per_sm);
-  kern<<<(unsigned)grid, PT, smem, stream>>>(tab, (const QT*)q, n, valid, reason, margins);
+  // NWB_RESERVE_SMS=k leaves k SMs free of persistent CTAs so that a concurrently running collective
+  // (the NCCL verdict gather of the multi-GPU step) finds room instead of queueing behind this grid
+  static const int reserve = getenv("NWB_RESERVE_SMS") ? atoi(getenv("NWB_RESERVE_SMS")) : 0;
+  const int64_t grid = std::min<int64_t>(tiles, (int64_t)std::max(1, g_sm_count - reserve) * blocks_per_sm);
+  kern<<<(unsigned)grid, PT, smem, stream>>>(tab, gp, (const QT*)q, n, valid, reason, margins);
   return cudaGetLastError();
 }
 
@@ -343,7 +351,7 @@ static cudaError_t launch_one(const ValidityTables& tab, const void* q, int64_t 
 
 template <typename QT, bool COLLISION_ONLY>
 static cudaError_t launch_qt(const ValidityTables& tab, const void* q, int64_t n, uint8_t* valid, uint8_t* reason,
-                             float* margins, bool static_pairs, cudaStream_t stream) {
+                             float* margins, bool static_pairs, cudaStream_t stream, const GatherPeers& gp) {
   constexpr int kStatic = COLLISION_ONLY ? PAIRS_STATIC_ALL : PAIRS_STATIC_GROUP;
 #ifdef NWB_ENABLE_PACKED
   if (static_pairs && !margins && getenv("NWB_PACKED"))
@@ -351,8 +359,9 @@ static cudaError_t launch_qt(const ValidityTables& tab, const void* q, int64_t n
 #endif
   // TMA bulk copies need 16-byte aligned sources; every tile offset is a multiple of 16 bytes
   if (static_pairs && (reinterpret_cast<uintptr_t>(q) & 15) == 0 && !getenv("NWB_NO_PERSISTENT"))
-    return margins ? launch_persistent<QT, true, COLLISION_ONLY, kStatic>(tab, q, n, valid, reason, margins, stream)
-                   : launch_persistent<QT, false, COLLISION_ONLY, kStatic>(tab, q, n, valid, reason, margins, stream);
+    return margins ? launch_persistent<QT, true, COLLISION_ONLY, kStatic>(tab, gp, q, n, valid, reason, margins, stream)
+                   : launch_persistent<QT, false, COLLISION_ONLY, kStatic>(tab, gp, q, n, valid, reason, margins, stream);
+  if (gp.n > 0) return cudaErrorNotSupported;   // the fused gather lives in the persistent kernel only
   if (static_pairs)
     return margins ? launch_one<QT, true, COLLISION_ONLY, kStatic>(tab, q, n, valid, reason, margins, stream)
                    : launch_one<QT, false, COLLISION_ONLY, kStatic>(tab, q, n, valid, reason, margins, stream);
@@ -363,13 +372,16 @@ static cudaError_t launch_qt(const ValidityTables& tab, const void* q, int64_t n
 // static_pairs: the context uses the default SRDF reading, so the compiled-in pair list applies
 // (group set for isFeasible, whole-robot set for the collision-only predicate).
 cudaError_t launch_validity(const ValidityTables& tab, const void* q, int dtype, int64_t n, uint8_t* valid,
-                            uint8_t* reason, float* margins, bool collision_only, bool static_pairs, cudaStream_t stream) {
+                            uint8_t* reason, float* margins, bool collision_only, bool static_pairs, cudaStream_t stream,
+                            const GatherPeers* gather) {
   if (n <= 0) return cudaSuccess;
+  GatherPeers none{};
+  const GatherPeers& gp = gather ? *gather : none;
   if (dtype == NWB_F64)
-    return collision_only ? launch_qt<double, true>(tab, q, n, valid, reason, margins, static_pairs, stream)
-                          : launch_qt<double, false>(tab, q, n, valid, reason, margins, static_pairs, stream);
-  return collision_only ? launch_qt<float, true>(tab, q, n, valid, reason, margins, static_pairs, stream)
-                        : launch_qt<float, false>(tab, q, n, valid, reason, margins, static_pairs, stream);
+    return collision_only ? launch_qt<double, true>(tab, q, n, valid, reason, margins, static_pairs, stream, gp)
+                          : launch_qt<double, false>(tab, q, n, valid, reason, margins, static_pairs, stream, gp);
+  return collision_only ? launch_qt<float, true>(tab, q, n, valid, reason, margins, static_pairs, stream, gp)
+                        : launch_qt<float, false>(tab, q, n, valid, reason, margins, static_pairs, stream, gp);
 }
 
 // ---- FK kernel (nwb_fk_batch): every frame + COM, one configuration per thread ----------------

@@ -188,3 +188,34 @@ def test_rotated_box(oracle):
         valid, reason, marg = c.isFeasible(q, want_margins=True)
         assert (((valid == o_valid) & (reason == o_reason)) | band).all()
         assert np.abs(marg[:, 0] - o_marg[:, 0]).max() < 3e-6
+
+
+def test_fused_gather_writes_every_ranks_array(oracle):
+    """Multi-GPU result gather emulated on one GPU: two 'ranks' (contexts) whose validity kernels store
+    their verdicts into both gathered arrays (the peer arrays are plain device buffers here; across
+    processes they are CUDA-IPC mappings - bench.py checks that path against an NCCL all_gather)."""
+    import torch
+    n = 5000
+    shards = [OL.noisy_db_configs(n, seed=41), OL.uniform_configs(n, seed=42)]
+    ctxs = [nwb.Context(), nwb.Context()]
+    gathered = [c.dev_alloc(2 * n) for c in ctxs]
+    outs = []
+    for r, c in enumerate(ctxs):
+        c.set_gather_peers(gathered, r * n)
+        qd = torch.tensor(shards[r], dtype=torch.float64, device="cuda")
+        valid = torch.empty(n, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        c.is_feasible_dev(qd.data_ptr(), nwb.F64, n, valid.data_ptr())
+        c.synchronize()
+        outs.append(valid.cpu().numpy())
+    expect = np.concatenate(outs)
+    for g in gathered:
+        class Raw:
+            __cuda_array_interface__ = {"shape": (2 * n,), "typestr": "|u1", "data": (int(g), False), "version": 3}
+        assert (torch.as_tensor(Raw(), device="cuda").cpu().numpy() == expect).all()
+    o_valid = np.concatenate([oracle.is_feasible(s)[0] for s in shards])
+    assert (expect != o_valid).sum() <= 5            # boundary-band flips only
+    for c, g in zip(ctxs, gathered):
+        c.set_gather_peers([], 0)
+        c.dev_free(g)
+        c.close()
