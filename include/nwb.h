@@ -279,6 +279,30 @@ NWB_API int nwb_ipc_import(nwb_ctx* ctx, const unsigned char* handle64, void** o
 NWB_API int nwb_ipc_close(nwb_ctx* ctx, void* p);
 NWB_API int nwb_set_gather_peers(nwb_ctx* ctx, void* const* gathered, int32_t n_ranks, int64_t my_offset);
 
+/* ---- on-disk formats + the database service ----------------------------------------------------------
+ * The reference's persistent artefacts are text files: one configuration per line, values printed by
+ * `ofstream << double << " "` (6 significant digits, trailing blank; SCG:463-468, RP:1444-1452) and
+ * parsed with strtod (RRT_Planner::load_DS_database, RP:121-191). */
+NWB_API int nwb_write_configs(const char* path, const double* rows, int64_t n_rows);
+/* Reads up to cap rows of 21 values; *n_rows = rows in the file.  NWB_E_IO if it cannot be opened
+ * (the reference prints a message and carries on, RP:140,189). */
+NWB_API int nwb_load_ds_database(const char* path, double* rows, int64_t cap, int64_t* n_rows);
+
+/* rrt_planner_msgs/srv/Generate_DS_Configs.srv:1-5 */
+typedef struct nwb_generate_ds_configs_request {
+  int32_t max_samples;
+  int32_t max_ik_iterations;
+} nwb_generate_ds_configs_request;
+typedef struct nwb_generate_ds_configs_response {
+  int32_t num_configs_generated;
+} nwb_generate_ds_configs_response;
+/* NAO_PLANNER_CONTROL::generate_ds_database (NPC:137-147): sample max_samples configurations, write
+ * the accepted ones to `path` (the node's ssc_double_support file), report their number.  `seed`
+ * replaces the reference's clock-seeded generator.  Like the service callback it reports failures
+ * through the return code instead of exiting (SCG:205,218). */
+NWB_API int nwb_generate_ds_database(nwb_ctx* ctx, const nwb_generate_ds_configs_request* req,
+                                     nwb_generate_ds_configs_response* resp, const char* path, uint64_t seed);
+
 /* Pinned host memory helpers: buffers from here make the host<->device copies of the batch
  * operators run at full PCIe speed. */
 NWB_API void* nwb_host_alloc(size_t bytes);

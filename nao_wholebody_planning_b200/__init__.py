@@ -6,7 +6,7 @@ does not load the library, creating a Context does - and fails loudly if it is n
 """
 from ._abi import (ADVANCED, F32, F64, NFRAMES, NJ, REACHED, REASON_COLLISION, REASON_UNSTABLE, TRAPPED, NwbError,
                    NwbParams, default_params, load_library)
-from .context import Context, PinnedArray, Tree
+from .context import Context, PinnedArray, Tree, load_ds_database, write_configs
 
-__all__ = ["Context", "PinnedArray", "Tree", "NwbParams", "NwbError", "default_params", "load_library", "NJ", "NFRAMES",
+__all__ = ["Context", "PinnedArray", "Tree", "load_ds_database", "write_configs", "NwbParams", "NwbError", "default_params", "load_library", "NJ", "NFRAMES",
            "ADVANCED", "REACHED", "TRAPPED", "REASON_COLLISION", "REASON_UNSTABLE", "F64", "F32"]

@@ -46,6 +46,14 @@ class NwbPlanResult(C.Structure):
                                          "nodes_start", "nodes_goal", "connector", "bridge_other", "raw_path_len")]
 
 
+class GenDsRequest(C.Structure):
+    _fields_ = [("max_samples", C.c_int32), ("max_ik_iterations", C.c_int32)]
+
+
+class GenDsResponse(C.Structure):
+    _fields_ = [("num_configs_generated", C.c_int32)]
+
+
 def default_params(**over):
     """Reference defaults (planning_config/planning_parameters.yaml, hard-coded constants)."""
     p = NwbParams(device=0, quirks=QUIRK_SIGNED_FOOT_ERROR | QUIRK_DB_INDEX_FLOOR, srdf_trim=1, scale_origin=1,
@@ -130,6 +138,9 @@ def _declare(lib):
         "nwb_ipc_import": (C.c_int, [vp, vp, C.POINTER(vp)]),
         "nwb_ipc_close": (C.c_int, [vp, vp]),
         "nwb_set_gather_peers": (C.c_int, [vp, C.POINTER(vp), i32, i64]),
+        "nwb_write_configs": (C.c_int, [C.c_char_p, vp, i64]),
+        "nwb_load_ds_database": (C.c_int, [C.c_char_p, vp, i64, C.POINTER(i64)]),
+        "nwb_generate_ds_database": (C.c_int, [vp, C.POINTER(GenDsRequest), C.POINTER(GenDsResponse), C.c_char_p, C.c_uint64]),
         "nwb_host_alloc": (vp, [C.c_size_t]),
         "nwb_host_free": (None, [vp]),
         "nwb_ffma_peak": (C.c_int, [vp, C.c_int, pd, pd]),

@@ -251,6 +251,15 @@ class Context:
         arr = (C.c_void_p * max(len(ptrs), 1))(*ptrs)
         self._check(self.lib.nwb_set_gather_peers(self.h, arr, len(ptrs), int(my_offset)), "nwb_set_gather_peers")
 
+    # ---- database service + files -----------------------------------------------------------------
+    def generate_ds_database(self, max_samples, max_ik_iterations, path, seed):
+        """generate_ds_database service (nao_planner_control.cpp:137-147) -> num_configs_generated."""
+        req = _abi.GenDsRequest(int(max_samples), int(max_ik_iterations))
+        resp = _abi.GenDsResponse()
+        self._check(self.lib.nwb_generate_ds_database(self.h, C.byref(req), C.byref(resp), str(path).encode(), int(seed)),
+                    "nwb_generate_ds_database")
+        return resp.num_configs_generated
+
     # ---- measurement ----------------------------------------------------------------------------
     def ffma_peak(self, iters=4096):
         t, ms = C.c_double(0), C.c_double(0)
@@ -311,6 +320,27 @@ class Tree:
     def nearest_dev(self, q_dev, nq, idx_dev, dist_dev=None):
         self.ctx._check(self.lib.nwb_nearest_neighbour_batch_dev(self.h, q_dev, nq, idx_dev, dist_dev),
                         "nwb_nearest_neighbour_batch_dev")
+
+
+def load_ds_database(path, cap=1 << 20):
+    """RRT_Planner::load_DS_database (rrt_planner.cpp:121-191): text file -> [n,21] float64."""
+    lib = load_library()
+    n = C.c_int64(0)
+    rc = lib.nwb_load_ds_database(str(path).encode(), None, 0, C.byref(n))
+    if rc != 0:
+        raise NwbError(f"nwb_load_ds_database({path}) failed ({rc})")
+    rows = np.empty((n.value, NJ))
+    rc = lib.nwb_load_ds_database(str(path).encode(), _p(rows), n.value, C.byref(n))
+    if rc != 0:
+        raise NwbError(f"nwb_load_ds_database({path}) failed ({rc})")
+    return rows
+
+
+def write_configs(path, rows):
+    rows = np.ascontiguousarray(rows, dtype=np.float64).reshape(-1, NJ)
+    rc = load_library().nwb_write_configs(str(path).encode(), _p(rows), len(rows))
+    if rc != 0:
+        raise NwbError(f"nwb_write_configs({path}) failed ({rc})")
 
 
 class PinnedArray:

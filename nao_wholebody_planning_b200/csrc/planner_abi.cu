@@ -2,8 +2,11 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
+#include <string>
 #include <vector>
 
 #include "nwb_internal.h"
@@ -248,6 +251,72 @@ int nwb_sample_stable_configs(nwb_ctx* ctx, uint64_t seed, uint64_t first, int64
     ctx->err = "nwb_sample_stable_configs: more rows accepted than the output capacity";
     return NWB_E_NOMEM;
   }
+  return NWB_OK;
+}
+
+// ---- on-disk formats -------------------------------------------------------------------------------------
+int nwb_write_configs(const char* path, const double* rows, int64_t n_rows) {
+  if (!path || n_rows < 0 || (n_rows > 0 && !rows)) return NWB_E_INVALID;
+  std::remove(path);                                    // SCG:191, RP:1428: the old file is removed first
+  FILE* f = std::fopen(path, "w");
+  if (!f) return NWB_E_IO;
+  for (int64_t r = 0; r < n_rows; ++r) {
+    for (int j = 0; j < NWB_NJ; ++j) std::fprintf(f, "%g ", rows[r * NWB_NJ + j]);   // ostream default: 6 significant digits
+    std::fputc('\n', f);
+  }
+  return std::fclose(f) == 0 ? NWB_OK : NWB_E_IO;
+}
+
+int nwb_load_ds_database(const char* path, double* rows, int64_t cap, int64_t* n_rows) {
+  if (!path || !n_rows || cap < 0 || (cap > 0 && !rows)) return NWB_E_INVALID;
+  *n_rows = 0;
+  FILE* f = std::fopen(path, "r");
+  if (!f) return NWB_E_IO;
+  std::string line;
+  int c;
+  int64_t n = 0;
+  auto flush = [&]() {
+    const char* p = line.c_str();
+    char* end = nullptr;
+    double v[NWB_NJ];
+    int got = 0;
+    for (; got < NWB_NJ; ++got) {
+      v[got] = std::strtod(p, &end);
+      if (end == p) break;
+      p = end;
+    }
+    if (got == NWB_NJ) {                                // blank / short lines are not configurations
+      if (n < cap) std::memcpy(rows + n * NWB_NJ, v, sizeof(v));
+      ++n;
+    }
+    line.clear();
+  };
+  while ((c = std::fgetc(f)) != EOF) {
+    if (c == '\n') flush();
+    else line.push_back((char)c);
+  }
+  if (!line.empty()) flush();
+  std::fclose(f);
+  *n_rows = n;
+  return NWB_OK;
+}
+
+int nwb_generate_ds_database(nwb_ctx* ctx, const nwb_generate_ds_configs_request* req, nwb_generate_ds_configs_response* resp,
+                             const char* path, uint64_t seed) {
+  if (!ctx) return NWB_E_INVALID;
+  if (!req || !resp || !path || req->max_samples < 0) return bad(ctx, "nwb_generate_ds_database: bad argument");
+  resp->num_configs_generated = 0;
+  std::vector<double> rows((size_t)std::max(req->max_samples, 1) * NWB_NJ);
+  int64_t n = 0;
+  int rc = nwb_sample_stable_configs(ctx, seed, 0, req->max_samples, req->max_ik_iterations, rows.data(), req->max_samples, &n,
+                                     nullptr, nullptr);
+  if (rc != NWB_OK) return rc;
+  rc = nwb_write_configs(path, rows.data(), n);
+  if (rc != NWB_OK) {
+    ctx->err = std::string("nwb_generate_ds_database: cannot write ") + path;
+    return rc;
+  }
+  resp->num_configs_generated = (int32_t)n;
   return NWB_OK;
 }
 

@@ -173,3 +173,21 @@ def test_sampler_quirk_c1_keeps_the_infeasible_samples(oracle):
 def test_sampler_capacity_overflow_is_reported(ctx):
     with pytest.raises(nwb.NwbError, match="capacity"):
         ctx.sample_stable_configs(1, 0, 20000, cap=10)
+
+
+def test_generate_ds_database_service(ctx, oracle, tmp_path):
+    """generate_ds_database (nao_planner_control.cpp:137-147) with the reference's default budget
+    (5000 samples, 5 IK attempts): file written in the reference format, loadable, rows as the oracle's."""
+    path = tmp_path / "ssc_double_support.dat"
+    n = ctx.generate_ds_database(5000, 5, path, seed=20121005)
+    rows = nwb.load_ds_database(path)
+    assert n == len(rows) and 20 < n < 2500
+    orows, oidx, _ = oracle.sample_stable_configs(20121005, 0, 5000)
+    assert abs(len(orows) - n) <= 1
+    if len(orows) == n:
+        assert np.abs(rows - orows).max() < 1e-5          # the file keeps 6 significant digits
+    valid, _, _ = ctx.isFeasible(rows)
+    assert valid.mean() > 0.99                            # rounding to 6 digits may push a boundary row over
+    # the generated database drives a planning query
+    res, paths = ctx.solveQuery(rows[:4], rows[4:8], rows, np.arange(4, dtype=np.uint64), W_APPROACH, max_iter=200)
+    assert sum(r["success"] for r in res) >= 3
