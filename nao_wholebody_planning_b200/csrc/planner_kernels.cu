@@ -160,21 +160,60 @@ connect_forest_kernel(const __grid_constant__ PlanConst pc, const __grid_constan
 }
 
 // ---- edge check: (edge, way-point) -> collision-only validity ------------------------------------------
-template <bool STATIC>
-__global__ void __launch_bounds__(128)
+// One way-point per thread, 256 consecutive (edge, way-point) slots per block.  The end points of the
+// few edges a block touches are staged in shared memory once (start + step width per joint, fp64 as
+// interpolateWaypoints computes them, RP:1758-1771); each thread then forms its way-point, evaluates
+// the whole-robot collision predicate in registers and posts the first colliding index per edge.
+constexpr int EC_THREADS = 256;
+constexpr int EC_MAX_EDGES = 8;     // edges a block can span when k + 2 >= 37 (a block of 256 slots covers <= 8 edges)
+
+// EARLY_EXIT: a way-point whose edge already has an earlier colliding way-point on record is skipped;
+// the warp votes (ballot) and leaves together, so no lane idles through a full evaluation for an
+// edge that is already lost.  Results (ok, first_bad) are identical to the full evaluation.
+template <bool STATIC, bool EARLY_EXIT>
+__global__ void __launch_bounds__(EC_THREADS, 2)
 edge_check_kernel(const __grid_constant__ ValidityTables tab, const double* __restrict__ qa, const double* __restrict__ qb,
                   int64_t n_edges, int k, int32_t* __restrict__ first_bad) {
+  __shared__ double s_a[EC_MAX_EDGES][NWB_NJ], s_sw[EC_MAX_EDGES][NWB_NJ];
   const int wp = k + 2;
-  int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t gid0 = (int64_t)blockIdx.x * EC_THREADS;
+  const int64_t e0 = gid0 / wp;
+  const bool staged = wp * EC_MAX_EDGES >= EC_THREADS + wp;          // the block's edges fit the staging area
+  if (staged) {
+    for (int t = threadIdx.x; t < EC_MAX_EDGES * NWB_NJ; t += EC_THREADS) {
+      const int le = t / NWB_NJ, j = t % NWB_NJ;
+      const int64_t e = e0 + le;
+      if (e < n_edges) {
+        const double a = qa[e * NWB_NJ + j], b = qb[e * NWB_NJ + j];
+        s_a[le][j] = a;
+        s_sw[le][j] = (b - a) / (k + 1);                    // RP:1758
+      }
+    }
+    __syncthreads();
+  }
+  int64_t gid = gid0 + threadIdx.x;
   const bool active = gid < n_edges * wp;
-  if (!active) gid = 0;
+  if (!active) gid = gid0;
   const int64_t e = gid / wp;
   const int n = (int)(gid - e * wp);
+  if constexpr (EARLY_EXIT) {
+    const bool needed = active && (*reinterpret_cast<volatile int32_t*>(first_bad + e) > n);
+    if (__ballot_sync(0xffffffffu, needed) == 0u) return;        // the whole warp is past a known collision
+  }
   double q[NWB_NJ];
-  for (int j = 0; j < NWB_NJ; ++j) {
-    double a = qa[e * NWB_NJ + j], b = qb[e * NWB_NJ + j];
-    double sw = (b - a) / (k + 1);                         // RP:1758
-    q[j] = (n == 0) ? a : __dadd_rn(a, __dmul_rn(sw, (double)n));   // RP:1763, 1771
+  if (staged) {
+    const int le = (int)(e - e0);
+#pragma unroll
+    for (int j = 0; j < NWB_NJ; ++j) {
+      const double a = s_a[le][j];
+      q[j] = (n == 0) ? a : __dadd_rn(a, __dmul_rn(s_sw[le][j], (double)n));   // RP:1763, 1771
+    }
+  } else {
+    for (int j = 0; j < NWB_NJ; ++j) {
+      const double a = qa[e * NWB_NJ + j], b = qb[e * NWB_NJ + j];
+      const double sw = (b - a) / (k + 1);
+      q[j] = (n == 0) ? a : __dadd_rn(a, __dmul_rn(sw, (double)n));
+    }
   }
   ValidityResult<float> r = eval_one<true, STATIC>(tab, q);
   if (active && r.hit) atomicMin(first_bad + e, n);
@@ -273,9 +312,15 @@ cudaError_t launch_edge_check(const ValidityTables& tab, bool static_pairs, cons
   cudaError_t e = cudaMemsetAsync(first_bad, 0x7f, sizeof(int32_t) * n_edges, s);   // 0x7f7f7f7f > any way-point index
   if (e != cudaSuccess) return e;
   const int64_t total = n_edges * (k + 2);
-  unsigned blocks = (unsigned)((total + 127) / 128);
-  if (static_pairs) edge_check_kernel<true><<<blocks, 128, 0, s>>>(tab, qa, qb, n_edges, k, first_bad);
-  else edge_check_kernel<false><<<blocks, 128, 0, s>>>(tab, qa, qb, n_edges, k, first_bad);
+  unsigned blocks = (unsigned)((total + EC_THREADS - 1) / EC_THREADS);
+  static const bool full = getenv("NWB_EDGE_FULL") != nullptr;    // roofline runs: evaluate every way-point
+  if (static_pairs) {
+    if (full) edge_check_kernel<true, false><<<blocks, EC_THREADS, 0, s>>>(tab, qa, qb, n_edges, k, first_bad);
+    else edge_check_kernel<true, true><<<blocks, EC_THREADS, 0, s>>>(tab, qa, qb, n_edges, k, first_bad);
+  } else {
+    if (full) edge_check_kernel<false, false><<<blocks, EC_THREADS, 0, s>>>(tab, qa, qb, n_edges, k, first_bad);
+    else edge_check_kernel<false, true><<<blocks, EC_THREADS, 0, s>>>(tab, qa, qb, n_edges, k, first_bad);
+  }
   edge_finish_kernel<<<(unsigned)((n_edges + 127) / 128), 128, 0, s>>>(first_bad, n_edges, ok);
   return cudaGetLastError();
 }
