@@ -15,7 +15,7 @@
 // squared distance, and only when that comes within a rigorous fp32 error bound of its running
 // minimum re-evaluates the distance exactly as the reference does (double, separately rounded
 // multiply and add, then sqrt, strict <) from the master copy.  Lexicographic (distance, index)
-// reductions (warp shuffle -> block -> grid) then reproduce "first strict minimum wins".
+// reductions (warp shuffle -> block -> last-block-done grid fold, one launch) then reproduce "first strict minimum wins".
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -92,7 +92,8 @@ constexpr int NN_STAGES = 4;      // 172 KB of shared memory: one persistent CTA
 template <int QT>
 __global__ void __launch_bounds__(NN_THREADS, 1)
 nn_scan_kernel(const float* __restrict__ soa, const double* __restrict__ aos, int64_t cap, int64_t N,
-               const double* __restrict__ q, int64_t nq, double* __restrict__ part_d, int32_t* __restrict__ part_i) {
+               const double* __restrict__ q, int64_t nq, double* __restrict__ part_d, int32_t* __restrict__ part_i,
+               unsigned* __restrict__ tickets, int32_t* __restrict__ idx_out, double* __restrict__ dist_out) {
   extern __shared__ __align__(128) unsigned char nn_smem[];
   float* ring = reinterpret_cast<float*>(nn_smem);                           // [NN_STAGES][21][NN_TILE]
   uint64_t* bars = reinterpret_cast<uint64_t*>(nn_smem + sizeof(float) * NN_STAGES * NWB_NJ * NN_TILE);
@@ -274,18 +275,41 @@ nn_scan_kernel(const float* __restrict__ soa, const double* __restrict__ aos, in
       part_i[(q0 + tid) * gridDim.x + blockIdx.x] = i;
     }
   }
-}
-
-__global__ void nn_final_kernel(const double* __restrict__ part_d, const int32_t* __restrict__ part_i, int nb, int64_t nq,
-                                int32_t* __restrict__ idx, double* __restrict__ dist) {
-  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= nq) return;
-  double d = part_d[k * nb];
-  int i = part_i[k * nb];
-  for (int b = 1; b < nb; ++b)
-    if (lex_less(part_d[k * nb + b], part_i[k * nb + b], d, i)) { d = part_d[k * nb + b]; i = part_i[k * nb + b]; }
-  idx[k] = i;
-  if (dist) dist[k] = d;
+  // grid reduction without a second launch: the last block to finish this query group folds the partials
+  __shared__ bool last;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) last = atomicAdd(&tickets[blockIdx.y], 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  for (int k = 0; k < QT; ++k) {
+    if (q0 + k >= nq) break;
+    double d = 10000.0;
+    int i = -1;
+    bool first = true;
+    for (int b = tid; b < (int)gridDim.x; b += NN_THREADS) {
+      const double db = part_d[(q0 + k) * gridDim.x + b];
+      const int ib = part_i[(q0 + k) * gridDim.x + b];
+      if (first || lex_less(db, ib, d, i)) { d = db; i = ib; first = false; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      double d2 = __shfl_xor_sync(0xffffffffu, d, o);
+      int i2 = __shfl_xor_sync(0xffffffffu, i, o);
+      if (lex_less(d2, i2, d, i)) { d = d2; i = i2; }
+    }
+    if ((tid & 31) == 0) { red_d[0][tid >> 5] = d; red_i[0][tid >> 5] = i; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < NN_THREADS / 32; ++w)
+        if (lex_less(red_d[0][w], red_i[0][w], d, i)) { d = red_d[0][w]; i = red_i[0][w]; }
+      idx_out[q0 + k] = i;
+      if (dist_out) dist_out[q0 + k] = d;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) tickets[blockIdx.y] = 0u;              // ready for the next call
 }
 
 }  // namespace nwb
@@ -302,6 +326,8 @@ struct nwb_tree {
   double* part_d = nullptr;
   int32_t* part_i = nullptr;
   size_t part_cap = 0;
+  unsigned* tickets = nullptr;   // one counter per query group (zero between calls)
+  size_t ticket_cap = 0;
   void* stage = nullptr;      // device staging for host-pointer calls
   size_t stage_bytes = 0;
 };
@@ -375,6 +401,17 @@ int nn_launch(nwb_tree* t, const double* q_dev, int64_t nq, int32_t* idx_dev, do
     TREE_CUDA(t, cudaMalloc(&t->part_i, sizeof(int32_t) * need));
     t->part_cap = need;
   }
+  {
+    const size_t groups = (size_t)nq;                 // >= number of query groups for either QT
+    if (groups > t->ticket_cap) {
+      if (t->tickets) cudaFree(t->tickets);
+      t->tickets = nullptr;
+      t->ticket_cap = 0;
+      TREE_CUDA(t, cudaMalloc(&t->tickets, sizeof(unsigned) * groups));
+      TREE_CUDA(t, cudaMemsetAsync(t->tickets, 0, sizeof(unsigned) * groups, t->ctx->stream));
+      t->ticket_cap = groups;
+    }
+  }
   cudaStream_t s = t->ctx->stream;
   constexpr size_t kNnSmem = sizeof(float) * NN_STAGES * NWB_NJ * NN_TILE + 8 * NN_STAGES;
   static bool configured = false;
@@ -392,16 +429,17 @@ int nn_launch(nwb_tree* t, const double* q_dev, int64_t nq, int32_t* idx_dev, do
     const int64_t qoff = y0 * QT;
     if (QT == 1)
       nn_scan_kernel<1><<<dim3(nb, (unsigned)ny), NN_THREADS, kNnSmem, s>>>(t->soa, t->aos, t->cap, t->size, q_dev + qoff * NWB_NJ,
-                                                                            nq - qoff, t->part_d + qoff * nb, t->part_i + qoff * nb);
+                                                                            nq - qoff, t->part_d + qoff * nb, t->part_i + qoff * nb,
+                                                                            t->tickets + y0, idx_dev + qoff, dist_dev ? dist_dev + qoff : nullptr);
     else
       nn_scan_kernel<8><<<dim3(nb, (unsigned)ny), NN_THREADS, kNnSmem, s>>>(t->soa, t->aos, t->cap, t->size, q_dev + qoff * NWB_NJ,
-                                                                            nq - qoff, t->part_d + qoff * nb, t->part_i + qoff * nb);
+                                                                            nq - qoff, t->part_d + qoff * nb, t->part_i + qoff * nb,
+                                                                            t->tickets + y0, idx_dev + qoff, dist_dev ? dist_dev + qoff : nullptr);
   }
-  nn_final_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, s>>>(t->part_d, t->part_i, nb, nq, idx_dev, dist_dev);
   TREE_CUDA(t, cudaGetLastError());
   TREE_CUDA(t, cudaEventRecord(t->ctx->ev1, s));
   t->ctx->last_ms = -1;
-  t->ctx->last_launches = (qtiles + 65534) / 65535 + 1;
+  t->ctx->last_launches = (qtiles + 65534) / 65535;
   t->ctx->last_nn_passes = qtiles;
   return NWB_OK;
 }
@@ -434,6 +472,7 @@ void nwb_tree_destroy(nwb_tree* t) {
   cudaFree(t->pred);
   cudaFree(t->part_d);
   cudaFree(t->part_i);
+  cudaFree(t->tickets);
   cudaFree(t->stage);
   delete t;
 }
