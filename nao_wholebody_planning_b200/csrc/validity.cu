@@ -238,7 +238,13 @@ constexpr int P2T = NWB_P2T;
 struct SmemStore2 {
   float2* base;   // shared memory, already offset by threadIdx.x
   __device__ __forceinline__ void put(int slot, F2 v) { base[slot * P2T] = v.v; }
-  __device__ __forceinline__ F2 get(int slot) const { return f2(base[slot * P2T]); }
+  // volatile: every use is a fresh LDS.64, so the compiler cannot pull the whole 222-float table of the
+  // two configurations into registers (which is what sank the first version: 255 registers + spills)
+  __device__ __forceinline__ F2 get(int slot) const {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"((unsigned)__cvta_generic_to_shared(base + slot * P2T)));
+    return f2(v);
+  }
 };
 
 template <typename QT, bool COLLISION_ONLY, int PAIRS>

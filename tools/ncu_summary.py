@@ -1,9 +1,10 @@
 #!/usr/bin/env python3
 """Summarise an ncu capture into profiles/: launch list shares + key metrics + SASS opcode mix.
 
-usage: tools/ncu_summary.py <launches.csv> <full.ncu-rep> <tag> [kernel-regex]
-Writes profiles/<tag>_launches.txt, profiles/<tag>_metrics.txt, profiles/<tag>_sass_mix.txt and
-profiles/validity_ncu_summary.json (read by bench.py for roofline.traffic).
+usage: tools/ncu_summary.py <launches.csv|-> <full.ncu-rep> <tag> [summary-name]
+Writes profiles/<tag>_launches.txt (skipped with "-"), profiles/<tag>_metrics.txt,
+profiles/<tag>_sass_mix.txt and profiles/<summary-name>_ncu_summary.json (default "validity":
+profiles/validity_ncu_summary.json is read by bench.py for roofline.traffic).
 """
 import csv
 import io
@@ -38,7 +39,14 @@ METRICS = [
 
 def main():
     launches, rep, tag = sys.argv[1], sys.argv[2], sys.argv[3]
+    summary_name = sys.argv[4] if len(sys.argv) > 4 else "validity"
     PROF.mkdir(exist_ok=True)
+    if launches != "-":
+        write_launch_list(launches, tag)
+    write_metrics(rep, tag, summary_name)
+
+
+def write_launch_list(launches, tag):
     rows = list(csv.reader(open(launches)))
     hdr = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
     h = rows[hdr]
@@ -52,6 +60,10 @@ def main():
         f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised: compare SHARES)\n# source: {launches}\n")
         for k, v in sorted(per.items(), key=lambda kv: -sum(kv[1])):
             f.write(f"{100 * sum(v) / tot:6.2f}%  n={len(v):3d}  avg={sum(v) / len(v) / 1e3:10.2f} us  max={max(v) / 1e3:10.2f} us  {k[:110]}\n")
+    print(open(PROF / f"{tag}_launches.txt").read())
+
+
+def write_metrics(rep, tag, summary_name):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rr = list(csv.reader(io.StringIO(raw)))
     h = rr[0]
@@ -71,7 +83,7 @@ def main():
     summary = {"kernel": rr[2][h.index("Kernel Name")], "duration_us_under_ncu": out["gpu__time_duration.sum"][0],
                "dram_bytes_per_launch": tobytes("dram__bytes_read.sum") + tobytes("dram__bytes_write.sum"),
                "registers": out["launch__registers_per_thread"][0], "source": Path(rep).name}
-    (PROF / "validity_ncu_summary.json").write_text(json.dumps(summary, indent=1) + "\n")
+    (PROF / f"{summary_name}_ncu_summary.json").write_text(json.dumps(summary, indent=1) + "\n")
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     sr = list(csv.reader(io.StringIO(src)))
     h = sr[1]
@@ -96,7 +108,6 @@ def main():
         f.write(f"# executed warp instructions by opcode (ncu source page), total {tot}\n")
         for op, c in ops.most_common(40):
             f.write(f"{op:10s} {c:12d} {100 * c / tot:6.2f}%  stall-samples {stalls[op]}\n")
-    print(open(PROF / f"{tag}_launches.txt").read())
     print(open(PROF / f"{tag}_metrics.txt").read())
     print(open(PROF / f"{tag}_sass_mix.txt").read()[:1500])
 
