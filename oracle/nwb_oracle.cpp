@@ -16,6 +16,7 @@
 #include <cstring>
 #include <thread>
 
+#include "arm_restated.h"
 #include "planner_restated.h"
 
 using namespace oracle;
@@ -351,6 +352,146 @@ int nwbo_solve_query(const nwb_params* p, const double* boxes, int nb, const dou
     stats[0] = r.success; stats[1] = r.iterations; stats[2] = r.num_nodes; stats[3] = r.nodes_start; stats[4] = r.nodes_goal;
   }
   return n;
+}
+
+// Right-arm position + direction solver (closed-form restatement of IKF:341-1517, oracle/arm_restated.h).
+void nwbo_arm5d_fk(const double* q, double* pos, double* dir) { arm5d_fk(q, pos, dir); }
+int nwbo_arm5d_ik(const double* pos, const double* dir, double* out /*[8][5]*/) { return arm5d_ik(pos, dir, out); }
+
+// ---- right arm / articulated-object constraint / goal sampling / services ----
+namespace {
+MaConstraint make_ma(const double* pts, int num_points) {
+  MaConstraint ma;
+  ma.num_points = num_points;
+  ma.pts.assign(pts, pts + (size_t)num_points * 6);
+  return ma;
+}
+ServiceParams make_service(const double* sv /*[13] or null*/) {
+  ServiceParams sp;
+  if (sv) {
+    sp.max_samples = (int)sv[0]; sp.max_ik_iterations = (int)sv[1]; sp.max_expand_iterations = (int)sv[2];
+    sp.advance_steps = sv[3];
+    for (int i = 0; i < 3; ++i) sp.w_approach[i] = sv[4 + i];
+    for (int i = 0; i < 3; ++i) sp.w_manipulate[i] = sv[7 + i];
+    sp.shortcut_waypoints = (int)sv[10]; sp.manipulate_waypoints = (int)sv[11]; sp.num_interp_points = (int)sv[12];
+  }
+  return sp;
+}
+int put_rows(const std::vector<double>& v, double* out, int cap_rows) {
+  int n = (int)(v.size() / NWB_NJ);
+  if (out) std::memcpy(out, v.data(), sizeof(double) * NWB_NJ * std::min(n, cap_rows));
+  return n;
+}
+void put_goal(const GoalResult& g, double* rows6, double* erg6, uint64_t* idx6, int32_t* found, uint64_t* drawn) {
+  if (rows6) std::memcpy(rows6, g.rows.data(), sizeof(double) * g.rows.size());
+  if (erg6) std::memcpy(erg6, g.ergonomics.data(), sizeof(double) * g.ergonomics.size());
+  if (idx6) std::memcpy(idx6, g.index.data(), sizeof(uint64_t) * g.index.size());
+  if (found) *found = g.num_found;
+  if (drawn) *drawn = g.samples_drawn;
+}
+}  // namespace
+
+// kind 0 = drawer (AOC:105-122), 1 = door (AOC:126-189); out [num_interp + 2][6].
+void nwbo_hand_trajectory(int kind, const double* start6, const double* goal6, int num_interp, const double* door4, double* out) {
+  MaConstraint ma = kind == 0 ? drawer_constraint(start6, goal6, num_interp) : door_constraint(start6, goal6, num_interp, door4);
+  std::memcpy(out, ma.pts.data(), sizeof(double) * ma.pts.size());
+}
+double nwbo_ergonomics_index(const double* arm5) { return ergonomics_index(arm5); }
+// FK of the sole->hand KDL chain (AOC:42-56): position + z-axis of the grasp frame.
+void nwbo_right_hand_fk(const double* q21, double* pos, double* zaxis) {
+  double q[10];
+  for (int i = 0; i < 5; ++i) q[i] = -q21[i];
+  for (int i = 0; i < 5; ++i) q[5 + i] = q21[10 + i];
+  Frame h = kdlr::fk(chains().r_leg_arm, q);
+  pos[0] = h.p.x; pos[1] = h.p.y; pos[2] = h.p.z;
+  zaxis[0] = h.M(0, 2); zaxis[1] = h.M(1, 2); zaxis[2] = h.M(2, 2);
+}
+// computeRightArmIK (NCK:224-506) for whole-body rows: ok[i], arm[i][5], ergonomics[i].
+void nwbo_goal_right_arm_ik_batch(const double* q /*[n][21]*/, int64_t n, const double* pose6, uint8_t* ok, double* arm,
+                                  double* ergonomics) {
+  for (int64_t i = 0; i < n; ++i) {
+    double rleg[5];
+    for (int k = 0; k < 5; ++k) rleg[k] = -q[i * NWB_NJ + k];
+    Frame hip = kdlr::fk(chains().right_leg, rleg);
+    double e = 0, a[5] = {0, 0, 0, 0, 0};
+    ok[i] = goal_right_arm_ik(hip, pose6, nwbm::kJointMin + 10, nwbm::kJointMax + 10, a, &e);
+    for (int k = 0; k < 5; ++k) arm[i * 5 + k] = a[k];
+    ergonomics[i] = e;
+  }
+}
+// enforce_MA_Constraints (RP:597-696) for n independent (q_near, q_new_ds) pairs.
+void nwbo_enforce_ma_batch(const double* pts, int num_points, int start_tree, const int32_t* near_hand_index,
+                           const double* q_near, const double* q_ds, int64_t n, double* q_out, int32_t* status) {
+  MaConstraint ma = make_ma(pts, num_points);
+  for (int64_t i = 0; i < n; ++i) {
+    double o[NWB_NJ];
+    for (int j = 0; j < NWB_NJ; ++j) o[j] = std::nan("");
+    status[i] = enforce_ma_constraints(ma, start_tree != 0, near_hand_index[i], q_near + i * NWB_NJ, q_ds + i * NWB_NJ, o);
+    std::memcpy(q_out + i * NWB_NJ, o, sizeof o);
+  }
+}
+// per-sample outcome of the goal branch for indices [first, first+count): stage 0/1/2, ergonomics, row.
+void nwbo_goal_sample_batch(const nwb_params* p, const double* boxes, int nb, uint64_t seed, uint64_t first, uint64_t count,
+                            const double* pose6, int max_ik_iter, uint8_t* stage, double* ergonomics, double* rows, int threads) {
+  PlanParams pp = make_params(p, boxes, nb);
+  parallel_for((int64_t)count, threads, [&](int64_t a, int64_t b) {
+    for (int64_t i = a; i < b; ++i) {
+      double q[NWB_NJ], e = 0;
+      stage[i] = (uint8_t)goal_sample(pp, seed, first + (uint64_t)i, pose6, max_ik_iter, q, &e);
+      if (ergonomics) ergonomics[i] = e;
+      if (rows) std::memcpy(rows + i * NWB_NJ, q, sizeof q);
+    }
+  });
+}
+void nwbo_sample_goal_configs(const nwb_params* p, const double* boxes, int nb, uint64_t seed, const double* pose6,
+                              int max_samples, int max_ik_iter, double* rows6, double* erg6, uint64_t* idx6, int32_t* found,
+                              uint64_t* drawn) {
+  PlanParams pp = make_params(p, boxes, nb);
+  put_goal(sample_goal_configs(pp, seed, pose6, max_samples, max_ik_iter), rows6, erg6, idx6, found, drawn);
+}
+// solve_query with an active articulation constraint (pts != null).
+int nwbo_solve_query_ma(const nwb_params* p, const double* boxes, int nb, const double* start, const double* goal,
+                        const double* db, int n_db, const double* w, uint64_t seed, int max_iter, double step,
+                        const double* pts, int num_points, double* raw_out, int cap, int32_t* stats) {
+  PlanParams pp = make_params(p, boxes, nb);
+  MaConstraint ma;
+  if (pts) ma = make_ma(pts, num_points);
+  SolveResult r = solve_query(pp, start, goal, db, n_db, w, seed, max_iter, step, pts ? &ma : nullptr);
+  int n = put_rows(r.raw_path, raw_out, cap);
+  if (stats) {
+    stats[0] = r.success; stats[1] = r.iterations; stats[2] = r.num_nodes; stats[3] = r.nodes_start; stats[4] = r.nodes_goal;
+  }
+  return n;
+}
+// compute_motion_plan (NPC:183-336).  stats = {success, num_nodes, goal configs found, way-points}.
+void nwbo_compute_motion_plan(const nwb_params* p, const double* boxes, int nb, const double* service13, const double* db,
+                              int n_db, const double* pose6, const double* start, int execute, uint64_t seed,
+                              double* goal_config, double* traj, double* tfs, int cap, int32_t* stats) {
+  PlanParams pp = make_params(p, boxes, nb);
+  MotionPlanOut o = compute_motion_plan(pp, make_service(service13), db, n_db, pose6, start, execute != 0, seed);
+  if (o.goal.num_found && goal_config) std::memcpy(goal_config, o.goal.rows.data(), sizeof(double) * NWB_NJ);
+  int n = put_rows(o.plan.trajectory, traj, cap);
+  if (tfs) std::memcpy(tfs, o.plan.time_from_start.data(), sizeof(double) * std::min(n, cap));
+  stats[0] = o.plan.success; stats[1] = o.plan.num_nodes; stats[2] = o.goal.num_found; stats[3] = n;
+}
+// compute_linear / compute_circular_manipulation_plan (NPC:338-588, 590-870).
+// stats = {success_approach, success_manipulation, nodes_approach, nodes_manipulate, goals_approach,
+//          goals_manipulate, way-points approach, way-points manipulation}.
+void nwbo_compute_manipulation_plan(const nwb_params* p, const double* boxes, int nb, const double* service13, const double* db,
+                                    int n_db, const double* pose6, const double* start, int circular, const double* object,
+                                    int execute, uint64_t seed, double* goal_approach, double* goal_manipulate,
+                                    double* traj_a, double* tfs_a, double* traj_m, double* tfs_m, int cap, int32_t* stats) {
+  PlanParams pp = make_params(p, boxes, nb);
+  ManipulationPlanOut o = compute_manipulation_plan(pp, make_service(service13), db, n_db, pose6, start, circular != 0, object,
+                                                    execute != 0, seed);
+  if (o.goal_approach.num_found && goal_approach) std::memcpy(goal_approach, o.goal_approach.rows.data(), sizeof(double) * NWB_NJ);
+  if (o.goal_manipulate.num_found && goal_manipulate) std::memcpy(goal_manipulate, o.goal_manipulate.rows.data(), sizeof(double) * NWB_NJ);
+  int na = put_rows(o.approach.trajectory, traj_a, cap), nm = put_rows(o.manipulation.trajectory, traj_m, cap);
+  if (tfs_a) std::memcpy(tfs_a, o.approach.time_from_start.data(), sizeof(double) * std::min(na, cap));
+  if (tfs_m) std::memcpy(tfs_m, o.manipulation.time_from_start.data(), sizeof(double) * std::min(nm, cap));
+  stats[0] = o.approach.success; stats[1] = o.manipulation.success; stats[2] = o.approach.num_nodes;
+  stats[3] = o.manipulation.num_nodes; stats[4] = o.goal_approach.num_found; stats[5] = o.goal_manipulate.num_found;
+  stats[6] = na; stats[7] = nm;
 }
 
 }  // extern "C"

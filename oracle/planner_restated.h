@@ -6,15 +6,20 @@
 //   LP  = rrt_connect_planner/src/local_planner.cpp
 //   SCG = rrt_connect_planner/src/stable_config_generator.cpp
 //   NCK = rrt_connect_planner/src/nao_constraint_kinematics.cpp
+//   AOC = rrt_connect_planner/src/articulated_object_constraints.cpp
+//   NPC = rrt_connect_planner/src/nao_planner_control.cpp
 // The reference seeds its RNG from the clock (random_numbers::RandomNumberGenerator, RPh:142), so
 // "identical results" is only defined with an injected stream: a counter-based Philox4x32-10
 // shared (as a specification, not as code) with the product - see DESIGN.md "random streams".
 #pragma once
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "../include/nwb.h"
+#include "arm_restated.h"
 #include "model_eval.h"
 
 namespace oracle {
@@ -47,7 +52,7 @@ inline double stream_uniform(uint64_t seed, uint32_t stream, uint64_t index, uin
 // ---------------------------------------------------------------------------------------------
 // The hand-built KDL chains (LP:18-47, NCK:23-47).
 struct Chains {
-  kdlr::Chain right_leg, left_leg, legs, right_arm;
+  kdlr::Chain right_leg, left_leg, legs, right_arm, r_leg_arm;
   Chains() {
     using namespace kdlr;
     auto rl = [](Chain& c) {
@@ -79,6 +84,9 @@ struct Chains {
     right_arm.add(RotZ, Vec{0.05595, 0, 0});
     right_arm.add(RotX, Vec{0.05775, 0, -0.01231});
     right_arm.add(None, Frame{rot_rpy(M_PI_2, 0, 0), Vec{0.01, 0, 0}});
+    // AOC:42-56: right sole -> hip -> right hand (grasp frame)
+    rl(r_leg_arm);
+    for (size_t i = 0; i < right_arm.segs.size(); ++i) r_leg_arm.segs.push_back(right_arm.segs[i]);
   }
 };
 inline const Chains& chains() {
@@ -228,12 +236,150 @@ inline int enforce_ds_constraints(const PlanParams& pp, const double* q_new, dou
 // RRT_Planner::isConfigValid (RP:701-745).
 inline bool is_config_valid(const PlanParams& pp, const double* q) { return is_feasible(pp.eval, q, nullptr, nullptr); }
 
-struct Node {  // RPh:30-36 (cart_hand_pose_index unused without an articulation constraint)
+// ---------------------------------------------------------------------------------------------
+// Articulated-object (manipulation) constraint: the hand must follow a discretised trajectory.
+struct MaConstraint {
+  int num_points = 0;             // num_interp_points + 2 (AOC:192-195)
+  std::vector<double> pts;        // [num_points][6]: position, direction of the hand z-axis
+  const double* pt(int i) const { return &pts[(size_t)i * 6]; }
+};
+// ArticulatedObjectConstraints::add_drawer_constraint + computeDrawerTrajectoryPoints (AOC:68-122).
+inline MaConstraint drawer_constraint(const double* start6, const double* goal6, int num_interp) {
+  MaConstraint ma;
+  ma.num_points = num_interp + 2;
+  ma.pts.resize((size_t)ma.num_points * 6);
+  double step[6];
+  for (int i = 0; i < 6; ++i) step[i] = (goal6[i] - start6[i]) / (num_interp + 1);
+  for (int s = 0; s < ma.num_points; ++s)
+    for (int i = 0; i < 6; ++i) ma.pts[(size_t)s * 6 + i] = start6[i] + (step[i] * s);
+  return ma;
+}
+// add_door_constraint + computeDoorTrajectoryPoints (AOC:86-189); door = {radius, opening angle [deg],
+// relative angle [deg], handle clearance}.
+inline MaConstraint door_constraint(const double* start6, const double* goal6, int num_interp, const double* door) {
+  MaConstraint ma;
+  ma.num_points = num_interp + 2;
+  ma.pts.resize((size_t)ma.num_points * 6);
+  double relative_angle = door[2] * (M_PI / 180);
+  double step_angle = (door[1] * (M_PI / 180)) / (num_interp + 1);
+  double sd[3];
+  for (int i = 0; i < 3; ++i) sd[i] = (goal6[3 + i] - start6[3 + i]) / (num_interp + 1);
+  double x_door = start6[0] + door[3] * std::cos(relative_angle);
+  double y_door = start6[1] - door[3] * std::sin(relative_angle);
+  double z_door = start6[2];
+  double x_hinge = x_door - door[0] * std::sin(relative_angle);
+  double y_hinge = y_door - door[0] * std::cos(relative_angle);
+  double z_hinge = z_door;
+  for (int s = 0; s < ma.num_points; ++s) {
+    double tmp_angle = ((step_angle * s) - relative_angle);
+    x_door = x_hinge - door[0] * std::sin(tmp_angle);
+    y_door = y_hinge + door[0] * std::cos(tmp_angle);
+    z_door = z_hinge;
+    tmp_angle = 1.5708 - tmp_angle;
+    double* o = &ma.pts[(size_t)s * 6];
+    o[0] = x_door - door[3] * std::sin(tmp_angle);
+    o[1] = y_door - door[3] * std::cos(tmp_angle);
+    o[2] = z_door;
+    for (int i = 0; i < 3; ++i) o[3 + i] = start6[3 + i] + (sd[i] * s);
+  }
+  return ma;
+}
+
+// Hand target of a pose given w.r.t. the right sole, expressed in the solver's torso frame
+// (NCK:226-282 == AOC:316-357): R = hip^T, pos = R (p - p_hip) - (0, 0, 0.085), dir = R d.
+inline void hand_target_in_torso(const Frame& hip, const double* pose6, double* pos, double* dir, kdlr::Rot* rot_out = nullptr) {
+  kdlr::Rot R = kdlr::transpose(hip.M);
+  for (int i = 0; i < 3; ++i) {
+    double tmp = -R(i, 0) * hip.p.x - R(i, 1) * hip.p.y - R(i, 2) * hip.p.z;
+    double tmp2 = R(i, 0) * pose6[0] + R(i, 1) * pose6[1] + R(i, 2) * pose6[2];
+    pos[i] = tmp + tmp2;
+  }
+  pos[2] = pos[2] - 0.085;
+  for (int i = 0; i < 3; ++i) dir[i] = R(i, 0) * pose6[3] + R(i, 1) * pose6[4] + R(i, 2) * pose6[5];
+  if (rot_out) *rot_out = R;
+}
+
+// ArticulatedObjectConstraints::right_hand_at_pose (AOC:204-262): FK of the sole->hand chain;
+// position within 5 mm and z-axis within 0.007 per component.
+inline bool right_hand_at_pose(const MaConstraint& ma, int pose_index, const double* r_leg5, const double* r_arm5) {
+  double q[10];
+  for (int i = 0; i < 5; ++i) q[i] = r_leg5[i];
+  for (int i = 0; i < 5; ++i) q[5 + i] = r_arm5[i];
+  Frame hand = kdlr::fk(chains().r_leg_arm, q);
+  const double* t = ma.pt(pose_index);
+  double e[6] = {std::fabs(hand.p.x - t[0]), std::fabs(hand.p.y - t[1]), std::fabs(hand.p.z - t[2]),
+                 std::fabs(hand.M(0, 2) - t[3]), std::fabs(hand.M(1, 2) - t[4]), std::fabs(hand.M(2, 2) - t[5])};
+  double max_pos = 0.0, max_dir = 0.0;
+  for (int i = 0; i < 3; ++i)
+    if (e[i] > max_pos) max_pos = e[i];
+  for (int i = 3; i < 6; ++i)
+    if (e[i] > max_dir) max_dir = e[i];
+  if (max_pos > 0.005) return false;
+  if (max_dir > 0.007) return false;
+  return true;
+}
+
+// ArticulatedObjectConstraints::compute_right_arm_IK (AOC:313-449): of the solutions inside the
+// (strict) joint limits take the one with the smallest L1 distance to the reference arm posture.
+inline bool ma_right_arm_ik(const MaConstraint& ma, int pose_index, const double* r_leg5, const double* arm_ref5,
+                            const double* mn5, const double* mx5, double* out5) {
+  Frame hip = kdlr::fk(chains().right_leg, r_leg5);
+  double pos[3], dir[3], sols[8 * 5];
+  hand_target_in_torso(hip, ma.pt(pose_index), pos, dir);
+  int n = arm5d_ik(pos, dir, sols);
+  if (n == 0) return false;
+  double best = 10000.0;
+  int best_i = 1000;
+  for (int s = 0; s < n; ++s) {
+    if (!check_joint_limits(sols + s * 5, mn5, mx5, 5)) continue;
+    double dist = 0.0;
+    for (int i = 0; i < 5; ++i) dist = dist + std::fabs(arm_ref5[i] - sols[s * 5 + i]);
+    if (dist < best) {
+      best = dist;
+      best_i = s;
+    }
+  }
+  if (best < 1000) {
+    for (int i = 0; i < 5; ++i) out5[i] = sols[best_i * 5 + i];
+    return true;
+  }
+  return false;
+}
+
+// RRT_Planner::enforce_MA_Constraints (RP:597-696).  near_hand_index = q_near.cart_hand_pose_index.
+inline int enforce_ma_constraints(const MaConstraint& ma, bool start_tree, int near_hand_index, const double* q_near,
+                                  const double* q_new_ds, double* q_new_manip) {
+  int desired;
+  if (start_tree && near_hand_index <= ma.num_points - 2)
+    desired = near_hand_index + 1;
+  else if (!start_tree && near_hand_index > 0)
+    desired = near_hand_index - 1;
+  else
+    desired = near_hand_index;
+  double r_leg[5], r_arm[5];
+  for (int i = 0; i < 5; ++i) r_leg[i] = -q_new_ds[i];
+  for (int i = 10; i < 15; ++i) r_arm[i - 10] = q_new_ds[i];
+  if (right_hand_at_pose(ma, desired, r_leg, r_arm)) {
+    for (int i = 0; i < NWB_NJ; ++i) q_new_manip[i] = q_new_ds[i];
+    return NWB_REACHED;
+  }
+  double sol[5];
+  if (ma_right_arm_ik(ma, desired, r_leg, q_near + 10, nwbm::kJointMin + 10, nwbm::kJointMax + 10, sol)) {
+    for (int i = 0; i < NWB_NJ; ++i) q_new_manip[i] = q_new_ds[i];
+    for (int i = 10; i < 15; ++i) q_new_manip[i] = sol[i - 10];
+    return NWB_ADVANCED;
+  }
+  return NWB_TRAPPED;
+}
+
+struct Node {  // RPh:30-36
   int index, predecessor_index;
   double config[NWB_NJ];
+  int cart_hand_pose_index = 0;
 };
 struct Tree {
   std::vector<Node> nodes;
+  bool start_tree = true;          // Tree::name == "start_tree" (RP:95-96)
 };
 
 // RRT_Planner::findNearestNeighbour (RP:336-419): strict <, initial best 10000.0 -> first minimum
@@ -274,38 +420,60 @@ inline int nearest_in_tree(const Tree& t, const double* q) {
   return nn;
 }
 
-inline void add_config(Tree& t, int near_index, const double* q) {  // RP:749-783
+// RRT_Planner::addConfigtoTree (RP:749-783).  Note the bound `< num_points - 2` here against
+// `<= num_points - 2` in enforce_MA_Constraints (RP:607): kept as shipped.
+inline void add_config(Tree& t, int near_index, const double* q, const MaConstraint* ma = nullptr, int near_hand_index = 0) {
   Node n;
   n.index = (int)t.nodes.size();
   n.predecessor_index = near_index;
   for (int i = 0; i < NWB_NJ; ++i) n.config[i] = q[i];
+  if (ma) {
+    if (t.start_tree && near_hand_index < ma->num_points - 2)
+      n.cart_hand_pose_index = near_hand_index + 1;
+    else if (!t.start_tree && near_hand_index > 0)
+      n.cart_hand_pose_index = near_hand_index - 1;
+    else
+      n.cart_hand_pose_index = near_hand_index;
+  }
   t.nodes.push_back(n);
 }
 
-// RRT_Planner::extendTree (RP:787-884), articulation constraint inactive.
-inline int extend_tree(const PlanParams& pp, Tree& t, const double* q_rand, const double* w, double step, int* q_near_idx) {
+// RRT_Planner::extendTree (RP:787-884).
+inline int extend_tree(const PlanParams& pp, Tree& t, const double* q_rand, const double* w, double step, int* q_near_idx,
+                       const MaConstraint* ma = nullptr) {
   int nn = nearest_in_tree(t, q_rand);
   *q_near_idx = nn;
-  double q_new[NWB_NJ], q_mod[NWB_NJ];
+  double q_new[NWB_NJ], q_mod[NWB_NJ], q_manip[NWB_NJ];
   int state = generate_q_new(t.nodes[nn].config, q_rand, w, step, q_new);
   int ds = enforce_ds_constraints(pp, q_new, q_mod);
   if (ds == NWB_TRAPPED) return NWB_TRAPPED;
   if (ds == NWB_ADVANCED) state = NWB_ADVANCED;
-  if (!is_config_valid(pp, q_mod)) return NWB_TRAPPED;
-  add_config(t, t.nodes[nn].index, q_mod);
+  if (ma) {
+    int mas = enforce_ma_constraints(*ma, t.start_tree, t.nodes[nn].cart_hand_pose_index, t.nodes[nn].config, q_mod, q_manip);
+    if (mas == NWB_TRAPPED) return NWB_TRAPPED;
+    if (mas == NWB_ADVANCED) state = NWB_ADVANCED;
+  } else {
+    for (int i = 0; i < NWB_NJ; ++i) q_manip[i] = q_mod[i];
+  }
+  if (!is_config_valid(pp, q_manip)) return NWB_TRAPPED;
+  add_config(t, t.nodes[nn].index, q_manip, ma, t.nodes[nn].cart_hand_pose_index);
   return state;
 }
 
-// RRT_Planner::connectTree (RP:890-1034), articulation constraint inactive.  *q_near_idx is the
-// node that finally connected (RP:1000-1001) or the initial nearest neighbour.
+// RRT_Planner::connectTree (RP:890-1034).  *q_near_idx is the node that finally connected
+// (RP:1000-1001) or the initial nearest neighbour.  connect_hand_index = q_connect.cart_hand_pose_index.
 inline int connect_tree(const PlanParams& pp, Tree& t, const double* q_connect, const double* w, double step,
-                        int* q_near_idx, int* steps_out = nullptr) {
+                        int* q_near_idx, int* steps_out = nullptr, const MaConstraint* ma = nullptr,
+                        int connect_hand_index = 0) {
   int nn = nearest_in_tree(t, q_connect);
   *q_near_idx = nn;
   int cur = nn;
+  if (steps_out) *steps_out = 0;
+  if (ma && t.start_tree && t.nodes[nn].cart_hand_pose_index > connect_hand_index) return NWB_TRAPPED;   // RP:917
+  if (ma && !t.start_tree && t.nodes[nn].cart_hand_pose_index < connect_hand_index) return NWB_TRAPPED;  // RP:921
   int state = NWB_ADVANCED, steps = 0;
   while (state != NWB_TRAPPED && state != NWB_REACHED) {
-    double q_new[NWB_NJ], q_mod[NWB_NJ];
+    double q_new[NWB_NJ], q_mod[NWB_NJ], q_manip[NWB_NJ];
     state = generate_q_new(t.nodes[cur].config, q_connect, w, step, q_new);
     ++steps;
     int ds = enforce_ds_constraints(pp, q_new, q_mod);
@@ -314,11 +482,20 @@ inline int connect_tree(const PlanParams& pp, Tree& t, const double* q_connect, 
       break;
     }
     if (ds == NWB_ADVANCED) state = NWB_ADVANCED;
-    if (!is_config_valid(pp, q_mod)) {
+    bool proceed = true;
+    if (ma) {
+      int mas = enforce_ma_constraints(*ma, t.start_tree, t.nodes[cur].cart_hand_pose_index, t.nodes[cur].config, q_mod, q_manip);
+      if (mas == NWB_TRAPPED) proceed = false;
+      if (mas == NWB_ADVANCED) state = NWB_ADVANCED;
+      if (t.nodes[cur].cart_hand_pose_index == connect_hand_index && state != NWB_REACHED) proceed = false;  // RP:968
+    } else {
+      for (int i = 0; i < NWB_NJ; ++i) q_manip[i] = q_mod[i];
+    }
+    if (!proceed || !is_config_valid(pp, q_manip)) {
       state = NWB_TRAPPED;
       break;
     }
-    add_config(t, t.nodes[cur].index, q_mod);
+    add_config(t, t.nodes[cur].index, q_manip, ma, t.nodes[cur].cart_hand_pose_index);
     if (state == NWB_REACHED)
       *q_near_idx = cur;
     else
@@ -421,14 +598,20 @@ inline int random_db_index(unsigned quirks, uint64_t seed, uint64_t iteration, i
 }
 
 // RRT_Planner::setStartGoalConfigs + solveQuery + writePath path extraction
-// (RP:227-302, RP:1039-1212, RP:1303-1392), articulation constraint inactive.
+// (RP:227-302, RP:1039-1212, RP:1303-1392); `ma` = the active articulation constraint or nullptr.
 inline SolveResult solve_query(const PlanParams& pp, const double* start, const double* goal, const double* db,
-                               int n_db, const double* w, uint64_t seed, int max_iter, double step) {
+                               int n_db, const double* w, uint64_t seed, int max_iter, double step,
+                               const MaConstraint* ma = nullptr) {
   SolveResult res;
   if (!is_config_valid(pp, start) || !is_config_valid(pp, goal)) return res;
   Tree Ts, Tg;
+  Tg.start_tree = false;
   add_config(Ts, 0, start);
   add_config(Tg, 0, goal);
+  if (ma) {  // RP:274-282
+    Ts.nodes[0].cart_hand_pose_index = 0;
+    Tg.nodes[0].cart_hand_pose_index = ma->num_points - 1;
+  }
   bool swap = false;
   for (int it = 0; it < max_iter; ++it) {
     res.iterations = it + 1;
@@ -436,9 +619,10 @@ inline SolveResult solve_query(const PlanParams& pp, const double* start, const 
     Tree& Ta = swap ? Tg : Ts;
     Tree& Tb = swap ? Ts : Tg;
     int q_near = -1;
-    int returned = extend_tree(pp, Ta, q_rand, w, step, &q_near);
+    int returned = extend_tree(pp, Ta, q_rand, w, step, &q_near, ma);
     if (returned != NWB_TRAPPED) {
-      int found = connect_tree(pp, Tb, Ta.nodes.back().config, w, step, &q_near);
+      int found = connect_tree(pp, Tb, Ta.nodes.back().config, w, step, &q_near, nullptr, ma,
+                               Ta.nodes.back().cart_hand_pose_index);
       if (found == NWB_REACHED) {
         // writePath: connector 1 = goal tree connected to start tree (RP:1317-1327)
         int idx_s = swap ? q_near : Ts.nodes.back().index;
@@ -497,6 +681,273 @@ inline void sample_stable_configs(const PlanParams& pp, uint64_t seed, uint64_t 
     }
     if (stage_out) stage_out->push_back(stage);
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Goal-configuration sampling.
+
+// ConstraintKinematics::compute_ergonomics_index (NCK:612-659): q0 * |"determinant"| where the
+// "determinant" of the 6x5 arm Jacobian is the shipped diagonal-product formula over [J J]:
+// forward sum of the 5 wrapped diagonals minus a "backward" sum that multiplies ONE column down all
+// six rows (quirk C15: not an anti-diagonal).
+inline double ergonomics_index(const double* arm5) {
+  double J[6 * 5];
+  kdlr::jacobian(chains().right_arm, arm5, J);
+  const int cols = 5, nc = 10;
+  double M[6][10];
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < cols; ++j) {
+      M[i][j] = J[i * cols + j];
+      M[i][j + cols] = M[i][j];
+    }
+  double sum_fw = 0.0, sum_bw = 0.0;
+  for (int i = 0; i < cols; ++i) {
+    sum_fw = sum_fw + (M[0][i] * M[1][i + 1] * M[2][i + 2] * M[3][i + 3] * M[4][i + 4] * M[5][i + 5]);
+    int c = nc - (1 + i);
+    sum_bw = sum_bw - (M[0][c] * M[1][c] * M[2][c] * M[3][c] * M[4][c] * M[5][c]);
+  }
+  double det_jac = std::fabs(sum_fw - sum_bw);
+  return arm5[0] * det_jac;
+}
+
+// ConstraintKinematics::computeRightArmIK, generated-solver branch (NCK:374-506): among the
+// solutions inside the strict limits keep the one with the LARGEST ergonomics index, starting from
+// 0.0 - a posture with RShoulderPitch <= 0 can therefore never be chosen (quirk C16).
+// (The position-only KDL branch NCK:291-372, taken when the direction is exactly (0,0,0), is not
+// restated: no shipped caller reaches it.)
+inline bool goal_right_arm_ik(const Frame& hip, const double* pose6, const double* mn5, const double* mx5,
+                              double* out5, double* ergonomics) {
+  double pos[3], dir[3], sols[8 * 5];
+  hand_target_in_torso(hip, pose6, pos, dir);
+  int n = arm5d_ik(pos, dir, sols);
+  if (n == 0) return false;
+  double best = 0.0;
+  int best_i = 1000;
+  for (int s = 0; s < n; ++s) {
+    if (!check_joint_limits(sols + s * 5, mn5, mx5, 5)) continue;
+    double e = ergonomics_index(sols + s * 5);
+    if (e > best) {
+      best = e;
+      best_i = s;
+    }
+  }
+  if (best_i == 1000) return false;
+  *ergonomics = best;
+  for (int i = 0; i < 5; ++i) out5[i] = sols[best_i * 5 + i];
+  return true;
+}
+
+constexpr double kGoalLeftArm[5] = {1.5708, 0.17, 0.0, -0.036, 0.0};  // SCG:296-300
+constexpr int kGoalSamplesWanted = 6;                                  // SCG:429 `goal_samples > 5`
+
+// One sample of the goal branch of sample_stable_configs (SCG:278-436): returns 0 = rejected,
+// 1 = both IKs solved but infeasible, 2 = accepted (q, ergonomics valid).
+inline int goal_sample(const PlanParams& pp, uint64_t seed, uint64_t i, const double* pose6, int max_ik_iter, double* q,
+                       double* ergonomics) {
+  for (int j = 0; j < NWB_NJ; ++j) {
+    double u = stream_uniform(seed, kStreamSampler, i, (uint32_t)j);
+    q[j] = (nwbm::kJointMax[j] - nwbm::kJointMin[j]) * u + nwbm::kJointMin[j];
+  }
+  q[15] = 0.0;
+  for (int k = 0; k < 5; ++k) q[5 + k] = kGoalLeftArm[k];
+  double rleg[5], lleg[5], rarm[5];
+  for (int k = 0; k < 5; ++k) rleg[k] = -q[k];
+  if (!left_leg_ik_sampler(pp, rleg, nwbm::kJointMin + 16, nwbm::kJointMax + 16, max_ik_iter, lleg)) return 0;
+  Frame hip = kdlr::fk(chains().right_leg, rleg);
+  if (!goal_right_arm_ik(hip, pose6, nwbm::kJointMin + 10, nwbm::kJointMax + 10, rarm, ergonomics)) return 0;
+  for (int k = 0; k < 5; ++k) q[16 + k] = lleg[k];
+  for (int k = 0; k < 5; ++k) q[10 + k] = rarm[k];
+  return is_feasible(pp.eval, q, nullptr, nullptr) ? 2 : 1;
+}
+
+// "%g" text round trip of the goal files (SCG:409-417 written, SCG:540-560 / 666-700 re-read).
+inline double through_text(double v) {
+  char buf[64];
+  std::snprintf(buf, sizeof buf, "%g", v);
+  return std::strtod(buf, nullptr);
+}
+
+struct GoalResult {
+  int num_found = 0;              // return value of sample_stable_configs (<= 6)
+  uint64_t samples_drawn = 0;     // loop iterations consumed
+  std::vector<double> rows;       // [num_found][21] sorted by ergonomics (descending), text-rounded
+  std::vector<double> ergonomics; // same order
+  std::vector<uint64_t> index;    // sample index of each row
+};
+
+// sample_stable_configs(max_samples, max_ik_iter, t, true, file) + sort_goal_configs_by_ergonomy
+// (SCG:176-507, 510-661); loadGoalConfig (SCG:666-756) then takes rows[0].
+inline GoalResult sample_goal_configs(const PlanParams& pp, uint64_t seed, const double* pose6, int max_samples,
+                                      int max_ik_iter) {
+  GoalResult g;
+  std::vector<double> rows, erg;
+  for (uint64_t i = 0; i < (uint64_t)max_samples; ++i) {
+    g.samples_drawn = i + 1;
+    double q[NWB_NJ], e = 0.0;
+    if (goal_sample(pp, seed, i, pose6, max_ik_iter, q, &e) != 2) continue;
+    erg.push_back(through_text(e));
+    for (int j = 0; j < NWB_NJ; ++j) rows.push_back(through_text(q[j]));
+    g.index.push_back(i);
+    if ((int)erg.size() > kGoalSamplesWanted - 1) break;
+  }
+  g.num_found = (int)erg.size();
+  // SCG:585-612: n rounds of "largest remaining value > 0.0", the winner zeroed afterwards
+  std::vector<double> e2 = erg;
+  std::vector<int> order(erg.size());
+  int imax = 0;
+  for (size_t n = 0; n < e2.size(); ++n) {
+    double vmax = 0.0;
+    for (size_t i = 0; i < e2.size(); ++i)
+      if (e2[i] > vmax) {
+        vmax = e2[i];
+        imax = (int)i;
+      }
+    order[n] = imax;
+    e2[imax] = 0.0;
+  }
+  std::vector<uint64_t> idx2;
+  for (size_t n = 0; n < order.size(); ++n) {
+    g.rows.insert(g.rows.end(), rows.begin() + order[n] * NWB_NJ, rows.begin() + (order[n] + 1) * NWB_NJ);
+    g.ergonomics.push_back(erg[order[n]]);
+    idx2.push_back(g.index[order[n]]);
+  }
+  g.index = idx2;
+  return g;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Service level (NPC:150-870).  Wall-clock outputs (time_goal_config, search_time) are not part of
+// the restatement.  Seeds: goal sampling uses `seed` (approach) and `seed + 1` (manipulation),
+// planning uses `seed + 2` and `seed + 3` - a convention shared with the product.
+struct ServiceParams {                 // NPC:20-33 defaults overridden by planning_parameters.yaml
+  int max_samples = 5000, max_ik_iterations = 5, max_expand_iterations = 8000;
+  double advance_steps = 0.1;
+  double w_approach[3] = {1.0, 1.0, 1.0};      // r_arm, l_arm, legs
+  double w_manipulate[3] = {1.0, 0.0, 1.0};
+  int shortcut_waypoints = 100, manipulate_waypoints = 4, shortcut_rounds = 500;   // RP:1397-1398, RP:1851
+  int num_interp_points = 20;                  // NPC:539,822
+};
+inline void limb_weights(const double* w3, double* w21) {  // NPC:280-306
+  for (int i = 0; i < 5; ++i) w21[i] = w3[2];
+  for (int i = 5; i < 10; ++i) w21[i] = w3[1];
+  for (int i = 10; i < 15; ++i) w21[i] = w3[0];
+  w21[15] = 0.0;
+  for (int i = 16; i < 21; ++i) w21[i] = w3[2];
+}
+
+struct PlanOut {
+  bool success = false;
+  int num_nodes = 0;
+  std::vector<double> trajectory;      // way-points of the DisplayTrajectory
+  std::vector<double> time_from_start; // before time parameterisation: 2.0 + i * increment (RP:1532-1553)
+};
+
+// writePath after a successful solveQuery (RP:1303-1455): shortcut + densify (free motion) or
+// densify with 4 way-points (articulated motion); `execute` = setTrajectoryMode(true).
+inline void finish_path(const PlanParams& pp, const ServiceParams& sp, const SolveResult& r, bool articulated,
+                        bool execute, double time_step_manip, PlanOut& out) {
+  std::vector<double> path;
+  if (!articulated) {
+    std::vector<double> shortp;
+    bool ok = path_shortcutter(pp, r.raw_path, sp.shortcut_waypoints, sp.shortcut_rounds, shortp);
+    if (ok) {
+      if (!execute) interpolate_short_path(shortp, sp.shortcut_waypoints, path);
+      else path = shortp;
+    }   // RP:1919-1926: on failure shortcutted_path stays empty
+  } else {
+    if (!execute) interpolate_short_path(r.raw_path, sp.manipulate_waypoints, path);
+    else path = r.raw_path;
+  }
+  out.trajectory = path;
+  float increment = 2.0f;
+  for (size_t i = 0; i < path.size() / NWB_NJ; ++i) {
+    out.time_from_start.push_back((double)increment);
+    increment = articulated ? increment + (float)time_step_manip : increment + 1.0f;
+  }
+  out.success = !path.empty();
+  out.num_nodes = r.num_nodes;
+}
+
+struct MotionPlanOut {
+  GoalResult goal;
+  PlanOut plan;
+};
+// NAO_PLANNER_CONTROL::compute_motion_plan (NPC:183-336).
+inline MotionPlanOut compute_motion_plan(const PlanParams& pp, const ServiceParams& sp, const double* db, int n_db,
+                                         const double* pose6, const double* start, bool execute, uint64_t seed) {
+  MotionPlanOut o;
+  o.goal = sample_goal_configs(pp, seed, pose6, sp.max_samples, sp.max_ik_iterations);
+  if (o.goal.num_found == 0) return o;
+  double w[NWB_NJ];
+  limb_weights(sp.w_approach, w);
+  SolveResult r = solve_query(pp, start, o.goal.rows.data(), db, n_db, w, seed + 2, sp.max_expand_iterations, sp.advance_steps);
+  if (r.success) finish_path(pp, sp, r, false, execute, 0.0, o.plan);
+  return o;
+}
+
+struct ManipulationPlanOut {
+  GoalResult goal_approach, goal_manipulate;
+  PlanOut approach, manipulation;
+  double pose_manipulate[6] = {0, 0, 0, 0, 0, 0};
+};
+// compute_linear_manipulation_plan (NPC:338-588) and compute_circular_manipulation_plan (NPC:590-870):
+// `object` = {relative_angle, translation_length} (linear) or {relative_angle, rotation_radius,
+// rotation_angle, clearance_handle} (circular).
+inline ManipulationPlanOut compute_manipulation_plan(const PlanParams& pp, const ServiceParams& sp, const double* db,
+                                                     int n_db, const double* pose6, const double* start, bool circular,
+                                                     const double* object, bool execute, uint64_t seed) {
+  ManipulationPlanOut o;
+  o.goal_approach = sample_goal_configs(pp, seed, pose6, sp.max_samples, sp.max_ik_iterations);
+  if (o.goal_approach.num_found == 0) return o;
+  double w[NWB_NJ];
+  limb_weights(sp.w_approach, w);
+  const double* goal_a = o.goal_approach.rows.data();
+  SolveResult r = solve_query(pp, start, goal_a, db, n_db, w, seed + 2, sp.max_expand_iterations, sp.advance_steps);
+  if (r.success) finish_path(pp, sp, r, false, execute, 0.0, o.approach);
+  if (!o.approach.success) return o;
+  double* pm = o.pose_manipulate;
+  MaConstraint ma;
+  float time_step;
+  const float manipulation_velocity = 0.02f;   // RP:92
+  if (!circular) {
+    double pos_angle = (90.0 - object[0]) * (M_PI / 180);                          // NPC:502
+    pm[0] = pose6[0] - object[1] * std::sin(pos_angle);
+    pm[1] = pose6[1] + object[1] * std::cos(pos_angle);
+    pm[2] = pose6[2];
+  } else {                                                                          // NPC:762-790
+    double rel = object[0] * (M_PI / 180);
+    double x_door = pose6[0] + object[3] * std::cos(rel);
+    double y_door = pose6[1] - object[3] * std::sin(rel);
+    double z_door = pose6[2];
+    double x_hinge = x_door - object[1] * std::sin(rel);
+    double y_hinge = y_door - object[1] * std::cos(rel);
+    double tmp_angle = (object[2] - object[0]) * (M_PI / 180);
+    x_door = x_hinge - object[1] * std::sin(tmp_angle);
+    y_door = y_hinge + object[1] * std::cos(tmp_angle);
+    tmp_angle = 1.5708 - tmp_angle;
+    pm[0] = x_door - object[3] * std::sin(tmp_angle);
+    pm[1] = y_door - object[3] * std::cos(tmp_angle);
+    pm[2] = z_door;
+  }
+  for (int i = 3; i < 6; ++i) pm[i] = pose6[i];
+  o.goal_manipulate = sample_goal_configs(pp, seed + 1, pm, sp.max_samples, sp.max_ik_iterations);
+  if (o.goal_manipulate.num_found == 0) return o;
+  if (!circular) {                                                                  // RP:195-206
+    ma = drawer_constraint(pose6, pm, sp.num_interp_points);
+    float manipulation_time = (float)(object[1]) / manipulation_velocity;
+    time_step = manipulation_time / float(sp.num_interp_points + 2);
+  } else {                                                                          // NPC:816-822, RP:209-223
+    double door[4] = {object[1], object[2], object[0], object[3]};
+    ma = door_constraint(pose6, pm, sp.num_interp_points, door);
+    float arc_length = float(door[0] * M_PI * door[1]) / 180.0f;
+    float manipulation_time = arc_length / manipulation_velocity;
+    time_step = manipulation_time / float(sp.num_interp_points + 2);
+  }
+  limb_weights(sp.w_manipulate, w);
+  SolveResult r2 = solve_query(pp, goal_a, o.goal_manipulate.rows.data(), db, n_db, w, seed + 3, sp.max_expand_iterations,
+                               sp.advance_steps, &ma);
+  if (r2.success) finish_path(pp, sp, r2, true, execute, (double)time_step, o.manipulation);
+  return o;
 }
 
 }  // namespace oracle

@@ -31,6 +31,7 @@ class Oracle:
         L.nwbo_stream_uniform.restype = C.c_double
         L.nwbo_stream_uniform.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32]
         L.nwbo_sample_stable_configs.restype = C.c_int64
+        L.nwbo_ergonomics_index.restype = C.c_double
         self.threads = L.nwbo_hardware_threads()
 
     @staticmethod
@@ -227,6 +228,132 @@ class Oracle:
                                       C.c_uint64(seed), max_iter, C.c_double(step), _ptr(raw), cap, _ptr(stats))
         return raw[:min(n, cap)].copy(), dict(success=bool(stats[0]), iterations=int(stats[1]), num_nodes=int(stats[2]),
                                                nodes_start=int(stats[3]), nodes_goal=int(stats[4]))
+
+    # ---- right arm, articulated-object constraint, goal sampling, services ----
+    def arm5d_fk(self, q5):
+        q5 = np.ascontiguousarray(q5, dtype=np.float64)
+        pos, d = np.empty(3), np.empty(3)
+        self.lib.nwbo_arm5d_fk(_ptr(q5), _ptr(pos), _ptr(d))
+        return pos, d
+
+    def arm5d_ik(self, pos, d):
+        pos = np.ascontiguousarray(pos, dtype=np.float64)
+        d = np.ascontiguousarray(d, dtype=np.float64)
+        out = np.empty((8, 5))
+        n = self.lib.nwbo_arm5d_ik(_ptr(pos), _ptr(d), _ptr(out))
+        return out[:n].copy()
+
+    def hand_trajectory(self, kind, start6, goal6, num_interp=20, door4=None):
+        start6 = np.ascontiguousarray(start6, dtype=np.float64)
+        goal6 = np.ascontiguousarray(goal6, dtype=np.float64)
+        door4 = None if door4 is None else np.ascontiguousarray(door4, dtype=np.float64)
+        out = np.empty((num_interp + 2, 6))
+        self.lib.nwbo_hand_trajectory(kind, _ptr(start6), _ptr(goal6), num_interp, _ptr(door4), _ptr(out))
+        return out
+
+    def ergonomics_index(self, arm5):
+        arm5 = np.ascontiguousarray(arm5, dtype=np.float64)
+        return self.lib.nwbo_ergonomics_index(_ptr(arm5))
+
+    def right_hand_fk(self, q):
+        q = np.ascontiguousarray(q, dtype=np.float64).reshape(NJ)
+        pos, z = np.empty(3), np.empty(3)
+        self.lib.nwbo_right_hand_fk(_ptr(q), _ptr(pos), _ptr(z))
+        return pos, z
+
+    def goal_right_arm_ik(self, q, pose6):
+        q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, NJ)
+        pose6 = np.ascontiguousarray(pose6, dtype=np.float64)
+        n = len(q)
+        ok, arm, erg = np.empty(n, np.uint8), np.empty((n, 5)), np.empty(n)
+        self.lib.nwbo_goal_right_arm_ik_batch(_ptr(q), C.c_int64(n), _ptr(pose6), _ptr(ok), _ptr(arm), _ptr(erg))
+        return ok, arm, erg
+
+    def enforce_ma(self, pts, start_tree, near_hand_index, q_near, q_ds):
+        pts = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 6)
+        q_near = np.ascontiguousarray(q_near, dtype=np.float64).reshape(-1, NJ)
+        q_ds = np.ascontiguousarray(q_ds, dtype=np.float64).reshape(-1, NJ)
+        hi = np.ascontiguousarray(near_hand_index, dtype=np.int32)
+        out = np.empty_like(q_ds)
+        st = np.empty(len(q_ds), np.int32)
+        self.lib.nwbo_enforce_ma_batch(_ptr(pts), len(pts), int(start_tree), _ptr(hi), _ptr(q_near), _ptr(q_ds),
+                                       C.c_int64(len(q_ds)), _ptr(out), _ptr(st))
+        return out, st
+
+    def goal_sample_batch(self, seed, first, count, pose6, max_ik_iter=5, params=None, boxes=None, threads=1):
+        p = params or default_params()
+        b, nb = self._boxes(boxes)
+        pose6 = np.ascontiguousarray(pose6, dtype=np.float64)
+        stage, erg, rows = np.empty(count, np.uint8), np.empty(count), np.empty((count, NJ))
+        self.lib.nwbo_goal_sample_batch(C.byref(p), _ptr(b), nb, C.c_uint64(seed), C.c_uint64(first), C.c_uint64(count),
+                                        _ptr(pose6), max_ik_iter, _ptr(stage), _ptr(erg), _ptr(rows), threads)
+        return stage, erg, rows
+
+    def sample_goal_configs(self, seed, pose6, max_samples=5000, max_ik_iter=5, params=None, boxes=None):
+        p = params or default_params()
+        b, nb = self._boxes(boxes)
+        pose6 = np.ascontiguousarray(pose6, dtype=np.float64)
+        rows, erg, idx = np.zeros((6, NJ)), np.zeros(6), np.zeros(6, np.uint64)
+        found, drawn = C.c_int32(0), C.c_uint64(0)
+        self.lib.nwbo_sample_goal_configs(C.byref(p), _ptr(b), nb, C.c_uint64(seed), _ptr(pose6), max_samples, max_ik_iter,
+                                          _ptr(rows), _ptr(erg), _ptr(idx), C.byref(found), C.byref(drawn))
+        n = found.value
+        return rows[:n].copy(), erg[:n].copy(), idx[:n].copy(), drawn.value
+
+    def solve_query_ma(self, start, goal, db, w, seed, pts, max_iter=8000, step=0.1, params=None, boxes=None, cap=8192):
+        start = np.ascontiguousarray(start, dtype=np.float64)
+        goal = np.ascontiguousarray(goal, dtype=np.float64)
+        db = np.ascontiguousarray(db, dtype=np.float64).reshape(-1, NJ)
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        pts = None if pts is None else np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 6)
+        p = params or default_params()
+        b, nb = self._boxes(boxes)
+        raw = np.empty((cap, NJ))
+        stats = np.zeros(5, np.int32)
+        n = self.lib.nwbo_solve_query_ma(C.byref(p), _ptr(b), nb, _ptr(start), _ptr(goal), _ptr(db), len(db), _ptr(w),
+                                         C.c_uint64(seed), max_iter, C.c_double(step), _ptr(pts), 0 if pts is None else len(pts),
+                                         _ptr(raw), cap, _ptr(stats))
+        return raw[:min(n, cap)].copy(), dict(success=bool(stats[0]), iterations=int(stats[1]), num_nodes=int(stats[2]),
+                                               nodes_start=int(stats[3]), nodes_goal=int(stats[4]))
+
+    @staticmethod
+    def _service(service):
+        return None if service is None else np.ascontiguousarray(service, dtype=np.float64)
+
+    def compute_motion_plan(self, db, pose6, start, seed, execute=False, service=None, params=None, boxes=None, cap=16384):
+        p = params or default_params()
+        b, nb = self._boxes(boxes)
+        db = np.ascontiguousarray(db, dtype=np.float64).reshape(-1, NJ)
+        pose6 = np.ascontiguousarray(pose6, dtype=np.float64)
+        start = np.ascontiguousarray(start, dtype=np.float64)
+        sv = self._service(service)
+        goal, traj, tfs, stats = np.zeros(NJ), np.empty((cap, NJ)), np.empty(cap), np.zeros(4, np.int32)
+        self.lib.nwbo_compute_motion_plan(C.byref(p), _ptr(b), nb, _ptr(sv), _ptr(db), len(db), _ptr(pose6), _ptr(start),
+                                          int(execute), C.c_uint64(seed), _ptr(goal), _ptr(traj), _ptr(tfs), cap, _ptr(stats))
+        n = min(int(stats[3]), cap)
+        return dict(success=bool(stats[0]), num_nodes=int(stats[1]), goals_found=int(stats[2]), goal_config=goal,
+                    trajectory=traj[:n].copy(), time_from_start=tfs[:n].copy())
+
+    def compute_manipulation_plan(self, db, pose6, start, seed, circular, obj, execute=False, service=None, params=None,
+                                  boxes=None, cap=16384):
+        p = params or default_params()
+        b, nb = self._boxes(boxes)
+        db = np.ascontiguousarray(db, dtype=np.float64).reshape(-1, NJ)
+        pose6 = np.ascontiguousarray(pose6, dtype=np.float64)
+        start = np.ascontiguousarray(start, dtype=np.float64)
+        obj = np.ascontiguousarray(obj, dtype=np.float64)
+        sv = self._service(service)
+        ga, gm = np.zeros(NJ), np.zeros(NJ)
+        ta, tm, fa, fm = np.empty((cap, NJ)), np.empty((cap, NJ)), np.empty(cap), np.empty(cap)
+        stats = np.zeros(8, np.int32)
+        self.lib.nwbo_compute_manipulation_plan(C.byref(p), _ptr(b), nb, _ptr(sv), _ptr(db), len(db), _ptr(pose6), _ptr(start),
+                                                int(circular), _ptr(obj), int(execute), C.c_uint64(seed), _ptr(ga), _ptr(gm),
+                                                _ptr(ta), _ptr(fa), _ptr(tm), _ptr(fm), cap, _ptr(stats))
+        na, nm = min(int(stats[6]), cap), min(int(stats[7]), cap)
+        return dict(success_approach=bool(stats[0]), success_manipulation=bool(stats[1]), nodes_approach=int(stats[2]),
+                    nodes_manipulate=int(stats[3]), goals_approach=int(stats[4]), goals_manipulate=int(stats[5]),
+                    goal_approach=ga, goal_manipulate=gm, traj_approach=ta[:na].copy(), tfs_approach=fa[:na].copy(),
+                    traj_manipulation=tm[:nm].copy(), tfs_manipulation=fm[:nm].copy())
 
     def philox(self, ctr, key):
         ctr = np.asarray(ctr, dtype=np.uint32)
