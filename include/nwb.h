@@ -8,6 +8,8 @@
  *   SCG = rrt_connect_planner/src/stable_config_generator.cpp
  *   NCK = rrt_connect_planner/src/nao_constraint_kinematics.cpp
  *   NPC = rrt_connect_planner/src/nao_planner_control.cpp
+ *   AOC = rrt_connect_planner/src/articulated_object_constraints.cpp
+ *   IKF = rrt_connect_planner/src/ikfast_TranslationDirection5D.cpp
  *
  * Conventions
  *   - A configuration is NWB_NJ = 21 doubles in the planner's joint order (RP:2003-2023), row-major.
@@ -92,6 +94,12 @@ typedef struct nwb_params {
   double pinv_eps;             /* KDL ChainIkSolverVel_pinv default (1e-5)                      */
   int32_t shortcut_waypoints;  /* RP:1396 (100)                                                 */
   int32_t shortcut_max_rounds; /* RP:1856 (500)                                                 */
+  /* limb weights of the approach / manipulation plans (planning_parameters.yaml:13-21, NPC:27-32) */
+  double r_arm_weight_approach, l_arm_weight_approach, legs_weight_approach;       /* 1.0, 1.0, 1.0 */
+  double r_arm_weight_manipulate, l_arm_weight_manipulate, legs_weight_manipulate; /* 1.0, 0.0, 1.0 */
+  int32_t manipulate_waypoints;   /* RP:1398 (4)   way-points per segment of an articulated path  */
+  int32_t object_interp_points;   /* NPC:539,822 (20) intermediate points of the hand trajectory  */
+  double manipulation_velocity;   /* RP:92 (0.02 m/s)                                             */
 } nwb_params;
 
 /* Fill `p` with the reference defaults. */
@@ -302,6 +310,155 @@ typedef struct nwb_generate_ds_configs_response {
  * through the return code instead of exiting (SCG:205,218). */
 NWB_API int nwb_generate_ds_database(nwb_ctx* ctx, const nwb_generate_ds_configs_request* req,
                                      nwb_generate_ds_configs_response* resp, const char* path, uint64_t seed);
+
+/* ---- right arm, articulated objects, goal configurations ----------------------------
+ * Hand poses are 6 doubles: position of the grasp point and direction of the hand z-axis, in the
+ * right-sole frame unless stated otherwise (Compute_Goal_Config.srv:1-4). */
+
+/* The generated right-arm solver IKSolver::ik (IKF:341-1517, entry IKF:1521) for n targets given in ITS
+ * torso frame: targets [n][6] = position + unit direction; solutions [n][8][5] (RShoulderPitch,
+ * RShoulderRoll, RElbowYaw, RElbowRoll, RWristYaw, each in (-pi, pi]), counts [n].  Solved in closed
+ * form on the device (csrc/arm_core.cuh); the solution SET equals the reference solver's. */
+NWB_API int nwb_arm_ik_batch(nwb_ctx* ctx, const double* targets, int64_t n, double* solutions, int32_t* counts);
+/* ConstraintKinematics::computeRightArmIK, generated-solver branch (NCK:224-506 with getHipPose
+ * NCK:512-544) for n whole-body rows q [n][21]: hip pose from the right leg, hand pose -> torso frame,
+ * all solutions, strict joint limits, the one with the largest compute_ergonomics_index (NCK:612-659).
+ * ok [n], arm [n][5], ergonomics [n].  A zero direction (the KDL position-only branch NCK:291-372, which
+ * no shipped caller reaches) is rejected with NWB_E_INVALID. */
+NWB_API int nwb_goal_arm_ik_batch(nwb_ctx* ctx, const double* q, int64_t n, const double* hand_pose6, uint8_t* ok, double* arm,
+                                  double* ergonomics);
+/* ArticulatedObjectConstraints::computeDrawerTrajectoryPoints (kind 0, AOC:105-122) /
+ * computeDoorTrajectoryPoints (kind 1, AOC:126-189; door4 = {rotation_radius, rotation_angle [deg],
+ * relative_angle [deg], clearance_handle} as NPC:816-820): out [num_interp_points + 2][6]. */
+NWB_API int nwb_hand_trajectory(int32_t kind, const double* start6, const double* goal6, int32_t num_interp_points,
+                                const double* door4, double* out);
+/* RRT_Planner::enforce_MA_Constraints (RP:597-696) for n independent (q_near, q_new_ds) pairs against
+ * the trajectory points pts [n_points][6]: start_tree selects the index rule of "start_tree" /
+ * "goal_tree"; near_hand_index [n] = q_near.cart_hand_pose_index.  status[i]: NWB_REACHED (hand already
+ * on the desired point, AOC:204-262), NWB_ADVANCED (right arm re-solved, AOC:313-449) or NWB_TRAPPED;
+ * q_out[i] written unless TRAPPED. */
+NWB_API int nwb_enforce_ma_batch(nwb_ctx* ctx, const double* pts, int32_t n_points, int32_t start_tree,
+                                 const int32_t* near_hand_index, const double* q_near, const double* q_new_ds, int64_t n,
+                                 double* q_out, int32_t* status);
+/* Goal branch of StableConfigGenerator::sample_stable_configs (SCG:278-436), one outcome per sample
+ * index in [first, first + count): stage [count] (0 rejected, 1 both IKs solved but infeasible,
+ * 2 accepted), ergonomics [count] and rows [count][21] (either may be NULL). */
+NWB_API int nwb_goal_sample_batch(nwb_ctx* ctx, uint64_t seed, uint64_t first, int64_t count, const double* hand_pose6,
+                                  int32_t max_ik_iter, uint8_t* stage, double* ergonomics, double* rows);
+/* sample_stable_configs(max_samples, max_ik_iter, t, true, file) + sort_goal_configs_by_ergonomy
+ * (SCG:176-507, 510-661): the first six accepted samples in sample order, passed through the goal
+ * file's text format (6 significant digits) and sorted by descending ergonomics index; row 0 is what
+ * loadGoalConfig (SCG:666-756) returns.  rows6 [6][21], ergonomics6 [6], index6 [6] (may be NULL),
+ * *n_found <= 6, *samples_drawn (may be NULL) = loop iterations the serial reference would have used. */
+NWB_API int nwb_sample_goal_configs(nwb_ctx* ctx, uint64_t seed, const double* hand_pose6, int32_t max_samples,
+                                    int32_t max_ik_iter, double* rows6, double* ergonomics6, uint64_t* index6,
+                                    int32_t* n_found, int64_t* samples_drawn);
+/* nwb_solve_query_batch with RRT_Planner::activate_drawer_constraint / activate_door_constraint in force
+ * (RP:195-223): hand_trajectories [nq][n_points][6], one per query; nodes carry cart_hand_pose_index
+ * (RPh:35), extendTree / connectTree apply enforce_MA_Constraints (RP:829-837, 917-973). */
+NWB_API int nwb_solve_query_constrained_batch(nwb_ctx* ctx, const double* starts, const double* goals, int64_t nq,
+                                              const double* db, int32_t n_db, const double* weights, const uint64_t* seeds,
+                                              int32_t max_iter, double step, int32_t tree_capacity,
+                                              const double* hand_trajectories, int32_t n_points, nwb_plan_result* results,
+                                              double* raw_paths, int32_t raw_path_capacity);
+
+/* ---- planning services (NPC:150-870, the .srv files of rrt_planner_msgs) ------------------------------------------
+ * Request / response structs mirror the .srv fields one to one; moveit_msgs/DisplayTrajectory is
+ * flattened into caller-provided arrays.  Like the callbacks, the functions report planning failure
+ * through the response flags and return NWB_OK; a negative return is an argument / device error.
+ * The stable-configuration database is the context's (nwb_ctx_set_ds_database, or the file loaded /
+ * generated through nwb_ctx_load_ds_database / nwb_generate_ds_database, NPC:98,144).  `seed` replaces
+ * the clock-seeded generators: goal sampling uses seed (approach) and seed + 1 (manipulation), the two
+ * solveQuery calls seed + 2 and seed + 3. */
+typedef struct nwb_point3 {  /* geometry_msgs/Point, geometry_msgs/Vector3 */
+  double x, y, z;
+} nwb_point3;
+typedef struct nwb_trajectory {   /* moveit_msgs/DisplayTrajectory -> joint_trajectory.points */
+  int32_t capacity;               /* in:  rows the two arrays can hold                                   */
+  int32_t n_points;               /* out: way-points of the plan (rows beyond capacity are not written)  */
+  double* positions;              /* [capacity][21]                                                      */
+  double* time_from_start;        /* [capacity] seconds: 2.0 + i * increment (RP:1532-1553)              */
+} nwb_trajectory;
+
+NWB_API int nwb_ctx_set_ds_database(nwb_ctx* ctx, const double* rows, int64_t n_rows);
+NWB_API int nwb_ctx_load_ds_database(nwb_ctx* ctx, const char* path);   /* RRT_Planner::load_DS_database, RP:121-191 */
+NWB_API int64_t nwb_ctx_ds_database_size(const nwb_ctx* ctx);
+
+typedef struct nwb_compute_goal_config_request {   /* Compute_Goal_Config.srv:1-4 */
+  nwb_point3 right_hand_position;
+  nwb_point3 right_hand_direction;
+} nwb_compute_goal_config_request;
+typedef struct nwb_compute_goal_config_response {  /* Compute_Goal_Config.srv:6-8 */
+  double wb_goal_config[NWB_NJ];
+  int32_t num_goal_configs_found;                  /* not in the .srv: the callback drops it (NPC:170) */
+} nwb_compute_goal_config_response;
+/* NAO_PLANNER_CONTROL::compute_goal_config (NPC:150-181) */
+NWB_API int nwb_compute_goal_config(nwb_ctx* ctx, const nwb_compute_goal_config_request* req,
+                                    nwb_compute_goal_config_response* resp, uint64_t seed);
+
+typedef struct nwb_compute_motion_plan_request {   /* Compute_Motion_Plan.srv:1-12 */
+  nwb_point3 right_hand_position;
+  nwb_point3 right_hand_direction;
+  const double* wb_start_config;                   /* float64[]: must hold 21 values (NPC:242 does not check) */
+  int32_t wb_start_config_len;
+  uint8_t execute_trajectory;
+} nwb_compute_motion_plan_request;
+typedef struct nwb_compute_motion_plan_response {  /* Compute_Motion_Plan.srv:14-29 */
+  double wb_goal_config[NWB_NJ];
+  double time_goal_config;
+  nwb_trajectory motion_plan;
+  uint32_t num_nodes_generated;
+  double search_time;
+  uint8_t success;
+} nwb_compute_motion_plan_response;
+/* NAO_PLANNER_CONTROL::compute_motion_plan (NPC:183-336) */
+NWB_API int nwb_compute_motion_plan(nwb_ctx* ctx, const nwb_compute_motion_plan_request* req,
+                                    nwb_compute_motion_plan_response* resp, uint64_t seed);
+
+typedef struct nwb_manipulation_plan_response {    /* Compute_Linear_Manipulation_Plan.srv:20-46 == Circular:27-53 */
+  nwb_trajectory motion_plan_approach;
+  nwb_trajectory motion_plan_manipulation;
+  double wb_goal_config_approach[NWB_NJ];
+  double time_goal_config_approach;
+  double wb_goal_config_manipulate[NWB_NJ];
+  double time_goal_config_manipulate;
+  uint32_t num_nodes_generated_approach;
+  uint32_t num_nodes_generated_manipulate;
+  double search_time_approach;
+  double search_time_manipulate;
+  uint8_t success_approach;
+  uint8_t success_manipulation;
+} nwb_manipulation_plan_response;
+
+typedef struct nwb_compute_linear_manipulation_plan_request {   /* Compute_Linear_Manipulation_Plan.srv:1-18 */
+  nwb_point3 right_hand_position;
+  nwb_point3 right_hand_direction;
+  const double* wb_start_config;
+  int32_t wb_start_config_len;
+  double relative_angle;               /* degrees */
+  double object_translation_length;    /* metres  */
+  uint8_t execute_trajectory;
+} nwb_compute_linear_manipulation_plan_request;
+/* NAO_PLANNER_CONTROL::compute_linear_manipulation_plan (NPC:338-588): approach plan, then the drawer
+ * pull under activate_drawer_constraint (RP:195-206). */
+NWB_API int nwb_compute_linear_manipulation_plan(nwb_ctx* ctx, const nwb_compute_linear_manipulation_plan_request* req,
+                                                 nwb_manipulation_plan_response* resp, uint64_t seed);
+
+typedef struct nwb_compute_circular_manipulation_plan_request { /* Compute_Circular_Manipulation_Plan.srv:1-25 */
+  nwb_point3 right_hand_position;
+  nwb_point3 right_hand_direction;
+  const double* wb_start_config;
+  int32_t wb_start_config_len;
+  double relative_angle;               /* degrees */
+  double rotation_radius;
+  double rotation_angle;               /* degrees */
+  double clearance_handle;
+  uint8_t execute_trajectory;
+} nwb_compute_circular_manipulation_plan_request;
+/* NAO_PLANNER_CONTROL::compute_circular_manipulation_plan (NPC:590-870): approach plan, then the door
+ * swing under activate_door_constraint (RP:209-223). */
+NWB_API int nwb_compute_circular_manipulation_plan(nwb_ctx* ctx, const nwb_compute_circular_manipulation_plan_request* req,
+                                                   nwb_manipulation_plan_response* resp, uint64_t seed);
 
 /* Pinned host memory helpers: buffers from here make the host<->device copies of the batch
  * operators run at full PCIe speed. */

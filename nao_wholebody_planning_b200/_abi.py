@@ -37,6 +37,15 @@ class NwbParams(C.Structure):
         ("pinv_eps", C.c_double),
         ("shortcut_waypoints", C.c_int32),
         ("shortcut_max_rounds", C.c_int32),
+        ("r_arm_weight_approach", C.c_double),
+        ("l_arm_weight_approach", C.c_double),
+        ("legs_weight_approach", C.c_double),
+        ("r_arm_weight_manipulate", C.c_double),
+        ("l_arm_weight_manipulate", C.c_double),
+        ("legs_weight_manipulate", C.c_double),
+        ("manipulate_waypoints", C.c_int32),
+        ("object_interp_points", C.c_int32),
+        ("manipulation_velocity", C.c_double),
     ]
 
 
@@ -54,12 +63,64 @@ class GenDsResponse(C.Structure):
     _fields_ = [("num_configs_generated", C.c_int32)]
 
 
+class Point3(C.Structure):
+    """struct nwb_point3: geometry_msgs/Point, geometry_msgs/Vector3."""
+    _fields_ = [("x", C.c_double), ("y", C.c_double), ("z", C.c_double)]
+
+
+class Trajectory(C.Structure):
+    """struct nwb_trajectory: moveit_msgs/DisplayTrajectory flattened into caller-provided arrays."""
+    _fields_ = [("capacity", C.c_int32), ("n_points", C.c_int32), ("positions", C.POINTER(C.c_double)),
+                ("time_from_start", C.POINTER(C.c_double))]
+
+
+class GoalConfigRequest(C.Structure):      # Compute_Goal_Config.srv:1-4
+    _fields_ = [("right_hand_position", Point3), ("right_hand_direction", Point3)]
+
+
+class GoalConfigResponse(C.Structure):     # Compute_Goal_Config.srv:6-8
+    _fields_ = [("wb_goal_config", C.c_double * NJ), ("num_goal_configs_found", C.c_int32)]
+
+
+class MotionPlanRequest(C.Structure):      # Compute_Motion_Plan.srv:1-12
+    _fields_ = [("right_hand_position", Point3), ("right_hand_direction", Point3), ("wb_start_config", C.POINTER(C.c_double)),
+                ("wb_start_config_len", C.c_int32), ("execute_trajectory", C.c_uint8)]
+
+
+class MotionPlanResponse(C.Structure):     # Compute_Motion_Plan.srv:14-29
+    _fields_ = [("wb_goal_config", C.c_double * NJ), ("time_goal_config", C.c_double), ("motion_plan", Trajectory),
+                ("num_nodes_generated", C.c_uint32), ("search_time", C.c_double), ("success", C.c_uint8)]
+
+
+class ManipulationPlanResponse(C.Structure):   # Compute_Linear_Manipulation_Plan.srv:20-46 == Circular:27-53
+    _fields_ = [("motion_plan_approach", Trajectory), ("motion_plan_manipulation", Trajectory),
+                ("wb_goal_config_approach", C.c_double * NJ), ("time_goal_config_approach", C.c_double),
+                ("wb_goal_config_manipulate", C.c_double * NJ), ("time_goal_config_manipulate", C.c_double),
+                ("num_nodes_generated_approach", C.c_uint32), ("num_nodes_generated_manipulate", C.c_uint32),
+                ("search_time_approach", C.c_double), ("search_time_manipulate", C.c_double),
+                ("success_approach", C.c_uint8), ("success_manipulation", C.c_uint8)]
+
+
+class LinearManipulationRequest(C.Structure):  # Compute_Linear_Manipulation_Plan.srv:1-18
+    _fields_ = [("right_hand_position", Point3), ("right_hand_direction", Point3), ("wb_start_config", C.POINTER(C.c_double)),
+                ("wb_start_config_len", C.c_int32), ("relative_angle", C.c_double), ("object_translation_length", C.c_double),
+                ("execute_trajectory", C.c_uint8)]
+
+
+class CircularManipulationRequest(C.Structure):  # Compute_Circular_Manipulation_Plan.srv:1-25
+    _fields_ = [("right_hand_position", Point3), ("right_hand_direction", Point3), ("wb_start_config", C.POINTER(C.c_double)),
+                ("wb_start_config_len", C.c_int32), ("relative_angle", C.c_double), ("rotation_radius", C.c_double),
+                ("rotation_angle", C.c_double), ("clearance_handle", C.c_double), ("execute_trajectory", C.c_uint8)]
+
+
 def default_params(**over):
     """Reference defaults (planning_config/planning_parameters.yaml, hard-coded constants)."""
     p = NwbParams(device=0, quirks=QUIRK_SIGNED_FOOT_ERROR | QUIRK_DB_INDEX_FLOOR, srdf_trim=1, scale_origin=1,
                   scale_sp=0.8, ds_tolerance=0.01, ik_eps=1e-3, ik_maxiter=100, scg_max_samples=5000,
                   scg_max_ik_iterations=5, planner_max_iterations=8000, planner_step_factor=0.1, pinv_eps=1e-5,
-                  shortcut_waypoints=100, shortcut_max_rounds=500)
+                  shortcut_waypoints=100, shortcut_max_rounds=500, r_arm_weight_approach=1.0, l_arm_weight_approach=1.0,
+                  legs_weight_approach=1.0, r_arm_weight_manipulate=1.0, l_arm_weight_manipulate=0.0,
+                  legs_weight_manipulate=1.0, manipulate_waypoints=4, object_interp_points=20, manipulation_velocity=0.02)
     for k, v in over.items():
         if not hasattr(p, k):
             raise AttributeError(k)
@@ -141,6 +202,22 @@ def _declare(lib):
         "nwb_write_configs": (C.c_int, [C.c_char_p, vp, i64]),
         "nwb_load_ds_database": (C.c_int, [C.c_char_p, vp, i64, C.POINTER(i64)]),
         "nwb_generate_ds_database": (C.c_int, [vp, C.POINTER(GenDsRequest), C.POINTER(GenDsResponse), C.c_char_p, C.c_uint64]),
+        "nwb_arm_ik_batch": (C.c_int, [vp, vp, i64, vp, vp]),
+        "nwb_goal_arm_ik_batch": (C.c_int, [vp, vp, i64, vp, vp, vp, vp]),
+        "nwb_hand_trajectory": (C.c_int, [i32, vp, vp, i32, vp, vp]),
+        "nwb_enforce_ma_batch": (C.c_int, [vp, vp, i32, i32, vp, vp, vp, i64, vp, vp]),
+        "nwb_goal_sample_batch": (C.c_int, [vp, C.c_uint64, C.c_uint64, i64, vp, i32, vp, vp, vp]),
+        "nwb_sample_goal_configs": (C.c_int, [vp, C.c_uint64, vp, i32, i32, vp, vp, vp, C.POINTER(i32), C.POINTER(i64)]),
+        "nwb_solve_query_constrained_batch": (C.c_int, [vp, vp, vp, i64, vp, i32, vp, vp, i32, dbl, i32, vp, i32, vp, vp, i32]),
+        "nwb_ctx_set_ds_database": (C.c_int, [vp, vp, i64]),
+        "nwb_ctx_load_ds_database": (C.c_int, [vp, C.c_char_p]),
+        "nwb_ctx_ds_database_size": (i64, [vp]),
+        "nwb_compute_goal_config": (C.c_int, [vp, C.POINTER(GoalConfigRequest), C.POINTER(GoalConfigResponse), C.c_uint64]),
+        "nwb_compute_motion_plan": (C.c_int, [vp, C.POINTER(MotionPlanRequest), C.POINTER(MotionPlanResponse), C.c_uint64]),
+        "nwb_compute_linear_manipulation_plan": (C.c_int, [vp, C.POINTER(LinearManipulationRequest),
+                                                           C.POINTER(ManipulationPlanResponse), C.c_uint64]),
+        "nwb_compute_circular_manipulation_plan": (C.c_int, [vp, C.POINTER(CircularManipulationRequest),
+                                                             C.POINTER(ManipulationPlanResponse), C.c_uint64]),
         "nwb_host_alloc": (vp, [C.c_size_t]),
         "nwb_host_free": (None, [vp]),
         "nwb_ffma_peak": (C.c_int, [vp, C.c_int, pd, pd]),

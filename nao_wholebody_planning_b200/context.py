@@ -186,8 +186,9 @@ class Context:
 
     # ---- RRT-Connect driver ---------------------------------------------------------------------
     def solveQuery(self, starts, goals, db, seeds, weights=None, max_iter=8000, step=0.1, tree_capacity=4096,
-                   raw_path_capacity=1024):
+                   raw_path_capacity=1024, hand_trajectories=None):
         """setStartGoalConfigs + solveQuery + raw path extraction for a batch of queries.
+        hand_trajectories [nq][n_points][6]: activate_drawer_constraint / activate_door_constraint per query.
         Returns (list of result dicts, list of raw paths [len,21])."""
         starts = np.ascontiguousarray(starts, dtype=np.float64).reshape(-1, NJ)
         goals = np.ascontiguousarray(goals, dtype=np.float64).reshape(-1, NJ)
@@ -197,9 +198,17 @@ class Context:
         w = self._weights(weights)
         res = (_abi.NwbPlanResult * nq)()
         raw = np.full((nq, raw_path_capacity, NJ), np.nan)
-        self._check(self.lib.nwb_solve_query_batch(self.h, _p(starts), _p(goals), nq, _p(db), len(db), _p(w), _p(seeds),
-                                                   int(max_iter), float(step), int(tree_capacity), C.byref(res), _p(raw),
-                                                   int(raw_path_capacity)), "nwb_solve_query_batch")
+        if hand_trajectories is None:
+            self._check(self.lib.nwb_solve_query_batch(self.h, _p(starts), _p(goals), nq, _p(db), len(db), _p(w), _p(seeds),
+                                                       int(max_iter), float(step), int(tree_capacity), C.byref(res), _p(raw),
+                                                       int(raw_path_capacity)), "nwb_solve_query_batch")
+        else:
+            ht = np.ascontiguousarray(hand_trajectories, dtype=np.float64)
+            ht = ht.reshape(nq, -1, 6)
+            self._check(self.lib.nwb_solve_query_constrained_batch(
+                self.h, _p(starts), _p(goals), nq, _p(db), len(db), _p(w), _p(seeds), int(max_iter), float(step),
+                int(tree_capacity), _p(ht), ht.shape[1], C.byref(res), _p(raw), int(raw_path_capacity)),
+                "nwb_solve_query_constrained_batch")
         out = [{n: getattr(r, n) for n, _ in _abi.NwbPlanResult._fields_} for r in res]
         paths = [raw[k, :min(out[k]["raw_path_len"], raw_path_capacity)].copy() for k in range(nq)]
         return out, paths
@@ -222,6 +231,137 @@ class Context:
         n = self.lib.nwb_interpolate_path(_p(path), len(path), int(k), _p(out), cap)
         assert n == cap
         return out
+
+    # ---- right arm / articulated objects / goal configurations ----------------------------------------
+    def arm_ik(self, targets):
+        """IKSolver::ik (ikfast_TranslationDirection5D.cpp:341) for [n][6] torso-frame targets ->
+        (solutions [n][8][5] NaN padded, counts [n])."""
+        t = np.ascontiguousarray(targets, dtype=np.float64).reshape(-1, 6)
+        sols = np.empty((len(t), 8, 5))
+        cnt = np.empty(len(t), np.int32)
+        self._check(self.lib.nwb_arm_ik_batch(self.h, _p(t), len(t), _p(sols), _p(cnt)), "nwb_arm_ik_batch")
+        return sols, cnt
+
+    def computeRightArmIK(self, q, hand_pose6):
+        """ConstraintKinematics::computeRightArmIK (nao_constraint_kinematics.cpp:224) for whole-body rows."""
+        q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, NJ)
+        pose = np.ascontiguousarray(hand_pose6, dtype=np.float64)
+        n = len(q)
+        ok, arm, erg = np.empty(n, np.uint8), np.empty((n, 5)), np.empty(n)
+        self._check(self.lib.nwb_goal_arm_ik_batch(self.h, _p(q), n, _p(pose), _p(ok), _p(arm), _p(erg)), "nwb_goal_arm_ik_batch")
+        return ok, arm, erg
+
+    def hand_trajectory(self, kind, start6, goal6, num_interp_points=20, door4=None):
+        a = np.ascontiguousarray(start6, dtype=np.float64)
+        b = np.ascontiguousarray(goal6, dtype=np.float64)
+        d = None if door4 is None else np.ascontiguousarray(door4, dtype=np.float64)
+        out = np.empty((num_interp_points + 2, 6))
+        rc = self.lib.nwb_hand_trajectory(int(kind), _p(a), _p(b), int(num_interp_points), _p(d), _p(out))
+        if rc != 0:
+            raise NwbError(f"nwb_hand_trajectory failed ({rc})")
+        return out
+
+    def enforce_MA_Constraints(self, pts, start_tree, near_hand_index, q_near, q_new_ds):
+        """RRT_Planner::enforce_MA_Constraints (rrt_planner.cpp:597) -> (q_out, status); TRAPPED rows are NaN."""
+        pts = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 6)
+        q_near = np.ascontiguousarray(q_near, dtype=np.float64).reshape(-1, NJ)
+        q_ds = np.ascontiguousarray(q_new_ds, dtype=np.float64).reshape(-1, NJ)
+        hi = np.ascontiguousarray(near_hand_index, dtype=np.int32)
+        out = np.full_like(q_ds, np.nan)
+        st = np.empty(len(q_ds), np.int32)
+        self._check(self.lib.nwb_enforce_ma_batch(self.h, _p(pts), len(pts), int(bool(start_tree)), _p(hi), _p(q_near), _p(q_ds),
+                                                  len(q_ds), _p(out), _p(st)), "nwb_enforce_ma_batch")
+        return out, st
+
+    def goal_sample_batch(self, seed, first, count, hand_pose6, max_ik_iter=5):
+        pose = np.ascontiguousarray(hand_pose6, dtype=np.float64)
+        stage, erg, rows = np.empty(count, np.uint8), np.empty(count), np.empty((count, NJ))
+        self._check(self.lib.nwb_goal_sample_batch(self.h, int(seed), int(first), int(count), _p(pose), int(max_ik_iter), _p(stage),
+                                                   _p(erg), _p(rows)), "nwb_goal_sample_batch")
+        return stage, erg, rows
+
+    def sample_goal_configs(self, seed, hand_pose6, max_samples=5000, max_ik_iter=5):
+        """sample_stable_configs(goal branch) + sort_goal_configs_by_ergonomy -> (rows, ergonomics, index, drawn)."""
+        pose = np.ascontiguousarray(hand_pose6, dtype=np.float64)
+        rows, erg, idx = np.zeros((6, NJ)), np.zeros(6), np.zeros(6, np.uint64)
+        found, drawn = C.c_int32(0), C.c_int64(0)
+        self._check(self.lib.nwb_sample_goal_configs(self.h, int(seed), _p(pose), int(max_samples), int(max_ik_iter), _p(rows),
+                                                     _p(erg), _p(idx), C.byref(found), C.byref(drawn)), "nwb_sample_goal_configs")
+        n = found.value
+        return rows[:n].copy(), erg[:n].copy(), idx[:n].copy(), drawn.value
+
+    # ---- planning services (nao_planner_control.cpp:150-870) ---------------------------------------------
+    def set_ds_database(self, rows):
+        rows = np.ascontiguousarray(rows, dtype=np.float64).reshape(-1, NJ)
+        self._check(self.lib.nwb_ctx_set_ds_database(self.h, _p(rows), len(rows)), "nwb_ctx_set_ds_database")
+
+    def load_ds_database(self, path):
+        self._check(self.lib.nwb_ctx_load_ds_database(self.h, str(path).encode()), "nwb_ctx_load_ds_database")
+        return self.lib.nwb_ctx_ds_database_size(self.h)
+
+    @staticmethod
+    def _traj(cap):
+        pos, tfs = np.full((cap, NJ), np.nan), np.full(cap, np.nan)
+        t = _abi.Trajectory(cap, 0, pos.ctypes.data_as(C.POINTER(C.c_double)), tfs.ctypes.data_as(C.POINTER(C.c_double)))
+        return t, pos, tfs
+
+    def compute_goal_config(self, position, direction, seed):
+        req = _abi.GoalConfigRequest(_abi.Point3(*position), _abi.Point3(*direction))
+        resp = _abi.GoalConfigResponse()
+        self._check(self.lib.nwb_compute_goal_config(self.h, C.byref(req), C.byref(resp), int(seed)), "nwb_compute_goal_config")
+        return np.array(resp.wb_goal_config), resp.num_goal_configs_found
+
+    def compute_motion_plan(self, position, direction, wb_start_config, seed, execute_trajectory=False, cap=16384):
+        start = np.ascontiguousarray(wb_start_config, dtype=np.float64)
+        req = _abi.MotionPlanRequest(_abi.Point3(*position), _abi.Point3(*direction), start.ctypes.data_as(C.POINTER(C.c_double)),
+                                     len(start), int(execute_trajectory))
+        resp = _abi.MotionPlanResponse()
+        resp.motion_plan, pos, tfs = self._traj(cap)
+        self._check(self.lib.nwb_compute_motion_plan(self.h, C.byref(req), C.byref(resp), int(seed)), "nwb_compute_motion_plan")
+        n = min(resp.motion_plan.n_points, cap)
+        return dict(success=bool(resp.success), wb_goal_config=np.array(resp.wb_goal_config), time_goal_config=resp.time_goal_config,
+                    num_nodes_generated=resp.num_nodes_generated, search_time=resp.search_time, trajectory=pos[:n].copy(),
+                    time_from_start=tfs[:n].copy())
+
+    def _manipulation_result(self, resp, pa, ta, pm, tm, cap):
+        na, nm = min(resp.motion_plan_approach.n_points, cap), min(resp.motion_plan_manipulation.n_points, cap)
+        return dict(success_approach=bool(resp.success_approach), success_manipulation=bool(resp.success_manipulation),
+                    wb_goal_config_approach=np.array(resp.wb_goal_config_approach),
+                    wb_goal_config_manipulate=np.array(resp.wb_goal_config_manipulate),
+                    time_goal_config_approach=resp.time_goal_config_approach,
+                    time_goal_config_manipulate=resp.time_goal_config_manipulate,
+                    num_nodes_generated_approach=resp.num_nodes_generated_approach,
+                    num_nodes_generated_manipulate=resp.num_nodes_generated_manipulate,
+                    search_time_approach=resp.search_time_approach, search_time_manipulate=resp.search_time_manipulate,
+                    traj_approach=pa[:na].copy(), tfs_approach=ta[:na].copy(), traj_manipulation=pm[:nm].copy(),
+                    tfs_manipulation=tm[:nm].copy())
+
+    def compute_linear_manipulation_plan(self, position, direction, wb_start_config, relative_angle, object_translation_length,
+                                         seed, execute_trajectory=False, cap=16384):
+        start = np.ascontiguousarray(wb_start_config, dtype=np.float64)
+        req = _abi.LinearManipulationRequest(_abi.Point3(*position), _abi.Point3(*direction),
+                                             start.ctypes.data_as(C.POINTER(C.c_double)), len(start), float(relative_angle),
+                                             float(object_translation_length), int(execute_trajectory))
+        resp = _abi.ManipulationPlanResponse()
+        resp.motion_plan_approach, pa, ta = self._traj(cap)
+        resp.motion_plan_manipulation, pm, tm = self._traj(cap)
+        self._check(self.lib.nwb_compute_linear_manipulation_plan(self.h, C.byref(req), C.byref(resp), int(seed)),
+                    "nwb_compute_linear_manipulation_plan")
+        return self._manipulation_result(resp, pa, ta, pm, tm, cap)
+
+    def compute_circular_manipulation_plan(self, position, direction, wb_start_config, relative_angle, rotation_radius,
+                                           rotation_angle, clearance_handle, seed, execute_trajectory=False, cap=16384):
+        start = np.ascontiguousarray(wb_start_config, dtype=np.float64)
+        req = _abi.CircularManipulationRequest(_abi.Point3(*position), _abi.Point3(*direction),
+                                               start.ctypes.data_as(C.POINTER(C.c_double)), len(start), float(relative_angle),
+                                               float(rotation_radius), float(rotation_angle), float(clearance_handle),
+                                               int(execute_trajectory))
+        resp = _abi.ManipulationPlanResponse()
+        resp.motion_plan_approach, pa, ta = self._traj(cap)
+        resp.motion_plan_manipulation, pm, tm = self._traj(cap)
+        self._check(self.lib.nwb_compute_circular_manipulation_plan(self.h, C.byref(req), C.byref(resp), int(seed)),
+                    "nwb_compute_circular_manipulation_plan")
+        return self._manipulation_result(resp, pa, ta, pm, tm, cap)
 
     # ---- multi-GPU fused gather ------------------------------------------------------------------
     def dev_alloc(self, nbytes):

@@ -1,0 +1,209 @@
+// arm_kernels.cu - batched right-arm operators for sm_100a:
+//   arm_ik           hand position + direction -> all (<= 8) joint solutions     (IKF:341-1517 in closed form)
+//   goal_arm_ik      computeRightArmIK, generated-solver branch                   (NCK:224-506)
+//   enforce_ma       enforce_MA_Constraints for independent (q_near, q_new) pairs (RP:597-696)
+//   goal_sample      sample_stable_configs, goal branch                           (SCG:278-436)
+//   ma_project       the same constraint inside the lock-step RRT driver          (RP:829-837)
+// IKF = rrt_connect_planner/src/ikfast_TranslationDirection5D.cpp, NCK = .../nao_constraint_kinematics.cpp,
+// RP = .../rrt_planner.cpp, SCG = .../stable_config_generator.cpp.
+// One unit (target, configuration, sample, query) per thread in fp64; the per-thread building blocks
+// are in arm_core.cuh / planner_core.cuh, the validity test in validity_core.cuh (fp32).
+#include <cuda_runtime.h>
+
+#include "arm_core.cuh"
+#include "nwb_internal.h"
+#include "validity_core.cuh"
+
+namespace nwb {
+
+struct Pose6 {
+  double v[6];
+};
+
+__global__ void __launch_bounds__(128)
+arm_ik_kernel(const double* __restrict__ targets /*[n][6]*/, int64_t n, double* __restrict__ sols /*[n][8][5]*/,
+              int32_t* __restrict__ counts) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double* t = targets + i * 6;
+  double* o = sols + i * 40;
+  int k = 0;
+  int c = arm5d_ik(d3(t[0], t[1], t[2]), d3(t[3], t[4], t[5]), [&](const double* q) {
+    for (int j = 0; j < 5; ++j) o[k * 5 + j] = q[j];
+    ++k;
+  });
+  counts[i] = c;
+}
+
+__global__ void __launch_bounds__(128)
+goal_arm_ik_kernel(const __grid_constant__ PlanConst pc, const __grid_constant__ Pose6 pose, const double* __restrict__ q, int64_t n,
+                   uint8_t* __restrict__ ok, double* __restrict__ arm, double* __restrict__ erg) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double rl[5];
+  for (int m = 0; m < 5; ++m) rl[m] = -q[i * NWB_NJ + m];
+  DFrame hip;
+  right_leg_fk(rl, hip);
+  double a[5] = {0, 0, 0, 0, 0}, e = 0.0;
+  ok[i] = goal_right_arm_ik(hip, pose.v, pc.jmin + 10, pc.jmax + 10, a, &e);
+  for (int m = 0; m < 5; ++m) arm[i * 5 + m] = a[m];
+  erg[i] = e;
+}
+
+__global__ void __launch_bounds__(128)
+enforce_ma_kernel(const __grid_constant__ PlanConst pc, MaView ma, int start_tree, const int32_t* __restrict__ near_hand,
+                  const double* __restrict__ q_near, const double* __restrict__ q_ds, int64_t n, double* __restrict__ q_out,
+                  int32_t* __restrict__ status) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double a[NWB_NJ], q[NWB_NJ];
+  for (int j = 0; j < NWB_NJ; ++j) {
+    a[j] = q_near[i * NWB_NJ + j];
+    q[j] = q_ds[i * NWB_NJ + j];
+  }
+  const int st = enforce_ma_constraints(ma, start_tree != 0, near_hand[i], a, q, pc);
+  status[i] = st;
+  if (st != NWB_TRAPPED)
+    for (int j = 0; j < NWB_NJ; ++j) q_out[i * NWB_NJ + j] = q[j];
+}
+
+// thread-private point table (as planner_kernels.cu)
+struct ArmLocalStore {
+  float v[nwbm::kPointFloats];
+  __device__ __forceinline__ void put(int slot, float x) { v[slot] = x; }
+  __device__ __forceinline__ float get(int slot) const { return v[slot]; }
+};
+
+// Goal branch of sample_stable_configs: sample i draws its 21 joints exactly as the database branch
+// does (same stream, same slots), then LHipYawPitch = 0 and the left arm is pinned (SCG:291-300).
+// Accepted rows are compacted with their sample index and ergonomics index; the caller keeps the six
+// lowest indices (the serial loop stops at `goal_samples > 5`, SCG:429).
+template <bool STATIC>
+__global__ void __launch_bounds__(64)
+goal_sample_kernel(const __grid_constant__ PlanConst pc, const __grid_constant__ ValidityTables tab, const __grid_constant__ Pose6 pose,
+                   uint64_t seed, uint64_t first, int64_t count, int max_ik_iter, double* __restrict__ rows, uint64_t* __restrict__ row_index,
+                   double* __restrict__ row_erg, int64_t cap, unsigned long long* __restrict__ n_out, uint8_t* __restrict__ stage_out,
+                   double* __restrict__ erg_all, double* __restrict__ rows_all) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  const uint64_t i = first + (uint64_t)t;
+  double q[NWB_NJ];
+#pragma unroll 1
+  for (int blk = 0; blk < (NWB_NJ + 3) / 4; ++blk) {
+    uint32_t r[4];
+    philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), (uint32_t)blk, kStreamSampler, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    for (int l = 0; l < 4; ++l) {
+      int j = 4 * blk + l;
+      if (j < NWB_NJ) q[j] = __dadd_rn(__dmul_rn(pc.jmax[j] - pc.jmin[j], u01(r[l])), pc.jmin[j]);
+    }
+  }
+  q[15] = 0.0;
+  q[5] = 1.5708; q[6] = 0.17; q[7] = 0.0; q[8] = -0.036; q[9] = 0.0;     // SCG:296-300
+  double rl[5], ll[5], arm[5], e = 0.0;
+  for (int m = 0; m < 5; ++m) rl[m] = -q[m];
+  DFrame hip, target;
+  right_leg_fk(rl, hip);
+  desired_left_leg_pose(hip, target);
+  uint8_t stage = 0;
+  for (int m = 0; m < 5; ++m) ll[m] = -rl[m];            // NCK:150 seed; further attempts repeat the same arithmetic (quirk C5)
+  bool solved = max_ik_iter > 0 && left_leg_ik_nr(target, ll, pc.ik_maxiter, pc.ik_eps, pc.pinv_eps, nullptr) &&
+                limits_ok(ll, pc.jmin + 16, pc.jmax + 16, 5);
+  if (solved) solved = goal_right_arm_ik(hip, pose.v, pc.jmin + 10, pc.jmax + 10, arm, &e);
+  if (solved) {
+    for (int m = 0; m < 5; ++m) {
+      q[16 + m] = ll[m];
+      q[10 + m] = arm[m];
+    }
+    float qf[NWB_NJ];
+#pragma unroll
+    for (int j = 0; j < NWB_NJ; ++j) qf[j] = (float)q[j];
+    ArmLocalStore st;
+    ValidityResult<float> r = evaluate_config<float, ArmLocalStore, false, false, STATIC ? PAIRS_STATIC_GROUP : PAIRS_TABLE>(tab, qf, st, nullptr, nullptr);
+    const bool feasible = !r.hit && r.stable;
+    stage = feasible ? 2 : 1;
+    if (feasible) {
+      unsigned long long slot = atomicAdd(n_out, 1ull);
+      if ((int64_t)slot < cap) {
+        for (int j = 0; j < NWB_NJ; ++j) rows[slot * NWB_NJ + j] = q[j];
+        row_index[slot] = i;
+        row_erg[slot] = e;
+      }
+    }
+  }
+  if (stage_out) stage_out[t] = stage;
+  if (erg_all) erg_all[t] = e;
+  if (rows_all)
+    for (int j = 0; j < NWB_NJ; ++j) rows_all[t * NWB_NJ + j] = q[j];
+}
+
+// enforce_MA_Constraints inside extendTree (RP:829-837) for the lock-step driver: one thread per query.
+__global__ void __launch_bounds__(32)
+ma_project_kernel(const __grid_constant__ PlanConst pc, const double* __restrict__ ma_pts, int n_pts, ForestView F, RrtState S,
+                  const int32_t* __restrict__ idx_a, const double* __restrict__ q_near, double* __restrict__ q_new,
+                  int32_t* __restrict__ status, int nq) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nq || !S.active[k] || status[k] == NWB_TRAPPED) return;
+  const int t = S.tree_a[k];
+  MaView ma{ma_pts + (size_t)k * n_pts * 6, n_pts};
+  double a[NWB_NJ], q[NWB_NJ];
+  for (int j = 0; j < NWB_NJ; ++j) {
+    a[j] = q_near[(size_t)k * NWB_NJ + j];
+    q[j] = q_new[(size_t)k * NWB_NJ + j];
+  }
+  const int near_hand = F.hand[(size_t)t * F.cap + idx_a[k]];
+  const int st = enforce_ma_constraints(ma, (t & 1) == 0, near_hand, a, q, pc);
+  if (st == NWB_TRAPPED) {
+    status[k] = NWB_TRAPPED;
+    return;
+  }
+  if (st == NWB_ADVANCED) {
+    status[k] = NWB_ADVANCED;
+    for (int j = 10; j < 15; ++j) q_new[(size_t)k * NWB_NJ + j] = q[j];
+  }
+}
+
+// ---- launchers ---------------------------------------------------------------------------------------
+cudaError_t launch_arm_ik(const double* targets, int64_t n, double* sols, int32_t* counts, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  arm_ik_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(targets, n, sols, counts);
+  return cudaGetLastError();
+}
+cudaError_t launch_goal_arm_ik(const PlanConst& pc, const double* pose6, const double* q, int64_t n, uint8_t* ok, double* arm,
+                               double* erg, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  Pose6 p;
+  for (int j = 0; j < 6; ++j) p.v[j] = pose6[j];
+  goal_arm_ik_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(pc, p, q, n, ok, arm, erg);
+  return cudaGetLastError();
+}
+cudaError_t launch_enforce_ma(const PlanConst& pc, const double* pts_dev, int n_pts, int start_tree, const int32_t* near_hand,
+                              const double* q_near, const double* q_ds, int64_t n, double* q_out, int32_t* status, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  enforce_ma_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(pc, MaView{pts_dev, n_pts}, start_tree, near_hand, q_near, q_ds, n,
+                                                               q_out, status);
+  return cudaGetLastError();
+}
+cudaError_t launch_goal_sample(const PlanConst& pc, const ValidityTables& tab, bool static_pairs, const double* pose6, uint64_t seed,
+                               uint64_t first, int64_t count, int max_ik_iter, double* rows, uint64_t* row_index, double* row_erg,
+                               int64_t cap, unsigned long long* n_out, uint8_t* stage_out, double* erg_all, double* rows_all,
+                               cudaStream_t s) {
+  if (count <= 0) return cudaSuccess;
+  Pose6 p;
+  for (int j = 0; j < 6; ++j) p.v[j] = pose6[j];
+  unsigned blocks = (unsigned)((count + 63) / 64);
+  if (static_pairs)
+    goal_sample_kernel<true><<<blocks, 64, 0, s>>>(pc, tab, p, seed, first, count, max_ik_iter, rows, row_index, row_erg, cap, n_out,
+                                                   stage_out, erg_all, rows_all);
+  else
+    goal_sample_kernel<false><<<blocks, 64, 0, s>>>(pc, tab, p, seed, first, count, max_ik_iter, rows, row_index, row_erg, cap, n_out,
+                                                    stage_out, erg_all, rows_all);
+  return cudaGetLastError();
+}
+cudaError_t launch_ma_project(const PlanConst& pc, const double* ma_pts, int n_pts, ForestView F, RrtState S, const int32_t* idx_a,
+                              const double* q_near, double* q_new, int32_t* status, int nq, cudaStream_t s) {
+  if (nq <= 0) return cudaSuccess;
+  ma_project_kernel<<<(unsigned)((nq + 31) / 32), 32, 0, s>>>(pc, ma_pts, n_pts, F, S, idx_a, q_near, q_new, status, nq);
+  return cudaGetLastError();
+}
+
+}  // namespace nwb

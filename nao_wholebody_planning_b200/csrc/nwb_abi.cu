@@ -75,6 +75,11 @@ int nwb_params_default(nwb_params* p) {
   p->pinv_eps = 1e-5;
   p->shortcut_waypoints = 100;
   p->shortcut_max_rounds = 500;
+  p->r_arm_weight_approach = 1.0; p->l_arm_weight_approach = 1.0; p->legs_weight_approach = 1.0;
+  p->r_arm_weight_manipulate = 1.0; p->l_arm_weight_manipulate = 0.0; p->legs_weight_manipulate = 1.0;
+  p->manipulate_waypoints = 4;
+  p->object_interp_points = 20;
+  p->manipulation_velocity = 0.02;
   return NWB_OK;
 }
 

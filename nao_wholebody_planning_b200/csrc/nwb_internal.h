@@ -84,6 +84,7 @@ struct Ctx {
   void* d_forest = nullptr; size_t d_forest_bytes = 0; // pooled forest of the RRT driver (grow-only)
   void* d_rrt = nullptr; size_t d_rrt_bytes = 0;       // control state / staging of the RRT driver (grow-only)
   int32_t* h_flag = nullptr;                           // pinned word the RRT driver polls
+  std::vector<double> ds_db;                           // stable-configuration database of the services (RP:121-191)
   double last_ms = 0;
   int64_t last_launches = 0;
   int64_t last_nn_passes = 0;        // passes over the node array of the last nearest-neighbour call
@@ -102,12 +103,14 @@ cudaError_t launch_ffma_peak(int sm_count, int iters, float* sink, cudaStream_t 
 
 // Pooled forest of the RRT driver: 2 trees per query, fixed capacity each (device pointers).
 //   soa float [T][21][cap] | aos double [T][cap][21] | pred int32 [T][cap] | size int32 [T]
+//   hand int32 [T][cap]: Node::cart_hand_pose_index (RPh:35), only with an articulation constraint
 struct ForestView {
   float* soa;
   double* aos;
   int32_t* pred;
   int32_t* size;
   int64_t cap;
+  int32_t* hand;
 };
 // Per-query control state of the lock-step RRT-Connect driver (device arrays of length nq).
 struct RrtState {
@@ -122,6 +125,7 @@ struct RrtState {
   int32_t* tree_b;      // tree that tries to connect
   int32_t* idx_b;       // nearest neighbour of q_connect in tree_b
   double* q_connect;    // node just added to tree_a
+  int32_t* connect_hand;// its cart_hand_pose_index (articulation constraint only)
   double* cstart;       // configuration of that nearest neighbour
   int32_t* n_active;    // [1]
   int32_t* overflow;    // [1] a tree outgrew its capacity
@@ -129,8 +133,9 @@ struct RrtState {
 
 // planner kernels (planner_kernels.cu); all pointers are device pointers
 struct PlanConst;
+// ma_pts: [nq][n_pts][6] hand trajectory per query (device) or nullptr = no articulation constraint
 cudaError_t launch_connect_forest(const PlanConst& pc, const ValidityTables& tab, bool static_pairs, ForestView F, RrtState S,
-                                  int nq, cudaStream_t s);
+                                  int nq, const double* ma_pts, int n_pts, cudaStream_t s);
 cudaError_t launch_steer_project(const PlanConst& pc, const double* q_near, const double* q_target, int64_t n, double* q_out,
                                  int32_t* status, int32_t* ds_status, int32_t* iters, cudaStream_t s);
 cudaError_t launch_connect(const PlanConst& pc, const ValidityTables& tab, bool static_pairs, const double* q_start,
@@ -141,6 +146,20 @@ cudaError_t launch_edge_check(const ValidityTables& tab, bool static_pairs, cons
 cudaError_t launch_sample(const PlanConst& pc, const ValidityTables& tab, bool static_pairs, uint64_t seed, uint64_t first,
                           int64_t count, int max_ik_iter, double* rows, uint64_t* row_index, int64_t cap,
                           unsigned long long* n_out, uint8_t* stage_out, cudaStream_t s);
+
+
+// right-arm kernels (arm_kernels.cu)
+cudaError_t launch_arm_ik(const double* targets, int64_t n, double* sols, int32_t* counts, cudaStream_t s);
+cudaError_t launch_goal_arm_ik(const PlanConst& pc, const double* pose6, const double* q, int64_t n, uint8_t* ok, double* arm,
+                               double* erg, cudaStream_t s);
+cudaError_t launch_enforce_ma(const PlanConst& pc, const double* pts_dev, int n_pts, int start_tree, const int32_t* near_hand,
+                              const double* q_near, const double* q_ds, int64_t n, double* q_out, int32_t* status, cudaStream_t s);
+cudaError_t launch_goal_sample(const PlanConst& pc, const ValidityTables& tab, bool static_pairs, const double* pose6, uint64_t seed,
+                               uint64_t first, int64_t count, int max_ik_iter, double* rows, uint64_t* row_index, double* row_erg,
+                               int64_t cap, unsigned long long* n_out, uint8_t* stage_out, double* erg_all, double* rows_all,
+                               cudaStream_t s);
+cudaError_t launch_ma_project(const PlanConst& pc, const double* ma_pts, int n_pts, ForestView F, RrtState S, const int32_t* idx_a,
+                              const double* q_near, double* q_new, int32_t* status, int nq, cudaStream_t s);
 
 }  // namespace nwb
 

@@ -14,6 +14,7 @@
 #include <climits>
 #include <cstdlib>
 
+#include "arm_core.cuh"
 #include "planner_core.cuh"
 #include "validity_core.cuh"
 
@@ -106,14 +107,17 @@ connect_kernel(const __grid_constant__ PlanConst pc, const __grid_constant__ Val
 template <bool STATIC>
 __global__ void __launch_bounds__(32)
 connect_forest_kernel(const __grid_constant__ PlanConst pc, const __grid_constant__ ValidityTables tab, ForestView F, RrtState S,
-                      int nq) {
+                      int nq, const double* __restrict__ ma_pts, int n_pts) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= nq || !S.active[k]) return;
   if (S.walking[k]) {
     const int t = S.tree_b[k];
+    const bool start_tree = (t & 1) == 0;
+    const MaView ma{ma_pts ? ma_pts + (size_t)k * n_pts * 6 : nullptr, n_pts};
     float* soa = F.soa + (size_t)t * NWB_NJ * F.cap;
     double* aos = F.aos + (size_t)t * F.cap * NWB_NJ;
     int32_t* pred = F.pred + (size_t)t * F.cap;
+    int32_t* hand = ma.pts ? F.hand + (size_t)t * F.cap : nullptr;
     int size = F.size[t];
     double cur[NWB_NJ], tgt[NWB_NJ], q[NWB_NJ];
     for (int j = 0; j < NWB_NJ; ++j) {
@@ -122,11 +126,24 @@ connect_forest_kernel(const __grid_constant__ PlanConst pc, const __grid_constan
     }
     int cur_idx = S.idx_b[k];
     int state = NWB_ADVANCED;
+    int cur_hand = 0, connect_hand = 0;
+    if (ma.pts) {
+      cur_hand = hand[cur_idx];
+      connect_hand = S.connect_hand[k];
+      // the trees may only meet with the hand indices in order (RP:917-922)
+      if ((start_tree && cur_hand > connect_hand) || (!start_tree && cur_hand < connect_hand)) state = NWB_TRAPPED;
+    }
     while (state == NWB_ADVANCED) {
       state = generate_q_new(cur, tgt, pc, q);
       int ds = enforce_ds_constraints(q, pc, nullptr);
       if (ds == NWB_TRAPPED) { state = NWB_TRAPPED; break; }
       if (ds == NWB_ADVANCED) state = NWB_ADVANCED;
+      if (ma.pts) {                              // enforce_MA_Constraints (RP:951-972)
+        const int mas = enforce_ma_constraints(ma, start_tree, cur_hand, cur, q, pc);
+        if (mas == NWB_TRAPPED) { state = NWB_TRAPPED; break; }
+        if (mas == NWB_ADVANCED) state = NWB_ADVANCED;
+        if (cur_hand == connect_hand && state != NWB_REACHED) { state = NWB_TRAPPED; break; }   // RP:968
+      }
       ValidityResult<float> r = eval_one<false, STATIC>(tab, q);
       if (r.hit || !r.stable) { state = NWB_TRAPPED; break; }
       if (size >= F.cap) {                       // tree full: give the query up and report it
@@ -139,10 +156,13 @@ connect_forest_kernel(const __grid_constant__ PlanConst pc, const __grid_constan
         soa[(size_t)j * F.cap + size] = (float)q[j];
       }
       pred[size] = cur_idx;
+      const int new_hand = ma.pts ? next_hand_index(ma, start_tree, cur_hand) : 0;
+      if (ma.pts) hand[size] = new_hand;
       if (state == NWB_REACHED) {
         S.bridge[k] = cur_idx;                   // q_near = current_q_near (RP:1000-1001)
       } else {
         cur_idx = size;                          // current_q_near = tree.nodes.back() (RP:1004)
+        cur_hand = new_hand;
         for (int j = 0; j < NWB_NJ; ++j) cur[j] = q[j];
       }
       ++size;
@@ -298,11 +318,11 @@ cudaError_t launch_connect(const PlanConst& pc, const ValidityTables& tab, bool 
 }
 
 cudaError_t launch_connect_forest(const PlanConst& pc, const ValidityTables& tab, bool static_pairs, ForestView F, RrtState S,
-                                  int nq, cudaStream_t s) {
+                                  int nq, const double* ma_pts, int n_pts, cudaStream_t s) {
   if (nq <= 0) return cudaSuccess;
   unsigned blocks = (unsigned)((nq + 31) / 32);
-  if (static_pairs) connect_forest_kernel<true><<<blocks, 32, 0, s>>>(pc, tab, F, S, nq);
-  else connect_forest_kernel<false><<<blocks, 32, 0, s>>>(pc, tab, F, S, nq);
+  if (static_pairs) connect_forest_kernel<true><<<blocks, 32, 0, s>>>(pc, tab, F, S, nq, ma_pts, n_pts);
+  else connect_forest_kernel<false><<<blocks, 32, 0, s>>>(pc, tab, F, S, nq, ma_pts, n_pts);
   return cudaGetLastError();
 }
 

@@ -21,6 +21,7 @@
 #include <cstring>
 #include <vector>
 
+#include "arm_core.cuh"
 #include "nwb_internal.h"
 #include "planner_core.cuh"
 
@@ -150,7 +151,7 @@ __global__ void forest_append_kernel(ForestView F, const int32_t* __restrict__ t
 // after steer/project + validity: extendTree's decision (RP:846-870).  A surviving q_new is appended to
 // tree_a (predecessor = its nearest neighbour) and becomes q_connect of this iteration's connectTree.
 __global__ void rrt_extend_commit_kernel(ForestView F, RrtState S, const int32_t* __restrict__ status, const uint8_t* __restrict__ valid,
-                                         const int32_t* __restrict__ idx_a, const double* __restrict__ q_new, int nq) {
+                                         const int32_t* __restrict__ idx_a, const double* __restrict__ q_new, int nq, int n_pts) {
   const int k = blockIdx.x;
   if (k >= nq || !S.active[k]) return;
   if (status[k] == NWB_TRAPPED || !valid[k]) return;        // walking stays 0: only the swap happens this iteration
@@ -175,7 +176,19 @@ __global__ void rrt_extend_commit_kernel(ForestView F, RrtState S, const int32_t
     F.pred[(size_t)t * F.cap + base] = idx_a[k];
     F.size[t] = base + 1;
     S.walking[k] = 1;
+    if (n_pts > 0) {                                        // addConfigtoTree's hand index (RP:757-767)
+      const int h = next_hand_index(MaView{nullptr, n_pts}, (t & 1) == 0, F.hand[(size_t)t * F.cap + idx_a[k]]);
+      F.hand[(size_t)t * F.cap + base] = h;
+      S.connect_hand[k] = h;
+    }
   }
+}
+
+// setStartGoalConfigs with an active articulation constraint (RP:274-282): the start root sits on the
+// first trajectory point, the goal root on the last.
+__global__ void forest_root_hand_kernel(ForestView F, int n_trees, int n_pts) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n_trees) F.hand[(size_t)t * F.cap] = (t & 1) ? n_pts - 1 : 0;
 }
 
 }  // namespace nwb
@@ -200,17 +213,17 @@ struct DevBuf {
 };
 }  // namespace
 
-extern "C" {
-
-int nwb_solve_query_batch(nwb_ctx* ctx, const double* starts, const double* goals, int64_t nq, const double* db, int32_t n_db,
-                          const double* weights, const uint64_t* seeds, int32_t max_iter, double step, int32_t tree_capacity,
-                          nwb_plan_result* results, double* raw_paths, int32_t raw_path_capacity) {
+static int solve_impl(nwb_ctx* ctx, const double* starts, const double* goals, int64_t nq, const double* db, int32_t n_db,
+                      const double* weights, const uint64_t* seeds, int32_t max_iter, double step, int32_t tree_capacity,
+                      const double* hand_traj, int32_t n_pts, nwb_plan_result* results, double* raw_paths,
+                      int32_t raw_path_capacity) {
   if (!ctx) return NWB_E_INVALID;
   if (nq < 0 || (nq > 0 && (!starts || !goals || !db || !seeds || !results)) || n_db < 2 || max_iter < 0 || !(step > 0) ||
-      (raw_paths && raw_path_capacity <= 0)) {
+      (raw_paths && raw_path_capacity <= 0) || (hand_traj && n_pts < 2)) {
     ctx->err = "nwb_solve_query_batch: bad argument";
     return NWB_E_INVALID;
   }
+  const int P = hand_traj ? n_pts : 0;
   if (nq == 0) return NWB_OK;
   R_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
@@ -232,7 +245,8 @@ int nwb_solve_query_batch(nwb_ctx* ctx, const double* starts, const double* goal
     return e;
   };
   const size_t soa_b = sizeof(float) * NWB_NJ * C * T, aos_b = sizeof(double) * NWB_NJ * C * T, pred_b = sizeof(int32_t) * C * T;
-  R_CUDA(ctx, grow(&ctx->d_forest, &ctx->d_forest_bytes, soa_b + aos_b + pred_b + 256));
+  const size_t hand_b = P ? pred_b : 0;
+  R_CUDA(ctx, grow(&ctx->d_forest, &ctx->d_forest_bytes, soa_b + aos_b + pred_b + hand_b + 256));
   size_t off = 0;
   auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
   const size_t o_size = carve(sizeof(int32_t) * T), o_db = carve(sizeof(double) * NWB_NJ * n_db), o_seeds = carve(sizeof(uint64_t) * Q),
@@ -242,13 +256,15 @@ int nwb_solve_query_batch(nwb_ctx* ctx, const double* starts, const double* goal
                o_succ = carve(sizeof(int32_t) * Q), o_conn = carve(sizeof(int32_t) * Q), o_bridge = carve(sizeof(int32_t) * Q),
                o_ta = carve(sizeof(int32_t) * Q), o_tb = carve(sizeof(int32_t) * Q), o_ia = carve(sizeof(int32_t) * Q),
                o_ib = carve(sizeof(int32_t) * Q), o_cnt = carve(sizeof(int32_t) * T), o_roots = carve(sizeof(int32_t) * T),
-               o_zero = carve(sizeof(int32_t) * T), o_nact = carve(16), o_ovf = carve(16);
+               o_zero = carve(sizeof(int32_t) * T), o_nact = carve(16), o_ovf = carve(16), o_chand = carve(sizeof(int32_t) * Q),
+               o_ma = carve(sizeof(double) * 6 * (size_t)P * Q);
   R_CUDA(ctx, grow(&ctx->d_rrt, &ctx->d_rrt_bytes, off));
   R_CUDA(ctx, cudaMemsetAsync(ctx->d_rrt, 0, off, s));           // inactive slots still flow through the kernels: keep them finite
   char* M = static_cast<char*>(ctx->d_rrt);
   char* FB = static_cast<char*>(ctx->d_forest);
   ForestView F{reinterpret_cast<float*>(FB), reinterpret_cast<double*>(FB + ((soa_b + 255) & ~(size_t)255)),
-               reinterpret_cast<int32_t*>(FB + ((soa_b + 255) & ~(size_t)255) + aos_b), reinterpret_cast<int32_t*>(M + o_size), C};
+               reinterpret_cast<int32_t*>(FB + ((soa_b + 255) & ~(size_t)255) + aos_b), reinterpret_cast<int32_t*>(M + o_size), C,
+               P ? reinterpret_cast<int32_t*>(FB + ((soa_b + 255) & ~(size_t)255) + aos_b + pred_b) : nullptr};
   RrtState S;
   S.active = reinterpret_cast<uint8_t*>(M + o_active);
   S.swap = reinterpret_cast<uint8_t*>(M + o_swap);
@@ -264,6 +280,8 @@ int nwb_solve_query_batch(nwb_ctx* ctx, const double* starts, const double* goal
   S.cstart = reinterpret_cast<double*>(M + o_cstart);
   S.n_active = reinterpret_cast<int32_t*>(M + o_nact);
   S.overflow = reinterpret_cast<int32_t*>(M + o_ovf);
+  S.connect_hand = reinterpret_cast<int32_t*>(M + o_chand);
+  double* d_ma = P ? reinterpret_cast<double*>(M + o_ma) : nullptr;
   double* d_db = reinterpret_cast<double*>(M + o_db);
   uint64_t* d_seeds = reinterpret_cast<uint64_t*>(M + o_seeds);
   double* d_sg = reinterpret_cast<double*>(M + o_sg);
@@ -276,6 +294,7 @@ int nwb_solve_query_batch(nwb_ctx* ctx, const double* starts, const double* goal
 
   R_CUDA(ctx, cudaMemcpyAsync(d_db, db, sizeof(double) * NWB_NJ * n_db, cudaMemcpyHostToDevice, s));
   R_CUDA(ctx, cudaMemcpyAsync(d_seeds, seeds, sizeof(uint64_t) * Q, cudaMemcpyHostToDevice, s));
+  if (P) R_CUDA(ctx, cudaMemcpyAsync(d_ma, hand_traj, sizeof(double) * 6 * (size_t)P * Q, cudaMemcpyHostToDevice, s));
   R_CUDA(ctx, cudaMemcpyAsync(d_sg, starts, qbytes, cudaMemcpyHostToDevice, s));
   R_CUDA(ctx, cudaMemcpyAsync(reinterpret_cast<char*>(d_sg) + qbytes, goals, qbytes, cudaMemcpyHostToDevice, s));
 
@@ -305,6 +324,10 @@ int nwb_solve_query_batch(nwb_ctx* ctx, const double* starts, const double* goal
   R_CUDA(ctx, cudaMemcpyAsync(S.n_active, &n_active, sizeof(int32_t), cudaMemcpyHostToDevice, s));
   forest_append_kernel<<<T, 32, 0, s>>>(F, reinterpret_cast<int32_t*>(M + o_roots), d_sg, 1, reinterpret_cast<int32_t*>(M + o_cnt),
                                         reinterpret_cast<int32_t*>(M + o_zero), T, nullptr, S.overflow);
+  if (P) {
+    forest_root_hand_kernel<<<(T + 63) / 64, 64, 0, s>>>(F, T, P);
+    ++launches;
+  }
   R_CUDA(ctx, cudaGetLastError());
   ++launches;
 
@@ -318,17 +341,18 @@ int nwb_solve_query_batch(nwb_ctx* ctx, const double* starts, const double* goal
     // extendTree (RP:787-884)
     forest_nn_kernel<<<Q, 128, 0, s>>>(F, S.tree_a, S.active, d_qrand, Q, d_idx_a, d_near);
     cudaError_t e = launch_steer_project(pc, d_near, d_qrand, Q, d_qnew, d_status, nullptr, nullptr, s);
+    if (e == cudaSuccess && P) e = launch_ma_project(pc, d_ma, P, F, S, d_idx_a, d_near, d_qnew, d_status, Q, s);   // RP:829-837
     if (e == cudaSuccess) e = launch_validity(ctx->tab_group, d_qnew, NWB_F64, Q, d_valid, nullptr, nullptr, false, sp, s);
-    rrt_extend_commit_kernel<<<Q, 32, 0, s>>>(F, S, d_status, d_valid, d_idx_a, d_qnew, Q);
+    rrt_extend_commit_kernel<<<Q, 32, 0, s>>>(F, S, d_status, d_valid, d_idx_a, d_qnew, Q, P);
     // connectTree (RP:890-1034) for the queries that extended, then the swap
     forest_nn_kernel<<<Q, 128, 0, s>>>(F, S.tree_b, S.walking, S.q_connect, Q, S.idx_b, S.cstart);
-    if (e == cudaSuccess) e = launch_connect_forest(pc, ctx->tab_group, sp, F, S, Q, s);
+    if (e == cudaSuccess) e = launch_connect_forest(pc, ctx->tab_group, sp, F, S, Q, d_ma, P, s);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) {
       ctx->err = std::string("nwb_solve_query_batch: ") + cudaGetErrorString(e);
       return NWB_E_CUDA;
     }
-    launches += 7;
+    launches += P ? 8 : 7;
     if (++since_check >= check_every || it + 1 == max_iter) {  // look at the active count now and then
       since_check = 0;
       check_every = std::min(16, check_every * 2);
@@ -397,6 +421,23 @@ int nwb_solve_query_batch(nwb_ctx* ctx, const double* starts, const double* goal
     return NWB_E_NOMEM;
   }
   return NWB_OK;
+}
+
+extern "C" {
+
+int nwb_solve_query_batch(nwb_ctx* ctx, const double* starts, const double* goals, int64_t nq, const double* db, int32_t n_db,
+                          const double* weights, const uint64_t* seeds, int32_t max_iter, double step, int32_t tree_capacity,
+                          nwb_plan_result* results, double* raw_paths, int32_t raw_path_capacity) {
+  return solve_impl(ctx, starts, goals, nq, db, n_db, weights, seeds, max_iter, step, tree_capacity, nullptr, 0, results, raw_paths,
+                    raw_path_capacity);
+}
+
+int nwb_solve_query_constrained_batch(nwb_ctx* ctx, const double* starts, const double* goals, int64_t nq, const double* db,
+                                      int32_t n_db, const double* weights, const uint64_t* seeds, int32_t max_iter, double step,
+                                      int32_t tree_capacity, const double* hand_trajectories, int32_t n_points,
+                                      nwb_plan_result* results, double* raw_paths, int32_t raw_path_capacity) {
+  return solve_impl(ctx, starts, goals, nq, db, n_db, weights, seeds, max_iter, step, tree_capacity, hand_trajectories,
+                    hand_trajectories ? n_points : 0, results, raw_paths, raw_path_capacity);
 }
 
 // path_shortcutter way-point selection (RP:1830-1951): every round evaluates ALL candidate edges of

@@ -1,0 +1,585 @@
+// service_abi.cu - extern "C" entry points of the right-arm operators, goal-configuration sampling and
+// the planning services (include/nwb.h).  Host-side orchestration only; the arithmetic runs in
+// arm_kernels.cu / planner_kernels.cu / validity.cu.
+//
+// Reference code replaced (file:line relative to the reference checkout):
+//   NAO_PLANNER_CONTROL::compute_goal_config / compute_motion_plan / compute_linear_manipulation_plan /
+//   compute_circular_manipulation_plan        rrt_connect_planner/src/nao_planner_control.cpp:150-870
+//   StableConfigGenerator::sample_stable_configs (goal branch), sort_goal_configs_by_ergonomy, loadGoalConfig
+//                                              rrt_connect_planner/src/stable_config_generator.cpp:176-507,510-661,666-756
+//   ArticulatedObjectConstraints::computeDrawerTrajectoryPoints / computeDoorTrajectoryPoints
+//                                              rrt_connect_planner/src/articulated_object_constraints.cpp:105-189
+//   RRT_Planner::activate_drawer_constraint / activate_door_constraint / writePath / generateTrajectory (time stamps)
+//                                              rrt_connect_planner/src/rrt_planner.cpp:195-223,1303-1455,1532-1553
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "nwb_internal.h"
+#include "planner_core.cuh"
+
+using namespace nwb;
+
+namespace nwb {
+void make_plan_const(const nwb_ctx* ctx, const double* weights, double step, PlanConst& pc);
+}
+
+namespace {
+#define S_CUDA(ctx, call)                                                      \
+  do {                                                                         \
+    cudaError_t e_ = (call);                                                   \
+    if (e_ != cudaSuccess) {                                                   \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_);         \
+      return NWB_E_CUDA;                                                       \
+    }                                                                          \
+  } while (0)
+
+int bad(nwb_ctx* ctx, const char* msg) {
+  if (ctx) ctx->err = msg;
+  return NWB_E_INVALID;
+}
+bool static_pairs(const nwb_ctx* ctx) { return ctx->params.srdf_trim != 0 && !ctx->force_table_pairs; }
+
+// device scratch of this file's operators (shares the planner scratch buffer of the context)
+struct Scratch {
+  nwb_ctx* ctx;
+  size_t off = 0;
+  explicit Scratch(nwb_ctx* c) : ctx(c) {}
+  size_t add(size_t bytes) {
+    size_t o = off;
+    off += (bytes + 255) & ~(size_t)255;
+    return o;
+  }
+  int commit() {
+    if (off <= ctx->d_plan_bytes) return NWB_OK;
+    if (ctx->d_plan) cudaFree(ctx->d_plan);
+    ctx->d_plan = nullptr;
+    ctx->d_plan_bytes = 0;
+    size_t cap = std::max(off, (size_t)1 << 20);
+    cudaError_t e = cudaMalloc(&ctx->d_plan, cap);
+    if (e != cudaSuccess) {
+      ctx->err = std::string("cudaMalloc(scratch): ") + cudaGetErrorString(e);
+      return NWB_E_CUDA;
+    }
+    ctx->d_plan_bytes = cap;
+    return NWB_OK;
+  }
+  template <class T>
+  T* at(size_t o) const { return reinterpret_cast<T*>(static_cast<char*>(ctx->d_plan) + o); }
+};
+
+bool zero_direction(const double* pose6) { return pose6[3] == 0.0 && pose6[4] == 0.0 && pose6[5] == 0.0; }   // NCK:291
+
+// the goal files keep 6 significant digits: `ofstream << double` (SCG:409-417), re-read with strtod (SCG:540-560)
+double through_text(double v) {
+  char buf[64];
+  std::snprintf(buf, sizeof buf, "%g", v);
+  return std::strtod(buf, nullptr);
+}
+
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+struct GoalSet {
+  int n_found = 0;
+  int64_t drawn = 0;
+  double rows[6][NWB_NJ];
+  double erg[6];
+  uint64_t index[6];
+};
+
+constexpr int kGoalsWanted = 6;   // SCG:429: the loop leaves once goal_samples > 5
+
+// sample_stable_configs(goal branch) + sort_goal_configs_by_ergonomy.  All max_samples candidates are
+// evaluated in ONE launch (the serial reference stops after the sixth accepted sample; the samples
+// behind it are independent, so evaluating them costs nothing but idle lanes) and the six accepted
+// rows with the lowest sample index are kept.
+int sample_goals(nwb_ctx* ctx, uint64_t seed, const double* pose6, int max_samples, int max_ik_iter, GoalSet& g) {
+  g = GoalSet();
+  if (zero_direction(pose6)) return bad(ctx, "hand direction (0,0,0): the position-only KDL branch (NCK:291-372) is not supported");
+  if (max_samples <= 0) return NWB_OK;
+  S_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  const int64_t cap = max_samples;
+  Scratch A(ctx);
+  size_t o_rows = A.add(sizeof(double) * NWB_NJ * cap), o_idx = A.add(sizeof(uint64_t) * cap), o_erg = A.add(sizeof(double) * cap),
+         o_n = A.add(8);
+  int rc = A.commit();
+  if (rc != NWB_OK) return rc;
+  PlanConst pc;
+  make_plan_const(ctx, nullptr, ctx->params.planner_step_factor, pc);
+  S_CUDA(ctx, cudaMemsetAsync(A.at<char>(o_n), 0, 8, s));
+  S_CUDA(ctx, launch_goal_sample(pc, ctx->tab_group, static_pairs(ctx), pose6, seed, 0, max_samples, max_ik_iter, A.at<double>(o_rows),
+                                 A.at<uint64_t>(o_idx), A.at<double>(o_erg), cap, A.at<unsigned long long>(o_n), nullptr, nullptr,
+                                 nullptr, s));
+  unsigned long long got = 0;
+  S_CUDA(ctx, cudaMemcpyAsync(&got, A.at<char>(o_n), 8, cudaMemcpyDeviceToHost, s));
+  S_CUDA(ctx, cudaStreamSynchronize(s));
+  ctx->last_launches = 1;
+  std::vector<double> rows(got * NWB_NJ), erg(got);
+  std::vector<uint64_t> idx(got);
+  if (got) {
+    S_CUDA(ctx, cudaMemcpyAsync(rows.data(), A.at<double>(o_rows), sizeof(double) * NWB_NJ * got, cudaMemcpyDeviceToHost, s));
+    S_CUDA(ctx, cudaMemcpyAsync(idx.data(), A.at<uint64_t>(o_idx), sizeof(uint64_t) * got, cudaMemcpyDeviceToHost, s));
+    S_CUDA(ctx, cudaMemcpyAsync(erg.data(), A.at<double>(o_erg), sizeof(double) * got, cudaMemcpyDeviceToHost, s));
+    S_CUDA(ctx, cudaStreamSynchronize(s));
+  }
+  std::vector<size_t> order(got);
+  std::iota(order.begin(), order.end(), (size_t)0);
+  std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return idx[a] < idx[b]; });
+  const int n = (int)std::min<size_t>(got, kGoalsWanted);
+  g.drawn = n == kGoalsWanted ? (int64_t)idx[order[n - 1]] + 1 : max_samples;
+  // file order = sample order; values pass through the text format before the sort reads them
+  double f_erg[6], f_rows[6][NWB_NJ];
+  uint64_t f_idx[6];
+  for (int r = 0; r < n; ++r) {
+    f_erg[r] = through_text(erg[order[r]]);
+    f_idx[r] = idx[order[r]];
+    for (int j = 0; j < NWB_NJ; ++j) f_rows[r][j] = through_text(rows[order[r] * NWB_NJ + j]);
+  }
+  // SCG:585-612: n rounds of "largest remaining value > 0.0"; the winner is zeroed afterwards
+  double e2[6];
+  for (int r = 0; r < n; ++r) e2[r] = f_erg[r];
+  int imax = 0;
+  for (int round = 0; round < n; ++round) {
+    double vmax = 0.0;
+    for (int i = 0; i < n; ++i)
+      if (e2[i] > vmax) {
+        vmax = e2[i];
+        imax = i;
+      }
+    g.erg[round] = f_erg[imax];
+    g.index[round] = f_idx[imax];
+    std::memcpy(g.rows[round], f_rows[imax], sizeof(double) * NWB_NJ);
+    e2[imax] = 0.0;
+  }
+  g.n_found = n;
+  return NWB_OK;
+}
+
+void limb_weights(double r_arm, double l_arm, double legs, double* w) {   // NPC:280-306
+  for (int i = 0; i < 5; ++i) w[i] = legs;
+  for (int i = 5; i < 10; ++i) w[i] = l_arm;
+  for (int i = 10; i < 15; ++i) w[i] = r_arm;
+  w[15] = 0.0;                                                            // LHipYawPitch
+  for (int i = 16; i < NWB_NJ; ++i) w[i] = legs;
+}
+
+void put_trajectory(const std::vector<double>& path, bool articulated, float time_step_manip, nwb_trajectory& t) {
+  const int n = (int)(path.size() / NWB_NJ);
+  t.n_points = n;
+  float increment = 2.0f;                                                 // RP:1532
+  for (int i = 0; i < n; ++i) {
+    if (i < t.capacity) {
+      if (t.positions) std::memcpy(t.positions + (size_t)i * NWB_NJ, path.data() + (size_t)i * NWB_NJ, sizeof(double) * NWB_NJ);
+      if (t.time_from_start) t.time_from_start[i] = (double)increment;
+    }
+    increment = articulated ? increment + time_step_manip : increment + 1.0f;   // RP:1547-1552
+  }
+}
+
+struct StageOut {
+  bool success = false;
+  uint32_t num_nodes = 0;
+  double search_time = 0.0;
+  std::vector<double> path;
+};
+
+// setStartGoalConfigs + solveQuery + writePath (RP:227-302, 1039-1212, 1303-1455) for one query
+int plan_stage(nwb_ctx* ctx, const double* start, const double* goal, const double* weights, uint64_t seed, const double* hand_traj,
+               int n_pts, bool execute, StageOut& out) {
+  out = StageOut();
+  if (ctx->ds_db.size() < 2 * NWB_NJ) {
+    ctx->err = "no stable-configuration database loaded (nwb_ctx_set_ds_database / nwb_ctx_load_ds_database)";
+    return NWB_E_STATE;
+  }
+  const nwb_params& P = ctx->params;
+  const int cap = 8192;
+  std::vector<double> raw((size_t)cap * NWB_NJ);
+  nwb_plan_result r;
+  const double t0 = now_s();
+  int rc = nwb_solve_query_constrained_batch(ctx, start, goal, 1, ctx->ds_db.data(), (int32_t)(ctx->ds_db.size() / NWB_NJ), weights,
+                                             &seed, P.planner_max_iterations, P.planner_step_factor, 0, hand_traj, n_pts, &r,
+                                             raw.data(), cap);
+  if (rc != NWB_OK) return rc;
+  out.search_time = now_s() - t0;                                         // RP:1092-1094: stops before writePath
+  if (!r.success) return NWB_OK;
+  out.num_nodes = (uint32_t)r.num_nodes_generated;
+  const int n_raw = std::min(r.raw_path_len, cap);
+  if (!hand_traj) {                                                       // RP:1400-1405
+    std::vector<double> sel((size_t)(n_raw + 8) * NWB_NJ);
+    int n_sel = nwb_shortcut_path(ctx, raw.data(), n_raw, sel.data(), n_raw + 8, nullptr);
+    if (n_sel == -100) return NWB_OK;                                     // RP:1919-1923: shortcutting failed, empty trajectory
+    if (n_sel < 0) return n_sel;
+    if (!execute) {                                                       // RP:1935-1945
+      const int rows = (n_sel - 1) * (P.shortcut_waypoints + 1) + 1;
+      out.path.resize((size_t)rows * NWB_NJ);
+      nwb_interpolate_path(sel.data(), n_sel, P.shortcut_waypoints, out.path.data(), rows);
+    } else {
+      out.path.assign(sel.begin(), sel.begin() + (size_t)n_sel * NWB_NJ);
+    }
+  } else if (!execute) {                                                  // RP:1408-1413
+    const int rows = (n_raw - 1) * (P.manipulate_waypoints + 1) + 1;
+    out.path.resize((size_t)rows * NWB_NJ);
+    nwb_interpolate_path(raw.data(), n_raw, P.manipulate_waypoints, out.path.data(), rows);
+  } else {
+    out.path.assign(raw.begin(), raw.begin() + (size_t)n_raw * NWB_NJ);   // RP:1417
+  }
+  out.success = !out.path.empty();
+  return NWB_OK;
+}
+
+void pose_of(const nwb_point3& p, const nwb_point3& d, double* pose6) {
+  pose6[0] = p.x; pose6[1] = p.y; pose6[2] = p.z;
+  pose6[3] = d.x; pose6[4] = d.y; pose6[5] = d.z;
+}
+
+void drawer_points(const double* a, const double* b, int num_interp, double* out) {          // AOC:105-122
+  double step[6];
+  for (int i = 0; i < 6; ++i) step[i] = (b[i] - a[i]) / (num_interp + 1);
+  for (int s = 0; s < num_interp + 2; ++s)
+    for (int i = 0; i < 6; ++i) out[s * 6 + i] = a[i] + (step[i] * s);
+}
+void door_points(const double* a, const double* b, int num_interp, const double* door, double* out) {   // AOC:126-189
+  const double relative_angle = door[2] * (M_PI / 180);
+  const double step_angle = (door[1] * (M_PI / 180)) / (num_interp + 1);
+  double sd[3];
+  for (int i = 0; i < 3; ++i) sd[i] = (b[3 + i] - a[3 + i]) / (num_interp + 1);
+  double x_door = a[0] + door[3] * std::cos(relative_angle);
+  double y_door = a[1] - door[3] * std::sin(relative_angle);
+  double z_door = a[2];
+  const double x_hinge = x_door - door[0] * std::sin(relative_angle);
+  const double y_hinge = y_door - door[0] * std::cos(relative_angle);
+  const double z_hinge = z_door;
+  for (int s = 0; s < num_interp + 2; ++s) {
+    double tmp_angle = ((step_angle * s) - relative_angle);
+    x_door = x_hinge - door[0] * std::sin(tmp_angle);
+    y_door = y_hinge + door[0] * std::cos(tmp_angle);
+    z_door = z_hinge;
+    tmp_angle = 1.5708 - tmp_angle;                                       // AOC:176: "90 degrees"
+    double* o = out + s * 6;
+    o[0] = x_door - door[3] * std::sin(tmp_angle);
+    o[1] = y_door - door[3] * std::cos(tmp_angle);
+    o[2] = z_door;
+    for (int i = 0; i < 3; ++i) o[3 + i] = a[3 + i] + (sd[i] * s);
+  }
+}
+
+// the common body of the linear / circular manipulation services
+int manipulation_plan(nwb_ctx* ctx, const double* pose6, const double* start, bool execute, bool circular, const double* object,
+                      nwb_manipulation_plan_response* resp, uint64_t seed) {
+  const nwb_params& P = ctx->params;
+  resp->motion_plan_approach.n_points = 0;
+  resp->motion_plan_manipulation.n_points = 0;
+  resp->time_goal_config_approach = resp->time_goal_config_manipulate = 0.0;
+  resp->num_nodes_generated_approach = resp->num_nodes_generated_manipulate = 0;
+  resp->search_time_approach = resp->search_time_manipulate = 0.0;
+  resp->success_approach = resp->success_manipulation = 0;
+  // ---- approach (NPC:430-494 / 690-753)
+  GoalSet ga;
+  double t0 = now_s();
+  int rc = sample_goals(ctx, seed, pose6, P.scg_max_samples, P.scg_max_ik_iterations, ga);
+  if (rc != NWB_OK) return rc;
+  resp->time_goal_config_approach = now_s() - t0;
+  if (ga.n_found == 0) return NWB_OK;
+  std::memcpy(resp->wb_goal_config_approach, ga.rows[0], sizeof(double) * NWB_NJ);
+  double w[NWB_NJ];
+  limb_weights(P.r_arm_weight_approach, P.l_arm_weight_approach, P.legs_weight_approach, w);
+  StageOut sa;
+  rc = plan_stage(ctx, start, ga.rows[0], w, seed + 2, nullptr, 0, execute, sa);
+  if (rc != NWB_OK) return rc;
+  resp->num_nodes_generated_approach = sa.num_nodes;
+  resp->search_time_approach = sa.search_time;
+  resp->success_approach = sa.success;
+  if (!sa.success) return NWB_OK;
+  put_trajectory(sa.path, false, 0.f, resp->motion_plan_approach);
+  // ---- manipulation (NPC:498-585 / 757-866)
+  double pm[6];
+  const int NI = P.object_interp_points;
+  std::vector<double> traj((size_t)(NI + 2) * 6);
+  float time_step;
+  if (!circular) {
+    const double pos_angle = (90.0 - object[0]) * (M_PI / 180);                       // NPC:502
+    pm[0] = pose6[0] - object[1] * std::sin(pos_angle);
+    pm[1] = pose6[1] + object[1] * std::cos(pos_angle);
+    pm[2] = pose6[2];
+  } else {                                                                             // NPC:762-790
+    const double rel = object[0] * (M_PI / 180);
+    double x_door = pose6[0] + object[3] * std::cos(rel);
+    double y_door = pose6[1] - object[3] * std::sin(rel);
+    const double z_door = pose6[2];
+    const double x_hinge = x_door - object[1] * std::sin(rel);
+    const double y_hinge = y_door - object[1] * std::cos(rel);
+    double tmp_angle = (object[2] - object[0]) * (M_PI / 180);
+    x_door = x_hinge - object[1] * std::sin(tmp_angle);
+    y_door = y_hinge + object[1] * std::cos(tmp_angle);
+    tmp_angle = 1.5708 - tmp_angle;
+    pm[0] = x_door - object[3] * std::sin(tmp_angle);
+    pm[1] = y_door - object[3] * std::cos(tmp_angle);
+    pm[2] = z_door;
+  }
+  for (int i = 3; i < 6; ++i) pm[i] = pose6[i];
+  GoalSet gm;
+  t0 = now_s();
+  rc = sample_goals(ctx, seed + 1, pm, P.scg_max_samples, P.scg_max_ik_iterations, gm);
+  if (rc != NWB_OK) return rc;
+  resp->time_goal_config_manipulate = now_s() - t0;
+  if (gm.n_found == 0) return NWB_OK;
+  std::memcpy(resp->wb_goal_config_manipulate, gm.rows[0], sizeof(double) * NWB_NJ);
+  const float velocity = (float)P.manipulation_velocity;
+  if (!circular) {                                                                     // RP:195-206
+    drawer_points(pose6, pm, NI, traj.data());
+    const float manipulation_time = (float)(object[1]) / velocity;
+    time_step = manipulation_time / float(NI + 2);
+  } else {                                                                             // NPC:816-822, RP:209-223
+    const double door[4] = {object[1], object[2], object[0], object[3]};
+    door_points(pose6, pm, NI, door, traj.data());
+    const float arc_length = float(door[0] * M_PI * door[1]) / 180.0f;
+    const float manipulation_time = arc_length / velocity;
+    time_step = manipulation_time / float(NI + 2);
+  }
+  limb_weights(P.r_arm_weight_manipulate, P.l_arm_weight_manipulate, P.legs_weight_manipulate, w);
+  StageOut sm;
+  rc = plan_stage(ctx, ga.rows[0], gm.rows[0], w, seed + 3, traj.data(), NI + 2, execute, sm);
+  if (rc != NWB_OK) return rc;
+  resp->num_nodes_generated_manipulate = sm.num_nodes;
+  resp->search_time_manipulate = sm.search_time;
+  resp->success_manipulation = sm.success;
+  if (sm.success) put_trajectory(sm.path, true, time_step, resp->motion_plan_manipulation);
+  return NWB_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int nwb_arm_ik_batch(nwb_ctx* ctx, const double* targets, int64_t n, double* solutions, int32_t* counts) {
+  if (!ctx) return NWB_E_INVALID;
+  if (n < 0 || (n > 0 && (!targets || !solutions || !counts))) return bad(ctx, "nwb_arm_ik_batch: bad argument");
+  if (n == 0) return NWB_OK;
+  S_CUDA(ctx, cudaSetDevice(ctx->device));
+  Scratch A(ctx);
+  size_t o_t = A.add(sizeof(double) * 6 * n), o_s = A.add(sizeof(double) * 40 * n), o_c = A.add(sizeof(int32_t) * n);
+  int rc = A.commit();
+  if (rc != NWB_OK) return rc;
+  cudaStream_t s = ctx->stream;
+  S_CUDA(ctx, cudaMemcpyAsync(A.at<double>(o_t), targets, sizeof(double) * 6 * n, cudaMemcpyHostToDevice, s));
+  S_CUDA(ctx, cudaMemsetAsync(A.at<char>(o_s), 0xff, sizeof(double) * 40 * n, s));           // unused slots read back as NaN
+  S_CUDA(ctx, launch_arm_ik(A.at<double>(o_t), n, A.at<double>(o_s), A.at<int32_t>(o_c), s));
+  S_CUDA(ctx, cudaMemcpyAsync(solutions, A.at<double>(o_s), sizeof(double) * 40 * n, cudaMemcpyDeviceToHost, s));
+  S_CUDA(ctx, cudaMemcpyAsync(counts, A.at<int32_t>(o_c), sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s));
+  S_CUDA(ctx, cudaStreamSynchronize(s));
+  ctx->last_launches = 1;
+  return NWB_OK;
+}
+
+int nwb_goal_arm_ik_batch(nwb_ctx* ctx, const double* q, int64_t n, const double* hand_pose6, uint8_t* ok, double* arm,
+                          double* ergonomics) {
+  if (!ctx) return NWB_E_INVALID;
+  if (n < 0 || !hand_pose6 || (n > 0 && (!q || !ok || !arm || !ergonomics))) return bad(ctx, "nwb_goal_arm_ik_batch: bad argument");
+  if (zero_direction(hand_pose6)) return bad(ctx, "hand direction (0,0,0): the position-only KDL branch (NCK:291-372) is not supported");
+  if (n == 0) return NWB_OK;
+  S_CUDA(ctx, cudaSetDevice(ctx->device));
+  Scratch A(ctx);
+  size_t o_q = A.add(sizeof(double) * NWB_NJ * n), o_ok = A.add(n), o_a = A.add(sizeof(double) * 5 * n), o_e = A.add(sizeof(double) * n);
+  int rc = A.commit();
+  if (rc != NWB_OK) return rc;
+  cudaStream_t s = ctx->stream;
+  PlanConst pc;
+  make_plan_const(ctx, nullptr, ctx->params.planner_step_factor, pc);
+  S_CUDA(ctx, cudaMemcpyAsync(A.at<double>(o_q), q, sizeof(double) * NWB_NJ * n, cudaMemcpyHostToDevice, s));
+  S_CUDA(ctx, launch_goal_arm_ik(pc, hand_pose6, A.at<double>(o_q), n, A.at<uint8_t>(o_ok), A.at<double>(o_a), A.at<double>(o_e), s));
+  S_CUDA(ctx, cudaMemcpyAsync(ok, A.at<uint8_t>(o_ok), n, cudaMemcpyDeviceToHost, s));
+  S_CUDA(ctx, cudaMemcpyAsync(arm, A.at<double>(o_a), sizeof(double) * 5 * n, cudaMemcpyDeviceToHost, s));
+  S_CUDA(ctx, cudaMemcpyAsync(ergonomics, A.at<double>(o_e), sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+  S_CUDA(ctx, cudaStreamSynchronize(s));
+  ctx->last_launches = 1;
+  return NWB_OK;
+}
+
+int nwb_hand_trajectory(int32_t kind, const double* start6, const double* goal6, int32_t num_interp_points, const double* door4,
+                        double* out) {
+  if (!start6 || !goal6 || !out || num_interp_points < 0 || (kind != 0 && kind != 1) || (kind == 1 && !door4)) return NWB_E_INVALID;
+  if (kind == 0) drawer_points(start6, goal6, num_interp_points, out);
+  else door_points(start6, goal6, num_interp_points, door4, out);
+  return NWB_OK;
+}
+
+int nwb_enforce_ma_batch(nwb_ctx* ctx, const double* pts, int32_t n_points, int32_t start_tree, const int32_t* near_hand_index,
+                         const double* q_near, const double* q_new_ds, int64_t n, double* q_out, int32_t* status) {
+  if (!ctx) return NWB_E_INVALID;
+  if (n < 0 || !pts || n_points < 2 || (n > 0 && (!near_hand_index || !q_near || !q_new_ds || !q_out || !status)))
+    return bad(ctx, "nwb_enforce_ma_batch: bad argument");
+  for (int64_t i = 0; i < n; ++i)
+    if (near_hand_index[i] < 0 || near_hand_index[i] >= n_points) return bad(ctx, "nwb_enforce_ma_batch: hand index out of range");
+  if (n == 0) return NWB_OK;
+  S_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t qb = sizeof(double) * NWB_NJ * n, ib = sizeof(int32_t) * n, pb = sizeof(double) * 6 * n_points;
+  Scratch A(ctx);
+  size_t o_p = A.add(pb), o_h = A.add(ib), o_n = A.add(qb), o_d = A.add(qb), o_o = A.add(qb), o_s = A.add(ib);
+  int rc = A.commit();
+  if (rc != NWB_OK) return rc;
+  cudaStream_t s = ctx->stream;
+  PlanConst pc;
+  make_plan_const(ctx, nullptr, ctx->params.planner_step_factor, pc);
+  S_CUDA(ctx, cudaMemcpyAsync(A.at<double>(o_p), pts, pb, cudaMemcpyHostToDevice, s));
+  S_CUDA(ctx, cudaMemcpyAsync(A.at<int32_t>(o_h), near_hand_index, ib, cudaMemcpyHostToDevice, s));
+  S_CUDA(ctx, cudaMemcpyAsync(A.at<double>(o_n), q_near, qb, cudaMemcpyHostToDevice, s));
+  S_CUDA(ctx, cudaMemcpyAsync(A.at<double>(o_d), q_new_ds, qb, cudaMemcpyHostToDevice, s));
+  S_CUDA(ctx, cudaMemcpyAsync(A.at<double>(o_o), q_out, qb, cudaMemcpyHostToDevice, s));   // TRAPPED rows stay as the caller left them
+  S_CUDA(ctx, launch_enforce_ma(pc, A.at<double>(o_p), n_points, start_tree, A.at<int32_t>(o_h), A.at<double>(o_n), A.at<double>(o_d), n,
+                                A.at<double>(o_o), A.at<int32_t>(o_s), s));
+  S_CUDA(ctx, cudaMemcpyAsync(q_out, A.at<double>(o_o), qb, cudaMemcpyDeviceToHost, s));
+  S_CUDA(ctx, cudaMemcpyAsync(status, A.at<int32_t>(o_s), ib, cudaMemcpyDeviceToHost, s));
+  S_CUDA(ctx, cudaStreamSynchronize(s));
+  ctx->last_launches = 1;
+  return NWB_OK;
+}
+
+int nwb_goal_sample_batch(nwb_ctx* ctx, uint64_t seed, uint64_t first, int64_t count, const double* hand_pose6, int32_t max_ik_iter,
+                          uint8_t* stage, double* ergonomics, double* rows) {
+  if (!ctx) return NWB_E_INVALID;
+  if (count < 0 || !hand_pose6 || (count > 0 && !stage)) return bad(ctx, "nwb_goal_sample_batch: bad argument");
+  if (zero_direction(hand_pose6)) return bad(ctx, "hand direction (0,0,0): the position-only KDL branch (NCK:291-372) is not supported");
+  if (count == 0) return NWB_OK;
+  S_CUDA(ctx, cudaSetDevice(ctx->device));
+  Scratch A(ctx);
+  size_t o_rows = A.add(sizeof(double) * NWB_NJ * 16), o_idx = A.add(sizeof(uint64_t) * 16), o_erg = A.add(sizeof(double) * 16),
+         o_n = A.add(8), o_st = A.add(count), o_ea = A.add(sizeof(double) * count), o_ra = A.add(sizeof(double) * NWB_NJ * count);
+  int rc = A.commit();
+  if (rc != NWB_OK) return rc;
+  cudaStream_t s = ctx->stream;
+  PlanConst pc;
+  make_plan_const(ctx, nullptr, ctx->params.planner_step_factor, pc);
+  S_CUDA(ctx, cudaMemsetAsync(A.at<char>(o_n), 0, 8, s));
+  S_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
+  S_CUDA(ctx, launch_goal_sample(pc, ctx->tab_group, static_pairs(ctx), hand_pose6, seed, first, count, max_ik_iter, A.at<double>(o_rows),
+                                 A.at<uint64_t>(o_idx), A.at<double>(o_erg), 16, A.at<unsigned long long>(o_n), A.at<uint8_t>(o_st),
+                                 ergonomics ? A.at<double>(o_ea) : nullptr, rows ? A.at<double>(o_ra) : nullptr, s));
+  S_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
+  S_CUDA(ctx, cudaMemcpyAsync(stage, A.at<uint8_t>(o_st), count, cudaMemcpyDeviceToHost, s));
+  if (ergonomics) S_CUDA(ctx, cudaMemcpyAsync(ergonomics, A.at<double>(o_ea), sizeof(double) * count, cudaMemcpyDeviceToHost, s));
+  if (rows) S_CUDA(ctx, cudaMemcpyAsync(rows, A.at<double>(o_ra), sizeof(double) * NWB_NJ * count, cudaMemcpyDeviceToHost, s));
+  S_CUDA(ctx, cudaStreamSynchronize(s));
+  ctx->last_ms = -1;
+  ctx->last_launches = 1;
+  return NWB_OK;
+}
+
+int nwb_sample_goal_configs(nwb_ctx* ctx, uint64_t seed, const double* hand_pose6, int32_t max_samples, int32_t max_ik_iter,
+                            double* rows6, double* ergonomics6, uint64_t* index6, int32_t* n_found, int64_t* samples_drawn) {
+  if (!ctx) return NWB_E_INVALID;
+  if (!hand_pose6 || !rows6 || !n_found || max_samples < 0) return bad(ctx, "nwb_sample_goal_configs: bad argument");
+  GoalSet g;
+  int rc = sample_goals(ctx, seed, hand_pose6, max_samples, max_ik_iter, g);
+  if (rc != NWB_OK) return rc;
+  *n_found = g.n_found;
+  if (samples_drawn) *samples_drawn = g.drawn;
+  for (int r = 0; r < g.n_found; ++r) {
+    std::memcpy(rows6 + (size_t)r * NWB_NJ, g.rows[r], sizeof(double) * NWB_NJ);
+    if (ergonomics6) ergonomics6[r] = g.erg[r];
+    if (index6) index6[r] = g.index[r];
+  }
+  return NWB_OK;
+}
+
+int nwb_ctx_set_ds_database(nwb_ctx* ctx, const double* rows, int64_t n_rows) {
+  if (!ctx) return NWB_E_INVALID;
+  if (n_rows < 0 || (n_rows > 0 && !rows)) return bad(ctx, "nwb_ctx_set_ds_database: bad argument");
+  ctx->ds_db.assign(rows, rows + (size_t)n_rows * NWB_NJ);
+  return NWB_OK;
+}
+
+int nwb_ctx_load_ds_database(nwb_ctx* ctx, const char* path) {
+  if (!ctx) return NWB_E_INVALID;
+  if (!path) return bad(ctx, "nwb_ctx_load_ds_database: bad argument");
+  int64_t n = 0;
+  int rc = nwb_load_ds_database(path, nullptr, 0, &n);
+  if (rc != NWB_OK) {
+    ctx->err = std::string("nwb_ctx_load_ds_database: cannot open ") + path;
+    return rc;
+  }
+  std::vector<double> rows((size_t)std::max<int64_t>(n, 1) * NWB_NJ);
+  rc = nwb_load_ds_database(path, rows.data(), n, &n);
+  if (rc != NWB_OK) return rc;
+  rows.resize((size_t)n * NWB_NJ);
+  ctx->ds_db.swap(rows);
+  return NWB_OK;
+}
+
+int64_t nwb_ctx_ds_database_size(const nwb_ctx* ctx) { return ctx ? (int64_t)(ctx->ds_db.size() / NWB_NJ) : 0; }
+
+int nwb_compute_goal_config(nwb_ctx* ctx, const nwb_compute_goal_config_request* req, nwb_compute_goal_config_response* resp,
+                            uint64_t seed) {
+  if (!ctx) return NWB_E_INVALID;
+  if (!req || !resp) return bad(ctx, "nwb_compute_goal_config: bad argument");
+  double pose6[6];
+  pose_of(req->right_hand_position, req->right_hand_direction, pose6);
+  GoalSet g;
+  int rc = sample_goals(ctx, seed, pose6, ctx->params.scg_max_samples, ctx->params.scg_max_ik_iterations, g);
+  if (rc != NWB_OK) return rc;
+  resp->num_goal_configs_found = g.n_found;
+  std::memset(resp->wb_goal_config, 0, sizeof resp->wb_goal_config);
+  if (g.n_found) std::memcpy(resp->wb_goal_config, g.rows[0], sizeof(double) * NWB_NJ);
+  return NWB_OK;
+}
+
+int nwb_compute_motion_plan(nwb_ctx* ctx, const nwb_compute_motion_plan_request* req, nwb_compute_motion_plan_response* resp,
+                            uint64_t seed) {
+  if (!ctx) return NWB_E_INVALID;
+  if (!req || !resp || !req->wb_start_config || req->wb_start_config_len < NWB_NJ) return bad(ctx, "nwb_compute_motion_plan: bad argument");
+  const nwb_params& P = ctx->params;
+  double pose6[6];
+  pose_of(req->right_hand_position, req->right_hand_direction, pose6);
+  resp->motion_plan.n_points = 0;
+  resp->num_nodes_generated = 0;
+  resp->search_time = 0.0;
+  resp->success = 0;
+  GoalSet g;
+  const double t0 = now_s();
+  int rc = sample_goals(ctx, seed, pose6, P.scg_max_samples, P.scg_max_ik_iterations, g);
+  if (rc != NWB_OK) return rc;
+  resp->time_goal_config = now_s() - t0;
+  if (g.n_found == 0) return NWB_OK;                                      // NPC:331-334
+  std::memcpy(resp->wb_goal_config, g.rows[0], sizeof(double) * NWB_NJ);
+  double w[NWB_NJ];
+  limb_weights(P.r_arm_weight_approach, P.l_arm_weight_approach, P.legs_weight_approach, w);
+  StageOut st;
+  rc = plan_stage(ctx, req->wb_start_config, g.rows[0], w, seed + 2, nullptr, 0, req->execute_trajectory != 0, st);
+  if (rc != NWB_OK) return rc;
+  resp->num_nodes_generated = st.num_nodes;
+  resp->search_time = st.search_time;
+  resp->success = st.success;
+  if (st.success) put_trajectory(st.path, false, 0.f, resp->motion_plan);
+  return NWB_OK;
+}
+
+int nwb_compute_linear_manipulation_plan(nwb_ctx* ctx, const nwb_compute_linear_manipulation_plan_request* req,
+                                         nwb_manipulation_plan_response* resp, uint64_t seed) {
+  if (!ctx) return NWB_E_INVALID;
+  if (!req || !resp || !req->wb_start_config || req->wb_start_config_len < NWB_NJ)
+    return bad(ctx, "nwb_compute_linear_manipulation_plan: bad argument");
+  double pose6[6];
+  pose_of(req->right_hand_position, req->right_hand_direction, pose6);
+  const double object[2] = {req->relative_angle, req->object_translation_length};
+  return manipulation_plan(ctx, pose6, req->wb_start_config, req->execute_trajectory != 0, false, object, resp, seed);
+}
+
+int nwb_compute_circular_manipulation_plan(nwb_ctx* ctx, const nwb_compute_circular_manipulation_plan_request* req,
+                                           nwb_manipulation_plan_response* resp, uint64_t seed) {
+  if (!ctx) return NWB_E_INVALID;
+  if (!req || !resp || !req->wb_start_config || req->wb_start_config_len < NWB_NJ)
+    return bad(ctx, "nwb_compute_circular_manipulation_plan: bad argument");
+  double pose6[6];
+  pose_of(req->right_hand_position, req->right_hand_direction, pose6);
+  const double object[4] = {req->relative_angle, req->rotation_radius, req->rotation_angle, req->clearance_handle};
+  return manipulation_plan(ctx, pose6, req->wb_start_config, req->execute_trajectory != 0, true, object, resp, seed);
+}
+
+}  // extern "C"
