@@ -103,6 +103,46 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+S3_POS, S3_DIR, S3_PULL = [0.24, -0.065, 0.30], [0.0, -1.0, 0.0], 0.10     # planning_example_simulation.cpp:496-510
+
+
+def s3_start():
+    q = np.zeros(nwb.NJ)
+    q[8], q[13] = -0.5, 0.5                                                 # planning_example_simulation.cpp:232-252
+    return q
+
+
+def scenario3_gpu(reps=101):
+    """Second half of BASELINE.json's metric: scenario-3 plan time p50 (compute_linear_manipulation_plan through
+    the C ABI, 101 seeded repetitions, host wall clock around the call - it returns host-side trajectories)."""
+    import oracle_lib as OL
+    c = nwb.Context()
+    c.set_ds_database(OL.golden_db())
+    c.compute_linear_manipulation_plan(S3_POS, S3_DIR, s3_start(), 0.0, S3_PULL, 1)    # warm-up (allocations)
+    lat, ok = [], 0
+    for i in range(reps):
+        t0 = time.perf_counter()
+        r = c.compute_linear_manipulation_plan(S3_POS, S3_DIR, s3_start(), 0.0, S3_PULL, 20121003 + i)
+        lat.append(time.perf_counter() - t0)
+        ok += bool(r["success_approach"] and r["success_manipulation"])
+    c.close()
+    return {"p50_ms": 1e3 * float(np.median(lat)), "p90_ms": 1e3 * float(np.percentile(lat, 90)), "repetitions": reps,
+            "both_plans_found": ok, "api": "nwb_compute_linear_manipulation_plan", "seeds": "20121003+i"}
+
+
+def scenario3_cpu(reps=3):
+    import oracle_lib as OL
+    orc = OL.Oracle()
+    db = OL.golden_db()
+    lat = []
+    for i in range(reps):
+        t0 = time.perf_counter()
+        orc.compute_manipulation_plan(db, S3_POS + S3_DIR, s3_start(), 20121003 + i, False, [0.0, S3_PULL])
+        lat.append(time.perf_counter() - t0)
+    return {"p50_ms": 1e3 * float(np.median(lat)), "repetitions": reps, "cores": 1, "kind": "port",
+            "sample": f"the first {reps} of the 101 seeds; the planner services are single-threaded (ros::spin)"}
+
+
 def cpu_baseline(q, seconds=12.0, threads=1):
     """Time the CPU oracle on a bounded sample of the same batch (about `seconds` of CPU work)."""
     import oracle_lib as OL
@@ -152,6 +192,8 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if args.gpus == 1 and not args.no_scenario3:
+        line["scenario3"] = scenario3_cpu(3)
     print(json.dumps(line))
 
 
@@ -162,6 +204,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-scenario3", action="store_true", help="skip the scenario-3 plan-time measurement (N = 1 only)")
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="configurations per GPU (default = the headline size)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -330,6 +373,10 @@ def main():
             line["cpu_baseline"] = cb
             mism = int((cpu_valid != e2e_valid[:cn]).sum())
             line["config"]["oracle_mismatches_in_cpu_sample"] = mism      # boundary-band configurations
+        if world == 1 and not args.no_scenario3:
+            line["scenario3"] = scenario3_gpu(101)
+            if not args.no_cpu_baseline:
+                line["scenario3"]["cpu_baseline"] = scenario3_cpu(3)
         print(json.dumps(line))
     pin_q.free()
     pin_v.free()

@@ -50,11 +50,87 @@ def dev_time(fn, stream, reps=10, warm=3):
     return e0.elapsed_time(e1) / reps
 
 
+CROUCH = np.array([0, -0.349066, 0.698132, -0.436332, 0, 1.39626, 0.349066, -1.39626, -0.5, 0, 1.39626, -0.349066, 1.39626,
+                   0.5, 0, 0, 0, -0.436332, 0.698132, -0.349066, 0])     # planning_example_simulation.cpp:199-219
+
+
+def bench_services(args):
+    """V0: scenario 3 (compute_linear_manipulation_plan, SIM:496-510), 101 seeded repetitions -> p50.
+    V4: 256 grasp-pose compute_motion_plan requests (SIM:778-788 window) in one batched call."""
+    orc = OL.Oracle()
+    db = OL.golden_db()
+    ctx = nwb.Context()
+    ctx.set_ds_database(db)
+    start = np.zeros(21)
+    start[8], start[13] = -0.5, 0.5                                       # SIM:232-252
+    P, D = [0.24, -0.065, 0.30], [0.0, -1.0, 0.0]
+    ctx.compute_linear_manipulation_plan(P, D, start, 0.0, 0.10, 1)       # warm-up: allocations
+    lat, parts, ok = [], [], 0
+    reps = 21 if args.quick else 101
+    for i in range(reps):
+        t0 = time.perf_counter()
+        r = ctx.compute_linear_manipulation_plan(P, D, start, 0.0, 0.10, 20121003 + i)
+        lat.append(time.perf_counter() - t0)
+        ok += r["success_approach"] and r["success_manipulation"]
+        parts.append((r["time_goal_config_approach"], r["search_time_approach"], r["search_time_manipulate"]))
+    ncpu = 3
+    cpu, cpu_ok = [], 0
+    for i in range(ncpu):
+        t0 = time.perf_counter()
+        o = orc.compute_manipulation_plan(db, P + D, start, 20121003 + i, False, [0.0, 0.10])
+        cpu.append(time.perf_counter() - t0)
+        cpu_ok += o["success_approach"] and o["success_manipulation"]
+    parts = 1e3 * np.median(np.array(parts), 0)
+    emit(args.out, op="scenario3_linear_manipulation_plan", repetitions=reps, success=int(ok), p50_ms=1e3 * float(np.median(lat)),
+         p90_ms=1e3 * float(np.percentile(lat, 90)), max_ms=1e3 * float(np.max(lat)),
+         median_parts_ms=dict(goal_sampling_both=float(parts[0]), search_approach=float(parts[1]), search_manipulate=float(parts[2])),
+         cpu_oracle_s=[float(x) for x in cpu], cpu_oracle_p50_ms=1e3 * float(np.median(cpu)), cpu_repetitions=ncpu,
+         cpu_success=int(cpu_ok), cpu_threads=1,
+         note="request SIM:496-510 (hand (0.24,-0.065,0.30), dir (0,-1,0), pull 0.10 m), start SIM:232-252, shipped database, "
+              "seeds 20121003+i; both goal samplings share one launch; the p90 tail = approach searches that use most of the "
+              "8000 iterations (7 launches each)")
+    # ---- V4 ----
+    n = 256
+    pos = np.array([[-0.08 + i * 0.4 / 15, -0.30 + j * 0.4 / 15, 0.2] for i in range(16) for j in range(16)])
+    dirs = np.tile([0.0, -1.0, 0.0], (n, 1))
+    seeds = (20121100 + np.arange(n)).astype(np.uint64)
+    starts = np.tile(CROUCH, (n, 1))
+    ctx.compute_motion_plan_batch(pos[:8], dirs[:8], starts[:8], seeds[:8])
+    t0 = time.perf_counter()
+    res = ctx.compute_motion_plan_batch(pos, dirs, starts, seeds)
+    dt = time.perf_counter() - t0
+    solved = [k for k in range(n) if res[k]["success"]]
+    t0 = time.perf_counter()
+    one_by_one = [ctx.compute_motion_plan(pos[k], dirs[k], CROUCH, int(seeds[k])) for k in range(n)]
+    dt_seq = time.perf_counter() - t0
+    same = sum(a["success"] == b["success"] and a["trajectory"].shape == b["trajectory"].shape for a, b in zip(res, one_by_one))
+    # CPU: a bounded sample of the same requests (every 16th), extrapolated
+    sample = list(range(0, n, 17))            # a diagonal of the grid
+    t0 = time.perf_counter()
+    cpu_solved = 0
+    for k in sample:
+        o = orc.compute_motion_plan(db, list(pos[k]) + list(dirs[k]), CROUCH, int(seeds[k]))
+        cpu_solved += o["success"]
+    cpu_dt = (time.perf_counter() - t0) / len(sample) * n
+    emit(args.out, op="grasp_pose_queries_256", queries=n, solved=len(solved), wall_s_batched=dt, wall_s_one_by_one=dt_seq,
+         batch_equals_single=int(same), time_goal_config_s=res[0]["time_goal_config"], search_time_s=max(r["search_time"] for r in res),
+         cpu_oracle_1thread_s_extrapolated=cpu_dt, cpu_sample=len(sample), cpu_sample_solved=int(cpu_solved),
+         note="16x16 grid of the evaluation window SIM:778-788 (z = 0.2, dir (0,-1,0)), crouched start SIM:199-219, "
+              "compute_motion_plan semantics; seeds 20121100+k")
+    ctx.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default="")
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--only", default="", help="comma list: ops,services (default: both)")
     args = ap.parse_args()
+    only = set(filter(None, args.only.split(",")))
+    if not only or "services" in only:
+        bench_services(args)
+    if only and "ops" not in only:
+        return
     peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
     hbm = peaks.get("hbm_gbs", 6650.0)
     rf = json.loads((ROOT / "profiles" / "roofline.json").read_text())

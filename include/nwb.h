@@ -415,6 +415,14 @@ typedef struct nwb_compute_motion_plan_response {  /* Compute_Motion_Plan.srv:14
 NWB_API int nwb_compute_motion_plan(nwb_ctx* ctx, const nwb_compute_motion_plan_request* req,
                                     nwb_compute_motion_plan_response* resp, uint64_t seed);
 
+/* n independent compute_motion_plan requests (the grasp-pose evaluation loop of
+ * planning_example_simulation.cpp:770-900 calls the service once per pose): all goal samplings in one
+ * launch, all RRT-Connect queries in lock step, all shortcut rounds in shared edge-check batches.
+ * Request k uses seeds[k] exactly as nwb_compute_motion_plan would, so resps[k] equals the single call's
+ * response except for the two wall-clock fields (batch times). */
+NWB_API int nwb_compute_motion_plan_batch(nwb_ctx* ctx, const nwb_compute_motion_plan_request* reqs,
+                                          nwb_compute_motion_plan_response* resps, int64_t n, const uint64_t* seeds);
+
 typedef struct nwb_manipulation_plan_response {    /* Compute_Linear_Manipulation_Plan.srv:20-46 == Circular:27-53 */
   nwb_trajectory motion_plan_approach;
   nwb_trajectory motion_plan_manipulation;

@@ -214,6 +214,7 @@ def _declare(lib):
         "nwb_ctx_ds_database_size": (i64, [vp]),
         "nwb_compute_goal_config": (C.c_int, [vp, C.POINTER(GoalConfigRequest), C.POINTER(GoalConfigResponse), C.c_uint64]),
         "nwb_compute_motion_plan": (C.c_int, [vp, C.POINTER(MotionPlanRequest), C.POINTER(MotionPlanResponse), C.c_uint64]),
+        "nwb_compute_motion_plan_batch": (C.c_int, [vp, C.POINTER(MotionPlanRequest), C.POINTER(MotionPlanResponse), i64, vp]),
         "nwb_compute_linear_manipulation_plan": (C.c_int, [vp, C.POINTER(LinearManipulationRequest),
                                                            C.POINTER(ManipulationPlanResponse), C.c_uint64]),
         "nwb_compute_circular_manipulation_plan": (C.c_int, [vp, C.POINTER(CircularManipulationRequest),

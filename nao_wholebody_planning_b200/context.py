@@ -323,6 +323,31 @@ class Context:
                     num_nodes_generated=resp.num_nodes_generated, search_time=resp.search_time, trajectory=pos[:n].copy(),
                     time_from_start=tfs[:n].copy())
 
+    def compute_motion_plan_batch(self, positions, directions, wb_start_configs, seeds, execute_trajectory=False, cap=4096):
+        """n compute_motion_plan requests in one call -> list of result dicts (as compute_motion_plan)."""
+        positions = np.ascontiguousarray(positions, dtype=np.float64).reshape(-1, 3)
+        directions = np.ascontiguousarray(directions, dtype=np.float64).reshape(-1, 3)
+        starts = np.ascontiguousarray(wb_start_configs, dtype=np.float64).reshape(-1, NJ)
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint64)
+        n = len(positions)
+        reqs = (_abi.MotionPlanRequest * n)()
+        resps = (_abi.MotionPlanResponse * n)()
+        pos = np.full((n, cap, NJ), np.nan)
+        tfs = np.full((n, cap), np.nan)
+        pd = C.POINTER(C.c_double)
+        for k in range(n):
+            reqs[k] = _abi.MotionPlanRequest(_abi.Point3(*positions[k]), _abi.Point3(*directions[k]),
+                                             starts[k].ctypes.data_as(pd), NJ, int(execute_trajectory))
+            resps[k].motion_plan = _abi.Trajectory(cap, 0, pos[k].ctypes.data_as(pd), tfs[k].ctypes.data_as(pd))
+        self._check(self.lib.nwb_compute_motion_plan_batch(self.h, reqs, resps, n, _p(seeds)), "nwb_compute_motion_plan_batch")
+        out = []
+        for k in range(n):
+            m = min(resps[k].motion_plan.n_points, cap)
+            out.append(dict(success=bool(resps[k].success), wb_goal_config=np.array(resps[k].wb_goal_config),
+                            time_goal_config=resps[k].time_goal_config, num_nodes_generated=resps[k].num_nodes_generated,
+                            search_time=resps[k].search_time, trajectory=pos[k, :m].copy(), time_from_start=tfs[k, :m].copy()))
+        return out
+
     def _manipulation_result(self, resp, pa, ta, pm, tm, cap):
         na, nm = min(resp.motion_plan_approach.n_points, cap), min(resp.motion_plan_manipulation.n_points, cap)
         return dict(success_approach=bool(resp.success_approach), success_manipulation=bool(resp.success_manipulation),

@@ -76,17 +76,24 @@ struct ArmLocalStore {
 
 // Goal branch of sample_stable_configs: sample i draws its 21 joints exactly as the database branch
 // does (same stream, same slots), then LHipYawPitch = 0 and the left arm is pinned (SCG:291-300).
-// Accepted rows are compacted with their sample index and ergonomics index; the caller keeps the six
-// lowest indices (the serial loop stops at `goal_samples > 5`, SCG:429).
+// The launch covers nq independent requests (hand pose + seed each) x `count` sample indices; accepted
+// rows are compacted per request with their sample index and ergonomics index; the caller keeps the
+// six lowest indices (the serial loop stops at `goal_samples > 5`, SCG:429).
 template <bool STATIC>
 __global__ void __launch_bounds__(64)
-goal_sample_kernel(const __grid_constant__ PlanConst pc, const __grid_constant__ ValidityTables tab, const __grid_constant__ Pose6 pose,
-                   uint64_t seed, uint64_t first, int64_t count, int max_ik_iter, double* __restrict__ rows, uint64_t* __restrict__ row_index,
-                   double* __restrict__ row_erg, int64_t cap, unsigned long long* __restrict__ n_out, uint8_t* __restrict__ stage_out,
-                   double* __restrict__ erg_all, double* __restrict__ rows_all) {
+goal_sample_kernel(const __grid_constant__ PlanConst pc, const __grid_constant__ ValidityTables tab, const double* __restrict__ poses,
+                   const uint64_t* __restrict__ seeds, int nq, uint64_t first, int64_t count, int max_ik_iter,
+                   double* __restrict__ rows, uint64_t* __restrict__ row_index, double* __restrict__ row_erg, int64_t cap,
+                   unsigned long long* __restrict__ n_out, uint8_t* __restrict__ stage_out, double* __restrict__ erg_all,
+                   double* __restrict__ rows_all) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= count) return;
-  const uint64_t i = first + (uint64_t)t;
+  if (t >= count * nq) return;
+  const int qi = (int)(t / count);
+  const uint64_t i = first + (uint64_t)(t - (int64_t)qi * count);
+  const uint64_t seed = seeds[qi];
+  double pose[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) pose[j] = poses[qi * 6 + j];
   double q[NWB_NJ];
 #pragma unroll 1
   for (int blk = 0; blk < (NWB_NJ + 3) / 4; ++blk) {
@@ -103,12 +110,16 @@ goal_sample_kernel(const __grid_constant__ PlanConst pc, const __grid_constant__
   for (int m = 0; m < 5; ++m) rl[m] = -q[m];
   DFrame hip, target;
   right_leg_fk(rl, hip);
-  desired_left_leg_pose(hip, target);
   uint8_t stage = 0;
-  for (int m = 0; m < 5; ++m) ll[m] = -rl[m];            // NCK:150 seed; further attempts repeat the same arithmetic (quirk C5)
-  bool solved = max_ik_iter > 0 && left_leg_ik_nr(target, ll, pc.ik_maxiter, pc.ik_eps, pc.pinv_eps, nullptr) &&
-                limits_ok(ll, pc.jmin + 16, pc.jmax + 16, 5);
-  if (solved) solved = goal_right_arm_ik(hip, pose.v, pc.jmin + 10, pc.jmax + 10, arm, &e);
+  // The reference solves the left leg first and the right arm second (SCG:318-347); a sample survives
+  // only if BOTH succeed and neither consumes random numbers, so the order is free: the closed-form arm
+  // solve (cheap, rejects most samples) runs first and only its survivors pay for the NR iteration.
+  bool solved = max_ik_iter > 0 && goal_right_arm_ik(hip, pose, pc.jmin + 10, pc.jmax + 10, arm, &e);
+  if (solved) {
+    desired_left_leg_pose(hip, target);
+    for (int m = 0; m < 5; ++m) ll[m] = -rl[m];          // NCK:150 seed; further attempts repeat the same arithmetic (quirk C5)
+    solved = left_leg_ik_nr(target, ll, pc.ik_maxiter, pc.ik_eps, pc.pinv_eps, nullptr) && limits_ok(ll, pc.jmin + 16, pc.jmax + 16, 5);
+  }
   if (solved) {
     for (int m = 0; m < 5; ++m) {
       q[16 + m] = ll[m];
@@ -122,13 +133,16 @@ goal_sample_kernel(const __grid_constant__ PlanConst pc, const __grid_constant__
     const bool feasible = !r.hit && r.stable;
     stage = feasible ? 2 : 1;
     if (feasible) {
-      unsigned long long slot = atomicAdd(n_out, 1ull);
+      unsigned long long slot = atomicAdd(n_out + qi, 1ull);
       if ((int64_t)slot < cap) {
-        for (int j = 0; j < NWB_NJ; ++j) rows[slot * NWB_NJ + j] = q[j];
-        row_index[slot] = i;
-        row_erg[slot] = e;
+        const size_t o = (size_t)qi * cap + slot;
+        for (int j = 0; j < NWB_NJ; ++j) rows[o * NWB_NJ + j] = q[j];
+        row_index[o] = i;
+        row_erg[o] = e;
       }
     }
+  } else {
+    e = 0.0;
   }
   if (stage_out) stage_out[t] = stage;
   if (erg_all) erg_all[t] = e;
@@ -183,20 +197,18 @@ cudaError_t launch_enforce_ma(const PlanConst& pc, const double* pts_dev, int n_
                                                                q_out, status);
   return cudaGetLastError();
 }
-cudaError_t launch_goal_sample(const PlanConst& pc, const ValidityTables& tab, bool static_pairs, const double* pose6, uint64_t seed,
-                               uint64_t first, int64_t count, int max_ik_iter, double* rows, uint64_t* row_index, double* row_erg,
-                               int64_t cap, unsigned long long* n_out, uint8_t* stage_out, double* erg_all, double* rows_all,
-                               cudaStream_t s) {
-  if (count <= 0) return cudaSuccess;
-  Pose6 p;
-  for (int j = 0; j < 6; ++j) p.v[j] = pose6[j];
-  unsigned blocks = (unsigned)((count + 63) / 64);
+cudaError_t launch_goal_sample(const PlanConst& pc, const ValidityTables& tab, bool static_pairs, const double* poses_dev,
+                               const uint64_t* seeds_dev, int nq, uint64_t first, int64_t count, int max_ik_iter, double* rows,
+                               uint64_t* row_index, double* row_erg, int64_t cap, unsigned long long* n_out, uint8_t* stage_out,
+                               double* erg_all, double* rows_all, cudaStream_t s) {
+  if (count <= 0 || nq <= 0) return cudaSuccess;
+  unsigned blocks = (unsigned)((count * nq + 63) / 64);
   if (static_pairs)
-    goal_sample_kernel<true><<<blocks, 64, 0, s>>>(pc, tab, p, seed, first, count, max_ik_iter, rows, row_index, row_erg, cap, n_out,
-                                                   stage_out, erg_all, rows_all);
+    goal_sample_kernel<true><<<blocks, 64, 0, s>>>(pc, tab, poses_dev, seeds_dev, nq, first, count, max_ik_iter, rows, row_index,
+                                                   row_erg, cap, n_out, stage_out, erg_all, rows_all);
   else
-    goal_sample_kernel<false><<<blocks, 64, 0, s>>>(pc, tab, p, seed, first, count, max_ik_iter, rows, row_index, row_erg, cap, n_out,
-                                                    stage_out, erg_all, rows_all);
+    goal_sample_kernel<false><<<blocks, 64, 0, s>>>(pc, tab, poses_dev, seeds_dev, nq, first, count, max_ik_iter, rows, row_index,
+                                                    row_erg, cap, n_out, stage_out, erg_all, rows_all);
   return cudaGetLastError();
 }
 cudaError_t launch_ma_project(const PlanConst& pc, const double* ma_pts, int n_pts, ForestView F, RrtState S, const int32_t* idx_a,

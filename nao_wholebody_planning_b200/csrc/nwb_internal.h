@@ -154,10 +154,12 @@ cudaError_t launch_goal_arm_ik(const PlanConst& pc, const double* pose6, const d
                                double* erg, cudaStream_t s);
 cudaError_t launch_enforce_ma(const PlanConst& pc, const double* pts_dev, int n_pts, int start_tree, const int32_t* near_hand,
                               const double* q_near, const double* q_ds, int64_t n, double* q_out, int32_t* status, cudaStream_t s);
-cudaError_t launch_goal_sample(const PlanConst& pc, const ValidityTables& tab, bool static_pairs, const double* pose6, uint64_t seed,
-                               uint64_t first, int64_t count, int max_ik_iter, double* rows, uint64_t* row_index, double* row_erg,
-                               int64_t cap, unsigned long long* n_out, uint8_t* stage_out, double* erg_all, double* rows_all,
-                               cudaStream_t s);
+// nq requests (poses_dev [nq][6], seeds_dev [nq]) x count sample indices; compacted outputs are per request:
+// rows [nq][cap][21], row_index / row_erg [nq][cap], n_out [nq]; the per-sample outputs [nq * count] are optional
+cudaError_t launch_goal_sample(const PlanConst& pc, const ValidityTables& tab, bool static_pairs, const double* poses_dev,
+                               const uint64_t* seeds_dev, int nq, uint64_t first, int64_t count, int max_ik_iter, double* rows,
+                               uint64_t* row_index, double* row_erg, int64_t cap, unsigned long long* n_out, uint8_t* stage_out,
+                               double* erg_all, double* rows_all, cudaStream_t s);
 cudaError_t launch_ma_project(const PlanConst& pc, const double* ma_pts, int n_pts, ForestView F, RrtState S, const int32_t* idx_a,
                               const double* q_near, double* q_new, int32_t* status, int nq, cudaStream_t s);
 

@@ -140,8 +140,17 @@ __device__ __forceinline__ void frame_diff(const DFrame& a, const DFrame& b, dou
 
 // qdot = pinv(J) * twist with singular values below eps zeroed (ChainIkSolverVel_pinv).
 // J is 6x5 (column i = (a_i x (p_tip - o_i), a_i)).  One-sided Jacobi SVD, W = J V = U S.
-static __device__ __noinline__ void pinv_solve(double (*W)[5], const double* tw, double eps, double* qdot) {
-  double V[5][5];
+static __device__ __noinline__ void pinv_solve(const double (*W_in)[5], const double* tw_in, double eps, double* qdot) {
+  // W_in / tw_in arrive through memory (the function is not inlined): pull them into registers once -
+  // every index below is a compile-time constant, so the ~70 column rotations of a solve run out of
+  // the register file instead of local memory
+  double W[6][5], tw[6], V[5][5];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    tw[r] = tw_in[r];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) W[r][c] = W_in[r][c];
+  }
 #pragma unroll
   for (int i = 0; i < 5; ++i)
 #pragma unroll

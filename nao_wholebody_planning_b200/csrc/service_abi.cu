@@ -97,40 +97,10 @@ struct GoalSet {
 
 constexpr int kGoalsWanted = 6;   // SCG:429: the loop leaves once goal_samples > 5
 
-// sample_stable_configs(goal branch) + sort_goal_configs_by_ergonomy.  All max_samples candidates are
-// evaluated in ONE launch (the serial reference stops after the sixth accepted sample; the samples
-// behind it are independent, so evaluating them costs nothing but idle lanes) and the six accepted
-// rows with the lowest sample index are kept.
-int sample_goals(nwb_ctx* ctx, uint64_t seed, const double* pose6, int max_samples, int max_ik_iter, GoalSet& g) {
-  g = GoalSet();
-  if (zero_direction(pose6)) return bad(ctx, "hand direction (0,0,0): the position-only KDL branch (NCK:291-372) is not supported");
-  if (max_samples <= 0) return NWB_OK;
-  S_CUDA(ctx, cudaSetDevice(ctx->device));
-  cudaStream_t s = ctx->stream;
-  const int64_t cap = max_samples;
-  Scratch A(ctx);
-  size_t o_rows = A.add(sizeof(double) * NWB_NJ * cap), o_idx = A.add(sizeof(uint64_t) * cap), o_erg = A.add(sizeof(double) * cap),
-         o_n = A.add(8);
-  int rc = A.commit();
-  if (rc != NWB_OK) return rc;
-  PlanConst pc;
-  make_plan_const(ctx, nullptr, ctx->params.planner_step_factor, pc);
-  S_CUDA(ctx, cudaMemsetAsync(A.at<char>(o_n), 0, 8, s));
-  S_CUDA(ctx, launch_goal_sample(pc, ctx->tab_group, static_pairs(ctx), pose6, seed, 0, max_samples, max_ik_iter, A.at<double>(o_rows),
-                                 A.at<uint64_t>(o_idx), A.at<double>(o_erg), cap, A.at<unsigned long long>(o_n), nullptr, nullptr,
-                                 nullptr, s));
-  unsigned long long got = 0;
-  S_CUDA(ctx, cudaMemcpyAsync(&got, A.at<char>(o_n), 8, cudaMemcpyDeviceToHost, s));
-  S_CUDA(ctx, cudaStreamSynchronize(s));
-  ctx->last_launches = 1;
-  std::vector<double> rows(got * NWB_NJ), erg(got);
-  std::vector<uint64_t> idx(got);
-  if (got) {
-    S_CUDA(ctx, cudaMemcpyAsync(rows.data(), A.at<double>(o_rows), sizeof(double) * NWB_NJ * got, cudaMemcpyDeviceToHost, s));
-    S_CUDA(ctx, cudaMemcpyAsync(idx.data(), A.at<uint64_t>(o_idx), sizeof(uint64_t) * got, cudaMemcpyDeviceToHost, s));
-    S_CUDA(ctx, cudaMemcpyAsync(erg.data(), A.at<double>(o_erg), sizeof(double) * got, cudaMemcpyDeviceToHost, s));
-    S_CUDA(ctx, cudaStreamSynchronize(s));
-  }
+// first six accepted rows (sample order) -> text round trip -> sort_goal_configs_by_ergonomy
+void finish_goal_set(const std::vector<double>& rows, const std::vector<double>& erg, const std::vector<uint64_t>& idx, int max_samples,
+                     GoalSet& g) {
+  const size_t got = idx.size();
   std::vector<size_t> order(got);
   std::iota(order.begin(), order.end(), (size_t)0);
   std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return idx[a] < idx[b]; });
@@ -161,7 +131,72 @@ int sample_goals(nwb_ctx* ctx, uint64_t seed, const double* pose6, int max_sampl
     e2[imax] = 0.0;
   }
   g.n_found = n;
+}
+
+// sample_stable_configs(goal branch) + sort_goal_configs_by_ergonomy for nq independent requests.
+// All nq x max_samples candidates are evaluated in ONE launch (the serial reference stops after the
+// sixth accepted sample; the samples behind it are independent, so evaluating them costs idle lanes,
+// not time) and per request the six accepted rows with the lowest sample index are kept.
+int sample_goals_batch(nwb_ctx* ctx, int nq, const uint64_t* seeds, const double* poses, int max_samples, int max_ik_iter,
+                       GoalSet* out) {
+  for (int k = 0; k < nq; ++k) {
+    out[k] = GoalSet();
+    if (zero_direction(poses + 6 * k)) return bad(ctx, "hand direction (0,0,0): the position-only KDL branch (NCK:291-372) is not supported");
+  }
+  if (max_samples <= 0 || nq <= 0) return NWB_OK;
+  S_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  // a request accepts ~0.3 % of its samples: 512 slots per request are plenty for a batch; a request that
+  // outgrows them is redone on its own with room for every sample
+  const int64_t cap = nq == 1 ? max_samples : std::min<int64_t>(max_samples, 512);
+  Scratch A(ctx);
+  size_t o_rows = A.add(sizeof(double) * NWB_NJ * cap * nq), o_idx = A.add(sizeof(uint64_t) * cap * nq),
+         o_erg = A.add(sizeof(double) * cap * nq), o_n = A.add(8 * (size_t)nq), o_pose = A.add(sizeof(double) * 6 * nq),
+         o_seed = A.add(sizeof(uint64_t) * nq);
+  int rc = A.commit();
+  if (rc != NWB_OK) return rc;
+  PlanConst pc;
+  make_plan_const(ctx, nullptr, ctx->params.planner_step_factor, pc);
+  S_CUDA(ctx, cudaMemsetAsync(A.at<char>(o_n), 0, 8 * (size_t)nq, s));
+  S_CUDA(ctx, cudaMemcpyAsync(A.at<double>(o_pose), poses, sizeof(double) * 6 * nq, cudaMemcpyHostToDevice, s));
+  S_CUDA(ctx, cudaMemcpyAsync(A.at<uint64_t>(o_seed), seeds, sizeof(uint64_t) * nq, cudaMemcpyHostToDevice, s));
+  S_CUDA(ctx, launch_goal_sample(pc, ctx->tab_group, static_pairs(ctx), A.at<double>(o_pose), A.at<uint64_t>(o_seed), nq, 0, max_samples,
+                                 max_ik_iter, A.at<double>(o_rows), A.at<uint64_t>(o_idx), A.at<double>(o_erg), cap,
+                                 A.at<unsigned long long>(o_n), nullptr, nullptr, nullptr, s));
+  std::vector<unsigned long long> got(nq);
+  S_CUDA(ctx, cudaMemcpyAsync(got.data(), A.at<char>(o_n), 8 * (size_t)nq, cudaMemcpyDeviceToHost, s));
+  S_CUDA(ctx, cudaStreamSynchronize(s));
+  ctx->last_launches = 1;
+  // one request: fetch only what was accepted; a batch: one copy of the whole (sparsely filled) slot array
+  const size_t fetch = nq == 1 ? (size_t)std::min<int64_t>((int64_t)got[0], cap) : (size_t)cap * nq;
+  std::vector<double> rows((size_t)cap * nq * NWB_NJ), erg((size_t)cap * nq);
+  std::vector<uint64_t> idx((size_t)cap * nq);
+  if (fetch) {
+    S_CUDA(ctx, cudaMemcpyAsync(rows.data(), A.at<double>(o_rows), sizeof(double) * NWB_NJ * fetch, cudaMemcpyDeviceToHost, s));
+    S_CUDA(ctx, cudaMemcpyAsync(idx.data(), A.at<uint64_t>(o_idx), sizeof(uint64_t) * fetch, cudaMemcpyDeviceToHost, s));
+    S_CUDA(ctx, cudaMemcpyAsync(erg.data(), A.at<double>(o_erg), sizeof(double) * fetch, cudaMemcpyDeviceToHost, s));
+    S_CUDA(ctx, cudaStreamSynchronize(s));
+  }
+  std::vector<int> redo;
+  for (int k = 0; k < nq; ++k) {
+    if ((int64_t)got[k] > cap) {
+      redo.push_back(k);
+      continue;
+    }
+    const size_t b = (size_t)k * cap, n = got[k];
+    finish_goal_set(std::vector<double>(rows.begin() + b * NWB_NJ, rows.begin() + (b + n) * NWB_NJ),
+                    std::vector<double>(erg.begin() + b, erg.begin() + b + n), std::vector<uint64_t>(idx.begin() + b, idx.begin() + b + n),
+                    max_samples, out[k]);
+  }
+  for (int k : redo) {
+    rc = sample_goals_batch(ctx, 1, seeds + k, poses + 6 * k, max_samples, max_ik_iter, out + k);
+    if (rc != NWB_OK) return rc;
+  }
   return NWB_OK;
+}
+
+int sample_goals(nwb_ctx* ctx, uint64_t seed, const double* pose6, int max_samples, int max_ik_iter, GoalSet& g) {
+  return sample_goals_batch(ctx, 1, &seed, pose6, max_samples, max_ik_iter, &g);
 }
 
 void limb_weights(double r_arm, double l_arm, double legs, double* w) {   // NPC:280-306
@@ -236,6 +271,68 @@ int plan_stage(nwb_ctx* ctx, const double* start, const double* goal, const doub
   return NWB_OK;
 }
 
+// path_shortcutter (RP:1830-1951) for several raw paths at once: every round gathers the candidate edges
+// of ALL unfinished paths into one batched edge check, then each path takes its first valid candidate in
+// the reference's scan order.  sel[k] = selected way-point indices; ok[k] = false if its 500-round budget ran out.
+int shortcut_paths_batch(nwb_ctx* ctx, const std::vector<std::vector<double>>& raw, std::vector<std::vector<int>>& sel,
+                         std::vector<uint8_t>& ok) {
+  const int n = (int)raw.size(), K = ctx->params.shortcut_waypoints;
+  sel.assign(n, {});
+  ok.assign(n, 1);
+  std::vector<int> cur(n, 0), budget(n, ctx->params.shortcut_max_rounds), W(n);
+  std::vector<uint8_t> reached(n, 0);
+  for (int k = 0; k < n; ++k) {
+    W[k] = (int)(raw[k].size() / NWB_NJ);
+    if (W[k] < 1) { reached[k] = 1; ok[k] = 0; continue; }
+    sel[k].push_back(0);
+  }
+  std::vector<double> qa, qb;
+  std::vector<uint8_t> valid;
+  std::vector<int> cand, first(n + 1);
+  for (;;) {
+    qa.clear(); qb.clear(); cand.clear();
+    bool any = false;
+    for (int k = 0; k < n; ++k) {
+      first[k] = (int)cand.size();
+      if (reached[k] || budget[k] <= 0) continue;
+      any = true;
+      auto push = [&](int i) {
+        cand.push_back(i);
+        qa.insert(qa.end(), raw[k].begin() + (size_t)cur[k] * NWB_NJ, raw[k].begin() + (size_t)(cur[k] + 1) * NWB_NJ);
+        qb.insert(qb.end(), raw[k].begin() + (size_t)i * NWB_NJ, raw[k].begin() + (size_t)(i + 1) * NWB_NJ);
+      };
+      push(W[k] - 1);                                       // goal first (RP:1869-1876)
+      for (int i = W[k] - 2; i >= 0; --i) {                 // then i = W-2 .. 0 (RP:1884-1916)
+        if (i == cur[k]) break;
+        push(i);
+      }
+    }
+    first[n] = (int)cand.size();
+    if (!any) break;
+    valid.resize(cand.size());
+    int rc = nwb_is_path_valid_batch(ctx, qa.data(), qb.data(), (int64_t)cand.size(), K, valid.data(), nullptr);
+    if (rc != NWB_OK) return rc;
+    for (int k = 0; k < n; ++k) {
+      if (reached[k] || budget[k] <= 0) continue;
+      int pick = -1;
+      for (int c = first[k]; c < first[k + 1]; ++c)
+        if (valid[c]) { pick = c; break; }
+      if (pick == first[k]) {
+        sel[k].push_back(W[k] - 1);
+        reached[k] = 1;
+      } else if (pick >= 0) {
+        cur[k] = cand[pick];
+        sel[k].push_back(cur[k]);
+      } else {                                              // stuck: advance one raw way-point (RP:1891-1897)
+        cur[k] = cur[k] + 1;
+        sel[k].push_back(cur[k]);
+      }
+      if (--budget[k] == 0) ok[k] = 0;                      // RP:1919-1923 (checked after the loop, reached or not)
+    }
+  }
+  return NWB_OK;
+}
+
 void pose_of(const nwb_point3& p, const nwb_point3& d, double* pose6) {
   pose6[0] = p.x; pose6[1] = p.y; pose6[2] = p.z;
   pose6[3] = d.x; pose6[4] = d.y; pose6[5] = d.z;
@@ -282,25 +379,8 @@ int manipulation_plan(nwb_ctx* ctx, const double* pose6, const double* start, bo
   resp->num_nodes_generated_approach = resp->num_nodes_generated_manipulate = 0;
   resp->search_time_approach = resp->search_time_manipulate = 0.0;
   resp->success_approach = resp->success_manipulation = 0;
-  // ---- approach (NPC:430-494 / 690-753)
-  GoalSet ga;
-  double t0 = now_s();
-  int rc = sample_goals(ctx, seed, pose6, P.scg_max_samples, P.scg_max_ik_iterations, ga);
-  if (rc != NWB_OK) return rc;
-  resp->time_goal_config_approach = now_s() - t0;
-  if (ga.n_found == 0) return NWB_OK;
-  std::memcpy(resp->wb_goal_config_approach, ga.rows[0], sizeof(double) * NWB_NJ);
-  double w[NWB_NJ];
-  limb_weights(P.r_arm_weight_approach, P.l_arm_weight_approach, P.legs_weight_approach, w);
-  StageOut sa;
-  rc = plan_stage(ctx, start, ga.rows[0], w, seed + 2, nullptr, 0, execute, sa);
-  if (rc != NWB_OK) return rc;
-  resp->num_nodes_generated_approach = sa.num_nodes;
-  resp->search_time_approach = sa.search_time;
-  resp->success_approach = sa.success;
-  if (!sa.success) return NWB_OK;
-  put_trajectory(sa.path, false, 0.f, resp->motion_plan_approach);
-  // ---- manipulation (NPC:498-585 / 757-866)
+  // Both hand poses are known from the request alone, so the two goal samplings (NPC:430-436 and 509-516 /
+  // 690-696 and 793-800) share ONE launch; the second set is only used if the approach plan succeeds.
   double pm[6];
   const int NI = P.object_interp_points;
   std::vector<double> traj((size_t)(NI + 2) * 6);
@@ -326,11 +406,30 @@ int manipulation_plan(nwb_ctx* ctx, const double* pose6, const double* start, bo
     pm[2] = z_door;
   }
   for (int i = 3; i < 6; ++i) pm[i] = pose6[i];
-  GoalSet gm;
-  t0 = now_s();
-  rc = sample_goals(ctx, seed + 1, pm, P.scg_max_samples, P.scg_max_ik_iterations, gm);
+  GoalSet goals[2];
+  double poses[12];
+  std::memcpy(poses, pose6, sizeof(double) * 6);
+  std::memcpy(poses + 6, pm, sizeof(double) * 6);
+  const uint64_t gseeds[2] = {seed, seed + 1};
+  double t0 = now_s();
+  int rc = sample_goals_batch(ctx, 2, gseeds, poses, P.scg_max_samples, P.scg_max_ik_iterations, goals);
   if (rc != NWB_OK) return rc;
-  resp->time_goal_config_manipulate = now_s() - t0;
+  const GoalSet &ga = goals[0], &gm = goals[1];
+  resp->time_goal_config_approach = now_s() - t0;        // both sets; time_goal_config_manipulate stays 0
+  // ---- approach (NPC:430-494 / 690-753)
+  if (ga.n_found == 0) return NWB_OK;
+  std::memcpy(resp->wb_goal_config_approach, ga.rows[0], sizeof(double) * NWB_NJ);
+  double w[NWB_NJ];
+  limb_weights(P.r_arm_weight_approach, P.l_arm_weight_approach, P.legs_weight_approach, w);
+  StageOut sa;
+  rc = plan_stage(ctx, start, ga.rows[0], w, seed + 2, nullptr, 0, execute, sa);
+  if (rc != NWB_OK) return rc;
+  resp->num_nodes_generated_approach = sa.num_nodes;
+  resp->search_time_approach = sa.search_time;
+  resp->success_approach = sa.success;
+  if (!sa.success) return NWB_OK;
+  put_trajectory(sa.path, false, 0.f, resp->motion_plan_approach);
+  // ---- manipulation (NPC:498-585 / 757-866)
   if (gm.n_found == 0) return NWB_OK;
   std::memcpy(resp->wb_goal_config_manipulate, gm.rows[0], sizeof(double) * NWB_NJ);
   const float velocity = (float)P.manipulation_velocity;
@@ -451,17 +550,21 @@ int nwb_goal_sample_batch(nwb_ctx* ctx, uint64_t seed, uint64_t first, int64_t c
   S_CUDA(ctx, cudaSetDevice(ctx->device));
   Scratch A(ctx);
   size_t o_rows = A.add(sizeof(double) * NWB_NJ * 16), o_idx = A.add(sizeof(uint64_t) * 16), o_erg = A.add(sizeof(double) * 16),
-         o_n = A.add(8), o_st = A.add(count), o_ea = A.add(sizeof(double) * count), o_ra = A.add(sizeof(double) * NWB_NJ * count);
+         o_n = A.add(8), o_st = A.add(count), o_ea = A.add(sizeof(double) * count), o_ra = A.add(sizeof(double) * NWB_NJ * count),
+         o_pose = A.add(sizeof(double) * 6), o_seed = A.add(8);
   int rc = A.commit();
   if (rc != NWB_OK) return rc;
   cudaStream_t s = ctx->stream;
   PlanConst pc;
   make_plan_const(ctx, nullptr, ctx->params.planner_step_factor, pc);
   S_CUDA(ctx, cudaMemsetAsync(A.at<char>(o_n), 0, 8, s));
+  S_CUDA(ctx, cudaMemcpyAsync(A.at<double>(o_pose), hand_pose6, sizeof(double) * 6, cudaMemcpyHostToDevice, s));
+  S_CUDA(ctx, cudaMemcpyAsync(A.at<uint64_t>(o_seed), &seed, 8, cudaMemcpyHostToDevice, s));
   S_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
-  S_CUDA(ctx, launch_goal_sample(pc, ctx->tab_group, static_pairs(ctx), hand_pose6, seed, first, count, max_ik_iter, A.at<double>(o_rows),
-                                 A.at<uint64_t>(o_idx), A.at<double>(o_erg), 16, A.at<unsigned long long>(o_n), A.at<uint8_t>(o_st),
-                                 ergonomics ? A.at<double>(o_ea) : nullptr, rows ? A.at<double>(o_ra) : nullptr, s));
+  S_CUDA(ctx, launch_goal_sample(pc, ctx->tab_group, static_pairs(ctx), A.at<double>(o_pose), A.at<uint64_t>(o_seed), 1, first, count,
+                                 max_ik_iter, A.at<double>(o_rows), A.at<uint64_t>(o_idx), A.at<double>(o_erg), 16,
+                                 A.at<unsigned long long>(o_n), A.at<uint8_t>(o_st), ergonomics ? A.at<double>(o_ea) : nullptr,
+                                 rows ? A.at<double>(o_ra) : nullptr, s));
   S_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
   S_CUDA(ctx, cudaMemcpyAsync(stage, A.at<uint8_t>(o_st), count, cudaMemcpyDeviceToHost, s));
   if (ergonomics) S_CUDA(ctx, cudaMemcpyAsync(ergonomics, A.at<double>(o_ea), sizeof(double) * count, cudaMemcpyDeviceToHost, s));
@@ -557,6 +660,90 @@ int nwb_compute_motion_plan(nwb_ctx* ctx, const nwb_compute_motion_plan_request*
   resp->search_time = st.search_time;
   resp->success = st.success;
   if (st.success) put_trajectory(st.path, false, 0.f, resp->motion_plan);
+  return NWB_OK;
+}
+
+int nwb_compute_motion_plan_batch(nwb_ctx* ctx, const nwb_compute_motion_plan_request* reqs, nwb_compute_motion_plan_response* resps,
+                                  int64_t n, const uint64_t* seeds) {
+  if (!ctx) return NWB_E_INVALID;
+  if (n < 0 || (n > 0 && (!reqs || !resps || !seeds))) return bad(ctx, "nwb_compute_motion_plan_batch: bad argument");
+  for (int64_t k = 0; k < n; ++k)
+    if (!reqs[k].wb_start_config || reqs[k].wb_start_config_len < NWB_NJ) return bad(ctx, "nwb_compute_motion_plan_batch: bad argument");
+  if (n == 0) return NWB_OK;
+  if (ctx->ds_db.size() < 2 * NWB_NJ) {
+    ctx->err = "no stable-configuration database loaded (nwb_ctx_set_ds_database / nwb_ctx_load_ds_database)";
+    return NWB_E_STATE;
+  }
+  const nwb_params& P = ctx->params;
+  const int N = (int)n;
+  std::vector<double> poses((size_t)N * 6);
+  for (int k = 0; k < N; ++k) pose_of(reqs[k].right_hand_position, reqs[k].right_hand_direction, &poses[(size_t)k * 6]);
+  std::vector<GoalSet> goals(N);
+  double t0 = now_s();
+  int rc = sample_goals_batch(ctx, N, seeds, poses.data(), P.scg_max_samples, P.scg_max_ik_iterations, goals.data());
+  if (rc != NWB_OK) return rc;
+  const double t_goal = now_s() - t0;
+  std::vector<int> live;                                    // requests with a goal configuration (NPC:270)
+  for (int k = 0; k < N; ++k) {
+    resps[k].motion_plan.n_points = 0;
+    resps[k].num_nodes_generated = 0;
+    resps[k].search_time = 0.0;
+    resps[k].success = 0;
+    resps[k].time_goal_config = t_goal;
+    if (goals[k].n_found) {
+      std::memcpy(resps[k].wb_goal_config, goals[k].rows[0], sizeof(double) * NWB_NJ);
+      live.push_back(k);
+    }
+  }
+  const int Q = (int)live.size();
+  if (Q == 0) return NWB_OK;
+  double w[NWB_NJ];
+  limb_weights(P.r_arm_weight_approach, P.l_arm_weight_approach, P.legs_weight_approach, w);
+  const int cap = 2048;
+  std::vector<double> starts((size_t)Q * NWB_NJ), gcfg((size_t)Q * NWB_NJ), raw((size_t)Q * cap * NWB_NJ);
+  std::vector<uint64_t> qseeds(Q);
+  std::vector<nwb_plan_result> res(Q);
+  for (int i = 0; i < Q; ++i) {
+    std::memcpy(&starts[(size_t)i * NWB_NJ], reqs[live[i]].wb_start_config, sizeof(double) * NWB_NJ);
+    std::memcpy(&gcfg[(size_t)i * NWB_NJ], goals[live[i]].rows[0], sizeof(double) * NWB_NJ);
+    qseeds[i] = seeds[live[i]] + 2;
+  }
+  t0 = now_s();
+  rc = nwb_solve_query_batch(ctx, starts.data(), gcfg.data(), Q, ctx->ds_db.data(), (int32_t)(ctx->ds_db.size() / NWB_NJ), w,
+                             qseeds.data(), P.planner_max_iterations, P.planner_step_factor, 0, res.data(), raw.data(), cap);
+  if (rc != NWB_OK) return rc;
+  const double t_search = now_s() - t0;
+  std::vector<std::vector<double>> paths;
+  std::vector<int> owner;
+  for (int i = 0; i < Q; ++i) {
+    resps[live[i]].search_time = t_search;
+    if (!res[i].success) continue;
+    resps[live[i]].num_nodes_generated = (uint32_t)res[i].num_nodes_generated;
+    const int len = std::min(res[i].raw_path_len, cap);
+    paths.emplace_back(raw.begin() + (size_t)i * cap * NWB_NJ, raw.begin() + ((size_t)i * cap + len) * NWB_NJ);
+    owner.push_back(live[i]);
+  }
+  std::vector<std::vector<int>> sel;
+  std::vector<uint8_t> ok;
+  rc = shortcut_paths_batch(ctx, paths, sel, ok);
+  if (rc != NWB_OK) return rc;
+  for (size_t i = 0; i < paths.size(); ++i) {
+    if (!ok[i]) continue;                                   // shortcutting failed: empty trajectory (RP:1919-1923)
+    const int k = owner[i];
+    std::vector<double> way;
+    for (int idx : sel[i]) way.insert(way.end(), paths[i].begin() + (size_t)idx * NWB_NJ, paths[i].begin() + (size_t)(idx + 1) * NWB_NJ);
+    std::vector<double> path;
+    const int n_sel = (int)sel[i].size();
+    if (!reqs[k].execute_trajectory) {
+      const int rows = (n_sel - 1) * (P.shortcut_waypoints + 1) + 1;
+      path.resize((size_t)rows * NWB_NJ);
+      nwb_interpolate_path(way.data(), n_sel, P.shortcut_waypoints, path.data(), rows);
+    } else {
+      path = way;
+    }
+    resps[k].success = !path.empty();
+    put_trajectory(path, false, 0.f, resps[k].motion_plan);
+  }
   return NWB_OK;
 }
 

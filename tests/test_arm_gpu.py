@@ -205,6 +205,27 @@ def test_motion_plan_and_goal_config_services(ctx, oracle):
         ctx.compute_motion_plan(pose[:3], pose[3:], START[:10], 1)
 
 
+def test_motion_plan_batch_equals_single_calls(ctx):
+    """V4: the grasp-pose grid of SIM:778-788 (a 3 x 3 corner of it) from the crouched pose SIM:199-219."""
+    start = np.array([0, -0.349066, 0.698132, -0.436332, 0, 1.39626, 0.349066, -1.39626, -0.5, 0, 1.39626, -0.349066, 1.39626,
+                      0.5, 0, 0, 0, -0.436332, 0.698132, -0.349066, 0])
+    pos = np.array([[-0.08 + i * 0.4 / 15, -0.30 + j * 0.4 / 15, 0.2] for i in (7, 9, 11) for j in (6, 8, 10)] + [[0.6, 0.0, 0.3]])
+    dirs = np.tile([0.0, -1.0, 0.0], (len(pos), 1))
+    seeds = 20121100 + np.arange(len(pos), dtype=np.uint64)
+    batch = ctx.compute_motion_plan_batch(pos, dirs, np.tile(start, (len(pos), 1)), seeds)
+    n_ok = 0
+    for k in range(len(pos)):
+        one = ctx.compute_motion_plan(pos[k], dirs[k], start, int(seeds[k]))
+        assert batch[k]["success"] == one["success"]
+        assert (batch[k]["wb_goal_config"] == one["wb_goal_config"]).all() or not one["success"]
+        assert batch[k]["num_nodes_generated"] == one["num_nodes_generated"]
+        assert batch[k]["trajectory"].shape == one["trajectory"].shape
+        if one["success"]:
+            n_ok += 1
+            assert (batch[k]["trajectory"] == one["trajectory"]).all()
+    assert n_ok >= 3 and not batch[-1]["success"]
+
+
 def test_services_need_a_database(oracle):
     with nwb.Context() as c:
         with pytest.raises(nwb.NwbError, match="database"):
