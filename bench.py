@@ -107,7 +107,7 @@ S3_POS, S3_DIR, S3_PULL = [0.24, -0.065, 0.30], [0.0, -1.0, 0.0], 0.10     # pla
 
 
 def s3_start():
-    q = np.zeros(nwb.NJ)
+    q = np.zeros(21)
     q[8], q[13] = -0.5, 0.5                                                 # planning_example_simulation.cpp:232-252
     return q
 
@@ -116,6 +116,7 @@ def scenario3_gpu(reps=101):
     """Second half of BASELINE.json's metric: scenario-3 plan time p50 (compute_linear_manipulation_plan through
     the C ABI, 101 seeded repetitions, host wall clock around the call - it returns host-side trajectories)."""
     import oracle_lib as OL
+    import nao_wholebody_planning_b200 as nwb
     c = nwb.Context()
     c.set_ds_database(OL.golden_db())
     c.compute_linear_manipulation_plan(S3_POS, S3_DIR, s3_start(), 0.0, S3_PULL, 1)    # warm-up (allocations)

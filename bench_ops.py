@@ -144,6 +144,31 @@ def main():
     w = np.ones(21)
     w[15] = 0.0
 
+    # ---- V1 / S1: validity against the 7-box shelf scene -------------------------
+    nv = 1 << (18 if args.quick else 20)
+    qv = OL.uniform_configs(nv, seed=20121001)
+    c1 = nwb.Context()
+    c1.set_stream(stream.cuda_stream)
+    c1.scene_add_boxes(OL.scene_boxes("S1"))
+    with torch.cuda.stream(stream):
+        qv_dev = torch.from_numpy(qv).to(dev)
+        v_dev = torch.empty(nv, dtype=torch.uint8, device=dev)
+    ms = dev_time(lambda: c1.is_feasible_dev(qv_dev.data_ptr(), nwb._abi.F64, nv, v_dev.data_ptr()), stream, reps=10)
+    ns = 40000
+    t0 = time.perf_counter()
+    cv, _, _ = orc.is_feasible(qv[:ns], boxes=OL.scene_boxes("S1"))
+    cpu1 = ns / (time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    orc.is_feasible(qv[:ns * 8], boxes=OL.scene_boxes("S1"), threads=orc.threads)
+    cpun = ns * 8 / (time.perf_counter() - t0)
+    fl = rf["validity_S1_shelf_flops_per_config"]
+    emit(args.out, op="validity_S1_shelf", configs=nv, boxes=c1.num_boxes, ms=ms, configs_per_s=nv / (ms * 1e-3),
+         valid_fraction=float(v_dev.float().mean().item()), mismatches_vs_oracle=int((v_dev[:ns].cpu().numpy() != cv).sum()),
+         oracle_sample=ns, cpu_configs_per_s_1thread=cpu1, cpu_configs_per_s_all_threads=cpun, cpu_threads=orc.threads,
+         roofline={"bound": "fp32", "achieved": fl * nv / (ms * 1e-3) / 1e12, "peak": ffma, "unit": "TFLOP/s",
+                   "frac": fl * nv / (ms * 1e-3) / 1e12 / ffma, "flops_per_config": fl})
+    c1.close()
+
     # ---- V2: nearest neighbour ------------------------------------------------------------------
     nodes_all = OL.uniform_configs(1_000_000, seed=20121001, lhyp_zero=True)
     rng = np.random.default_rng(20121002)
