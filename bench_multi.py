@@ -1,0 +1,137 @@
+#!/usr/bin/env python3
+"""bench_multi.py - the sharded workloads of SURVEY.md section 8e other than the headline validity batch:
+
+  V3  stable-configuration database generation: sample-index ranges per rank (the Philox counter is the
+      GLOBAL sample index, so the accepted set does not depend on the number of GPUs), rows gathered
+      and merged in ascending sample index
+  V4  256 grasp-pose compute_motion_plan requests: round-robin request -> rank, every rank runs its
+      share as ONE batched call, results gathered
+
+Launch like bench.py: `python bench_multi.py` (1 GPU) or
+`python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench_multi.py`.
+One JSON line per workload from rank 0; timing = barrier + synchronize on both sides, max over ranks.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+for p in (str(ROOT), str(ROOT / "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+CROUCH = np.array([0, -0.349066, 0.698132, -0.436332, 0, 1.39626, 0.349066, -1.39626, -0.5, 0, 1.39626, -0.349066, 1.39626,
+                   0.5, 0, 0, 0, -0.436332, 0.698132, -0.349066, 0])     # planning_example_simulation.cpp:199-219
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--samples-log2", type=int, default=22)
+    ap.add_argument("--check-log2", type=int, default=16, help="size of the partition-independence check")
+    ap.add_argument("--out", default="")
+    args = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+    import nao_wholebody_planning_b200 as nwb
+    from nao_wholebody_planning_b200 import sharding
+    import oracle_lib as OL                       # golden database + joint limits only
+
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench_multi.py needs CUDA devices: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = nwb.Context(device=local)
+    ctx.set_ds_database(OL.golden_db())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(dt):
+        if world == 1:
+            return dt
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def emit(**kw):
+        if rank == 0:
+            line = json.dumps(kw)
+            print(line, flush=True)
+            if args.out:
+                with open(args.out, "a") as f:
+                    f.write(line + "\n")
+
+    # ---- V3 ---------------------------------------------------------------------------------------------------
+    seed = 20121005
+
+    def generate(total):
+        lo, hi = sharding.shard_bounds(total, world)[rank]
+        rows, idx, _ = ctx.sample_stable_configs(seed, lo, hi - lo, max_ik_iter=5, cap=max(1024, (hi - lo) // 6), want_stage=False)
+        r = torch.from_numpy(rows).to(dev)
+        i = torch.from_numpy(idx.astype(np.int64)).to(dev)
+        if world > 1:
+            r, i = sharding.gather_sampler_rows(r, i)
+        return r, i
+
+    small = 1 << args.check_log2
+    r_small, i_small = generate(small)
+    ref_rows, ref_idx, _ = ctx.sample_stable_configs(seed, 0, small, max_ik_iter=5, cap=max(1024, small // 6), want_stage=False)   # unsharded, this rank alone
+    same = bool(len(ref_idx) == len(i_small) and (i_small.cpu().numpy() == ref_idx.astype(np.int64)).all()
+                and (r_small.cpu().numpy() == ref_rows).all())
+    total = 1 << args.samples_log2
+    generate(total >> 2)                                                    # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    rows, idx = generate(total)
+    barrier()
+    dt = max_over_ranks(time.perf_counter() - t0)
+    emit(op="db_generation_sharded", n_gpus=world, samples=total, accepted=int(len(idx)), wall_s=dt, samples_per_s=total / dt,
+         sharded_equals_unsharded=same, check_samples=small, scaling="strong",
+         note="host API per rank (rows come back to the host, are re-uploaded and gathered with NCCL); accepted set identical "
+              "to the single-GPU run by construction (global Philox counter)")
+
+    # ---- V4 ---------------------------------------------------------------------------------------------------
+    n = 256
+    pos = np.array([[-0.08 + i * 0.4 / 15, -0.30 + j * 0.4 / 15, 0.2] for i in range(16) for j in range(16)])
+    dirs = np.tile([0.0, -1.0, 0.0], (n, 1))
+    seeds = (20121100 + np.arange(n)).astype(np.uint64)
+    mine = sharding.round_robin(n, rank, world)
+
+    def plan():
+        res = ctx.compute_motion_plan_batch(pos[mine], dirs[mine], np.tile(CROUCH, (len(mine), 1)), seeds[mine], cap=2048)
+        out = [(k, r["success"], r["num_nodes_generated"], r["trajectory"]) for k, r in zip(mine, res)]
+        if world > 1:
+            parts = [None] * world
+            dist.all_gather_object(parts, out)
+            out = sorted((x for p in parts for x in p), key=lambda x: x[0])
+        return out
+
+    plan()                                                                  # warm-up (allocations)
+    barrier()
+    t0 = time.perf_counter()
+    out = plan()
+    barrier()
+    dt = max_over_ranks(time.perf_counter() - t0)
+    digest = int(sum(int(s) * (k + 1) + int(nn) for k, s, nn, _ in out))    # compare across GPU counts
+    emit(op="grasp_pose_queries_256_sharded", n_gpus=world, queries=n, solved=int(sum(s for _, s, _, _ in out)), wall_s=dt,
+         digest=digest, scaling="strong",
+         note="round-robin request -> rank, one batched compute_motion_plan call per rank, results gathered as objects; the "
+              "digest (solved flags and node counts) must not depend on the number of GPUs")
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
