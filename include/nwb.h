@@ -100,6 +100,15 @@ typedef struct nwb_params {
   int32_t manipulate_waypoints;   /* RP:1398 (4)   way-points per segment of an articulated path  */
   int32_t object_interp_points;   /* NPC:539,822 (20) intermediate points of the hand trajectory  */
   double manipulation_velocity;   /* RP:92 (0.02 m/s)                                             */
+  /* generateTrajectory's time parameterisation (RP:1596-1618, MoveIt IterativeParabolicTimeParameterization):
+   * the limits MoveIt reads from the robot model.  nao_description2 is not in the reference tree: the
+   * velocity defaults are the NAO V4 URDF values quoted from memory (UNVERIFIED); the URDF carries no
+   * acceleration limits, so MoveIt's default 1.0 rad/s^2 applies. */
+  int32_t time_parameterization;  /* 1: apply it where the reference does (not for execute && articulated) */
+  int32_t iptp_max_iterations;    /* 100  (IterativeParabolicTimeParameterization default)        */
+  double iptp_max_time_change;    /* 0.01 (max_time_change_per_it)                                */
+  double joint_max_velocity[NWB_NJ];
+  double joint_max_acceleration[NWB_NJ];
 } nwb_params;
 
 /* Fill `p` with the reference defaults. */
@@ -377,12 +386,22 @@ typedef struct nwb_trajectory {   /* moveit_msgs/DisplayTrajectory -> joint_traj
   int32_t capacity;               /* in:  rows the two arrays can hold                                   */
   int32_t n_points;               /* out: way-points of the plan (rows beyond capacity are not written)  */
   double* positions;              /* [capacity][21]                                                      */
-  double* time_from_start;        /* [capacity] seconds: 2.0 + i * increment (RP:1532-1553)              */
+  double* time_from_start;        /* [capacity] seconds: nwb_time_parameterize of the way-points, or - for an
+                                   * executed articulated plan / time_parameterization = 0 - the stamps
+                                   * 2.0 + i * increment of RP:1532-1553                                   */
 } nwb_trajectory;
 
 NWB_API int nwb_ctx_set_ds_database(nwb_ctx* ctx, const double* rows, int64_t n_rows);
 NWB_API int nwb_ctx_load_ds_database(nwb_ctx* ctx, const char* path);   /* RRT_Planner::load_DS_database, RP:121-191 */
 NWB_API int64_t nwb_ctx_ds_database_size(const nwb_ctx* ctx);
+
+/* trajectory_processing::IterativeParabolicTimeParameterization::computeTimeStamps as called by
+ * RRT_Planner::generateTrajectory (RP:1610-1611) on n_points way-points [n_points][21]: velocity
+ * constraints, then the iterative forward / backward expansion of the intervals until every joint's
+ * parabolic-blend acceleration is within its limit.  time_from_start [n_points] receives the cumulative
+ * durations + 2.0 s (RP:1614-1618).  Host-side and serial, as in the reference.  MoveIt is not vendored:
+ * restated from its published algorithm - PARITY UNPINNED (no shipped file carries time stamps). */
+NWB_API int nwb_time_parameterize(const nwb_ctx* ctx, const double* positions, int32_t n_points, double* time_from_start);
 
 typedef struct nwb_compute_goal_config_request {   /* Compute_Goal_Config.srv:1-4 */
   nwb_point3 right_hand_position;

@@ -46,6 +46,11 @@ class NwbParams(C.Structure):
         ("manipulate_waypoints", C.c_int32),
         ("object_interp_points", C.c_int32),
         ("manipulation_velocity", C.c_double),
+        ("time_parameterization", C.c_int32),
+        ("iptp_max_iterations", C.c_int32),
+        ("iptp_max_time_change", C.c_double),
+        ("joint_max_velocity", C.c_double * NJ),
+        ("joint_max_acceleration", C.c_double * NJ),
     ]
 
 
@@ -113,6 +118,11 @@ class CircularManipulationRequest(C.Structure):  # Compute_Circular_Manipulation
                 ("rotation_angle", C.c_double), ("clearance_handle", C.c_double), ("execute_trajectory", C.c_uint8)]
 
 
+# NAO V4 URDF velocity limits in planner joint order (from memory, UNVERIFIED; see include/nwb.h)
+NAO_MAX_VELOCITY = [4.16174, 6.40239, 6.40239, 6.40239, 4.16174, 8.26797, 7.19407, 8.26797, 7.19407, 24.6229,
+                    8.26797, 7.19407, 8.26797, 7.19407, 24.6229, 4.16174, 4.16174, 6.40239, 6.40239, 6.40239, 4.16174]
+
+
 def default_params(**over):
     """Reference defaults (planning_config/planning_parameters.yaml, hard-coded constants)."""
     p = NwbParams(device=0, quirks=QUIRK_SIGNED_FOOT_ERROR | QUIRK_DB_INDEX_FLOOR, srdf_trim=1, scale_origin=1,
@@ -120,7 +130,10 @@ def default_params(**over):
                   scg_max_ik_iterations=5, planner_max_iterations=8000, planner_step_factor=0.1, pinv_eps=1e-5,
                   shortcut_waypoints=100, shortcut_max_rounds=500, r_arm_weight_approach=1.0, l_arm_weight_approach=1.0,
                   legs_weight_approach=1.0, r_arm_weight_manipulate=1.0, l_arm_weight_manipulate=0.0,
-                  legs_weight_manipulate=1.0, manipulate_waypoints=4, object_interp_points=20, manipulation_velocity=0.02)
+                  legs_weight_manipulate=1.0, manipulate_waypoints=4, object_interp_points=20, manipulation_velocity=0.02,
+                  time_parameterization=1, iptp_max_iterations=100, iptp_max_time_change=0.01)
+    p.joint_max_velocity[:] = NAO_MAX_VELOCITY
+    p.joint_max_acceleration[:] = [1.0] * NJ
     for k, v in over.items():
         if not hasattr(p, k):
             raise AttributeError(k)
@@ -212,6 +225,7 @@ def _declare(lib):
         "nwb_ctx_set_ds_database": (C.c_int, [vp, vp, i64]),
         "nwb_ctx_load_ds_database": (C.c_int, [vp, C.c_char_p]),
         "nwb_ctx_ds_database_size": (i64, [vp]),
+        "nwb_time_parameterize": (C.c_int, [vp, vp, i32, vp]),
         "nwb_compute_goal_config": (C.c_int, [vp, C.POINTER(GoalConfigRequest), C.POINTER(GoalConfigResponse), C.c_uint64]),
         "nwb_compute_motion_plan": (C.c_int, [vp, C.POINTER(MotionPlanRequest), C.POINTER(MotionPlanResponse), C.c_uint64]),
         "nwb_compute_motion_plan_batch": (C.c_int, [vp, C.POINTER(MotionPlanRequest), C.POINTER(MotionPlanResponse), i64, vp]),

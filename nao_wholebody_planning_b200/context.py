@@ -305,6 +305,13 @@ class Context:
         t = _abi.Trajectory(cap, 0, pos.ctypes.data_as(C.POINTER(C.c_double)), tfs.ctypes.data_as(C.POINTER(C.c_double)))
         return t, pos, tfs
 
+    def time_parameterize(self, positions):
+        """generateTrajectory's time parameterisation (rrt_planner.cpp:1596-1618) -> time_from_start [n]."""
+        positions = np.ascontiguousarray(positions, dtype=np.float64).reshape(-1, NJ)
+        out = np.empty(len(positions))
+        self._check(self.lib.nwb_time_parameterize(self.h, _p(positions), len(positions), _p(out)), "nwb_time_parameterize")
+        return out
+
     def compute_goal_config(self, position, direction, seed):
         req = _abi.GoalConfigRequest(_abi.Point3(*position), _abi.Point3(*direction))
         resp = _abi.GoalConfigResponse()

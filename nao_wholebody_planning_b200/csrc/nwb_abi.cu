@@ -80,6 +80,19 @@ int nwb_params_default(nwb_params* p) {
   p->manipulate_waypoints = 4;
   p->object_interp_points = 20;
   p->manipulation_velocity = 0.02;
+  p->time_parameterization = 1;
+  p->iptp_max_iterations = 100;
+  p->iptp_max_time_change = 0.01;
+  // planner joint order (RP:2003-2023): R leg (AnkleRoll, AnklePitch, KneePitch, HipPitch, HipRoll), L arm, R arm
+  // (ShoulderPitch, ShoulderRoll, ElbowYaw, ElbowRoll, WristYaw), LHipYawPitch, L leg (HipRoll, HipPitch, KneePitch,
+  // AnklePitch, AnkleRoll).  NAO V4 URDF velocity limits [rad/s], from memory (UNVERIFIED).
+  static const double vmax[NWB_NJ] = {4.16174, 6.40239, 6.40239, 6.40239, 4.16174, 8.26797, 7.19407, 8.26797, 7.19407, 24.6229,
+                                      8.26797, 7.19407, 8.26797, 7.19407, 24.6229, 4.16174, 4.16174, 6.40239, 6.40239, 6.40239,
+                                      4.16174};
+  for (int j = 0; j < NWB_NJ; ++j) {
+    p->joint_max_velocity[j] = vmax[j];
+    p->joint_max_acceleration[j] = 1.0;
+  }
   return NWB_OK;
 }
 

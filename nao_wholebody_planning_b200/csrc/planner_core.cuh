@@ -138,12 +138,48 @@ __device__ __forceinline__ void frame_diff(const DFrame& a, const DFrame& b, dou
   tw[3] = w.x; tw[4] = w.y; tw[5] = w.z;
 }
 
+// One Hestenes rotation of columns (P, Q) of W (6x5) and V (5x5).  All indices are compile-time constants.
+// t = tan(theta) of the rotation that orthogonalises the two columns, written without the intermediate
+// zeta = (beta - alpha) / (2 gamma):  t = sgn(zeta) 2|gamma| / (|d| + sqrt(d^2 + 4 gamma^2)),  d = beta - alpha
+// (one square root, one division, one reciprocal square root per rotation).
+template <int P, int Q>
+__device__ __forceinline__ void jacobi_rotate(double (&W)[6][5], double (&V)[5][5], bool& rotated) {
+  double alpha = 0, beta = 0, gamma = 0;
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    alpha += W[r][P] * W[r][P];
+    beta += W[r][Q] * W[r][Q];
+    gamma += W[r][P] * W[r][Q];
+  }
+  // converged pair: |gamma| <= 1e-15 sqrt(alpha beta)   (compared squared: no root, no division)
+  if (gamma * gamma > 1e-30 * (alpha * beta)) {
+    rotated = true;
+    const double d = beta - alpha;
+    const double sg = ((d >= 0) == (gamma >= 0) || d == 0) ? 1.0 : -1.0;
+    const double t = sg * (2.0 * fabs(gamma)) / (fabs(d) + sqrt(d * d + 4.0 * gamma * gamma));
+    const double c = rsqrt(1.0 + t * t), s = c * t;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      const double wp = W[r][P], wq = W[r][Q];
+      W[r][P] = c * wp - s * wq;
+      W[r][Q] = s * wp + c * wq;
+    }
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+      const double vp = V[r][P], vq = V[r][Q];
+      V[r][P] = c * vp - s * vq;
+      V[r][Q] = s * vp + c * vq;
+    }
+  }
+}
+
 // qdot = pinv(J) * twist with singular values below eps zeroed (ChainIkSolverVel_pinv).
-// J is 6x5 (column i = (a_i x (p_tip - o_i), a_i)).  One-sided Jacobi SVD, W = J V = U S.
+// J is 6x5 (column i = (a_i x (p_tip - o_i), a_i)).  One-sided Jacobi SVD, W = J V = U S.  A sweep visits the
+// 10 column pairs in a round-robin order - five rounds of two DISJOINT pairs - so the two rotations of a
+// round are independent instruction streams: this code runs one warp per scheduler with nothing else to
+// hide the fp64 dependency chains behind.
 static __device__ __noinline__ void pinv_solve(const double (*W_in)[5], const double* tw_in, double eps, double* qdot) {
-  // W_in / tw_in arrive through memory (the function is not inlined): pull them into registers once -
-  // every index below is a compile-time constant, so the ~70 column rotations of a solve run out of
-  // the register file instead of local memory
+  // W_in / tw_in arrive through memory (the function is not inlined): pull them into registers once
   double W[6][5], tw[6], V[5][5];
 #pragma unroll
   for (int r = 0; r < 6; ++r) {
@@ -156,38 +192,13 @@ static __device__ __noinline__ void pinv_solve(const double (*W_in)[5], const do
 #pragma unroll
     for (int j = 0; j < 5; ++j) V[i][j] = (i == j) ? 1.0 : 0.0;
   for (int sweep = 0; sweep < 60; ++sweep) {
-    double off = 0;
-#pragma unroll
-    for (int p = 0; p < 4; ++p)
-#pragma unroll
-      for (int q = p + 1; q < 5; ++q) {
-        double alpha = 0, beta = 0, gamma = 0;
-#pragma unroll
-        for (int r = 0; r < 6; ++r) {
-          alpha += W[r][p] * W[r][p];
-          beta += W[r][q] * W[r][q];
-          gamma += W[r][p] * W[r][q];
-        }
-        if (gamma != 0.0) {
-          off = fmax(off, fabs(gamma) / sqrt(alpha * beta + 1e-300));
-          double zeta = (beta - alpha) / (2 * gamma);
-          double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1 + zeta * zeta));
-          double c = 1 / sqrt(1 + t * t), s = c * t;
-#pragma unroll
-          for (int r = 0; r < 6; ++r) {
-            double wp = W[r][p], wq = W[r][q];
-            W[r][p] = c * wp - s * wq;
-            W[r][q] = s * wp + c * wq;
-          }
-#pragma unroll
-          for (int r = 0; r < 5; ++r) {
-            double vp = V[r][p], vq = V[r][q];
-            V[r][p] = c * vp - s * vq;
-            V[r][q] = s * vp + c * vq;
-          }
-        }
-      }
-    if (off < 1e-15) break;
+    bool rotated = false;
+    jacobi_rotate<1, 4>(W, V, rotated); jacobi_rotate<2, 3>(W, V, rotated);
+    jacobi_rotate<0, 2>(W, V, rotated); jacobi_rotate<3, 4>(W, V, rotated);
+    jacobi_rotate<0, 4>(W, V, rotated); jacobi_rotate<1, 3>(W, V, rotated);
+    jacobi_rotate<0, 1>(W, V, rotated); jacobi_rotate<2, 4>(W, V, rotated);
+    jacobi_rotate<0, 3>(W, V, rotated); jacobi_rotate<1, 2>(W, V, rotated);
+    if (!rotated) break;
   }
   // tmp_i = (u_i . tw) / s_i  with u_i = W[:,i]/s_i  ->  (W[:,i] . tw) / s_i^2 ; zero if s_i < eps
   double tmp[5];

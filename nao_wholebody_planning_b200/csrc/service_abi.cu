@@ -207,7 +207,106 @@ void limb_weights(double r_arm, double l_arm, double legs, double* w) {   // NPC
   for (int i = 16; i < NWB_NJ; ++i) w[i] = legs;
 }
 
-void put_trajectory(const std::vector<double>& path, bool articulated, float time_step_manip, nwb_trajectory& t) {
+// ---- trajectory_processing::IterativeParabolicTimeParameterization (MoveIt, called RP:1610-1611) -----------------
+// Restated from the published algorithm (moveit_core/trajectory_processing, Hydro/Indigo vintage): MoveIt is
+// not vendored in the reference.  time_diff[i] = duration of the interval between way-points i and i+1.
+namespace iptp {
+constexpr double kRoundingThreshold = 0.01;
+
+void apply_velocity_constraints(const double* q, int n, const double* v_max, std::vector<double>& time_diff) {
+  for (int i = 0; i < n - 1; ++i)
+    for (int j = 0; j < NWB_NJ; ++j) {
+      const double dq1 = q[(size_t)i * NWB_NJ + j], dq2 = q[(size_t)(i + 1) * NWB_NJ + j];
+      const double t_min = std::fabs(dq2 - dq1) / v_max[j];
+      if (t_min > time_diff[i]) time_diff[i] = t_min;
+    }
+}
+// grow dt1 (resp. dt2) by 1 % until the blend acceleration is within a_max
+double find_t1(double dq1, double dq2, double dt1, double dt2, double a_max) {
+  const double mult_factor = 1.01;
+  double v1 = dq1 / dt1, v2 = dq2 / dt2, a = 2.0 * (v2 - v1) / (dt1 + dt2);
+  while (std::fabs(a) > a_max) {
+    v1 = dq1 / dt1;
+    v2 = dq2 / dt2;
+    a = 2.0 * (v2 - v1) / (dt1 + dt2);
+    dt1 *= mult_factor;
+  }
+  return dt1;
+}
+double find_t2(double dq1, double dq2, double dt1, double dt2, double a_max) {
+  const double mult_factor = 1.01;
+  double v1 = dq1 / dt1, v2 = dq2 / dt2, a = 2.0 * (v2 - v1) / (dt1 + dt2);
+  while (std::fabs(a) > a_max) {
+    v1 = dq1 / dt1;
+    v2 = dq2 / dt2;
+    a = 2.0 * (v2 - v1) / (dt1 + dt2);
+    dt2 *= mult_factor;
+  }
+  return dt2;
+}
+void apply_acceleration_constraints(const double* q, int n, const double* a_lim, int max_iterations, double max_time_change,
+                                    std::vector<double>& time_diff) {
+  int num_updates = 0, iteration = 0;
+  bool backwards = false;
+  do {
+    num_updates = 0;
+    ++iteration;
+    for (int j = 0; j < NWB_NJ; ++j) {                   // joints outermost: an enlarged interval propagates along the path
+      for (int count = 0; count < 2; ++count) {          // forwards, then backwards
+        for (int i = 0; i < n - 1; ++i) {
+          const int index = backwards ? (n - 1) - i : i;
+          const double a_max = a_lim[j];
+          const double cur = q[(size_t)index * NWB_NJ + j];
+          double q1, q2, q3, dt1, dt2;
+          if (index == 0) {                              // first point: mirrored neighbour
+            q1 = q[(size_t)(index + 1) * NWB_NJ + j]; q2 = cur; q3 = q1;
+            dt1 = dt2 = time_diff[index];
+          } else if (index < n - 1) {
+            q1 = q[(size_t)(index - 1) * NWB_NJ + j]; q2 = cur; q3 = q[(size_t)(index + 1) * NWB_NJ + j];
+            dt1 = time_diff[index - 1];
+            dt2 = time_diff[index];
+          } else {                                       // last point: only n-1 intervals
+            q1 = q[(size_t)(index - 1) * NWB_NJ + j]; q2 = cur; q3 = q1;
+            dt1 = dt2 = time_diff[index - 1];
+          }
+          double a = 0.0;
+          if (!(dt1 == 0.0 || dt2 == 0.0)) {
+            const double v1 = (q2 - q1) / dt1, v2 = (q3 - q2) / dt2;
+            a = 2.0 * (v2 - v1) / (dt1 + dt2);
+          }
+          if (std::fabs(a) > a_max + kRoundingThreshold) {
+            if (!backwards) {
+              dt2 = std::min(dt2 + max_time_change, find_t2(q2 - q1, q3 - q2, dt1, dt2, a_max));
+              time_diff[index] = dt2;
+            } else {
+              dt1 = std::min(dt1 + max_time_change, find_t1(q2 - q1, q3 - q2, dt1, dt2, a_max));
+              time_diff[index - 1] = dt1;
+            }
+            ++num_updates;
+          }
+        }
+        backwards = !backwards;
+      }
+    }
+  } while (num_updates > 0 && iteration < max_iterations);
+}
+// computeTimeStamps + the 2 s head start of RP:1614-1618
+void time_stamps(const nwb_params& P, const double* q, int n, double* tfs) {
+  if (n <= 0) return;
+  std::vector<double> time_diff((size_t)std::max(n - 1, 0), 0.0);
+  apply_velocity_constraints(q, n, P.joint_max_velocity, time_diff);
+  apply_acceleration_constraints(q, n, P.joint_max_acceleration, P.iptp_max_iterations, P.iptp_max_time_change, time_diff);
+  double t = 0.0;
+  tfs[0] = t + 2.0;
+  for (int i = 1; i < n; ++i) {
+    t += time_diff[i - 1];
+    tfs[i] = t + 2.0;
+  }
+}
+}  // namespace iptp
+
+void put_trajectory(const nwb_params& P, const std::vector<double>& path, bool articulated, bool execute, float time_step_manip,
+                    nwb_trajectory& t) {
   const int n = (int)(path.size() / NWB_NJ);
   t.n_points = n;
   float increment = 2.0f;                                                 // RP:1532
@@ -217,6 +316,12 @@ void put_trajectory(const std::vector<double>& path, bool articulated, float tim
       if (t.time_from_start) t.time_from_start[i] = (double)increment;
     }
     increment = articulated ? increment + time_step_manip : increment + 1.0f;   // RP:1547-1552
+  }
+  // RP:1569-1618: everything but an executed articulated plan goes through the time parameterisation
+  if (P.time_parameterization && !(execute && articulated) && n > 0 && t.time_from_start) {
+    std::vector<double> tfs(n);
+    iptp::time_stamps(P, path.data(), n, tfs.data());
+    for (int i = 0; i < std::min(n, (int)t.capacity); ++i) t.time_from_start[i] = tfs[i];
   }
 }
 
@@ -428,7 +533,7 @@ int manipulation_plan(nwb_ctx* ctx, const double* pose6, const double* start, bo
   resp->search_time_approach = sa.search_time;
   resp->success_approach = sa.success;
   if (!sa.success) return NWB_OK;
-  put_trajectory(sa.path, false, 0.f, resp->motion_plan_approach);
+  put_trajectory(P, sa.path, false, execute, 0.f, resp->motion_plan_approach);
   // ---- manipulation (NPC:498-585 / 757-866)
   if (gm.n_found == 0) return NWB_OK;
   std::memcpy(resp->wb_goal_config_manipulate, gm.rows[0], sizeof(double) * NWB_NJ);
@@ -451,7 +556,7 @@ int manipulation_plan(nwb_ctx* ctx, const double* pose6, const double* start, bo
   resp->num_nodes_generated_manipulate = sm.num_nodes;
   resp->search_time_manipulate = sm.search_time;
   resp->success_manipulation = sm.success;
-  if (sm.success) put_trajectory(sm.path, true, time_step, resp->motion_plan_manipulation);
+  if (sm.success) put_trajectory(P, sm.path, true, execute, time_step, resp->motion_plan_manipulation);
   return NWB_OK;
 }
 }  // namespace
@@ -592,6 +697,12 @@ int nwb_sample_goal_configs(nwb_ctx* ctx, uint64_t seed, const double* hand_pose
   return NWB_OK;
 }
 
+int nwb_time_parameterize(const nwb_ctx* ctx, const double* positions, int32_t n_points, double* time_from_start) {
+  if (!ctx || n_points < 0 || (n_points > 0 && (!positions || !time_from_start))) return NWB_E_INVALID;
+  iptp::time_stamps(ctx->params, positions, n_points, time_from_start);
+  return NWB_OK;
+}
+
 int nwb_ctx_set_ds_database(nwb_ctx* ctx, const double* rows, int64_t n_rows) {
   if (!ctx) return NWB_E_INVALID;
   if (n_rows < 0 || (n_rows > 0 && !rows)) return bad(ctx, "nwb_ctx_set_ds_database: bad argument");
@@ -659,7 +770,7 @@ int nwb_compute_motion_plan(nwb_ctx* ctx, const nwb_compute_motion_plan_request*
   resp->num_nodes_generated = st.num_nodes;
   resp->search_time = st.search_time;
   resp->success = st.success;
-  if (st.success) put_trajectory(st.path, false, 0.f, resp->motion_plan);
+  if (st.success) put_trajectory(P, st.path, false, req->execute_trajectory != 0, 0.f, resp->motion_plan);
   return NWB_OK;
 }
 
@@ -742,7 +853,7 @@ int nwb_compute_motion_plan_batch(nwb_ctx* ctx, const nwb_compute_motion_plan_re
       path = way;
     }
     resps[k].success = !path.empty();
-    put_trajectory(path, false, 0.f, resps[k].motion_plan);
+    put_trajectory(P, path, false, reqs[k].execute_trajectory != 0, 0.f, resps[k].motion_plan);
   }
   return NWB_OK;
 }

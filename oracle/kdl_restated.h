@@ -15,6 +15,7 @@
 // code to file precision.
 #pragma once
 #include <cmath>
+#include <utility>
 #include <vector>
 
 namespace kdlr {
@@ -180,37 +181,49 @@ inline void diff(const Frame& a, const Frame& b, double* tw) {
 // Thin SVD of a row-major m x n matrix (m >= n) by one-sided Jacobi (Hestenes): A = U diag(S) V^T.
 // KDL uses a Householder SVD (svd_HH, maxiter 150); the decomposition it converges to is the same
 // up to column signs / order, which do not affect the pseudo-inverse built from it.
+// Column pairs are visited in round-robin order (rounds of disjoint pairs; for n = 5:
+// (1,4)(2,3) (0,2)(3,4) (0,4)(1,3) (0,1)(2,4) (0,3)(1,2)) and a pair counts as converged when
+// |gamma| <= 1e-15 sqrt(alpha beta) - the specification shared with the product.
 inline void svd_jacobi(const double* A, int m, int n, double* U, double* S, double* V) {
   std::vector<double> W(A, A + m * n);
   for (int i = 0; i < n; ++i)
     for (int j = 0; j < n; ++j) V[i * n + j] = (i == j);
-  for (int sweep = 0; sweep < 60; ++sweep) {
-    double off = 0;
+  // round-robin tournament over n players (n odd: one sits out per round)
+  std::vector<std::pair<int, int>> order;
+  if (n == 5) {
+    order = {{1, 4}, {2, 3}, {0, 2}, {3, 4}, {0, 4}, {1, 3}, {0, 1}, {2, 4}, {0, 3}, {1, 2}};
+  } else {
     for (int p = 0; p < n - 1; ++p)
-      for (int q = p + 1; q < n; ++q) {
-        double alpha = 0, beta = 0, gamma = 0;
-        for (int r = 0; r < m; ++r) {
-          alpha += W[r * n + p] * W[r * n + p];
-          beta += W[r * n + q] * W[r * n + q];
-          gamma += W[r * n + p] * W[r * n + q];
-        }
-        if (gamma == 0) continue;
-        off = std::fmax(off, std::fabs(gamma) / std::sqrt(alpha * beta + 1e-300));
-        double zeta = (beta - alpha) / (2 * gamma);
-        double t = (zeta >= 0 ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(1 + zeta * zeta));
-        double c = 1 / std::sqrt(1 + t * t), s = c * t;
-        for (int r = 0; r < m; ++r) {
-          double wp = W[r * n + p], wq = W[r * n + q];
-          W[r * n + p] = c * wp - s * wq;
-          W[r * n + q] = s * wp + c * wq;
-        }
-        for (int r = 0; r < n; ++r) {
-          double vp = V[r * n + p], vq = V[r * n + q];
-          V[r * n + p] = c * vp - s * vq;
-          V[r * n + q] = s * vp + c * vq;
-        }
+      for (int q = p + 1; q < n; ++q) order.push_back({p, q});
+  }
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    bool rotated = false;
+    for (auto pq : order) {
+      const int p = pq.first, q = pq.second;
+      double alpha = 0, beta = 0, gamma = 0;
+      for (int r = 0; r < m; ++r) {
+        alpha += W[r * n + p] * W[r * n + p];
+        beta += W[r * n + q] * W[r * n + q];
+        gamma += W[r * n + p] * W[r * n + q];
       }
-    if (off < 1e-15) break;
+      if (!(gamma * gamma > 1e-30 * (alpha * beta))) continue;
+      rotated = true;
+      const double d = beta - alpha;
+      const double sg = ((d >= 0) == (gamma >= 0) || d == 0) ? 1.0 : -1.0;
+      const double t = sg * (2.0 * std::fabs(gamma)) / (std::fabs(d) + std::sqrt(d * d + 4.0 * gamma * gamma));
+      const double c = 1 / std::sqrt(1 + t * t), s = c * t;
+      for (int r = 0; r < m; ++r) {
+        double wp = W[r * n + p], wq = W[r * n + q];
+        W[r * n + p] = c * wp - s * wq;
+        W[r * n + q] = s * wp + c * wq;
+      }
+      for (int r = 0; r < n; ++r) {
+        double vp = V[r * n + p], vq = V[r * n + q];
+        V[r * n + p] = c * vp - s * vq;
+        V[r * n + q] = s * vp + c * vq;
+      }
+    }
+    if (!rotated) break;
   }
   for (int j = 0; j < n; ++j) {
     double nrm = 0;

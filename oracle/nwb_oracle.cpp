@@ -366,8 +366,17 @@ MaConstraint make_ma(const double* pts, int num_points) {
   ma.pts.assign(pts, pts + (size_t)num_points * 6);
   return ma;
 }
-ServiceParams make_service(const double* sv /*[13] or null*/) {
+ServiceParams make_service(const double* sv /*[13] or null*/, const nwb_params* p = nullptr) {
   ServiceParams sp;
+  if (p) {
+    sp.time_parameterization = p->time_parameterization != 0;
+    for (int j = 0; j < NWB_NJ; ++j) {
+      sp.limits.v_max[j] = p->joint_max_velocity[j];
+      sp.limits.a_max[j] = p->joint_max_acceleration[j];
+    }
+    sp.limits.max_iterations = p->iptp_max_iterations;
+    sp.limits.max_time_change = p->iptp_max_time_change;
+  }
   if (sv) {
     sp.max_samples = (int)sv[0]; sp.max_ik_iterations = (int)sv[1]; sp.max_expand_iterations = (int)sv[2];
     sp.advance_steps = sv[3];
@@ -468,7 +477,7 @@ void nwbo_compute_motion_plan(const nwb_params* p, const double* boxes, int nb, 
                               int n_db, const double* pose6, const double* start, int execute, uint64_t seed,
                               double* goal_config, double* traj, double* tfs, int cap, int32_t* stats) {
   PlanParams pp = make_params(p, boxes, nb);
-  MotionPlanOut o = compute_motion_plan(pp, make_service(service13), db, n_db, pose6, start, execute != 0, seed);
+  MotionPlanOut o = compute_motion_plan(pp, make_service(service13, p), db, n_db, pose6, start, execute != 0, seed);
   if (o.goal.num_found && goal_config) std::memcpy(goal_config, o.goal.rows.data(), sizeof(double) * NWB_NJ);
   int n = put_rows(o.plan.trajectory, traj, cap);
   if (tfs) std::memcpy(tfs, o.plan.time_from_start.data(), sizeof(double) * std::min(n, cap));
@@ -482,7 +491,7 @@ void nwbo_compute_manipulation_plan(const nwb_params* p, const double* boxes, in
                                     int execute, uint64_t seed, double* goal_approach, double* goal_manipulate,
                                     double* traj_a, double* tfs_a, double* traj_m, double* tfs_m, int cap, int32_t* stats) {
   PlanParams pp = make_params(p, boxes, nb);
-  ManipulationPlanOut o = compute_manipulation_plan(pp, make_service(service13), db, n_db, pose6, start, circular != 0, object,
+  ManipulationPlanOut o = compute_manipulation_plan(pp, make_service(service13, p), db, n_db, pose6, start, circular != 0, object,
                                                     execute != 0, seed);
   if (o.goal_approach.num_found && goal_approach) std::memcpy(goal_approach, o.goal_approach.rows.data(), sizeof(double) * NWB_NJ);
   if (o.goal_manipulate.num_found && goal_manipulate) std::memcpy(goal_manipulate, o.goal_manipulate.rows.data(), sizeof(double) * NWB_NJ);
@@ -492,6 +501,20 @@ void nwbo_compute_manipulation_plan(const nwb_params* p, const double* boxes, in
   stats[0] = o.approach.success; stats[1] = o.manipulation.success; stats[2] = o.approach.num_nodes;
   stats[3] = o.manipulation.num_nodes; stats[4] = o.goal_approach.num_found; stats[5] = o.goal_manipulate.num_found;
   stats[6] = na; stats[7] = nm;
+}
+
+// generateTrajectory's time parameterisation (RP:1596-1618); limits taken from nwb_params.
+void nwbo_time_parameterize(const nwb_params* p, const double* positions, int n_points, double* time_from_start) {
+  TimeParamLimits L;
+  for (int j = 0; j < NWB_NJ; ++j) {
+    L.v_max[j] = p->joint_max_velocity[j];
+    L.a_max[j] = p->joint_max_acceleration[j];
+  }
+  L.max_iterations = p->iptp_max_iterations;
+  L.max_time_change = p->iptp_max_time_change;
+  std::vector<double> path(positions, positions + (size_t)n_points * NWB_NJ);
+  std::vector<double> st = time_parameterize(L, path);
+  std::memcpy(time_from_start, st.data(), sizeof(double) * st.size());
 }
 
 }  // extern "C"

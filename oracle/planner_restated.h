@@ -816,6 +816,65 @@ inline GoalResult sample_goal_configs(const PlanParams& pp, uint64_t seed, const
 }
 
 // ---------------------------------------------------------------------------------------------
+// MoveIt trajectory_processing::IterativeParabolicTimeParameterization::computeTimeStamps as called by
+// RRT_Planner::generateTrajectory (RP:1596-1618), followed by the 2 s offset of RP:1614-1618.
+// MoveIt is not vendored in the reference; restated from its published algorithm (Hydro/Indigo vintage:
+// max_iterations 100, max_time_change_per_it 0.01, rounding threshold 0.01, interval growth factor 1.01).
+// PARITY UNPINNED: no shipped file carries time stamps, and the velocity limits come from a URDF that is
+// not in the reference tree.
+struct TimeParamLimits {
+  double v_max[NWB_NJ], a_max[NWB_NJ];
+  int max_iterations = 100;
+  double max_time_change = 0.01;
+};
+inline double iptp_grow(double dq1, double dq2, double dt1, double dt2, double a_max, bool grow_first) {
+  double a = 2.0 * (dq2 / dt2 - dq1 / dt1) / (dt1 + dt2);
+  while (std::fabs(a) > a_max) {
+    a = 2.0 * (dq2 / dt2 - dq1 / dt1) / (dt1 + dt2);
+    if (grow_first) dt1 *= 1.01;
+    else dt2 *= 1.01;
+  }
+  return grow_first ? dt1 : dt2;
+}
+inline std::vector<double> time_parameterize(const TimeParamLimits& L, const std::vector<double>& path) {
+  const int n = (int)(path.size() / NWB_NJ);
+  std::vector<double> stamps(n, 2.0);
+  if (n < 2) return stamps;
+  auto q = [&](int i, int j) { return path[(size_t)i * NWB_NJ + j]; };
+  std::vector<double> dt(n - 1, 0.0);
+  for (int i = 0; i + 1 < n; ++i)                                   // applyVelocityConstraints
+    for (int j = 0; j < NWB_NJ; ++j) dt[i] = std::max(dt[i], std::fabs(q(i + 1, j) - q(i, j)) / L.v_max[j]);
+  int updates, iteration = 0;                                      // applyAccelerationConstraints
+  bool backwards = false;
+  do {
+    updates = 0;
+    ++iteration;
+    for (int j = 0; j < NWB_NJ; ++j)
+      for (int pass = 0; pass < 2; ++pass, backwards = !backwards)
+        for (int i = 0; i + 1 < n; ++i) {
+          const int k = backwards ? n - 1 - i : i;
+          const int prev = k == 0 ? 1 : k - 1, next = k == n - 1 ? n - 2 : k + 1;   // mirrored neighbour at the ends
+          const double d1 = q(k, j) - q(prev, j), d2 = q(next, j) - q(k, j);
+          const int i1 = k == 0 ? 0 : k - 1, i2 = k == n - 1 ? n - 2 : k;           // intervals before / after point k
+          const double t1 = dt[i1], t2 = dt[i2];
+          if (t1 == 0.0 || t2 == 0.0) continue;
+          const double a = 2.0 * (d2 / t2 - d1 / t1) / (t1 + t2);
+          if (std::fabs(a) > L.a_max[j] + 0.01) {
+            if (!backwards) dt[i2] = std::min(t2 + L.max_time_change, iptp_grow(d1, d2, t1, t2, L.a_max[j], false));
+            else dt[i1] = std::min(t1 + L.max_time_change, iptp_grow(d1, d2, t1, t2, L.a_max[j], true));
+            ++updates;
+          }
+        }
+  } while (updates > 0 && iteration < L.max_iterations);
+  double t = 0.0;
+  for (int i = 1; i < n; ++i) {
+    t += dt[i - 1];
+    stamps[i] = t + 2.0;
+  }
+  return stamps;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Service level (NPC:150-870).  Wall-clock outputs (time_goal_config, search_time) are not part of
 // the restatement.  Seeds: goal sampling uses `seed` (approach) and `seed + 1` (manipulation),
 // planning uses `seed + 2` and `seed + 3` - a convention shared with the product.
@@ -826,6 +885,18 @@ struct ServiceParams {                 // NPC:20-33 defaults overridden by plann
   double w_manipulate[3] = {1.0, 0.0, 1.0};
   int shortcut_waypoints = 100, manipulate_waypoints = 4, shortcut_rounds = 500;   // RP:1397-1398, RP:1851
   int num_interp_points = 20;                  // NPC:539,822
+  bool time_parameterization = true;           // RP:1569-1618
+  TimeParamLimits limits;
+  ServiceParams() {
+    // NAO V4 URDF velocity limits in planner joint order, from memory (UNVERIFIED, see include/nwb.h); no
+    // acceleration limits in the URDF -> MoveIt's default 1.0
+    const double v[NWB_NJ] = {4.16174, 6.40239, 6.40239, 6.40239, 4.16174, 8.26797, 7.19407, 8.26797, 7.19407, 24.6229,
+                              8.26797, 7.19407, 8.26797, 7.19407, 24.6229, 4.16174, 4.16174, 6.40239, 6.40239, 6.40239, 4.16174};
+    for (int j = 0; j < NWB_NJ; ++j) {
+      limits.v_max[j] = v[j];
+      limits.a_max[j] = 1.0;
+    }
+  }
 };
 inline void limb_weights(const double* w3, double* w21) {  // NPC:280-306
   for (int i = 0; i < 5; ++i) w21[i] = w3[2];
@@ -864,6 +935,7 @@ inline void finish_path(const PlanParams& pp, const ServiceParams& sp, const Sol
     out.time_from_start.push_back((double)increment);
     increment = articulated ? increment + (float)time_step_manip : increment + 1.0f;
   }
+  if (sp.time_parameterization && !(execute && articulated) && !path.empty()) out.time_from_start = time_parameterize(sp.limits, path);
   out.success = !path.empty();
   out.num_nodes = r.num_nodes;
 }

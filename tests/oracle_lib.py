@@ -355,6 +355,13 @@ class Oracle:
                     goal_approach=ga, goal_manipulate=gm, traj_approach=ta[:na].copy(), tfs_approach=fa[:na].copy(),
                     traj_manipulation=tm[:nm].copy(), tfs_manipulation=fm[:nm].copy())
 
+    def time_parameterize(self, positions, params=None):
+        positions = np.ascontiguousarray(positions, dtype=np.float64).reshape(-1, NJ)
+        p = params or default_params()
+        out = np.empty(len(positions))
+        self.lib.nwbo_time_parameterize(C.byref(p), _ptr(positions), len(positions), _ptr(out))
+        return out
+
     def philox(self, ctr, key):
         ctr = np.asarray(ctr, dtype=np.uint32)
         key = np.asarray(key, dtype=np.uint32)

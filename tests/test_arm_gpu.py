@@ -226,6 +226,17 @@ def test_motion_plan_batch_equals_single_calls(ctx):
     assert n_ok >= 3 and not batch[-1]["success"]
 
 
+def test_time_parameterization_matches_oracle(ctx, oracle):
+    sol = OL.load_dat(OL.GOLDEN / "solutions" / "solution_path_second.dat")
+    for path in (sol, sol[::7], sol[:2], sol[:1]):
+        assert (ctx.time_parameterize(path) == oracle.time_parameterize(path)).all()
+    with nwb.Context(time_parameterization=0) as c:
+        c.set_ds_database(OL.golden_db())
+        r = c.compute_linear_manipulation_plan(POSE_DRAWER[:3], POSE_DRAWER[3:], START, 0.0, 0.10, 20121003)
+        assert np.allclose(r["tfs_manipulation"][:2], [2.0, 2.0 + (0.10 / 0.02) / 22], atol=1e-6)
+        assert np.allclose(np.diff(r["tfs_approach"]), 1.0)
+
+
 def test_services_need_a_database(oracle):
     with nwb.Context() as c:
         with pytest.raises(nwb.NwbError, match="database"):

@@ -203,7 +203,37 @@ def test_scenario_3_linear_manipulation_plan(oracle):
     for k, n in enumerate(tm[::5]):
         pos, z = oracle.right_hand_fk(n)
         assert abs(pos[0] - (0.24 - 0.10 * k / 21)) < 6.5e-3 and abs(pos[1] + 0.065) < 6.5e-3 and abs(pos[2] - 0.30) < 6.5e-3   # 5 mm predicate + ~1 mm chain/solver model offset
-    assert np.allclose(r["tfs_manipulation"][:2], [2.0, 2.0 + (0.10 / 0.02) / 22], atol=1e-6)
+    tfs = r["tfs_manipulation"]
+    assert tfs[0] == 2.0 and (np.diff(tfs) > 0).all() and len(tfs) == len(tm)                    # time-parameterised
+    raw = oracle.compute_manipulation_plan(db, pose, start, 20121003, False, [0.0, 0.10],
+                                           params=OL.default_params(time_parameterization=0))
+    assert np.allclose(raw["tfs_manipulation"][:2], [2.0, 2.0 + (0.10 / 0.02) / 22], atol=1e-6)   # RP:1532-1553 stamps
     assert (tm[0] == r["goal_approach"]).all() and np.abs(tm[-1] - r["goal_manipulate"]).max() < 1e-12
     ta = r["traj_approach"]
     assert (ta[0] == start).all() and np.abs(ta[-1] - r["goal_approach"]).max() < 1e-12 and (len(ta) - 1) % 101 == 0
+
+
+def test_time_parameterization_known_answers(oracle):
+    """IterativeParabolicTimeParameterization as generateTrajectory calls it (RP:1596-1618): one joint moving
+    1 rad between two way-points needs T with 2/T^2 <= a_max + 0.01 (mirrored end points), reached in 0.01 s
+    steps; durations respect the velocity limits; stamps start at 2.0 s and increase."""
+    path = np.zeros((2, 21))
+    path[1, 10] = 1.0
+    t = oracle.time_parameterize(path)
+    T = t[1] - t[0]
+    assert t[0] == 2.0 and np.sqrt(2 / 1.01) <= T <= np.sqrt(2 / 1.01) + 0.02
+    sol = OL.load_dat(OL.GOLDEN / "solutions" / "solution_path_second.dat")
+    t = oracle.time_parameterize(sol)
+    dt = np.diff(t)
+    assert (dt > 0).all()
+    v = np.abs(np.diff(sol, axis=0)) / dt[:, None]
+    assert (v <= np.array(nwb_vmax()) * (1 + 1e-12)).all()
+    # interior accelerations of the parabolic blends are within the limit + rounding threshold once converged
+    a = 2 * (np.diff(sol, axis=0)[1:] / dt[1:, None] - np.diff(sol, axis=0)[:-1] / dt[:-1, None]) / (dt[1:] + dt[:-1])[:, None]
+    assert np.abs(a).max() <= 1.0 + 0.01 + 1e-9
+    assert oracle.time_parameterize(sol[:1])[0] == 2.0
+
+
+def nwb_vmax():
+    from nao_wholebody_planning_b200._abi import NAO_MAX_VELOCITY
+    return NAO_MAX_VELOCITY
