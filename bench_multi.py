@@ -4,6 +4,8 @@
   V3  stable-configuration database generation: sample-index ranges per rank (the Philox counter is the
       GLOBAL sample index, so the accepted set does not depend on the number of GPUs), rows gathered
       and merged in ascending sample index
+  V2  nearest neighbour over ONE big tree (2^24 nodes): node ranges per rank, every rank scans its shard,
+      all_gather of (distance, global index) per query + lexicographic minimum (the one exchange step)
   V4  256 grasp-pose compute_motion_plan requests: round-robin request -> rank, every rank runs its
       share as ONE batched call, results gathered
 
@@ -33,6 +35,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--samples-log2", type=int, default=22)
     ap.add_argument("--check-log2", type=int, default=16, help="size of the partition-independence check")
+    ap.add_argument("--nodes-log2", type=int, default=24, help="nodes of the one big tree of the NN workload")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
     import torch
@@ -100,6 +103,57 @@ def main():
          sharded_equals_unsharded=same, check_samples=small, scaling="strong",
          note="host API per rank (rows come back to the host, are re-uploaded and gathered with NCCL); accepted set identical "
               "to the single-GPU run by construction (global Philox counter)")
+
+    # ---- V2: one big tree, node-range shards ---------------------------------------------------------------------
+    lo_j, hi_j = OL.joint_limits()
+    lo_t, hi_t = torch.tensor(lo_j, device=dev), torch.tensor(hi_j, device=dev)
+    BLK = 1 << 20
+    n_blocks = 1 << max(0, args.nodes_log2 - 20)
+    b0, b1 = sharding.shard_bounds(n_blocks, world)[rank]                 # contiguous blocks of 2^20 nodes per rank
+    tree = nwb.Tree(ctx, max(1, (b1 - b0)) * BLK)
+    for b in range(b0, b1):                                                 # block b is the same whatever the GPU count
+        g = torch.Generator(device=dev)
+        g.manual_seed(20121001 + b)
+        blk = lo_t + (hi_t - lo_t) * torch.rand((BLK, 21), generator=g, device=dev, dtype=torch.float64)
+        torch.cuda.synchronize()
+        tree.add_dev(blk.data_ptr(), BLK)
+        ctx.synchronize()
+    nq = 64
+    db = OL.golden_db()
+    queries = db[np.floor(np.random.default_rng(20121002).random(nq) * (len(db) - 1)).astype(int)]
+    q_dev = torch.from_numpy(queries).to(dev)
+    idx_dev = torch.empty(nq, dtype=torch.int32, device=dev)
+    dist_dev = torch.empty(nq, dtype=torch.float64, device=dev)
+
+    def nn():
+        if b1 > b0:
+            tree.nearest_dev(q_dev.data_ptr(), nq, idx_dev.data_ptr(), dist_dev.data_ptr())
+            ctx.synchronize()
+            gidx = torch.where(idx_dev >= 0, idx_dev.to(torch.int64) + b0 * BLK, idx_dev.to(torch.int64))
+            d = dist_dev
+        else:                                                               # more ranks than blocks: an empty shard
+            gidx = torch.full((nq,), -1, dtype=torch.int64, device=dev)
+            d = torch.full((nq,), 10000.0, dtype=torch.float64, device=dev)
+        if world > 1:
+            return sharding.nn_reduce(d, gidx)
+        return d, gidx
+
+    nn()
+    barrier()
+    reps = 10
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        dmin, imin = nn()
+    barrier()
+    dt = max_over_ranks(time.perf_counter() - t0) / reps
+    total_nodes = n_blocks * BLK
+    emit(op="nn_one_big_tree_sharded", n_gpus=world, nodes=total_nodes, queries=nq, wall_ms_per_batch=1e3 * dt,
+         scan_gbs=84.0 * total_nodes * (nq / 8) / dt / 1e9, digest=int(imin.sum().item()), dist_digest=float(dmin.sum().item()),
+         scaling="strong",
+         note="64 queries (8 share a pass): each rank scans its node range, then all_gather + lexicographic min; host wall "
+              "clock per batch incl. the exchange; the digests (winning global indices / distances) must not depend on the "
+              "number of GPUs")
+    tree.close()
 
     # ---- V4 ---------------------------------------------------------------------------------------------------
     n = 256

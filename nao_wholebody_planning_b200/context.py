@@ -301,7 +301,7 @@ class Context:
 
     @staticmethod
     def _traj(cap):
-        pos, tfs = np.full((cap, NJ), np.nan), np.full(cap, np.nan)
+        pos, tfs = np.empty((cap, NJ)), np.empty(cap)       # rows beyond n_points are never read
         t = _abi.Trajectory(cap, 0, pos.ctypes.data_as(C.POINTER(C.c_double)), tfs.ctypes.data_as(C.POINTER(C.c_double)))
         return t, pos, tfs
 
@@ -318,7 +318,7 @@ class Context:
         self._check(self.lib.nwb_compute_goal_config(self.h, C.byref(req), C.byref(resp), int(seed)), "nwb_compute_goal_config")
         return np.array(resp.wb_goal_config), resp.num_goal_configs_found
 
-    def compute_motion_plan(self, position, direction, wb_start_config, seed, execute_trajectory=False, cap=16384):
+    def compute_motion_plan(self, position, direction, wb_start_config, seed, execute_trajectory=False, cap=4096):
         start = np.ascontiguousarray(wb_start_config, dtype=np.float64)
         req = _abi.MotionPlanRequest(_abi.Point3(*position), _abi.Point3(*direction), start.ctypes.data_as(C.POINTER(C.c_double)),
                                      len(start), int(execute_trajectory))
@@ -330,7 +330,7 @@ class Context:
                     num_nodes_generated=resp.num_nodes_generated, search_time=resp.search_time, trajectory=pos[:n].copy(),
                     time_from_start=tfs[:n].copy())
 
-    def compute_motion_plan_batch(self, positions, directions, wb_start_configs, seeds, execute_trajectory=False, cap=4096):
+    def compute_motion_plan_batch(self, positions, directions, wb_start_configs, seeds, execute_trajectory=False, cap=2048):
         """n compute_motion_plan requests in one call -> list of result dicts (as compute_motion_plan)."""
         positions = np.ascontiguousarray(positions, dtype=np.float64).reshape(-1, 3)
         directions = np.ascontiguousarray(directions, dtype=np.float64).reshape(-1, 3)
@@ -339,8 +339,8 @@ class Context:
         n = len(positions)
         reqs = (_abi.MotionPlanRequest * n)()
         resps = (_abi.MotionPlanResponse * n)()
-        pos = np.full((n, cap, NJ), np.nan)
-        tfs = np.full((n, cap), np.nan)
+        pos = np.empty((n, cap, NJ))                     # rows beyond n_points are never read
+        tfs = np.empty((n, cap))
         pd = C.POINTER(C.c_double)
         for k in range(n):
             reqs[k] = _abi.MotionPlanRequest(_abi.Point3(*positions[k]), _abi.Point3(*directions[k]),
@@ -369,7 +369,7 @@ class Context:
                     tfs_manipulation=tm[:nm].copy())
 
     def compute_linear_manipulation_plan(self, position, direction, wb_start_config, relative_angle, object_translation_length,
-                                         seed, execute_trajectory=False, cap=16384):
+                                         seed, execute_trajectory=False, cap=4096):
         start = np.ascontiguousarray(wb_start_config, dtype=np.float64)
         req = _abi.LinearManipulationRequest(_abi.Point3(*position), _abi.Point3(*direction),
                                              start.ctypes.data_as(C.POINTER(C.c_double)), len(start), float(relative_angle),
@@ -382,7 +382,7 @@ class Context:
         return self._manipulation_result(resp, pa, ta, pm, tm, cap)
 
     def compute_circular_manipulation_plan(self, position, direction, wb_start_config, relative_angle, rotation_radius,
-                                           rotation_angle, clearance_handle, seed, execute_trajectory=False, cap=16384):
+                                           rotation_angle, clearance_handle, seed, execute_trajectory=False, cap=4096):
         start = np.ascontiguousarray(wb_start_config, dtype=np.float64)
         req = _abi.CircularManipulationRequest(_abi.Point3(*position), _abi.Point3(*direction),
                                                start.ctypes.data_as(C.POINTER(C.c_double)), len(start), float(relative_angle),

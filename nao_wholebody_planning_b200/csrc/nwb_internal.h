@@ -85,6 +85,7 @@ struct Ctx {
   void* d_rrt = nullptr; size_t d_rrt_bytes = 0;       // control state / staging of the RRT driver (grow-only)
   int32_t* h_flag = nullptr;                           // pinned word the RRT driver polls
   std::vector<double> ds_db;                           // stable-configuration database of the services (RP:121-191)
+  std::vector<double> h_raw;                           // raw-path staging of the services (kept across calls)
   double last_ms = 0;
   int64_t last_launches = 0;
   int64_t last_nn_passes = 0;        // passes over the node array of the last nearest-neighbour call

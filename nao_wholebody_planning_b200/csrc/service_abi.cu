@@ -342,7 +342,8 @@ int plan_stage(nwb_ctx* ctx, const double* start, const double* goal, const doub
   }
   const nwb_params& P = ctx->params;
   const int cap = 8192;
-  std::vector<double> raw((size_t)cap * NWB_NJ);
+  if (ctx->h_raw.size() < (size_t)cap * NWB_NJ) ctx->h_raw.resize((size_t)cap * NWB_NJ);
+  std::vector<double>& raw = ctx->h_raw;
   nwb_plan_result r;
   const double t0 = now_s();
   int rc = nwb_solve_query_constrained_batch(ctx, start, goal, 1, ctx->ds_db.data(), (int32_t)(ctx->ds_db.size() / NWB_NJ), weights,
