@@ -82,6 +82,7 @@ __device__ __forceinline__ void nn_bulk_g2s(void* dst, const void* src, uint32_t
 
 constexpr int NN_TILE = 512;      // nodes per tile: 21 rows x 2 KB = 43 KB per stage
 constexpr int NN_STAGES = 4;      // 172 KB of shared memory: one persistent CTA per SM
+constexpr int NN_CAND_MAX = 512;  // exact-pass candidates a block lists (a handful per query is typical)
 
 // one pass over the nodes for NN_QT queries; writes one (dist, idx) partial per (query, block).
 // Persistent CTAs (one per SM) stream the 21 SoA rows of their tiles through a 4-stage shared-memory
@@ -99,6 +100,7 @@ nn_scan_kernel(const float* __restrict__ soa, const double* __restrict__ aos, in
   uint64_t* bars = reinterpret_cast<uint64_t*>(nn_smem + sizeof(float) * NN_STAGES * NWB_NJ * NN_TILE);
   __shared__ double qd[QT][NWB_NJ];
   __shared__ float qf[QT][NWB_NJ];
+  __shared__ __align__(16) float2 qn2[NWB_NJ][QT];     // (-q, -q): second operand of the packed subtract
   __shared__ unsigned run_min[QT];                    // running fp32 minimum of the block (float bits, s >= 0)
   __shared__ double red_d[QT][NN_THREADS / 32];
   __shared__ int red_i[QT][NN_THREADS / 32];
@@ -110,6 +112,7 @@ nn_scan_kernel(const float* __restrict__ soa, const double* __restrict__ aos, in
     double v = (q0 + k < nq) ? q[(q0 + k) * NWB_NJ + j] : 0.0;
     qd[k][j] = v;
     qf[k][j] = (float)v;
+    qn2[j][k] = make_float2(-(float)v, -(float)v);
   }
   if (tid < QT) run_min[tid] = 0x7f7fffffu;           // FLT_MAX
   if (tid == 0) {
@@ -150,29 +153,37 @@ nn_scan_kernel(const float* __restrict__ soa, const double* __restrict__ aos, in
     nn_mbar_wait(&bars[stage], phase);
     const float* x = ring + (size_t)stage * NWB_NJ * NN_TILE;
     const int64_t n0 = tile * NN_TILE;
-    float s[QT][2];
+    // A thread owns the node pair (2 tid, 2 tid + 1) of the tile and works on it with packed fp32 pairs
+    // (add.f32x2 / fma.f32x2 -> FADD2 / FFMA2: two nodes per dispatch slot): per joint one 8-byte load of
+    // the pair, then per query one packed subtract of the broadcast (-q, -q) and one packed multiply-add.
+    float2 s2[QT];
 #pragma unroll
-    for (int k = 0; k < QT; ++k) s[k][0] = s[k][1] = 0.f;
+    for (int k = 0; k < QT; ++k) s2[k] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < NWB_NJ; ++j) {
-      const float x0 = x[j * NN_TILE + tid], x1 = x[j * NN_TILE + tid + NN_THREADS];
+      const float2 x2 = *reinterpret_cast<const float2*>(&x[j * NN_TILE + 2 * tid]);
 #pragma unroll
       for (int k = 0; k < QT; ++k) {
-        const float c = qf[k][j];
-        const float d0 = c - x0, d1 = c - x1;
-        s[k][0] = fmaf(d0, d0, s[k][0]);
-        s[k][1] = fmaf(d1, d1, s[k][1]);
+        const float2 d = __fadd2_rn(x2, qn2[j][k]);
+        s2[k] = __ffma2_rn(d, d, s2[k]);
       }
     }
-    const bool live0 = n0 + tid < N, live1 = n0 + tid + NN_THREADS < N;
+    float s[QT][2];
+#pragma unroll
+    for (int k = 0; k < QT; ++k) {
+      s[k][0] = s2[k].x;
+      s[k][1] = s2[k].y;
+    }
+    const bool live0 = n0 + 2 * tid < N, live1 = n0 + 2 * tid + 1 < N;
+    float lo[QT];                                       // the smaller of the thread's two distances per query
 #pragma unroll
     for (int k = 0; k < QT; ++k) {
       if (!live0) s[k][0] = 3.0e38f;
       if (!live1) s[k][1] = 3.0e38f;
-      float m = fminf(s[k][0], s[k][1]);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
-      if ((tid & 31) == 0) atomicMin(&run_min[k], __float_as_uint(m));
+      lo[k] = fminf(s[k][0], s[k][1]);
+      // non-negative floats order like their bit patterns: one REDUX.MIN instead of a shuffle ladder
+      const unsigned wmin = __reduce_min_sync(0xffffffffu, __float_as_uint(lo[k]));
+      if ((tid & 31) == 0) atomicMin(&run_min[k], wmin);
     }
     __syncthreads();                                    // the stage is consumed and run_min is current
     if (tid == 0) {                                     // refill this stage with the tile NN_STAGES rounds ahead
@@ -185,14 +196,16 @@ nn_scan_kernel(const float* __restrict__ soa, const double* __restrict__ aos, in
 #pragma unroll
     for (int k = 0; k < QT; ++k) {
       const float bound = nn_candidate_bound(__uint_as_float(run_min[k]));
+      if (lo[k] <= bound) {                             // rare: at least one of the two nodes is a candidate
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const float v = s[k][u];
-        if (v <= bound) {                               // candidate (nodes arrive in ascending index per thread)
-          const int node = (int)(n0 + tid + u * NN_THREADS);
-          if (v < cs[k][0]) { cs[k][1] = cs[k][0]; ci[k][1] = ci[k][0]; cs[k][0] = v; ci[k][0] = node; }
-          else if (v < cs[k][1]) { cs[k][1] = v; ci[k][1] = node; }
-          else ovf = true;                              // a third candidate: resolved by the exact rescan below
+        for (int u = 0; u < 2; ++u) {
+          const float v = s[k][u];
+          if (v <= bound) {                             // candidate (nodes arrive in ascending index per thread)
+            const int node = (int)(n0 + 2 * tid + u);
+            if (v < cs[k][0]) { cs[k][1] = cs[k][0]; ci[k][1] = ci[k][0]; cs[k][0] = v; ci[k][0] = node; }
+            else if (v < cs[k][1]) { cs[k][1] = v; ci[k][1] = node; }
+            else ovf = true;                            // a third candidate: resolved by the exact rescan below
+          }
         }
       }
     }
@@ -201,14 +214,15 @@ nn_scan_kernel(const float* __restrict__ soa, const double* __restrict__ aos, in
   if (ovf) overflow = 1;
   __syncthreads();
 
-  double best[QT];
-  int besti[QT];
-#pragma unroll
-  for (int k = 0; k < QT; ++k) {
-    best[k] = 10000.0;       // RP:347
-    besti[k] = -1;
-  }
-  auto exact = [&](int k, int64_t node) {               // the reference's arithmetic: RP:361-377
+  // ---- exact pass (the reference's arithmetic, RP:361-377) ------------------------------------------------
+  // Candidates under the final bound go to a shared list, then EVERY candidate gets its own thread: one round
+  // of independent global loads for the whole block instead of a chain of dependent round trips per thread.
+  __shared__ int cand_n;
+  __shared__ int cand_k[NN_CAND_MAX], cand_node[NN_CAND_MAX];
+  __shared__ double cand_d[NN_CAND_MAX];
+  if (tid == 0) cand_n = 0;
+  __syncthreads();
+  auto exact_dist = [&](int k, int64_t node) {
     const double* row = aos + node * NWB_NJ;
     double r[NWB_NJ];
 #pragma unroll
@@ -219,11 +233,11 @@ nn_scan_kernel(const float* __restrict__ soa, const double* __restrict__ aos, in
       double d = __dsub_rn(qd[k][j], r[j]);
       sum = __dadd_rn(sum, __dmul_rn(d, d));            // separately rounded multiply and add
     }
-    double dn = sqrt(sum);
-    if (dn < best[k] || (dn == best[k] && (unsigned)node < (unsigned)besti[k])) {   // first strict minimum in index order
-      best[k] = dn;
-      besti[k] = (int)node;
-    }
+    return sqrt(sum);
+  };
+  auto push = [&](int k, int node) {
+    const int slot = atomicAdd(&cand_n, 1);
+    if (slot < NN_CAND_MAX) { cand_k[slot] = k; cand_node[slot] = node; }
   };
   if (!overflow) {
 #pragma unroll
@@ -231,14 +245,36 @@ nn_scan_kernel(const float* __restrict__ soa, const double* __restrict__ aos, in
       const float bound = nn_candidate_bound(__uint_as_float(run_min[k]));
 #pragma unroll
       for (int u = 0; u < 2; ++u)
-        if (ci[k][u] >= 0 && cs[k][u] <= bound) exact(k, ci[k][u]);
+        if (ci[k][u] >= 0 && cs[k][u] <= bound) push(k, ci[k][u]);
+    }
+  }
+  __syncthreads();
+  const bool list_ok = !overflow && cand_n <= NN_CAND_MAX;
+  if (list_ok)
+    for (int c = tid; c < cand_n; c += NN_THREADS) cand_d[c] = exact_dist(cand_k[c], cand_node[c]);
+  __syncthreads();
+  if (list_ok) {
+    if (tid < QT && q0 + tid < nq) {                    // first strict minimum in index order, 10000.0 / -1 if none (RP:347)
+      double d = 10000.0;
+      int i = -1;
+      for (int c = 0; c < cand_n; ++c)
+        if (cand_k[c] == tid && lex_less(cand_d[c], cand_node[c], d, i) && cand_d[c] < 10000.0) { d = cand_d[c]; i = cand_node[c]; }
+      part_d[(q0 + tid) * gridDim.x + blockIdx.x] = d;
+      part_i[(q0 + tid) * gridDim.x + blockIdx.x] = i;
     }
   } else {
-    // pathological input (three or more near-ties in one thread): rescan this block's tiles from global
-    // memory and take the exact path for every node under the final bound
+    // pathological input (three or more near-ties in one thread, or a flood of candidates): rescan this block's
+    // tiles from global memory and take the exact path for every node under the final bound
+    double best[QT];
+    int besti[QT];
+#pragma unroll
+    for (int k = 0; k < QT; ++k) {
+      best[k] = 10000.0;
+      besti[k] = -1;
+    }
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x)
       for (int u = 0; u < 2; ++u) {
-        const int64_t node = tile * NN_TILE + tid + u * NN_THREADS;
+        const int64_t node = tile * NN_TILE + 2 * tid + u;
         if (node >= N) continue;
         for (int k = 0; k < QT; ++k) {
           float sv = 0.f;
@@ -246,33 +282,34 @@ nn_scan_kernel(const float* __restrict__ soa, const double* __restrict__ aos, in
             float d = qf[k][j] - soa[(int64_t)j * cap + node];
             sv = fmaf(d, d, sv);
           }
-          if (sv <= nn_candidate_bound(__uint_as_float(run_min[k]))) exact(k, node);
+          if (sv <= nn_candidate_bound(__uint_as_float(run_min[k]))) {
+            const double dn = exact_dist(k, node);
+            if (dn < best[k] || (dn == best[k] && (unsigned)node < (unsigned)besti[k])) { best[k] = dn; besti[k] = (int)node; }
+          }
         }
       }
-  }
-  // block reduction per query
-  const int lane = tid & 31, warp = tid >> 5;
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int k = 0; k < QT; ++k) {
+      double d = best[k];
+      int i = besti[k];
 #pragma unroll
-  for (int k = 0; k < QT; ++k) {
-    double d = best[k];
-    int i = besti[k];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      double d2 = __shfl_xor_sync(0xffffffffu, d, o);
-      int i2 = __shfl_xor_sync(0xffffffffu, i, o);
-      if (lex_less(d2, i2, d, i)) { d = d2; i = i2; }
+      for (int o = 16; o > 0; o >>= 1) {
+        double d2 = __shfl_xor_sync(0xffffffffu, d, o);
+        int i2 = __shfl_xor_sync(0xffffffffu, i, o);
+        if (lex_less(d2, i2, d, i)) { d = d2; i = i2; }
+      }
+      if (lane == 0) { red_d[k][warp] = d; red_i[k][warp] = i; }
     }
-    if (lane == 0) { red_d[k][warp] = d; red_i[k][warp] = i; }
-  }
-  __syncthreads();
-  if (tid < QT) {
-    double d = red_d[tid][0];
-    int i = red_i[tid][0];
-    for (int w = 1; w < NN_THREADS / 32; ++w)
-      if (lex_less(red_d[tid][w], red_i[tid][w], d, i)) { d = red_d[tid][w]; i = red_i[tid][w]; }
-    if (q0 + tid < nq) {
-      part_d[(q0 + tid) * gridDim.x + blockIdx.x] = d;
-      part_i[(q0 + tid) * gridDim.x + blockIdx.x] = i;
+    __syncthreads();
+    if (tid < QT) {
+      double d = red_d[tid][0];
+      int i = red_i[tid][0];
+      for (int w = 1; w < NN_THREADS / 32; ++w)
+        if (lex_less(red_d[tid][w], red_i[tid][w], d, i)) { d = red_d[tid][w]; i = red_i[tid][w]; }
+      if (q0 + tid < nq) {
+        part_d[(q0 + tid) * gridDim.x + blockIdx.x] = d;
+        part_i[(q0 + tid) * gridDim.x + blockIdx.x] = i;
+      }
     }
   }
   // grid reduction without a second launch: the last block to finish this query group folds the partials
@@ -418,11 +455,13 @@ int nn_launch(nwb_tree* t, const double* q_dev, int64_t nq, int32_t* idx_dev, do
   if (!configured) {
     TREE_CUDA(t, cudaFuncSetAttribute(nn_scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNnSmem));
     TREE_CUDA(t, cudaFuncSetAttribute(nn_scan_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNnSmem));
+    TREE_CUDA(t, cudaFuncSetAttribute(nn_scan_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNnSmem));
     configured = true;
   }
   TREE_CUDA(t, cudaEventRecord(t->ctx->ev0, s));
-  // one query (the RRT loop): minimum arithmetic per tile; batches: 8 queries share each pass over the nodes
-  const int QT = nq == 1 ? 1 : 8;
+  // one query (the RRT loop): minimum arithmetic per tile; batches: 8 or 16 queries share each pass over the nodes
+  static const int qt_batch = getenv("NWB_NN_QT") ? atoi(getenv("NWB_NN_QT")) : 16;
+  const int QT = nq == 1 ? 1 : (nq <= 8 || qt_batch == 8 ? 8 : 16);
   const int64_t qtiles = (nq + QT - 1) / QT;
   for (int64_t y0 = 0; y0 < qtiles; y0 += 65535) {       // gridDim.y limit
     const int64_t ny = std::min<int64_t>(65535, qtiles - y0);
@@ -431,10 +470,14 @@ int nn_launch(nwb_tree* t, const double* q_dev, int64_t nq, int32_t* idx_dev, do
       nn_scan_kernel<1><<<dim3(nb, (unsigned)ny), NN_THREADS, kNnSmem, s>>>(t->soa, t->aos, t->cap, t->size, q_dev + qoff * NWB_NJ,
                                                                             nq - qoff, t->part_d + qoff * nb, t->part_i + qoff * nb,
                                                                             t->tickets + y0, idx_dev + qoff, dist_dev ? dist_dev + qoff : nullptr);
-    else
+    else if (QT == 8)
       nn_scan_kernel<8><<<dim3(nb, (unsigned)ny), NN_THREADS, kNnSmem, s>>>(t->soa, t->aos, t->cap, t->size, q_dev + qoff * NWB_NJ,
                                                                             nq - qoff, t->part_d + qoff * nb, t->part_i + qoff * nb,
                                                                             t->tickets + y0, idx_dev + qoff, dist_dev ? dist_dev + qoff : nullptr);
+    else
+      nn_scan_kernel<16><<<dim3(nb, (unsigned)ny), NN_THREADS, kNnSmem, s>>>(t->soa, t->aos, t->cap, t->size, q_dev + qoff * NWB_NJ,
+                                                                             nq - qoff, t->part_d + qoff * nb, t->part_i + qoff * nb,
+                                                                             t->tickets + y0, idx_dev + qoff, dist_dev ? dist_dev + qoff : nullptr);
   }
   TREE_CUDA(t, cudaGetLastError());
   TREE_CUDA(t, cudaEventRecord(t->ctx->ev1, s));

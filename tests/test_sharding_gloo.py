@@ -68,7 +68,20 @@ def _worker(rank, world, port, tmp):
     i_ref, d_ref = orc.nearest_neighbour(nodes, queries)
     assert (i.numpy() == i_ref).all() and (d.numpy() == d_ref).all()
 
-    # 4. ragged gather with an empty rank
+    # 4. planning requests: round-robin request -> rank, objects gathered and re-ordered == the serial loop
+    poses = [[0.24, -0.065, 0.30, 0, -1, 0], [0.14, -0.065, 0.30, 0, -1, 0], [0.6, 0.0, 0.3, 0, -1, 0]]
+    mine = sharding.round_robin(len(poses))
+    part = [(k, orc.sample_goal_configs(20121100 + k, poses[k], max_samples=400)) for k in mine]
+    parts = [None] * world
+    dist.all_gather_object(parts, part)
+    merged = sorted((x for p in parts for x in p), key=lambda x: x[0])
+    assert [k for k, _ in merged] == [0, 1, 2]
+    for k, (rows, erg, idx, drawn) in merged:
+        r_ref, e_ref, i_ref, d_ref = orc.sample_goal_configs(20121100 + k, poses[k], max_samples=400)
+        assert (rows == r_ref).all() and (idx == i_ref).all() and drawn == d_ref
+    assert len(merged[2][1][0]) == 0                      # the unreachable pose finds no goal configuration
+
+    # 5. ragged gather with an empty rank
     local = torch.arange(5 if rank == 0 else 0, dtype=torch.float64).reshape(-1, 1)
     out, counts = sharding.all_gather_ragged(local)
     assert counts == [5, 0] and out.shape == (5, 1)
