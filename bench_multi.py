@@ -104,6 +104,56 @@ def main():
          note="host API per rank (rows come back to the host, are re-uploaded and gathered with NCCL); accepted set identical "
               "to the single-GPU run by construction (global Philox counter)")
 
+    # ---- V3, device-resident with the gather fused into the sampler: every rank appends its accepted rows straight
+    # into rank 0's database (peer-mapped memory, system-scope atomic slot counter) - no host round trip, no collective
+    total = 1 << args.samples_log2
+    cap = total // 6
+    blk_bytes = 256 + 8 * cap + 8 * 21 * cap                               # counter | index [cap] | rows [cap][21]
+    root_ptr = ctx.dev_alloc(blk_bytes) if rank == 0 else None
+    if world > 1:
+        h = [ctx.ipc_export(root_ptr) if rank == 0 else None]
+        dist.broadcast_object_list(h, src=0)
+        base = root_ptr if rank == 0 else ctx.ipc_import(h[0])
+    else:
+        base = root_ptr
+    p_cnt, p_idx, p_rows = base, base + 256, base + 256 + 8 * cap
+
+    class _Raw:
+        def __init__(self, ptr, shape, typestr):
+            self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (int(ptr), False), "version": 3}
+
+    def generate_fused(n_total):
+        if rank == 0:
+            torch.as_tensor(_Raw(p_cnt, (1,), "<u8"), device=dev).zero_()
+            torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        lo, hi = sharding.shard_bounds(n_total, world)[rank]
+        ctx._check(ctx.lib.nwb_sample_stable_configs_dev(ctx.h, seed, lo, hi - lo, 5, p_rows, p_idx, cap, p_cnt, None),
+                   "nwb_sample_stable_configs_dev")
+        ctx.synchronize()
+        barrier()
+        return max_over_ranks(time.perf_counter() - t0)
+
+    generate_fused(total >> 2)
+    dt = generate_fused(total)
+    fused_ok, n_acc = None, None
+    if rank == 0:
+        n_acc = int(torch.as_tensor(_Raw(p_cnt, (1,), "<u8"), device=dev).cpu().numpy().view(np.uint64)[0])
+        g_idx = torch.as_tensor(_Raw(p_idx, (n_acc,), "<u8"), device=dev).cpu().numpy().view(np.uint64).astype(np.int64)
+        g_rows = torch.as_tensor(_Raw(p_rows, (n_acc, 21), "<f8"), device=dev).cpu().numpy()
+        order = np.argsort(g_idx, kind="stable")
+        fused_ok = bool(len(idx) == n_acc and (g_idx[order] == idx.cpu().numpy()).all() and (g_rows[order] == rows.cpu().numpy()).all())
+    emit(op="db_generation_fused_gather", n_gpus=world, samples=total, accepted=n_acc, wall_s=dt, samples_per_s=total / dt,
+         equals_host_path=fused_ok, scaling="strong",
+         note="device-resident: all ranks append into rank 0's arrays through peer-mapped memory inside the sampler kernel "
+              "(system-scope atomic slot counter); rows compared with the host-API run above after sorting by sample index")
+    if world > 1 and rank != 0:
+        ctx.ipc_close(base)
+    barrier()
+    if rank == 0:
+        ctx.dev_free(root_ptr)
+
     # ---- V2: one big tree, node-range shards ---------------------------------------------------------------------
     lo_j, hi_j = OL.joint_limits()
     lo_t, hi_t = torch.tensor(lo_j, device=dev), torch.tensor(hi_j, device=dev)

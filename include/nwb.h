@@ -232,7 +232,9 @@ NWB_API int nwb_sample_stable_configs(nwb_ctx* ctx, uint64_t seed, uint64_t firs
                                       double* rows_out, int64_t cap, int64_t* n_out, uint64_t* index_out,
                                       uint8_t* stage_out);
 /* Device-resident form for throughput runs: rows in arrival order (not sorted), *n_out_dev is an
- * unsigned 64-bit counter the caller zeroes. */
+ * unsigned 64-bit counter the caller zeroes.  rows_dev / index_dev / n_out_dev may be PEER memory (another
+ * rank's nwb_dev_alloc block opened with nwb_ipc_import): the counter is bumped with a system-scope atomic,
+ * so all ranks of a sharded generation can append into one rank's database - no separate gather. */
 NWB_API int nwb_sample_stable_configs_dev(nwb_ctx* ctx, uint64_t seed, uint64_t first, int64_t count,
                                           int32_t max_ik_iter, double* rows_dev, uint64_t* index_dev, int64_t cap,
                                           unsigned long long* n_out_dev, uint8_t* stage_dev);

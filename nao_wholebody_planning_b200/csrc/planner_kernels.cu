@@ -289,7 +289,9 @@ sample_kernel(const __grid_constant__ PlanConst pc, const __grid_constant__ Vali
     stage = feasible ? 2 : 1;
     const bool keep = (pc.quirks & NWB_QUIRK_DB_KEEPS_INFEASIBLE) ? !feasible : feasible;   // SCG:452-456
     if (keep) {
-      unsigned long long slot = atomicAdd(n_out, 1ull);
+      // system scope: the output arrays may live on ANOTHER GPU (peer-mapped through nwb_ipc_import): every rank of
+      // a sharded generation then appends into one rank's database directly over NVLink - the gather is the store
+      unsigned long long slot = atomicAdd_system(n_out, 1ull);
       if ((int64_t)slot < cap) {
         for (int j = 0; j < NWB_NJ; ++j) rows[slot * NWB_NJ + j] = q[j];
         row_index[slot] = i;

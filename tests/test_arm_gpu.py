@@ -172,6 +172,23 @@ def test_linear_manipulation_plan_service_matches_oracle(ctx, oracle):
         assert r["time_goal_config_approach"] > 0 and r["search_time_manipulate"] > 0
 
 
+def test_linear_manipulation_plan_for_execution(ctx, oracle):
+    """setTrajectoryMode(true) (NPC:362): the articulated plan is returned raw - one way-point per tree node,
+    stamps 2.0 + i * time_steps_manipulation (RP:1417, 1547-1575), no time parameterisation - and the approach
+    plan keeps only the shortcut way-points (RP:1941-1945)."""
+    db = OL.golden_db()
+    r = ctx.compute_linear_manipulation_plan(POSE_DRAWER[:3], POSE_DRAWER[3:], START, 0.0, 0.10, 20121003, execute_trajectory=True)
+    o = oracle.compute_manipulation_plan(db, POSE_DRAWER, START, 20121003, False, [0.0, 0.10], execute=True)
+    assert r["success_approach"] and r["success_manipulation"] and o["success_manipulation"]
+    assert r["traj_manipulation"].shape == o["traj_manipulation"].shape == (22, 21)
+    assert np.abs(r["traj_manipulation"] - o["traj_manipulation"]).max() < 1e-8
+    step = np.float32(np.float32(0.10) / np.float32(0.02)) / np.float32(22)
+    assert np.allclose(np.diff(r["tfs_manipulation"]), step, atol=1e-6) and r["tfs_manipulation"][0] == 2.0
+    assert (r["tfs_manipulation"] == o["tfs_manipulation"]).all()
+    assert r["traj_approach"].shape == o["traj_approach"].shape and len(r["traj_approach"]) < 20
+    assert np.abs(r["traj_approach"] - o["traj_approach"]).max() < 1e-8
+
+
 def test_circular_manipulation_plan_service_matches_oracle(ctx, oracle):
     """Door opening (SIM:551-561)."""
     db = OL.golden_db()
