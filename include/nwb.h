@@ -331,13 +331,17 @@ NWB_API int nwb_generate_ds_database(nwb_ctx* ctx, const nwb_generate_ds_configs
  * RShoulderRoll, RElbowYaw, RElbowRoll, RWristYaw, each in (-pi, pi]), counts [n].  Solved in closed
  * form on the device (csrc/arm_core.cuh); the solution SET equals the reference solver's. */
 NWB_API int nwb_arm_ik_batch(nwb_ctx* ctx, const double* targets, int64_t n, double* solutions, int32_t* counts);
-/* ConstraintKinematics::computeRightArmIK, generated-solver branch (NCK:224-506 with getHipPose
- * NCK:512-544) for n whole-body rows q [n][21]: hip pose from the right leg, hand pose -> torso frame,
- * all solutions, strict joint limits, the one with the largest compute_ergonomics_index (NCK:612-659).
- * ok [n], arm [n][5], ergonomics [n].  A zero direction (the KDL position-only branch NCK:291-372, which
- * no shipped caller reaches) is rejected with NWB_E_INVALID. */
-NWB_API int nwb_goal_arm_ik_batch(nwb_ctx* ctx, const double* q, int64_t n, const double* hand_pose6, uint8_t* ok, double* arm,
-                                  double* ergonomics);
+/* ConstraintKinematics::computeRightArmIK (NCK:224-506 with getHipPose NCK:512-544) for n whole-body rows
+ * q [n][21]: hip pose from the right leg, then
+ *   direction != 0 (NCK:374-506): hand pose -> the solver's torso frame, all solutions, strict joint limits, the one
+ *     with the largest compute_ergonomics_index (NCK:612-659);
+ *   direction == (0,0,0) exactly (NCK:291-372): KDL NR(100, 1e-3) on the right-arm chain towards
+ *     Frame(position in the hip frame) from up to 5 random seeds inside the arm limits; row i draws its seeds
+ *     from Philox(seed; counter = first_index + i, stream 3) in place of the class's clock-seeded rng_;
+ *     ergonomics stays 0.
+ * ok [n], arm [n][5], ergonomics [n]. */
+NWB_API int nwb_goal_arm_ik_batch(nwb_ctx* ctx, const double* q, int64_t n, const double* hand_pose6, uint64_t seed,
+                                  uint64_t first_index, uint8_t* ok, double* arm, double* ergonomics);
 /* ArticulatedObjectConstraints::computeDrawerTrajectoryPoints (kind 0, AOC:105-122) /
  * computeDoorTrajectoryPoints (kind 1, AOC:126-189; door4 = {rotation_radius, rotation_angle [deg],
  * relative_angle [deg], clearance_handle} as NPC:816-820): out [num_interp_points + 2][6]. */

@@ -216,7 +216,7 @@ def _declare(lib):
         "nwb_load_ds_database": (C.c_int, [C.c_char_p, vp, i64, C.POINTER(i64)]),
         "nwb_generate_ds_database": (C.c_int, [vp, C.POINTER(GenDsRequest), C.POINTER(GenDsResponse), C.c_char_p, C.c_uint64]),
         "nwb_arm_ik_batch": (C.c_int, [vp, vp, i64, vp, vp]),
-        "nwb_goal_arm_ik_batch": (C.c_int, [vp, vp, i64, vp, vp, vp, vp]),
+        "nwb_goal_arm_ik_batch": (C.c_int, [vp, vp, i64, vp, C.c_uint64, C.c_uint64, vp, vp, vp]),
         "nwb_hand_trajectory": (C.c_int, [i32, vp, vp, i32, vp, vp]),
         "nwb_enforce_ma_batch": (C.c_int, [vp, vp, i32, i32, vp, vp, vp, i64, vp, vp]),
         "nwb_goal_sample_batch": (C.c_int, [vp, C.c_uint64, C.c_uint64, i64, vp, i32, vp, vp, vp]),

@@ -242,13 +242,14 @@ class Context:
         self._check(self.lib.nwb_arm_ik_batch(self.h, _p(t), len(t), _p(sols), _p(cnt)), "nwb_arm_ik_batch")
         return sols, cnt
 
-    def computeRightArmIK(self, q, hand_pose6):
+    def computeRightArmIK(self, q, hand_pose6, seed=0, first_index=0):
         """ConstraintKinematics::computeRightArmIK (nao_constraint_kinematics.cpp:224) for whole-body rows."""
         q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, NJ)
         pose = np.ascontiguousarray(hand_pose6, dtype=np.float64)
         n = len(q)
         ok, arm, erg = np.empty(n, np.uint8), np.empty((n, 5)), np.empty(n)
-        self._check(self.lib.nwb_goal_arm_ik_batch(self.h, _p(q), n, _p(pose), _p(ok), _p(arm), _p(erg)), "nwb_goal_arm_ik_batch")
+        self._check(self.lib.nwb_goal_arm_ik_batch(self.h, _p(q), n, _p(pose), int(seed), int(first_index), _p(ok), _p(arm),
+                                                   _p(erg)), "nwb_goal_arm_ik_batch")
         return ok, arm, erg
 
     def hand_trajectory(self, kind, start6, goal6, num_interp_points=20, door4=None):

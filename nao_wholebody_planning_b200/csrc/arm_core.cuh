@@ -179,10 +179,85 @@ __device__ __forceinline__ double ergonomics_index(const double* q5) {
   return __dmul_rn(q5[0], fabs(__dsub_rn(sum_fw, sum_bw)));
 }
 
-// computeRightArmIK, generated-solver branch: the in-limits solution with the largest ergonomics
-// index (> 0.0).  hip = right-leg FK of the sample.
-__device__ __forceinline__ bool goal_right_arm_ik(const DFrame& hip, const double* pose6, const double* mn5, const double* mx5,
-                                                  double* out5, double* ergonomics) {
+// ChainIkSolverPos_NR::CartToJnt on the right-arm chain (base = hip frame), as the position-only branch of
+// computeRightArmIK constructs it (nao_constraint_kinematics.cpp:311-317).  Same iteration as left_leg_ik_nr.
+__device__ __forceinline__ bool right_arm_ik_nr(const DFrame& target, double* q /*[5] in: seed*/, int maxiter, double eps,
+                                                double pinv_eps) {
+  int i;
+  for (i = 0; i < maxiter; ++i) {
+    DFrame f;
+    dframe_identity(f);
+    D3 o[5], a[5];
+    right_arm_fk(q, f, o, a);
+    double tw[6];
+    frame_diff(f, target, tw);
+    double W[6][5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      D3 v = cross(a[k], f.p - o[k]);
+      W[0][k] = v.x; W[1][k] = v.y; W[2][k] = v.z;
+      W[3][k] = a[k].x; W[4][k] = a[k].y; W[5][k] = a[k].z;
+    }
+    double dq[5];
+    pinv_solve(W, tw, pinv_eps, dq);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) q[k] += dq[k];
+    bool conv = true;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) conv = conv && (eps > tw[k]) && (tw[k] > -eps);
+    if (conv) break;
+  }
+  return i != maxiter;
+}
+
+constexpr uint32_t kStreamArmSeed = 3;
+
+// computeRightArmIK (nao_constraint_kinematics.cpp:224-506).  hip = right-leg FK of the sample.
+// Direction != 0: the generated solver's solutions, strict limits, largest ergonomics index (> 0.0).
+// Direction == (0,0,0) exactly (nao_constraint_kinematics.cpp:291-372): KDL NR towards Frame(position in the hip
+// frame) - identity rotation - from up to 5 random seeds inside the arm limits (stream kStreamArmSeed of the
+// sample, slot 5 * attempt + joint); the ergonomics index stays untouched (0).
+__device__ __forceinline__ bool goal_right_arm_ik(const DFrame& hip, const double* pose6, const PlanConst& pc, uint64_t seed,
+                                                  uint64_t sample_index, double* out5, double* ergonomics) {
+  const double* mn5 = pc.jmin + 10;
+  const double* mx5 = pc.jmax + 10;
+  *ergonomics = 0.0;
+  if (pose6[3] == 0.0 && pose6[4] == 0.0 && pose6[5] == 0.0) {
+    DFrame target;
+    dframe_identity(target);
+    double o[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const double r0 = hip.r[i], r1 = hip.r[3 + i], r2 = hip.r[6 + i];
+      double tmp = __dsub_rn(__dsub_rn(__dmul_rn(-r0, hip.p.x), __dmul_rn(r1, hip.p.y)), __dmul_rn(r2, hip.p.z));
+      double tmp2 = __dadd_rn(__dadd_rn(__dmul_rn(r0, pose6[0]), __dmul_rn(r1, pose6[1])), __dmul_rn(r2, pose6[2]));
+      o[i] = __dadd_rn(tmp, tmp2);
+    }
+    target.p = d3(o[0], o[1], o[2]);
+    bool ok = false;
+#pragma unroll 1
+    for (int attempt = 0; attempt < 5 && !ok; ++attempt) {
+      double q[5];
+#pragma unroll 1
+      for (int blk = 0; blk < 2; ++blk) {                  // slots 5 * attempt .. 5 * attempt + 4 span at most two counter blocks
+        const int first_slot = 5 * attempt, b = first_slot / 4 + blk;
+        uint32_t r[4];
+        philox4x32_10((uint32_t)sample_index, (uint32_t)(sample_index >> 32), (uint32_t)b, kStreamArmSeed, (uint32_t)seed,
+                      (uint32_t)(seed >> 32), r);
+        for (int l = 0; l < 4; ++l) {
+          const int j = 4 * b + l - first_slot;
+          if (j >= 0 && j < 5) q[j] = __dadd_rn(__dmul_rn(mx5[j] - mn5[j], u01(r[l])), mn5[j]);
+        }
+      }
+      // slots 5a..5a+4 may need a third block only if they straddle two boundaries: 5 consecutive slots never do
+      if (right_arm_ik_nr(target, q, pc.ik_maxiter, pc.ik_eps, pc.pinv_eps) && limits_ok(q, mn5, mx5, 5)) {
+        ok = true;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) out5[j] = q[j];
+      }
+    }
+    return ok;
+  }
   D3 pos, dir;
   hand_target_in_torso(hip, pose6, pos, dir);
   double best = 0.0;

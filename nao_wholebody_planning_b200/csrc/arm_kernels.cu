@@ -36,8 +36,9 @@ arm_ik_kernel(const double* __restrict__ targets /*[n][6]*/, int64_t n, double* 
 }
 
 __global__ void __launch_bounds__(128)
-goal_arm_ik_kernel(const __grid_constant__ PlanConst pc, const __grid_constant__ Pose6 pose, const double* __restrict__ q, int64_t n,
-                   uint8_t* __restrict__ ok, double* __restrict__ arm, double* __restrict__ erg) {
+goal_arm_ik_kernel(const __grid_constant__ PlanConst pc, const __grid_constant__ Pose6 pose, uint64_t seed, uint64_t first_index,
+                   const double* __restrict__ q, int64_t n, uint8_t* __restrict__ ok, double* __restrict__ arm,
+                   double* __restrict__ erg) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double rl[5];
@@ -45,7 +46,7 @@ goal_arm_ik_kernel(const __grid_constant__ PlanConst pc, const __grid_constant__
   DFrame hip;
   right_leg_fk(rl, hip);
   double a[5] = {0, 0, 0, 0, 0}, e = 0.0;
-  ok[i] = goal_right_arm_ik(hip, pose.v, pc.jmin + 10, pc.jmax + 10, a, &e);
+  ok[i] = goal_right_arm_ik(hip, pose.v, pc, seed, first_index + (uint64_t)i, a, &e);
   for (int m = 0; m < 5; ++m) arm[i * 5 + m] = a[m];
   erg[i] = e;
 }
@@ -114,7 +115,7 @@ goal_sample_kernel(const __grid_constant__ PlanConst pc, const __grid_constant__
   // The reference solves the left leg first and the right arm second (SCG:318-347); a sample survives
   // only if BOTH succeed and neither consumes random numbers, so the order is free: the closed-form arm
   // solve (cheap, rejects most samples) runs first and only its survivors pay for the NR iteration.
-  bool solved = max_ik_iter > 0 && goal_right_arm_ik(hip, pose, pc.jmin + 10, pc.jmax + 10, arm, &e);
+  bool solved = max_ik_iter > 0 && goal_right_arm_ik(hip, pose, pc, seed, i, arm, &e);
   if (solved) {
     desired_left_leg_pose(hip, target);
     for (int m = 0; m < 5; ++m) ll[m] = -rl[m];          // NCK:150 seed; further attempts repeat the same arithmetic (quirk C5)
@@ -182,12 +183,12 @@ cudaError_t launch_arm_ik(const double* targets, int64_t n, double* sols, int32_
   arm_ik_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(targets, n, sols, counts);
   return cudaGetLastError();
 }
-cudaError_t launch_goal_arm_ik(const PlanConst& pc, const double* pose6, const double* q, int64_t n, uint8_t* ok, double* arm,
-                               double* erg, cudaStream_t s) {
+cudaError_t launch_goal_arm_ik(const PlanConst& pc, const double* pose6, uint64_t seed, uint64_t first_index, const double* q,
+                               int64_t n, uint8_t* ok, double* arm, double* erg, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
   Pose6 p;
   for (int j = 0; j < 6; ++j) p.v[j] = pose6[j];
-  goal_arm_ik_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(pc, p, q, n, ok, arm, erg);
+  goal_arm_ik_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(pc, p, seed, first_index, q, n, ok, arm, erg);
   return cudaGetLastError();
 }
 cudaError_t launch_enforce_ma(const PlanConst& pc, const double* pts_dev, int n_pts, int start_tree, const int32_t* near_hand,

@@ -151,8 +151,8 @@ cudaError_t launch_sample(const PlanConst& pc, const ValidityTables& tab, bool s
 
 // right-arm kernels (arm_kernels.cu)
 cudaError_t launch_arm_ik(const double* targets, int64_t n, double* sols, int32_t* counts, cudaStream_t s);
-cudaError_t launch_goal_arm_ik(const PlanConst& pc, const double* pose6, const double* q, int64_t n, uint8_t* ok, double* arm,
-                               double* erg, cudaStream_t s);
+cudaError_t launch_goal_arm_ik(const PlanConst& pc, const double* pose6, uint64_t seed, uint64_t first_index, const double* q,
+                               int64_t n, uint8_t* ok, double* arm, double* erg, cudaStream_t s);
 cudaError_t launch_enforce_ma(const PlanConst& pc, const double* pts_dev, int n_pts, int start_tree, const int32_t* near_hand,
                               const double* q_near, const double* q_ds, int64_t n, double* q_out, int32_t* status, cudaStream_t s);
 // nq requests (poses_dev [nq][6], seeds_dev [nq]) x count sample indices; compacted outputs are per request:

@@ -76,8 +76,6 @@ struct Scratch {
   T* at(size_t o) const { return reinterpret_cast<T*>(static_cast<char*>(ctx->d_plan) + o); }
 };
 
-bool zero_direction(const double* pose6) { return pose6[3] == 0.0 && pose6[4] == 0.0 && pose6[5] == 0.0; }   // NCK:291
-
 // the goal files keep 6 significant digits: `ofstream << double` (SCG:409-417), re-read with strtod (SCG:540-560)
 double through_text(double v) {
   char buf[64];
@@ -139,10 +137,7 @@ void finish_goal_set(const std::vector<double>& rows, const std::vector<double>&
 // not time) and per request the six accepted rows with the lowest sample index are kept.
 int sample_goals_batch(nwb_ctx* ctx, int nq, const uint64_t* seeds, const double* poses, int max_samples, int max_ik_iter,
                        GoalSet* out) {
-  for (int k = 0; k < nq; ++k) {
-    out[k] = GoalSet();
-    if (zero_direction(poses + 6 * k)) return bad(ctx, "hand direction (0,0,0): the position-only KDL branch (NCK:291-372) is not supported");
-  }
+  for (int k = 0; k < nq; ++k) out[k] = GoalSet();
   if (max_samples <= 0 || nq <= 0) return NWB_OK;
   S_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
@@ -584,11 +579,10 @@ int nwb_arm_ik_batch(nwb_ctx* ctx, const double* targets, int64_t n, double* sol
   return NWB_OK;
 }
 
-int nwb_goal_arm_ik_batch(nwb_ctx* ctx, const double* q, int64_t n, const double* hand_pose6, uint8_t* ok, double* arm,
-                          double* ergonomics) {
+int nwb_goal_arm_ik_batch(nwb_ctx* ctx, const double* q, int64_t n, const double* hand_pose6, uint64_t seed, uint64_t first_index,
+                          uint8_t* ok, double* arm, double* ergonomics) {
   if (!ctx) return NWB_E_INVALID;
   if (n < 0 || !hand_pose6 || (n > 0 && (!q || !ok || !arm || !ergonomics))) return bad(ctx, "nwb_goal_arm_ik_batch: bad argument");
-  if (zero_direction(hand_pose6)) return bad(ctx, "hand direction (0,0,0): the position-only KDL branch (NCK:291-372) is not supported");
   if (n == 0) return NWB_OK;
   S_CUDA(ctx, cudaSetDevice(ctx->device));
   Scratch A(ctx);
@@ -599,7 +593,8 @@ int nwb_goal_arm_ik_batch(nwb_ctx* ctx, const double* q, int64_t n, const double
   PlanConst pc;
   make_plan_const(ctx, nullptr, ctx->params.planner_step_factor, pc);
   S_CUDA(ctx, cudaMemcpyAsync(A.at<double>(o_q), q, sizeof(double) * NWB_NJ * n, cudaMemcpyHostToDevice, s));
-  S_CUDA(ctx, launch_goal_arm_ik(pc, hand_pose6, A.at<double>(o_q), n, A.at<uint8_t>(o_ok), A.at<double>(o_a), A.at<double>(o_e), s));
+  S_CUDA(ctx, launch_goal_arm_ik(pc, hand_pose6, seed, first_index, A.at<double>(o_q), n, A.at<uint8_t>(o_ok), A.at<double>(o_a),
+                                 A.at<double>(o_e), s));
   S_CUDA(ctx, cudaMemcpyAsync(ok, A.at<uint8_t>(o_ok), n, cudaMemcpyDeviceToHost, s));
   S_CUDA(ctx, cudaMemcpyAsync(arm, A.at<double>(o_a), sizeof(double) * 5 * n, cudaMemcpyDeviceToHost, s));
   S_CUDA(ctx, cudaMemcpyAsync(ergonomics, A.at<double>(o_e), sizeof(double) * n, cudaMemcpyDeviceToHost, s));
@@ -651,7 +646,6 @@ int nwb_goal_sample_batch(nwb_ctx* ctx, uint64_t seed, uint64_t first, int64_t c
                           uint8_t* stage, double* ergonomics, double* rows) {
   if (!ctx) return NWB_E_INVALID;
   if (count < 0 || !hand_pose6 || (count > 0 && !stage)) return bad(ctx, "nwb_goal_sample_batch: bad argument");
-  if (zero_direction(hand_pose6)) return bad(ctx, "hand direction (0,0,0): the position-only KDL branch (NCK:291-372) is not supported");
   if (count == 0) return NWB_OK;
   S_CUDA(ctx, cudaSetDevice(ctx->device));
   Scratch A(ctx);

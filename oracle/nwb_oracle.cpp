@@ -416,14 +416,15 @@ void nwbo_right_hand_fk(const double* q21, double* pos, double* zaxis) {
   zaxis[0] = h.M(0, 2); zaxis[1] = h.M(1, 2); zaxis[2] = h.M(2, 2);
 }
 // computeRightArmIK (NCK:224-506) for whole-body rows: ok[i], arm[i][5], ergonomics[i].
-void nwbo_goal_right_arm_ik_batch(const double* q /*[n][21]*/, int64_t n, const double* pose6, uint8_t* ok, double* arm,
-                                  double* ergonomics) {
+void nwbo_goal_right_arm_ik_batch(const nwb_params* p, const double* q /*[n][21]*/, int64_t n, const double* pose6, uint64_t seed,
+                                  uint64_t first_index, uint8_t* ok, double* arm, double* ergonomics) {
+  PlanParams pp = make_params(p, nullptr, 0);
   for (int64_t i = 0; i < n; ++i) {
     double rleg[5];
     for (int k = 0; k < 5; ++k) rleg[k] = -q[i * NWB_NJ + k];
     Frame hip = kdlr::fk(chains().right_leg, rleg);
     double e = 0, a[5] = {0, 0, 0, 0, 0};
-    ok[i] = goal_right_arm_ik(hip, pose6, nwbm::kJointMin + 10, nwbm::kJointMax + 10, a, &e);
+    ok[i] = goal_right_arm_ik(pp, hip, pose6, nwbm::kJointMin + 10, nwbm::kJointMax + 10, seed, first_index + (uint64_t)i, a, &e);
     for (int k = 0; k < 5; ++k) arm[i * 5 + k] = a[k];
     ergonomics[i] = e;
   }

@@ -38,7 +38,7 @@ inline void philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t
   }
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
-constexpr uint32_t kStreamSampler = 1, kStreamPlanner = 2;
+constexpr uint32_t kStreamSampler = 1, kStreamPlanner = 2, kStreamArmSeed = 3;
 inline double u01(uint32_t x) { return ((double)x + 0.5) * (1.0 / 4294967296.0); }
 // uniform number `slot` of item `index` in stream `stream`
 inline double stream_uniform(uint64_t seed, uint32_t stream, uint64_t index, uint32_t slot) {
@@ -710,13 +710,44 @@ inline double ergonomics_index(const double* arm5) {
   return arm5[0] * det_jac;
 }
 
-// ConstraintKinematics::computeRightArmIK, generated-solver branch (NCK:374-506): among the
-// solutions inside the strict limits keep the one with the LARGEST ergonomics index, starting from
-// 0.0 - a posture with RShoulderPitch <= 0 can therefore never be chosen (quirk C16).
-// (The position-only KDL branch NCK:291-372, taken when the direction is exactly (0,0,0), is not
-// restated: no shipped caller reaches it.)
-inline bool goal_right_arm_ik(const Frame& hip, const double* pose6, const double* mn5, const double* mx5,
-                              double* out5, double* ergonomics) {
+// ConstraintKinematics::computeRightArmIK (NCK:224-506).
+// Generated-solver branch (NCK:374-506): among the solutions inside the strict limits keep the one with the
+// LARGEST ergonomics index, starting from 0.0 - a posture with RShoulderPitch <= 0 can therefore never be
+// chosen (quirk C16).
+// Position-only branch (NCK:291-372), taken when the requested direction is exactly (0,0,0): KDL NR on the
+// right-arm chain towards Frame(position in the HIP frame) - identity rotation, so the hand orientation is
+// constrained after all - from up to 5 random seeds inside the arm limits; the ergonomics index is left
+// untouched.  The seeds come from stream kStreamArmSeed of the sample (slot 5 * attempt + joint).
+inline bool goal_right_arm_ik(const PlanParams& pp, const Frame& hip, const double* pose6, const double* mn5,
+                              const double* mx5, uint64_t seed, uint64_t sample_index, double* out5, double* ergonomics) {
+  if (pose6[3] == 0.0 && pose6[4] == 0.0 && pose6[5] == 0.0) {
+    kdlr::Rot R = kdlr::transpose(hip.M);
+    Frame target;
+    double ph[3];
+    for (int i = 0; i < 3; ++i) {
+      double tmp = -R(i, 0) * hip.p.x - R(i, 1) * hip.p.y - R(i, 2) * hip.p.z;
+      double tmp2 = R(i, 0) * pose6[0] + R(i, 1) * pose6[1] + R(i, 2) * pose6[2];
+      ph[i] = tmp + tmp2;
+    }
+    target.p = {ph[0], ph[1], ph[2]};
+    int rc = -3;
+    bool valid = false;
+    double q_init[5], q_out[5];
+    for (int iter = 0; iter < 5; ++iter) {                                // NCK:329 max_ik_iter = 5
+      for (int i = 0; i < 5; ++i)
+        q_init[i] = (mx5[i] - mn5[i]) * stream_uniform(seed, kStreamArmSeed, sample_index, (uint32_t)(5 * iter + i)) + mn5[i];
+      rc = kdlr::ik_pos_nr(chains().right_arm, q_init, target, q_out, pp.ik_maxiter, pp.ik_eps, pp.pinv_eps);
+      if (rc >= 0) {
+        valid = check_joint_limits(q_out, mn5, mx5, 5);
+        if (valid) break;
+      }
+    }
+    if (rc >= 0 && valid) {
+      for (int i = 0; i < 5; ++i) out5[i] = q_out[i];
+      return true;
+    }
+    return false;
+  }
   double pos[3], dir[3], sols[8 * 5];
   hand_target_in_torso(hip, pose6, pos, dir);
   int n = arm5d_ik(pos, dir, sols);
@@ -754,7 +785,7 @@ inline int goal_sample(const PlanParams& pp, uint64_t seed, uint64_t i, const do
   for (int k = 0; k < 5; ++k) rleg[k] = -q[k];
   if (!left_leg_ik_sampler(pp, rleg, nwbm::kJointMin + 16, nwbm::kJointMax + 16, max_ik_iter, lleg)) return 0;
   Frame hip = kdlr::fk(chains().right_leg, rleg);
-  if (!goal_right_arm_ik(hip, pose6, nwbm::kJointMin + 10, nwbm::kJointMax + 10, rarm, ergonomics)) return 0;
+  if (!goal_right_arm_ik(pp, hip, pose6, nwbm::kJointMin + 10, nwbm::kJointMax + 10, seed, i, rarm, ergonomics)) return 0;
   for (int k = 0; k < 5; ++k) q[16 + k] = lleg[k];
   for (int k = 0; k < 5; ++k) q[10 + k] = rarm[k];
   return is_feasible(pp.eval, q, nullptr, nullptr) ? 2 : 1;

@@ -261,12 +261,14 @@ class Oracle:
         self.lib.nwbo_right_hand_fk(_ptr(q), _ptr(pos), _ptr(z))
         return pos, z
 
-    def goal_right_arm_ik(self, q, pose6):
+    def goal_right_arm_ik(self, q, pose6, seed=0, first_index=0, params=None):
         q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, NJ)
         pose6 = np.ascontiguousarray(pose6, dtype=np.float64)
+        p = params or default_params()
         n = len(q)
         ok, arm, erg = np.empty(n, np.uint8), np.empty((n, 5)), np.empty(n)
-        self.lib.nwbo_goal_right_arm_ik_batch(_ptr(q), C.c_int64(n), _ptr(pose6), _ptr(ok), _ptr(arm), _ptr(erg))
+        self.lib.nwbo_goal_right_arm_ik_batch(C.byref(p), _ptr(q), C.c_int64(n), _ptr(pose6), C.c_uint64(seed),
+                                              C.c_uint64(first_index), _ptr(ok), _ptr(arm), _ptr(erg))
         return ok, arm, erg
 
     def enforce_ma(self, pts, start_tree, near_hand_index, q_near, q_ds):

@@ -63,8 +63,29 @@ def test_goal_arm_ik_matches_oracle_and_shipped_goal_file(ctx, oracle):
         m = ok == 1
         assert np.abs(arm[m] - oarm[m]).max() < 1e-9
         assert np.abs(erg[m] - oerg[m]).max() < 1e-12 * max(1.0, np.abs(oerg).max()) + 1e-15
-    with pytest.raises(nwb.NwbError, match="direction"):
-        ctx.computeRightArmIK(db[:2], [0.2, 0, 0.2, 0, 0, 0])
+
+
+def test_position_only_arm_ik_branch_matches_oracle(ctx, oracle):
+    """NCK:291-372: a hand direction of exactly (0,0,0) selects KDL NR on the arm chain towards Frame(position) -
+    identity rotation, so it almost never succeeds; statuses and solutions must match the oracle, the seeds come
+    from the injected stream."""
+    db = OL.golden_db()
+    rows = db[:300].copy()
+    # give some rows a target they can reach: hand pose of the row itself, orientation forced to identity
+    for i in range(0, 300, 3):
+        rows[i, 10:15] = [0.3, -0.2, -1.2, 0.04, -0.37]
+    pose = [0.2, -0.1, 0.25, 0, 0, 0]
+    ok, arm, erg = ctx.computeRightArmIK(rows, pose, seed=7, first_index=100)
+    ook, oarm, oerg = oracle.goal_right_arm_ik(rows, pose, seed=7, first_index=100)
+    assert (ok == ook).all() and (erg == 0).all() and (oerg == 0).all()
+    if ok.any():
+        assert np.abs(arm[ok == 1] - oarm[ok == 1]).max() < 1e-8
+    # through the sampler: no goal configuration, no error
+    rows6, e6, idx6, drawn = ctx.sample_goal_configs(3, pose, max_samples=600)
+    orows6, _, oidx6, odrawn = oracle.sample_goal_configs(3, pose, max_samples=600)
+    assert len(rows6) == len(orows6) and drawn == odrawn
+    r = ctx.compute_motion_plan(pose[:3], pose[3:], START, 1)
+    assert r["success"] in (False, True)
 
 
 def test_hand_trajectories_match_oracle(ctx, oracle):
