@@ -137,6 +137,10 @@ struct PlanConst;
 // ma_pts: [nq][n_pts][6] hand trajectory per query (device) or nullptr = no articulation constraint
 cudaError_t launch_connect_forest(const PlanConst& pc, const ValidityTables& tab, bool static_pairs, ForestView F, RrtState S,
                                   int nq, const double* ma_pts, int n_pts, cudaStream_t s);
+// the whole solveQuery loop of nq queries in one launch (one warp per query, queries finish independently)
+cudaError_t launch_rrt_persistent(const PlanConst& pc, const ValidityTables& tab, bool static_pairs, ForestView F, RrtState S,
+                                  const double* db, int n_db, const uint64_t* seeds, int max_iter, int nq, const double* ma_pts,
+                                  int n_pts, cudaStream_t s);
 cudaError_t launch_steer_project(const PlanConst& pc, const double* q_near, const double* q_target, int64_t n, double* q_out,
                                  int32_t* status, int32_t* ds_status, int32_t* iters, cudaStream_t s);
 cudaError_t launch_connect(const PlanConst& pc, const ValidityTables& tab, bool static_pairs, const double* q_start,

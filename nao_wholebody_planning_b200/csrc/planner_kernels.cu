@@ -179,6 +179,208 @@ connect_forest_kernel(const __grid_constant__ PlanConst pc, const __grid_constan
   S.swap[k] ^= 1;                                // trees swap every iteration regardless of outcome (RP:1125-1192)
 }
 
+// ---- the whole RRT-Connect query in ONE launch: one warp per query -------------------------------------------------------
+// The lock-step driver above pays 7-8 launches per iteration and makes every query wait for the slowest
+// one.  Here a warp owns a query from setStartGoalConfigs' trees to the connecting node: the nearest-
+// neighbour scans use all 32 lanes, the serial steps (steer, projections, validity, the connect walk)
+// run on lane 0 with exactly the device functions of the kernels above, so trees, iteration counts and
+// bridge nodes are the same as the lock-step path's (and the oracle's).  Queries finish independently.
+__device__ __forceinline__ bool lex_less_di(double da, int ia, double db, int ib) {
+  return (da < db) || (da == db && (unsigned)ia < (unsigned)ib);
+}
+
+// findNearestNeighbour (RP:336-419) over tree t (n nodes) for the query in shared memory; every lane returns the winner
+__device__ __forceinline__ int warp_nearest(const ForestView& F, int t, int n, const double* qd, const float* qf, int lane) {
+  const float* soa = F.soa + (size_t)t * NWB_NJ * F.cap;
+  const double* aos = F.aos + (size_t)t * F.cap * NWB_NJ;
+  double best = 10000.0;
+  int besti = -1;
+  float thr = 3.0e38f;
+  for (int node = lane; node < n; node += 32) {
+    float sf = 0.f;
+#pragma unroll
+    for (int j = 0; j < NWB_NJ; ++j) {
+      float d = qf[j] - soa[(size_t)j * F.cap + node];
+      sf = fmaf(d, d, sf);
+    }
+    if (sf <= thr) {
+      double sum = 0.0;
+      const double* row = aos + (size_t)node * NWB_NJ;
+      for (int j = 0; j < NWB_NJ; ++j) {
+        double d = __dsub_rn(qd[j], row[j]);
+        sum = __dadd_rn(sum, __dmul_rn(d, d));
+      }
+      double dn = sqrt(sum);
+      if (dn < best) { best = dn; besti = node; }
+      thr = __double2float_ru((best * best + 1.2e-5 * best + 1e-10) * (1.0 + 1e-6));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double d2 = __shfl_xor_sync(0xffffffffu, best, o);
+    int i2 = __shfl_xor_sync(0xffffffffu, besti, o);
+    if (lex_less_di(d2, i2, best, besti)) { best = d2; besti = i2; }
+  }
+  return besti;
+}
+
+template <bool STATIC>
+__global__ void __launch_bounds__(32)
+rrt_persistent_kernel(const __grid_constant__ PlanConst pc, const __grid_constant__ ValidityTables tab, ForestView F, RrtState S,
+                      const double* __restrict__ db, int n_db, const uint64_t* __restrict__ seeds, int max_iter, int nq,
+                      const double* __restrict__ ma_pts, int n_pts) {
+  const int k = blockIdx.x;
+  const int lane = threadIdx.x;
+  if (k >= nq || !S.active[k]) return;
+  __shared__ double qd[NWB_NJ];          // current query of the nearest-neighbour scan (q_rand, then q_connect)
+  __shared__ float qf[NWB_NJ];
+  const MaView ma{ma_pts ? ma_pts + (size_t)k * n_pts * 6 : nullptr, n_pts};
+  const uint64_t seed = seeds[k];
+  int size[2] = {F.size[2 * k], F.size[2 * k + 1]};      // kept in registers of every lane
+  int swap = 0, done = 0, success = 0, connector = 0, bridge = 0, it = 0;
+  for (; it < max_iter && !done; ++it) {
+    // getRandomStableConfig (RP:316-332) with the injected stream
+    uint32_t r[4];
+    philox4x32_10((uint32_t)it, 0u, 0u, kStreamPlanner, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    const double u = u01(r[0]);
+    const int row = (pc.quirks & NWB_QUIRK_DB_INDEX_FLOOR) ? (int)floor(0.0 + (double)(n_db - 1 - 0) * u) : (int)floor((double)n_db * u);
+    const int ta = 2 * k + swap, tb = 2 * k + 1 - swap;
+    if (lane < NWB_NJ) {
+      const double v = db[(size_t)row * NWB_NJ + lane];
+      qd[lane] = v;
+      qf[lane] = (float)v;
+    }
+    __syncwarp();
+    // ---- extendTree (RP:787-884)
+    const int idx_a = warp_nearest(F, ta, size[ta & 1], qd, qf, lane);
+    int walking = 0, connect_hand = 0;
+    if (lane == 0) {
+      double near[NWB_NJ], tgt[NWB_NJ], q[NWB_NJ];
+      const double* nrow = F.aos + ((size_t)ta * F.cap + idx_a) * NWB_NJ;
+      for (int j = 0; j < NWB_NJ; ++j) {
+        near[j] = nrow[j];
+        tgt[j] = qd[j];
+      }
+      int st = generate_q_new(near, tgt, pc, q);
+      const int ds = enforce_ds_constraints(q, pc, nullptr);
+      if (ds == NWB_TRAPPED) st = NWB_TRAPPED;
+      else if (ds == NWB_ADVANCED) st = NWB_ADVANCED;
+      const bool start_tree = (ta & 1) == 0;
+      int near_hand = 0;
+      if (st != NWB_TRAPPED && ma.pts) {                  // enforce_MA_Constraints (RP:829-837)
+        near_hand = F.hand[(size_t)ta * F.cap + idx_a];
+        const int mas = enforce_ma_constraints(ma, start_tree, near_hand, near, q, pc);
+        if (mas == NWB_TRAPPED) st = NWB_TRAPPED;
+        else if (mas == NWB_ADVANCED) st = NWB_ADVANCED;
+      }
+      if (st != NWB_TRAPPED) {
+        ValidityResult<float> v = eval_one<false, STATIC>(tab, q);
+        if (!v.hit && v.stable) {
+          const int base = size[ta & 1];
+          if (base >= F.cap) {
+            atomicExch(S.overflow, 1);
+            done = 2;
+          } else {                                        // addConfigtoTree (RP:749-783)
+            for (int j = 0; j < NWB_NJ; ++j) {
+              F.aos[((size_t)ta * F.cap + base) * NWB_NJ + j] = q[j];
+              F.soa[(size_t)ta * NWB_NJ * F.cap + (size_t)j * F.cap + base] = (float)q[j];
+              qd[j] = q[j];                               // q_connect of this iteration's connectTree
+              qf[j] = (float)q[j];
+            }
+            F.pred[(size_t)ta * F.cap + base] = idx_a;
+            if (ma.pts) {
+              connect_hand = next_hand_index(ma, start_tree, near_hand);
+              F.hand[(size_t)ta * F.cap + base] = connect_hand;
+            }
+            walking = 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+    walking = __shfl_sync(0xffffffffu, walking, 0);
+    done = __shfl_sync(0xffffffffu, done, 0);
+    if (walking) size[ta & 1] += 1;
+    if (walking && !done) {
+      // ---- connectTree (RP:890-1034)
+      const int idx_b = warp_nearest(F, tb, size[tb & 1], qd, qf, lane);
+      int added = 0;
+      if (lane == 0) {
+        const bool start_tree = (tb & 1) == 0;
+        float* soa = F.soa + (size_t)tb * NWB_NJ * F.cap;
+        double* aos = F.aos + (size_t)tb * F.cap * NWB_NJ;
+        int32_t* pred = F.pred + (size_t)tb * F.cap;
+        int32_t* hand = ma.pts ? F.hand + (size_t)tb * F.cap : nullptr;
+        int sz = size[tb & 1];
+        double cur[NWB_NJ], tgt[NWB_NJ], q[NWB_NJ];
+        for (int j = 0; j < NWB_NJ; ++j) {
+          cur[j] = aos[(size_t)idx_b * NWB_NJ + j];
+          tgt[j] = qd[j];
+        }
+        int cur_idx = idx_b, state = NWB_ADVANCED, cur_hand = 0;
+        if (ma.pts) {
+          cur_hand = hand[cur_idx];
+          if ((start_tree && cur_hand > connect_hand) || (!start_tree && cur_hand < connect_hand)) state = NWB_TRAPPED;   // RP:917-922
+        }
+        while (state == NWB_ADVANCED) {
+          state = generate_q_new(cur, tgt, pc, q);
+          const int ds = enforce_ds_constraints(q, pc, nullptr);
+          if (ds == NWB_TRAPPED) { state = NWB_TRAPPED; break; }
+          if (ds == NWB_ADVANCED) state = NWB_ADVANCED;
+          if (ma.pts) {                                   // RP:951-972
+            const int mas = enforce_ma_constraints(ma, start_tree, cur_hand, cur, q, pc);
+            if (mas == NWB_TRAPPED) { state = NWB_TRAPPED; break; }
+            if (mas == NWB_ADVANCED) state = NWB_ADVANCED;
+            if (cur_hand == connect_hand && state != NWB_REACHED) { state = NWB_TRAPPED; break; }
+          }
+          ValidityResult<float> v = eval_one<false, STATIC>(tab, q);
+          if (v.hit || !v.stable) { state = NWB_TRAPPED; break; }
+          if (sz >= F.cap) {
+            atomicExch(S.overflow, 1);
+            state = -1;
+            break;
+          }
+          for (int j = 0; j < NWB_NJ; ++j) {
+            aos[(size_t)sz * NWB_NJ + j] = q[j];
+            soa[(size_t)j * F.cap + sz] = (float)q[j];
+          }
+          pred[sz] = cur_idx;
+          const int new_hand = ma.pts ? next_hand_index(ma, start_tree, cur_hand) : 0;
+          if (ma.pts) hand[sz] = new_hand;
+          if (state == NWB_REACHED) {
+            bridge = cur_idx;                             // RP:1000-1001
+          } else {
+            cur_idx = sz;                                 // RP:1004
+            cur_hand = new_hand;
+            for (int j = 0; j < NWB_NJ; ++j) cur[j] = q[j];
+          }
+          ++sz;
+          ++added;
+        }
+        if (state == NWB_REACHED || state == -1) {
+          success = state == NWB_REACHED;
+          connector = swap ? 2 : 1;
+          done = 1;
+        }
+      }
+      __syncwarp();
+      added = __shfl_sync(0xffffffffu, added, 0);
+      done = __shfl_sync(0xffffffffu, done, 0);
+      size[tb & 1] += added;
+    }
+    swap ^= 1;                                            // RP:1125-1192: every iteration, whatever the outcome
+  }
+  if (lane == 0) {
+    F.size[2 * k] = size[0];
+    F.size[2 * k + 1] = size[1];
+    S.iterations[k] = it;
+    S.success[k] = success;
+    S.connector[k] = connector;
+    S.bridge[k] = bridge;
+    S.active[k] = 0;
+  }
+}
+
 // ---- edge check: (edge, way-point) -> collision-only validity ------------------------------------------
 // One way-point per thread, 256 consecutive (edge, way-point) slots per block.  The end points of the
 // few edges a block touches are staged in shared memory once (start + step width per joint, fp64 as
@@ -325,6 +527,15 @@ cudaError_t launch_connect_forest(const PlanConst& pc, const ValidityTables& tab
   unsigned blocks = (unsigned)((nq + 31) / 32);
   if (static_pairs) connect_forest_kernel<true><<<blocks, 32, 0, s>>>(pc, tab, F, S, nq, ma_pts, n_pts);
   else connect_forest_kernel<false><<<blocks, 32, 0, s>>>(pc, tab, F, S, nq, ma_pts, n_pts);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_rrt_persistent(const PlanConst& pc, const ValidityTables& tab, bool static_pairs, ForestView F, RrtState S,
+                                  const double* db, int n_db, const uint64_t* seeds, int max_iter, int nq, const double* ma_pts,
+                                  int n_pts, cudaStream_t s) {
+  if (nq <= 0) return cudaSuccess;
+  if (static_pairs) rrt_persistent_kernel<true><<<nq, 32, 0, s>>>(pc, tab, F, S, db, n_db, seeds, max_iter, nq, ma_pts, n_pts);
+  else rrt_persistent_kernel<false><<<nq, 32, 0, s>>>(pc, tab, F, S, db, n_db, seeds, max_iter, nq, ma_pts, n_pts);
   return cudaGetLastError();
 }
 

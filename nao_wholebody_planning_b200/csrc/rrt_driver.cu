@@ -1,4 +1,4 @@
-// rrt_driver.cu - host RRT-Connect driver over the batched device operators.
+// rrt_driver.cu - host side of the RRT-Connect driver (device loop: rrt_persistent_kernel in planner_kernels.cu).
 //
 // Replaces RRT_Planner::setStartGoalConfigs / solveQuery / extendTree / connectTree /
 // addConfigtoTree / writePath (rrt_connect_planner/src/rrt_planner.cpp:227-302, 1039-1212, 787-884,
@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -191,6 +192,45 @@ __global__ void forest_root_hand_kernel(ForestView F, int n_trees, int n_pts) {
   if (t < n_trees) F.hand[(size_t)t * F.cap] = (t & 1) ? n_pts - 1 : 0;
 }
 
+// writePath, path extraction part (RP:1303-1392), on the device.  Pass 1 (rows == nullptr): length of the start-
+// and goal-tree branches of every solved query.  Pass 2: the way-points, start root ... bridge | bridge ... goal
+// root, packed at offset[k].  One warp per query; the predecessor walk is serial, the row copies use the lanes.
+__global__ void __launch_bounds__(32)
+rrt_path_kernel(ForestView F, const int32_t* __restrict__ success, const int32_t* __restrict__ connector,
+                const int32_t* __restrict__ bridge, int nq, int32_t* __restrict__ lens /*[nq][2]*/,
+                const int64_t* __restrict__ offset, double* __restrict__ rows) {
+  const int k = blockIdx.x, lane = threadIdx.x;
+  if (k >= nq || !success[k]) return;
+  const int ts = 2 * k, tg = 2 * k + 1;
+  int idx_s, idx_g;
+  if (connector[k] == 1) { idx_s = F.size[ts] - 1; idx_g = bridge[k]; }       // RP:1317-1327
+  else { idx_s = bridge[k]; idx_g = F.size[tg] - 1; }
+  const int32_t* pred_s = F.pred + (size_t)ts * F.cap;
+  const int32_t* pred_g = F.pred + (size_t)tg * F.cap;
+  if (!rows) {
+    if (lane == 0) {
+      int ls = 1, lg = 1;
+      for (int i = idx_s; i > 0; i = pred_s[i]) ++ls;
+      for (int i = idx_g; i > 0; i = pred_g[i]) ++lg;
+      lens[2 * k] = ls;
+      lens[2 * k + 1] = lg;
+    }
+    return;
+  }
+  const int ls = lens[2 * k], lg = lens[2 * k + 1];
+  double* out = rows + offset[k] * NWB_NJ;
+  int i = idx_s;
+  for (int pos = ls - 1; pos >= 0; --pos) {                                    // start branch, reversed into place
+    if (lane < NWB_NJ) out[(size_t)pos * NWB_NJ + lane] = F.aos[((size_t)ts * F.cap + i) * NWB_NJ + lane];
+    i = pred_s[i];
+  }
+  i = idx_g;
+  for (int pos = 0; pos < lg; ++pos) {                                         // goal branch as walked
+    if (lane < NWB_NJ) out[(size_t)(ls + pos) * NWB_NJ + lane] = F.aos[((size_t)tg * F.cap + i) * NWB_NJ + lane];
+    i = pred_g[i];
+  }
+}
+
 }  // namespace nwb
 
 using namespace nwb;
@@ -331,7 +371,19 @@ static int solve_impl(nwb_ctx* ctx, const double* starts, const double* goals, i
   R_CUDA(ctx, cudaGetLastError());
   ++launches;
 
-  // ---- solveQuery main loop (RP:1067-1198): no host synchronisation inside an iteration -----------------
+  // ---- solveQuery main loop (RP:1067-1198) ---------------------------------------------------------------------------
+  // Default: ONE launch, one warp per query, queries finish independently (rrt_persistent_kernel).
+  // NWB_RRT_LOCKSTEP=1 selects the earlier driver: every iteration = 7-8 kernels over all still-active queries.
+  static const bool lockstep = getenv("NWB_RRT_LOCKSTEP") != nullptr;
+  if (!lockstep) {
+    cudaError_t e = launch_rrt_persistent(pc, ctx->tab_group, sp, F, S, d_db, n_db, d_seeds, max_iter, Q, d_ma, P, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) {
+      ctx->err = std::string("nwb_solve_query_batch: ") + cudaGetErrorString(e);
+      return NWB_E_CUDA;
+    }
+    ++launches;
+  } else {
   if (!ctx->h_flag) R_CUDA(ctx, cudaMallocHost(&ctx->h_flag, 64));
   int32_t* h_flag = ctx->h_flag;                               // pinned: remaining active queries
   *h_flag = n_active;
@@ -364,6 +416,7 @@ static int solve_impl(nwb_ctx* ctx, const double* starts, const double* goals, i
       }
     }
   }
+  }
 
   int32_t overflow = 0;
   std::vector<int32_t> sizes(T), h_iter(Q), h_succ(Q), h_conn(Q), h_bridge(Q);
@@ -375,9 +428,7 @@ static int solve_impl(nwb_ctx* ctx, const double* starts, const double* goals, i
   R_CUDA(ctx, cudaMemcpyAsync(h_bridge.data(), S.bridge, sizeof(int32_t) * Q, cudaMemcpyDeviceToHost, s));
   R_CUDA(ctx, cudaStreamSynchronize(s));
 
-  // ---- writePath, path extraction part (RP:1303-1392) -------------------------------------------------------
-  std::vector<double> cfg;
-  std::vector<int32_t> pred;
+  // ---- writePath, path extraction part (RP:1303-1392): on the device, two synchronisations in total --------------
   for (int k = 0; k < Q; ++k) {
     nwb_plan_result& r = results[k];
     r.iterations = h_iter[k];
@@ -388,32 +439,45 @@ static int solve_impl(nwb_ctx* ctx, const double* starts, const double* goals, i
     r.nodes_goal = sizes[2 * k + 1];
     r.num_nodes_generated = r.success ? r.nodes_start + r.nodes_goal : 0;   // RP:1045: stays 0 unless a path is found
     r.raw_path_len = 0;
-    if (!r.success) continue;
-    int idx_s, idx_g;
-    if (r.connector == 1) { idx_s = r.nodes_start - 1; idx_g = r.bridge_other; }
-    else { idx_s = r.bridge_other; idx_g = r.nodes_goal - 1; }
-    std::vector<std::vector<double>> path;
-    for (int side = 0; side < 2; ++side) {
-      const int t = 2 * k + side, n = sizes[t];
-      cfg.resize((size_t)n * NWB_NJ);
-      pred.resize(n);
-      R_CUDA(ctx, cudaMemcpyAsync(cfg.data(), F.aos + (size_t)t * C * NWB_NJ, sizeof(double) * NWB_NJ * n, cudaMemcpyDeviceToHost, s));
-      R_CUDA(ctx, cudaMemcpyAsync(pred.data(), F.pred + (size_t)t * C, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s));
-      R_CUDA(ctx, cudaStreamSynchronize(s));
-      std::vector<std::vector<double>> branch;
-      int i = side == 0 ? idx_s : idx_g;
-      while (i > 0) {
-        branch.emplace_back(cfg.begin() + (size_t)i * NWB_NJ, cfg.begin() + (size_t)(i + 1) * NWB_NJ);
-        i = pred[i];
-      }
-      branch.emplace_back(cfg.begin(), cfg.begin() + NWB_NJ);
-      if (side == 0) path.assign(branch.rbegin(), branch.rend());        // root ... bridge
-      else path.insert(path.end(), branch.begin(), branch.end());        // bridge ... goal root
+  }
+  {
+    int32_t* d_lens = reinterpret_cast<int32_t*>(M + o_cnt);                  // [Q][2] (the root-insertion counts are spent)
+    R_CUDA(ctx, cudaMemsetAsync(d_lens, 0, sizeof(int32_t) * T, s));
+    rrt_path_kernel<<<Q, 32, 0, s>>>(F, S.success, S.connector, S.bridge, Q, d_lens, nullptr, nullptr);
+    std::vector<int32_t> lens(T);
+    R_CUDA(ctx, cudaMemcpyAsync(lens.data(), d_lens, sizeof(int32_t) * T, cudaMemcpyDeviceToHost, s));
+    R_CUDA(ctx, cudaStreamSynchronize(s));
+    ++launches;
+    std::vector<int64_t> offs(Q);
+    int64_t total = 0;
+    for (int k = 0; k < Q; ++k) {
+      offs[k] = total;
+      results[k].raw_path_len = lens[2 * k] + lens[2 * k + 1];
+      total += results[k].raw_path_len;
     }
-    r.raw_path_len = (int32_t)path.size();
-    if (raw_paths)
-      for (int i = 0; i < std::min<int>(r.raw_path_len, raw_path_capacity); ++i)
-        std::memcpy(raw_paths + ((size_t)k * raw_path_capacity + i) * NWB_NJ, path[i].data(), sizeof(double) * NWB_NJ);
+    if (raw_paths && total > 0) {
+      const size_t need = sizeof(int64_t) * Q + 256 + sizeof(double) * NWB_NJ * (size_t)total;
+      if (need > ctx->d_plan_bytes) {
+        if (ctx->d_plan) cudaFree(ctx->d_plan);
+        ctx->d_plan = nullptr;
+        ctx->d_plan_bytes = 0;
+        R_CUDA(ctx, cudaMalloc(&ctx->d_plan, std::max(need, (size_t)1 << 20)));
+        ctx->d_plan_bytes = std::max(need, (size_t)1 << 20);
+      }
+      int64_t* d_offs = static_cast<int64_t*>(ctx->d_plan);
+      double* d_rows = reinterpret_cast<double*>(static_cast<char*>(ctx->d_plan) + ((sizeof(int64_t) * Q + 255) & ~(size_t)255));
+      R_CUDA(ctx, cudaMemcpyAsync(d_offs, offs.data(), sizeof(int64_t) * Q, cudaMemcpyHostToDevice, s));
+      rrt_path_kernel<<<Q, 32, 0, s>>>(F, S.success, S.connector, S.bridge, Q, d_lens, d_offs, d_rows);
+      std::vector<double> packed((size_t)total * NWB_NJ);
+      R_CUDA(ctx, cudaMemcpyAsync(packed.data(), d_rows, sizeof(double) * NWB_NJ * (size_t)total, cudaMemcpyDeviceToHost, s));
+      R_CUDA(ctx, cudaStreamSynchronize(s));
+      ++launches;
+      for (int k = 0; k < Q; ++k) {
+        const int n = std::min<int>(results[k].raw_path_len, raw_path_capacity);
+        if (n > 0)
+          std::memcpy(raw_paths + (size_t)k * raw_path_capacity * NWB_NJ, packed.data() + (size_t)offs[k] * NWB_NJ, sizeof(double) * NWB_NJ * n);
+      }
+    }
   }
   ctx->last_launches = launches;
   if (overflow) {
