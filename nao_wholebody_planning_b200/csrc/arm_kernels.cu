@@ -130,7 +130,7 @@ goal_sample_kernel(const __grid_constant__ PlanConst pc, const __grid_constant__
 #pragma unroll
     for (int j = 0; j < NWB_NJ; ++j) qf[j] = (float)q[j];
     ArmLocalStore st;
-    ValidityResult<float> r = evaluate_config<float, ArmLocalStore, false, false, STATIC ? PAIRS_STATIC_GROUP : PAIRS_TABLE>(tab, qf, st, nullptr, nullptr);
+    ValidityResult<float> r = evaluate_config<float, ArmLocalStore, false, false, STATIC ? PAIRS_STATIC_GROUP : PAIRS_TABLE, /*ENV_CULL=*/true>(tab, qf, st, nullptr, nullptr);
     const bool feasible = !r.hit && r.stable;
     stage = feasible ? 2 : 1;
     if (feasible) {

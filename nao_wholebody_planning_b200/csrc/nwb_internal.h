@@ -40,6 +40,7 @@ struct EnvLink {    // a robot proxy tested against the scene boxes
   float inv_a;     // 1/|b-a|^2, 0 for spheres
   float radius;
   int is_sphere;
+  float half_len;  // |b-a|/2: with the radius, the bounding sphere of the capsule about its mid point
 };
 
 // Passed to the kernels by value (__grid_constant__): lives in the constant bank, per launch,
@@ -49,6 +50,7 @@ struct ValidityTables {
   float foot_left[nwbm::kFootN][2];    // scaled left-foot polygon, l_sole frame
   int n_runs_cc, n_runs_cs, n_runs_ss; // runs are stored in this order
   int n_boxes, n_env_links;
+  int env_cull;                        // 1: skip the exact capsule-box test where a warp agrees the bounding sphere is clear
   PairRun runs[kMaxRuns];
   PairEntry entries[kMaxPairs];
   SceneBox boxes[kMaxBoxes];

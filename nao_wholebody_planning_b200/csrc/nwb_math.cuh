@@ -133,6 +133,18 @@ template <class M>
 NWB_HD M nwb_mask(bool v);
 template <>
 NWB_HD bool nwb_mask<bool>(bool v) { return v; }
+// "every active lane of the warp agrees": a real vote for the scalar device path, false elsewhere (host
+// instantiations such as the flop counter, packed lanes), so a cull guarded by it is simply not taken there
+template <class M>
+NWB_HD bool nwb_warp_all(M) { return false; }
+NWB_HD bool nwb_warp_all(bool v) {
+#ifdef __CUDA_ARCH__
+  return __all_sync(__activemask(), v);
+#else
+  (void)v;
+  return false;
+#endif
+}
 #if defined(__CUDACC__)
 template <>
 __device__ __forceinline__ M2 nwb_mask<M2>(bool v) { return M2{v, v}; }

@@ -2,6 +2,7 @@
 // (pair runs from the SRDF-derived pair list, scaled foot polygons, scene boxes).  Header-only so the
 // flop-counting tool can build the same tables without the CUDA runtime.
 #pragma once
+#include <cmath>
 #include <cstring>
 #include <map>
 #include <vector>
@@ -66,6 +67,7 @@ inline void fill_pairs(const nwb_params& params, ValidityTables& t, bool group_o
     el.inv_a = l > 0 ? (float)(1.0 / l) : 0.f;
     el.radius = (float)nwbm::kProxies[g].r;
     el.is_sphere = nwbm::kProxies[g].is_sphere;
+    el.half_len = (float)(0.5 * std::sqrt(l));
   }
 }
 
@@ -93,6 +95,7 @@ inline void build_validity_tables(const nwb_params& params, const std::vector<Sc
   fill_pairs(params, t, group_only);
   t.n_boxes = (int)boxes.size();
   for (int b = 0; b < t.n_boxes; ++b) t.boxes[b] = boxes[b];
+  t.env_cull = 1;
 }
 
 }  // namespace nwb

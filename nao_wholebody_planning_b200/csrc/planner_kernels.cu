@@ -35,7 +35,7 @@ __device__ __forceinline__ ValidityResult<float> eval_one(const ValidityTables& 
   for (int j = 0; j < NWB_NJ; ++j) qf[j] = (float)q[j];
   LocalStore st;
   constexpr int P = STATIC ? (COLLISION_ONLY ? PAIRS_STATIC_ALL : PAIRS_STATIC_GROUP) : PAIRS_TABLE;
-  return evaluate_config<float, LocalStore, false, COLLISION_ONLY, P>(tab, qf, st, nullptr, nullptr);
+  return evaluate_config<float, LocalStore, false, COLLISION_ONLY, P, /*ENV_CULL=*/true>(tab, qf, st, nullptr, nullptr);
 }
 
 // ---- steer + project ----------------------------------------------------------------------------

@@ -119,7 +119,11 @@ enum PairMode { PAIRS_TABLE = 0, PAIRS_STATIC_GROUP = 1, PAIRS_STATIC_ALL = 2 };
 
 // Evaluate one configuration (or one lane-pair of configurations).  q = 21 joint values.
 // MARGINS: also min separation / hull distance (one-lane scalars only).
-template <class T, class Store, bool MARGINS, bool COLLISION_ONLY, int PAIRS = PAIRS_TABLE>
+// ENV_CULL: conservative bounding-sphere cull of the capsule-box tests under a warp vote.  It pays where the
+// lanes of a warp are coherent (one lane of a planner kernel, consecutive way-points of an edge) and costs
+// time on batches of unrelated configurations, whose warps almost never agree - the batched validity
+// kernels instantiate it off.
+template <class T, class Store, bool MARGINS, bool COLLISION_ONLY, int PAIRS = PAIRS_TABLE, bool ENV_CULL = false>
 NWB_HD ValidityResult<T> evaluate_config(const ValidityTables& tab, const T* q, Store& st, T* min_sep_out, T* hull_out) {
   using M = typename mask_of<T>::type;
   ValidityVisitor<T, Store, !COLLISION_ONLY> V(st);
@@ -259,9 +263,28 @@ NWB_HD ValidityResult<T> evaluate_config(const ValidityTables& tab, const T* q, 
   for (int b = 0; b < tab.n_boxes; ++b) {
     const SceneBox& bx = tab.boxes[b];
     const T H[3] = {T(bx.h[0]), T(bx.h[1]), T(bx.h[2])};
-    auto env_link = [&](int off, bool is_sphere, T radius) {
+    auto env_link = [&](int off, bool is_sphere, T radius, float half_len) {
       T pa[3], A[3];
       load3(st, off, pa);
+      if constexpr (!MARGINS && ENV_CULL) {
+        // Conservative cull: if the capsule's bounding sphere (mid point, half length + radius) is clear of the
+        // box for EVERY lane of the warp, the exact segment-box distance cannot report contact - skip it.
+        // Never changes a verdict; off (tab.env_cull = 0) for the full-evaluation roofline runs.
+        if (!is_sphere && tab.env_cull) {
+          T qm[3];
+          load3(st, off + 3, qm);
+          T mx = nwb_fma(T(0.5f), qm[0] - pa[0], pa[0]) - T(bx.c[0]);
+          T my = nwb_fma(T(0.5f), qm[1] - pa[1], pa[1]) - T(bx.c[1]);
+          T mz = nwb_fma(T(0.5f), qm[2] - pa[2], pa[2]) - T(bx.c[2]);
+          T c0 = nwb_fma(T(bx.r[6]), mz, nwb_fma(T(bx.r[3]), my, T(bx.r[0]) * mx));
+          T c1 = nwb_fma(T(bx.r[7]), mz, nwb_fma(T(bx.r[4]), my, T(bx.r[1]) * mx));
+          T c2 = nwb_fma(T(bx.r[8]), mz, nwb_fma(T(bx.r[5]), my, T(bx.r[2]) * mx));
+          T e0 = box_excess(c0, H[0]), e1 = box_excess(c1, H[1]), e2 = box_excess(c2, H[2]);
+          T dm2 = nwb_fma(e2, e2, nwb_fma(e1, e1, e0 * e0));
+          const float rb = half_len + 1.0e-4f;               // slack for the fp32 evaluation of the exact test
+          if (nwb_warp_all(dm2 > (T(rb) + radius) * (T(rb) + radius))) return;
+        }
+      }
       T rx = pa[0] - T(bx.c[0]), ry = pa[1] - T(bx.c[1]), rz = pa[2] - T(bx.c[2]);
       A[0] = nwb_fma(T(bx.r[6]), rz, nwb_fma(T(bx.r[3]), ry, T(bx.r[0]) * rx));      // R^T (a - c)
       A[1] = nwb_fma(T(bx.r[7]), rz, nwb_fma(T(bx.r[4]), ry, T(bx.r[1]) * rx));
@@ -284,10 +307,10 @@ NWB_HD ValidityResult<T> evaluate_config(const ValidityTables& tab, const T* q, 
     if constexpr (PAIRS == PAIRS_TABLE) {
       for (int l = 0; l < tab.n_env_links; ++l) {
         const EnvLink& el = tab.env_links[l];
-        env_link(el.off, el.is_sphere != 0, T(el.radius));
+        env_link(el.off, el.is_sphere != 0, T(el.radius), el.half_len);
       }
     } else {
-#define NWB_X_ENV(SLOT, SPHERE, R) env_link(SLOT, SPHERE, T(R));
+#define NWB_X_ENV(SLOT, SPHERE, R, HALF) env_link(SLOT, SPHERE, T(R), HALF);
       if constexpr (PAIRS == PAIRS_STATIC_GROUP) { NWB_ENV_LINKS_GROUP(NWB_X_ENV) }
       else { NWB_ENV_LINKS_ALL(NWB_X_ENV) }
 #undef NWB_X_ENV

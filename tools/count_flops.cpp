@@ -99,6 +99,7 @@ int main() {
   build_validity_tables(p, {}, true, s0g);
   build_validity_tables(p, {}, false, s0a);
   build_validity_tables(p, shelf_scene(), true, s1g);
+  s0g.env_cull = s0a.env_cull = s1g.env_cull = 0;      // the roofline counts the FULL evaluation (no culling)
   const int N = 2000;
   int ncc = 0, ncs = 0, nss = 0;
   for (int r = 0; r < s0g.n_runs_cc; ++r) ncc += s0g.runs[r].count;
