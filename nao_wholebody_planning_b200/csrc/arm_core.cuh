@@ -183,6 +183,11 @@ __device__ __forceinline__ double ergonomics_index(const double* q5) {
 // computeRightArmIK constructs it (nao_constraint_kinematics.cpp:311-317).  Same iteration as left_leg_ik_nr.
 __device__ __forceinline__ bool right_arm_ik_nr(const DFrame& target, double* q /*[5] in: seed*/, int maxiter, double eps,
                                                 double pinv_eps) {
+  double V[5][5];                                         // warm start of the Jacobi SVD across iterations
+#pragma unroll
+  for (int a = 0; a < 5; ++a)
+#pragma unroll
+    for (int b = 0; b < 5; ++b) V[a][b] = (a == b) ? 1.0 : 0.0;
   int i;
   for (i = 0; i < maxiter; ++i) {
     DFrame f;
@@ -199,7 +204,7 @@ __device__ __forceinline__ bool right_arm_ik_nr(const DFrame& target, double* q 
       W[3][k] = a[k].x; W[4][k] = a[k].y; W[5][k] = a[k].z;
     }
     double dq[5];
-    pinv_solve(W, tw, pinv_eps, dq);
+    pinv_solve(W, tw, pinv_eps, dq, V);
 #pragma unroll
     for (int k = 0; k < 5; ++k) q[k] += dq[k];
     bool conv = true;

@@ -178,19 +178,29 @@ __device__ __forceinline__ void jacobi_rotate(double (&W)[6][5], double (&V)[5][
 // 10 column pairs in a round-robin order - five rounds of two DISJOINT pairs - so the two rotations of a
 // round are independent instruction streams: this code runs one warp per scheduler with nothing else to
 // hide the fp64 dependency chains behind.
-static __device__ __noinline__ void pinv_solve(const double (*W_in)[5], const double* tw_in, double eps, double* qdot) {
-  // W_in / tw_in arrive through memory (the function is not inlined): pull them into registers once
+// WARM START: V_io carries the right singular vectors from one Newton-Raphson iteration to the next.  The
+// Jacobian moves little between iterations, so J V_prev is already nearly orthogonal and one or two sweeps
+// finish the job instead of six; the first call of a solve passes the identity.  The decomposition reached
+// is the same (the pseudo-inverse is unique), only the route is shorter.
+static __device__ __noinline__ void pinv_solve(const double (*W_in)[5], const double* tw_in, double eps, double* qdot,
+                                               double (*V_io)[5]) {
+  // W_in / tw_in / V_io arrive through memory (the function is not inlined): pull them into registers once
   double W[6][5], tw[6], V[5][5];
+#pragma unroll
+  for (int i = 0; i < 5; ++i)
+#pragma unroll
+    for (int j = 0; j < 5; ++j) V[i][j] = V_io[i][j];
 #pragma unroll
   for (int r = 0; r < 6; ++r) {
     tw[r] = tw_in[r];
 #pragma unroll
-    for (int c = 0; c < 5; ++c) W[r][c] = W_in[r][c];
+    for (int c = 0; c < 5; ++c) {                        // W = J V
+      double acc = 0.0;
+#pragma unroll
+      for (int m = 0; m < 5; ++m) acc += W_in[r][m] * V[m][c];
+      W[r][c] = acc;
+    }
   }
-#pragma unroll
-  for (int i = 0; i < 5; ++i)
-#pragma unroll
-    for (int j = 0; j < 5; ++j) V[i][j] = (i == j) ? 1.0 : 0.0;
   for (int sweep = 0; sweep < 60; ++sweep) {
     bool rotated = false;
     jacobi_rotate<1, 4>(W, V, rotated); jacobi_rotate<2, 3>(W, V, rotated);
@@ -217,7 +227,10 @@ static __device__ __noinline__ void pinv_solve(const double (*W_in)[5], const do
   for (int i = 0; i < 5; ++i) {
     double s = 0;
 #pragma unroll
-    for (int j = 0; j < 5; ++j) s += V[i][j] * tmp[j];
+    for (int j = 0; j < 5; ++j) {
+      s += V[i][j] * tmp[j];
+      V_io[i][j] = V[i][j];
+    }
     qdot[i] = s;
   }
 }
@@ -226,6 +239,11 @@ static __device__ __noinline__ void pinv_solve(const double (*W_in)[5], const do
 // BEFORE the convergence test.  Returns true on convergence; q holds the result.
 __device__ __forceinline__ bool left_leg_ik_nr(const DFrame& target, double* q /*[5] in: seed*/, int maxiter, double eps,
                                                double pinv_eps, int* iters_out) {
+  double V[5][5];                                         // right singular vectors, carried across the iterations
+#pragma unroll
+  for (int a = 0; a < 5; ++a)
+#pragma unroll
+    for (int b = 0; b < 5; ++b) V[a][b] = (a == b) ? 1.0 : 0.0;
   int i;
   for (i = 0; i < maxiter; ++i) {
     DFrame f;
@@ -242,7 +260,7 @@ __device__ __forceinline__ bool left_leg_ik_nr(const DFrame& target, double* q /
       W[3][k] = a[k].x; W[4][k] = a[k].y; W[5][k] = a[k].z;
     }
     double dq[5];
-    pinv_solve(W, tw, pinv_eps, dq);
+    pinv_solve(W, tw, pinv_eps, dq, V);
 #pragma unroll
     for (int k = 0; k < 5; ++k) q[k] += dq[k];
     bool conv = true;

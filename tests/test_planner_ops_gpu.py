@@ -175,6 +175,33 @@ def test_sampler_capacity_overflow_is_reported(ctx):
         ctx.sample_stable_configs(1, 0, 20000, cap=10)
 
 
+def test_sampler_ranks_append_into_one_database(oracle):
+    """Sharded generation with the gather fused into the sampler, emulated on one GPU: two 'ranks' (contexts) sample
+    their halves of the index range straight into ONE set of output arrays with a shared slot counter (across
+    processes the arrays are CUDA-IPC mappings of rank 0's memory - bench_multi.py runs that path)."""
+    import torch
+    seed, count = 20121005, 30000
+    cap = count // 4
+    rows = torch.zeros((cap, 21), dtype=torch.float64, device="cuda")
+    idx = torch.zeros(cap, dtype=torch.int64, device="cuda")
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    ctxs = [nwb.Context(), nwb.Context()]
+    for r, c in enumerate(ctxs):
+        lo, hi = r * count // 2, (r + 1) * count // 2
+        c._check(c.lib.nwb_sample_stable_configs_dev(c.h, seed, lo, hi - lo, 5, rows.data_ptr(), idx.data_ptr(), cap,
+                                                     cnt.data_ptr(), None), "nwb_sample_stable_configs_dev")
+    for c in ctxs:
+        c.synchronize()
+    n = int(cnt.item())
+    order = torch.argsort(idx[:n])
+    ref_rows, ref_idx, _ = ctxs[0].sample_stable_configs(seed, 0, count)
+    assert n == len(ref_idx) and (idx[:n][order].cpu().numpy() == ref_idx.astype(np.int64)).all()
+    assert (rows[:n][order].cpu().numpy() == ref_rows).all()
+    for c in ctxs:
+        c.close()
+
+
 def test_generate_ds_database_service(ctx, oracle, tmp_path):
     """generate_ds_database (nao_planner_control.cpp:137-147) with the reference's default budget
     (5000 samples, 5 IK attempts): file written in the reference format, loadable, rows as the oracle's."""
