@@ -155,6 +155,8 @@ void nwb_ctx_destroy(nwb_ctx* ctx) {
   if (ctx->d_forest) cudaFree(ctx->d_forest);
   if (ctx->d_rrt) cudaFree(ctx->d_rrt);
   if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
+  if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+  if (ctx->d_dbcache) cudaFree(ctx->d_dbcache);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);

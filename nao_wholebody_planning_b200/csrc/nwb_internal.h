@@ -88,6 +88,9 @@ struct Ctx {
   int32_t* h_flag = nullptr;                           // pinned word the RRT driver polls
   std::vector<double> ds_db;                           // stable-configuration database of the services (RP:121-191)
   std::vector<double> h_raw;                           // raw-path staging of the services (kept across calls)
+  uint64_t ds_db_version = 0;                          // bumped whenever ds_db changes
+  double* d_dbcache = nullptr; size_t d_dbcache_rows = 0; uint64_t d_dbcache_version = ~0ull;   // device copy of ds_db
+  void* h_pin = nullptr; size_t h_pin_bytes = 0;       // pinned staging of the fused RRT call (inputs out, results back)
   double last_ms = 0;
   int64_t last_launches = 0;
   int64_t last_nn_passes = 0;        // passes over the node array of the last nearest-neighbour call
@@ -143,6 +146,11 @@ cudaError_t launch_connect_forest(const PlanConst& pc, const ValidityTables& tab
 cudaError_t launch_rrt_persistent(const PlanConst& pc, const ValidityTables& tab, bool static_pairs, ForestView F, RrtState S,
                                   const double* db, int n_db, const uint64_t* seeds, int max_iter, int nq, const double* ma_pts,
                                   int n_pts, cudaStream_t s);
+// roots validated + inserted, loop, results and raw paths in one launch (planner_kernels.cu: rrt_fused_kernel)
+cudaError_t launch_rrt_fused(const PlanConst& pc, const ValidityTables& tab, bool static_pairs, ForestView F, const double* starts,
+                             const double* goals, const uint64_t* seeds, int32_t* res, double* path_rows,
+                             unsigned long long* path_used, long long path_cap, const double* db, int n_db, int max_iter, int nq,
+                             const double* ma_pts, int n_pts, int32_t* overflow_flag, cudaStream_t s);
 cudaError_t launch_steer_project(const PlanConst& pc, const double* q_near, const double* q_target, int64_t n, double* q_out,
                                  int32_t* status, int32_t* ds_status, int32_t* iters, cudaStream_t s);
 cudaError_t launch_connect(const PlanConst& pc, const ValidityTables& tab, bool static_pairs, const double* q_start,

@@ -318,6 +318,7 @@ int nwb_generate_ds_database(nwb_ctx* ctx, const nwb_generate_ds_configs_request
   }
   resp->num_configs_generated = (int32_t)n;
   ctx->ds_db.assign(rows.begin(), rows.begin() + (size_t)n * NWB_NJ);   // planner_->load_DS_database(SSC_DS_CONFIGS), NPC:144
+  ++ctx->ds_db_version;
   for (double& v : ctx->ds_db) {                                        // ... which reads the 6-digit text back
     char buf[64];
     std::snprintf(buf, sizeof buf, "%g", v);

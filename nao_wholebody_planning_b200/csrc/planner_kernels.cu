@@ -224,19 +224,23 @@ __device__ __forceinline__ int warp_nearest(const ForestView& F, int t, int n, c
   return besti;
 }
 
+// one out-of-line copy of the full validity evaluation for the RRT kernels (they call it from four places)
 template <bool STATIC>
-__global__ void __launch_bounds__(32)
-rrt_persistent_kernel(const __grid_constant__ PlanConst pc, const __grid_constant__ ValidityTables tab, ForestView F, RrtState S,
-                      const double* __restrict__ db, int n_db, const uint64_t* __restrict__ seeds, int max_iter, int nq,
-                      const double* __restrict__ ma_pts, int n_pts) {
-  const int k = blockIdx.x;
-  const int lane = threadIdx.x;
-  if (k >= nq || !S.active[k]) return;
-  __shared__ double qd[NWB_NJ];          // current query of the nearest-neighbour scan (q_rand, then q_connect)
-  __shared__ float qf[NWB_NJ];
-  const MaView ma{ma_pts ? ma_pts + (size_t)k * n_pts * 6 : nullptr, n_pts};
-  const uint64_t seed = seeds[k];
-  int size[2] = {F.size[2 * k], F.size[2 * k + 1]};      // kept in registers of every lane
+static __device__ __noinline__ bool config_valid(const ValidityTables& tab, const double* q) {
+  ValidityResult<float> v = eval_one<false, STATIC>(tab, q);
+  return !v.hit && v.stable;
+}
+
+struct RrtOutcome {
+  int iterations, success, connector, bridge, overflow;
+};
+
+// solveQuery's loop (RP:1067-1198) for query k, executed by one warp.  size[0/1] = node counts of the start / goal tree
+// (kept in registers of every lane, updated as nodes are appended); qd / qf = 21-element shared scratch of the warp.
+template <bool STATIC>
+__device__ __forceinline__ RrtOutcome rrt_query_loop(const PlanConst& pc, const ValidityTables& tab, const ForestView& F, int k, int lane,
+                                                     uint64_t seed, const double* __restrict__ db, int n_db, int max_iter,
+                                                     const MaView& ma, double* qd, float* qf, int (&size)[2], int32_t* overflow_flag) {
   int swap = 0, done = 0, success = 0, connector = 0, bridge = 0, it = 0;
   for (; it < max_iter && !done; ++it) {
     // getRandomStableConfig (RP:316-332) with the injected stream
@@ -274,11 +278,10 @@ rrt_persistent_kernel(const __grid_constant__ PlanConst pc, const __grid_constan
         else if (mas == NWB_ADVANCED) st = NWB_ADVANCED;
       }
       if (st != NWB_TRAPPED) {
-        ValidityResult<float> v = eval_one<false, STATIC>(tab, q);
-        if (!v.hit && v.stable) {
+        if (config_valid<STATIC>(tab, q)) {
           const int base = size[ta & 1];
           if (base >= F.cap) {
-            atomicExch(S.overflow, 1);
+            atomicExch(overflow_flag, 1);
             done = 2;
           } else {                                        // addConfigtoTree (RP:749-783)
             for (int j = 0; j < NWB_NJ; ++j) {
@@ -333,10 +336,9 @@ rrt_persistent_kernel(const __grid_constant__ PlanConst pc, const __grid_constan
             if (mas == NWB_ADVANCED) state = NWB_ADVANCED;
             if (cur_hand == connect_hand && state != NWB_REACHED) { state = NWB_TRAPPED; break; }
           }
-          ValidityResult<float> v = eval_one<false, STATIC>(tab, q);
-          if (v.hit || !v.stable) { state = NWB_TRAPPED; break; }
+          if (!config_valid<STATIC>(tab, q)) { state = NWB_TRAPPED; break; }
           if (sz >= F.cap) {
-            atomicExch(S.overflow, 1);
+            atomicExch(overflow_flag, 1);
             state = -1;
             break;
           }
@@ -370,14 +372,142 @@ rrt_persistent_kernel(const __grid_constant__ PlanConst pc, const __grid_constan
     }
     swap ^= 1;                                            // RP:1125-1192: every iteration, whatever the outcome
   }
+  RrtOutcome o;                                           // lane 0 holds the outcome: give it to every lane
+  o.iterations = it;
+  o.success = __shfl_sync(0xffffffffu, success, 0);
+  o.connector = __shfl_sync(0xffffffffu, connector, 0);
+  o.bridge = __shfl_sync(0xffffffffu, bridge, 0);
+  o.overflow = done == 2 || (done == 1 && !o.success);
+  return o;
+}
+
+template <bool STATIC>
+__global__ void __launch_bounds__(32)
+rrt_persistent_kernel(const __grid_constant__ PlanConst pc, const __grid_constant__ ValidityTables tab, ForestView F, RrtState S,
+                      const double* __restrict__ db, int n_db, const uint64_t* __restrict__ seeds, int max_iter, int nq,
+                      const double* __restrict__ ma_pts, int n_pts) {
+  const int k = blockIdx.x;
+  const int lane = threadIdx.x;
+  if (k >= nq || !S.active[k]) return;
+  __shared__ double qd[NWB_NJ];          // current query of the nearest-neighbour scan (q_rand, then q_connect)
+  __shared__ float qf[NWB_NJ];
+  const MaView ma{ma_pts ? ma_pts + (size_t)k * n_pts * 6 : nullptr, n_pts};
+  int size[2] = {F.size[2 * k], F.size[2 * k + 1]};      // kept in registers of every lane
+  const RrtOutcome o = rrt_query_loop<STATIC>(pc, tab, F, k, lane, seeds[k], db, n_db, max_iter, ma, qd, qf, size, S.overflow);
   if (lane == 0) {
     F.size[2 * k] = size[0];
     F.size[2 * k + 1] = size[1];
-    S.iterations[k] = it;
-    S.success[k] = success;
-    S.connector[k] = connector;
-    S.bridge[k] = bridge;
+    S.iterations[k] = o.iterations;
+    S.success[k] = o.success;
+    S.connector[k] = o.connector;
+    S.bridge[k] = o.bridge;
     S.active[k] = 0;
+  }
+}
+
+// Fused form: the query's roots are validated and inserted here (setStartGoalConfigs, RP:227-302), the loop runs,
+// and on success the raw path (writePath's extraction, RP:1303-1392) is written into a shared row pool - so the
+// host issues ONE upload, ONE launch and ONE download per call.  res[k] = {start_valid, goal_valid, success,
+// iterations, connector, bridge, nodes_start, nodes_goal, path_len, path_offset (-1: pool exhausted), overflow, 0}.
+struct RrtIo {
+  const double* starts;     // [nq][21]
+  const double* goals;      // [nq][21]
+  const uint64_t* seeds;    // [nq]
+  int32_t* res;             // [nq][12]
+  double* path_rows;        // [path_cap][21]
+  unsigned long long* path_used;
+  long long path_cap;
+};
+
+template <bool STATIC>
+__global__ void __launch_bounds__(32)
+rrt_fused_kernel(const __grid_constant__ PlanConst pc, const __grid_constant__ ValidityTables tab, ForestView F, RrtIo io,
+                 const double* __restrict__ db, int n_db, int max_iter, int nq, const double* __restrict__ ma_pts, int n_pts,
+                 int32_t* __restrict__ overflow_flag) {
+  const int k = blockIdx.x;
+  const int lane = threadIdx.x;
+  if (k >= nq) return;
+  __shared__ double qd[NWB_NJ];
+  __shared__ float qf[NWB_NJ];
+  const MaView ma{ma_pts ? ma_pts + (size_t)k * n_pts * 6 : nullptr, n_pts};
+  int32_t* res = io.res + (size_t)k * 12;
+  const int ts = 2 * k, tg = 2 * k + 1;
+  // ---- setStartGoalConfigs: both roots must be valid (RP:241-265)
+  int ok = 0;
+  if (lane == 0) {
+    double q[NWB_NJ];
+    for (int j = 0; j < NWB_NJ; ++j) q[j] = io.starts[(size_t)k * NWB_NJ + j];
+    const int sv = config_valid<STATIC>(tab, q);
+    for (int j = 0; j < NWB_NJ; ++j) q[j] = io.goals[(size_t)k * NWB_NJ + j];
+    const int gv = config_valid<STATIC>(tab, q);
+    for (int j = 0; j < 12; ++j) res[j] = 0;
+    res[0] = sv;
+    res[1] = gv;
+    res[9] = -1;
+    ok = sv && gv;
+    if (ok) {                                             // roots: index 0, predecessor 0 (RP:236-258)
+      for (int side = 0; side < 2; ++side) {
+        const int t = side ? tg : ts;
+        const double* src = (side ? io.goals : io.starts) + (size_t)k * NWB_NJ;
+        for (int j = 0; j < NWB_NJ; ++j) {
+          F.aos[(size_t)t * F.cap * NWB_NJ + j] = src[j];
+          F.soa[(size_t)t * NWB_NJ * F.cap + (size_t)j * F.cap] = (float)src[j];
+        }
+        F.pred[(size_t)t * F.cap] = 0;
+        if (ma.pts) F.hand[(size_t)t * F.cap] = side ? n_pts - 1 : 0;   // RP:274-282
+      }
+    }
+  }
+  __syncwarp();
+  ok = __shfl_sync(0xffffffffu, ok, 0);
+  if (!ok) return;
+  int size[2] = {1, 1};
+  const RrtOutcome o = rrt_query_loop<STATIC>(pc, tab, F, k, lane, io.seeds[k], db, n_db, max_iter, ma, qd, qf, size, overflow_flag);
+  // ---- results + raw path
+  int ls = 0, lg = 0, idx_s = 0, idx_g = 0;
+  long long off = -1;
+  const int32_t* pred_s = F.pred + (size_t)ts * F.cap;
+  const int32_t* pred_g = F.pred + (size_t)tg * F.cap;
+  if (lane == 0) {
+    F.size[ts] = size[0];
+    F.size[tg] = size[1];
+    res[2] = o.success;
+    res[3] = o.iterations;
+    res[4] = o.success ? o.connector : 0;
+    res[5] = o.success ? o.bridge : 0;
+    res[6] = size[0];
+    res[7] = size[1];
+    res[10] = o.overflow;
+    if (o.success) {
+      if (o.connector == 1) { idx_s = size[0] - 1; idx_g = o.bridge; }       // RP:1317-1327
+      else { idx_s = o.bridge; idx_g = size[1] - 1; }
+      ls = lg = 1;
+      for (int i = idx_s; i > 0; i = pred_s[i]) ++ls;
+      for (int i = idx_g; i > 0; i = pred_g[i]) ++lg;
+      const unsigned long long o0 = atomicAdd(io.path_used, (unsigned long long)(ls + lg));
+      if ((long long)(o0 + ls + lg) <= io.path_cap) off = (long long)o0;
+      res[8] = ls + lg;
+      res[9] = (int32_t)off;
+    }
+  }
+  __syncwarp();
+  if (!o.success) return;
+  ls = __shfl_sync(0xffffffffu, ls, 0);
+  lg = __shfl_sync(0xffffffffu, lg, 0);
+  idx_s = __shfl_sync(0xffffffffu, idx_s, 0);
+  idx_g = __shfl_sync(0xffffffffu, idx_g, 0);
+  off = __shfl_sync(0xffffffffu, off, 0);
+  if (off < 0) return;                                    // pool exhausted: the host extracts this path separately
+  double* out = io.path_rows + off * NWB_NJ;
+  int i = idx_s;
+  for (int pos = ls - 1; pos >= 0; --pos) {               // start branch, reversed into place
+    if (lane < NWB_NJ) out[(size_t)pos * NWB_NJ + lane] = F.aos[((size_t)ts * F.cap + i) * NWB_NJ + lane];
+    i = pred_s[i];
+  }
+  i = idx_g;
+  for (int pos = 0; pos < lg; ++pos) {                    // goal branch as walked
+    if (lane < NWB_NJ) out[(size_t)(ls + pos) * NWB_NJ + lane] = F.aos[((size_t)tg * F.cap + i) * NWB_NJ + lane];
+    i = pred_g[i];
   }
 }
 
@@ -536,6 +666,17 @@ cudaError_t launch_rrt_persistent(const PlanConst& pc, const ValidityTables& tab
   if (nq <= 0) return cudaSuccess;
   if (static_pairs) rrt_persistent_kernel<true><<<nq, 32, 0, s>>>(pc, tab, F, S, db, n_db, seeds, max_iter, nq, ma_pts, n_pts);
   else rrt_persistent_kernel<false><<<nq, 32, 0, s>>>(pc, tab, F, S, db, n_db, seeds, max_iter, nq, ma_pts, n_pts);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_rrt_fused(const PlanConst& pc, const ValidityTables& tab, bool static_pairs, ForestView F, const double* starts,
+                             const double* goals, const uint64_t* seeds, int32_t* res, double* path_rows,
+                             unsigned long long* path_used, long long path_cap, const double* db, int n_db, int max_iter, int nq,
+                             const double* ma_pts, int n_pts, int32_t* overflow_flag, cudaStream_t s) {
+  if (nq <= 0) return cudaSuccess;
+  RrtIo io{starts, goals, seeds, res, path_rows, path_used, path_cap};
+  if (static_pairs) rrt_fused_kernel<true><<<nq, 32, 0, s>>>(pc, tab, F, io, db, n_db, max_iter, nq, ma_pts, n_pts, overflow_flag);
+  else rrt_fused_kernel<false><<<nq, 32, 0, s>>>(pc, tab, F, io, db, n_db, max_iter, nq, ma_pts, n_pts, overflow_flag);
   return cudaGetLastError();
 }
 

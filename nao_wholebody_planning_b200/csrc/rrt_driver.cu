@@ -253,6 +253,143 @@ struct DevBuf {
 };
 }  // namespace
 
+// One upload, one launch, one download: the default form of solveQuery for nq queries (rrt_fused_kernel).
+static int solve_fused(nwb_ctx* ctx, const double* starts, const double* goals, int64_t nq, const double* db, int32_t n_db,
+                       const double* weights, const uint64_t* seeds, int32_t max_iter, double step, int32_t tree_capacity,
+                       const double* hand_traj, int P, nwb_plan_result* results, double* raw_paths, int32_t raw_path_capacity) {
+  cudaStream_t s = ctx->stream;
+  const int Q = (int)nq, T = 2 * Q;
+  const int64_t C = tree_capacity > 0 ? tree_capacity : 4096;
+  const bool sp = ctx->params.srdf_trim != 0 && !ctx->force_table_pairs;
+  PlanConst pc;
+  make_plan_const(ctx, weights, step, pc);
+  auto grow = [&](void** buf, size_t* have, size_t need) -> cudaError_t {
+    if (*have >= need) return cudaSuccess;
+    if (*buf) cudaFree(*buf);
+    *buf = nullptr;
+    *have = 0;
+    cudaError_t e = cudaMalloc(buf, need);
+    if (e == cudaSuccess) *have = need;
+    return e;
+  };
+  const size_t soa_b = sizeof(float) * NWB_NJ * C * T, aos_b = sizeof(double) * NWB_NJ * C * T, pred_b = sizeof(int32_t) * C * T;
+  const size_t hand_b = P ? pred_b : 0;
+  R_CUDA(ctx, grow(&ctx->d_forest, &ctx->d_forest_bytes, soa_b + aos_b + pred_b + hand_b + 256));
+  char* FB = static_cast<char*>(ctx->d_forest);
+
+  // the stable-configuration database of the services stays on the device between calls
+  const double* d_db = nullptr;
+  bool db_inline = true;
+  if (db == ctx->ds_db.data() && (size_t)n_db * NWB_NJ == ctx->ds_db.size()) {
+    if (ctx->d_dbcache_version != ctx->ds_db_version || ctx->d_dbcache_rows != (size_t)n_db) {
+      if (ctx->d_dbcache) cudaFree(ctx->d_dbcache);
+      ctx->d_dbcache = nullptr;
+      R_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_dbcache), sizeof(double) * NWB_NJ * (size_t)n_db));
+      R_CUDA(ctx, cudaMemcpyAsync(ctx->d_dbcache, db, sizeof(double) * NWB_NJ * (size_t)n_db, cudaMemcpyHostToDevice, s));
+      ctx->d_dbcache_rows = (size_t)n_db;
+      ctx->d_dbcache_version = ctx->ds_db_version;
+    }
+    d_db = ctx->d_dbcache;
+    db_inline = false;
+  }
+
+  // device arena: [inputs: starts | goals | seeds | hand trajectories | database] [outputs: res | used | overflow | paths]
+  const size_t qbytes = sizeof(double) * NWB_NJ * Q;
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  const size_t o_size = carve(sizeof(int32_t) * T);
+  const size_t o_in = off;
+  const size_t o_starts = carve(qbytes), o_goals = carve(qbytes), o_seeds = carve(sizeof(uint64_t) * Q),
+               o_ma = carve(sizeof(double) * 6 * (size_t)P * Q), o_db = carve(db_inline ? sizeof(double) * NWB_NJ * (size_t)n_db : 0);
+  const size_t in_bytes = off - o_in;
+  const size_t o_out = off;
+  const size_t o_res = carve(sizeof(int32_t) * 12 * Q), o_used = carve(16), o_ovf = carve(16);
+  const long long path_cap = (long long)Q * 512;
+  const size_t o_paths = carve(sizeof(double) * NWB_NJ * (size_t)path_cap);
+  const size_t head_bytes = o_paths - o_out;                             // res + used + overflow
+  R_CUDA(ctx, grow(&ctx->d_rrt, &ctx->d_rrt_bytes, off));
+  char* M = static_cast<char*>(ctx->d_rrt);
+  ForestView F{reinterpret_cast<float*>(FB), reinterpret_cast<double*>(FB + ((soa_b + 255) & ~(size_t)255)),
+               reinterpret_cast<int32_t*>(FB + ((soa_b + 255) & ~(size_t)255) + aos_b), reinterpret_cast<int32_t*>(M + o_size), C,
+               P ? reinterpret_cast<int32_t*>(FB + ((soa_b + 255) & ~(size_t)255) + aos_b + pred_b) : nullptr};
+
+  // pinned staging: inputs in the arena's layout, so one copy moves them all; results come back the same way
+  const int64_t spec_rows = Q <= 4 ? std::min<long long>(path_cap, 768) : 0;   // small calls: fetch the path rows speculatively
+  const size_t back_bytes = head_bytes + sizeof(double) * NWB_NJ * (size_t)spec_rows;
+  const size_t pin_need = std::max(in_bytes, back_bytes) + 256;
+  if (ctx->h_pin_bytes < pin_need) {
+    if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+    ctx->h_pin = nullptr;
+    ctx->h_pin_bytes = 0;
+    R_CUDA(ctx, cudaMallocHost(&ctx->h_pin, std::max(pin_need, (size_t)1 << 20)));
+    ctx->h_pin_bytes = std::max(pin_need, (size_t)1 << 20);
+  }
+  char* H = static_cast<char*>(ctx->h_pin);
+  std::memcpy(H + (o_starts - o_in), starts, qbytes);
+  std::memcpy(H + (o_goals - o_in), goals, qbytes);
+  std::memcpy(H + (o_seeds - o_in), seeds, sizeof(uint64_t) * Q);
+  if (P) std::memcpy(H + (o_ma - o_in), hand_traj, sizeof(double) * 6 * (size_t)P * Q);
+  if (db_inline) std::memcpy(H + (o_db - o_in), db, sizeof(double) * NWB_NJ * (size_t)n_db);
+  R_CUDA(ctx, cudaMemcpyAsync(M + o_in, H, in_bytes, cudaMemcpyHostToDevice, s));
+  R_CUDA(ctx, cudaMemsetAsync(M + o_used, 0, o_paths - o_used, s));       // row counter + overflow flag
+  if (db_inline) d_db = reinterpret_cast<const double*>(M + o_db);
+  R_CUDA(ctx, launch_rrt_fused(pc, ctx->tab_group, sp, F, reinterpret_cast<const double*>(M + o_starts),
+                               reinterpret_cast<const double*>(M + o_goals), reinterpret_cast<const uint64_t*>(M + o_seeds),
+                               reinterpret_cast<int32_t*>(M + o_res), reinterpret_cast<double*>(M + o_paths),
+                               reinterpret_cast<unsigned long long*>(M + o_used), path_cap, d_db, n_db, max_iter, Q,
+                               P ? reinterpret_cast<const double*>(M + o_ma) : nullptr, P, reinterpret_cast<int32_t*>(M + o_ovf), s));
+  R_CUDA(ctx, cudaMemcpyAsync(H, M + o_out, back_bytes, cudaMemcpyDeviceToHost, s));
+  R_CUDA(ctx, cudaStreamSynchronize(s));
+  int64_t launches = 1;
+
+  const int32_t* res = reinterpret_cast<const int32_t*>(H + (o_res - o_out));
+  const unsigned long long used = *reinterpret_cast<const unsigned long long*>(H + (o_used - o_out));
+  const int32_t overflow = *reinterpret_cast<const int32_t*>(H + (o_ovf - o_out));
+  bool pool_short = false;
+  for (int k = 0; k < Q; ++k) {
+    const int32_t* r = res + (size_t)k * 12;
+    nwb_plan_result& o = results[k];
+    std::memset(&o, 0, sizeof o);
+    o.start_valid = r[0];
+    o.goal_valid = r[1];
+    o.success = r[2];
+    o.iterations = r[3];
+    o.connector = r[4];
+    o.bridge_other = r[5];
+    o.nodes_start = r[6];
+    o.nodes_goal = r[7];
+    o.num_nodes_generated = o.success ? o.nodes_start + o.nodes_goal : 0;   // RP:1045: stays 0 unless a path is found
+    o.raw_path_len = o.success ? r[8] : 0;
+    if (o.success && r[9] < 0) pool_short = true;
+  }
+  if (pool_short) {
+    ctx->err = "nwb_solve_query_batch: raw-path pool exhausted";
+    return NWB_E_NOMEM;
+  }
+  if (raw_paths && used > 0) {
+    const double* rows = reinterpret_cast<const double*>(H + head_bytes);
+    std::vector<double> big;
+    if ((int64_t)used > spec_rows) {                                       // fetch exactly what was written
+      big.resize((size_t)used * NWB_NJ);
+      R_CUDA(ctx, cudaMemcpyAsync(big.data(), M + o_paths, sizeof(double) * NWB_NJ * (size_t)used, cudaMemcpyDeviceToHost, s));
+      R_CUDA(ctx, cudaStreamSynchronize(s));
+      rows = big.data();
+    }
+    for (int k = 0; k < Q; ++k) {
+      const int32_t* r = res + (size_t)k * 12;
+      if (!r[2]) continue;
+      const int n = std::min<int>(r[8], raw_path_capacity);
+      std::memcpy(raw_paths + (size_t)k * raw_path_capacity * NWB_NJ, rows + (size_t)r[9] * NWB_NJ, sizeof(double) * NWB_NJ * n);
+    }
+  }
+  ctx->last_launches = launches;
+  if (overflow) {
+    ctx->err = "nwb_solve_query_batch: a tree outgrew tree_capacity";
+    return NWB_E_NOMEM;
+  }
+  return NWB_OK;
+}
+
 static int solve_impl(nwb_ctx* ctx, const double* starts, const double* goals, int64_t nq, const double* db, int32_t n_db,
                       const double* weights, const uint64_t* seeds, int32_t max_iter, double step, int32_t tree_capacity,
                       const double* hand_traj, int32_t n_pts, nwb_plan_result* results, double* raw_paths,
@@ -266,6 +403,12 @@ static int solve_impl(nwb_ctx* ctx, const double* starts, const double* goals, i
   const int P = hand_traj ? n_pts : 0;
   if (nq == 0) return NWB_OK;
   R_CUDA(ctx, cudaSetDevice(ctx->device));
+  // default: the fused form; NWB_RRT_STAGED=1 (separate root validation / path extraction around the one-launch loop)
+  // and NWB_RRT_LOCKSTEP=1 (7-8 kernels per iteration) keep the earlier drivers for comparison
+  static const bool staged = getenv("NWB_RRT_STAGED") != nullptr || getenv("NWB_RRT_LOCKSTEP") != nullptr;
+  if (!staged)
+    return solve_fused(ctx, starts, goals, nq, db, n_db, weights, seeds, max_iter, step, tree_capacity, hand_traj, P, results,
+                       raw_paths, raw_path_capacity);
   cudaStream_t s = ctx->stream;
   const int Q = (int)nq, T = 2 * Q;
   const int64_t C = tree_capacity > 0 ? tree_capacity : 4096;

@@ -702,6 +702,7 @@ int nwb_ctx_set_ds_database(nwb_ctx* ctx, const double* rows, int64_t n_rows) {
   if (!ctx) return NWB_E_INVALID;
   if (n_rows < 0 || (n_rows > 0 && !rows)) return bad(ctx, "nwb_ctx_set_ds_database: bad argument");
   ctx->ds_db.assign(rows, rows + (size_t)n_rows * NWB_NJ);
+  ++ctx->ds_db_version;
   return NWB_OK;
 }
 
@@ -719,6 +720,7 @@ int nwb_ctx_load_ds_database(nwb_ctx* ctx, const char* path) {
   if (rc != NWB_OK) return rc;
   rows.resize((size_t)n * NWB_NJ);
   ctx->ds_db.swap(rows);
+  ++ctx->ds_db_version;
   return NWB_OK;
 }
 
