@@ -224,11 +224,118 @@ __device__ __forceinline__ int warp_nearest(const ForestView& F, int t, int n, c
   return besti;
 }
 
+// ---- one configuration evaluated by a whole warp ---------------------------------------------------------------------
+// The RRT kernels evaluate ONE configuration at a time (a step of a walk).  Every lane runs the forward kinematics,
+// the centre of mass and the support test redundantly (same instruction stream, no extra time), then the 108
+// collision pairs and the (link, box) tests are dealt out over the 32 lanes and the verdict is a warp vote.  Same
+// arithmetic per pair as evaluate_config (seg_seg_dist2 & co. on the same point table), so the verdict is the same.
+struct PairFlat {
+  int off_a, off_b;
+  float a, inv_a, e, inv_e, rsum2;
+  int type;                       // 0 capsule-capsule, 1 capsule-sphere, 2 sphere-sphere
+};
+#define NWB_F_CC(SA, LA, ILA, SB, LB, ILB, RS, RS2) {SA, SB, LA, ILA, LB, ILB, RS2, 0},
+#define NWB_F_CS(SA, LA, ILA, SB, LB, ILB, RS, RS2) {SA, SB, LA, ILA, LB, ILB, RS2, 1},
+#define NWB_F_SS(SA, LA, ILA, SB, LB, ILB, RS, RS2) {SA, SB, LA, ILA, LB, ILB, RS2, 2},
+__device__ const PairFlat kFlatPairsGroup[] = {NWB_PAIRS_CC_GROUP(NWB_F_CC) NWB_PAIRS_CS_GROUP(NWB_F_CS) NWB_PAIRS_SS_GROUP(NWB_F_SS)};
+#undef NWB_F_CC
+#undef NWB_F_CS
+#undef NWB_F_SS
+constexpr int kNumFlatPairsGroup = (int)(sizeof(kFlatPairsGroup) / sizeof(PairFlat));
+
+// q: the configuration, identical on every lane (shared memory).  Returns the verdict on every lane.
+__device__ __forceinline__ bool config_valid_warp(const ValidityTables& tab, const double* q, int lane) {
+  float qf[NWB_NJ];
+#pragma unroll
+  for (int j = 0; j < NWB_NJ; ++j) qf[j] = (float)q[j];
+  LocalStore st;
+  ValidityVisitor<float, LocalStore, true> V(st);
+  { NWB_MODEL_FK_WALK(float, XF<float>, qf, V) }
+  // static stability (as evaluate_config, wedge form)
+  const XF<float>& L = V.lsole;
+  Wedge<float> w;
+  w.init(tab.foot_right[0][0] - V.comx, tab.foot_right[0][1] - V.comy);
+#pragma unroll
+  for (int k = 1; k < nwbm::kFootN; ++k) w.add(tab.foot_right[k][0] - V.comx, tab.foot_right[k][1] - V.comy);
+  const float ox = L.p[0] - V.comx, oy = L.p[1] - V.comy;
+#pragma unroll
+  for (int k = 0; k < nwbm::kFootN; ++k) {
+    const float x = tab.foot_left[k][0], y = tab.foot_left[k][1];
+    w.add(fmaf(L.r[1], y, fmaf(L.r[0], x, ox)), fmaf(L.r[4], y, fmaf(L.r[3], x, oy)));
+  }
+  const bool stable = w.surrounded;
+  bool hit = false;
+  // self collision: pairs lane, lane + 32, ...
+  for (int p = lane; p < kNumFlatPairsGroup; p += 32) {
+    const PairFlat pf = kFlatPairsGroup[p];
+    float pa[3], pb[3];
+    load3(st, pf.off_a, pa);
+    load3(st, pf.off_b, pb);
+    float d2;
+    if (pf.type == 2) {
+      d2 = point_point_dist2(pa, pb);
+    } else {
+      float qa[3], d1[3];
+      load3(st, pf.off_a + 3, qa);
+      d1[0] = qa[0] - pa[0]; d1[1] = qa[1] - pa[1]; d1[2] = qa[2] - pa[2];
+      if (pf.type == 1) {
+        d2 = seg_point_dist2(pa, d1, pf.inv_a, pb);
+      } else {
+        float qb[3], dd[3];
+        load3(st, pf.off_b + 3, qb);
+        dd[0] = qb[0] - pb[0]; dd[1] = qb[1] - pb[1]; dd[2] = qb[2] - pb[2];
+        d2 = seg_seg_dist2(pa, d1, pf.a, pf.inv_a, pb, dd, pf.e, pf.inv_e);
+      }
+    }
+    hit = hit || (d2 < pf.rsum2);
+  }
+  // environment: (link, box) tests lane, lane + 32, ...
+  const int n_env = tab.n_env_links * tab.n_boxes;
+  for (int e = lane; e < n_env; e += 32) {
+    const int b = e / tab.n_env_links, l = e - b * tab.n_env_links;
+    const SceneBox& bx = tab.boxes[b];
+    const EnvLink& el = tab.env_links[l];
+    const float H[3] = {bx.h[0], bx.h[1], bx.h[2]};
+    float pa[3], A[3];
+    load3(st, el.off, pa);
+    const float rx = pa[0] - bx.c[0], ry = pa[1] - bx.c[1], rz = pa[2] - bx.c[2];
+    A[0] = fmaf(bx.r[6], rz, fmaf(bx.r[3], ry, bx.r[0] * rx));
+    A[1] = fmaf(bx.r[7], rz, fmaf(bx.r[4], ry, bx.r[1] * rx));
+    A[2] = fmaf(bx.r[8], rz, fmaf(bx.r[5], ry, bx.r[2] * rx));
+    float d2;
+    if (el.is_sphere) {
+      const float ex = box_excess(A[0], H[0]), ey = box_excess(A[1], H[1]), ez = box_excess(A[2], H[2]);
+      d2 = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
+    } else {
+      float qa[3], D[3];
+      load3(st, el.off + 3, qa);
+      const float dx = qa[0] - pa[0], dy = qa[1] - pa[1], dz = qa[2] - pa[2];
+      D[0] = fmaf(bx.r[6], dz, fmaf(bx.r[3], dy, bx.r[0] * dx));
+      D[1] = fmaf(bx.r[7], dz, fmaf(bx.r[4], dy, bx.r[1] * dx));
+      D[2] = fmaf(bx.r[8], dz, fmaf(bx.r[5], dy, bx.r[2] * dx));
+      d2 = seg_box_dist2(A, D, H);
+    }
+    hit = hit || (d2 < el.radius * el.radius);
+  }
+  hit = __any_sync(0xffffffffu, hit);
+  return !hit && stable;
+}
+
 // one out-of-line copy of the full validity evaluation for the RRT kernels (they call it from four places)
+// q lives in shared memory and is the same for every lane; all 32 lanes call this together.  With the compiled-in
+// pair set the warp shares the work; the table-driven set (srdf_trim = 0) is evaluated by lane 0 as before.
 template <bool STATIC>
-static __device__ __noinline__ bool config_valid(const ValidityTables& tab, const double* q) {
-  ValidityResult<float> v = eval_one<false, STATIC>(tab, q);
-  return !v.hit && v.stable;
+static __device__ __noinline__ bool config_valid(const ValidityTables& tab, const double* q, int lane) {
+  if constexpr (STATIC) {
+    return config_valid_warp(tab, q, lane);
+  } else {
+    int ok = 0;
+    if (lane == 0) {
+      ValidityResult<float> v = eval_one<false, false>(tab, q);
+      ok = !v.hit && v.stable;
+    }
+    return __shfl_sync(0xffffffffu, ok, 0) != 0;
+  }
 }
 
 struct RrtOutcome {
@@ -236,11 +343,16 @@ struct RrtOutcome {
 };
 
 // solveQuery's loop (RP:1067-1198) for query k, executed by one warp.  size[0/1] = node counts of the start / goal tree
-// (kept in registers of every lane, updated as nodes are appended); qd / qf = 21-element shared scratch of the warp.
+// (kept in registers of every lane, updated as nodes are appended); qd / qf = 21-element shared scratch of the warp
+// (query of the nearest-neighbour scans), qv = the configuration handed to the warp-wide validity evaluation.
+// The serial arithmetic (steer, projections, tree bookkeeping) runs on lane 0; the scans and the validity
+// evaluation use all lanes, so every lane walks the same control flow (decisions are broadcast from lane 0).
 template <bool STATIC>
 __device__ __forceinline__ RrtOutcome rrt_query_loop(const PlanConst& pc, const ValidityTables& tab, const ForestView& F, int k, int lane,
                                                      uint64_t seed, const double* __restrict__ db, int n_db, int max_iter,
-                                                     const MaView& ma, double* qd, float* qf, int (&size)[2], int32_t* overflow_flag) {
+                                                     const MaView& ma, double* qd, float* qf, double* qv, int (&size)[2],
+                                                     int32_t* overflow_flag) {
+  const unsigned FULL = 0xffffffffu;
   int swap = 0, done = 0, success = 0, connector = 0, bridge = 0, it = 0;
   for (; it < max_iter && !done; ++it) {
     // getRandomStableConfig (RP:316-332) with the injected stream
@@ -257,7 +369,8 @@ __device__ __forceinline__ RrtOutcome rrt_query_loop(const PlanConst& pc, const 
     __syncwarp();
     // ---- extendTree (RP:787-884)
     const int idx_a = warp_nearest(F, ta, size[ta & 1], qd, qf, lane);
-    int walking = 0, connect_hand = 0;
+    const bool a_start = (ta & 1) == 0;
+    int near_hand = 0, go = 0;
     if (lane == 0) {
       double near[NWB_NJ], tgt[NWB_NJ], q[NWB_NJ];
       const double* nrow = F.aos + ((size_t)ta * F.cap + idx_a) * NWB_NJ;
@@ -269,115 +382,142 @@ __device__ __forceinline__ RrtOutcome rrt_query_loop(const PlanConst& pc, const 
       const int ds = enforce_ds_constraints(q, pc, nullptr);
       if (ds == NWB_TRAPPED) st = NWB_TRAPPED;
       else if (ds == NWB_ADVANCED) st = NWB_ADVANCED;
-      const bool start_tree = (ta & 1) == 0;
-      int near_hand = 0;
       if (st != NWB_TRAPPED && ma.pts) {                  // enforce_MA_Constraints (RP:829-837)
         near_hand = F.hand[(size_t)ta * F.cap + idx_a];
-        const int mas = enforce_ma_constraints(ma, start_tree, near_hand, near, q, pc);
+        const int mas = enforce_ma_constraints(ma, a_start, near_hand, near, q, pc);
         if (mas == NWB_TRAPPED) st = NWB_TRAPPED;
         else if (mas == NWB_ADVANCED) st = NWB_ADVANCED;
       }
       if (st != NWB_TRAPPED) {
-        if (config_valid<STATIC>(tab, q)) {
-          const int base = size[ta & 1];
-          if (base >= F.cap) {
-            atomicExch(overflow_flag, 1);
-            done = 2;
-          } else {                                        // addConfigtoTree (RP:749-783)
+        go = 1;
+        for (int j = 0; j < NWB_NJ; ++j) qv[j] = q[j];
+      }
+    }
+    __syncwarp();
+    go = __shfl_sync(FULL, go, 0);
+    int walking = 0, connect_hand = 0;
+    if (go) {
+      const bool valid = config_valid<STATIC>(tab, qv, lane);         // isConfigValid (RP:846), all lanes
+      if (valid) {
+        const int base = size[ta & 1];
+        if (base >= F.cap) {
+          if (lane == 0) atomicExch(overflow_flag, 1);
+          done = 2;
+        } else {
+          if (lane == 0) {                                // addConfigtoTree (RP:749-783)
             for (int j = 0; j < NWB_NJ; ++j) {
-              F.aos[((size_t)ta * F.cap + base) * NWB_NJ + j] = q[j];
-              F.soa[(size_t)ta * NWB_NJ * F.cap + (size_t)j * F.cap + base] = (float)q[j];
-              qd[j] = q[j];                               // q_connect of this iteration's connectTree
-              qf[j] = (float)q[j];
+              const double v = qv[j];
+              F.aos[((size_t)ta * F.cap + base) * NWB_NJ + j] = v;
+              F.soa[(size_t)ta * NWB_NJ * F.cap + (size_t)j * F.cap + base] = (float)v;
+              qd[j] = v;                                  // q_connect of this iteration's connectTree
+              qf[j] = (float)v;
             }
             F.pred[(size_t)ta * F.cap + base] = idx_a;
             if (ma.pts) {
-              connect_hand = next_hand_index(ma, start_tree, near_hand);
+              connect_hand = next_hand_index(ma, a_start, near_hand);
               F.hand[(size_t)ta * F.cap + base] = connect_hand;
             }
-            walking = 1;
           }
+          walking = 1;
+          size[ta & 1] += 1;
         }
       }
     }
     __syncwarp();
-    walking = __shfl_sync(0xffffffffu, walking, 0);
-    done = __shfl_sync(0xffffffffu, done, 0);
-    if (walking) size[ta & 1] += 1;
-    if (walking && !done) {
+    if (walking) {
       // ---- connectTree (RP:890-1034)
       const int idx_b = warp_nearest(F, tb, size[tb & 1], qd, qf, lane);
-      int added = 0;
+      const bool b_start = (tb & 1) == 0;
+      float* soa = F.soa + (size_t)tb * NWB_NJ * F.cap;
+      double* aos = F.aos + (size_t)tb * F.cap * NWB_NJ;
+      int32_t* pred = F.pred + (size_t)tb * F.cap;
+      int32_t* hand = ma.pts ? F.hand + (size_t)tb * F.cap : nullptr;
+      int sz = size[tb & 1];
+      // lane 0's walk state
+      double cur[NWB_NJ], tgt[NWB_NJ];
+      int cur_idx = idx_b, state = NWB_ADVANCED, cur_hand = 0;
       if (lane == 0) {
-        const bool start_tree = (tb & 1) == 0;
-        float* soa = F.soa + (size_t)tb * NWB_NJ * F.cap;
-        double* aos = F.aos + (size_t)tb * F.cap * NWB_NJ;
-        int32_t* pred = F.pred + (size_t)tb * F.cap;
-        int32_t* hand = ma.pts ? F.hand + (size_t)tb * F.cap : nullptr;
-        int sz = size[tb & 1];
-        double cur[NWB_NJ], tgt[NWB_NJ], q[NWB_NJ];
         for (int j = 0; j < NWB_NJ; ++j) {
           cur[j] = aos[(size_t)idx_b * NWB_NJ + j];
           tgt[j] = qd[j];
         }
-        int cur_idx = idx_b, state = NWB_ADVANCED, cur_hand = 0;
         if (ma.pts) {
           cur_hand = hand[cur_idx];
-          if ((start_tree && cur_hand > connect_hand) || (!start_tree && cur_hand < connect_hand)) state = NWB_TRAPPED;   // RP:917-922
+          if ((b_start && cur_hand > connect_hand) || (!b_start && cur_hand < connect_hand)) state = NWB_TRAPPED;   // RP:917-922
         }
-        while (state == NWB_ADVANCED) {
+      }
+      state = __shfl_sync(FULL, state, 0);
+      while (state == NWB_ADVANCED) {
+        int need = 0;                                     // 1: a candidate node waits in qv for its validity test
+        if (lane == 0) {
+          double q[NWB_NJ];
           state = generate_q_new(cur, tgt, pc, q);
           const int ds = enforce_ds_constraints(q, pc, nullptr);
-          if (ds == NWB_TRAPPED) { state = NWB_TRAPPED; break; }
-          if (ds == NWB_ADVANCED) state = NWB_ADVANCED;
-          if (ma.pts) {                                   // RP:951-972
-            const int mas = enforce_ma_constraints(ma, start_tree, cur_hand, cur, q, pc);
-            if (mas == NWB_TRAPPED) { state = NWB_TRAPPED; break; }
-            if (mas == NWB_ADVANCED) state = NWB_ADVANCED;
-            if (cur_hand == connect_hand && state != NWB_REACHED) { state = NWB_TRAPPED; break; }
+          if (ds == NWB_TRAPPED) state = NWB_TRAPPED;
+          else {
+            if (ds == NWB_ADVANCED) state = NWB_ADVANCED;
+            bool proceed = true;
+            if (ma.pts) {                                 // RP:951-972
+              const int mas = enforce_ma_constraints(ma, b_start, cur_hand, cur, q, pc);
+              if (mas == NWB_TRAPPED) proceed = false;
+              else {
+                if (mas == NWB_ADVANCED) state = NWB_ADVANCED;
+                if (cur_hand == connect_hand && state != NWB_REACHED) proceed = false;
+              }
+            }
+            if (!proceed) state = NWB_TRAPPED;
+            else {
+              need = 1;
+              for (int j = 0; j < NWB_NJ; ++j) qv[j] = q[j];
+            }
           }
-          if (!config_valid<STATIC>(tab, q)) { state = NWB_TRAPPED; break; }
-          if (sz >= F.cap) {
-            atomicExch(overflow_flag, 1);
-            state = -1;
-            break;
-          }
+        }
+        __syncwarp();
+        need = __shfl_sync(FULL, need, 0);
+        state = __shfl_sync(FULL, state, 0);              // ADVANCED / REACHED when need, TRAPPED otherwise
+        if (!need) break;
+        const bool valid = config_valid<STATIC>(tab, qv, lane);
+        if (!valid) { state = NWB_TRAPPED; break; }
+        if (sz >= F.cap) {
+          if (lane == 0) atomicExch(overflow_flag, 1);
+          state = -1;
+          break;
+        }
+        if (lane == 0) {
           for (int j = 0; j < NWB_NJ; ++j) {
-            aos[(size_t)sz * NWB_NJ + j] = q[j];
-            soa[(size_t)j * F.cap + sz] = (float)q[j];
+            const double v = qv[j];
+            aos[(size_t)sz * NWB_NJ + j] = v;
+            soa[(size_t)j * F.cap + sz] = (float)v;
           }
           pred[sz] = cur_idx;
-          const int new_hand = ma.pts ? next_hand_index(ma, start_tree, cur_hand) : 0;
+          const int new_hand = ma.pts ? next_hand_index(ma, b_start, cur_hand) : 0;
           if (ma.pts) hand[sz] = new_hand;
           if (state == NWB_REACHED) {
             bridge = cur_idx;                             // RP:1000-1001
           } else {
             cur_idx = sz;                                 // RP:1004
             cur_hand = new_hand;
-            for (int j = 0; j < NWB_NJ; ++j) cur[j] = q[j];
+            for (int j = 0; j < NWB_NJ; ++j) cur[j] = qv[j];
           }
-          ++sz;
-          ++added;
         }
-        if (state == NWB_REACHED || state == -1) {
-          success = state == NWB_REACHED;
-          connector = swap ? 2 : 1;
-          done = 1;
-        }
+        ++sz;
+        __syncwarp();
       }
-      __syncwarp();
-      added = __shfl_sync(0xffffffffu, added, 0);
-      done = __shfl_sync(0xffffffffu, done, 0);
-      size[tb & 1] += added;
+      size[tb & 1] = sz;
+      if (state == NWB_REACHED || state == -1) {
+        success = state == NWB_REACHED;
+        connector = swap ? 2 : 1;
+        done = 1;
+      }
     }
     swap ^= 1;                                            // RP:1125-1192: every iteration, whatever the outcome
   }
-  RrtOutcome o;                                           // lane 0 holds the outcome: give it to every lane
+  RrtOutcome o;                                           // bridge lives on lane 0: give it to every lane
   o.iterations = it;
-  o.success = __shfl_sync(0xffffffffu, success, 0);
-  o.connector = __shfl_sync(0xffffffffu, connector, 0);
-  o.bridge = __shfl_sync(0xffffffffu, bridge, 0);
-  o.overflow = done == 2 || (done == 1 && !o.success);
+  o.success = success;
+  o.connector = connector;
+  o.bridge = __shfl_sync(FULL, bridge, 0);
+  o.overflow = done == 2 || (done == 1 && !success);
   return o;
 }
 
@@ -391,9 +531,10 @@ rrt_persistent_kernel(const __grid_constant__ PlanConst pc, const __grid_constan
   if (k >= nq || !S.active[k]) return;
   __shared__ double qd[NWB_NJ];          // current query of the nearest-neighbour scan (q_rand, then q_connect)
   __shared__ float qf[NWB_NJ];
+  __shared__ double qv[NWB_NJ];          // configuration under the warp-wide validity evaluation
   const MaView ma{ma_pts ? ma_pts + (size_t)k * n_pts * 6 : nullptr, n_pts};
   int size[2] = {F.size[2 * k], F.size[2 * k + 1]};      // kept in registers of every lane
-  const RrtOutcome o = rrt_query_loop<STATIC>(pc, tab, F, k, lane, seeds[k], db, n_db, max_iter, ma, qd, qf, size, S.overflow);
+  const RrtOutcome o = rrt_query_loop<STATIC>(pc, tab, F, k, lane, seeds[k], db, n_db, max_iter, ma, qd, qf, qv, size, S.overflow);
   if (lane == 0) {
     F.size[2 * k] = size[0];
     F.size[2 * k + 1] = size[1];
@@ -429,22 +570,24 @@ rrt_fused_kernel(const __grid_constant__ PlanConst pc, const __grid_constant__ V
   if (k >= nq) return;
   __shared__ double qd[NWB_NJ];
   __shared__ float qf[NWB_NJ];
+  __shared__ double qv[NWB_NJ];
   const MaView ma{ma_pts ? ma_pts + (size_t)k * n_pts * 6 : nullptr, n_pts};
   int32_t* res = io.res + (size_t)k * 12;
   const int ts = 2 * k, tg = 2 * k + 1;
   // ---- setStartGoalConfigs: both roots must be valid (RP:241-265)
-  int ok = 0;
+  if (lane < NWB_NJ) qv[lane] = io.starts[(size_t)k * NWB_NJ + lane];
+  __syncwarp();
+  const int sv = config_valid<STATIC>(tab, qv, lane);
+  __syncwarp();
+  if (lane < NWB_NJ) qv[lane] = io.goals[(size_t)k * NWB_NJ + lane];
+  __syncwarp();
+  const int gv = config_valid<STATIC>(tab, qv, lane);
+  const int ok = sv && gv;
   if (lane == 0) {
-    double q[NWB_NJ];
-    for (int j = 0; j < NWB_NJ; ++j) q[j] = io.starts[(size_t)k * NWB_NJ + j];
-    const int sv = config_valid<STATIC>(tab, q);
-    for (int j = 0; j < NWB_NJ; ++j) q[j] = io.goals[(size_t)k * NWB_NJ + j];
-    const int gv = config_valid<STATIC>(tab, q);
     for (int j = 0; j < 12; ++j) res[j] = 0;
     res[0] = sv;
     res[1] = gv;
     res[9] = -1;
-    ok = sv && gv;
     if (ok) {                                             // roots: index 0, predecessor 0 (RP:236-258)
       for (int side = 0; side < 2; ++side) {
         const int t = side ? tg : ts;
@@ -459,10 +602,9 @@ rrt_fused_kernel(const __grid_constant__ PlanConst pc, const __grid_constant__ V
     }
   }
   __syncwarp();
-  ok = __shfl_sync(0xffffffffu, ok, 0);
   if (!ok) return;
   int size[2] = {1, 1};
-  const RrtOutcome o = rrt_query_loop<STATIC>(pc, tab, F, k, lane, io.seeds[k], db, n_db, max_iter, ma, qd, qf, size, overflow_flag);
+  const RrtOutcome o = rrt_query_loop<STATIC>(pc, tab, F, k, lane, io.seeds[k], db, n_db, max_iter, ma, qd, qf, qv, size, overflow_flag);
   // ---- results + raw path
   int ls = 0, lg = 0, idx_s = 0, idx_g = 0;
   long long off = -1;
