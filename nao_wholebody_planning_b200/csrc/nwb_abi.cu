@@ -19,14 +19,7 @@ using namespace nwb;
 namespace {
 thread_local std::string g_create_error;
 
-#define NWB_CUDA(ctx, call)                                                                   \
-  do {                                                                                        \
-    cudaError_t e_ = (call);                                                                  \
-    if (e_ != cudaSuccess) {                                                                  \
-      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                        \
-      return NWB_E_CUDA;                                                                      \
-    }                                                                                         \
-  } while (0)
+#define NWB_CUDA(ctx, call) NWB_TRY_CUDA(ctx, call)
 
 int fail(Ctx* ctx, int code, const char* msg) {
   if (ctx) ctx->err = msg;

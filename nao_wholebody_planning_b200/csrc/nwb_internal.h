@@ -181,3 +181,44 @@ cudaError_t launch_ma_project(const PlanConst& pc, const double* ma_pts, int n_p
 }  // namespace nwb
 
 struct nwb_ctx : nwb::Ctx {};
+
+// ---- helpers shared by the extern "C" translation units ----------------------------------------------------------------
+// CUDA call -> NWB_E_CUDA with the failing expression and the runtime's message in nwb_last_error()
+#define NWB_TRY_CUDA(ctx, call)                                                \
+  do {                                                                         \
+    cudaError_t e_ = (call);                                                   \
+    if (e_ != cudaSuccess) {                                                   \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_);         \
+      return NWB_E_CUDA;                                                       \
+    }                                                                          \
+  } while (0)
+
+namespace nwb {
+// bump allocator over the context's planner scratch buffer (grow-only), 256-byte aligned sections
+struct DeviceArena {
+  nwb_ctx* ctx;
+  size_t off = 0;
+  explicit DeviceArena(nwb_ctx* c) : ctx(c) {}
+  size_t add(size_t bytes) {
+    size_t o = off;
+    off += (bytes + 255) & ~(size_t)255;
+    return o;
+  }
+  int commit() {
+    if (off <= ctx->d_plan_bytes) return NWB_OK;
+    if (ctx->d_plan) cudaFree(ctx->d_plan);
+    ctx->d_plan = nullptr;
+    ctx->d_plan_bytes = 0;
+    size_t cap = off > ((size_t)1 << 20) ? off : ((size_t)1 << 20);
+    cudaError_t e = cudaMalloc(&ctx->d_plan, cap);
+    if (e != cudaSuccess) {
+      ctx->err = std::string("cudaMalloc(scratch): ") + cudaGetErrorString(e);
+      return NWB_E_CUDA;
+    }
+    ctx->d_plan_bytes = cap;
+    return NWB_OK;
+  }
+  template <class T>
+  T* at(size_t o) const { return reinterpret_cast<T*>(static_cast<char*>(ctx->d_plan) + o); }
+};
+}  // namespace nwb

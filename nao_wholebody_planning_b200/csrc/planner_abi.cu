@@ -15,48 +15,14 @@
 using namespace nwb;
 
 namespace {
-#define P_CUDA(ctx, call)                                                      \
-  do {                                                                         \
-    cudaError_t e_ = (call);                                                   \
-    if (e_ != cudaSuccess) {                                                   \
-      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_);         \
-      return NWB_E_CUDA;                                                       \
-    }                                                                          \
-  } while (0)
+#define P_CUDA(ctx, call) NWB_TRY_CUDA(ctx, call)
 
 int bad(nwb_ctx* ctx, const char* msg) {
   if (ctx) ctx->err = msg;
   return NWB_E_INVALID;
 }
 
-// bump allocator over one device scratch buffer, 256-byte aligned sections
-struct Arena {
-  nwb_ctx* ctx;
-  size_t off = 0;
-  std::vector<size_t> sizes;
-  explicit Arena(nwb_ctx* c) : ctx(c) {}
-  size_t add(size_t bytes) {
-    size_t o = off;
-    off += (bytes + 255) & ~(size_t)255;
-    return o;
-  }
-  int commit() {
-    if (off <= ctx->d_plan_bytes) return NWB_OK;
-    if (ctx->d_plan) cudaFree(ctx->d_plan);
-    ctx->d_plan = nullptr;
-    ctx->d_plan_bytes = 0;
-    size_t cap = std::max(off, (size_t)1 << 20);
-    cudaError_t e = cudaMalloc(&ctx->d_plan, cap);
-    if (e != cudaSuccess) {
-      ctx->err = std::string("cudaMalloc(scratch): ") + cudaGetErrorString(e);
-      return NWB_E_CUDA;
-    }
-    ctx->d_plan_bytes = cap;
-    return NWB_OK;
-  }
-  template <class T>
-  T* at(size_t o) const { return reinterpret_cast<T*>(static_cast<char*>(ctx->d_plan) + o); }
-};
+using Arena = nwb::DeviceArena;
 
 bool static_pairs(const nwb_ctx* ctx) { return ctx->params.srdf_trim != 0 && !ctx->force_table_pairs; }
 }  // namespace

@@ -236,21 +236,8 @@ rrt_path_kernel(ForestView F, const int32_t* __restrict__ success, const int32_t
 using namespace nwb;
 
 namespace {
-#define R_CUDA(ctx, call)                                                      \
-  do {                                                                         \
-    cudaError_t e_ = (call);                                                   \
-    if (e_ != cudaSuccess) {                                                   \
-      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_);         \
-      return NWB_E_CUDA;                                                       \
-    }                                                                          \
-  } while (0)
+#define R_CUDA(ctx, call) NWB_TRY_CUDA(ctx, call)
 
-struct DevBuf {
-  void* p = nullptr;
-  ~DevBuf() { if (p) cudaFree(p); }
-  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, std::max<size_t>(bytes, 16)); }
-  template <class T> T* as() const { return static_cast<T*>(p); }
-};
 }  // namespace
 
 // One upload, one launch, one download: the default form of solveQuery for nq queries (rrt_fused_kernel).

@@ -33,14 +33,7 @@ void make_plan_const(const nwb_ctx* ctx, const double* weights, double step, Pla
 }
 
 namespace {
-#define S_CUDA(ctx, call)                                                      \
-  do {                                                                         \
-    cudaError_t e_ = (call);                                                   \
-    if (e_ != cudaSuccess) {                                                   \
-      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_);         \
-      return NWB_E_CUDA;                                                       \
-    }                                                                          \
-  } while (0)
+#define S_CUDA(ctx, call) NWB_TRY_CUDA(ctx, call)
 
 int bad(nwb_ctx* ctx, const char* msg) {
   if (ctx) ctx->err = msg;
@@ -48,33 +41,7 @@ int bad(nwb_ctx* ctx, const char* msg) {
 }
 bool static_pairs(const nwb_ctx* ctx) { return ctx->params.srdf_trim != 0 && !ctx->force_table_pairs; }
 
-// device scratch of this file's operators (shares the planner scratch buffer of the context)
-struct Scratch {
-  nwb_ctx* ctx;
-  size_t off = 0;
-  explicit Scratch(nwb_ctx* c) : ctx(c) {}
-  size_t add(size_t bytes) {
-    size_t o = off;
-    off += (bytes + 255) & ~(size_t)255;
-    return o;
-  }
-  int commit() {
-    if (off <= ctx->d_plan_bytes) return NWB_OK;
-    if (ctx->d_plan) cudaFree(ctx->d_plan);
-    ctx->d_plan = nullptr;
-    ctx->d_plan_bytes = 0;
-    size_t cap = std::max(off, (size_t)1 << 20);
-    cudaError_t e = cudaMalloc(&ctx->d_plan, cap);
-    if (e != cudaSuccess) {
-      ctx->err = std::string("cudaMalloc(scratch): ") + cudaGetErrorString(e);
-      return NWB_E_CUDA;
-    }
-    ctx->d_plan_bytes = cap;
-    return NWB_OK;
-  }
-  template <class T>
-  T* at(size_t o) const { return reinterpret_cast<T*>(static_cast<char*>(ctx->d_plan) + o); }
-};
+using Scratch = nwb::DeviceArena;
 
 // the goal files keep 6 significant digits: `ofstream << double` (SCG:409-417), re-read with strtod (SCG:540-560)
 double through_text(double v) {
