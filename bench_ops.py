@@ -252,7 +252,8 @@ def main():
         n_d = torch.zeros(1, dtype=torch.int64, device=dev)
 
     def gen():
-        n_d.zero_()
+        with torch.cuda.stream(stream):                 # the counter must be cleared on the stream the sampler runs on
+            n_d.zero_()
         ctx.lib.nwb_sample_stable_configs_dev(ctx.h, 20121005, 0, count, 5, rows_d.data_ptr(), idx_d.data_ptr(), count,
                                               n_d.data_ptr(), None)
     ms = dev_time(gen, stream, reps=3, warm=1)

@@ -39,7 +39,10 @@ __device__ __forceinline__ ValidityResult<float> eval_one(const ValidityTables& 
 }
 
 // ---- steer + project ----------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+#ifndef NWB_STEER_MIN_BLOCKS
+#define NWB_STEER_MIN_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(128, NWB_STEER_MIN_BLOCKS)
 steer_project_kernel(const __grid_constant__ PlanConst pc, const double* __restrict__ q_near, const double* __restrict__ q_target,
                      int64_t n, double* __restrict__ q_out, int32_t* __restrict__ status, int32_t* __restrict__ ds_status,
                      int32_t* __restrict__ iters) {
@@ -725,8 +728,12 @@ __global__ void edge_finish_kernel(int32_t* __restrict__ first_bad, int64_t n_ed
 // ---- stable-configuration sampler ------------------------------------------------------------------------
 // Sample i draws its 21 joints from Philox(seed; counter = (i, slot/4, stream)), so the accepted set
 // is independent of how [first, first+count) is partitioned over launches, streams or GPUs.
+#ifndef NWB_SAMPLE_MIN_BLOCKS
+#define NWB_SAMPLE_MIN_BLOCKS 6      // resident 64-thread blocks per SM the register allocation aims at (168 registers;
+                                     // measured 23.4 M samples/s against 21.5 at 4 blocks / 255 registers and 21.9 at 8 / 128)
+#endif
 template <bool STATIC>
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(64, NWB_SAMPLE_MIN_BLOCKS)
 sample_kernel(const __grid_constant__ PlanConst pc, const __grid_constant__ ValidityTables tab, uint64_t seed, uint64_t first,
               int64_t count, int max_ik_iter, double* __restrict__ rows /*[cap][21]*/, uint64_t* __restrict__ row_index,
               int64_t cap, unsigned long long* __restrict__ n_out, uint8_t* __restrict__ stage_out) {
