@@ -108,3 +108,33 @@ def test_shortcutter_and_interpolation_match_oracle(oracle):
                 assert len(dense) == (len(short) - 1) * 101 + 1
                 n_checked += 1
         assert n_checked >= 6
+
+
+@pytest.mark.parametrize("env", ["NWB_RRT_STAGED", "NWB_RRT_LOCKSTEP"])
+def test_alternative_drivers_give_the_same_plans(env, tmp_path):
+    """The earlier RRT drivers (staged root validation / path extraction; lock-step kernels per iteration) stay
+    selectable through the environment and must produce exactly what the fused one-launch driver produces."""
+    import json
+    import os
+    import subprocess
+    import sys
+    code = """
+import sys, json
+sys.path.insert(0, 'tests'); sys.path.insert(0, '.')
+import numpy as np, oracle_lib as OL, nao_wholebody_planning_b200 as nwb
+db = OL.golden_db(); rng = np.random.default_rng(3)
+starts = db[rng.integers(0, len(db), 12)]; goals = db[rng.integers(0, len(db), 12)]
+w = np.ones(21); w[15] = 0
+with nwb.Context() as c:
+    res, paths = c.solveQuery(starts, goals, db, np.arange(12, dtype=np.uint64) + 50, w, max_iter=300)
+print(json.dumps([[r['success'], r['iterations'], r['num_nodes_generated'], r['raw_path_len'], float(np.nansum(p))] for r, p in zip(res, paths)]))
+"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for extra in ({}, {env: "1"}):
+        e = dict(os.environ, **extra)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=root, env=e, timeout=300)
+        assert r.returncode == 0, r.stderr[-1500:]
+        outs.append(json.loads(r.stdout.strip().splitlines()[-1]))
+    assert outs[0] == outs[1]
+    assert sum(o[0] for o in outs[0]) >= 6
