@@ -341,6 +341,26 @@ def main():
     e2e_value = n * world * e2e_steps / e2e_dt
     e2e_valid = pin_v.array.copy()
     assert (e2e_valid == valid.cpu().numpy()).all(), "host-buffer path and device path disagree"
+    # supplementary: the same call for a caller that keeps its configurations in float32 (half the PCIe bytes)
+    pin_qf = nwb.PinnedArray((n, nwb.NJ), np.float32)
+    pin_vf = nwb.PinnedArray((n,), np.uint8)
+    pin_qf.array[:] = q_host.astype(np.float32)
+    for _ in range(2):
+        ctx.is_feasible_host_buffers_f32(pin_qf.ptr, n, pin_vf.ptr)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ctx.is_feasible_host_buffers_f32(pin_qf.ptr, n, pin_vf.ptr)
+    torch.cuda.synchronize(dev)
+    e2e32_dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e32_dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e32_dt = float(t.item())
+    e2e32_value = n * world * e2e_steps / e2e32_dt
+    e2e32_same = int((pin_vf.array == e2e_valid).sum())
+    pin_qf.free()
+    pin_vf.free()
 
     if rank == 0:
         rf = load_json(ROOT / "profiles" / "roofline.json", {})
@@ -367,7 +387,10 @@ def main():
                                              "all_gather after the timed region: %s" % gather_ok) if world > 1 else None,
                            "valid_fraction": float(valid.float().mean().item())},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * nwb.NJ * 8, "d2h_bytes_per_step": n,
-                        "steps": e2e_steps, "api": "nwb_is_feasible_batch (pinned host buffers)"},
+                        "steps": e2e_steps, "api": "nwb_is_feasible_batch (pinned host buffers, float64 as the reference keeps them)"},
+                "e2e_f32_input": {"value": e2e32_value, "unit": UNIT, "h2d_bytes_per_step": n * nwb.NJ * 4, "d2h_bytes_per_step": n,
+                                  "api": "nwb_is_feasible_batch_f32 (supplementary: callers holding float32 configurations)",
+                                  "verdicts_equal_to_f64_input": e2e32_same, "of": n},
                 "gpu_launches": args.steps, "clocks": clk, "roofline": roofline}
         if not args.no_cpu_baseline:
             cb, cpu_valid, cn = cpu_baseline(q_host)

@@ -152,6 +152,11 @@ NWB_API int nwb_scene_num_boxes(const nwb_ctx* ctx);
  */
 NWB_API int nwb_is_feasible_batch(nwb_ctx* ctx, const double* q, int64_t n, uint8_t* valid, uint8_t* reason,
                           float* margins);
+/* Same for callers that keep their configurations in single precision: q [n][21] float (host).  The kernels
+ * evaluate in fp32 either way (the fp64 input is rounded on load), so for float data the verdicts are those of
+ * nwb_is_feasible_batch on the widened values; the host->device traffic, which bounds this entry point, halves. */
+NWB_API int nwb_is_feasible_batch_f32(nwb_ctx* ctx, const float* q, int64_t n, uint8_t* valid, uint8_t* reason,
+                                      float* margins);
 /* Same, device-resident.  q_dev is [n][21] of `dtype` (NWB_F64 | NWB_F32). */
 NWB_API int nwb_is_feasible_batch_dev(nwb_ctx* ctx, const void* q_dev, int dtype, int64_t n,
                               uint8_t* valid_dev, uint8_t* reason_dev, float* margins_dev);

@@ -183,6 +183,7 @@ def _declare(lib):
         "nwb_scene_add_box": (C.c_int, [vp, pd, pd, pd]),
         "nwb_scene_num_boxes": (C.c_int, [vp]),
         "nwb_is_feasible_batch": (C.c_int, [vp, vp, i64, vp, vp, vp]),
+        "nwb_is_feasible_batch_f32": (C.c_int, [vp, vp, i64, vp, vp, vp]),
         "nwb_is_feasible_batch_dev": (C.c_int, [vp, vp, C.c_int, i64, vp, vp, vp]),
         "nwb_is_state_colliding_batch": (C.c_int, [vp, vp, i64, vp, vp]),
         "nwb_fk_batch": (C.c_int, [vp, vp, i64, vp, vp]),

@@ -104,6 +104,11 @@ class Context:
                     "nwb_is_feasible_batch")
         return valid, reason, margins
 
+    def is_feasible_host_buffers_f32(self, q_ptr, n, valid_ptr, reason_ptr=None, margins_ptr=None):
+        """nwb_is_feasible_batch_f32 on raw host pointers (float32 configurations)."""
+        self._check(self.lib.nwb_is_feasible_batch_f32(self.h, q_ptr, int(n), valid_ptr, reason_ptr, margins_ptr),
+                    "nwb_is_feasible_batch_f32")
+
     def is_feasible_host_buffers(self, q_ptr, n, valid_ptr, reason_ptr=None, margins_ptr=None):
         """Raw-pointer form (pinned buffers from host_alloc) used by the end-to-end benchmark."""
         self._check(self.lib.nwb_is_feasible_batch(self.h, q_ptr, n, valid_ptr, reason_ptr, margins_ptr),

@@ -253,13 +253,14 @@ int nwb_is_feasible_batch_dev(nwb_ctx* ctx, const void* q_dev, int dtype, int64_
 
 // Host-buffer operator: chunks of the batch are copied in, checked and copied out on the context's
 // stream.  With pinned caller buffers (nwb_host_alloc) the copies run at full PCIe speed.
-static int feasible_host(nwb_ctx* ctx, const ValidityTables& tab, const double* q, int64_t n, uint8_t* valid,
+static int feasible_host(nwb_ctx* ctx, const ValidityTables& tab, const void* q, int dtype, int64_t n, uint8_t* valid,
                          uint8_t* reason, float* margins, bool collision_only) {
   if (n == 0) return NWB_OK;
   NWB_CUDA(ctx, cudaSetDevice(ctx->device));
   const int mcols = collision_only ? 1 : 2;
   const int64_t chunk = std::min<int64_t>(n, (int64_t)1 << 18);
-  const size_t in_bytes = (size_t)chunk * NWB_NJ * sizeof(double);
+  const size_t elem = dtype == NWB_F32 ? sizeof(float) : sizeof(double);
+  const size_t in_bytes = (size_t)chunk * NWB_NJ * elem;
   const size_t chunk_a = ((size_t)chunk + 255) & ~(size_t)255;          // keeps every section 256 B aligned
   const size_t out_bytes = chunk_a * (2 + sizeof(float) * mcols);
   int rc;
@@ -283,10 +284,11 @@ static int feasible_host(nwb_ctx* ctx, const ValidityTables& tab, const double* 
     float* d_marg = (float*)(dout + 2 * chunk_a);
     // the buffer pair s was last used by chunk c-2: its kernel / copy-out are ordered on ctx->stream
     if (c >= 2) NWB_CUDA(ctx, cudaStreamWaitEvent(copy_stream, k_done[s], 0));
-    NWB_CUDA(ctx, cudaMemcpyAsync(din, q + off * NWB_NJ, (size_t)cn * NWB_NJ * sizeof(double), cudaMemcpyHostToDevice, copy_stream));
+    NWB_CUDA(ctx, cudaMemcpyAsync(din, static_cast<const char*>(q) + (size_t)off * NWB_NJ * elem, (size_t)cn * NWB_NJ * elem,
+                                  cudaMemcpyHostToDevice, copy_stream));
     NWB_CUDA(ctx, cudaEventRecord(in_done[s], copy_stream));
     NWB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, in_done[s], 0));
-    NWB_CUDA(ctx, launch_validity(tab, din, NWB_F64, cn, d_valid, reason ? d_reason : nullptr, margins ? d_marg : nullptr,
+    NWB_CUDA(ctx, launch_validity(tab, din, dtype, cn, d_valid, reason ? d_reason : nullptr, margins ? d_marg : nullptr,
                                   collision_only, ctx->params.srdf_trim != 0 && !ctx->force_table_pairs, ctx->stream));
     ++launches;
     NWB_CUDA(ctx, cudaMemcpyAsync(valid + off, d_valid, (size_t)cn, cudaMemcpyDeviceToHost, ctx->stream));
@@ -304,13 +306,19 @@ static int feasible_host(nwb_ctx* ctx, const ValidityTables& tab, const double* 
 int nwb_is_feasible_batch(nwb_ctx* ctx, const double* q, int64_t n, uint8_t* valid, uint8_t* reason, float* margins) {
   if (!ctx) return NWB_E_INVALID;
   if (n < 0 || (n > 0 && (!q || !valid))) return fail(ctx, NWB_E_INVALID, "nwb_is_feasible_batch: bad argument");
-  return feasible_host(ctx, ctx->tab_group, q, n, valid, reason, margins, false);
+  return feasible_host(ctx, ctx->tab_group, q, NWB_F64, n, valid, reason, margins, false);
+}
+
+int nwb_is_feasible_batch_f32(nwb_ctx* ctx, const float* q, int64_t n, uint8_t* valid, uint8_t* reason, float* margins) {
+  if (!ctx) return NWB_E_INVALID;
+  if (n < 0 || (n > 0 && (!q || !valid))) return fail(ctx, NWB_E_INVALID, "nwb_is_feasible_batch_f32: bad argument");
+  return feasible_host(ctx, ctx->tab_group, q, NWB_F32, n, valid, reason, margins, false);
 }
 
 int nwb_is_state_colliding_batch(nwb_ctx* ctx, const double* q, int64_t n, uint8_t* colliding, float* min_separation) {
   if (!ctx) return NWB_E_INVALID;
   if (n < 0 || (n > 0 && (!q || !colliding))) return fail(ctx, NWB_E_INVALID, "nwb_is_state_colliding_batch: bad argument");
-  return feasible_host(ctx, ctx->tab_all, q, n, colliding, nullptr, min_separation, true);
+  return feasible_host(ctx, ctx->tab_all, q, NWB_F64, n, colliding, nullptr, min_separation, true);
 }
 
 // ---- FK -----------------------------------------------------------------------------------------

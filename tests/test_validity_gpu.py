@@ -133,6 +133,16 @@ def test_full_size_properties(ctx):
     assert 0.05 < v1.mean() < 0.3
 
 
+def test_float32_host_entry_point(ctx):
+    """nwb_is_feasible_batch_f32: verdicts of the widened float configurations."""
+    q = OL.uniform_configs(30000, seed=77)
+    qf = np.ascontiguousarray(q.astype(np.float32))
+    vf, rf = np.empty(len(q), np.uint8), np.empty(len(q), np.uint8)
+    ctx.is_feasible_host_buffers_f32(qf.ctypes.data, len(q), vf.ctypes.data, rf.ctypes.data)
+    v, r, _ = ctx.isFeasible(qf.astype(np.float64))
+    assert (vf == v).all() and (rf == r).all()
+
+
 def test_device_pointer_variant_f32_and_f64(ctx, oracle):
     import torch
     q = OL.noisy_db_configs(50000, seed=13)
