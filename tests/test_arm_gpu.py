@@ -277,6 +277,38 @@ def test_time_parameterization_matches_oracle(ctx, oracle):
         assert np.allclose(np.diff(r["tfs_approach"]), 1.0)
 
 
+def test_motion_plan_service_with_scene_boxes(oracle):
+    """The drawer + beam scene (PAR:465-472) in front of the robot: goal sampling rejects colliding goal postures,
+    the search and the shortcutter see the boxes; same plan as the oracle."""
+    db = OL.golden_db()
+    boxes = OL.scene_boxes("S3")
+    pose = [0.24, -0.065, 0.30, 0, -1, 0]
+    with nwb.Context() as c:
+        c.scene_add_boxes(boxes)
+        c.set_ds_database(db)
+        r = c.compute_motion_plan(pose[:3], pose[3:], START, 20121003)
+        free = nwb.Context()
+        free.set_ds_database(db)
+        r0 = free.compute_motion_plan(pose[:3], pose[3:], START, 20121003)
+        free.close()
+    o = oracle.compute_motion_plan(db, pose, START, 20121003, boxes=boxes)
+    assert r["success"] == o["success"] and r["num_nodes_generated"] == o["num_nodes"]
+    assert np.abs(r["wb_goal_config"] - o["goal_config"]).max() < 2e-6
+    assert r["trajectory"].shape == o["trajectory"].shape
+    if o["success"]:
+        assert np.abs(r["trajectory"] - o["trajectory"]).max() < 1e-5
+        col, _ = oracle.is_state_colliding(r["trajectory"][::10], boxes=boxes)
+        assert not col.any()
+    # a hand pose inside the shelf of scene S1 (between two boards): every goal posture collides -> no plan, no error
+    with nwb.Context() as c:
+        c.scene_add_boxes(OL.scene_boxes("S1"))
+        c.set_ds_database(db)
+        r1 = c.compute_motion_plan([0.30, -0.06, 0.30], [0, -1, 0], START, 7)
+    o1 = oracle.compute_motion_plan(db, [0.30, -0.06, 0.30, 0, -1, 0], START, 7, boxes=OL.scene_boxes("S1"))
+    assert r1["success"] == o1["success"] and len(r1["trajectory"]) == len(o1["trajectory"])
+    assert r0["success"]
+
+
 def test_services_need_a_database(oracle):
     with nwb.Context() as c:
         with pytest.raises(nwb.NwbError, match="database"):
