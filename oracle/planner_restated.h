@@ -689,7 +689,7 @@ inline void sample_stable_configs(const PlanParams& pp, uint64_t seed, uint64_t 
 // ConstraintKinematics::compute_ergonomics_index (NCK:612-659): q0 * |"determinant"| where the
 // "determinant" of the 6x5 arm Jacobian is the shipped diagonal-product formula over [J J]:
 // forward sum of the 5 wrapped diagonals minus a "backward" sum that multiplies ONE column down all
-// six rows (quirk C15: not an anti-diagonal).
+// six rows (quirk C10: not an anti-diagonal).
 inline double ergonomics_index(const double* arm5) {
   double J[6 * 5];
   kdlr::jacobian(chains().right_arm, arm5, J);
@@ -713,7 +713,7 @@ inline double ergonomics_index(const double* arm5) {
 // ConstraintKinematics::computeRightArmIK (NCK:224-506).
 // Generated-solver branch (NCK:374-506): among the solutions inside the strict limits keep the one with the
 // LARGEST ergonomics index, starting from 0.0 - a posture with RShoulderPitch <= 0 can therefore never be
-// chosen (quirk C16).
+// chosen (quirk C15).
 // Position-only branch (NCK:291-372), taken when the requested direction is exactly (0,0,0): KDL NR on the
 // right-arm chain towards Frame(position in the HIP frame) - identity rotation, so the hand orientation is
 // constrained after all - from up to 5 random seeds inside the arm limits; the ergonomics index is left
