@@ -90,14 +90,24 @@ constexpr int NN_CAND_MAX = 512;  // exact-pass candidates a block lists (a hand
 // while the threads compute on the stage that has landed.  Per tile the block first agrees on the
 // running fp32 minimum per query (warp shuffle + shared atomicMin on the float bits), then only the
 // nodes within the error bound of that minimum take the exact fp64 path.
+// nodes per thread and tile geometry: one query streams 2 nodes per thread through 4 stages of 512 nodes; a query
+// group takes 4 nodes per thread (a broadcast load of the query values then feeds twice the arithmetic) through
+// 2 stages of 1024 nodes - the same 172 KB of shared memory either way.
+template <int QT> struct NnCfg {
+  static constexpr int NPT = QT > 1 ? 4 : 2;
+  static constexpr int TILE = NN_THREADS * NPT;
+  static constexpr int STAGES = (NN_TILE * NN_STAGES) / TILE;
+};
+
 template <int QT>
 __global__ void __launch_bounds__(NN_THREADS, 1)
 nn_scan_kernel(const float* __restrict__ soa, const double* __restrict__ aos, int64_t cap, int64_t N,
                const double* __restrict__ q, int64_t nq, double* __restrict__ part_d, int32_t* __restrict__ part_i,
                unsigned* __restrict__ tickets, int32_t* __restrict__ idx_out, double* __restrict__ dist_out) {
+  constexpr int NPT = NnCfg<QT>::NPT, TILE = NnCfg<QT>::TILE, STAGES = NnCfg<QT>::STAGES;
   extern __shared__ __align__(128) unsigned char nn_smem[];
-  float* ring = reinterpret_cast<float*>(nn_smem);                           // [NN_STAGES][21][NN_TILE]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(nn_smem + sizeof(float) * NN_STAGES * NWB_NJ * NN_TILE);
+  float* ring = reinterpret_cast<float*>(nn_smem);                           // [STAGES][21][TILE]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(nn_smem + sizeof(float) * STAGES * NWB_NJ * TILE);
   __shared__ double qd[QT][NWB_NJ];
   __shared__ float qf[QT][NWB_NJ];
   __shared__ __align__(16) float2 qn2[NWB_NJ][QT];     // (-q, -q): second operand of the packed subtract
@@ -117,22 +127,22 @@ nn_scan_kernel(const float* __restrict__ soa, const double* __restrict__ aos, in
   if (tid < QT) run_min[tid] = 0x7f7fffffu;           // FLT_MAX
   if (tid == 0) {
     overflow = 0;
-    for (int sg = 0; sg < NN_STAGES; ++sg) nn_mbar_init(&bars[sg], 1);
+    for (int sg = 0; sg < STAGES; ++sg) nn_mbar_init(&bars[sg], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  const int64_t tiles = (N + NN_TILE - 1) / NN_TILE;
+  const int64_t tiles = (N + TILE - 1) / TILE;
   auto issue = [&](int64_t tile, int stage) {          // thread 0: 21 row copies of one tile
-    const int64_t n0 = tile * NN_TILE;
-    const int64_t cnt = min((int64_t)NN_TILE, ((N - n0) + 3) & ~(int64_t)3);   // rows are padded to 64 nodes
+    const int64_t n0 = tile * TILE;
+    const int64_t cnt = min((int64_t)TILE, ((N - n0) + 3) & ~(int64_t)3);   // rows are padded to 64 nodes
     const uint32_t bytes = (uint32_t)(cnt * sizeof(float));
     nn_mbar_expect_tx(&bars[stage], bytes * NWB_NJ);
-    float* dst = ring + (size_t)stage * NWB_NJ * NN_TILE;
-    for (int j = 0; j < NWB_NJ; ++j) nn_bulk_g2s(dst + j * NN_TILE, soa + (int64_t)j * cap + n0, bytes, &bars[stage]);
+    float* dst = ring + (size_t)stage * NWB_NJ * TILE;
+    for (int j = 0; j < NWB_NJ; ++j) nn_bulk_g2s(dst + j * TILE, soa + (int64_t)j * cap + n0, bytes, &bars[stage]);
   };
   if (tid == 0)
-    for (int sg = 0; sg < NN_STAGES; ++sg) {
+    for (int sg = 0; sg < STAGES; ++sg) {
       const int64_t t = (int64_t)blockIdx.x + (int64_t)sg * gridDim.x;
       if (t < tiles) issue(t, sg);
     }
@@ -151,43 +161,61 @@ nn_scan_kernel(const float* __restrict__ soa, const double* __restrict__ aos, in
   int stage = 0;
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     nn_mbar_wait(&bars[stage], phase);
-    const float* x = ring + (size_t)stage * NWB_NJ * NN_TILE;
-    const int64_t n0 = tile * NN_TILE;
+    const float* x = ring + (size_t)stage * NWB_NJ * TILE;
+    const int64_t n0 = tile * TILE;
     // A thread owns the node pair (2 tid, 2 tid + 1) of the tile and works on it with packed fp32 pairs
     // (add.f32x2 / fma.f32x2 -> FADD2 / FFMA2: two nodes per dispatch slot): per joint one 8-byte load of
     // the pair, then per query one packed subtract of the broadcast (-q, -q) and one packed multiply-add.
-    float2 s2[QT];
+    float2 s2[QT][NPT / 2];
 #pragma unroll
-    for (int k = 0; k < QT; ++k) s2[k] = make_float2(0.f, 0.f);
+    for (int k = 0; k < QT; ++k)
+#pragma unroll
+      for (int h = 0; h < NPT / 2; ++h) s2[k][h] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < NWB_NJ; ++j) {
-      const float2 x2 = *reinterpret_cast<const float2*>(&x[j * NN_TILE + 2 * tid]);
+      float2 x2[NPT / 2];
+      if constexpr (NPT == 4) {
+        const float4 v = *reinterpret_cast<const float4*>(&x[j * TILE + 4 * tid]);
+        x2[0] = make_float2(v.x, v.y);
+        x2[1] = make_float2(v.z, v.w);
+      } else {
+        x2[0] = *reinterpret_cast<const float2*>(&x[j * TILE + 2 * tid]);
+      }
 #pragma unroll
       for (int k = 0; k < QT; ++k) {
-        const float2 d = __fadd2_rn(x2, qn2[j][k]);
-        s2[k] = __ffma2_rn(d, d, s2[k]);
+        const float2 c = qn2[j][k];
+#pragma unroll
+        for (int h = 0; h < NPT / 2; ++h) {
+          const float2 d = __fadd2_rn(x2[h], c);
+          s2[k][h] = __ffma2_rn(d, d, s2[k][h]);
+        }
       }
     }
-    float s[QT][2];
+    float s[QT][NPT];
+#pragma unroll
+    for (int k = 0; k < QT; ++k)
+#pragma unroll
+      for (int h = 0; h < NPT / 2; ++h) {
+        s[k][2 * h] = s2[k][h].x;
+        s[k][2 * h + 1] = s2[k][h].y;
+      }
+    float lo[QT];                                       // the smallest of the thread's distances per query
 #pragma unroll
     for (int k = 0; k < QT; ++k) {
-      s[k][0] = s2[k].x;
-      s[k][1] = s2[k].y;
-    }
-    const bool live0 = n0 + 2 * tid < N, live1 = n0 + 2 * tid + 1 < N;
-    float lo[QT];                                       // the smaller of the thread's two distances per query
+      float m = 3.0e38f;
 #pragma unroll
-    for (int k = 0; k < QT; ++k) {
-      if (!live0) s[k][0] = 3.0e38f;
-      if (!live1) s[k][1] = 3.0e38f;
-      lo[k] = fminf(s[k][0], s[k][1]);
+      for (int u = 0; u < NPT; ++u) {
+        if (!(n0 + NPT * tid + u < N)) s[k][u] = 3.0e38f;
+        m = fminf(m, s[k][u]);
+      }
+      lo[k] = m;
       // non-negative floats order like their bit patterns: one REDUX.MIN instead of a shuffle ladder
-      const unsigned wmin = __reduce_min_sync(0xffffffffu, __float_as_uint(lo[k]));
+      const unsigned wmin = __reduce_min_sync(0xffffffffu, __float_as_uint(m));
       if ((tid & 31) == 0) atomicMin(&run_min[k], wmin);
     }
     __syncthreads();                                    // the stage is consumed and run_min is current
-    if (tid == 0) {                                     // refill this stage with the tile NN_STAGES rounds ahead
-      const int64_t nt = tile + (int64_t)NN_STAGES * gridDim.x;
+    if (tid == 0) {                                     // refill this stage with the tile STAGES rounds ahead
+      const int64_t nt = tile + (int64_t)STAGES * gridDim.x;
       if (nt < tiles) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         issue(nt, stage);
@@ -198,10 +226,10 @@ nn_scan_kernel(const float* __restrict__ soa, const double* __restrict__ aos, in
       const float bound = nn_candidate_bound(__uint_as_float(run_min[k]));
       if (lo[k] <= bound) {                             // rare: at least one of the two nodes is a candidate
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < NPT; ++u) {
           const float v = s[k][u];
           if (v <= bound) {                             // candidate (nodes arrive in ascending index per thread)
-            const int node = (int)(n0 + 2 * tid + u);
+            const int node = (int)(n0 + NPT * tid + u);
             if (v < cs[k][0]) { cs[k][1] = cs[k][0]; ci[k][1] = ci[k][0]; cs[k][0] = v; ci[k][0] = node; }
             else if (v < cs[k][1]) { cs[k][1] = v; ci[k][1] = node; }
             else ovf = true;                            // a third candidate: resolved by the exact rescan below
@@ -209,7 +237,7 @@ nn_scan_kernel(const float* __restrict__ soa, const double* __restrict__ aos, in
         }
       }
     }
-    if (++stage == NN_STAGES) { stage = 0; phase ^= 1u; }
+    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
   }
   if (ovf) overflow = 1;
   __syncthreads();
@@ -273,8 +301,8 @@ nn_scan_kernel(const float* __restrict__ soa, const double* __restrict__ aos, in
       besti[k] = -1;
     }
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x)
-      for (int u = 0; u < 2; ++u) {
-        const int64_t node = tile * NN_TILE + 2 * tid + u;
+      for (int u = 0; u < NPT; ++u) {
+        const int64_t node = tile * TILE + NPT * tid + u;
         if (node >= N) continue;
         for (int k = 0; k < QT; ++k) {
           float sv = 0.f;
