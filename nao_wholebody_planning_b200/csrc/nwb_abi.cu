@@ -149,6 +149,7 @@ void nwb_ctx_destroy(nwb_ctx* ctx) {
   if (ctx->d_rrt) cudaFree(ctx->d_rrt);
   if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+  if (ctx->d_work) cudaFree(ctx->d_work);
   if (ctx->d_dbcache) cudaFree(ctx->d_dbcache);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);

@@ -90,6 +90,7 @@ struct Ctx {
   std::vector<double> h_raw;                           // raw-path staging of the services (kept across calls)
   uint64_t ds_db_version = 0;                          // bumped whenever ds_db changes
   double* d_dbcache = nullptr; size_t d_dbcache_rows = 0; uint64_t d_dbcache_version = ~0ull;   // device copy of ds_db
+  void* d_work = nullptr; size_t d_work_bytes = 0;     // work list of the two-phase sampler (grow-only)
   void* h_pin = nullptr; size_t h_pin_bytes = 0;       // pinned staging of the fused RRT call (inputs out, results back)
   double last_ms = 0;
   int64_t last_launches = 0;
@@ -158,9 +159,10 @@ cudaError_t launch_connect(const PlanConst& pc, const ValidityTables& tab, bool 
                            int32_t* status, cudaStream_t s);
 cudaError_t launch_edge_check(const ValidityTables& tab, bool static_pairs, const double* qa, const double* qb, int64_t n_edges,
                               int k, uint8_t* ok, int32_t* first_bad, cudaStream_t s);
+// work [count] / work_n [1]: device scratch of the two-phase sampler (dense list of the samples that need the IK solve)
 cudaError_t launch_sample(const PlanConst& pc, const ValidityTables& tab, bool static_pairs, uint64_t seed, uint64_t first,
                           int64_t count, int max_ik_iter, double* rows, uint64_t* row_index, int64_t cap,
-                          unsigned long long* n_out, uint8_t* stage_out, cudaStream_t s);
+                          unsigned long long* n_out, uint8_t* stage_out, uint32_t* work, unsigned* work_n, cudaStream_t s);
 
 
 // right-arm kernels (arm_kernels.cu)

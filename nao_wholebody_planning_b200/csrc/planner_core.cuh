@@ -235,10 +235,26 @@ static __device__ __noinline__ void pinv_solve(const double (*W_in)[5], const do
   }
 }
 
+// false: the target is farther from the left hip joint than the leg can reach plus the convergence tolerance
+__device__ __forceinline__ bool left_leg_target_in_reach(const DFrame& target, double eps) {
+  const double L = 0.1 + 0.1029 + 0.04519, reach = L + 1.7320508075688772 * eps + 1e-6;
+  const double dx = target.p.x, dy = target.p.y - 0.05, dz = target.p.z;
+  return !(dx * dx + dy * dy + dz * dz > reach * reach);
+}
+
 // ChainIkSolverPos_NR::CartToJnt on the left-leg chain (base = hip frame).  The update is applied
 // BEFORE the convergence test.  Returns true on convergence; q holds the result.
 __device__ __forceinline__ bool left_leg_ik_nr(const DFrame& target, double* q /*[5] in: seed*/, int maxiter, double eps,
                                                double pinv_eps, int* iters_out) {
+  // Exact early out.  The left sole is c + R1 (0,0,-0.1) + R2 (0,0,-0.1029) + R3 (0,0,-0.04519) with
+  // c = (0,0.05,0), so for ANY joint vector it lies within L = 0.24809 m of c; convergence needs every twist
+  // component below eps, i.e. the sole within sqrt(3) eps of the target.  A target farther than L + sqrt(3) eps
+  // from c can therefore never be converged to: all `maxiter` iterations would run and fail (42 % of the failing
+  // solves on uniform samples).  The CPU oracle does run them - the parity tests check that the verdicts agree.
+  if (!left_leg_target_in_reach(target, eps)) {
+    if (iters_out) *iters_out = maxiter;
+    return false;
+  }
   double V[5][5];                                         // right singular vectors, carried across the iterations
 #pragma unroll
   for (int a = 0; a < 5; ++a)

@@ -732,15 +732,9 @@ __global__ void edge_finish_kernel(int32_t* __restrict__ first_bad, int64_t n_ed
 #define NWB_SAMPLE_MIN_BLOCKS 6      // resident 64-thread blocks per SM the register allocation aims at (168 registers;
                                      // measured 23.4 M samples/s against 21.5 at 4 blocks / 255 registers and 21.9 at 8 / 128)
 #endif
-template <bool STATIC>
-__global__ void __launch_bounds__(64, NWB_SAMPLE_MIN_BLOCKS)
-sample_kernel(const __grid_constant__ PlanConst pc, const __grid_constant__ ValidityTables tab, uint64_t seed, uint64_t first,
-              int64_t count, int max_ik_iter, double* __restrict__ rows /*[cap][21]*/, uint64_t* __restrict__ row_index,
-              int64_t cap, unsigned long long* __restrict__ n_out, uint8_t* __restrict__ stage_out) {
-  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= count) return;
-  const uint64_t i = first + (uint64_t)t;
-  double q[NWB_NJ];
+
+// sample i -> its 21 uniform joints, LHipYawPitch = 0 (SCG:285-291)
+__device__ __forceinline__ void sampler_draw(const PlanConst& pc, uint64_t seed, uint64_t i, double* q) {
 #pragma unroll 1
   for (int blk = 0; blk < (NWB_NJ + 3) / 4; ++blk) {
     uint32_t r[4];
@@ -751,18 +745,58 @@ sample_kernel(const __grid_constant__ PlanConst pc, const __grid_constant__ Vali
     }
   }
   q[15] = 0.0;                                           // SCG:291
+}
+
+// Phase 1: one thread per sample.  Draw the sample, run the right-leg FK and decide whether the left-foot target
+// can be reached at all (the exact test of left_leg_ik_nr).  The samples that still need the Newton-Raphson solve
+// are appended to a dense work list (one atomic per warp), so that phase 2 runs warps FULL of solves instead of
+// warps in which every lane waits for the one lane that needs all 100 iterations.
+__global__ void __launch_bounds__(128)
+sample_filter_kernel(const __grid_constant__ PlanConst pc, uint64_t seed, uint64_t first, int64_t count, int max_ik_iter,
+                     uint32_t* __restrict__ work, unsigned* __restrict__ work_n, uint8_t* __restrict__ stage_out) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool need = false;
+  if (t < count && max_ik_iter > 0) {
+    double q[NWB_NJ], rl[5];
+    sampler_draw(pc, seed, first + (uint64_t)t, q);
+    for (int m = 0; m < 5; ++m) rl[m] = -q[m];           // SCG:307-313
+    DFrame hip, target;
+    right_leg_fk(rl, hip);
+    desired_left_leg_pose(hip, target);
+    need = left_leg_target_in_reach(target, pc.ik_eps);
+  }
+  if (t < count && stage_out) stage_out[t] = 0;           // phase 2 overwrites it for the samples it solves
+  const unsigned mask = __ballot_sync(0xffffffffu, need);
+  if (mask) {
+    const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
+    unsigned base = 0;
+    if (lane == leader) base = atomicAdd(work_n, (unsigned)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (need) work[base + __popc(mask & ((1u << lane) - 1u))] = (uint32_t)t;
+  }
+}
+
+// Phase 2: one thread per work item: left-leg IK, validity, compaction of the kept rows.
+template <bool STATIC>
+__global__ void __launch_bounds__(64, NWB_SAMPLE_MIN_BLOCKS)
+sample_kernel(const __grid_constant__ PlanConst pc, const __grid_constant__ ValidityTables tab, uint64_t seed, uint64_t first,
+              int64_t count, int max_ik_iter, const uint32_t* __restrict__ work, const unsigned* __restrict__ work_n,
+              double* __restrict__ rows /*[cap][21]*/, uint64_t* __restrict__ row_index, int64_t cap,
+              unsigned long long* __restrict__ n_out, uint8_t* __restrict__ stage_out) {
+  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= (int64_t)*work_n) return;
+  const int64_t t = work[w];
+  const uint64_t i = first + (uint64_t)t;
+  double q[NWB_NJ];
+  sampler_draw(pc, seed, i, q);
   double rl[5], ll[5];
   for (int m = 0; m < 5; ++m) rl[m] = -q[m];             // SCG:307-313
   DFrame hip, target;
   right_leg_fk(rl, hip);
   desired_left_leg_pose(hip, target);
   uint8_t stage = 0;
-  bool solved = false;
-  for (int attempt = 0; attempt < max_ik_iter && !solved; ++attempt) {   // identical attempts (quirk C5)
-    for (int m = 0; m < 5; ++m) ll[m] = -rl[m];          // NCK:150 seed
-    if (left_leg_ik_nr(target, ll, pc.ik_maxiter, pc.ik_eps, pc.pinv_eps, nullptr)) solved = limits_ok(ll, pc.jmin + 16, pc.jmax + 16, 5);
-    if (!solved && attempt == 0 && max_ik_iter > 1) break;   // every further attempt repeats the same arithmetic
-  }
+  for (int m = 0; m < 5; ++m) ll[m] = -rl[m];            // NCK:150 seed; every further attempt repeats the same arithmetic (quirk C5)
+  const bool solved = left_leg_ik_nr(target, ll, pc.ik_maxiter, pc.ik_eps, pc.pinv_eps, nullptr) && limits_ok(ll, pc.jmin + 16, pc.jmax + 16, 5);
   if (solved) {
     for (int m = 0; m < 5; ++m) q[16 + m] = ll[m];
     ValidityResult<float> r = eval_one<false, STATIC>(tab, q);
@@ -850,11 +884,15 @@ cudaError_t launch_edge_check(const ValidityTables& tab, bool static_pairs, cons
 
 cudaError_t launch_sample(const PlanConst& pc, const ValidityTables& tab, bool static_pairs, uint64_t seed, uint64_t first,
                           int64_t count, int max_ik_iter, double* rows, uint64_t* row_index, int64_t cap,
-                          unsigned long long* n_out, uint8_t* stage_out, cudaStream_t s) {
+                          unsigned long long* n_out, uint8_t* stage_out, uint32_t* work, unsigned* work_n, cudaStream_t s) {
   if (count <= 0) return cudaSuccess;
+  cudaError_t e = cudaMemsetAsync(work_n, 0, sizeof(unsigned), s);
+  if (e != cudaSuccess) return e;
+  sample_filter_kernel<<<(unsigned)((count + 127) / 128), 128, 0, s>>>(pc, seed, first, count, max_ik_iter, work, work_n, stage_out);
+  // the size of the work list stays on the device: launch for the worst case, surplus blocks leave at once
   unsigned blocks = (unsigned)((count + 63) / 64);
-  if (static_pairs) sample_kernel<true><<<blocks, 64, 0, s>>>(pc, tab, seed, first, count, max_ik_iter, rows, row_index, cap, n_out, stage_out);
-  else sample_kernel<false><<<blocks, 64, 0, s>>>(pc, tab, seed, first, count, max_ik_iter, rows, row_index, cap, n_out, stage_out);
+  if (static_pairs) sample_kernel<true><<<blocks, 64, 0, s>>>(pc, tab, seed, first, count, max_ik_iter, work, work_n, rows, row_index, cap, n_out, stage_out);
+  else sample_kernel<false><<<blocks, 64, 0, s>>>(pc, tab, seed, first, count, max_ik_iter, work, work_n, rows, row_index, cap, n_out, stage_out);
   return cudaGetLastError();
 }
 
