@@ -86,7 +86,7 @@ goal_sample_kernel(const __grid_constant__ PlanConst pc, const __grid_constant__
                    const uint64_t* __restrict__ seeds, int nq, uint64_t first, int64_t count, int max_ik_iter,
                    double* __restrict__ rows, uint64_t* __restrict__ row_index, double* __restrict__ row_erg, int64_t cap,
                    unsigned long long* __restrict__ n_out, uint8_t* __restrict__ stage_out, double* __restrict__ erg_all,
-                   double* __restrict__ rows_all) {
+                   double* __restrict__ rows_all, int32_t* __restrict__ row_req) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= count * nq) return;
   const int qi = (int)(t / count);
@@ -134,9 +134,11 @@ goal_sample_kernel(const __grid_constant__ PlanConst pc, const __grid_constant__
     const bool feasible = !r.hit && r.stable;
     stage = feasible ? 2 : 1;
     if (feasible) {
-      unsigned long long slot = atomicAdd(n_out + qi, 1ull);
+      // row_req: all requests share ONE pool of cap rows (the host fetches only the rows in use), else cap rows each
+      unsigned long long slot = atomicAdd(row_req ? n_out : n_out + qi, 1ull);
       if ((int64_t)slot < cap) {
-        const size_t o = (size_t)qi * cap + slot;
+        const size_t o = row_req ? (size_t)slot : (size_t)qi * cap + slot;
+        if (row_req) row_req[o] = qi;
         for (int j = 0; j < NWB_NJ; ++j) rows[o * NWB_NJ + j] = q[j];
         row_index[o] = i;
         row_erg[o] = e;
@@ -149,6 +151,140 @@ goal_sample_kernel(const __grid_constant__ PlanConst pc, const __grid_constant__
   if (erg_all) erg_all[t] = e;
   if (rows_all)
     for (int j = 0; j < NWB_NJ; ++j) rows_all[t * NWB_NJ + j] = q[j];
+}
+
+// ---- the same sampler in three phases (service path: no per-sample outputs) ------------------------------------------
+// A request keeps ~0.2 % of its samples, and what rejects the others is cheap for most of them and expensive for a
+// few: in the one-kernel form every warp waits for its slowest lane (one 100-iteration leg solve stalls 31 rejected
+// neighbours).  So: (1) every sample runs the two exact reach tests, (2) the survivors - packed densely - run the
+// closed-form arm solve, (3) ITS survivors - packed again - run the leg solve and the validity test.  Each phase
+// redraws the sample from its counter (cheaper than carrying 21 doubles through memory).
+struct GoalDraw {
+  int qi;
+  uint64_t i, seed;
+  double q[NWB_NJ], rl[5];
+  DFrame hip;
+};
+__device__ __forceinline__ void goal_draw(const PlanConst& pc, const uint64_t* __restrict__ seeds, uint64_t first, int64_t count,
+                                          int64_t t, GoalDraw& g) {
+  g.qi = (int)(t / count);
+  g.i = first + (uint64_t)(t - (int64_t)g.qi * count);
+  g.seed = seeds[g.qi];
+#pragma unroll 1
+  for (int blk = 0; blk < (NWB_NJ + 3) / 4; ++blk) {
+    uint32_t r[4];
+    philox4x32_10((uint32_t)g.i, (uint32_t)(g.i >> 32), (uint32_t)blk, kStreamSampler, (uint32_t)g.seed, (uint32_t)(g.seed >> 32), r);
+    for (int l = 0; l < 4; ++l) {
+      int j = 4 * blk + l;
+      if (j < NWB_NJ) g.q[j] = __dadd_rn(__dmul_rn(pc.jmax[j] - pc.jmin[j], u01(r[l])), pc.jmin[j]);
+    }
+  }
+  g.q[15] = 0.0;
+  g.q[5] = 1.5708; g.q[6] = 0.17; g.q[7] = 0.0; g.q[8] = -0.036; g.q[9] = 0.0;     // SCG:296-300
+  for (int m = 0; m < 5; ++m) g.rl[m] = -g.q[m];
+  right_leg_fk(g.rl, g.hip);
+}
+// dense append of the lanes with `keep` to list[]: one atomic per warp; returns the lane's slot (undefined if !keep)
+__device__ __forceinline__ unsigned warp_append(bool keep, unsigned* counter) {
+  const unsigned mask = __ballot_sync(0xffffffffu, keep);
+  if (!mask) return 0;
+  const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
+  unsigned base = 0;
+  if (lane == leader) base = atomicAdd(counter, (unsigned)__popc(mask));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  return base + __popc(mask & ((1u << lane) - 1u));
+}
+
+// counters[0] = |work1|, counters[1] = |work2|
+__global__ void __launch_bounds__(128)
+goal_filter_kernel(const __grid_constant__ PlanConst pc, const double* __restrict__ poses, const uint64_t* __restrict__ seeds, int nq,
+                   uint64_t first, int64_t count, int max_ik_iter, uint32_t* __restrict__ work1, unsigned* __restrict__ counters) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool keep = false;
+  if (t < count * nq && max_ik_iter > 0) {
+    GoalDraw g;
+    goal_draw(pc, seeds, first, count, t, g);
+    const double* pose = poses + g.qi * 6;
+    DFrame target;
+    desired_left_leg_pose(g.hip, target);
+    keep = left_leg_target_in_reach(target, pc.ik_eps);
+    if (keep && !(pose[3] == 0.0 && pose[4] == 0.0 && pose[5] == 0.0)) {
+      // |grasp point - shoulder| <= |upper arm| + forearm + hand offset (scaled by |direction|): a necessary
+      // condition of the closed-form solve, with 1e-6 of slack against rounding
+      double p6[6];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) p6[j] = pose[j];
+      D3 pos, dir;
+      hand_target_in_torso(g.hip, p6, pos, dir);
+      const double dn = sqrt(ddot(dir, dir));
+      const double reach = sqrt(kArmUpperX * kArmUpperX + kArmUpperY * kArmUpperY) + kArmForearm + kArmHandOffset * fmax(1.0, dn) + 1e-6;
+      const double rx = pos.x, ry = pos.y - kArmShoulderY, rz = pos.z - kArmShoulderZ;
+      keep = !(rx * rx + ry * ry + rz * rz > reach * reach);
+    }
+  }
+  const unsigned slot = warp_append(keep, counters);
+  if (keep) work1[slot] = (uint32_t)t;
+}
+
+__global__ void __launch_bounds__(64)
+goal_arm_kernel(const __grid_constant__ PlanConst pc, const double* __restrict__ poses, const uint64_t* __restrict__ seeds,
+                uint64_t first, int64_t count, const uint32_t* __restrict__ work1, unsigned* __restrict__ counters,
+                uint32_t* __restrict__ work2, double* __restrict__ work2_arm /*[.][6]: 5 joints + ergonomics*/) {
+  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool keep = false;
+  uint32_t t = 0;
+  double arm[5], e = 0.0;
+  if (w < (int64_t)counters[0]) {
+    t = work1[w];
+    GoalDraw g;
+    goal_draw(pc, seeds, first, count, (int64_t)t, g);
+    double pose[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) pose[j] = poses[g.qi * 6 + j];
+    keep = goal_right_arm_ik(g.hip, pose, pc, g.seed, g.i, arm, &e);
+  }
+  const unsigned slot = warp_append(keep, counters + 1);
+  if (keep) {
+    work2[slot] = t;
+#pragma unroll
+    for (int m = 0; m < 5; ++m) work2_arm[(size_t)slot * 6 + m] = arm[m];
+    work2_arm[(size_t)slot * 6 + 5] = e;
+  }
+}
+
+template <bool STATIC>
+__global__ void __launch_bounds__(64)
+goal_solve_kernel(const __grid_constant__ PlanConst pc, const __grid_constant__ ValidityTables tab, const uint64_t* __restrict__ seeds,
+                  uint64_t first, int64_t count, const unsigned* __restrict__ counters, const uint32_t* __restrict__ work2,
+                  const double* __restrict__ work2_arm, double* __restrict__ rows, uint64_t* __restrict__ row_index,
+                  double* __restrict__ row_erg, int64_t cap, unsigned long long* __restrict__ n_out, int32_t* __restrict__ row_req) {
+  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= (int64_t)counters[1]) return;
+  GoalDraw g;
+  goal_draw(pc, seeds, first, count, (int64_t)work2[w], g);
+  DFrame target;
+  desired_left_leg_pose(g.hip, target);
+  double ll[5];
+  for (int m = 0; m < 5; ++m) ll[m] = -g.rl[m];          // NCK:150 seed (quirk C5 as above)
+  if (!(left_leg_ik_nr(target, ll, pc.ik_maxiter, pc.ik_eps, pc.pinv_eps, nullptr) && limits_ok(ll, pc.jmin + 16, pc.jmax + 16, 5))) return;
+  for (int m = 0; m < 5; ++m) {
+    g.q[16 + m] = ll[m];
+    g.q[10 + m] = work2_arm[(size_t)w * 6 + m];
+  }
+  float qf[NWB_NJ];
+#pragma unroll
+  for (int j = 0; j < NWB_NJ; ++j) qf[j] = (float)g.q[j];
+  ArmLocalStore st;
+  ValidityResult<float> r = evaluate_config<float, ArmLocalStore, false, false, STATIC ? PAIRS_STATIC_GROUP : PAIRS_TABLE, /*ENV_CULL=*/true>(tab, qf, st, nullptr, nullptr);
+  if (r.hit || !r.stable) return;
+  unsigned long long slot = atomicAdd(row_req ? n_out : n_out + g.qi, 1ull);
+  if ((int64_t)slot < cap) {
+    const size_t o = row_req ? (size_t)slot : (size_t)g.qi * cap + slot;
+    if (row_req) row_req[o] = g.qi;
+    for (int j = 0; j < NWB_NJ; ++j) rows[o * NWB_NJ + j] = g.q[j];
+    row_index[o] = g.i;
+    row_erg[o] = work2_arm[(size_t)w * 6 + 5];
+  }
 }
 
 // enforce_MA_Constraints inside extendTree (RP:829-837) for the lock-step driver: one thread per query.
@@ -201,15 +337,38 @@ cudaError_t launch_enforce_ma(const PlanConst& pc, const double* pts_dev, int n_
 cudaError_t launch_goal_sample(const PlanConst& pc, const ValidityTables& tab, bool static_pairs, const double* poses_dev,
                                const uint64_t* seeds_dev, int nq, uint64_t first, int64_t count, int max_ik_iter, double* rows,
                                uint64_t* row_index, double* row_erg, int64_t cap, unsigned long long* n_out, uint8_t* stage_out,
-                               double* erg_all, double* rows_all, cudaStream_t s) {
+                               double* erg_all, double* rows_all, int32_t* row_req, cudaStream_t s) {
   if (count <= 0 || nq <= 0) return cudaSuccess;
   unsigned blocks = (unsigned)((count * nq + 63) / 64);
   if (static_pairs)
     goal_sample_kernel<true><<<blocks, 64, 0, s>>>(pc, tab, poses_dev, seeds_dev, nq, first, count, max_ik_iter, rows, row_index,
-                                                   row_erg, cap, n_out, stage_out, erg_all, rows_all);
+                                                   row_erg, cap, n_out, stage_out, erg_all, rows_all, row_req);
   else
     goal_sample_kernel<false><<<blocks, 64, 0, s>>>(pc, tab, poses_dev, seeds_dev, nq, first, count, max_ik_iter, rows, row_index,
-                                                    row_erg, cap, n_out, stage_out, erg_all, rows_all);
+                                                    row_erg, cap, n_out, stage_out, erg_all, rows_all, row_req);
+  return cudaGetLastError();
+}
+size_t goal_sample_phased_scratch_bytes(int64_t items) { return 256 + (size_t)items * (4 + 4 + 48); }
+cudaError_t launch_goal_sample_phased(const PlanConst& pc, const ValidityTables& tab, bool static_pairs, const double* poses_dev,
+                                      const uint64_t* seeds_dev, int nq, uint64_t first, int64_t count, int max_ik_iter, double* rows,
+                                      uint64_t* row_index, double* row_erg, int64_t cap, unsigned long long* n_out, int32_t* row_req,
+                                      void* scratch, cudaStream_t s) {
+  if (count <= 0 || nq <= 0) return cudaSuccess;
+  const int64_t items = count * nq;
+  unsigned* counters = static_cast<unsigned*>(scratch);
+  double* work2_arm = reinterpret_cast<double*>(static_cast<char*>(scratch) + 256);
+  uint32_t* work1 = reinterpret_cast<uint32_t*>(work2_arm + (size_t)items * 6);
+  uint32_t* work2 = work1 + items;
+  cudaError_t e = cudaMemsetAsync(counters, 0, 8, s);
+  if (e != cudaSuccess) return e;
+  // the list sizes stay on the device: phases 2 and 3 are launched for the worst case and surplus blocks leave at once
+  goal_filter_kernel<<<(unsigned)((items + 127) / 128), 128, 0, s>>>(pc, poses_dev, seeds_dev, nq, first, count, max_ik_iter, work1, counters);
+  const unsigned blocks = (unsigned)((items + 63) / 64);
+  goal_arm_kernel<<<blocks, 64, 0, s>>>(pc, poses_dev, seeds_dev, first, count, work1, counters, work2, work2_arm);
+  if (static_pairs)
+    goal_solve_kernel<true><<<blocks, 64, 0, s>>>(pc, tab, seeds_dev, first, count, counters, work2, work2_arm, rows, row_index, row_erg, cap, n_out, row_req);
+  else
+    goal_solve_kernel<false><<<blocks, 64, 0, s>>>(pc, tab, seeds_dev, first, count, counters, work2, work2_arm, rows, row_index, row_erg, cap, n_out, row_req);
   return cudaGetLastError();
 }
 cudaError_t launch_ma_project(const PlanConst& pc, const double* ma_pts, int n_pts, ForestView F, RrtState S, const int32_t* idx_a,

@@ -4,7 +4,7 @@ set -euo pipefail
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 OUT=../libnwb.so
-FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -fvisibility=hidden
+FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -pthread -Xcompiler -fvisibility=hidden
        --expt-relaxed-constexpr -cudart static -Xptxas -v -DNWB_FAST_SINCOS ${NWB_EXTRA_FLAGS:-})
 SRCS=(validity.cu nwb_abi.cu tree.cu planner_kernels.cu planner_abi.cu rrt_driver.cu arm_kernels.cu service_abi.cu)
 OBJS=()
@@ -16,5 +16,5 @@ for s in "${SRCS[@]}"; do
   fi
   OBJS+=("$o")
 done
-"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -cudart static -o "$OUT" "${OBJS[@]}"
+"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -cudart static -Xcompiler -pthread -o "$OUT" "${OBJS[@]}"
 echo "built $OUT"

@@ -172,11 +172,19 @@ cudaError_t launch_goal_arm_ik(const PlanConst& pc, const double* pose6, uint64_
 cudaError_t launch_enforce_ma(const PlanConst& pc, const double* pts_dev, int n_pts, int start_tree, const int32_t* near_hand,
                               const double* q_near, const double* q_ds, int64_t n, double* q_out, int32_t* status, cudaStream_t s);
 // nq requests (poses_dev [nq][6], seeds_dev [nq]) x count sample indices; compacted outputs are per request:
-// rows [nq][cap][21], row_index / row_erg [nq][cap], n_out [nq]; the per-sample outputs [nq * count] are optional
+// rows [nq][cap][21], row_index / row_erg [nq][cap], n_out [nq]; the per-sample outputs [nq * count] are optional.
+// With row_req the requests share one pool instead: rows [cap][21], row_index / row_erg / row_req [cap], n_out [1].
 cudaError_t launch_goal_sample(const PlanConst& pc, const ValidityTables& tab, bool static_pairs, const double* poses_dev,
                                const uint64_t* seeds_dev, int nq, uint64_t first, int64_t count, int max_ik_iter, double* rows,
                                uint64_t* row_index, double* row_erg, int64_t cap, unsigned long long* n_out, uint8_t* stage_out,
-                               double* erg_all, double* rows_all, cudaStream_t s);
+                               double* erg_all, double* rows_all, int32_t* row_req, cudaStream_t s);
+// the same sampler without per-sample outputs, as three launches over densely packed work lists (arm_kernels.cu);
+// scratch: goal_sample_phased_scratch_bytes(nq * count) bytes of device memory
+size_t goal_sample_phased_scratch_bytes(int64_t items);
+cudaError_t launch_goal_sample_phased(const PlanConst& pc, const ValidityTables& tab, bool static_pairs, const double* poses_dev,
+                                      const uint64_t* seeds_dev, int nq, uint64_t first, int64_t count, int max_ik_iter, double* rows,
+                                      uint64_t* row_index, double* row_erg, int64_t cap, unsigned long long* n_out, int32_t* row_req,
+                                      void* scratch, cudaStream_t s);
 cudaError_t launch_ma_project(const PlanConst& pc, const double* ma_pts, int n_pts, ForestView F, RrtState S, const int32_t* idx_a,
                               const double* q_near, double* q_new, int32_t* status, int nq, cudaStream_t s);
 

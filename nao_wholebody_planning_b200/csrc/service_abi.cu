@@ -20,7 +20,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
+#include <atomic>
+#include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "nwb_internal.h"
@@ -59,6 +62,28 @@ struct GoalSet {
   double erg[6];
   uint64_t index[6];
 };
+
+// Host-side finishing of a BATCH (text round trip of the goal rows, time parameterisation of the trajectories) is
+// independent per request: spread it over the host cores.  NWB_HOST_THREADS overrides the thread count.
+template <class F>
+void parallel_for(int n, F&& body) {
+  int threads = (int)std::thread::hardware_concurrency();
+  if (const char* e = std::getenv("NWB_HOST_THREADS")) threads = std::atoi(e);
+  threads = std::max(1, std::min({threads, 32, n}));
+  if (threads == 1) {
+    for (int i = 0; i < n; ++i) body(i);
+    return;
+  }
+  std::atomic<int> next{0};
+  auto worker = [&] {
+    for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) body(i);
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < threads; ++t) pool.emplace_back(worker);
+  worker();
+  for (auto& t : pool) t.join();
+}
+bool trace_on() { return std::getenv("NWB_TRACE") != nullptr; }
 
 constexpr int kGoalsWanted = 6;   // SCG:429: the loop leaves once goal_samples > 5
 
@@ -108,52 +133,66 @@ int sample_goals_batch(nwb_ctx* ctx, int nq, const uint64_t* seeds, const double
   if (max_samples <= 0 || nq <= 0) return NWB_OK;
   S_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
-  // a request accepts ~0.3 % of its samples: 512 slots per request are plenty for a batch; a request that
-  // outgrows them is redone on its own with room for every sample
-  const int64_t cap = nq == 1 ? max_samples : std::min<int64_t>(max_samples, 512);
+  // The accepted samples of all requests go into ONE pool (a request accepts ~0.3 % of its samples, so 512 rows
+  // per request on average are plenty) and only the rows in use come back.  A batch that outgrows the pool is
+  // redone one request at a time, each with room for every sample.
+  const int64_t cap = nq == 1 ? max_samples : (int64_t)nq * std::min<int64_t>(max_samples, 512);
   Scratch A(ctx);
-  size_t o_rows = A.add(sizeof(double) * NWB_NJ * cap * nq), o_idx = A.add(sizeof(uint64_t) * cap * nq),
-         o_erg = A.add(sizeof(double) * cap * nq), o_n = A.add(8 * (size_t)nq), o_pose = A.add(sizeof(double) * 6 * nq),
-         o_seed = A.add(sizeof(uint64_t) * nq);
+  size_t o_rows = A.add(sizeof(double) * NWB_NJ * cap), o_idx = A.add(sizeof(uint64_t) * cap), o_erg = A.add(sizeof(double) * cap),
+         o_req = A.add(sizeof(int32_t) * cap), o_n = A.add(8), o_pose = A.add(sizeof(double) * 6 * nq),
+         o_seed = A.add(sizeof(uint64_t) * nq), o_work = A.add(goal_sample_phased_scratch_bytes((int64_t)nq * max_samples));
   int rc = A.commit();
   if (rc != NWB_OK) return rc;
   PlanConst pc;
   make_plan_const(ctx, nullptr, ctx->params.planner_step_factor, pc);
-  S_CUDA(ctx, cudaMemsetAsync(A.at<char>(o_n), 0, 8 * (size_t)nq, s));
+  S_CUDA(ctx, cudaMemsetAsync(A.at<char>(o_n), 0, 8, s));
   S_CUDA(ctx, cudaMemcpyAsync(A.at<double>(o_pose), poses, sizeof(double) * 6 * nq, cudaMemcpyHostToDevice, s));
   S_CUDA(ctx, cudaMemcpyAsync(A.at<uint64_t>(o_seed), seeds, sizeof(uint64_t) * nq, cudaMemcpyHostToDevice, s));
-  S_CUDA(ctx, launch_goal_sample(pc, ctx->tab_group, static_pairs(ctx), A.at<double>(o_pose), A.at<uint64_t>(o_seed), nq, 0, max_samples,
-                                 max_ik_iter, A.at<double>(o_rows), A.at<uint64_t>(o_idx), A.at<double>(o_erg), cap,
-                                 A.at<unsigned long long>(o_n), nullptr, nullptr, nullptr, s));
-  std::vector<unsigned long long> got(nq);
-  S_CUDA(ctx, cudaMemcpyAsync(got.data(), A.at<char>(o_n), 8 * (size_t)nq, cudaMemcpyDeviceToHost, s));
+  if (std::getenv("NWB_GOAL_ONE_KERNEL"))                   // the one-launch form of the same sampler (cross-check / timing)
+    S_CUDA(ctx, launch_goal_sample(pc, ctx->tab_group, static_pairs(ctx), A.at<double>(o_pose), A.at<uint64_t>(o_seed), nq, 0, max_samples,
+                                   max_ik_iter, A.at<double>(o_rows), A.at<uint64_t>(o_idx), A.at<double>(o_erg), cap,
+                                   A.at<unsigned long long>(o_n), nullptr, nullptr, nullptr, A.at<int32_t>(o_req), s));
+  else
+    S_CUDA(ctx, launch_goal_sample_phased(pc, ctx->tab_group, static_pairs(ctx), A.at<double>(o_pose), A.at<uint64_t>(o_seed), nq, 0,
+                                          max_samples, max_ik_iter, A.at<double>(o_rows), A.at<uint64_t>(o_idx), A.at<double>(o_erg), cap,
+                                          A.at<unsigned long long>(o_n), A.at<int32_t>(o_req), A.at<char>(o_work), s));
+  unsigned long long got = 0;
+  const double t_launch = now_s();
+  S_CUDA(ctx, cudaMemcpyAsync(&got, A.at<char>(o_n), 8, cudaMemcpyDeviceToHost, s));
   S_CUDA(ctx, cudaStreamSynchronize(s));
-  ctx->last_launches = 1;
-  // one request: fetch only what was accepted; a batch: one copy of the whole (sparsely filled) slot array
-  const size_t fetch = nq == 1 ? (size_t)std::min<int64_t>((int64_t)got[0], cap) : (size_t)cap * nq;
-  std::vector<double> rows((size_t)cap * nq * NWB_NJ), erg((size_t)cap * nq);
-  std::vector<uint64_t> idx((size_t)cap * nq);
-  if (fetch) {
-    S_CUDA(ctx, cudaMemcpyAsync(rows.data(), A.at<double>(o_rows), sizeof(double) * NWB_NJ * fetch, cudaMemcpyDeviceToHost, s));
-    S_CUDA(ctx, cudaMemcpyAsync(idx.data(), A.at<uint64_t>(o_idx), sizeof(uint64_t) * fetch, cudaMemcpyDeviceToHost, s));
-    S_CUDA(ctx, cudaMemcpyAsync(erg.data(), A.at<double>(o_erg), sizeof(double) * fetch, cudaMemcpyDeviceToHost, s));
+  const double t_kernel = now_s();
+  ctx->last_launches = std::getenv("NWB_GOAL_ONE_KERNEL") ? 1 : 3;
+  if ((int64_t)got > cap) {                                  // nq > 1 only: a single request's pool holds every sample
+    for (int k = 0; k < nq; ++k) {
+      rc = sample_goals_batch(ctx, 1, seeds + k, poses + 6 * k, max_samples, max_ik_iter, out + k);
+      if (rc != NWB_OK) return rc;
+    }
+    return NWB_OK;
+  }
+  const size_t n = (size_t)got;
+  std::vector<double> rows(n * NWB_NJ), erg(n);
+  std::vector<uint64_t> idx(n);
+  std::vector<int32_t> req(n);
+  if (n) {
+    S_CUDA(ctx, cudaMemcpyAsync(rows.data(), A.at<double>(o_rows), sizeof(double) * NWB_NJ * n, cudaMemcpyDeviceToHost, s));
+    S_CUDA(ctx, cudaMemcpyAsync(idx.data(), A.at<uint64_t>(o_idx), sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, s));
+    S_CUDA(ctx, cudaMemcpyAsync(erg.data(), A.at<double>(o_erg), sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+    S_CUDA(ctx, cudaMemcpyAsync(req.data(), A.at<int32_t>(o_req), sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s));
     S_CUDA(ctx, cudaStreamSynchronize(s));
   }
-  std::vector<int> redo;
-  for (int k = 0; k < nq; ++k) {
-    if ((int64_t)got[k] > cap) {
-      redo.push_back(k);
-      continue;
-    }
-    const size_t b = (size_t)k * cap, n = got[k];
-    finish_goal_set(std::vector<double>(rows.begin() + b * NWB_NJ, rows.begin() + (b + n) * NWB_NJ),
-                    std::vector<double>(erg.begin() + b, erg.begin() + b + n), std::vector<uint64_t>(idx.begin() + b, idx.begin() + b + n),
-                    max_samples, out[k]);
+  std::vector<std::vector<double>> k_rows(nq), k_erg(nq);
+  std::vector<std::vector<uint64_t>> k_idx(nq);
+  for (size_t r = 0; r < n; ++r) {
+    const int k = req[r];
+    k_rows[k].insert(k_rows[k].end(), rows.begin() + r * NWB_NJ, rows.begin() + (r + 1) * NWB_NJ);
+    k_erg[k].push_back(erg[r]);
+    k_idx[k].push_back(idx[r]);
   }
-  for (int k : redo) {
-    rc = sample_goals_batch(ctx, 1, seeds + k, poses + 6 * k, max_samples, max_ik_iter, out + k);
-    if (rc != NWB_OK) return rc;
-  }
+  const double t_fetch = now_s();
+  parallel_for(nq, [&](int k) { finish_goal_set(k_rows[k], k_erg[k], k_idx[k], max_samples, out[k]); });
+  if (trace_on())
+    std::fprintf(stderr, "[nwb] goal sampling nq=%d accepted=%llu: kernel %.3f ms, fetch %.3f ms, finish %.3f ms\n", nq, got,
+                 (t_kernel - t_launch) * 1e3, (t_fetch - t_kernel) * 1e3, (now_s() - t_fetch) * 1e3);
   return NWB_OK;
 }
 
@@ -631,7 +670,7 @@ int nwb_goal_sample_batch(nwb_ctx* ctx, uint64_t seed, uint64_t first, int64_t c
   S_CUDA(ctx, launch_goal_sample(pc, ctx->tab_group, static_pairs(ctx), A.at<double>(o_pose), A.at<uint64_t>(o_seed), 1, first, count,
                                  max_ik_iter, A.at<double>(o_rows), A.at<uint64_t>(o_idx), A.at<double>(o_erg), 16,
                                  A.at<unsigned long long>(o_n), A.at<uint8_t>(o_st), ergonomics ? A.at<double>(o_ea) : nullptr,
-                                 rows ? A.at<double>(o_ra) : nullptr, s));
+                                 rows ? A.at<double>(o_ra) : nullptr, nullptr, s));
   S_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
   S_CUDA(ctx, cudaMemcpyAsync(stage, A.at<uint8_t>(o_st), count, cudaMemcpyDeviceToHost, s));
   if (ergonomics) S_CUDA(ctx, cudaMemcpyAsync(ergonomics, A.at<double>(o_ea), sizeof(double) * count, cudaMemcpyDeviceToHost, s));
@@ -775,7 +814,8 @@ int nwb_compute_motion_plan_batch(nwb_ctx* ctx, const nwb_compute_motion_plan_re
   double w[NWB_NJ];
   limb_weights(P.r_arm_weight_approach, P.l_arm_weight_approach, P.legs_weight_approach, w);
   const int cap = 2048;
-  std::vector<double> starts((size_t)Q * NWB_NJ), gcfg((size_t)Q * NWB_NJ), raw((size_t)Q * cap * NWB_NJ);
+  std::vector<double> starts((size_t)Q * NWB_NJ), gcfg((size_t)Q * NWB_NJ);
+  std::unique_ptr<double[]> raw(new double[(size_t)Q * cap * NWB_NJ]);    // not zero-filled: only the path rows are ever touched
   std::vector<uint64_t> qseeds(Q);
   std::vector<nwb_plan_result> res(Q);
   for (int i = 0; i < Q; ++i) {
@@ -785,7 +825,7 @@ int nwb_compute_motion_plan_batch(nwb_ctx* ctx, const nwb_compute_motion_plan_re
   }
   t0 = now_s();
   rc = nwb_solve_query_batch(ctx, starts.data(), gcfg.data(), Q, ctx->ds_db.data(), (int32_t)(ctx->ds_db.size() / NWB_NJ), w,
-                             qseeds.data(), P.planner_max_iterations, P.planner_step_factor, 0, res.data(), raw.data(), cap);
+                             qseeds.data(), P.planner_max_iterations, P.planner_step_factor, 0, res.data(), raw.get(), cap);
   if (rc != NWB_OK) return rc;
   const double t_search = now_s() - t0;
   std::vector<std::vector<double>> paths;
@@ -795,15 +835,27 @@ int nwb_compute_motion_plan_batch(nwb_ctx* ctx, const nwb_compute_motion_plan_re
     if (!res[i].success) continue;
     resps[live[i]].num_nodes_generated = (uint32_t)res[i].num_nodes_generated;
     const int len = std::min(res[i].raw_path_len, cap);
-    paths.emplace_back(raw.begin() + (size_t)i * cap * NWB_NJ, raw.begin() + ((size_t)i * cap + len) * NWB_NJ);
+    paths.emplace_back(raw.get() + (size_t)i * cap * NWB_NJ, raw.get() + ((size_t)i * cap + len) * NWB_NJ);
     owner.push_back(live[i]);
   }
   std::vector<std::vector<int>> sel;
   std::vector<uint8_t> ok;
+  t0 = now_s();
   rc = shortcut_paths_batch(ctx, paths, sel, ok);
   if (rc != NWB_OK) return rc;
-  for (size_t i = 0; i < paths.size(); ++i) {
-    if (!ok[i]) continue;                                   // shortcutting failed: empty trajectory (RP:1919-1923)
+  const double t_shortcut = now_s() - t0;
+  t0 = now_s();
+  struct Trace {                                            // NWB_TRACE=1: where a batch spends its time, on stderr
+    double goal, search, shortcut, &start;
+    int n, q;
+    ~Trace() {
+      if (trace_on())
+        std::fprintf(stderr, "[nwb] compute_motion_plan_batch n=%d goals=%d: goal sampling %.3f ms, search %.3f ms, shortcut %.3f ms, trajectories %.3f ms\n",
+                     n, q, goal * 1e3, search * 1e3, shortcut * 1e3, (now_s() - start) * 1e3);
+    }
+  } trace{t_goal, t_search, t_shortcut, t0, N, Q};
+  parallel_for((int)paths.size(), [&](int i) {
+    if (!ok[i]) return;                                     // shortcutting failed: empty trajectory (RP:1919-1923)
     const int k = owner[i];
     std::vector<double> way;
     for (int idx : sel[i]) way.insert(way.end(), paths[i].begin() + (size_t)idx * NWB_NJ, paths[i].begin() + (size_t)(idx + 1) * NWB_NJ);
@@ -818,7 +870,7 @@ int nwb_compute_motion_plan_batch(nwb_ctx* ctx, const nwb_compute_motion_plan_re
     }
     resps[k].success = !path.empty();
     put_trajectory(P, path, false, reqs[k].execute_trajectory != 0, 0.f, resps[k].motion_plan);
-  }
+  });
   return NWB_OK;
 }
 
