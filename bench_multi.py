@@ -36,6 +36,8 @@ def main():
     ap.add_argument("--samples-log2", type=int, default=22)
     ap.add_argument("--check-log2", type=int, default=16, help="size of the partition-independence check")
     ap.add_argument("--nodes-log2", type=int, default=24, help="nodes of the one big tree of the NN workload")
+    ap.add_argument("--grasp-grid", type=int, default=16, help="V4: G x G hand targets over the evaluation window (the reference's design is 41)")
+    ap.add_argument("--skip-nn", action="store_true", help="leave out the one-big-tree workload")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
     import torch
@@ -154,60 +156,62 @@ def main():
     if rank == 0:
         ctx.dev_free(root_ptr)
 
-    # ---- V2: one big tree, node-range shards ---------------------------------------------------------------------
-    lo_j, hi_j = OL.joint_limits()
-    lo_t, hi_t = torch.tensor(lo_j, device=dev), torch.tensor(hi_j, device=dev)
-    BLK = 1 << 20
-    n_blocks = 1 << max(0, args.nodes_log2 - 20)
-    b0, b1 = sharding.shard_bounds(n_blocks, world)[rank]                 # contiguous blocks of 2^20 nodes per rank
-    tree = nwb.Tree(ctx, max(1, (b1 - b0)) * BLK)
-    for b in range(b0, b1):                                                 # block b is the same whatever the GPU count
-        g = torch.Generator(device=dev)
-        g.manual_seed(20121001 + b)
-        blk = lo_t + (hi_t - lo_t) * torch.rand((BLK, 21), generator=g, device=dev, dtype=torch.float64)
-        torch.cuda.synchronize()
-        tree.add_dev(blk.data_ptr(), BLK)
-        ctx.synchronize()
-    nq = 64
-    db = OL.golden_db()
-    queries = db[np.floor(np.random.default_rng(20121002).random(nq) * (len(db) - 1)).astype(int)]
-    q_dev = torch.from_numpy(queries).to(dev)
-    idx_dev = torch.empty(nq, dtype=torch.int32, device=dev)
-    dist_dev = torch.empty(nq, dtype=torch.float64, device=dev)
-
-    def nn():
-        if b1 > b0:
-            tree.nearest_dev(q_dev.data_ptr(), nq, idx_dev.data_ptr(), dist_dev.data_ptr())
+    if not args.skip_nn:
+        # ---- V2: one big tree, node-range shards ---------------------------------------------------------------------
+        lo_j, hi_j = OL.joint_limits()
+        lo_t, hi_t = torch.tensor(lo_j, device=dev), torch.tensor(hi_j, device=dev)
+        BLK = 1 << 20
+        n_blocks = 1 << max(0, args.nodes_log2 - 20)
+        b0, b1 = sharding.shard_bounds(n_blocks, world)[rank]                 # contiguous blocks of 2^20 nodes per rank
+        tree = nwb.Tree(ctx, max(1, (b1 - b0)) * BLK)
+        for b in range(b0, b1):                                                 # block b is the same whatever the GPU count
+            g = torch.Generator(device=dev)
+            g.manual_seed(20121001 + b)
+            blk = lo_t + (hi_t - lo_t) * torch.rand((BLK, 21), generator=g, device=dev, dtype=torch.float64)
+            torch.cuda.synchronize()
+            tree.add_dev(blk.data_ptr(), BLK)
             ctx.synchronize()
-            gidx = torch.where(idx_dev >= 0, idx_dev.to(torch.int64) + b0 * BLK, idx_dev.to(torch.int64))
-            d = dist_dev
-        else:                                                               # more ranks than blocks: an empty shard
-            gidx = torch.full((nq,), -1, dtype=torch.int64, device=dev)
-            d = torch.full((nq,), 10000.0, dtype=torch.float64, device=dev)
-        if world > 1:
-            return sharding.nn_reduce(d, gidx)
-        return d, gidx
+        nq = 64
+        db = OL.golden_db()
+        queries = db[np.floor(np.random.default_rng(20121002).random(nq) * (len(db) - 1)).astype(int)]
+        q_dev = torch.from_numpy(queries).to(dev)
+        idx_dev = torch.empty(nq, dtype=torch.int32, device=dev)
+        dist_dev = torch.empty(nq, dtype=torch.float64, device=dev)
 
-    nn()
-    barrier()
-    reps = 10
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        dmin, imin = nn()
-    barrier()
-    dt = max_over_ranks(time.perf_counter() - t0) / reps
-    total_nodes = n_blocks * BLK
-    emit(op="nn_one_big_tree_sharded", n_gpus=world, nodes=total_nodes, queries=nq, wall_ms_per_batch=1e3 * dt,
-         scan_gbs=84.0 * total_nodes * (nq / 8) / dt / 1e9, digest=int(imin.sum().item()), dist_digest=float(dmin.sum().item()),
-         scaling="strong",
-         note="64 queries (8 share a pass): each rank scans its node range, then all_gather + lexicographic min; host wall "
-              "clock per batch incl. the exchange; the digests (winning global indices / distances) must not depend on the "
-              "number of GPUs")
-    tree.close()
+        def nn():
+            if b1 > b0:
+                tree.nearest_dev(q_dev.data_ptr(), nq, idx_dev.data_ptr(), dist_dev.data_ptr())
+                ctx.synchronize()
+                gidx = torch.where(idx_dev >= 0, idx_dev.to(torch.int64) + b0 * BLK, idx_dev.to(torch.int64))
+                d = dist_dev
+            else:                                                               # more ranks than blocks: an empty shard
+                gidx = torch.full((nq,), -1, dtype=torch.int64, device=dev)
+                d = torch.full((nq,), 10000.0, dtype=torch.float64, device=dev)
+            if world > 1:
+                return sharding.nn_reduce(d, gidx)
+            return d, gidx
+
+        nn()
+        barrier()
+        reps = 10
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            dmin, imin = nn()
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0) / reps
+        total_nodes = n_blocks * BLK
+        emit(op="nn_one_big_tree_sharded", n_gpus=world, nodes=total_nodes, queries=nq, wall_ms_per_batch=1e3 * dt,
+             scan_gbs=84.0 * total_nodes * (nq / 8) / dt / 1e9, digest=int(imin.sum().item()), dist_digest=float(dmin.sum().item()),
+             scaling="strong",
+             note="64 queries (8 share a pass): each rank scans its node range, then all_gather + lexicographic min; host wall "
+                  "clock per batch incl. the exchange; the digests (winning global indices / distances) must not depend on the "
+                  "number of GPUs")
+        tree.close()
 
     # ---- V4 ---------------------------------------------------------------------------------------------------
-    n = 256
-    pos = np.array([[-0.08 + i * 0.4 / 15, -0.30 + j * 0.4 / 15, 0.2] for i in range(16) for j in range(16)])
+    G = args.grasp_grid
+    n = G * G
+    pos = np.array([[-0.08 + i * 0.4 / (G - 1), -0.30 + j * 0.4 / (G - 1), 0.2] for i in range(G) for j in range(G)])
     dirs = np.tile([0.0, -1.0, 0.0], (n, 1))
     seeds = (20121100 + np.arange(n)).astype(np.uint64)
     mine = sharding.round_robin(n, rank, world)
@@ -228,7 +232,7 @@ def main():
     barrier()
     dt = max_over_ranks(time.perf_counter() - t0)
     digest = int(sum(int(s) * (k + 1) + int(nn) for k, s, nn, _ in out))    # compare across GPU counts
-    emit(op="grasp_pose_queries_256_sharded", n_gpus=world, queries=n, solved=int(sum(s for _, s, _, _ in out)), wall_s=dt,
+    emit(op=f"grasp_pose_queries_{n}_sharded", n_gpus=world, queries=n, solved=int(sum(s for _, s, _, _ in out)), wall_s=dt,
          digest=digest, scaling="strong",
          note="round-robin request -> rank, one batched compute_motion_plan call per rank, results gathered as objects; the "
               "digest (solved flags and node counts) must not depend on the number of GPUs")
