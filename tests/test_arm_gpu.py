@@ -245,6 +245,38 @@ def test_motion_plan_and_goal_config_services(ctx, oracle):
         ctx.compute_motion_plan(pose[:3], pose[3:], START[:10], 1)
 
 
+def test_phased_goal_sampler_equals_the_one_kernel_form(ctx, monkeypatch):
+    """The services run the goal sampler as three launches over packed work lists; NWB_GOAL_ONE_KERNEL selects the
+    one-thread-per-sample kernel (the operator form the oracle test above checks).  Same goal sets, bit for bit -
+    direction given, position only (KDL branch), an unreachable pose, and a batch with host-thread finishing."""
+    poses = [POSE_DRAWER, POSE_DOOR, [0.14, -0.065, 0.30, 0, -1, 0], [0.20, -0.10, 0.28, 0, 0, 0], [0.9, 0.0, 0.3, 0, -1, 0]]
+
+    def run():
+        sets = [ctx.sample_goal_configs(40 + k, p, max_samples=3000 if k == 3 else 5000) for k, p in enumerate(poses)]
+        pos = np.array([[-0.08 + i * 0.4 / 15, -0.30 + j * 0.4 / 15, 0.2] for i in (5, 8, 11, 14) for j in (2, 6, 10, 14)])
+        start = np.zeros(21)
+        batch = ctx.compute_motion_plan_batch(pos, np.tile([0.0, -1.0, 0.0], (16, 1)), np.tile(start, (16, 1)),
+                                              300 + np.arange(16, dtype=np.uint64))
+        return sets, batch
+
+    monkeypatch.delenv("NWB_GOAL_ONE_KERNEL", raising=False)
+    monkeypatch.setenv("NWB_HOST_THREADS", "4")
+    sets_a, batch_a = run()
+    monkeypatch.setenv("NWB_GOAL_ONE_KERNEL", "1")
+    monkeypatch.setenv("NWB_HOST_THREADS", "1")
+    sets_b, batch_b = run()
+    assert sum(len(a[0]) for a in sets_a) >= 12 and len(sets_a[4][0]) == 0
+    for a, b in zip(sets_a, sets_b):
+        assert len(a[0]) == len(b[0]) and a[3] == b[3]
+        assert (a[0] == b[0]).all() and (a[1] == b[1]).all() and (a[2] == b[2]).all()
+    assert sum(r["success"] for r in batch_a) >= 4
+    for a, b in zip(batch_a, batch_b):
+        assert a["success"] == b["success"] and a["num_nodes_generated"] == b["num_nodes_generated"]
+        assert (a["wb_goal_config"] == b["wb_goal_config"]).all()
+        assert a["trajectory"].shape == b["trajectory"].shape and (a["trajectory"] == b["trajectory"]).all()
+        assert (a["time_from_start"] == b["time_from_start"]).all()
+
+
 def test_motion_plan_batch_equals_single_calls(ctx):
     """V4: the grasp-pose grid of SIM:778-788 (a 3 x 3 corner of it) from the crouched pose SIM:199-219."""
     start = np.array([0, -0.349066, 0.698132, -0.436332, 0, 1.39626, 0.349066, -1.39626, -0.5, 0, 1.39626, -0.349066, 1.39626,
