@@ -207,7 +207,7 @@ goal_filter_kernel(const __grid_constant__ PlanConst pc, const double* __restric
     const double* pose = poses + g.qi * 6;
     DFrame target;
     desired_left_leg_pose(g.hip, target);
-    keep = left_leg_target_in_reach(target, pc.ik_eps);
+    keep = left_leg_target_feasible(target, pc.ik_eps);
     if (keep && !(pose[3] == 0.0 && pose[4] == 0.0 && pose[5] == 0.0)) {
       // |grasp point - shoulder| <= |upper arm| + forearm + hand offset (scaled by |direction|): a necessary
       // condition of the closed-form solve, with 1e-6 of slack against rounding

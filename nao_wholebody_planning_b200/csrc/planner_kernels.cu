@@ -763,7 +763,7 @@ sample_filter_kernel(const __grid_constant__ PlanConst pc, uint64_t seed, uint64
     DFrame hip, target;
     right_leg_fk(rl, hip);
     desired_left_leg_pose(hip, target);
-    need = left_leg_target_in_reach(target, pc.ik_eps);
+    need = left_leg_target_feasible(target, pc.ik_eps);
   }
   if (t < count && stage_out) stage_out[t] = 0;           // phase 2 overwrites it for the samples it solves
   const unsigned mask = __ballot_sync(0xffffffffu, need);
