@@ -262,11 +262,16 @@ def main():
     orc.sample_stable_configs(20121005, 0, 20000)
     cpu1 = 20000 / (time.perf_counter() - t0)
     t0 = time.perf_counter()
-    orc.sample_stable_configs(20121005, 0, 200000, threads=orc.threads)
+    _, oidx, ostage = orc.sample_stable_configs(20121005, 0, 200000, threads=orc.threads)
     cpun = 200000 / (time.perf_counter() - t0)
+    # the oracle runs every Newton-Raphson solve to the end; the device rejects the unreachable targets up front
+    _, gidx, gstage = ctx.sample_stable_configs(20121005, 0, 200000)
     emit(args.out, op="sample_stable_configs", samples=count, accepted=accepted, ms=ms, samples_per_s=count / (ms * 1e-3),
          cpu_samples_per_s_1thread=cpu1, cpu_samples_per_s_all_threads=cpun, cpu_threads=orc.threads,
-         note="Philox sample -> hip FK -> NR/pinv IK (fp64) -> validity (fp32) -> atomic compaction")
+         oracle_sample=200000, ik_verdict_mismatches_vs_oracle=int(((gstage == 0) != (ostage == 0)).sum()),
+         stage_mismatches_vs_oracle=int((gstage != ostage).sum()), accepted_oracle_sample=[int(len(gidx)), int(len(oidx))],
+         note="Philox sample -> hip FK -> reach / leg-plane rejection -> NR/pinv IK (fp64) on the packed survivors -> validity "
+              "(fp32) -> atomic compaction")
 
     # ---- V0 / V4: planning ----------------------------------------------------------------------------------------
     ctx.set_stream(None)

@@ -243,27 +243,32 @@ static __device__ __noinline__ void pinv_solve(const double (*W_in)[5], const do
 //   (1) |sole - c| <= L = 0.24809,
 //   (2) the ankle A = sole + 0.04519 R e_z satisfies |A - c| <= 0.2029,
 //   (3) n . (A - c) = 0 for n = Rx(q0) e_y, and n is also normal to e_x and to R e_x, i.e. n = +-u/|u|, u = e_x x R e_x.
-// Carrying the tolerances through (|d(R e_x)| <= t, |d(u/|u|)| <= 2 t / |u_target|, |dA| <= t + 0.04519 t) a target
-// that CAN be converged to obeys
-//   |sole_t - c| <= L + t,   |A_t - c| <= 0.2029 + 1.04519 t,   |n_t . (A_t - c)| <= 0.2029 * 2 t / |u_t| + 1.04519 t.
-// Anything else runs all `maxiter` iterations and fails: 75 % of the failing solves on uniform samples (oracle,
-// 10^5 samples: 42.7 % by (1), 3 % by (2), 29.9 % by (3); the converging solves reach at most half the bound of (3)).
-// 10 % slack on (3) and 1e-6 on the lengths cover rounding.  The CPU oracle runs the full iteration for every
-// target - the parity tests compare the verdicts.
+// Carrying the tolerances through: |d(R e_x)| <= t and |du| <= t, so for t < |u_t| the angle phi between n and n_t
+// obeys sin phi <= r = t / |u_t| and |n - n_t| = 2 sin(phi / 2) = r / sqrt((1 + sqrt(1 - r^2)) / 2) =: dn;  |dA| <= da =
+// 1.04519 t;  and n . (A - c) = 0 with |A - c| <= min(0.2029, |A_t - c| + da) =: arm.  A target that CAN be converged
+// to therefore obeys
+//   |sole_t - c| <= L + t,   |A_t - c| <= 0.2029 + da,   |n_t . (A_t - c)| <= da + dn * arm.
+// Anything else runs all `maxiter` iterations and fails: 87 % of the failing solves on uniform samples (oracle, 3 x
+// 10^5 samples: 43 % by (1), 3 % by (2), 41 % by (3); none of the 37 874 converging solves is rejected, they reach at
+// most 0.64 of the bound of (3)).  10 % slack on (3) and 1e-6 on the lengths cover rounding.  The CPU oracle runs
+// the full iteration for every target - the parity tests compare the verdicts.
 __device__ __forceinline__ bool left_leg_target_feasible(const DFrame& target, double eps) {
   const double t = 1.7320508075688772 * eps, foot = 0.04519, legs = 0.1 + 0.1029;
   const double dx = target.p.x, dy = target.p.y - 0.05, dz = target.p.z;
   const double reach = legs + foot + t + 1e-6;
   if (dx * dx + dy * dy + dz * dz > reach * reach) return false;
   const double ax = dx + foot * target.r[2], ay = dy + foot * target.r[5], az = dz + foot * target.r[8];
-  const double ankle = legs + (1.0 + foot) * t + 1e-6;
-  if (ax * ax + ay * ay + az * az > ankle * ankle) return false;
+  const double da = (1.0 + foot) * t, ankle = legs + da + 1e-6;
+  const double an2 = ax * ax + ay * ay + az * az;
+  if (an2 > ankle * ankle) return false;
   const double uy = -target.r[6], uz = target.r[3];         // u = e_x x (R e_x) = (0, -x_z, x_y)
   const double un = sqrt(uy * uy + uz * uz);
-  if (un > 0.0) {
+  if (un > t) {
+    const double r = t / un;
+    const double dn = r / sqrt(0.5 * (1.0 + sqrt(1.0 - r * r)));
+    const double arm = fmin(legs, sqrt(an2) + da);
     const double g = fabs(uy * ay + uz * az);               // |u . (A - c)|, compared against bound * |u|
-    const double bound = legs * 2.0 * t + (1.0 + foot) * t * un;
-    if (g > 1.1 * bound + 1e-12) return false;
+    if (g > 1.1 * (un * (da + dn * arm)) + 1e-12) return false;
   }
   return true;
 }
