@@ -159,10 +159,11 @@ cudaError_t launch_connect(const PlanConst& pc, const ValidityTables& tab, bool 
                            int32_t* status, cudaStream_t s);
 cudaError_t launch_edge_check(const ValidityTables& tab, bool static_pairs, const double* qa, const double* qb, int64_t n_edges,
                               int k, uint8_t* ok, int32_t* first_bad, cudaStream_t s);
-// work [count] / work_n [1]: device scratch of the two-phase sampler (dense list of the samples that need the IK solve)
+// scratch: sampler_scratch_bytes(count) bytes of device memory (work lists of the phased sampler, planner_kernels.cu)
+size_t sampler_scratch_bytes(int64_t count);
 cudaError_t launch_sample(const PlanConst& pc, const ValidityTables& tab, bool static_pairs, uint64_t seed, uint64_t first,
                           int64_t count, int max_ik_iter, double* rows, uint64_t* row_index, int64_t cap,
-                          unsigned long long* n_out, uint8_t* stage_out, uint32_t* work, unsigned* work_n, cudaStream_t s);
+                          unsigned long long* n_out, uint8_t* stage_out, void* scratch, cudaStream_t s);
 
 
 // right-arm kernels (arm_kernels.cu)

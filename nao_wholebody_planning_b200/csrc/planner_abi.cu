@@ -156,7 +156,7 @@ int nwb_sample_stable_configs_dev(nwb_ctx* ctx, uint64_t seed, uint64_t first, i
   if (count > (int64_t)0xffffffff) return bad(ctx, "nwb_sample_stable_configs_dev: at most 2^32 - 1 samples per call");
   PlanConst pc;
   make_plan_const(ctx, nullptr, ctx->params.planner_step_factor, pc);
-  const size_t work_need = sizeof(uint32_t) * (size_t)count + 256;
+  const size_t work_need = sampler_scratch_bytes(count);
   if (ctx->d_work_bytes < work_need) {
     if (ctx->d_work) cudaFree(ctx->d_work);
     ctx->d_work = nullptr;
@@ -164,14 +164,12 @@ int nwb_sample_stable_configs_dev(nwb_ctx* ctx, uint64_t seed, uint64_t first, i
     P_CUDA(ctx, cudaMalloc(&ctx->d_work, work_need));
     ctx->d_work_bytes = work_need;
   }
-  unsigned* work_n = static_cast<unsigned*>(ctx->d_work);
-  uint32_t* work = reinterpret_cast<uint32_t*>(static_cast<char*>(ctx->d_work) + 256);
   P_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
   P_CUDA(ctx, launch_sample(pc, ctx->tab_group, static_pairs(ctx), seed, first, count, max_ik_iter, rows, index, cap, n_out, stage,
-                            work, work_n, ctx->stream));
+                            ctx->d_work, ctx->stream));
   P_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->last_ms = -1;
-  ctx->last_launches = count > 0 ? 2 : 0;
+  ctx->last_launches = count > 0 ? 3 * (int)((count + ((int64_t)1 << 22) - 1) >> 22) : 0;
   return NWB_OK;
 }
 

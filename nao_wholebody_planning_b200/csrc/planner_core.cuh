@@ -273,22 +273,12 @@ __device__ __forceinline__ bool left_leg_target_feasible(const DFrame& target, d
   return true;
 }
 
-// ChainIkSolverPos_NR::CartToJnt on the left-leg chain (base = hip frame).  The update is applied
-// BEFORE the convergence test.  Returns true on convergence; q holds the result.
-__device__ __forceinline__ bool left_leg_ik_nr(const DFrame& target, double* q /*[5] in: seed*/, int maxiter, double eps,
-                                               double pinv_eps, int* iters_out) {
-  // exact early out (see left_leg_target_feasible): the verdict and the iteration count of the full loop
-  if (!left_leg_target_feasible(target, eps)) {
-    if (iters_out) *iters_out = maxiter;
-    return false;
-  }
-  double V[5][5];                                         // right singular vectors, carried across the iterations
-#pragma unroll
-  for (int a = 0; a < 5; ++a)
-#pragma unroll
-    for (int b = 0; b < 5; ++b) V[a][b] = (a == b) ? 1.0 : 0.0;
-  int i;
-  for (i = 0; i < maxiter; ++i) {
+// Iterations [i0, i1) of ChainIkSolverPos_NR::CartToJnt on the left-leg chain (base = hip frame).  The update is
+// applied BEFORE the convergence test.  Returns the index of the iteration whose test succeeded, or -1; q and V (the
+// right singular vectors carried from one iteration to the next) hold the state to resume from.
+__device__ __forceinline__ int left_leg_ik_nr_span(const DFrame& target, double* q, double (*V)[5], int i0, int i1, double eps,
+                                                   double pinv_eps) {
+  for (int i = i0; i < i1; ++i) {
     DFrame f;
     dframe_identity(f);
     D3 o[5], a[5];
@@ -309,10 +299,30 @@ __device__ __forceinline__ bool left_leg_ik_nr(const DFrame& target, double* q /
     bool conv = true;
 #pragma unroll
     for (int k = 0; k < 6; ++k) conv = conv && (eps > tw[k]) && (tw[k] > -eps);
-    if (conv) break;
+    if (conv) return i;
   }
-  if (iters_out) *iters_out = (i < maxiter) ? i + 1 : maxiter;
-  return i != maxiter;
+  return -1;
+}
+__device__ __forceinline__ void nr_identity(double (*V)[5]) {
+#pragma unroll
+  for (int a = 0; a < 5; ++a)
+#pragma unroll
+    for (int b = 0; b < 5; ++b) V[a][b] = (a == b) ? 1.0 : 0.0;
+}
+
+// The whole solve.  Returns true on convergence; q holds the result.
+__device__ __forceinline__ bool left_leg_ik_nr(const DFrame& target, double* q /*[5] in: seed*/, int maxiter, double eps,
+                                               double pinv_eps, int* iters_out) {
+  // exact early out (see left_leg_target_feasible): the verdict and the iteration count of the full loop
+  if (!left_leg_target_feasible(target, eps)) {
+    if (iters_out) *iters_out = maxiter;
+    return false;
+  }
+  double V[5][5];
+  nr_identity(V);
+  const int i = left_leg_ik_nr_span(target, q, V, 0, maxiter, eps, pinv_eps);
+  if (iters_out) *iters_out = (i >= 0) ? i + 1 : maxiter;
+  return i >= 0;
 }
 
 // target = (R^T, R^T ((0,0.1,0) - p_hip))   (getDesiredLeftLegPose, local_planner.cpp:59-110)

@@ -776,44 +776,118 @@ sample_filter_kernel(const __grid_constant__ PlanConst pc, uint64_t seed, uint64
   }
 }
 
-// Phase 2: one thread per work item: left-leg IK, validity, compaction of the kept rows.
+// dense append of the lanes with `keep`: one atomic per warp; every lane of the warp must call it
+__device__ __forceinline__ unsigned sampler_warp_append(bool keep, unsigned* counter) {
+  const unsigned mask = __ballot_sync(0xffffffffu, keep);
+  if (!mask) return 0;
+  const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
+  unsigned base = 0;
+  if (lane == leader) base = atomicAdd(counter, (unsigned)__popc(mask));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  return base + __popc(mask & ((1u << lane) - 1u));
+}
+
+// what follows a converged solve: joint limits, validity, compaction of the kept rows
+template <bool STATIC>
+__device__ __forceinline__ void sampler_finish(const PlanConst& pc, const ValidityTables& tab, double* q, const double* ll, uint64_t i,
+                                               int64_t t, double* __restrict__ rows, uint64_t* __restrict__ row_index, int64_t cap,
+                                               unsigned long long* __restrict__ n_out, uint8_t* __restrict__ stage_out) {
+  if (!limits_ok(ll, pc.jmin + 16, pc.jmax + 16, 5)) return;              // stage stays 0 (written by the filter)
+  for (int m = 0; m < 5; ++m) q[16 + m] = ll[m];
+  ValidityResult<float> r = eval_one<false, STATIC>(tab, q);
+  const bool feasible = !r.hit && r.stable;
+  const bool keep = (pc.quirks & NWB_QUIRK_DB_KEEPS_INFEASIBLE) ? !feasible : feasible;   // SCG:452-456
+  if (keep) {
+    // system scope: the output arrays may live on ANOTHER GPU (peer-mapped through nwb_ipc_import): every rank of
+    // a sharded generation then appends into one rank's database directly over NVLink - the gather is the store
+    unsigned long long slot = atomicAdd_system(n_out, 1ull);
+    if ((int64_t)slot < cap) {
+      for (int j = 0; j < NWB_NJ; ++j) rows[slot * NWB_NJ + j] = q[j];
+      row_index[slot] = i;
+    }
+  }
+  if (stage_out) stage_out[t] = feasible ? 2 : 1;
+}
+
+// Phase 2 (head): one thread per work item, the first kSamplerHead Newton-Raphson iterations.  91 % of the solves that
+// converge at all have done so by then; the others (and everything that will fail after all 100 iterations) hand
+// their state - 5 joints and the 5x5 right singular vectors - to a second dense list, so the long tail again runs
+// in full warps instead of warps where the converged lanes idle.  A lane that finds the tail list full simply keeps
+// iterating here.  counters[0] = |work|, counters[1] = |tail|.
+constexpr int kSamplerHead = 10;
+constexpr int kTailState = 30;                           // q[5] + V[5][5], struct-of-arrays [kTailState][tail_cap]
 template <bool STATIC>
 __global__ void __launch_bounds__(64, NWB_SAMPLE_MIN_BLOCKS)
 sample_kernel(const __grid_constant__ PlanConst pc, const __grid_constant__ ValidityTables tab, uint64_t seed, uint64_t first,
-              int64_t count, int max_ik_iter, const uint32_t* __restrict__ work, const unsigned* __restrict__ work_n,
-              double* __restrict__ rows /*[cap][21]*/, uint64_t* __restrict__ row_index, int64_t cap,
-              unsigned long long* __restrict__ n_out, uint8_t* __restrict__ stage_out) {
+              const uint32_t* __restrict__ work, unsigned* __restrict__ counters, uint32_t* __restrict__ tail_t,
+              double* __restrict__ tail_state, unsigned tail_cap, double* __restrict__ rows /*[cap][21]*/,
+              uint64_t* __restrict__ row_index, int64_t cap, unsigned long long* __restrict__ n_out, uint8_t* __restrict__ stage_out) {
   const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= (int64_t)*work_n) return;
-  const int64_t t = work[w];
+  const bool active = w < (int64_t)counters[0];
+  if (__ballot_sync(0xffffffffu, active) == 0) return;
+  int64_t t = 0;
+  uint64_t i = 0;
+  double q[NWB_NJ], ll[5], V[5][5];
+  DFrame target;
+  int it = -1;
+  const int head = pc.ik_maxiter < kSamplerHead ? pc.ik_maxiter : kSamplerHead;
+  if (active) {
+    t = work[w];
+    i = first + (uint64_t)t;
+    sampler_draw(pc, seed, i, q);
+    double rl[5];
+    for (int m = 0; m < 5; ++m) rl[m] = -q[m];           // SCG:307-313
+    DFrame hip;
+    right_leg_fk(rl, hip);
+    desired_left_leg_pose(hip, target);
+    for (int m = 0; m < 5; ++m) ll[m] = -rl[m];          // NCK:150 seed; every further attempt repeats the same arithmetic (quirk C5)
+    nr_identity(V);
+    it = left_leg_ik_nr_span(target, ll, V, 0, head, pc.ik_eps, pc.pinv_eps);
+  }
+  const bool more = active && it < 0 && head < pc.ik_maxiter;
+  const unsigned slot = sampler_warp_append(more, counters + 1);
+  if (more) {
+    if (slot < tail_cap) {
+      tail_t[slot] = (uint32_t)t;
+#pragma unroll
+      for (int m = 0; m < 5; ++m) tail_state[(size_t)m * tail_cap + slot] = ll[m];
+#pragma unroll
+      for (int a = 0; a < 5; ++a)
+#pragma unroll
+        for (int b = 0; b < 5; ++b) tail_state[(size_t)(5 + 5 * a + b) * tail_cap + slot] = V[a][b];
+      return;
+    }
+    it = left_leg_ik_nr_span(target, ll, V, head, pc.ik_maxiter, pc.ik_eps, pc.pinv_eps);
+  }
+  if (active && it >= 0) sampler_finish<STATIC>(pc, tab, q, ll, i, t, rows, row_index, cap, n_out, stage_out);
+}
+
+// Phase 2 (tail): iterations kSamplerHead .. maxiter of the solves that were still running.
+template <bool STATIC>
+__global__ void __launch_bounds__(64, NWB_SAMPLE_MIN_BLOCKS)
+sample_tail_kernel(const __grid_constant__ PlanConst pc, const __grid_constant__ ValidityTables tab, uint64_t seed, uint64_t first,
+                   const unsigned* __restrict__ counters, const uint32_t* __restrict__ tail_t, const double* __restrict__ tail_state,
+                   unsigned tail_cap, double* __restrict__ rows, uint64_t* __restrict__ row_index, int64_t cap,
+                   unsigned long long* __restrict__ n_out, uint8_t* __restrict__ stage_out) {
+  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned queued = counters[1] < tail_cap ? counters[1] : tail_cap;
+  if (w >= (int64_t)queued) return;
+  const int64_t t = tail_t[w];
   const uint64_t i = first + (uint64_t)t;
-  double q[NWB_NJ];
+  double q[NWB_NJ], ll[5], V[5][5], rl[5];
   sampler_draw(pc, seed, i, q);
-  double rl[5], ll[5];
-  for (int m = 0; m < 5; ++m) rl[m] = -q[m];             // SCG:307-313
+  for (int m = 0; m < 5; ++m) rl[m] = -q[m];
   DFrame hip, target;
   right_leg_fk(rl, hip);
   desired_left_leg_pose(hip, target);
-  uint8_t stage = 0;
-  for (int m = 0; m < 5; ++m) ll[m] = -rl[m];            // NCK:150 seed; every further attempt repeats the same arithmetic (quirk C5)
-  const bool solved = left_leg_ik_nr(target, ll, pc.ik_maxiter, pc.ik_eps, pc.pinv_eps, nullptr) && limits_ok(ll, pc.jmin + 16, pc.jmax + 16, 5);
-  if (solved) {
-    for (int m = 0; m < 5; ++m) q[16 + m] = ll[m];
-    ValidityResult<float> r = eval_one<false, STATIC>(tab, q);
-    const bool feasible = !r.hit && r.stable;
-    stage = feasible ? 2 : 1;
-    const bool keep = (pc.quirks & NWB_QUIRK_DB_KEEPS_INFEASIBLE) ? !feasible : feasible;   // SCG:452-456
-    if (keep) {
-      // system scope: the output arrays may live on ANOTHER GPU (peer-mapped through nwb_ipc_import): every rank of
-      // a sharded generation then appends into one rank's database directly over NVLink - the gather is the store
-      unsigned long long slot = atomicAdd_system(n_out, 1ull);
-      if ((int64_t)slot < cap) {
-        for (int j = 0; j < NWB_NJ; ++j) rows[slot * NWB_NJ + j] = q[j];
-        row_index[slot] = i;
-      }
-    }
-  }
-  if (stage_out) stage_out[t] = stage;
+#pragma unroll
+  for (int m = 0; m < 5; ++m) ll[m] = tail_state[(size_t)m * tail_cap + w];
+#pragma unroll
+  for (int a = 0; a < 5; ++a)
+#pragma unroll
+    for (int b = 0; b < 5; ++b) V[a][b] = tail_state[(size_t)(5 + 5 * a + b) * tail_cap + w];
+  const int it = left_leg_ik_nr_span(target, ll, V, kSamplerHead, pc.ik_maxiter, pc.ik_eps, pc.pinv_eps);
+  if (it >= 0) sampler_finish<STATIC>(pc, tab, q, ll, i, t, rows, row_index, cap, n_out, stage_out);
 }
 
 // ---- launchers -------------------------------------------------------------------------------------------------
@@ -882,17 +956,40 @@ cudaError_t launch_edge_check(const ValidityTables& tab, bool static_pairs, cons
   return cudaGetLastError();
 }
 
+// the sampler works through its range in chunks of at most kSamplerChunk samples, so the scratch stays bounded
+constexpr int64_t kSamplerChunk = (int64_t)1 << 22;
+static unsigned sampler_tail_cap(int64_t chunk) { return (unsigned)std::max<int64_t>(1024, chunk / 4); }
+size_t sampler_scratch_bytes(int64_t count) {
+  const int64_t chunk = std::min(count, kSamplerChunk);
+  const size_t tc = sampler_tail_cap(chunk);
+  return 256 + sizeof(double) * kTailState * tc + sizeof(uint32_t) * tc + sizeof(uint32_t) * (size_t)chunk;
+}
 cudaError_t launch_sample(const PlanConst& pc, const ValidityTables& tab, bool static_pairs, uint64_t seed, uint64_t first,
                           int64_t count, int max_ik_iter, double* rows, uint64_t* row_index, int64_t cap,
-                          unsigned long long* n_out, uint8_t* stage_out, uint32_t* work, unsigned* work_n, cudaStream_t s) {
+                          unsigned long long* n_out, uint8_t* stage_out, void* scratch, cudaStream_t s) {
   if (count <= 0) return cudaSuccess;
-  cudaError_t e = cudaMemsetAsync(work_n, 0, sizeof(unsigned), s);
-  if (e != cudaSuccess) return e;
-  sample_filter_kernel<<<(unsigned)((count + 127) / 128), 128, 0, s>>>(pc, seed, first, count, max_ik_iter, work, work_n, stage_out);
-  // the size of the work list stays on the device: launch for the worst case, surplus blocks leave at once
-  unsigned blocks = (unsigned)((count + 63) / 64);
-  if (static_pairs) sample_kernel<true><<<blocks, 64, 0, s>>>(pc, tab, seed, first, count, max_ik_iter, work, work_n, rows, row_index, cap, n_out, stage_out);
-  else sample_kernel<false><<<blocks, 64, 0, s>>>(pc, tab, seed, first, count, max_ik_iter, work, work_n, rows, row_index, cap, n_out, stage_out);
+  const int64_t chunk_max = std::min(count, kSamplerChunk);
+  const unsigned tc = sampler_tail_cap(chunk_max);
+  unsigned* counters = static_cast<unsigned*>(scratch);
+  double* tail_state = reinterpret_cast<double*>(static_cast<char*>(scratch) + 256);
+  uint32_t* tail_t = reinterpret_cast<uint32_t*>(tail_state + (size_t)kTailState * tc);
+  uint32_t* work = tail_t + tc;
+  for (int64_t off = 0; off < count; off += kSamplerChunk) {
+    const int64_t n = std::min(kSamplerChunk, count - off);
+    uint8_t* st = stage_out ? stage_out + off : nullptr;
+    cudaError_t e = cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned), s);
+    if (e != cudaSuccess) return e;
+    sample_filter_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(pc, seed, first + (uint64_t)off, n, max_ik_iter, work, counters, st);
+    // the list sizes stay on the device: launch for the worst case, surplus blocks leave at once
+    const unsigned blocks = (unsigned)((n + 63) / 64), tail_blocks = (tc + 63) / 64;
+    if (static_pairs) {
+      sample_kernel<true><<<blocks, 64, 0, s>>>(pc, tab, seed, first + (uint64_t)off, work, counters, tail_t, tail_state, tc, rows, row_index, cap, n_out, st);
+      sample_tail_kernel<true><<<tail_blocks, 64, 0, s>>>(pc, tab, seed, first + (uint64_t)off, counters, tail_t, tail_state, tc, rows, row_index, cap, n_out, st);
+    } else {
+      sample_kernel<false><<<blocks, 64, 0, s>>>(pc, tab, seed, first + (uint64_t)off, work, counters, tail_t, tail_state, tc, rows, row_index, cap, n_out, st);
+      sample_tail_kernel<false><<<tail_blocks, 64, 0, s>>>(pc, tab, seed, first + (uint64_t)off, counters, tail_t, tail_state, tc, rows, row_index, cap, n_out, st);
+    }
+  }
   return cudaGetLastError();
 }
 
