@@ -152,8 +152,9 @@ cudaError_t launch_rrt_fused(const PlanConst& pc, const ValidityTables& tab, boo
                              const double* goals, const uint64_t* seeds, int32_t* res, double* path_rows,
                              unsigned long long* path_used, long long path_cap, const double* db, int n_db, int max_iter, int nq,
                              const double* ma_pts, int n_pts, int32_t* overflow_flag, cudaStream_t s);
+// scratch: 256 + 4 n bytes of device memory selects the two-launch form for n >= 4096 (nullptr: one launch)
 cudaError_t launch_steer_project(const PlanConst& pc, const double* q_near, const double* q_target, int64_t n, double* q_out,
-                                 int32_t* status, int32_t* ds_status, int32_t* iters, cudaStream_t s);
+                                 int32_t* status, int32_t* ds_status, int32_t* iters, void* scratch, cudaStream_t s);
 cudaError_t launch_connect(const PlanConst& pc, const ValidityTables& tab, bool static_pairs, const double* q_start,
                            const double* q_connect, int64_t n_edges, int max_steps, double* nodes_out, int32_t* n_added,
                            int32_t* status, cudaStream_t s);

@@ -52,11 +52,20 @@ int nwb_steer_project_batch_dev(nwb_ctx* ctx, const double* q_near, const double
   P_CUDA(ctx, cudaSetDevice(ctx->device));
   PlanConst pc;
   make_plan_const(ctx, weights, step, pc);
+  const size_t work_need = 256 + sizeof(uint32_t) * (size_t)std::max<int64_t>(n, 0);
+  if (n >= 4096 && ctx->d_work_bytes < work_need) {
+    if (ctx->d_work) cudaFree(ctx->d_work);
+    ctx->d_work = nullptr;
+    ctx->d_work_bytes = 0;
+    P_CUDA(ctx, cudaMalloc(&ctx->d_work, work_need));
+    ctx->d_work_bytes = work_need;
+  }
   P_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-  P_CUDA(ctx, launch_steer_project(pc, q_near, q_target, n, q_out, status, ds_status, nullptr, ctx->stream));
+  P_CUDA(ctx, launch_steer_project(pc, q_near, q_target, n, q_out, status, ds_status, nullptr, n >= 4096 ? ctx->d_work : nullptr,
+                                   ctx->stream));
   P_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->last_ms = -1;
-  ctx->last_launches = n > 0;
+  ctx->last_launches = n >= 4096 ? 2 : (n > 0);
   return NWB_OK;
 }
 

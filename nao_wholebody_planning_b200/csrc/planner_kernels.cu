@@ -67,6 +67,105 @@ steer_project_kernel(const __grid_constant__ PlanConst pc, const double* __restr
   for (int j = 0; j < NWB_NJ; ++j) q_out[i * NWB_NJ + j] = q[j];
 }
 
+// The same operator as two launches (large batches): the first classifies every pair - joint limits, already in double
+// support, or a foot target the solve can never converge to (left_leg_target_feasible) - and packs the pairs that need
+// the Newton-Raphson solve into a dense list; the second runs one solve per thread on full warps.  generate_q_new is
+// recomputed in the second launch (cheap, and rows of TRAPPED pairs must stay untouched in q_out).
+__device__ __forceinline__ unsigned steer_warp_append(bool keep, unsigned* counter) {
+  const unsigned mask = __ballot_sync(0xffffffffu, keep);
+  if (!mask) return 0;
+  const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
+  unsigned base = 0;
+  if (lane == leader) base = atomicAdd(counter, (unsigned)__popc(mask));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  return base + __popc(mask & ((1u << lane) - 1u));
+}
+__global__ void __launch_bounds__(128)
+steer_filter_kernel(const __grid_constant__ PlanConst pc, const double* __restrict__ q_near, const double* __restrict__ q_target,
+                    int64_t n, double* __restrict__ q_out, int32_t* __restrict__ status, int32_t* __restrict__ ds_status,
+                    int32_t* __restrict__ iters, uint32_t* __restrict__ work, unsigned* __restrict__ counter) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool need = false;
+  if (i < n) {
+    double a[NWB_NJ], b[NWB_NJ], q[NWB_NJ];
+    for (int j = 0; j < NWB_NJ; ++j) {
+      a[j] = q_near[i * NWB_NJ + j];
+      b[j] = q_target[i * NWB_NJ + j];
+    }
+    const int st = generate_q_new(a, b, pc, q);
+    int ds = NWB_TRAPPED, it = 0;
+    if (limits_ok(q, pc.jmin, pc.jmax, NWB_NJ)) {
+      double rl[5];
+#pragma unroll
+      for (int m = 0; m < 5; ++m) rl[m] = -q[m];
+      DFrame hip;
+      right_leg_fk(rl, hip);
+      DFrame foot = hip;
+      left_leg_fk(q + 16, foot, nullptr, nullptr);
+      const double des[3] = {nwbm::kLeftSoleTarget[0], nwbm::kLeftSoleTarget[1], nwbm::kLeftSoleTarget[2]};
+      const double act[3] = {foot.p.x, foot.p.y, foot.p.z};
+      double max_err = 0.0;
+#pragma unroll
+      for (int m = 0; m < 3; ++m) {
+        double e = des[m] - act[m];
+        if (!(pc.quirks & NWB_QUIRK_SIGNED_FOOT_ERROR)) e = fabs(e);
+        if (e > max_err) max_err = e;
+      }
+      if (!(max_err > pc.ds_tolerance)) {
+        ds = NWB_REACHED;
+      } else {
+        DFrame target;
+        desired_left_leg_pose(hip, target);
+        if (left_leg_target_feasible(target, pc.ik_eps)) need = true;
+        else it = pc.ik_maxiter;                            // what the full loop would report
+      }
+    }
+    if (!need) {
+      if (ds_status) ds_status[i] = ds;
+      if (iters) iters[i] = it;
+      status[i] = ds == NWB_TRAPPED ? NWB_TRAPPED : st;
+      if (ds != NWB_TRAPPED)
+        for (int j = 0; j < NWB_NJ; ++j) q_out[i * NWB_NJ + j] = q[j];
+    }
+  }
+  const unsigned slot = steer_warp_append(need, counter);
+  if (need) work[slot] = (uint32_t)i;
+}
+__global__ void __launch_bounds__(64, 2 * NWB_STEER_MIN_BLOCKS)   // 12 warps per SM, as the one-launch form
+steer_solve_kernel(const __grid_constant__ PlanConst pc, const double* __restrict__ q_near, const double* __restrict__ q_target,
+                   const uint32_t* __restrict__ work, const unsigned* __restrict__ counter, double* __restrict__ q_out,
+                   int32_t* __restrict__ status, int32_t* __restrict__ ds_status, int32_t* __restrict__ iters) {
+  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= (int64_t)*counter) return;
+  const int64_t i = work[w];
+  double a[NWB_NJ], b[NWB_NJ], q[NWB_NJ];
+  for (int j = 0; j < NWB_NJ; ++j) {
+    a[j] = q_near[i * NWB_NJ + j];
+    b[j] = q_target[i * NWB_NJ + j];
+  }
+  generate_q_new(a, b, pc, q);
+  double rl[5], ll[5], V[5][5];
+#pragma unroll
+  for (int m = 0; m < 5; ++m) {
+    rl[m] = -q[m];
+    ll[m] = q[16 + m];
+  }
+  DFrame hip, target;
+  right_leg_fk(rl, hip);
+  desired_left_leg_pose(hip, target);
+  nr_identity(V);
+  const int it = left_leg_ik_nr_span(target, ll, V, 0, pc.ik_maxiter, pc.ik_eps, pc.pinv_eps);
+  const bool ok = it >= 0 && limits_ok(ll, pc.jmin + 16, pc.jmax + 16, 5);
+  if (iters) iters[i] = it >= 0 ? it + 1 : pc.ik_maxiter;
+  if (ds_status) ds_status[i] = ok ? NWB_ADVANCED : NWB_TRAPPED;
+  status[i] = ok ? NWB_ADVANCED : NWB_TRAPPED;
+  if (ok) {
+#pragma unroll
+    for (int m = 0; m < 5; ++m) q[16 + m] = ll[m];
+    for (int j = 0; j < NWB_NJ; ++j) q_out[i * NWB_NJ + j] = q[j];
+  }
+}
+
 // ---- connect: one thread walks one edge -------------------------------------------------------------
 // From q_start repeat {generate_q_new -> enforce_DS -> isConfigValid -> append} until REACHED or
 // TRAPPED; step k+1 starts from the PROJECTED node of step k (RP:1004), so the walk is serial by
@@ -892,9 +991,18 @@ sample_tail_kernel(const __grid_constant__ PlanConst pc, const __grid_constant__
 
 // ---- launchers -------------------------------------------------------------------------------------------------
 cudaError_t launch_steer_project(const PlanConst& pc, const double* q_near, const double* q_target, int64_t n, double* q_out,
-                                 int32_t* status, int32_t* ds_status, int32_t* iters, cudaStream_t s) {
+                                 int32_t* status, int32_t* ds_status, int32_t* iters, void* scratch, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
-  steer_project_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(pc, q_near, q_target, n, q_out, status, ds_status, iters);
+  if (!scratch || n < 4096 || n > (int64_t)0xffffffff) {       // small batches (the lock-step driver): one launch
+    steer_project_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(pc, q_near, q_target, n, q_out, status, ds_status, iters);
+    return cudaGetLastError();
+  }
+  unsigned* counter = static_cast<unsigned*>(scratch);         // scratch: 256 + 4 n bytes
+  uint32_t* work = reinterpret_cast<uint32_t*>(static_cast<char*>(scratch) + 256);
+  cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned), s);
+  if (e != cudaSuccess) return e;
+  steer_filter_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(pc, q_near, q_target, n, q_out, status, ds_status, iters, work, counter);
+  steer_solve_kernel<<<(unsigned)((n + 63) / 64), 64, 0, s>>>(pc, q_near, q_target, work, counter, q_out, status, ds_status, iters);
   return cudaGetLastError();
 }
 

@@ -522,7 +522,7 @@ static int solve_impl(nwb_ctx* ctx, const double* starts, const double* goals, i
     rrt_begin_kernel<<<Q, 32, 0, s>>>(d_db, n_db, d_seeds, it, pc.quirks, Q, S, d_qrand);
     // extendTree (RP:787-884)
     forest_nn_kernel<<<Q, 128, 0, s>>>(F, S.tree_a, S.active, d_qrand, Q, d_idx_a, d_near);
-    cudaError_t e = launch_steer_project(pc, d_near, d_qrand, Q, d_qnew, d_status, nullptr, nullptr, s);
+    cudaError_t e = launch_steer_project(pc, d_near, d_qrand, Q, d_qnew, d_status, nullptr, nullptr, nullptr, s);
     if (e == cudaSuccess && P) e = launch_ma_project(pc, d_ma, P, F, S, d_idx_a, d_near, d_qnew, d_status, Q, s);   // RP:829-837
     if (e == cudaSuccess) e = launch_validity(ctx->tab_group, d_qnew, NWB_F64, Q, d_valid, nullptr, nullptr, false, sp, s);
     rrt_extend_commit_kernel<<<Q, 32, 0, s>>>(F, S, d_status, d_valid, d_idx_a, d_qnew, Q, P);
