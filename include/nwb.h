@@ -446,8 +446,9 @@ NWB_API int nwb_compute_motion_plan(nwb_ctx* ctx, const nwb_compute_motion_plan_
                                     nwb_compute_motion_plan_response* resp, uint64_t seed);
 
 /* n independent compute_motion_plan requests (the grasp-pose evaluation loop of
- * planning_example_simulation.cpp:770-900 calls the service once per pose): all goal samplings in one
- * launch, all RRT-Connect queries in lock step, all shortcut rounds in shared edge-check batches.
+ * planning_example_simulation.cpp:770-900 calls the service once per pose): all goal samplings share
+ * three launches, all RRT-Connect queries run in one, all shortcut rounds in shared edge-check batches;
+ * the per-request host finishing (goal-file text round trip, time parameterisation) runs on host threads.
  * Request k uses seeds[k] exactly as nwb_compute_motion_plan would, so resps[k] equals the single call's
  * response except for the two wall-clock fields (batch times). */
 NWB_API int nwb_compute_motion_plan_batch(nwb_ctx* ctx, const nwb_compute_motion_plan_request* reqs,
