@@ -82,7 +82,7 @@ typedef struct nwb_params {
   int32_t device;              /* CUDA device ordinal                                          */
   int32_t quirks;              /* NWB_QUIRK_* bit mask                                          */
   int32_t srdf_trim;           /* 1: trim stray blanks in SRDF link names (srdfdom), SRDF:230,236,301 */
-  int32_t scale_origin;        /* support-polygon scaling about 1: vertex centroid, 0: sole origin */
+  int32_t scale_origin;        /* support-polygon scaling about 0: sole origin, 1: the model's foot centre (default), 2: mean of the polygon vertices */
   double scale_sp;             /* planning_parameters.yaml:3 (0.8); RP:105-109                  */
   double ds_tolerance;         /* LP:293 (0.01 m)                                               */
   double ik_eps;               /* LP:182, NCK:127 (1e-3)                                        */

@@ -57,7 +57,7 @@ int nwb_params_default(nwb_params* p) {
   p->device = 0;
   p->quirks = NWB_QUIRKS_DEFAULT;
   p->srdf_trim = 1;
-  p->scale_origin = nwbm::kScaleOriginCentroid;
+  p->scale_origin = nwbm::kScaleOriginDefault;
   p->scale_sp = nwbm::kSupportScaleDefault;
   p->ds_tolerance = 0.01;
   p->ik_eps = 1e-3;

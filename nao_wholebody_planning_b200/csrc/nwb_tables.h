@@ -75,15 +75,20 @@ inline void fill_pairs(const nwb_params& params, ValidityTables& t, bool group_o
 inline void build_validity_tables(const nwb_params& params, const std::vector<SceneBox>& boxes, bool group_only,
                                   ValidityTables& t) {
   std::memset(&t, 0, sizeof(t));
-  // TestStability::scaleConvexHull: scale about the vertex centroid or the sole origin
+  // TestStability::scaleConvexHull: scale about the sole origin (0), the foot centre of the model (1: mean of the
+  // foot-mesh vertices, calibrated - see the model file) or the mean of the polygon vertices (2)
   double cx = 0, cy = 0;
-  for (int i = 0; i < nwbm::kFootN; ++i) {
-    cx += nwbm::kFootRight[i][0];
-    cy += nwbm::kFootRight[i][1];
+  if (params.scale_origin == 1) {
+    cx = nwbm::kFootCenter[0];
+    cy = nwbm::kFootCenter[1];
+  } else if (params.scale_origin == 2) {
+    for (int i = 0; i < nwbm::kFootN; ++i) {
+      cx += nwbm::kFootRight[i][0];
+      cy += nwbm::kFootRight[i][1];
+    }
+    cx /= nwbm::kFootN;
+    cy /= nwbm::kFootN;
   }
-  cx /= nwbm::kFootN;
-  cy /= nwbm::kFootN;
-  if (!params.scale_origin) cx = cy = 0;
   const double s = params.scale_sp;
   for (int i = 0; i < nwbm::kFootN; ++i) {
     double x = cx + s * (nwbm::kFootRight[i][0] - cx), y = cy + s * (nwbm::kFootRight[i][1] - cy);

@@ -33,7 +33,7 @@ struct Box {  // oriented box of the planning scene, expressed in the r_sole fra
 
 struct EvalParams {
   double scale_sp = nwbm::kSupportScaleDefault;
-  int scale_origin = nwbm::kScaleOriginCentroid;
+  int scale_origin = nwbm::kScaleOriginDefault;
   int srdf_trim = 1;
   std::vector<Box> boxes;
 };
@@ -81,20 +81,23 @@ struct P2 {
   double x, y;
 };
 
-// TestStability::scaleConvexHull: both foot polygons scaled by s (about the vertex centroid or
-// about the sole origin - model parameter).  Left = right mirrored in y.
+// TestStability::scaleConvexHull: both foot polygons scaled by s about the foot centre (scale_origin 1: the
+// model's calibrated mean of the foot-mesh vertices, models/nao_h25_rfoot.json foot_center_doc), about the sole
+// origin (0) or about the mean of the polygon vertices (2) - SURVEY.md Appendix B.4.  Left = right mirrored in y.
 inline void foot_polygons(const EvalParams& ep, std::vector<P2>& right, std::vector<P2>& left) {
   const int n = nwbm::kFootN;
   right.resize(n);
   left.resize(n);
   double cx = 0, cy = 0;
-  for (int i = 0; i < n; ++i) {
-    cx += nwbm::kFootRight[i][0];
-    cy += nwbm::kFootRight[i][1];
+  if (ep.scale_origin == 1) {
+    cx = nwbm::kFootCenter[0];
+    cy = nwbm::kFootCenter[1];
+  } else if (ep.scale_origin == 2) {
+    for (int i = 0; i < n; ++i) {
+      cx += nwbm::kFootRight[i][0] / n;
+      cy += nwbm::kFootRight[i][1] / n;
+    }
   }
-  cx /= n;
-  cy /= n;
-  if (!ep.scale_origin) cx = cy = 0;
   for (int i = 0; i < n; ++i) {
     double x = nwbm::kFootRight[i][0], y = nwbm::kFootRight[i][1];
     right[i] = {cx + ep.scale_sp * (x - cx), cy + ep.scale_sp * (y - cy)};

@@ -48,6 +48,19 @@ def main():
     print("COM x range [%.3f, %.3f], y range [%.3f, %.3f], z mean %.3f" % (
         c[:, 0].min(), c[:, 0].max(), c[:, 1].min(), c[:, 1].max(), c[:, 2].mean()))
 
+    # window the shipped rows leave for the scale centre of the foot polygon (foot_center_right in the model file)
+    import copy
+    trial = copy.deepcopy(model)
+    trial["support_scale_origin"] = "center"
+    print("scale-centre window (rows unstable / min margin):")
+    for cx in np.arange(0.0075, 0.0121, 0.0005):
+        cells = []
+        for cy in (-0.017, -0.010, -0.006, -0.002, 0.002):
+            trial["foot_center_right"] = [float(cx), cy]
+            mm = M.stability_margin(trial, fr)
+            cells.append("%2d/%+.5f" % ((mm <= 0).sum(), mm.min()))
+        print("   cx %.4f | cy -0.017 .. 0.002: %s" % (cx, "  ".join(cells)))
+
     for kind in ("enabled_group", "enabled_all"):
         pairs = M.enabled_pairs(kind)
         sep = M.pair_separations(model, fr, pairs)

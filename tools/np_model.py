@@ -78,7 +78,10 @@ def scaled_foot_polygons(model, scale=None):
     s = model["support_scale"] if scale is None else scale
     right = np.asarray(model["foot_polygon_right"], dtype=np.float64)
     left = right * np.array([1.0, -1.0])
-    if model["support_scale_origin"] == "centroid":
+    if model["support_scale_origin"] == "center":
+        cr = np.asarray(model["foot_center_right"], dtype=np.float64)
+        cl = cr * np.array([1.0, -1.0])
+    elif model["support_scale_origin"] == "hull_centroid":
         cr, cl = right.mean(0), left.mean(0)
     else:
         cr = cl = np.zeros(2)
