@@ -197,6 +197,10 @@ NWB_API int nwb_nearest_neighbour_batch(nwb_tree* tree, const double* q, int64_t
 NWB_API int nwb_nearest_neighbour_batch_dev(nwb_tree* tree, const double* q_dev, int64_t nq, int32_t* idx_dev,
                                             double* dist_dev);
 
+/* Diagnostic for the tests: an id of the scan thread that evaluates `node` when nq queries are passed (nodes with
+ * equal ids are evaluated one after the other by the same thread, in index order).  No reference counterpart. */
+NWB_API int64_t nwb_nn_scan_owner(const nwb_tree* tree, int64_t nq, int64_t node);
+
 /* ---- local planner operators ---------------------------------------------------------------------
  * weights: the 21 joint weights of RRT_Planner::setJointWeights (RP:307-311), NULL = all 1.0 (RP:76-78).
  * step:    max_step_size of solveQuery (planner_step_factor, 0.1). */

@@ -495,6 +495,10 @@ class Tree:
                         "nwb_nearest_neighbour_batch")
         return idx, dist
 
+    def scan_owner(self, nq, node):
+        """Diagnostic: id of the scan thread that evaluates `node` for a call with nq queries."""
+        return int(self.lib.nwb_nn_scan_owner(self.h, nq, node))
+
     def nearest_dev(self, q_dev, nq, idx_dev, dist_dev=None):
         self.ctx._check(self.lib.nwb_nearest_neighbour_batch_dev(self.h, q_dev, nq, idx_dev, dist_dev),
                         "nwb_nearest_neighbour_batch_dev")

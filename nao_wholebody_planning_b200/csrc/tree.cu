@@ -230,9 +230,12 @@ nn_scan_kernel(const float* __restrict__ soa, const double* __restrict__ aos, in
           const float v = s[k][u];
           if (v <= bound) {                             // candidate (nodes arrive in ascending index per thread)
             const int node = (int)(n0 + NPT * tid + u);
+            // a slot that is pushed out may still hold a node under the bound (the bound only shrinks, so one
+            // that is above it now stays out for good): that is a third live candidate -> exact rescan below
+            if (ci[k][1] >= 0 && cs[k][1] <= bound) ovf = true;
             if (v < cs[k][0]) { cs[k][1] = cs[k][0]; ci[k][1] = ci[k][0]; cs[k][0] = v; ci[k][0] = node; }
             else if (v < cs[k][1]) { cs[k][1] = v; ci[k][1] = node; }
-            else ovf = true;                            // a third candidate: resolved by the exact rescan below
+            else ovf = true;                            // neither slot gives way: also a third candidate
           }
         }
       }
@@ -599,6 +602,13 @@ int nwb_tree_get(nwb_tree* t, int64_t first, int64_t n, double* q_out, int32_t* 
   if (pred_out) TREE_CUDA(t, cudaMemcpyAsync(pred_out, t->pred + first, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s));
   TREE_CUDA(t, cudaStreamSynchronize(s));
   return NWB_OK;
+}
+
+int64_t nwb_nn_scan_owner(const nwb_tree* t, int64_t nq, int64_t node) {
+  if (!t || nq < 1 || node < 0 || node >= t->size) return NWB_E_INVALID;
+  const int64_t npt = nq == 1 ? NnCfg<1>::NPT : NnCfg<16>::NPT, tile = NN_THREADS * npt;
+  const int64_t nb = nn_grid_blocks(t);
+  return ((node / tile) % nb) * NN_THREADS + (node % tile) / npt;
 }
 
 int nwb_nearest_neighbour_batch_dev(nwb_tree* t, const double* q_dev, int64_t nq, int32_t* idx_dev, double* dist_dev) {

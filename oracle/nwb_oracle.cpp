@@ -169,6 +169,29 @@ void nwbo_chain_jacobian(int which, const double* q, double* J) {
   kdlr::jacobian(ch, q, J);
 }
 
+// ChainIkSolverVel_pinv on a chain at q (twist 6 -> qdot n) and the same pseudo-inverse application on an arbitrary
+// row-major 6 x n matrix (tests/test_pinv_svd_cpu.py checks both against numpy.linalg.svd, incl. sigma_min near eps)
+void nwbo_ik_vel_pinv(int which, const double* q, const double* twist, double eps, double* qdot) {
+  const Chains& c = chains();
+  const kdlr::Chain& ch = which == 0 ? c.right_leg : which == 1 ? c.left_leg : which == 2 ? c.legs : c.right_arm;
+  kdlr::ik_vel_pinv(ch, q, twist, qdot, eps);
+}
+void nwbo_pinv_apply(const double* J, int n, const double* twist, double eps, double* qdot, double* S_out) {
+  std::vector<double> U(6 * n), S(n), V(n * n), tmp(n);
+  kdlr::svd_jacobi(J, 6, n, U.data(), S.data(), V.data());
+  for (int i = 0; i < n; ++i) {
+    double sum = 0;
+    for (int j = 0; j < 6; ++j) sum += U[j * n + i] * twist[j];
+    tmp[i] = sum * (std::fabs(S[i]) < eps ? 0.0 : 1.0 / S[i]);
+    if (S_out) S_out[i] = S[i];
+  }
+  for (int i = 0; i < n; ++i) {
+    double sum = 0;
+    for (int j = 0; j < n; ++j) sum += V[i * n + j] * tmp[j];
+    qdot[i] = sum;
+  }
+}
+
 int nwbo_check_joint_limits(const double* q21) { return check_joint_limits(q21, nwbm::kJointMin, nwbm::kJointMax, NWB_NJ); }
 int nwbo_check_left_leg_pose(const nwb_params* p, const double* legs10) {
   return check_left_leg_pose(make_params(p, nullptr, 0), legs10);

@@ -75,6 +75,57 @@ def test_nn_near_ties_need_the_exact_pass(ctx, oracle):
     t.close()
 
 
+@pytest.mark.parametrize("nq", [1, 16])
+@pytest.mark.parametrize("order", ["descending", "ascending", "middle_first"])
+def test_nn_three_near_ties_in_one_scan_thread(ctx, oracle, nq, order):
+    """Three nodes that one scan thread evaluates one after the other, closer to the query than anything else and
+    within the fp32 band of each other (the band is 1.2e-5 in distance, the tie tolerance 1e-6): whatever order
+    their fp32 distances arrive in, the exact fp64 winner (lowest index on a tie) must come out.  Round 1 dropped
+    a live candidate when a thread's two-slot list was pushed from the front."""
+    n = 400_000
+    nodes = OL.uniform_configs(n, seed=77, lhyp_zero=True)
+    q = np.tile(OL.golden_db()[9], (nq, 1))
+    q[1:] += 1e-3 * np.random.default_rng(5).normal(size=(nq - 1, 21))
+    t = nwb.Tree(ctx, n)
+    t.add(nodes)
+    # three nodes of one owner
+    first = 1234
+    own = t.scan_owner(nq, first)
+    same = [first]
+    k = first + 1
+    while len(same) < 3 and k < n:
+        if t.scan_owner(nq, k) == own:
+            same.append(k)
+        k += 1
+    assert len(same) == 3, "tree too small for three nodes per scan thread"
+    t.close()
+    d = np.random.default_rng(6).normal(size=21)
+    d[15] = 0.0
+    d /= np.linalg.norm(d)
+    # radii: distinct in fp32 (2e-6 apart in distance -> 1.2e-6 in d^2 at r = 0.3, 40 ulp) but inside the band
+    radii = {"descending": [0.300004, 0.300002, 0.300000], "ascending": [0.300000, 0.300002, 0.300004],
+             "middle_first": [0.300002, 0.300004, 0.300000]}[order]
+    for node, r in zip(same, radii):
+        rot = np.roll(d, node % 5)
+        rot[15] = 0.0
+        rot /= np.linalg.norm(rot)
+        nodes[node] = q[0] + r * rot
+    t = nwb.Tree(ctx, n)
+    t.add(nodes)
+    idx, dist = t.findNearestNeighbour(q)
+    o_idx, o_dist = oracle.nearest_neighbour(nodes, q, threads=oracle.threads)
+    assert o_idx[0] in same
+    check(idx, dist, o_idx, o_dist, nodes, q)
+    # and an exact three-way tie inside one thread: lowest index wins
+    for node in same:
+        nodes[node] = nodes[same[2]]
+    t.clear()
+    t.add(nodes)
+    idx, dist = t.findNearestNeighbour(q)
+    assert idx[0] == same[0]
+    t.close()
+
+
 def test_nn_empty_tree_and_far_nodes(ctx):
     t = nwb.Tree(ctx)
     idx, dist = t.findNearestNeighbour(np.zeros((3, 21)))
