@@ -291,7 +291,7 @@ static int solve_fused(nwb_ctx* ctx, const double* starts, const double* goals, 
   const size_t in_bytes = off - o_in;
   const size_t o_out = off;
   const size_t o_res = carve(sizeof(int32_t) * 12 * Q), o_used = carve(16), o_ovf = carve(16);
-  const long long path_cap = (long long)Q * 512;
+  const long long path_cap = std::max<long long>((long long)Q * 512, 2 * C);   // one query's path always fits: <= 2 C rows
   const size_t o_paths = carve(sizeof(double) * NWB_NJ * (size_t)path_cap);
   const size_t head_bytes = o_paths - o_out;                             // res + used + overflow
   R_CUDA(ctx, grow(&ctx->d_rrt, &ctx->d_rrt_bytes, off));
@@ -332,7 +332,10 @@ static int solve_fused(nwb_ctx* ctx, const double* starts, const double* goals, 
   const int32_t* res = reinterpret_cast<const int32_t*>(H + (o_res - o_out));
   const unsigned long long used = *reinterpret_cast<const unsigned long long*>(H + (o_used - o_out));
   const int32_t overflow = *reinterpret_cast<const int32_t*>(H + (o_ovf - o_out));
-  bool pool_short = false;
+  // A query whose tree outgrew the capacity, or whose raw path did not fit the shared row pool, is NOT an error of the
+  // call: the reference's trees are unbounded std::vectors (RP:1067-1198).  Such queries are solved again on their own
+  // with doubled capacity (same seed, hence the same search) while every other result of the batch stands.
+  std::vector<int> redo;
   for (int k = 0; k < Q; ++k) {
     const int32_t* r = res + (size_t)k * 12;
     nwb_plan_result& o = results[k];
@@ -347,12 +350,9 @@ static int solve_fused(nwb_ctx* ctx, const double* starts, const double* goals, 
     o.nodes_goal = r[7];
     o.num_nodes_generated = o.success ? o.nodes_start + o.nodes_goal : 0;   // RP:1045: stays 0 unless a path is found
     o.raw_path_len = o.success ? r[8] : 0;
-    if (o.success && r[9] < 0) pool_short = true;
+    if (r[10] || (o.success && r[9] < 0)) redo.push_back(k);
   }
-  if (pool_short) {
-    ctx->err = "nwb_solve_query_batch: raw-path pool exhausted";
-    return NWB_E_NOMEM;
-  }
+  (void)overflow;
   if (raw_paths && used > 0) {
     const double* rows = reinterpret_cast<const double*>(H + head_bytes);
     std::vector<double> big;
@@ -364,15 +364,50 @@ static int solve_fused(nwb_ctx* ctx, const double* starts, const double* goals, 
     }
     for (int k = 0; k < Q; ++k) {
       const int32_t* r = res + (size_t)k * 12;
-      if (!r[2]) continue;
-      const int n = std::min<int>(r[8], raw_path_capacity);
+      if (!r[2] || r[9] < 0 || r[10]) continue;
+      const int n = std::min<int>(r[8], raw_path_capacity);                // the caller sees the full length in raw_path_len
       std::memcpy(raw_paths + (size_t)k * raw_path_capacity * NWB_NJ, rows + (size_t)r[9] * NWB_NJ, sizeof(double) * NWB_NJ * n);
     }
   }
   ctx->last_launches = launches;
-  if (overflow) {
-    ctx->err = "nwb_solve_query_batch: a tree outgrew tree_capacity";
-    return NWB_E_NOMEM;
+  if (!redo.empty()) {
+    constexpr int64_t kMaxTreeCapacity = (int64_t)1 << 21;                  // 2 M nodes per tree: 1.1 GB per query
+    if (2 * C > kMaxTreeCapacity) {
+      for (int k : redo) {
+        results[k].success = 0;
+        results[k].raw_path_len = 0;
+        results[k].num_nodes_generated = 0;
+      }
+      ctx->err = "nwb_solve_query_batch: a tree outgrew the largest supported capacity (2^21 nodes); that query is reported as failed";
+      return NWB_E_NOMEM;
+    }
+    const int R = (int)redo.size();
+    std::vector<double> st((size_t)R * NWB_NJ), go((size_t)R * NWB_NJ), ht(P ? (size_t)R * 6 * P : 0);
+    std::vector<uint64_t> sd(R);
+    std::vector<nwb_plan_result> rr(R);
+    std::vector<double> rp(raw_paths ? (size_t)R * raw_path_capacity * NWB_NJ : 0);
+    for (int i = 0; i < R; ++i) {
+      const int k = redo[i];
+      std::memcpy(&st[(size_t)i * NWB_NJ], starts + (size_t)k * NWB_NJ, sizeof(double) * NWB_NJ);
+      std::memcpy(&go[(size_t)i * NWB_NJ], goals + (size_t)k * NWB_NJ, sizeof(double) * NWB_NJ);
+      if (P) std::memcpy(&ht[(size_t)i * 6 * P], hand_traj + (size_t)k * 6 * P, sizeof(double) * 6 * P);
+      sd[i] = seeds[k];
+    }
+    const int64_t launches_so_far = ctx->last_launches;
+    int rc = NWB_OK;
+    for (int i = 0; i < R && rc == NWB_OK; ++i)                            // one at a time: the memory goes into ONE big forest
+      rc = solve_fused(ctx, &st[(size_t)i * NWB_NJ], &go[(size_t)i * NWB_NJ], 1, db, n_db, weights, &sd[i], max_iter, step,
+                       (int32_t)(2 * C), P ? &ht[(size_t)i * 6 * P] : nullptr, P, &rr[i],
+                       raw_paths ? &rp[(size_t)i * raw_path_capacity * NWB_NJ] : nullptr, raw_path_capacity);
+    for (int i = 0; i < R; ++i) {
+      const int k = redo[i];
+      results[k] = rr[i];
+      if (raw_paths && rr[i].success)
+        std::memcpy(raw_paths + (size_t)k * raw_path_capacity * NWB_NJ, &rp[(size_t)i * raw_path_capacity * NWB_NJ],
+                    sizeof(double) * NWB_NJ * std::min<int>(rr[i].raw_path_len, raw_path_capacity));
+    }
+    ctx->last_launches += launches_so_far;
+    return rc;
   }
   return NWB_OK;
 }
@@ -680,12 +715,12 @@ int nwb_shortcut_path(nwb_ctx* ctx, const double* raw, int32_t n_raw, double* ou
       cur_idx = cand[pick];
       cur = row(cur_idx);
       sel.push_back(cur);
-    } else {                                     // stuck: advance one raw way-point (RP:1891-1897)
+    } else if (cur_idx + 1 < W) {                // stuck: advance one raw way-point (RP:1891-1897)
       cur_idx = cur_idx + 1;
       cur = row(cur_idx);
       sel.push_back(cur);
-    }
-    --budget;
+    }                                            // else: the reference's loop never meets i == current_start_index (the
+    --budget;                                    // start already IS the last way-point): nothing is pushed, the budget runs down
   }
   if (edges_checked) *edges_checked = edges;
   if (budget == 0) return -100;

@@ -350,11 +350,18 @@ int plan_stage(nwb_ctx* ctx, const double* start, const double* goal, const doub
   int rc = nwb_solve_query_constrained_batch(ctx, start, goal, 1, ctx->ds_db.data(), (int32_t)(ctx->ds_db.size() / NWB_NJ), weights,
                                              &seed, P.planner_max_iterations, P.planner_step_factor, 0, hand_traj, n_pts, &r,
                                              raw.data(), cap);
+  if (rc == NWB_OK && r.success && r.raw_path_len > cap) {                // a raw path longer than the buffer: never truncate,
+    raw.resize((size_t)r.raw_path_len * NWB_NJ);                          // fetch it whole (same seed, same search)
+    rc = nwb_solve_query_constrained_batch(ctx, start, goal, 1, ctx->ds_db.data(), (int32_t)(ctx->ds_db.size() / NWB_NJ), weights,
+                                           &seed, P.planner_max_iterations, P.planner_step_factor, 0, hand_traj, n_pts, &r,
+                                           raw.data(), r.raw_path_len);
+  }
+  if (rc == NWB_E_NOMEM) rc = NWB_OK;       // the search outgrew the largest forest: reported as "no path" (r.success == 0)
   if (rc != NWB_OK) return rc;
   out.search_time = now_s() - t0;                                         // RP:1092-1094: stops before writePath
   if (!r.success) return NWB_OK;
   out.num_nodes = (uint32_t)r.num_nodes_generated;
-  const int n_raw = std::min(r.raw_path_len, cap);
+  const int n_raw = r.raw_path_len;
   if (!hand_traj) {                                                       // RP:1400-1405
     std::vector<double> sel((size_t)(n_raw + 8) * NWB_NJ);
     int n_sel = nwb_shortcut_path(ctx, raw.data(), n_raw, sel.data(), n_raw + 8, nullptr);
@@ -430,10 +437,10 @@ int shortcut_paths_batch(nwb_ctx* ctx, const std::vector<std::vector<double>>& r
       } else if (pick >= 0) {
         cur[k] = cand[pick];
         sel[k].push_back(cur[k]);
-      } else {                                              // stuck: advance one raw way-point (RP:1891-1897)
+      } else if (cur[k] + 1 < W[k]) {                       // stuck: advance one raw way-point (RP:1891-1897)
         cur[k] = cur[k] + 1;
         sel[k].push_back(cur[k]);
-      }
+      }                                                     // else nothing is pushed and the budget runs down (as RP:1884-1916)
       if (--budget[k] == 0) ok[k] = 0;                      // RP:1919-1923 (checked after the loop, reached or not)
     }
   }
@@ -826,6 +833,7 @@ int nwb_compute_motion_plan_batch(nwb_ctx* ctx, const nwb_compute_motion_plan_re
   t0 = now_s();
   rc = nwb_solve_query_batch(ctx, starts.data(), gcfg.data(), Q, ctx->ds_db.data(), (int32_t)(ctx->ds_db.size() / NWB_NJ), w,
                              qseeds.data(), P.planner_max_iterations, P.planner_step_factor, 0, res.data(), raw.get(), cap);
+  if (rc == NWB_E_NOMEM) rc = NWB_OK;       // a search that outgrew the largest forest is that request's failure, not the batch's
   if (rc != NWB_OK) return rc;
   const double t_search = now_s() - t0;
   std::vector<std::vector<double>> paths;
@@ -834,8 +842,19 @@ int nwb_compute_motion_plan_batch(nwb_ctx* ctx, const nwb_compute_motion_plan_re
     resps[live[i]].search_time = t_search;
     if (!res[i].success) continue;
     resps[live[i]].num_nodes_generated = (uint32_t)res[i].num_nodes_generated;
-    const int len = std::min(res[i].raw_path_len, cap);
-    paths.emplace_back(raw.get() + (size_t)i * cap * NWB_NJ, raw.get() + ((size_t)i * cap + len) * NWB_NJ);
+    const int len = res[i].raw_path_len;
+    if (len > cap) {                        // longer than the shared buffer's slot: fetch this path whole, never truncate
+      std::vector<double> whole((size_t)len * NWB_NJ);
+      nwb_plan_result r1;
+      rc = nwb_solve_query_batch(ctx, &starts[(size_t)i * NWB_NJ], &gcfg[(size_t)i * NWB_NJ], 1, ctx->ds_db.data(),
+                                 (int32_t)(ctx->ds_db.size() / NWB_NJ), w, &qseeds[i], P.planner_max_iterations,
+                                 P.planner_step_factor, 0, &r1, whole.data(), len);
+      if (rc != NWB_OK) return rc;
+      if (!r1.success || r1.raw_path_len != len) return bad(ctx, "nwb_compute_motion_plan_batch: a repeated search differs");
+      paths.push_back(std::move(whole));
+    } else {
+      paths.emplace_back(raw.get() + (size_t)i * cap * NWB_NJ, raw.get() + ((size_t)i * cap + len) * NWB_NJ);
+    }
     owner.push_back(live[i]);
   }
   std::vector<std::vector<int>> sel;

@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 #include <new>
 
@@ -482,12 +483,13 @@ int nn_launch(nwb_tree* t, const double* q_dev, int64_t nq, int32_t* idx_dev, do
   }
   cudaStream_t s = t->ctx->stream;
   constexpr size_t kNnSmem = sizeof(float) * NN_STAGES * NWB_NJ * NN_TILE + 8 * NN_STAGES;
-  static bool configured = false;
-  if (!configured) {
+  static std::atomic<bool> configured[64];             // the attribute is per device (contexts may live on several GPUs)
+  const int dev = t->ctx->device >= 0 && t->ctx->device < 64 ? t->ctx->device : 0;
+  if (!configured[dev].load(std::memory_order_relaxed)) {
     TREE_CUDA(t, cudaFuncSetAttribute(nn_scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNnSmem));
     TREE_CUDA(t, cudaFuncSetAttribute(nn_scan_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNnSmem));
     TREE_CUDA(t, cudaFuncSetAttribute(nn_scan_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNnSmem));
-    configured = true;
+    configured[dev].store(true, std::memory_order_relaxed);
   }
   TREE_CUDA(t, cudaEventRecord(t->ctx->ev0, s));
   // one query (the RRT loop): minimum arithmetic per tile; batches: 8 or 16 queries share each pass over the nodes

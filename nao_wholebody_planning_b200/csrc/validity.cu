@@ -14,6 +14,8 @@
 // so no tensor cores (BASELINE.json north_star).
 #include <cuda_runtime.h>
 
+#include <atomic>
+
 #include <algorithm>
 #include <cstdlib>
 
@@ -295,13 +297,11 @@ template <typename QT, bool COLLISION_ONLY, int PAIRS>
 static cudaError_t launch_packed(const ValidityTables& tab, const void* q, int64_t n, uint8_t* valid, uint8_t* reason,
                                  cudaStream_t stream) {
   auto kern = validity_packed_kernel<QT, COLLISION_ONLY, PAIRS>;
-  static bool configured = false;
   const size_t smem = (size_t)nwbm::kPointFloats * P2T * sizeof(float2);
   static_assert((size_t)nwbm::kPointFloats * sizeof(float2) >= 2 * NWB_NJ * sizeof(float), "staging must fit in the table");
-  if (!configured) {
+  {                                            // experiment build only: set on every launch (the attribute is per device)
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   const int64_t blocks = (n + 2 * P2T - 1) / (2 * P2T);
   kern<<<(unsigned)blocks, P2T, smem, stream>>>(tab, (const QT*)q, n, valid, reason);
@@ -310,26 +310,41 @@ static cudaError_t launch_packed(const ValidityTables& tab, const void* q, int64
 
 #endif  // NWB_ENABLE_PACKED
 
-static int g_sm_count = 0;
+// Function attributes and occupancy are PER DEVICE, and nwb_params.device allows contexts on several GPUs in one
+// process: every cache below is indexed by the current device and written atomically (benign races write equal values).
+constexpr int kMaxDevices = 64;
+static int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev < 0 || dev >= kMaxDevices ? 0 : dev;
+}
+static int device_sm_count(int dev) {
+  static std::atomic<int> sm[kMaxDevices];
+  int v = sm[dev].load(std::memory_order_relaxed);
+  if (!v) {
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    sm[dev].store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
 
 template <typename QT, bool MARGINS, bool COLLISION_ONLY, int PAIRS>
 static cudaError_t launch_persistent(const ValidityTables& tab, const GatherPeers& gp, const void* q, int64_t n, uint8_t* valid,
                                      uint8_t* reason, float* margins, cudaStream_t stream) {
   auto kern = validity_persistent_kernel<QT, MARGINS, COLLISION_ONLY, PAIRS>;
-  static int blocks_per_sm = 0;   // per instantiation
+  static std::atomic<int> bps[kMaxDevices];   // per instantiation and device
   const size_t smem = 2 * (size_t)PT * NWB_NJ * sizeof(QT) + 16;
+  const int dev = current_device();
+  int blocks_per_sm = bps[dev].load(std::memory_order_relaxed);
   if (!blocks_per_sm) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, PT, smem);
     if (e != cudaSuccess) return e;
     if (blocks_per_sm < 1) blocks_per_sm = 1;
-    if (!g_sm_count) {
-      int dev = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-    }
+    bps[dev].store(blocks_per_sm, std::memory_order_relaxed);
   }
+  const int g_sm_count = device_sm_count(dev);
   const int64_t tiles = (n + PT - 1) / PT;
   // NWB_RESERVE_SMS=k leaves k SMs free of persistent CTAs so that a concurrently running collective
   // (the NCCL verdict gather of the multi-GPU step) finds room instead of queueing behind this grid
@@ -343,12 +358,13 @@ template <typename QT, bool MARGINS, bool COLLISION_ONLY, int PAIRS>
 static cudaError_t launch_one(const ValidityTables& tab, const void* q, int64_t n, uint8_t* valid, uint8_t* reason,
                               float* margins, cudaStream_t stream) {
   auto kern = validity_kernel<QT, MARGINS, COLLISION_ONLY, PAIRS>;
-  static bool configured = false;   // per instantiation
+  static std::atomic<bool> configured[kMaxDevices];   // per instantiation and device
   const size_t smem = (PAIRS == PAIRS_TABLE ? kSmemFloats : NT * NWB_NJ) * sizeof(float);
-  if (!configured) {
+  const int dev = current_device();
+  if (!configured[dev].load(std::memory_order_relaxed)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured[dev].store(true, std::memory_order_relaxed);
   }
   const int64_t blocks = (n + NT - 1) / NT;
   kern<<<(unsigned)blocks, NT, smem, stream>>>(tab, (const QT*)q, n, valid, reason, margins);
