@@ -19,6 +19,11 @@ tests always evaluated, one kernel launch).
   cpu_baseline  the CPU oracle (a port: the reference cannot be built here) on a bounded sample,
             one thread, on this box's host cores
 
+Extra keys of the same line (bench_sections.py; BASELINE configs 3-5, inputs of SURVEY.md section 8d): `validity_scenes`
+(S1 shelf and a generated 256-box scene), `nn_scan` {1e4,1e5,1e6} x {1,1024}, `connect`, `edge_check` 4096 x 102, `dbgen`
+(2^20 on one GPU + 2^26 strong-scaled over the ranks, fused peer append, digest equal at every N), `grasp_queries` 256 / 1681
+sharded round-robin with a packed NCCL gather (digest equal at every N).  `--no-sections` skips them.
+
 Multi-GPU: the batch shards by index, no data-path collective; the 1 B/config verdicts reach every
 rank because the validity kernel stores them into all ranks' gathered arrays through peer-mapped
 memory (NVLink / NVSwitch) - a fused compute + gather.  NCCL is used for the barrier, the max-over-ranks
@@ -189,13 +194,72 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample_per_step": n},
+            "config": {"workload": WORKLOAD, "batch_per_gpu": B_PER_GPU},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     if args.gpus == 1 and not args.no_scenario3:
         line["scenario3"] = scenario3_cpu(3)
     print(json.dumps(line))
+
+
+def run_sections(args, torch, dist, nwb, ctx, dev, rank, world, barrier, ffma_tflops):
+    """BASELINE configs 3-5 as extra keys (bench_sections.py).  A section that fails reports {"error": ...} instead of
+    taking the headline down with it.  Single-GPU operators (scenes, nn_scan, connect, edge_check) run at N = 1 only;
+    dbgen and grasp_queries run at every N (strong scaling, digests equal across N)."""
+    import bench_sections as BS
+    import oracle_lib as OL
+    from nao_wholebody_planning_b200 import sharding
+    out = {}
+    orc = OL.Oracle() if rank == 0 else None
+    cpu = not args.no_cpu_baseline
+    rf = load_json(ROOT / "profiles" / "roofline.json", {})
+    peaks = load_json(ROOT / "MEASURED_PEAKS.json", {})
+    hbm = peaks.get("hbm_gbs") or 6538.9
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def guarded(name, fn):
+        try:
+            v = fn()
+            if rank == 0 and v is not None:
+                out[name] = v
+        except Exception as e:                                   # noqa: BLE001 - reported, never hidden
+            import traceback
+            traceback.print_exc()
+            if rank == 0:
+                out[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            if world > 1:
+                raise                                            # a rank out of step would hang the others: fail loudly
+
+    if world == 1:
+        stream = torch.cuda.Stream(device=dev)
+        ctx.set_stream(stream.cuda_stream)
+        flush = BS.L2Flush(torch, dev, stream)
+        t0 = time.perf_counter()
+        nodes_all, n_proj = BS.v1c_nodes(nwb, ctx, OL, 1_000_000)
+        prep_s = time.perf_counter() - t0
+        guarded("validity_scenes", lambda: BS.section_validity_scenes(torch, nwb, OL, orc, stream, dev, ffma_tflops, rf, cpu))
+        guarded("nn_scan", lambda: BS.section_nn_scan(torch, nwb, ctx, OL, orc, stream, dev, nodes_all, hbm, ffma_tflops, flush))
+        guarded("edge_check", lambda: BS.section_edge_check(torch, nwb, ctx, OL, orc, stream, dev, nodes_all, ffma_tflops,
+                                                            rf.get("collision_only_S0_all_pairs_flops_per_config", 0)))
+        ctx.set_stream(None)
+        guarded("connect", lambda: BS.section_connect(nwb, ctx, OL, orc, nodes_all))
+        out["v2_inputs"] = {"nodes": "first N rows of V1c (uniform, LHipYawPitch = 0, after the double-support projection)",
+                            "rows_changed_by_the_projection": n_proj, "prepare_s": prep_s,
+                            "queries": "1024 database rows, index stream seed 20121002 (RP:319-320)"}
+        del nodes_all
+    ctx.set_stream(None)
+    ctx.set_ds_database(OL.golden_db())
+    guarded("dbgen", lambda: BS.section_dbgen(torch, dist, nwb, sharding, ctx, orc, dev, rank, world, barrier, max_over_ranks, cpu=cpu))
+    guarded("grasp_queries", lambda: BS.section_grasp_queries(torch, dist, nwb, sharding, ctx, OL, orc, dev, rank, world, barrier,
+                                                              max_over_ranks, cpu=cpu))
+    return out
 
 
 def main():
@@ -207,6 +271,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-scenario3", action="store_true", help="skip the scenario-3 plan-time measurement (N = 1 only)")
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="configurations per GPU (default = the headline size)")
+    ap.add_argument("--no-sections", action="store_true", help="skip the extra keys (configs 3-5: nn_scan, edge_check, connect, dbgen, grasp_queries)")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the process to the GPU's NUMA node before allocating pinned memory")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -226,6 +292,17 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    os.environ.setdefault("NWB_EDGE_FULL", "1")     # edge checks evaluate every way-point: the roofline counts all of them
+    # pinned staging buffers NUMA-local to this GPU's PCIe root: bind BEFORE anything allocates pinned memory
+    numa = None
+    if not args.no_numa_bind:
+        from nao_wholebody_planning_b200 import sharding as _sh
+        pr = torch.cuda.get_device_properties(local_rank)
+        try:
+            bus_id = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        except AttributeError:
+            bus_id = ""
+        numa = _sh.bind_to_gpu_numa_node(bus_id) if bus_id else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -328,6 +405,26 @@ def main():
     for _ in range(2):
         ctx.is_feasible_host_buffers(pin_q.ptr, n, pin_v.ptr)
     barrier()
+    # the wire under the end-to-end number: this rank's pinned H2D copy rate while ALL ranks copy at the same time
+    h2d_src = torch.empty(n * nwb.NJ, dtype=torch.float64).pin_memory()
+    h2d_dst = torch.empty(n * nwb.NJ, dtype=torch.float64, device=dev)
+    h2d_dst.copy_(h2d_src, non_blocking=True)
+    barrier()
+    ha, hb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ha.record()
+    for _ in range(4):
+        h2d_dst.copy_(h2d_src, non_blocking=True)
+    hb.record()
+    torch.cuda.synchronize(dev)
+    h2d_gbs = 4 * n * nwb.NJ * 8 / (ha.elapsed_time(hb) * 1e-3) / 1e9
+    h2d_all = [h2d_gbs]
+    if world > 1:
+        t = torch.tensor([h2d_gbs], device=dev, dtype=torch.float64)
+        parts = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(parts, t)
+        h2d_all = [float(x.item()) for x in parts]
+    del h2d_src, h2d_dst
+    barrier()
     e2e_steps = max(3, min(args.steps, 10))
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
@@ -362,18 +459,23 @@ def main():
     pin_qf.free()
     pin_vf.free()
 
+    sections = {} if args.no_sections else run_sections(args, torch, dist, nwb, ctx, dev, rank, world, barrier, ffma_tflops)
+
     if rank == 0:
         rf = load_json(ROOT / "profiles" / "roofline.json", {})
         flops_cfg = rf.get("validity_S0_flops_per_config")
         peaks = load_json(ROOT / "MEASURED_PEAKS.json", {})
         ncu = load_json(ROOT / "profiles" / "validity_ncu_summary.json", {})
         achieved = flops_cfg * n / (kern_ms * 1e-3) / 1e12 if flops_cfg else None
-        roofline = {"bound": "fp32", "kernel": "nwb::validity_kernel<double,false,false>",
+        roofline = {"bound": "fp32", "kernel": "nwb::validity_persistent_kernel<double, MARGINS=false, COLLISION_ONLY=false, PAIRS_STATIC_GROUP>",
                     "achieved": achieved, "peak": ffma_tflops, "unit": "TFLOP/s",
                     "frac": (achieved / ffma_tflops) if achieved else None,
                     "peak_source": "nwb_ffma_peak measured live in this run (MEASURED_PEAKS.json has no FP32 figure; nominal 74.4)",
                     "flops_per_config": flops_cfg, "kernel_ms": kern_ms,
                     "traffic": ncu.get("dram_bytes_per_launch"),
+                    "traffic_source": "profiles/validity_ncu_summary.json (dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full "
+                                      "capture of this kernel, per launch; not re-measured in this run)",
+                    "algorithmic_bytes_per_launch": n * 170,
                     "hbm_view": {"achieved_gbs": n * 170 / (kern_ms * 1e-3) / 1e9, "peak_gbs": peaks.get("hbm_gbs"),
                                  "note": "170 B/config (168 in, 2 out): far from the HBM bound, as designed"}}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -387,7 +489,9 @@ def main():
                                              "all_gather after the timed region: %s" % gather_ok) if world > 1 else None,
                            "valid_fraction": float(valid.float().mean().item())},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * nwb.NJ * 8, "d2h_bytes_per_step": n,
-                        "steps": e2e_steps, "api": "nwb_is_feasible_batch (pinned host buffers, float64 as the reference keeps them)"},
+                        "steps": e2e_steps, "h2d_gbs_per_rank_all_ranks_copying": h2d_all,
+                        "wire_bound_configs_per_s": sum(h2d_all) * 1e9 / (nwb.NJ * 8),
+                        "numa_bind": ({"node": numa[0], "cpus": numa[1]} if numa else None), "api": "nwb_is_feasible_batch (pinned host buffers, float64 as the reference keeps them)"},
                 "e2e_f32_input": {"value": e2e32_value, "unit": UNIT, "h2d_bytes_per_step": n * nwb.NJ * 4, "d2h_bytes_per_step": n,
                                   "api": "nwb_is_feasible_batch_f32 (supplementary: callers holding float32 configurations)",
                                   "verdicts_equal_to_f64_input": e2e32_same, "of": n},
@@ -401,6 +505,7 @@ def main():
             line["scenario3"] = scenario3_gpu(101)
             if not args.no_cpu_baseline:
                 line["scenario3"]["cpu_baseline"] = scenario3_cpu(3)
+        line.update(sections)
         print(json.dumps(line))
     pin_q.free()
     pin_v.free()

@@ -140,6 +140,11 @@ NWB_API int nwb_ctx_set_stream(nwb_ctx* ctx, void* cuda_stream);
  *   center[3], size[3] = full extents, rot[9] = row-major rotation (NULL = axis aligned). */
 NWB_API int nwb_scene_clear(nwb_ctx* ctx);
 NWB_API int nwb_scene_add_box(nwb_ctx* ctx, const double* center, const double* size, const double* rot);
+/* n boxes at once, boxes15 [n][15] = {center[3], size[3], rot[9]}: one rebuild of the scene structures for the set.
+ * Up to 16 boxes travel in the kernel parameters; larger scenes (up to 2^20 boxes) are kept in device memory under a
+ * flattened bounding-volume hierarchy that the validity kernels stage through shared memory (exact capsule-box leaf
+ * test either way: same verdicts as testing every box). */
+NWB_API int nwb_scene_add_boxes(nwb_ctx* ctx, const double* boxes15, int64_t n);
 NWB_API int nwb_scene_num_boxes(const nwb_ctx* ctx);
 
 /* Batched state validity: collision-free AND statically stable, both tests always evaluated

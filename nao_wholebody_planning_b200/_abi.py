@@ -181,6 +181,7 @@ def _declare(lib):
         "nwb_ctx_set_stream": (C.c_int, [vp, vp]),
         "nwb_scene_clear": (C.c_int, [vp]),
         "nwb_scene_add_box": (C.c_int, [vp, pd, pd, pd]),
+        "nwb_scene_add_boxes": (C.c_int, [vp, vp, i64]),
         "nwb_scene_num_boxes": (C.c_int, [vp]),
         "nwb_is_feasible_batch": (C.c_int, [vp, vp, i64, vp, vp, vp]),
         "nwb_is_feasible_batch_f32": (C.c_int, [vp, vp, i64, vp, vp, vp]),

@@ -85,8 +85,8 @@ class Context:
 
     def scene_add_boxes(self, boxes15):
         """rows of [cx,cy,cz, sx,sy,sz, R row-major] (tests/oracle_lib.scene_boxes layout)."""
-        for b in np.asarray(boxes15, dtype=np.float64).reshape(-1, 15):
-            self.scene_add_box(b[0:3], b[3:6], b[6:15])
+        b = np.ascontiguousarray(boxes15, dtype=np.float64).reshape(-1, 15)
+        self._check(self.lib.nwb_scene_add_boxes(self.h, _p(b), len(b)), "nwb_scene_add_boxes")
 
     @property
     def num_boxes(self):

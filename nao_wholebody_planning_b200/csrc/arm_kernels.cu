@@ -130,7 +130,7 @@ goal_sample_kernel(const __grid_constant__ PlanConst pc, const __grid_constant__
 #pragma unroll
     for (int j = 0; j < NWB_NJ; ++j) qf[j] = (float)q[j];
     ArmLocalStore st;
-    ValidityResult<float> r = evaluate_config<float, ArmLocalStore, false, false, STATIC ? PAIRS_STATIC_GROUP : PAIRS_TABLE, /*ENV_CULL=*/true>(tab, qf, st, nullptr, nullptr);
+    ValidityResult<float> r = evaluate_config<float, ArmLocalStore, false, false, STATIC ? PAIRS_STATIC_GROUP : PAIRS_TABLE, /*ENV_CULL=*/true, /*BIG_SCENE=*/true>(tab, qf, st, nullptr, nullptr);
     const bool feasible = !r.hit && r.stable;
     stage = feasible ? 2 : 1;
     if (feasible) {
@@ -275,7 +275,7 @@ goal_solve_kernel(const __grid_constant__ PlanConst pc, const __grid_constant__ 
 #pragma unroll
   for (int j = 0; j < NWB_NJ; ++j) qf[j] = (float)g.q[j];
   ArmLocalStore st;
-  ValidityResult<float> r = evaluate_config<float, ArmLocalStore, false, false, STATIC ? PAIRS_STATIC_GROUP : PAIRS_TABLE, /*ENV_CULL=*/true>(tab, qf, st, nullptr, nullptr);
+  ValidityResult<float> r = evaluate_config<float, ArmLocalStore, false, false, STATIC ? PAIRS_STATIC_GROUP : PAIRS_TABLE, /*ENV_CULL=*/true, /*BIG_SCENE=*/true>(tab, qf, st, nullptr, nullptr);
   if (r.hit || !r.stable) return;
   unsigned long long slot = atomicAdd(row_req ? n_out : n_out + g.qi, 1ull);
   if ((int64_t)slot < cap) {

@@ -40,9 +40,41 @@ int ensure(Ctx* ctx, void** buf, size_t* have, size_t need) {
 }  // namespace
 
 namespace nwb {
+// Scenes of more than kMaxBoxes boxes: hierarchy + boxes in one device block [nodes | boxes], rebuilt on every change
+// of the scene.  The stream is drained first: kernels in flight may still read the previous block.
+static void upload_scene(Ctx* ctx, SceneView& view) {
+  view = SceneView{nullptr, nullptr, 0, 0};
+  if (ctx->boxes.size() <= (size_t)kMaxBoxes) return;
+  build_scene_bvh(ctx->boxes, ctx->bvh);
+  const size_t nb = sizeof(SceneNode) * ctx->bvh.size(), bb = sizeof(SceneBox) * ctx->boxes.size();
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->d_scene_bytes < nb + bb) {
+    if (ctx->d_scene) cudaFree(ctx->d_scene);
+    ctx->d_scene = nullptr;
+    ctx->d_scene_bytes = 0;
+    const size_t cap = std::max(nb + bb, (size_t)1 << 16) * 2;
+    if (cudaMalloc(&ctx->d_scene, cap) != cudaSuccess) {
+      ctx->err = "scene upload: out of device memory";
+      return;
+    }
+    ctx->d_scene_bytes = cap;
+  }
+  char* base = static_cast<char*>(ctx->d_scene);
+  cudaMemcpy(base, ctx->bvh.data(), nb, cudaMemcpyHostToDevice);
+  cudaMemcpy(base + nb, ctx->boxes.data(), bb, cudaMemcpyHostToDevice);
+  view.nodes = reinterpret_cast<const SceneNode*>(base);
+  view.boxes = reinterpret_cast<const SceneBox*>(base + nb);
+  view.n_nodes = (int)ctx->bvh.size();
+  view.n_boxes = (int)ctx->boxes.size();
+}
+
 void build_tables(Ctx* ctx) {
   build_validity_tables(ctx->params, ctx->boxes, true, ctx->tab_group);
   build_validity_tables(ctx->params, ctx->boxes, false, ctx->tab_all);
+  upload_scene(ctx, ctx->tab_group.scene);
+  ctx->tab_all.scene = ctx->tab_group.scene;
+  ctx->scene_dirty = false;
   if (getenv("NWB_ENV_NO_CULL")) ctx->tab_group.env_cull = ctx->tab_all.env_cull = 0;   // full evaluation (roofline runs)
 }
 }  // namespace nwb
@@ -143,6 +175,7 @@ void nwb_ctx_destroy(nwb_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
   if (ctx->d_in) cudaFree(ctx->d_in);
+  if (ctx->d_scene) cudaFree(ctx->d_scene);
   if (ctx->d_out) cudaFree(ctx->d_out);
   if (ctx->d_plan) cudaFree(ctx->d_plan);
   if (ctx->d_forest) cudaFree(ctx->d_forest);
@@ -189,7 +222,7 @@ int nwb_scene_clear(nwb_ctx* ctx) {
 
 int nwb_scene_add_box(nwb_ctx* ctx, const double* center, const double* size, const double* rot) {
   if (!ctx || !center || !size) return fail(ctx, NWB_E_INVALID, "nwb_scene_add_box: bad argument");
-  if ((int)ctx->boxes.size() >= kMaxBoxes) return fail(ctx, NWB_E_INVALID, "nwb_scene_add_box: scene is full (16 boxes)");
+  if (ctx->boxes.size() >= (size_t)kSceneBoxLimit) return fail(ctx, NWB_E_INVALID, "nwb_scene_add_box: scene is full (2^20 boxes)");
   if (!(size[0] > 0 && size[1] > 0 && size[2] > 0)) return fail(ctx, NWB_E_INVALID, "nwb_scene_add_box: size must be > 0");
   SceneBox b{};
   for (int k = 0; k < 3; ++k) {
@@ -199,7 +232,28 @@ int nwb_scene_add_box(nwb_ctx* ctx, const double* center, const double* size, co
   for (int k = 0; k < 9; ++k) b.r[k] = rot ? (float)rot[k] : (k % 4 == 0 ? 1.f : 0.f);
   ctx->boxes.push_back(b);
   build_tables(ctx);
-  return NWB_OK;
+  return ctx->boxes.size() > (size_t)kMaxBoxes && !ctx->tab_group.scene.nodes ? NWB_E_NOMEM : NWB_OK;
+}
+
+int nwb_scene_add_boxes(nwb_ctx* ctx, const double* boxes15, int64_t n) {
+  if (!ctx || n < 0 || (n > 0 && !boxes15)) return fail(ctx, NWB_E_INVALID, "nwb_scene_add_boxes: bad argument");
+  if (ctx->boxes.size() + (size_t)n > (size_t)kSceneBoxLimit) return fail(ctx, NWB_E_INVALID, "nwb_scene_add_boxes: scene is full (2^20 boxes)");
+  for (int64_t i = 0; i < n; ++i) {
+    const double* v = boxes15 + 15 * i;
+    if (!(v[3] > 0 && v[4] > 0 && v[5] > 0)) return fail(ctx, NWB_E_INVALID, "nwb_scene_add_boxes: size must be > 0");
+  }
+  for (int64_t i = 0; i < n; ++i) {
+    const double* v = boxes15 + 15 * i;
+    SceneBox b{};
+    for (int k = 0; k < 3; ++k) {
+      b.c[k] = (float)v[k];
+      b.h[k] = (float)(0.5 * v[3 + k]);
+    }
+    for (int k = 0; k < 9; ++k) b.r[k] = (float)v[6 + k];
+    ctx->boxes.push_back(b);
+  }
+  build_tables(ctx);                         // one hierarchy build + upload for the whole set
+  return ctx->boxes.size() > (size_t)kMaxBoxes && !ctx->tab_group.scene.nodes ? NWB_E_NOMEM : NWB_OK;
 }
 
 int nwb_scene_num_boxes(const nwb_ctx* ctx) { return ctx ? (int)ctx->boxes.size() : NWB_E_INVALID; }

@@ -13,7 +13,8 @@ namespace nwb {
 
 constexpr int kMaxPairs = 112;
 constexpr int kMaxRuns = 48;
-constexpr int kMaxBoxes = 16;
+constexpr int kMaxBoxes = 16;              // boxes that travel inline in the kernel parameters
+constexpr int kSceneBoxLimit = 1 << 20;    // boxes of a scene held in global memory under the hierarchy
 
 // One collision pair inside a run: B's point-table slot and constants.
 struct PairEntry {
@@ -30,10 +31,25 @@ struct PairRun {
   int first;     // index of the first PairEntry
   int count;
 };
-struct SceneBox {   // oriented box in the r_sole frame
+struct alignas(16) SceneBox {   // oriented box in the r_sole frame (64 B: four 16-byte loads from global / shared memory)
   float c[3];
   float h[3];      // half extents
   float r[9];      // row-major rotation, columns = box axes
+  float pad;
+};
+// Scenes of more than kMaxBoxes boxes live in global memory under a flattened bounding-volume hierarchy: nodes in
+// depth-first order, `skip` = index of the next node when this subtree is culled (stack-free walk), a leaf holds ONE box.
+struct alignas(16) SceneNode {
+  float lo[3];
+  int skip;
+  float hi[3];
+  int box;         // >= 0: leaf, index into the box array; -1: inner node
+};
+struct SceneView {
+  const SceneNode* nodes;   // device memory, nullptr when the scene is inline (<= kMaxBoxes boxes)
+  const SceneBox* boxes;
+  int n_nodes;
+  int n_boxes;
 };
 struct EnvLink {    // a robot proxy tested against the scene boxes
   int off;
@@ -53,8 +69,9 @@ struct ValidityTables {
   int env_cull;                        // 1: skip the exact capsule-box test where a warp agrees the bounding sphere is clear
   PairRun runs[kMaxRuns];
   PairEntry entries[kMaxPairs];
-  SceneBox boxes[kMaxBoxes];
+  SceneBox boxes[kMaxBoxes];            // inline scene (n_boxes <= kMaxBoxes), else n_boxes = 0 and `scene` holds it
   EnvLink env_links[nwbm::kNumGeom];
+  SceneView scene;                      // large scene: BVH + boxes in global memory (owned by the context)
 };
 
 // Fused result gather: besides its own verdict array, the validity kernel stores each verdict into
@@ -76,6 +93,9 @@ struct Ctx {
   cudaEvent_t in_done[2] = {nullptr, nullptr}, k_done[2] = {nullptr, nullptr};
   std::string err;
   std::vector<SceneBox> boxes;
+  std::vector<SceneNode> bvh;                          // host copy of the hierarchy (scenes of more than kMaxBoxes boxes)
+  void* d_scene = nullptr; size_t d_scene_bytes = 0;   // [nodes | boxes] on the device
+  bool scene_dirty = false;                            // boxes changed since the last upload (bulk adds upload once)
   ValidityTables tab_group;   // isFeasible pair set
   ValidityTables tab_all;     // isPathValid pair set
   // scratch device buffers for the host-pointer entry points (grown on demand)

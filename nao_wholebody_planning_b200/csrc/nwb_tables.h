@@ -2,6 +2,7 @@
 // (pair runs from the SRDF-derived pair list, scaled foot polygons, scene boxes).  Header-only so the
 // flop-counting tool can build the same tables without the CUDA runtime.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <map>
@@ -98,9 +99,67 @@ inline void build_validity_tables(const nwb_params& params, const std::vector<Sc
     t.foot_left[i][1] = (float)(-y);
   }
   fill_pairs(params, t, group_only);
-  t.n_boxes = (int)boxes.size();
+  // up to kMaxBoxes boxes travel inline in the kernel parameters; larger scenes go through t.scene (set by the caller)
+  t.n_boxes = boxes.size() <= (size_t)kMaxBoxes ? (int)boxes.size() : 0;
   for (int b = 0; b < t.n_boxes; ++b) t.boxes[b] = boxes[b];
   t.env_cull = 1;
+}
+
+// Axis-aligned bounds of an oriented box.
+inline void box_aabb(const SceneBox& b, float* lo, float* hi) {
+  for (int k = 0; k < 3; ++k) {
+    const float e = std::fabs(b.r[3 * k + 0]) * b.h[0] + std::fabs(b.r[3 * k + 1]) * b.h[1] + std::fabs(b.r[3 * k + 2]) * b.h[2];
+    lo[k] = b.c[k] - e;
+    hi[k] = b.c[k] + e;
+  }
+}
+
+// Flattened bounding-volume hierarchy over the scene boxes: median split of the box centres along the widest axis,
+// one box per leaf, nodes in depth-first order with skip links.
+inline void build_scene_bvh(const std::vector<SceneBox>& boxes, std::vector<SceneNode>& nodes) {
+  nodes.clear();
+  const int n = (int)boxes.size();
+  if (n == 0) return;
+  std::vector<int> order(n);
+  for (int i = 0; i < n; ++i) order[i] = i;
+  nodes.reserve(2 * n);
+  struct Rec {
+    static int build(const std::vector<SceneBox>& boxes, std::vector<int>& order, int first, int last, std::vector<SceneNode>& nodes) {
+      const int me = (int)nodes.size();
+      nodes.push_back(SceneNode{});
+      float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f}, clo[3] = {1e30f, 1e30f, 1e30f}, chi[3] = {-1e30f, -1e30f, -1e30f};
+      for (int i = first; i < last; ++i) {
+        float l[3], h[3];
+        box_aabb(boxes[order[i]], l, h);
+        for (int k = 0; k < 3; ++k) {
+          lo[k] = std::min(lo[k], l[k]);
+          hi[k] = std::max(hi[k], h[k]);
+          clo[k] = std::min(clo[k], boxes[order[i]].c[k]);
+          chi[k] = std::max(chi[k], boxes[order[i]].c[k]);
+        }
+      }
+      if (last - first == 1) {
+        nodes[me].box = order[first];
+      } else {
+        nodes[me].box = -1;
+        int ax = 0;
+        for (int k = 1; k < 3; ++k)
+          if (chi[k] - clo[k] > chi[ax] - clo[ax]) ax = k;
+        const int mid = (first + last) / 2;
+        std::nth_element(order.begin() + first, order.begin() + mid, order.begin() + last,
+                         [&](int a, int b) { return boxes[a].c[ax] < boxes[b].c[ax] || (boxes[a].c[ax] == boxes[b].c[ax] && a < b); });
+        build(boxes, order, first, mid, nodes);
+        build(boxes, order, mid, last, nodes);
+      }
+      for (int k = 0; k < 3; ++k) {
+        nodes[me].lo[k] = lo[k];
+        nodes[me].hi[k] = hi[k];
+      }
+      nodes[me].skip = (int)nodes.size();
+      return me;
+    }
+  };
+  Rec::build(boxes, order, 0, n, nodes);
 }
 
 }  // namespace nwb

@@ -112,8 +112,11 @@ int nwb_connect_batch(nwb_ctx* ctx, const double* q_start, const double* q_conne
   make_plan_const(ctx, weights, step, pc);
   P_CUDA(ctx, cudaMemcpyAsync(A.at<double>(o_s), q_start, qb, cudaMemcpyHostToDevice, s));
   P_CUDA(ctx, cudaMemcpyAsync(A.at<double>(o_c), q_connect, qb, cudaMemcpyHostToDevice, s));
+  P_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
   P_CUDA(ctx, launch_connect(pc, ctx->tab_group, static_pairs(ctx), A.at<double>(o_s), A.at<double>(o_c), n_edges, max_steps,
                              A.at<double>(o_n), A.at<int32_t>(o_a), A.at<int32_t>(o_st), s));
+  P_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
+  ctx->last_ms = -1;
   P_CUDA(ctx, cudaMemcpyAsync(nodes_out, A.at<double>(o_n), nb, cudaMemcpyDeviceToHost, s));
   P_CUDA(ctx, cudaMemcpyAsync(n_added, A.at<int32_t>(o_a), ib, cudaMemcpyDeviceToHost, s));
   P_CUDA(ctx, cudaMemcpyAsync(status, A.at<int32_t>(o_st), ib, cudaMemcpyDeviceToHost, s));

@@ -35,7 +35,7 @@ __device__ __forceinline__ ValidityResult<float> eval_one(const ValidityTables& 
   for (int j = 0; j < NWB_NJ; ++j) qf[j] = (float)q[j];
   LocalStore st;
   constexpr int P = STATIC ? (COLLISION_ONLY ? PAIRS_STATIC_ALL : PAIRS_STATIC_GROUP) : PAIRS_TABLE;
-  return evaluate_config<float, LocalStore, false, COLLISION_ONLY, P, /*ENV_CULL=*/true>(tab, qf, st, nullptr, nullptr);
+  return evaluate_config<float, LocalStore, false, COLLISION_ONLY, P, /*ENV_CULL=*/true, /*BIG_SCENE=*/true>(tab, qf, st, nullptr, nullptr);
 }
 
 // ---- steer + project ----------------------------------------------------------------------------
@@ -418,6 +418,58 @@ __device__ __forceinline__ bool config_valid_warp(const ValidityTables& tab, con
       d2 = seg_box_dist2(A, D, H);
     }
     hit = hit || (d2 < el.radius * el.radius);
+  }
+  // large scene: the whole warp walks the hierarchy with the (identical) bounding box of the robot; at a leaf the
+  // links are dealt out over the lanes
+  if (tab.scene.n_nodes > 0) {
+    float rlo[3] = {1e30f, 1e30f, 1e30f}, rhi[3] = {-1e30f, -1e30f, -1e30f};
+    for (int l = 0; l < tab.n_env_links; ++l) {
+      const EnvLink& el = tab.env_links[l];
+      const float rr = el.radius + 1.0e-4f;
+      float p[3];
+      load3(st, el.off, p);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { rlo[k] = fminf(rlo[k], p[k] - rr); rhi[k] = fmaxf(rhi[k], p[k] + rr); }
+      if (!el.is_sphere) {
+        load3(st, el.off + 3, p);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { rlo[k] = fminf(rlo[k], p[k] - rr); rhi[k] = fmaxf(rhi[k], p[k] + rr); }
+      }
+    }
+    int node = 0;
+    while (node < tab.scene.n_nodes) {
+      const SceneNode nd = tab.scene.nodes[node];
+      const bool apart = nd.lo[0] > rhi[0] || rlo[0] > nd.hi[0] || nd.lo[1] > rhi[1] || rlo[1] > nd.hi[1] || nd.lo[2] > rhi[2] ||
+                         rlo[2] > nd.hi[2];
+      if (apart) { node = nd.skip; continue; }
+      ++node;
+      if (nd.box < 0) continue;
+      const SceneBox bx = tab.scene.boxes[nd.box];
+      for (int l = lane; l < tab.n_env_links; l += 32) {
+        const EnvLink& el = tab.env_links[l];
+        const float H[3] = {bx.h[0], bx.h[1], bx.h[2]};
+        float pa[3], A[3];
+        load3(st, el.off, pa);
+        const float rx = pa[0] - bx.c[0], ry = pa[1] - bx.c[1], rz = pa[2] - bx.c[2];
+        A[0] = fmaf(bx.r[6], rz, fmaf(bx.r[3], ry, bx.r[0] * rx));
+        A[1] = fmaf(bx.r[7], rz, fmaf(bx.r[4], ry, bx.r[1] * rx));
+        A[2] = fmaf(bx.r[8], rz, fmaf(bx.r[5], ry, bx.r[2] * rx));
+        float d2;
+        if (el.is_sphere) {
+          const float ex = box_excess(A[0], H[0]), ey = box_excess(A[1], H[1]), ez = box_excess(A[2], H[2]);
+          d2 = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
+        } else {
+          float qa[3], D[3];
+          load3(st, el.off + 3, qa);
+          const float dx = qa[0] - pa[0], dy = qa[1] - pa[1], dz = qa[2] - pa[2];
+          D[0] = fmaf(bx.r[6], dz, fmaf(bx.r[3], dy, bx.r[0] * dx));
+          D[1] = fmaf(bx.r[7], dz, fmaf(bx.r[4], dy, bx.r[1] * dx));
+          D[2] = fmaf(bx.r[8], dz, fmaf(bx.r[5], dy, bx.r[2] * dx));
+          d2 = seg_box_dist2(A, D, H);
+        }
+        hit = hit || (d2 < el.radius * el.radius);
+      }
+    }
   }
   hit = __any_sync(0xffffffffu, hit);
   return !hit && stable;

@@ -73,7 +73,7 @@ struct FkVisitor {
 // ---- the validity kernel ------------------------------------------------------------------------
 //   MARGINS        also produce {min separation, signed hull distance} (sqrt per pair + gift wrapping)
 //   COLLISION_ONLY skip COM / support (isPathValid way-points)
-template <typename QT, bool MARGINS, bool COLLISION_ONLY, int PAIRS>
+template <typename QT, bool MARGINS, bool COLLISION_ONLY, int PAIRS, bool BIG_SCENE = false>
 __global__ void __launch_bounds__(NT, NWB_MINB)
 validity_kernel(const __grid_constant__ ValidityTables tab, const QT* __restrict__ q, int64_t n,
                 uint8_t* __restrict__ valid, uint8_t* __restrict__ reason, float* __restrict__ margins) {
@@ -96,10 +96,10 @@ validity_kernel(const __grid_constant__ ValidityTables tab, const QT* __restrict
   ValidityResult<float> res;
   if constexpr (PAIRS == PAIRS_TABLE) {
     SmemStore st{smem + tid};
-    res = evaluate_config<float, SmemStore, MARGINS, COLLISION_ONLY, PAIRS>(tab, qv, st, &min_sep, &hull_margin);
+    res = evaluate_config<float, SmemStore, MARGINS, COLLISION_ONLY, PAIRS, false, BIG_SCENE>(tab, qv, st, &min_sep, &hull_margin);
   } else {
     RegStore st;
-    res = evaluate_config<float, RegStore, MARGINS, COLLISION_ONLY, PAIRS>(tab, qv, st, &min_sep, &hull_margin);
+    res = evaluate_config<float, RegStore, MARGINS, COLLISION_ONLY, PAIRS, false, BIG_SCENE>(tab, qv, st, &min_sep, &hull_margin);
   }
 
   if (i < n) {
@@ -354,10 +354,10 @@ static cudaError_t launch_persistent(const ValidityTables& tab, const GatherPeer
   return cudaGetLastError();
 }
 
-template <typename QT, bool MARGINS, bool COLLISION_ONLY, int PAIRS>
+template <typename QT, bool MARGINS, bool COLLISION_ONLY, int PAIRS, bool BIG_SCENE = false>
 static cudaError_t launch_one(const ValidityTables& tab, const void* q, int64_t n, uint8_t* valid, uint8_t* reason,
                               float* margins, cudaStream_t stream) {
-  auto kern = validity_kernel<QT, MARGINS, COLLISION_ONLY, PAIRS>;
+  auto kern = validity_kernel<QT, MARGINS, COLLISION_ONLY, PAIRS, BIG_SCENE>;
   static std::atomic<bool> configured[kMaxDevices];   // per instantiation and device
   const size_t smem = (PAIRS == PAIRS_TABLE ? kSmemFloats : NT * NWB_NJ) * sizeof(float);
   const int dev = current_device();
@@ -379,6 +379,14 @@ static cudaError_t launch_qt(const ValidityTables& tab, const void* q, int64_t n
   if (static_pairs && !margins && getenv("NWB_PACKED"))
     return launch_packed<QT, COLLISION_ONLY, kStatic>(tab, q, n, valid, reason, stream);
 #endif
+  if (tab.scene.n_nodes > 0) {                  // scene of more than kMaxBoxes boxes: the instantiations that walk the hierarchy
+    if (gp.n > 0) return cudaErrorNotSupported; // the fused gather lives in the persistent kernel only
+    if (static_pairs)
+      return margins ? launch_one<QT, true, COLLISION_ONLY, kStatic, true>(tab, q, n, valid, reason, margins, stream)
+                     : launch_one<QT, false, COLLISION_ONLY, kStatic, true>(tab, q, n, valid, reason, margins, stream);
+    return margins ? launch_one<QT, true, COLLISION_ONLY, PAIRS_TABLE, true>(tab, q, n, valid, reason, margins, stream)
+                   : launch_one<QT, false, COLLISION_ONLY, PAIRS_TABLE, true>(tab, q, n, valid, reason, margins, stream);
+  }
   // TMA bulk copies need 16-byte aligned sources; every tile offset is a multiple of 16 bytes
   if (static_pairs && (reinterpret_cast<uintptr_t>(q) & 15) == 0 && !getenv("NWB_NO_PERSISTENT"))
     return margins ? launch_persistent<QT, true, COLLISION_ONLY, kStatic>(tab, gp, q, n, valid, reason, margins, stream)

@@ -7,6 +7,8 @@
 // a flop-counting scalar to freeze the algorithmic flops per configuration used by the roofline
 // (profiles/roofline.json).
 #pragma once
+#include <type_traits>
+
 #include "nwb_internal.h"
 #include "nwb_math.cuh"
 
@@ -123,7 +125,7 @@ enum PairMode { PAIRS_TABLE = 0, PAIRS_STATIC_GROUP = 1, PAIRS_STATIC_ALL = 2 };
 // lanes of a warp are coherent (one lane of a planner kernel, consecutive way-points of an edge) and costs
 // time on batches of unrelated configurations, whose warps almost never agree - the batched validity
 // kernels instantiate it off.
-template <class T, class Store, bool MARGINS, bool COLLISION_ONLY, int PAIRS = PAIRS_TABLE, bool ENV_CULL = false>
+template <class T, class Store, bool MARGINS, bool COLLISION_ONLY, int PAIRS = PAIRS_TABLE, bool ENV_CULL = false, bool BIG_SCENE = false>
 NWB_HD ValidityResult<T> evaluate_config(const ValidityTables& tab, const T* q, Store& st, T* min_sep_out, T* hull_out) {
   using M = typename mask_of<T>::type;
   ValidityVisitor<T, Store, !COLLISION_ONLY> V(st);
@@ -260,8 +262,8 @@ NWB_HD ValidityResult<T> evaluate_config(const ValidityTables& tab, const T* q, 
   }
 
   // ---- environment: robot proxies against the scene boxes ---------------------------------------
-  for (int b = 0; b < tab.n_boxes; ++b) {
-    const SceneBox& bx = tab.boxes[b];
+  // One box against every tested link: exact capsule-box / sphere-box distance.
+  auto test_box = [&](const SceneBox& bx) {
     const T H[3] = {T(bx.h[0]), T(bx.h[1]), T(bx.h[2])};
     auto env_link = [&](int off, bool is_sphere, T radius, float half_len) {
       T pa[3], A[3];
@@ -314,6 +316,59 @@ NWB_HD ValidityResult<T> evaluate_config(const ValidityTables& tab, const T* q, 
       if constexpr (PAIRS == PAIRS_STATIC_GROUP) { NWB_ENV_LINKS_GROUP(NWB_X_ENV) }
       else { NWB_ENV_LINKS_ALL(NWB_X_ENV) }
 #undef NWB_X_ENV
+    }
+  };
+  // inline boxes of the kernel parameters (scenes of <= kMaxBoxes boxes)
+  for (int b = 0; b < tab.n_boxes; ++b) test_box(tab.boxes[b]);
+  // Larger scenes (BIG_SCENE instantiations, float only): boxes in global memory under a flattened bounding-volume
+  // hierarchy.  The walk visits the leaves whose bounds the robot's own bounding box (all tested proxies, radii
+  // included) reaches and runs the SAME exact test on them, so the hierarchy never changes a verdict - it only skips
+  // boxes that are clear of the whole robot.  MARGINS: a subtree is also entered while it could still lower the minimum
+  // separation (branch and bound), so the reported minimum stays exact.
+  if constexpr (BIG_SCENE && std::is_same<T, float>::value) {
+    if (tab.scene.n_nodes > 0) {
+      float rlo[3] = {1e30f, 1e30f, 1e30f}, rhi[3] = {-1e30f, -1e30f, -1e30f};
+      auto grow = [&](int off, bool is_sphere, float radius) {
+        const float rr = radius + 1.0e-4f;                              // slack for the fp32 evaluation of the exact test
+        float p[3];
+        load3(st, off, p);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { rlo[k] = fminf(rlo[k], p[k] - rr); rhi[k] = fmaxf(rhi[k], p[k] + rr); }
+        if (!is_sphere) {
+          load3(st, off + 3, p);
+#pragma unroll
+          for (int k = 0; k < 3; ++k) { rlo[k] = fminf(rlo[k], p[k] - rr); rhi[k] = fmaxf(rhi[k], p[k] + rr); }
+        }
+      };
+      if constexpr (PAIRS == PAIRS_TABLE) {
+        for (int l = 0; l < tab.n_env_links; ++l) grow(tab.env_links[l].off, tab.env_links[l].is_sphere != 0, tab.env_links[l].radius);
+      } else {
+#define NWB_X_GROW(SLOT, SPHERE, R, HALF) grow(SLOT, SPHERE, R);
+        if constexpr (PAIRS == PAIRS_STATIC_GROUP) { NWB_ENV_LINKS_GROUP(NWB_X_GROW) }
+        else { NWB_ENV_LINKS_ALL(NWB_X_GROW) }
+#undef NWB_X_GROW
+      }
+      int node = 0;
+      while (node < tab.scene.n_nodes) {
+        if constexpr (!MARGINS) {
+          if (hit) break;                                               // verdict settled: the rest of the scene cannot change it
+        }
+        const SceneNode nd = tab.scene.nodes[node];
+        float g2 = 0.f;                                                 // squared gap between the two bounding boxes
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const float g = fmaxf(0.f, fmaxf(nd.lo[k] - rhi[k], rlo[k] - nd.hi[k]));
+          g2 = fmaf(g, g, g2);
+        }
+        bool visit = g2 <= 0.f;
+        if constexpr (MARGINS) visit = visit || (min_sep > 0.f && g2 < min_sep * min_sep);
+        if (!visit) { node = nd.skip; continue; }
+        ++node;
+        if (nd.box >= 0) {
+          const SceneBox bx = tab.scene.boxes[nd.box];
+          test_box(bx);
+        }
+      }
     }
   }
   if constexpr (MARGINS) {

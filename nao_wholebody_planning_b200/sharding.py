@@ -81,3 +81,74 @@ def nn_reduce(dist_local, index_local_global, group=None):
     best_i = cand.min(dim=0).values
     best_i = torch.where(best_i == big, torch.full_like(best_i, -1), best_i)
     return dmin, best_i.to(index_local_global.dtype)
+
+
+def pack_trajectories(trajectories):
+    """Per-request results -> one packed buffer: (rows [sum n_k, 21] float64, lengths [len] int64).  A request
+    without a trajectory contributes length 0."""
+    import numpy as np
+    lengths = np.array([0 if t is None else len(t) for t in trajectories], dtype=np.int64)
+    rows = (np.concatenate([np.asarray(t, dtype=np.float64).reshape(-1, 21) for t in trajectories if t is not None and len(t)])
+            if lengths.sum() else np.zeros((0, 21)))
+    return rows, lengths
+
+
+def gather_round_robin_trajectories(rows_local, lengths_local, meta_local, n_total, group=None):
+    """Planning requests sharded with round_robin(n_total): every rank contributes ONE packed row buffer, its
+    per-request lengths and a small per-request int64 record (success flag, node count ...); two ragged
+    all_gathers of numbers replace the pickled-object gather.  Returns, in request order, (rows [sum, 21],
+    offsets [n_total + 1], meta [n_total, m]) on every rank."""
+    world = dist.get_world_size(group)
+    rows_all, row_counts = all_gather_ragged(rows_local, group)
+    rec_local = torch.cat([lengths_local.reshape(-1, 1), meta_local.reshape(len(lengths_local), -1)], dim=1)
+    rec_all, req_counts = all_gather_ragged(rec_local, group)
+    m = rec_all.shape[1] - 1
+    lengths = torch.zeros(n_total, dtype=torch.int64, device=rows_all.device)
+    meta = torch.zeros((n_total, m), dtype=torch.int64, device=rows_all.device)
+    src_start = torch.zeros(n_total, dtype=torch.int64, device=rows_all.device)
+    row_base, req_base = 0, 0
+    for r in range(world):
+        owned = torch.arange(r, n_total, world, device=rows_all.device)            # round_robin(n_total, r, world)
+        assert len(owned) == req_counts[r], (r, len(owned), req_counts[r])
+        rec = rec_all[req_base:req_base + req_counts[r]]
+        lengths[owned] = rec[:, 0]
+        meta[owned] = rec[:, 1:]
+        src_start[owned] = row_base + torch.cumsum(rec[:, 0], 0) - rec[:, 0]
+        row_base += row_counts[r]
+        req_base += req_counts[r]
+    offsets = torch.zeros(n_total + 1, dtype=torch.int64, device=rows_all.device)
+    offsets[1:] = torch.cumsum(lengths, 0)
+    # permute the rows into request order with one gather
+    total = int(offsets[-1].item())
+    if total:
+        req_of_row = torch.repeat_interleave(torch.arange(n_total, device=rows_all.device), lengths)
+        within = torch.arange(total, device=rows_all.device) - offsets[:-1][req_of_row]
+        rows = rows_all[src_start[req_of_row] + within]
+    else:
+        rows = rows_all[:0]
+    return rows, offsets, meta
+
+
+def bind_to_gpu_numa_node(pci_bus_id):
+    """Pin this process (and therefore its later page allocations: Linux places pages on the node of the allocating
+    CPU) to the CPUs of the NUMA node the GPU hangs off, so that pinned staging buffers are NUMA-local to the GPU's
+    PCIe root.  Returns (node, n_cpus) or None when the topology is not exposed.  Call BEFORE allocating pinned memory."""
+    import os
+    try:
+        dom = pci_bus_id.lower()
+        if len(dom.split(":")[0]) == 8:                       # CUDA prints an 8-digit domain, sysfs uses 4
+            dom = dom[4:]
+        node = int(open(f"/sys/bus/pci/devices/{dom}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node, len(cpus)
+    except (OSError, ValueError):
+        return None

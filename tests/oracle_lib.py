@@ -452,4 +452,36 @@ def scene_boxes(name):
         return np.array([[0.35, 0.06, 0.32, 0.3, 0.6, 0.03] + eye], dtype=np.float64)
     if name == "S3":   # drawer + beam (PAR:465-472)
         return np.array([[0.15, -0.08, 0.125, 0.06, 0.08, 0.25] + eye, [0.39, -0.15, 0.25, 0.16, 0.17, 0.5] + eye])
+    if name == "S4":   # pole (initScene.cpp:175-176)
+        return np.array([[0.15, -0.17, 0.02, 0.02, 1.0, 0.02] + eye], dtype=np.float64)
+    if name == "S5":   # bottle table (PAR:484-485)
+        return np.array([[0.34, 0.18, 0.21, 0.3, 0.4, 0.1] + eye], dtype=np.float64)
+    if name == "ALL":  # every object the reference's scene builders ever insert, at once (21 boxes > the 16 inline slots):
+        shelf30 = scene_boxes("S1").copy()                 # the shelf at both shelf_x values (0.33 in the examples, 0.30 in initScene.cpp:120)
+        shelf30[:, 0] -= 0.03
+        tables = np.array([[0.32, 0.05, 0.333, 0.3, 0.3, 0.03] + eye, [0.35, 0.06, 0.35, 0.3, 0.6, 0.03] + eye])   # initScene.cpp:572-573, nao_rrt_planner.cpp:158-159
+        return np.concatenate([scene_boxes("S1"), shelf30, scene_boxes("S2"), tables, scene_boxes("S3"), scene_boxes("S4"), scene_boxes("S5")])
     raise KeyError(name)
+
+
+def generated_scene(n, seed=20121006, keep_out=0.22):
+    """n oriented boxes scattered through the robot's workspace (r_sole frame): centres uniform in
+    [-0.6, 0.8] x [-0.7, 0.7] x [0, 1.0] m outside a vertical keep-out cylinder of radius `keep_out` around the stance
+    (so that part of the configurations stays collision-free), full extents 2-12 cm, every second box rotated."""
+    rng = np.random.default_rng(seed)
+    out = []
+    while len(out) < n:
+        c = np.array([rng.uniform(-0.6, 0.8), rng.uniform(-0.7, 0.7), rng.uniform(0.0, 1.0)])
+        size = rng.uniform(0.02, 0.12, 3)
+        if np.hypot(c[0] - 0.02, c[1] - 0.05) < keep_out + 0.5 * np.linalg.norm(size):
+            continue
+        if len(out) % 2:
+            ax = rng.normal(size=3)
+            ax /= np.linalg.norm(ax)
+            ang = rng.uniform(-np.pi, np.pi)
+            K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+            R = np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * K @ K
+        else:
+            R = np.eye(3)
+        out.append(np.concatenate([c, size, R.reshape(9)]))
+    return np.array(out)

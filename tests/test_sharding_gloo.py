@@ -81,6 +81,20 @@ def _worker(rank, world, port, tmp):
         assert (rows == r_ref).all() and (idx == i_ref).all() and drawn == d_ref
     assert len(merged[2][1][0]) == 0                      # the unreachable pose finds no goal configuration
 
+    # 4b. the same requests' trajectories as ONE packed buffer per rank (no pickled objects): request order restored
+    n_req = 7
+    trajs = {k: (np.full((k % 3 + (k != 4), 21), float(k)) if k != 4 else None) for k in range(n_req)}   # request 4: no plan
+    mine = sharding.round_robin(n_req)
+    rows_l, len_l = sharding.pack_trajectories([trajs[k] for k in mine])
+    meta_l = np.array([[int(trajs[k] is not None), 100 + k] for k in mine], dtype=np.int64).reshape(-1, 2)
+    rows, offsets, meta = sharding.gather_round_robin_trajectories(torch.from_numpy(rows_l), torch.from_numpy(len_l),
+                                                                   torch.from_numpy(meta_l), n_req)
+    assert offsets.tolist() == np.concatenate([[0], np.cumsum([0 if trajs[k] is None else len(trajs[k]) for k in range(n_req)])]).tolist()
+    for k in range(n_req):
+        seg = rows[offsets[k]:offsets[k + 1]].numpy()
+        assert (len(seg) == 0 and (trajs[k] is None or len(trajs[k]) == 0)) or (seg == trajs[k]).all()
+        assert meta[k].tolist() == [int(trajs[k] is not None), 100 + k]
+
     # 5. ragged gather with an empty rank
     local = torch.arange(5 if rank == 0 else 0, dtype=torch.float64).reshape(-1, 1)
     out, counts = sharding.all_gather_ragged(local)
