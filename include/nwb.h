@@ -205,6 +205,9 @@ NWB_API int nwb_nearest_neighbour_batch_dev(nwb_tree* tree, const double* q_dev,
 /* Diagnostic for the tests: an id of the scan thread that evaluates `node` when nq queries are passed (nodes with
  * equal ids are evaluated one after the other by the same thread, in index order).  No reference counterpart. */
 NWB_API int64_t nwb_nn_scan_owner(const nwb_tree* tree, int64_t nq, int64_t node);
+/* Diagnostic for the tests: the raw tensor-core accumulator of the batched scan for the first 128 nodes,
+ * tile_out [128 queries][128 nodes] = |n|^2 - 2 q.n evaluated on bf16 hi/mid splits (rows >= nq are padding). */
+NWB_API int nwb_nn_debug_tensor_tile(nwb_tree* tree, const double* q, int64_t nq, float* tile_out);
 
 /* ---- local planner operators ---------------------------------------------------------------------
  * weights: the 21 joint weights of RRT_Planner::setJointWeights (RP:307-311), NULL = all 1.0 (RP:76-78).

@@ -199,6 +199,7 @@ def _declare(lib):
         "nwb_nearest_neighbour_batch": (C.c_int, [vp, vp, i64, vp, vp]),
         "nwb_nearest_neighbour_batch_dev": (C.c_int, [vp, vp, i64, vp, vp]),
         "nwb_nn_scan_owner": (C.c_int64, [vp, i64, i64]),
+        "nwb_nn_debug_tensor_tile": (C.c_int, [vp, vp, i64, vp]),
         "nwb_steer_project_batch": (C.c_int, [vp, vp, vp, i64, vp, dbl, vp, vp, vp]),
         "nwb_steer_project_batch_dev": (C.c_int, [vp, vp, vp, i64, vp, dbl, vp, vp, vp]),
         "nwb_connect_batch": (C.c_int, [vp, vp, vp, i64, vp, dbl, i32, vp, vp, vp]),

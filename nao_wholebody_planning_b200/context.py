@@ -499,6 +499,13 @@ class Tree:
         """Diagnostic: id of the scan thread that evaluates `node` for a call with nq queries."""
         return int(self.lib.nwb_nn_scan_owner(self.h, nq, node))
 
+    def debug_tensor_tile(self, q):
+        """Diagnostic: raw tcgen05 accumulator [128 queries][128 nodes] of the first node tile."""
+        q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, NJ)
+        out = np.zeros((128, 128), np.float32)
+        self.ctx._check(self.lib.nwb_nn_debug_tensor_tile(self.h, _p(q), len(q), _p(out)), "nwb_nn_debug_tensor_tile")
+        return out
+
     def nearest_dev(self, q_dev, nq, idx_dev, dist_dev=None):
         self.ctx._check(self.lib.nwb_nearest_neighbour_batch_dev(self.h, q_dev, nq, idx_dev, dist_dev),
                         "nwb_nearest_neighbour_batch_dev")

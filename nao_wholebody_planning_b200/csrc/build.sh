@@ -6,7 +6,7 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 OUT=../libnwb.so
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -pthread -Xcompiler -fvisibility=hidden
        --expt-relaxed-constexpr -cudart static -Xptxas -v -DNWB_FAST_SINCOS ${NWB_EXTRA_FLAGS:-})
-SRCS=(validity.cu nwb_abi.cu tree.cu planner_kernels.cu planner_abi.cu rrt_driver.cu arm_kernels.cu service_abi.cu)
+SRCS=(validity.cu nwb_abi.cu tree.cu nn_tensor.cu planner_kernels.cu planner_abi.cu rrt_driver.cu arm_kernels.cu service_abi.cu)
 OBJS=()
 PIDS=()
 NAMES=()

@@ -1,0 +1,431 @@
+// nn_tensor.cu - batched nearest neighbour on the 5th-generation tensor cores (tcgen05 / TMEM) for sm_100a.
+//
+// RRT_Planner::findNearestNeighbour (rrt_connect_planner/src/rrt_planner.cpp:336-419) for MANY queries against one
+// tree is a contraction: |q - n|^2 = |q|^2 + |n|^2 - 2 q.n, i.e. a (Q x 21) . (21 x N) product plus norms.  The
+// CUDA-core scan of tree.cu does that on the FP32 pipe (14.5 TFLOP/s of contraction at 1024 x 10^6); here the product
+// runs as tcgen05.mma with the accumulator in tensor memory:
+//
+//   * operands are bf16, and a bf16 product alone would be far too coarse, so every value x is split x = hi + mid
+//     (bf16 each, 16 significant bits together) and the three leading cross terms q_hi n_hi + q_hi n_mid + q_mid n_hi
+//     are laid side by side along K (63 slots); three more slots carry |n|^2 (split in three bf16 pieces) against 1.0,
+//     and the query side is pre-scaled by -2, so ONE accumulator element is v = |n|^2 - 2 q.n up to a bounded error E
+//     (the |q|^2 term is constant per query and irrelevant for the argmin).  K = 80 (5 MMA steps of 16).
+//   * A = 128 queries (one TMEM lane each), B = tiles of 128 nodes streamed with 1-D bulk copies (UBLKCP) through a
+//     shared-memory ring; the node copy is stored in HBM already in the tcgen05 K-major core-matrix order
+//     (tree_internal.h), so no tensor map and no swizzle are needed.  D = 128 x 128 fp32, double-buffered in TMEM: the
+//     MMA of tile t+1 runs while the four warps read tile t back with tcgen05.ld.
+//   * The epilogue is a filter, not the answer: every thread owns one query, keeps its running minimum of v and lists
+//     the nodes within 2E of it.  Only those candidates are re-evaluated in fp64 with the reference's exact rounding
+//     sequence (separately rounded multiply/add, sqrt, strict <, lowest index on ties), so the result is bit-identical
+//     to the CUDA-core scan and to the oracle.  A tile whose candidates overflow the list is evaluated exactly, pair by
+//     pair, by the CTA itself - no CPU path, no approximation.
+//
+// Grid: (node slices, query groups).  Partials (dist, idx) per (query, slice) are folded by the last CTA of a group.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+
+#include "tree_internal.h"
+
+namespace nwb {
+
+constexpr int TC_THREADS = 128;
+constexpr int TC_STAGES = 6;
+constexpr int TC_CAND = 2048;
+
+__device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tc_mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void tc_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "TCWAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra TCDONE_%=;\n"
+      "bra TCWAIT_%=;\n"
+      "TCDONE_%=:\n"
+      "}\n" ::"r"(tc_smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tc_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tc_smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(tc_smem_u32(bar))
+               : "memory");
+}
+// shared-memory matrix descriptor, K-major, no swizzle: 8-row x 16-byte core matrices; LBO = distance between the two
+// 16-byte K chunks of one MMA step, SBO = distance between 8-row groups (both in 16-byte units), descriptor version 1
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(128u >> 4) << 16) | ((uint64_t)((TC_KB * 128u) >> 4) << 32) |
+         (1ull << 46);
+}
+// instruction descriptor, kind::f16: D = F32, A = B = BF16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+constexpr uint32_t kTcInstrDesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kTcInstrDesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// 32 lanes x 32 consecutive columns: thread i of the warp receives row (lane base + i)
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Error bound of one accumulator element against the true |n|^2 - 2 q.n: dropped cross terms of the
+// bf16 split (3.1 * 2^-18 per product, doubled by the -2) + 66 accumulation steps of at most 2^-22 of the running
+// magnitude each (twice the fp32 unit round-off: the tensor core may truncate) + 25 % slack.
+__device__ __forceinline__ float tc_error_bound(float qnorm, float nmax) {
+  const float qn = qnorm * nmax;
+  return 1.25f * (2.4e-5f * qn + 1.6e-5f * (fmaf(nmax, nmax, 2.02f * qn)) + 1e-7f);
+}
+
+struct TcSmem {
+  static constexpr size_t kA = 0;
+  static constexpr size_t kB = kA + TC_TILE_BYTES;
+  static constexpr size_t kQd = kB + (size_t)TC_STAGES * TC_TILE_BYTES;               // double [128][21]
+  static constexpr size_t kCandD = kQd + sizeof(double) * TC_M * NWB_NJ;              // double [TC_CAND]
+  static constexpr size_t kBestKey = kCandD + sizeof(double) * TC_CAND;               // u64 [128]
+  static constexpr size_t kOldKey = kBestKey + 8 * TC_M;                              // u64 [128]
+  static constexpr size_t kBars = kOldKey + 8 * TC_M;                                 // u64 [TC_STAGES + 2]
+  static constexpr size_t kCandNode = kBars + 8 * (TC_STAGES + 2);                    // int [TC_CAND]
+  static constexpr size_t kCandQ = kCandNode + 4 * TC_CAND;                           // int [TC_CAND]
+  static constexpr size_t kCandV = kCandQ + 4 * TC_CAND;                              // float [TC_CAND]
+  static constexpr size_t kMPub = kCandV + 4 * TC_CAND;                               // float [128]
+  static constexpr size_t kE2 = kMPub + 4 * TC_M;                                     // float [128]
+  static constexpr size_t kBestIdx = kE2 + 4 * TC_M;                                  // int [128]
+  static constexpr size_t kIdxTmp = kBestIdx + 4 * TC_M;                              // int [128]
+  static constexpr size_t kMisc = kIdxTmp + 4 * TC_M;                                 // int [8]: cand_n, tmem base, last flag
+  static constexpr size_t kBytes = kMisc + 32;
+};
+
+__device__ __forceinline__ double tc_exact_dist(const double* __restrict__ aos, const double* qrow, int64_t node) {
+  const double* row = aos + node * NWB_NJ;
+  double r[NWB_NJ];
+#pragma unroll
+  for (int j = 0; j < NWB_NJ; ++j) r[j] = row[j];
+  double sum = 0.0;
+#pragma unroll
+  for (int j = 0; j < NWB_NJ; ++j) {
+    const double d = __dsub_rn(qrow[j], r[j]);
+    sum = __dadd_rn(sum, __dmul_rn(d, d));               // separately rounded multiply and add (RP:361-366)
+  }
+  return sqrt(sum);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+nn_tc_kernel(const unsigned char* __restrict__ tc, const double* __restrict__ aos, const unsigned* __restrict__ max_nn_bits,
+             int64_t N, const double* __restrict__ q, int64_t nq, double* __restrict__ part_d, int32_t* __restrict__ part_i,
+             unsigned* __restrict__ tickets, int32_t* __restrict__ idx_out, double* __restrict__ dist_out,
+             float* __restrict__ debug_tile) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* a_tile = smem + TcSmem::kA;
+  unsigned char* b_ring = smem + TcSmem::kB;
+  double* qd = reinterpret_cast<double*>(smem + TcSmem::kQd);
+  double* cand_d = reinterpret_cast<double*>(smem + TcSmem::kCandD);
+  unsigned long long* best_key = reinterpret_cast<unsigned long long*>(smem + TcSmem::kBestKey);
+  unsigned long long* old_key = reinterpret_cast<unsigned long long*>(smem + TcSmem::kOldKey);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TcSmem::kBars);        // [0, STAGES): tile landed; [STAGES, +2): MMA done
+  int* cand_node = reinterpret_cast<int*>(smem + TcSmem::kCandNode);
+  int* cand_q = reinterpret_cast<int*>(smem + TcSmem::kCandQ);
+  float* cand_v = reinterpret_cast<float*>(smem + TcSmem::kCandV);
+  float* m_pub = reinterpret_cast<float*>(smem + TcSmem::kMPub);
+  float* e2s = reinterpret_cast<float*>(smem + TcSmem::kE2);
+  int* best_idx = reinterpret_cast<int*>(smem + TcSmem::kBestIdx);
+  int* idx_tmp = reinterpret_cast<int*>(smem + TcSmem::kIdxTmp);
+  int* misc = reinterpret_cast<int*>(smem + TcSmem::kMisc);
+  int& cand_n = misc[0];
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&misc[1]);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int slice = blockIdx.x, n_slices = gridDim.x;
+  const int64_t q0 = (int64_t)blockIdx.y * TC_M;
+  const bool q_live = q0 + tid < nq;
+
+  // ---- set-up: barriers, tensor memory, the query tile ---------------------------------------------------------
+  if (tid == 0) {
+    for (int b = 0; b < TC_STAGES; ++b) tc_mbar_init(&bars[b], 1);
+    tc_mbar_init(&bars[TC_STAGES], 1);
+    tc_mbar_init(&bars[TC_STAGES + 1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    cand_n = 0;
+  }
+  if (warp == 0) {                                           // 2 accumulators x 128 columns
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // node tiles of this slice: contiguous range
+  const int64_t tiles_total = (N + TC_N - 1) / TC_N;
+  const int64_t per = (tiles_total + n_slices - 1) / n_slices;
+  const int64_t tile_lo = min(tiles_total, (int64_t)slice * per), tile_hi = min(tiles_total, tile_lo + per);
+  const int T = (int)(tile_hi - tile_lo);
+  if (tid == 0) {                                            // start the node stream before anything else needs it
+    for (int s = 0; s < TC_STAGES && s < T; ++s) {
+      tc_mbar_expect_tx(&bars[s], TC_TILE_BYTES);
+      tc_bulk_g2s(b_ring + (size_t)s * TC_TILE_BYTES, tc + (size_t)(tile_lo + s) * TC_TILE_BYTES, TC_TILE_BYTES, &bars[s]);
+    }
+  }
+  // query row -> fp64 copy for the exact pass, bf16 split for the MMA (slot map: tree_internal.h)
+  float qnorm2 = 0.f;
+  {
+    __nv_bfloat16 row[TC_K];
+#pragma unroll
+    for (int j = 0; j < NWB_NJ; ++j) {
+      const double xd = q_live ? q[(q0 + tid) * NWB_NJ + j] : 0.0;
+      qd[tid * NWB_NJ + j] = xd;
+      const float x = (float)xd;
+      qnorm2 = fmaf(x, x, qnorm2);
+      const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+      const __nv_bfloat16 mid = __float2bfloat16_rn(x - __bfloat162float(hi));
+      const __nv_bfloat16 hi2 = __float2bfloat16_rn(-2.f * __bfloat162float(hi));      // exact: power of two
+      const __nv_bfloat16 mid2 = __float2bfloat16_rn(-2.f * __bfloat162float(mid));
+      row[j] = hi2;
+      row[NWB_NJ + j] = hi2;
+      row[2 * NWB_NJ + j] = mid2;
+    }
+    row[63] = row[64] = row[65] = __float2bfloat16_rn(q_live ? 1.f : 0.f);
+#pragma unroll
+    for (int k = 66; k < TC_K; ++k) row[k] = __float2bfloat16_rn(0.f);
+    unsigned char* base = a_tile + (size_t)(tid >> 3) * (TC_KB * 128) + (size_t)(tid & 7) * 16;
+#pragma unroll
+    for (int kb = 0; kb < TC_KB; ++kb) *reinterpret_cast<uint4*>(base + kb * 128) = *reinterpret_cast<const uint4*>(&row[kb * 8]);
+  }
+  const float nmax = sqrtf(__uint_as_float(*max_nn_bits));
+  const float e2 = 2.f * tc_error_bound(sqrtf(qnorm2) * (1.f + 1e-6f), nmax);
+  e2s[tid] = e2;
+  best_key[tid] = 0x7FF0000000000000ull;                     // +inf
+  best_idx[tid] = -1;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the query tile is read by the tensor core (async proxy)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t a_addr = tc_smem_u32(a_tile);
+
+  auto mma_issue = [&](int t) {                              // thread 0: D[t % 2] = A . B(tile t)^T
+    const int stage = t % TC_STAGES;
+    tc_mbar_wait(&bars[stage], (uint32_t)((t / TC_STAGES) & 1));
+    tc_fence_after();
+    const uint32_t b_addr = tc_smem_u32(b_ring + (size_t)stage * TC_TILE_BYTES);
+    const uint32_t d_addr = tmem_base + (uint32_t)((t & 1) * TC_N);
+#pragma unroll
+    for (int ks = 0; ks < TC_K / 16; ++ks)                    // one step = 16 slots = two 16-byte chunks = 256 B further
+      tc_mma(d_addr, tc_smem_desc(a_addr + ks * 256), tc_smem_desc(b_addr + ks * 256), ks > 0 ? 1u : 0u);
+    tc_commit(&bars[TC_STAGES + (t & 1)]);
+  };
+
+  float m_run = 3.0e38f;
+  if (tid == 0 && T > 0) mma_issue(0);
+
+  // exact fp64 evaluation of the listed candidates that are still under their query's bound, folded into
+  // (best_key, best_idx) per query: lexicographic (distance, index)
+  auto flush = [&]() {
+    const int n_c = min(cand_n, TC_CAND);
+    old_key[tid] = best_key[tid];
+    idx_tmp[tid] = 0x7FFFFFFF;
+    __syncthreads();
+    for (int c = tid; c < n_c; c += TC_THREADS) {
+      const int ql = cand_q[c];
+      double d = __longlong_as_double(0x7FF0000000000000ll);
+      if (cand_v[c] <= m_pub[ql] + e2s[ql]) {
+        d = tc_exact_dist(aos, qd + ql * NWB_NJ, cand_node[c]);
+        atomicMin(&best_key[ql], (unsigned long long)__double_as_longlong(d));     // d >= 0: bit order = value order
+      }
+      cand_d[c] = d;
+    }
+    __syncthreads();
+    for (int c = tid; c < n_c; c += TC_THREADS) {
+      const int ql = cand_q[c];
+      if ((unsigned long long)__double_as_longlong(cand_d[c]) == best_key[ql]) atomicMin(&idx_tmp[ql], cand_node[c]);
+    }
+    __syncthreads();
+    if (best_key[tid] < old_key[tid]) best_idx[tid] = idx_tmp[tid];
+    else if (idx_tmp[tid] != 0x7FFFFFFF && (best_idx[tid] < 0 || idx_tmp[tid] < best_idx[tid])) best_idx[tid] = idx_tmp[tid];
+    if (tid == 0) cand_n = 0;
+    __syncthreads();
+  };
+
+  for (int t = 0; t < T; ++t) {
+    if (tid == 0 && t + 1 < T) mma_issue(t + 1);            // runs on the tensor core while tile t is read back
+    tc_mbar_wait(&bars[TC_STAGES + (t & 1)], (uint32_t)((t >> 1) & 1));
+    tc_fence_after();
+    const int64_t n0 = (tile_lo + t) * TC_N;
+    const bool full_tile = n0 + TC_N <= N;
+    bool want_flush = false, overflow = false;
+    if (debug_tile && slice == 0 && blockIdx.y == 0 && t == 0) {      // diagnostics: raw accumulator of the first tile
+      for (int c = 0; c < TC_N / 32; ++c) {
+        float v[32];
+        tc_ld32(tmem_base + (uint32_t)((t & 1) * TC_N + c * 32) + ((uint32_t)(warp * 32) << 16), v);
+#pragma unroll
+        for (int u = 0; u < 32; ++u) debug_tile[tid * TC_N + c * 32 + u] = v[u];
+      }
+    }
+#pragma unroll 1
+    for (int c = 0; c < TC_N / 32; ++c) {
+      float v[32];
+      tc_ld32(tmem_base + (uint32_t)((t & 1) * TC_N + c * 32) + ((uint32_t)(warp * 32) << 16), v);
+      float cm = v[0];
+#pragma unroll
+      for (int u = 1; u < 32; ++u) cm = fminf(cm, v[u]);
+      if (cm <= m_run + e2) {                                 // rare: a new running minimum or a near tie in this chunk
+#pragma unroll
+        for (int u = 0; u < 32; ++u) {
+          const int64_t node = n0 + c * 32 + u;
+          if (full_tile || node < N) {
+            const float x = v[u];
+            if (x < m_run) m_run = x;
+            if (x <= m_run + e2 && q_live) {
+              const int slot = atomicAdd(&cand_n, 1);
+              if (slot < TC_CAND) {
+                cand_node[slot] = (int)node;
+                cand_q[slot] = tid;
+                cand_v[slot] = x;
+              } else {
+                overflow = true;
+              }
+              want_flush = want_flush || slot >= TC_CAND / 2;
+            }
+          }
+        }
+      }
+      __syncwarp();
+    }
+    m_pub[tid] = m_run;
+    tc_fence_before();
+    const int act = __syncthreads_or((want_flush ? 1 : 0) | (overflow ? 2 : 0));
+    if (tid == 0 && t + TC_STAGES < T) {                     // the MMA of tile t is complete: its stage is free again
+      const int stage = t % TC_STAGES;
+      tc_mbar_expect_tx(&bars[stage], TC_TILE_BYTES);
+      tc_bulk_g2s(b_ring + (size_t)stage * TC_TILE_BYTES, tc + (size_t)(tile_lo + t + TC_STAGES) * TC_TILE_BYTES, TC_TILE_BYTES,
+                  &bars[stage]);
+    }
+    if (act & 2) {
+      // the list could not hold this tile's candidates: evaluate the whole tile exactly for the own query
+      if (q_live) {
+        unsigned long long bk = best_key[tid];
+        int bi = best_idx[tid];
+        for (int u = 0; u < TC_N; ++u) {
+          const int64_t node = n0 + u;
+          if (node >= N) break;
+          const unsigned long long k = (unsigned long long)__double_as_longlong(tc_exact_dist(aos, qd + tid * NWB_NJ, node));
+          if (k < bk || (k == bk && (bi < 0 || (int)node < bi))) { bk = k; bi = (int)node; }
+        }
+        best_key[tid] = bk;
+        best_idx[tid] = bi;
+      }
+      __syncthreads();
+    }
+    if (act) flush();
+  }
+  flush();
+
+  // ---- partial of this slice, then the last CTA of the query group folds the slices --------------------------------
+  if (q_live) {
+    part_d[(q0 + tid) * n_slices + slice] = __longlong_as_double((long long)best_key[tid]);
+    part_i[(q0 + tid) * n_slices + slice] = best_idx[tid];
+  }
+  tc_fence_before();
+  __threadfence();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+  }
+  if (tid == 0) misc[2] = atomicAdd(&tickets[blockIdx.y], 1u) == (unsigned)n_slices - 1 ? 1 : 0;
+  __syncthreads();
+  if (!misc[2]) return;
+  __threadfence();
+  if (q_live) {
+    double d = 10000.0;                                       // RP:347: best_norm starts at 10000.0, strict <
+    int i = -1;
+    for (int s = 0; s < n_slices; ++s) {
+      const double ds = part_d[(q0 + tid) * n_slices + s];
+      const int is = part_i[(q0 + tid) * n_slices + s];
+      if (is >= 0 && (ds < d || (ds == d && i >= 0 && is < i))) { d = ds; i = is; }
+    }
+    idx_out[q0 + tid] = i;
+    if (dist_out) dist_out[q0 + tid] = d;
+  }
+  if (tid == 0) tickets[blockIdx.y] = 0u;                    // ready for the next call
+}
+
+}  // namespace nwb
+
+using namespace nwb;
+
+cudaError_t nn_tc_launch(nwb_tree* t, const double* q_dev, int64_t nq, int32_t* idx_dev, double* dist_dev, float* debug_tile,
+                         int* n_launches) {
+  const int64_t groups = (nq + TC_M - 1) / TC_M;
+  const int64_t tiles = (t->size + TC_N - 1) / TC_N;
+  const int sm = std::max(1, t->ctx->sm_count);
+  // one CTA per SM (the shared-memory ring allows no more): slices x groups fills the machine once
+  int64_t slices = std::max<int64_t>(1, sm / std::min<int64_t>(groups, sm));
+  slices = std::max<int64_t>(1, std::min(slices, tiles));
+  const size_t need = (size_t)groups * TC_M * slices;
+  cudaError_t e;
+  if (need > t->part_cap) {
+    if (t->part_d) cudaFree(t->part_d);
+    if (t->part_i) cudaFree(t->part_i);
+    t->part_d = nullptr;
+    t->part_i = nullptr;
+    t->part_cap = 0;
+    if ((e = cudaMalloc(&t->part_d, sizeof(double) * need)) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&t->part_i, sizeof(int32_t) * need)) != cudaSuccess) return e;
+    t->part_cap = need;
+  }
+  cudaStream_t s = t->ctx->stream;
+  if ((size_t)groups > t->ticket_cap) {
+    if (t->tickets) cudaFree(t->tickets);
+    t->tickets = nullptr;
+    t->ticket_cap = 0;
+    const size_t cap = std::max<size_t>((size_t)groups, 1024);
+    if ((e = cudaMalloc(&t->tickets, sizeof(unsigned) * cap)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(t->tickets, 0, sizeof(unsigned) * cap, s)) != cudaSuccess) return e;
+    t->ticket_cap = cap;
+  }
+  static std::atomic<bool> configured[64];
+  const int dev = t->ctx->device >= 0 && t->ctx->device < 64 ? t->ctx->device : 0;
+  if (!configured[dev].load(std::memory_order_relaxed)) {
+    if ((e = cudaFuncSetAttribute(nn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcSmem::kBytes)) != cudaSuccess) return e;
+    configured[dev].store(true, std::memory_order_relaxed);
+  }
+  int launches = 0;
+  for (int64_t g0 = 0; g0 < groups; g0 += 65535) {
+    const int64_t ng = std::min<int64_t>(65535, groups - g0);
+    const int64_t qoff = g0 * TC_M;
+    nn_tc_kernel<<<dim3((unsigned)slices, (unsigned)ng), TC_THREADS, TcSmem::kBytes, s>>>(
+        t->tc, t->aos, t->max_nn, t->size, q_dev + qoff * NWB_NJ, nq - qoff, t->part_d + (size_t)qoff * slices,
+        t->part_i + (size_t)qoff * slices, t->tickets + g0, idx_dev + qoff, dist_dev ? dist_dev + qoff : nullptr, debug_tile);
+    ++launches;
+    debug_tile = nullptr;
+  }
+  if (n_launches) *n_launches = launches;
+  return cudaGetLastError();
+}

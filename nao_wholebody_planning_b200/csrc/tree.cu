@@ -16,6 +16,7 @@
 // minimum re-evaluates the distance exactly as the reference does (double, separately rounded
 // multiply and add, then sqrt, strict <) from the master copy.  Lexicographic (distance, index)
 // reductions (warp shuffle -> block -> last-block-done grid fold, one launch) then reproduce "first strict minimum wins".
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -23,7 +24,7 @@
 #include <cstring>
 #include <new>
 
-#include "nwb_internal.h"
+#include "tree_internal.h"
 
 namespace nwb {
 
@@ -40,6 +41,41 @@ __global__ void tree_append_kernel(const double* __restrict__ src, const int32_t
   aos[(size + i) * NWB_NJ + j] = v;
   soa[(int64_t)j * cap + size + i] = (float)v;
   if (j == 0) pred[size + i] = pred_src ? pred_src[i] : -1;
+}
+
+// Tensor-core scan copy of the appended nodes (layout and slot map: tree_internal.h): one thread per node.
+__global__ void tree_append_tc_kernel(const double* __restrict__ src, int64_t n, unsigned char* __restrict__ tc, int64_t size,
+                                      unsigned* __restrict__ max_nn) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  __nv_bfloat16 row[TC_K];
+  double nn = 0.0;
+#pragma unroll
+  for (int j = 0; j < NWB_NJ; ++j) {
+    const double xd = src[i * NWB_NJ + j];
+    nn = fma(xd, xd, nn);
+    const float x = (float)xd;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+    const __nv_bfloat16 mid = __float2bfloat16_rn(x - __bfloat162float(hi));
+    row[j] = hi;
+    row[NWB_NJ + j] = mid;
+    row[2 * NWB_NJ + j] = hi;
+  }
+  const float nnf = (float)nn;
+  const __nv_bfloat16 n0 = __float2bfloat16_rn(nnf);
+  const float r1 = nnf - __bfloat162float(n0);
+  const __nv_bfloat16 n1 = __float2bfloat16_rn(r1);
+  const __nv_bfloat16 n2 = __float2bfloat16_rn(r1 - __bfloat162float(n1));
+  row[63] = n0;
+  row[64] = n1;
+  row[65] = n2;
+#pragma unroll
+  for (int k = 66; k < TC_K; ++k) row[k] = __float2bfloat16_rn(0.f);
+  unsigned char* base = tc + tc_slot_offset(size + i, 0);
+#pragma unroll
+  for (int kb = 0; kb < TC_KB; ++kb) *reinterpret_cast<uint4*>(base + kb * 128) = *reinterpret_cast<const uint4*>(&row[kb * 8]);
+  // max |node|^2 (non-negative floats order like their bit patterns); rounded up so the bound stays a bound
+  atomicMax(max_nn, __float_as_uint(nnf * (1.0f + 1e-6f)));
 }
 
 __device__ __forceinline__ bool lex_less(double da, int ia, double db, int ib) {
@@ -385,22 +421,6 @@ nn_scan_kernel(const float* __restrict__ soa, const double* __restrict__ aos, in
 
 using namespace nwb;
 
-struct nwb_tree {
-  nwb_ctx* ctx = nullptr;
-  int64_t size = 0, cap = 0;
-  float* soa = nullptr;
-  double* aos = nullptr;
-  int32_t* pred = nullptr;
-  // scratch
-  double* part_d = nullptr;
-  int32_t* part_i = nullptr;
-  size_t part_cap = 0;
-  unsigned* tickets = nullptr;   // one counter per query group (zero between calls)
-  size_t ticket_cap = 0;
-  void* stage = nullptr;      // device staging for host-pointer calls
-  size_t stage_bytes = 0;
-};
-
 namespace {
 #define TREE_CUDA(t, call)                                                           \
   do {                                                                               \
@@ -416,14 +436,24 @@ int tree_reserve(nwb_tree* t, int64_t need) {
   int64_t cap = std::max<int64_t>(1024, t->cap);
   while (cap < need) cap *= 2;
   cap = (cap + 63) & ~(int64_t)63;
+  cap = (cap + TC_N - 1) / TC_N * TC_N;                 // whole tiles of the tensor-core scan copy
   float* soa = nullptr;
   double* aos = nullptr;
   int32_t* pred = nullptr;
+  unsigned char* tc = nullptr;
+  const size_t tc_bytes = (size_t)(cap / TC_N) * TC_TILE_BYTES;
   TREE_CUDA(t, cudaMalloc(&soa, sizeof(float) * NWB_NJ * cap));
   TREE_CUDA(t, cudaMalloc(&aos, sizeof(double) * NWB_NJ * cap));
   TREE_CUDA(t, cudaMalloc(&pred, sizeof(int32_t) * cap));
+  TREE_CUDA(t, cudaMalloc(&tc, tc_bytes));
   cudaStream_t s = t->ctx->stream;
+  TREE_CUDA(t, cudaMemsetAsync(tc, 0, tc_bytes, s));    // rows past the end of the tree hold finite values
+  if (!t->max_nn) {
+    TREE_CUDA(t, cudaMalloc(&t->max_nn, sizeof(unsigned)));
+    TREE_CUDA(t, cudaMemsetAsync(t->max_nn, 0, sizeof(unsigned), s));
+  }
   if (t->size > 0) {
+    TREE_CUDA(t, cudaMemcpyAsync(tc, t->tc, (size_t)((t->size + TC_N - 1) / TC_N) * TC_TILE_BYTES, cudaMemcpyDeviceToDevice, s));
     TREE_CUDA(t, cudaMemcpy2DAsync(soa, sizeof(float) * cap, t->soa, sizeof(float) * t->cap, sizeof(float) * t->size, NWB_NJ,
                                    cudaMemcpyDeviceToDevice, s));
     TREE_CUDA(t, cudaMemcpyAsync(aos, t->aos, sizeof(double) * NWB_NJ * t->size, cudaMemcpyDeviceToDevice, s));
@@ -433,9 +463,11 @@ int tree_reserve(nwb_tree* t, int64_t need) {
   cudaFree(t->soa);
   cudaFree(t->aos);
   cudaFree(t->pred);
+  cudaFree(t->tc);
   t->soa = soa;
   t->aos = aos;
   t->pred = pred;
+  t->tc = tc;
   t->cap = cap;
   return NWB_OK;
 }
@@ -490,6 +522,19 @@ int nn_launch(nwb_tree* t, const double* q_dev, int64_t nq, int32_t* idx_dev, do
     TREE_CUDA(t, cudaFuncSetAttribute(nn_scan_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNnSmem));
     TREE_CUDA(t, cudaFuncSetAttribute(nn_scan_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNnSmem));
     configured[dev].store(true, std::memory_order_relaxed);
+  }
+  // batches of 32 queries and more: the distance matrix is a contraction and runs on the tensor cores (nn_tensor.cu);
+  // NWB_NN_NO_TC=1 keeps the CUDA-core scan for A/B measurements
+  static const bool no_tc = getenv("NWB_NN_NO_TC") != nullptr;
+  if (nq >= 32 && !no_tc) {
+    TREE_CUDA(t, cudaEventRecord(t->ctx->ev0, s));
+    int launches = 0;
+    TREE_CUDA(t, nn_tc_launch(t, q_dev, nq, idx_dev, dist_dev, nullptr, &launches));
+    TREE_CUDA(t, cudaEventRecord(t->ctx->ev1, s));
+    t->ctx->last_ms = -1;
+    t->ctx->last_launches = launches;
+    t->ctx->last_nn_passes = (nq + TC_M - 1) / TC_M;
+    return NWB_OK;
   }
   TREE_CUDA(t, cudaEventRecord(t->ctx->ev0, s));
   // one query (the RRT loop): minimum arithmetic per tile; batches: 8 or 16 queries share each pass over the nodes
@@ -546,6 +591,8 @@ void nwb_tree_destroy(nwb_tree* t) {
   cudaFree(t->soa);
   cudaFree(t->aos);
   cudaFree(t->pred);
+  cudaFree(t->tc);
+  cudaFree(t->max_nn);
   cudaFree(t->part_d);
   cudaFree(t->part_i);
   cudaFree(t->tickets);
@@ -556,6 +603,10 @@ void nwb_tree_destroy(nwb_tree* t) {
 int nwb_tree_clear(nwb_tree* t) {
   if (!t) return NWB_E_INVALID;
   t->size = 0;
+  if (t->max_nn) {
+    cudaSetDevice(t->ctx->device);
+    TREE_CUDA(t, cudaMemsetAsync(t->max_nn, 0, sizeof(unsigned), t->ctx->stream));
+  }
   return NWB_OK;
 }
 
@@ -570,6 +621,7 @@ int nwb_tree_add_dev(nwb_tree* t, const double* q_dev, const int32_t* pred_dev, 
   const int64_t e = n * NWB_NJ;
   tree_append_kernel<<<(unsigned)((e + 255) / 256), 256, 0, t->ctx->stream>>>(q_dev, pred_dev, n, t->soa, t->aos, t->pred, t->cap,
                                                                                t->size);
+  tree_append_tc_kernel<<<(unsigned)((n + 127) / 128), 128, 0, t->ctx->stream>>>(q_dev, n, t->tc, t->size, t->max_nn);
   TREE_CUDA(t, cudaGetLastError());
   t->size += n;
   return NWB_OK;
@@ -611,6 +663,24 @@ int64_t nwb_nn_scan_owner(const nwb_tree* t, int64_t nq, int64_t node) {
   const int64_t npt = nq == 1 ? NnCfg<1>::NPT : NnCfg<16>::NPT, tile = NN_THREADS * npt;
   const int64_t nb = nn_grid_blocks(t);
   return ((node / tile) % nb) * NN_THREADS + (node % tile) / npt;
+}
+
+int nwb_nn_debug_tensor_tile(nwb_tree* t, const double* q, int64_t nq, float* tile_out) {
+  if (!t || !q || nq < 1 || nq > TC_M || !tile_out || t->size < 1) return NWB_E_INVALID;
+  cudaSetDevice(t->ctx->device);
+  const size_t qb = sizeof(double) * NWB_NJ * nq, ob = sizeof(float) * TC_M * TC_N, ib = sizeof(int32_t) * nq;
+  int rc = stage_reserve(t, ((qb + 255) & ~(size_t)255) + ob + ib);
+  if (rc != NWB_OK) return rc;
+  cudaStream_t s = t->ctx->stream;
+  double* qd = (double*)t->stage;
+  float* od = (float*)((char*)t->stage + ((qb + 255) & ~(size_t)255));
+  int32_t* id = (int32_t*)((char*)od + ob);
+  TREE_CUDA(t, cudaMemcpyAsync(qd, q, qb, cudaMemcpyHostToDevice, s));
+  TREE_CUDA(t, cudaMemsetAsync(od, 0, ob, s));
+  TREE_CUDA(t, nn_tc_launch(t, qd, nq, id, nullptr, od, nullptr));
+  TREE_CUDA(t, cudaMemcpyAsync(tile_out, od, ob, cudaMemcpyDeviceToHost, s));
+  TREE_CUDA(t, cudaStreamSynchronize(s));
+  return NWB_OK;
 }
 
 int nwb_nearest_neighbour_batch_dev(nwb_tree* t, const double* q_dev, int64_t nq, int32_t* idx_dev, double* dist_dev) {

@@ -126,6 +126,79 @@ def test_nn_three_near_ties_in_one_scan_thread(ctx, oracle, nq, order):
     t.close()
 
 
+def _bf16(x):
+    import torch
+    return torch.from_numpy(np.asarray(x, dtype=np.float32)).to(torch.bfloat16).to(torch.float32).numpy()
+
+
+def test_tensor_core_accumulator_matches_its_specification_and_error_bound(ctx):
+    """The raw tcgen05 accumulator of the batched scan (first 128 nodes x up to 128 queries) against a NumPy evaluation
+    of the same bf16 hi/mid split, and its distance to the TRUE |n|^2 - 2 q.n against the bound E the filter uses
+    (nn_tensor.cu tc_error_bound): the filter is only as good as that bound."""
+    nodes = OL.uniform_configs(1000, seed=5, lhyp_zero=True)
+    q = np.concatenate([OL.golden_db()[:60], OL.uniform_configs(40, seed=6)])
+    t = nwb.Tree(ctx)
+    t.add(nodes)
+    tile = t.debug_tensor_tile(q)
+    t.close()
+    n128 = nodes[:128]
+    qf, nf = q.astype(np.float32), n128.astype(np.float32)
+    qh, nh = _bf16(qf), _bf16(nf)
+    qm, nm = _bf16(qf - qh), _bf16(nf - nh)
+    nn = (n128 ** 2).sum(1).astype(np.float32)
+    n0 = _bf16(nn)
+    n1 = _bf16(nn - n0)
+    n2 = _bf16(nn - n0 - n1)
+    spec = (n0 + n1 + n2)[None, :].astype(np.float64) - 2.0 * (qh.astype(np.float64) @ nh.T.astype(np.float64)
+                                                                + qh.astype(np.float64) @ nm.T.astype(np.float64)
+                                                                + qm.astype(np.float64) @ nh.T.astype(np.float64))
+    got = tile[:len(q)].astype(np.float64)
+    scale = (n128 ** 2).sum(1)[None, :] + 2 * np.linalg.norm(q, axis=1)[:, None] * np.linalg.norm(n128, axis=1)[None, :]
+    assert np.abs(got - spec).max() < 1e-5 * scale.max(), np.abs(got - spec).max()      # fp32 accumulation of 66 terms
+    true = (n128 ** 2).sum(1)[None, :] - 2.0 * q @ n128.T
+    nmax = np.sqrt((nodes ** 2).sum(1).max())
+    qn = np.linalg.norm(q, axis=1) * nmax
+    bound = 1.25 * (2.4e-5 * qn + 1.6e-5 * (nmax * nmax + 2.02 * qn) + 1e-7)
+    ratio = np.abs(got - true).max(1) / bound
+    print(f"\ntensor-core filter: max |v - true| / E = {ratio.max():.3f} (must stay well below 1)")
+    assert ratio.max() < 0.5
+    assert np.abs(tile[len(q):]).max() < 1e3                         # padding rows: |n|^2 only (no query), finite
+
+
+def test_tensor_core_path_flood_of_near_ties(ctx, oracle):
+    """More near ties than the candidate list of a CTA holds: the flooded tiles are evaluated exactly, pair by pair."""
+    rng = np.random.default_rng(12)
+    q = OL.golden_db()[20:84]                                            # 64 queries -> tensor-core path
+    dirs = rng.normal(size=(6000, 21))
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    nodes = q[0] + dirs * (0.5 + 1e-9 * rng.random(6000))[:, None]       # a shell around query 0
+    nodes[100:140] = nodes[3000:3040]                                    # and exact duplicates
+    t = nwb.Tree(ctx)
+    t.add(nodes)
+    idx, dist = t.findNearestNeighbour(q)
+    t.close()
+    o_idx, o_dist = oracle.nearest_neighbour(nodes, q, threads=oracle.threads)
+    check(idx, dist, o_idx, o_dist, nodes, q)
+
+
+@pytest.mark.parametrize("nq", [32, 127, 128, 129, 300])
+def test_tensor_core_path_ragged_query_counts(ctx, oracle, nq):
+    nodes = OL.noisy_db_configs(5000 + nq, seed=nq)                      # clustered data: many candidates per query
+    q = OL.noisy_db_configs(nq, seed=1000 + nq, sigma=0.02)
+    t = nwb.Tree(ctx)
+    t.add(nodes[:1000])
+    t.add(nodes[1000:])
+    idx, dist = t.findNearestNeighbour(q)
+    o_idx, o_dist = oracle.nearest_neighbour(nodes, q, threads=oracle.threads)
+    check(idx, dist, o_idx, o_dist, nodes, q)
+    t.clear()                                                            # stale rows past the new end must not be seen
+    t.add(nodes[:77])
+    idx, dist = t.findNearestNeighbour(q)
+    o_idx, o_dist = oracle.nearest_neighbour(nodes[:77], q)
+    check(idx, dist, o_idx, o_dist, nodes[:77], q)
+    t.close()
+
+
 def test_nn_empty_tree_and_far_nodes(ctx):
     t = nwb.Tree(ctx)
     idx, dist = t.findNearestNeighbour(np.zeros((3, 21)))
