@@ -31,7 +31,7 @@
 
 namespace nwb {
 
-constexpr int TC_THREADS = 128;
+constexpr int TC_THREADS = 512;                  // 16 warps: 4 lane quadrants x 4 column chunks of a tile
 constexpr int TC_STAGES = 6;
 constexpr int TC_CAND = 2048;
 
@@ -117,8 +117,8 @@ struct TcSmem {
   static constexpr size_t kCandNode = kBars + 8 * (TC_STAGES + 2);                    // int [TC_CAND]
   static constexpr size_t kCandQ = kCandNode + 4 * TC_CAND;                           // int [TC_CAND]
   static constexpr size_t kCandV = kCandQ + 4 * TC_CAND;                              // float [TC_CAND]
-  static constexpr size_t kMPub = kCandV + 4 * TC_CAND;                               // float [128]
-  static constexpr size_t kE2 = kMPub + 4 * TC_M;                                     // float [128]
+  static constexpr size_t kMPub = kCandV + 4 * TC_CAND;                               // float [4][128]
+  static constexpr size_t kE2 = kMPub + 4 * 4 * TC_M;                                 // float [128]
   static constexpr size_t kBestIdx = kE2 + 4 * TC_M;                                  // int [128]
   static constexpr size_t kIdxTmp = kBestIdx + 4 * TC_M;                              // int [128]
   static constexpr size_t kMisc = kIdxTmp + 4 * TC_M;                                 // int [8]: cand_n, tmem base, last flag
@@ -139,6 +139,11 @@ __device__ __forceinline__ double tc_exact_dist(const double* __restrict__ aos, 
   return sqrt(sum);
 }
 
+// Thread layout: 16 warps.  Warp w reads TMEM lanes 32 (w & 3) .. +31 (the lane quadrant the hardware lets it touch)
+// and the 32 columns (w >> 2) of every accumulator tile, so a query has four threads, one per column chunk, each with
+// its own running minimum (a candidate test against a minimum that is too LARGE only lists more nodes, never fewer).
+// Four warps per scheduler hide the TMEM-load and dependent-issue latencies that one warp per scheduler exposed
+// (profiles/r02_nn_tc_first_*: 9.5 cycles per issued instruction with 4 warps).
 __global__ void __launch_bounds__(TC_THREADS, 1)
 nn_tc_kernel(const unsigned char* __restrict__ tc, const double* __restrict__ aos, const unsigned* __restrict__ max_nn_bits,
              int64_t N, const double* __restrict__ q, int64_t nq, double* __restrict__ part_d, int32_t* __restrict__ part_i,
@@ -155,7 +160,7 @@ nn_tc_kernel(const unsigned char* __restrict__ tc, const double* __restrict__ ao
   int* cand_node = reinterpret_cast<int*>(smem + TcSmem::kCandNode);
   int* cand_q = reinterpret_cast<int*>(smem + TcSmem::kCandQ);
   float* cand_v = reinterpret_cast<float*>(smem + TcSmem::kCandV);
-  float* m_pub = reinterpret_cast<float*>(smem + TcSmem::kMPub);
+  float* m_pub = reinterpret_cast<float*>(smem + TcSmem::kMPub);             // [4 chunks][128 queries]
   float* e2s = reinterpret_cast<float*>(smem + TcSmem::kE2);
   int* best_idx = reinterpret_cast<int*>(smem + TcSmem::kBestIdx);
   int* idx_tmp = reinterpret_cast<int*>(smem + TcSmem::kIdxTmp);
@@ -163,10 +168,13 @@ nn_tc_kernel(const unsigned char* __restrict__ tc, const double* __restrict__ ao
   int& cand_n = misc[0];
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&misc[1]);
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ql = (warp & 3) * 32 + lane;                     // the query (= TMEM lane) this thread reads
+  const int chunk = warp >> 2;                               // its 32 columns of every tile
+  const bool owner = tid < TC_M;                             // warps 0-3: tid == ql, they also own the per-query state
   const int slice = blockIdx.x, n_slices = gridDim.x;
   const int64_t q0 = (int64_t)blockIdx.y * TC_M;
-  const bool q_live = q0 + tid < nq;
+  const bool q_live = q0 + ql < nq;
 
   // ---- set-up: barriers, tensor memory, the query tile ---------------------------------------------------------
   if (tid == 0) {
@@ -193,8 +201,8 @@ nn_tc_kernel(const unsigned char* __restrict__ tc, const double* __restrict__ ao
     }
   }
   // query row -> fp64 copy for the exact pass, bf16 split for the MMA (slot map: tree_internal.h)
-  float qnorm2 = 0.f;
-  {
+  if (owner) {
+    float qnorm2 = 0.f;
     __nv_bfloat16 row[TC_K];
 #pragma unroll
     for (int j = 0; j < NWB_NJ; ++j) {
@@ -216,18 +224,19 @@ nn_tc_kernel(const unsigned char* __restrict__ tc, const double* __restrict__ ao
     unsigned char* base = a_tile + (size_t)(tid >> 3) * (TC_KB * 128) + (size_t)(tid & 7) * 16;
 #pragma unroll
     for (int kb = 0; kb < TC_KB; ++kb) *reinterpret_cast<uint4*>(base + kb * 128) = *reinterpret_cast<const uint4*>(&row[kb * 8]);
+    const float nmax = sqrtf(__uint_as_float(*max_nn_bits));
+    e2s[tid] = 2.f * tc_error_bound(sqrtf(qnorm2) * (1.f + 1e-6f), nmax);
+    best_key[tid] = 0x7FF0000000000000ull;                   // +inf
+    best_idx[tid] = -1;
   }
-  const float nmax = sqrtf(__uint_as_float(*max_nn_bits));
-  const float e2 = 2.f * tc_error_bound(sqrtf(qnorm2) * (1.f + 1e-6f), nmax);
-  e2s[tid] = e2;
-  best_key[tid] = 0x7FF0000000000000ull;                     // +inf
-  best_idx[tid] = -1;
+  m_pub[chunk * TC_M + ql] = 3.0e38f;
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the query tile is read by the tensor core (async proxy)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t a_addr = tc_smem_u32(a_tile);
+  const float e2 = e2s[ql];
 
   auto mma_issue = [&](int t) {                              // thread 0: D[t % 2] = A . B(tile t)^T
     const int stage = t % TC_STAGES;
@@ -244,30 +253,45 @@ nn_tc_kernel(const unsigned char* __restrict__ tc, const double* __restrict__ ao
   float m_run = 3.0e38f;
   if (tid == 0 && T > 0) mma_issue(0);
 
-  // exact fp64 evaluation of the listed candidates that are still under their query's bound, folded into
-  // (best_key, best_idx) per query: lexicographic (distance, index)
+  // Fold (key = bits of an exact fp64 distance, node) contributions into (best_key, best_idx) per query,
+  // lexicographically: smaller distance first, lower index on equal distance.  Collective: every thread calls it
+  // with the same number of rounds; `contribute(round, ql_out, key_out, node_out)` returns false for "nothing".
+  auto fold_begin = [&]() {
+    if (owner) {
+      old_key[tid] = best_key[tid];
+      idx_tmp[tid] = 0x7FFFFFFF;
+    }
+    __syncthreads();
+  };
+  auto fold_end = [&]() {
+    __syncthreads();
+    if (owner) {
+      if (best_key[tid] < old_key[tid]) best_idx[tid] = idx_tmp[tid];
+      else if (idx_tmp[tid] != 0x7FFFFFFF && (best_idx[tid] < 0 || idx_tmp[tid] < best_idx[tid])) best_idx[tid] = idx_tmp[tid];
+    }
+    __syncthreads();
+  };
+
+  // exact fp64 evaluation of the listed candidates that are still under their query's bound
   auto flush = [&]() {
     const int n_c = min(cand_n, TC_CAND);
-    old_key[tid] = best_key[tid];
-    idx_tmp[tid] = 0x7FFFFFFF;
-    __syncthreads();
+    fold_begin();
     for (int c = tid; c < n_c; c += TC_THREADS) {
-      const int ql = cand_q[c];
+      const int cq = cand_q[c];
+      const float mq = fminf(fminf(m_pub[cq], m_pub[TC_M + cq]), fminf(m_pub[2 * TC_M + cq], m_pub[3 * TC_M + cq]));
       double d = __longlong_as_double(0x7FF0000000000000ll);
-      if (cand_v[c] <= m_pub[ql] + e2s[ql]) {
-        d = tc_exact_dist(aos, qd + ql * NWB_NJ, cand_node[c]);
-        atomicMin(&best_key[ql], (unsigned long long)__double_as_longlong(d));     // d >= 0: bit order = value order
+      if (cand_v[c] <= mq + e2s[cq]) {
+        d = tc_exact_dist(aos, qd + cq * NWB_NJ, cand_node[c]);
+        atomicMin(&best_key[cq], (unsigned long long)__double_as_longlong(d));     // d >= 0: bit order = value order
       }
       cand_d[c] = d;
     }
     __syncthreads();
     for (int c = tid; c < n_c; c += TC_THREADS) {
-      const int ql = cand_q[c];
-      if ((unsigned long long)__double_as_longlong(cand_d[c]) == best_key[ql]) atomicMin(&idx_tmp[ql], cand_node[c]);
+      const int cq = cand_q[c];
+      if ((unsigned long long)__double_as_longlong(cand_d[c]) == best_key[cq]) atomicMin(&idx_tmp[cq], cand_node[c]);
     }
-    __syncthreads();
-    if (best_key[tid] < old_key[tid]) best_idx[tid] = idx_tmp[tid];
-    else if (idx_tmp[tid] != 0x7FFFFFFF && (best_idx[tid] < 0 || idx_tmp[tid] < best_idx[tid])) best_idx[tid] = idx_tmp[tid];
+    fold_end();
     if (tid == 0) cand_n = 0;
     __syncthreads();
   };
@@ -276,48 +300,58 @@ nn_tc_kernel(const unsigned char* __restrict__ tc, const double* __restrict__ ao
     if (tid == 0 && t + 1 < T) mma_issue(t + 1);            // runs on the tensor core while tile t is read back
     tc_mbar_wait(&bars[TC_STAGES + (t & 1)], (uint32_t)((t >> 1) & 1));
     tc_fence_after();
-    const int64_t n0 = (tile_lo + t) * TC_N;
-    const bool full_tile = n0 + TC_N <= N;
+    const int64_t n0 = (tile_lo + t) * TC_N + chunk * 32;    // first node of this thread's columns
+    const bool full_chunk = n0 + 32 <= N;
     bool want_flush = false, overflow = false;
+    float v[32];
+    tc_ld32(tmem_base + (uint32_t)((t & 1) * TC_N + chunk * 32) + ((uint32_t)((warp & 3) * 32) << 16), v);
     if (debug_tile && slice == 0 && blockIdx.y == 0 && t == 0) {      // diagnostics: raw accumulator of the first tile
-      for (int c = 0; c < TC_N / 32; ++c) {
-        float v[32];
-        tc_ld32(tmem_base + (uint32_t)((t & 1) * TC_N + c * 32) + ((uint32_t)(warp * 32) << 16), v);
 #pragma unroll
-        for (int u = 0; u < 32; ++u) debug_tile[tid * TC_N + c * 32 + u] = v[u];
-      }
+      for (int u = 0; u < 32; ++u) debug_tile[ql * TC_N + chunk * 32 + u] = v[u];
     }
-#pragma unroll 1
-    for (int c = 0; c < TC_N / 32; ++c) {
-      float v[32];
-      tc_ld32(tmem_base + (uint32_t)((t & 1) * TC_N + c * 32) + ((uint32_t)(warp * 32) << 16), v);
-      float cm = v[0];
+    // minimum of the chunk as a tree (independent operations; a serial chain costs 31 dependent latencies); the
+    // second level r8[k] = min of columns {k, k+8, k+16, k+24} is kept for the candidate search
+    float r16[16], r8[8];
 #pragma unroll
-      for (int u = 1; u < 32; ++u) cm = fminf(cm, v[u]);
-      if (cm <= m_run + e2) {                                 // rare: a new running minimum or a near tie in this chunk
+    for (int u = 0; u < 16; ++u) r16[u] = fminf(v[u], v[u + 16]);
 #pragma unroll
-        for (int u = 0; u < 32; ++u) {
-          const int64_t node = n0 + c * 32 + u;
-          if (full_tile || node < N) {
-            const float x = v[u];
-            if (x < m_run) m_run = x;
-            if (x <= m_run + e2 && q_live) {
-              const int slot = atomicAdd(&cand_n, 1);
-              if (slot < TC_CAND) {
-                cand_node[slot] = (int)node;
-                cand_q[slot] = tid;
-                cand_v[slot] = x;
-              } else {
-                overflow = true;
-              }
-              want_flush = want_flush || slot >= TC_CAND / 2;
-            }
+    for (int u = 0; u < 8; ++u) r8[u] = fminf(r16[u], r16[u + 8]);
+    const float cm = fminf(fminf(fminf(r8[0], r8[1]), fminf(r8[2], r8[3])), fminf(fminf(r8[4], r8[5]), fminf(r8[6], r8[7])));
+    if (cm <= m_run + e2) {                                   // rare: a new running minimum or a near tie in this chunk
+      // The whole warp takes this path when ONE lane does and the CTA waits for it at the tile barrier, so it is kept
+      // short: lower the running minimum first, then list what lies within the band of it - 8 group tests, and the 4
+      // members only of a group that passes.  (A threshold above the final minimum + band lists a superset.)
+      if (full_chunk) m_run = fminf(m_run, cm);
+      else {
+#pragma unroll
+        for (int u = 0; u < 32; ++u)
+          if (n0 + u < N) m_run = fminf(m_run, v[u]);
+      }
+      const float thr = m_run + e2;
+      auto push = [&](int u, float x) {
+        if (x <= thr && q_live && (full_chunk || n0 + u < N)) {
+          const int slot = atomicAdd(&cand_n, 1);
+          if (slot < TC_CAND) {
+            cand_node[slot] = (int)(n0 + u);
+            cand_q[slot] = ql;
+            cand_v[slot] = x;
+          } else {
+            overflow = true;
           }
+          want_flush = want_flush || slot >= TC_CAND / 2;
         }
-      }
-      __syncwarp();
+      };
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (r8[k] <= thr) {
+          push(k, v[k]);
+          push(k + 8, v[k + 8]);
+          push(k + 16, v[k + 16]);
+          push(k + 24, v[k + 24]);
+        }
+      m_pub[chunk * TC_M + ql] = m_run;
     }
-    m_pub[tid] = m_run;
+    __syncwarp();
     tc_fence_before();
     const int act = __syncthreads_or((want_flush ? 1 : 0) | (overflow ? 2 : 0));
     if (tid == 0 && t + TC_STAGES < T) {                     // the MMA of tile t is complete: its stage is free again
@@ -327,27 +361,29 @@ nn_tc_kernel(const unsigned char* __restrict__ tc, const double* __restrict__ ao
                   &bars[stage]);
     }
     if (act & 2) {
-      // the list could not hold this tile's candidates: evaluate the whole tile exactly for the own query
+      // the list could not hold this tile's candidates: every thread evaluates its 32 (query, node) pairs exactly
+      unsigned long long bk = 0x7FF0000000000000ull;
+      int bi = 0x7FFFFFFF;
       if (q_live) {
-        unsigned long long bk = best_key[tid];
-        int bi = best_idx[tid];
-        for (int u = 0; u < TC_N; ++u) {
+        for (int u = 0; u < 32; ++u) {
           const int64_t node = n0 + u;
           if (node >= N) break;
-          const unsigned long long k = (unsigned long long)__double_as_longlong(tc_exact_dist(aos, qd + tid * NWB_NJ, node));
-          if (k < bk || (k == bk && (bi < 0 || (int)node < bi))) { bk = k; bi = (int)node; }
+          const unsigned long long k = (unsigned long long)__double_as_longlong(tc_exact_dist(aos, qd + ql * NWB_NJ, node));
+          if (k < bk) { bk = k; bi = (int)node; }             // ascending node order: the first minimum has the lowest index
         }
-        best_key[tid] = bk;
-        best_idx[tid] = bi;
       }
+      fold_begin();
+      if (bi != 0x7FFFFFFF) atomicMin(&best_key[ql], bk);
       __syncthreads();
+      if (bi != 0x7FFFFFFF && bk == best_key[ql]) atomicMin(&idx_tmp[ql], bi);
+      fold_end();
     }
     if (act) flush();
   }
   flush();
 
   // ---- partial of this slice, then the last CTA of the query group folds the slices --------------------------------
-  if (q_live) {
+  if (owner && q_live) {
     part_d[(q0 + tid) * n_slices + slice] = __longlong_as_double((long long)best_key[tid]);
     part_i[(q0 + tid) * n_slices + slice] = best_idx[tid];
   }
@@ -362,7 +398,7 @@ nn_tc_kernel(const unsigned char* __restrict__ tc, const double* __restrict__ ao
   __syncthreads();
   if (!misc[2]) return;
   __threadfence();
-  if (q_live) {
+  if (owner && q_live) {
     double d = 10000.0;                                       // RP:347: best_norm starts at 10000.0, strict <
     int i = -1;
     for (int s = 0; s < n_slices; ++s) {

@@ -17,6 +17,9 @@ def ctx():
 
 
 def check(idx, dist, o_idx, o_dist, nodes, q):
+    if np.abs(dist - o_dist).max() >= 1e-12:
+        bad = np.nonzero(np.abs(dist - o_dist) >= 1e-12)[0]
+        print("NN mismatches at queries", bad[:20], "got", idx[bad[:20]], dist[bad[:20]], "want", o_idx[bad[:20]], o_dist[bad[:20]])
     assert np.abs(dist - o_dist).max() < 1e-12
     bad = np.nonzero(idx != o_idx)[0]
     for k in bad:       # only exact-distance ties may differ (none expected: both take the lowest index)
