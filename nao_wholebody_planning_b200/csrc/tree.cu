@@ -417,6 +417,281 @@ nn_scan_kernel(const float* __restrict__ soa, const double* __restrict__ aos, in
   if (tid == 0) tickets[blockIdx.y] = 0u;              // ready for the next call
 }
 
+
+// ---- single query, small trees: exact fp64 straight from the master copy -------------------------------------------
+// Below ~2 10^5 nodes the scan is latency-, not bandwidth-bound, so the filter + exact second trip of the fp32 scan
+// costs more than it saves: one block per 256 nodes pulls its rows (43 KB, contiguous in the AoS master copy) into
+// shared memory with ONE bulk copy and every thread evaluates its node exactly as RP:361-377 does.  No candidates, no
+// second dependent memory trip; grid reduction by a last-block-done ticket.
+constexpr int NN1_THREADS = 256;
+constexpr int64_t kNnSmallMax = 65536;     // nodes up to which the exact small-tree kernel serves a single query
+
+__device__ __forceinline__ void nn_lex_warp_min(double& d, int& i) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double d2 = __shfl_xor_sync(0xffffffffu, d, o);
+    const int i2 = __shfl_xor_sync(0xffffffffu, i, o);
+    if (lex_less(d2, i2, d, i)) { d = d2; i = i2; }
+  }
+}
+
+__global__ void __launch_bounds__(NN1_THREADS)
+nn_small_kernel(const double* __restrict__ aos, int64_t N, const double* __restrict__ q, double* __restrict__ part_d,
+                int32_t* __restrict__ part_i, unsigned* __restrict__ ticket, int32_t* __restrict__ idx_out,
+                double* __restrict__ dist_out) {
+  __shared__ __align__(128) double rows[NN1_THREADS * NWB_NJ];
+  __shared__ double qd[NWB_NJ];
+  __shared__ uint64_t bar;
+  __shared__ double red_d[NN1_THREADS / 32];
+  __shared__ int red_i[NN1_THREADS / 32];
+  __shared__ bool last;
+  const int tid = threadIdx.x;
+  const int64_t n0 = (int64_t)blockIdx.x * NN1_THREADS;
+  const int cnt = (int)min((int64_t)NN1_THREADS, N - n0);
+  if (tid == 0) {
+    nn_mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const uint32_t bytes = (uint32_t)(cnt * NWB_NJ * sizeof(double));      // 168 B per node: a multiple of 8, ...
+    const uint32_t b16 = bytes & ~15u;                                      // ... the bulk copy moves whole 16-byte units
+    if (b16) {
+      nn_mbar_expect_tx(&bar, b16);
+      nn_bulk_g2s(rows, aos + n0 * NWB_NJ, b16, &bar);
+    } else {
+      nn_mbar_expect_tx(&bar, 0);
+    }
+    if (bytes != b16) rows[b16 / 8] = aos[n0 * NWB_NJ + b16 / 8];           // odd node count: the last 8 bytes by hand
+  }
+  if (tid < NWB_NJ) qd[tid] = q[tid];
+  __syncthreads();
+  nn_mbar_wait(&bar, 0);
+  double d = 10000.0;                                  // RP:347: best_norm starts at 10000.0, strict <
+  int i = -1;
+  if (tid < cnt) {
+    double sum = 0.0;
+#pragma unroll
+    for (int j = 0; j < NWB_NJ; ++j) {
+      const double e = __dsub_rn(qd[j], rows[tid * NWB_NJ + j]);
+      sum = __dadd_rn(sum, __dmul_rn(e, e));           // separately rounded multiply and add
+    }
+    const double dn = sqrt(sum);
+    if (dn < 10000.0) { d = dn; i = (int)(n0 + tid); }
+  }
+  nn_lex_warp_min(d, i);
+  if ((tid & 31) == 0) { red_d[tid >> 5] = d; red_i[tid >> 5] = i; }
+  __syncthreads();
+  if (tid < 32) {
+    d = tid < NN1_THREADS / 32 ? red_d[tid] : 10000.0;
+    i = tid < NN1_THREADS / 32 ? red_i[tid] : -1;
+    nn_lex_warp_min(d, i);
+    if (tid == 0) {
+      if (gridDim.x == 1) {
+        idx_out[0] = i;
+        if (dist_out) dist_out[0] = d;
+        last = false;
+      } else {
+        part_d[blockIdx.x] = d;
+        part_i[blockIdx.x] = i;
+        __threadfence();
+        last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+      }
+    }
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  d = 10000.0;
+  i = -1;
+  for (int b = tid; b < (int)gridDim.x; b += NN1_THREADS) {
+    const double db = part_d[b];
+    const int ib = part_i[b];
+    if (ib >= 0 && lex_less(db, ib, d, i)) { d = db; i = ib; }
+  }
+  nn_lex_warp_min(d, i);
+  if ((tid & 31) == 0) { red_d[tid >> 5] = d; red_i[tid >> 5] = i; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < NN1_THREADS / 32; ++w)
+      if (red_i[w] >= 0 && lex_less(red_d[w], red_i[w], d, i)) { d = red_d[w]; i = red_i[w]; }
+    idx_out[0] = i;
+    if (dist_out) dist_out[0] = d;
+    *ticket = 0u;
+  }
+}
+
+// ---- single query, large trees: fp32 SoA stream + exact re-evaluation of the listed candidates ----------------------
+// One persistent CTA per SM streams its CONTIGUOUS node range (balanced to 4 nodes) through a 4-stage ring.  The 21 row
+// copies of a tile are issued by 21 lanes of warp 0 side by side (one thread issuing them one after the other was on the
+// critical path: ~0.5 us per tile).  A node whose fp32 squared distance lies within the rigorous error bound of the
+// block's running minimum is listed in shared memory the moment it is seen (and its master-copy row is prefetched into
+// L2); there are no per-thread candidate slots that could silently overflow.  After the stream only the listed nodes
+// still under the final bound are evaluated in fp64.  A list overflow (a flood of near ties) falls back to an exact
+// rescan of the block's range.
+constexpr int NN2_THREADS = 256;
+constexpr int NN2_TILE = 512;
+constexpr int NN2_STAGES = 4;
+constexpr int NN2_CAND = 1024;
+
+__global__ void __launch_bounds__(NN2_THREADS, 1)
+nn_stream_kernel(const float* __restrict__ soa, const double* __restrict__ aos, int64_t cap, int64_t N,
+                 const double* __restrict__ q, double* __restrict__ part_d, int32_t* __restrict__ part_i,
+                 unsigned* __restrict__ ticket, int32_t* __restrict__ idx_out, double* __restrict__ dist_out) {
+  extern __shared__ __align__(128) unsigned char nn_smem[];
+  float* ring = reinterpret_cast<float*>(nn_smem);                           // [STAGES][21][TILE]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(nn_smem + sizeof(float) * NN2_STAGES * NWB_NJ * NN2_TILE);
+  __shared__ double qd[NWB_NJ];
+  __shared__ __align__(8) float2 qn2[NWB_NJ];
+  __shared__ unsigned run_min;
+  __shared__ int cand_n;
+  __shared__ int cand_node[NN2_CAND];
+  __shared__ float cand_s[NN2_CAND];
+  __shared__ double red_d[NN2_THREADS / 32];
+  __shared__ int red_i[NN2_THREADS / 32];
+  __shared__ bool last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // contiguous node range of this CTA, boundaries on multiples of 4 nodes (16-byte bulk copies)
+  const int64_t quads = (N + 3) >> 2;
+  const int64_t lo = (quads * blockIdx.x / gridDim.x) << 2, hi = min(N, (quads * (blockIdx.x + 1) / gridDim.x) << 2);
+  const int tiles = (int)((hi - lo + NN2_TILE - 1) / NN2_TILE);
+  if (tid == 0) {
+    for (int sg = 0; sg < NN2_STAGES; ++sg) nn_mbar_init(&bars[sg], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    run_min = 0x7f7fffffu;
+    cand_n = 0;
+  }
+  __syncthreads();
+  auto issue = [&](int tile, int stage) {              // warp 0: lane j < 21 copies row j of the tile
+    const int64_t t0 = lo + (int64_t)tile * NN2_TILE;
+    const int64_t cnt = min((int64_t)NN2_TILE, ((hi - t0) + 3) & ~(int64_t)3);   // rows are padded to 64 nodes
+    const uint32_t bytes = (uint32_t)(cnt * sizeof(float));
+    if (lane == 0) nn_mbar_expect_tx(&bars[stage], bytes * NWB_NJ);
+    __syncwarp();
+    if (lane < NWB_NJ)
+      nn_bulk_g2s(ring + ((size_t)stage * NWB_NJ + lane) * NN2_TILE, soa + (int64_t)lane * cap + t0, bytes, &bars[stage]);
+  };
+  if (warp == 0)
+    for (int sg = 0; sg < NN2_STAGES && sg < tiles; ++sg) issue(sg, sg);
+  if (tid >= 32 && tid < 32 + NWB_NJ) {                // the query arrives while the first tiles are in flight
+    const double v = q[tid - 32];
+    qd[tid - 32] = v;
+    qn2[tid - 32] = make_float2(-(float)v, -(float)v);
+  }
+  __syncthreads();
+
+  uint32_t phase = 0;
+  int stage = 0;
+  bool flooded = false;
+  for (int tile = 0; tile < tiles; ++tile) {
+    nn_mbar_wait(&bars[stage], phase);
+    const float* x = ring + (size_t)stage * NWB_NJ * NN2_TILE;
+    const int64_t t0 = lo + (int64_t)tile * NN2_TILE;
+    float2 s2 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < NWB_NJ; ++j) {
+      const float2 d = __fadd2_rn(*reinterpret_cast<const float2*>(&x[j * NN2_TILE + 2 * tid]), qn2[j]);
+      s2 = __ffma2_rn(d, d, s2);
+    }
+    const int64_t node0 = t0 + 2 * tid;
+    const float sa = node0 < hi ? s2.x : 3.0e38f, sb = node0 + 1 < hi ? s2.y : 3.0e38f;
+    const unsigned wmin = __reduce_min_sync(0xffffffffu, __float_as_uint(fminf(sa, sb)));
+    if (lane == 0) atomicMin(&run_min, wmin);
+    __syncthreads();                                    // the stage is consumed and run_min is current
+    if (warp == 0 && tile + NN2_STAGES < tiles) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      issue(tile + NN2_STAGES, stage);
+    }
+    const float bound = nn_candidate_bound(__uint_as_float(run_min));
+    if (fminf(sa, sb) <= bound) {                       // rare
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const float v = u ? sb : sa;
+        if (v <= bound) {
+          const int slot = atomicAdd(&cand_n, 1);
+          if (slot < NN2_CAND) {
+            cand_node[slot] = (int)(node0 + u);
+            cand_s[slot] = v;
+            const double* row = aos + (node0 + u) * NWB_NJ;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 16));
+          } else {
+            flooded = true;
+          }
+        }
+      }
+    }
+    if (++stage == NN2_STAGES) { stage = 0; phase ^= 1u; }
+  }
+  const int any_flood = __syncthreads_or(flooded ? 1 : 0);
+
+  auto exact_dist = [&](int64_t node) {
+    const double* row = aos + node * NWB_NJ;
+    double r[NWB_NJ];
+#pragma unroll
+    for (int j = 0; j < NWB_NJ; ++j) r[j] = row[j];
+    double sum = 0.0;
+#pragma unroll
+    for (int j = 0; j < NWB_NJ; ++j) {
+      const double d = __dsub_rn(qd[j], r[j]);
+      sum = __dadd_rn(sum, __dmul_rn(d, d));
+    }
+    return sqrt(sum);
+  };
+  double d = 10000.0;
+  int i = -1;
+  const float fbound = nn_candidate_bound(__uint_as_float(run_min));
+  if (!any_flood) {
+    const int n_c = cand_n;
+    for (int c = tid; c < n_c; c += NN2_THREADS)
+      if (cand_s[c] <= fbound) {
+        const double dn = exact_dist(cand_node[c]);
+        if (dn < 10000.0 && lex_less(dn, cand_node[c], d, i)) { d = dn; i = cand_node[c]; }
+      }
+  } else {
+    // a flood of near ties: exact rescan of this CTA's range from global memory
+    for (int64_t node = lo + tid; node < hi; node += NN2_THREADS) {
+      float sv = 0.f;
+      for (int j = 0; j < NWB_NJ; ++j) {
+        const float e = (float)qd[j] - soa[(int64_t)j * cap + node];
+        sv = fmaf(e, e, sv);
+      }
+      if (sv <= fbound) {
+        const double dn = exact_dist(node);
+        if (dn < 10000.0 && lex_less(dn, (int)node, d, i)) { d = dn; i = (int)node; }
+      }
+    }
+  }
+  nn_lex_warp_min(d, i);
+  if (lane == 0) { red_d[warp] = d; red_i[warp] = i; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < NN2_THREADS / 32; ++w)
+      if (red_i[w] >= 0 && lex_less(red_d[w], red_i[w], d, i)) { d = red_d[w]; i = red_i[w]; }
+    part_d[blockIdx.x] = d;
+    part_i[blockIdx.x] = i;
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  d = 10000.0;
+  i = -1;
+  for (int b = tid; b < (int)gridDim.x; b += NN2_THREADS) {
+    const double db = part_d[b];
+    const int ib = part_i[b];
+    if (ib >= 0 && lex_less(db, ib, d, i)) { d = db; i = ib; }
+  }
+  nn_lex_warp_min(d, i);
+  if (lane == 0) { red_d[warp] = d; red_i[warp] = i; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < NN2_THREADS / 32; ++w)
+      if (red_i[w] >= 0 && lex_less(red_d[w], red_i[w], d, i)) { d = red_d[w]; i = red_i[w]; }
+    idx_out[0] = i;
+    if (dist_out) dist_out[0] = d;
+    *ticket = 0u;
+  }
+}
+
 }  // namespace nwb
 
 using namespace nwb;
@@ -491,7 +766,7 @@ int nn_grid_blocks(const nwb_tree* t) {
 
 int nn_launch(nwb_tree* t, const double* q_dev, int64_t nq, int32_t* idx_dev, double* dist_dev) {
   const int nb = nn_grid_blocks(t);
-  size_t need = (size_t)nq * nb;
+  size_t need = std::max((size_t)nq * nb, (size_t)(kNnSmallMax / NN1_THREADS + 1));   // the small-tree kernel: one partial per block
   if (need > t->part_cap) {
     if (t->part_d) cudaFree(t->part_d);
     if (t->part_i) cudaFree(t->part_i);
@@ -536,8 +811,38 @@ int nn_launch(nwb_tree* t, const double* q_dev, int64_t nq, int32_t* idx_dev, do
     t->ctx->last_nn_passes = (nq + TC_M - 1) / TC_M;
     return NWB_OK;
   }
+  // one query (the RRT loop's own call pattern): exact fp64 blocks for small trees, the fp32 stream for large ones;
+  // NWB_NN_OLD=1 keeps the round-1 tile-interleaved kernel for A/B measurements
+  static const bool old_single = getenv("NWB_NN_OLD") != nullptr;
+  if (nq == 1 && !old_single) {
+    TREE_CUDA(t, cudaEventRecord(t->ctx->ev0, s));
+    if (t->size <= kNnSmallMax) {
+      const unsigned blocks = (unsigned)std::max<int64_t>(1, (t->size + NN1_THREADS - 1) / NN1_THREADS);
+      if (t->size == 0) {
+        nn_small_kernel<<<1, NN1_THREADS, 0, s>>>(t->aos, 0, q_dev, t->part_d, t->part_i, t->tickets, idx_dev, dist_dev);
+      } else {
+        nn_small_kernel<<<blocks, NN1_THREADS, 0, s>>>(t->aos, t->size, q_dev, t->part_d, t->part_i, t->tickets, idx_dev, dist_dev);
+      }
+    } else {
+      constexpr size_t kSmem2 = sizeof(float) * NN2_STAGES * NWB_NJ * NN2_TILE + 8 * NN2_STAGES;
+      static std::atomic<bool> cfg2[64];
+      if (!cfg2[dev].load(std::memory_order_relaxed)) {
+        TREE_CUDA(t, cudaFuncSetAttribute(nn_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem2));
+        cfg2[dev].store(true, std::memory_order_relaxed);
+      }
+      const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>(t->ctx->sm_count, (t->size + NN2_TILE - 1) / NN2_TILE));
+      nn_stream_kernel<<<blocks, NN2_THREADS, kSmem2, s>>>(t->soa, t->aos, t->cap, t->size, q_dev, t->part_d, t->part_i, t->tickets,
+                                                           idx_dev, dist_dev);
+    }
+    TREE_CUDA(t, cudaGetLastError());
+    TREE_CUDA(t, cudaEventRecord(t->ctx->ev1, s));
+    t->ctx->last_ms = -1;
+    t->ctx->last_launches = 1;
+    t->ctx->last_nn_passes = 1;
+    return NWB_OK;
+  }
   TREE_CUDA(t, cudaEventRecord(t->ctx->ev0, s));
-  // one query (the RRT loop): minimum arithmetic per tile; batches: 8 or 16 queries share each pass over the nodes
+  // batches below 32 queries: 8 or 16 queries share each pass over the nodes on the FP32 pipe
   static const int qt_batch = getenv("NWB_NN_QT") ? atoi(getenv("NWB_NN_QT")) : 16;
   const int QT = nq == 1 ? 1 : (nq <= 8 || qt_batch == 8 ? 8 : 16);
   const int64_t qtiles = (nq + QT - 1) / QT;
@@ -660,7 +965,17 @@ int nwb_tree_get(nwb_tree* t, int64_t first, int64_t n, double* q_out, int32_t* 
 
 int64_t nwb_nn_scan_owner(const nwb_tree* t, int64_t nq, int64_t node) {
   if (!t || nq < 1 || node < 0 || node >= t->size) return NWB_E_INVALID;
-  const int64_t npt = nq == 1 ? NnCfg<1>::NPT : NnCfg<16>::NPT, tile = NN_THREADS * npt;
+  if (nq == 1) {
+    if (t->size <= kNnSmallMax) return node;                              // exact kernel: one node per thread
+    const int64_t blocks = std::max<int64_t>(1, std::min<int64_t>(t->ctx->sm_count, (t->size + NN2_TILE - 1) / NN2_TILE));
+    const int64_t quads = (t->size + 3) >> 2;
+    int64_t b = 0;                                                        // contiguous ranges (nn_stream_kernel)
+    while (b + 1 < blocks && ((quads * (b + 1) / blocks) << 2) <= node) ++b;
+    const int64_t lo = (quads * b / blocks) << 2;
+    return b * NN2_THREADS + ((node - lo) % NN2_TILE) / 2;
+  }
+  if (nq >= 32) return (node % TC_N) / 32 * TC_M + 0;                     // tensor-core path: a thread per (query, 32-column chunk)
+  const int64_t npt = NnCfg<16>::NPT, tile = NN_THREADS * npt;
   const int64_t nb = nn_grid_blocks(t);
   return ((node / tile) % nb) * NN_THREADS + (node % tile) / npt;
 }
