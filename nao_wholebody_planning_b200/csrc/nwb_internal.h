@@ -14,6 +14,7 @@ namespace nwb {
 constexpr int kMaxPairs = 112;
 constexpr int kMaxRuns = 48;
 constexpr int kMaxBoxes = 16;              // boxes that travel inline in the kernel parameters
+constexpr int kStagedNodes = 1024;         // hierarchy nodes a CTA of the batched validity kernel stages in shared memory
 constexpr int kSceneBoxLimit = 1 << 20;    // boxes of a scene held in global memory under the hierarchy
 
 // One collision pair inside a run: B's point-table slot and constants.

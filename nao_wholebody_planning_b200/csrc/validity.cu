@@ -70,6 +70,31 @@ struct FkVisitor {
   }
 };
 
+// ---- TMA bulk-copy helpers (cp.async.bulk 1-D, completion on an mbarrier) ----------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // ---- the validity kernel ------------------------------------------------------------------------
 //   MARGINS        also produce {min separation, signed hull distance} (sqrt per pair + gift wrapping)
 //   COLLISION_ONLY skip COM / support (isPathValid way-points)
@@ -77,11 +102,29 @@ template <typename QT, bool MARGINS, bool COLLISION_ONLY, int PAIRS, bool BIG_SC
 __global__ void __launch_bounds__(NT, NWB_MINB)
 validity_kernel(const __grid_constant__ ValidityTables tab, const QT* __restrict__ q, int64_t n,
                 uint8_t* __restrict__ valid, uint8_t* __restrict__ reason, float* __restrict__ margins) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   const int tid = threadIdx.x;
   const int64_t base = (int64_t)blockIdx.x * NT;
   const int64_t i = base + tid;
   const int nvalid = (int)min((int64_t)NT, n - base);
+  // Large scene: the head of the bounding-volume hierarchy (up to kStagedNodes nodes, 32 KB) is staged in shared memory
+  // with ONE bulk copy (UBLKCP, mbarrier complete_tx) issued first thing, so it lands while the block stages its
+  // configurations; every node visit of the walk then costs a shared-memory read instead of an L1/L2 round trip.
+  const SceneNode* staged = nullptr;
+  int n_staged = 0;
+  uint64_t* scene_bar = nullptr;
+  if constexpr (BIG_SCENE) {
+    SceneNode* area = reinterpret_cast<SceneNode*>(smem + (PAIRS == PAIRS_TABLE ? kSmemFloats : NT * NWB_NJ));
+    scene_bar = reinterpret_cast<uint64_t*>(area + kStagedNodes);
+    n_staged = min(tab.scene.n_nodes, kStagedNodes);
+    staged = area;
+    if (tid == 0) {
+      mbar_init(scene_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      mbar_expect_tx(scene_bar, (uint32_t)(n_staged * sizeof(SceneNode)));
+      bulk_g2s(area, tab.scene.nodes, (uint32_t)(n_staged * sizeof(SceneNode)), scene_bar);
+    }
+  }
 
   // stage this block's configurations: coalesced global read, fp32 in shared, AoS order
   for (int e = tid; e < nvalid * NWB_NJ; e += NT) smem[e] = (float)q[base * NWB_NJ + e];
@@ -92,14 +135,15 @@ validity_kernel(const __grid_constant__ ValidityTables tab, const QT* __restrict
   for (int j = 0; j < NWB_NJ; ++j) qv[j] = smem[row * NWB_NJ + j];   // stride 21 words: conflict-free
   if constexpr (PAIRS == PAIRS_TABLE) __syncthreads();   // staging area is reused as the point table below
 
+  if constexpr (BIG_SCENE) mbar_wait(scene_bar, 0);   // after the __syncthreads above: the barrier word is visible to all
   float min_sep = 0.f, hull_margin = 0.f;
   ValidityResult<float> res;
   if constexpr (PAIRS == PAIRS_TABLE) {
     SmemStore st{smem + tid};
-    res = evaluate_config<float, SmemStore, MARGINS, COLLISION_ONLY, PAIRS, false, BIG_SCENE>(tab, qv, st, &min_sep, &hull_margin);
+    res = evaluate_config<float, SmemStore, MARGINS, COLLISION_ONLY, PAIRS, false, BIG_SCENE>(tab, qv, st, &min_sep, &hull_margin, staged, n_staged);
   } else {
     RegStore st;
-    res = evaluate_config<float, RegStore, MARGINS, COLLISION_ONLY, PAIRS, false, BIG_SCENE>(tab, qv, st, &min_sep, &hull_margin);
+    res = evaluate_config<float, RegStore, MARGINS, COLLISION_ONLY, PAIRS, false, BIG_SCENE>(tab, qv, st, &min_sep, &hull_margin, staged, n_staged);
   }
 
   if (i < n) {
@@ -127,30 +171,6 @@ validity_kernel(const __grid_constant__ ValidityTables tab, const QT* __restrict
 #define NWB_PMINB 2
 #endif
 constexpr int PT = NWB_PT;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
 
 template <typename QT, bool MARGINS, bool COLLISION_ONLY, int PAIRS>
 __global__ void __launch_bounds__(PT, NWB_PMINB)
@@ -359,7 +379,8 @@ static cudaError_t launch_one(const ValidityTables& tab, const void* q, int64_t 
                               float* margins, cudaStream_t stream) {
   auto kern = validity_kernel<QT, MARGINS, COLLISION_ONLY, PAIRS, BIG_SCENE>;
   static std::atomic<bool> configured[kMaxDevices];   // per instantiation and device
-  const size_t smem = (PAIRS == PAIRS_TABLE ? kSmemFloats : NT * NWB_NJ) * sizeof(float);
+  const size_t smem = (PAIRS == PAIRS_TABLE ? kSmemFloats : NT * NWB_NJ) * sizeof(float) +
+                      (BIG_SCENE ? (size_t)kStagedNodes * sizeof(SceneNode) + 16 : 0);
   const int dev = current_device();
   if (!configured[dev].load(std::memory_order_relaxed)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -126,7 +126,8 @@ enum PairMode { PAIRS_TABLE = 0, PAIRS_STATIC_GROUP = 1, PAIRS_STATIC_ALL = 2 };
 // time on batches of unrelated configurations, whose warps almost never agree - the batched validity
 // kernels instantiate it off.
 template <class T, class Store, bool MARGINS, bool COLLISION_ONLY, int PAIRS = PAIRS_TABLE, bool ENV_CULL = false, bool BIG_SCENE = false>
-NWB_HD ValidityResult<T> evaluate_config(const ValidityTables& tab, const T* q, Store& st, T* min_sep_out, T* hull_out) {
+NWB_HD ValidityResult<T> evaluate_config(const ValidityTables& tab, const T* q, Store& st, T* min_sep_out, T* hull_out,
+                                         const SceneNode* staged_nodes = nullptr, int n_staged = 0) {
   using M = typename mask_of<T>::type;
   ValidityVisitor<T, Store, !COLLISION_ONLY> V(st);
   { NWB_MODEL_FK_WALK(T, XF<T>, q, V) }
@@ -353,7 +354,8 @@ NWB_HD ValidityResult<T> evaluate_config(const ValidityTables& tab, const T* q, 
         if constexpr (!MARGINS) {
           if (hit) break;                                               // verdict settled: the rest of the scene cannot change it
         }
-        const SceneNode nd = tab.scene.nodes[node];
+        // the first n_staged nodes of the hierarchy sit in shared memory (bulk-copied once per CTA by the batched kernel)
+        const SceneNode nd = node < n_staged ? staged_nodes[node] : tab.scene.nodes[node];
         float g2 = 0.f;                                                 // squared gap between the two bounding boxes
 #pragma unroll
         for (int k = 0; k < 3; ++k) {

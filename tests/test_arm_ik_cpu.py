@@ -234,6 +234,33 @@ def test_time_parameterization_known_answers(oracle):
     assert oracle.time_parameterize(sol[:1])[0] == 2.0
 
 
+def test_time_parameterization_three_way_points_by_hand(oracle):
+    """Two hand-computed three-way-point answers.
+    (1) Velocity regime - accelerations unbounded, so computeTimeStamps reduces to applyVelocityConstraints: every
+        interval lasts max_j |dq_j| / v_max_j exactly, stamps = 2.0 + running sum (RP:1614-1618 adds the 2 s head start).
+    (2) Acceleration regime - one joint going 0 -> D -> 0: at all three points the blend acceleration is 2 D / T^2 in
+        magnitude (the end points mirror their only neighbour), so both intervals must reach T >= sqrt(2 D / (a_max +
+        0.01)) and the 0.01 s growth steps stop within two steps of it."""
+    vmax = np.array(nwb_vmax())
+    p = OL.default_params()
+    p.joint_max_acceleration[:] = [1e9] * 21
+    path = np.zeros((3, 21))
+    path[1, 10], path[1, 11] = 0.5, -0.2
+    path[2, 10], path[2, 11] = 0.6, 0.2
+    t = oracle.time_parameterize(path, params=p)
+    dt0 = max(0.5 / vmax[10], 0.2 / vmax[11])
+    dt1 = max(0.1 / vmax[10], 0.4 / vmax[11])
+    assert np.allclose(t, [2.0, 2.0 + dt0, 2.0 + dt0 + dt1], rtol=0, atol=1e-15)
+    D = 0.4
+    path = np.zeros((3, 21))
+    path[1, 12] = D
+    t = oracle.time_parameterize(path)                                  # default limits: a_max = 1.0
+    T = np.sqrt(2 * D / 1.01)
+    assert t[0] == 2.0
+    for dt in np.diff(t):
+        assert T <= dt <= T + 0.02, (dt, T)
+
+
 def nwb_vmax():
     from nao_wholebody_planning_b200._abi import NAO_MAX_VELOCITY
     return NAO_MAX_VELOCITY
