@@ -71,7 +71,11 @@ NWB_HD double nwb_sel(bool c, double a, double b) { return c ? a : b; }
 // one MUFU.RCP + one FMUL on the device instead of the IEEE division sequence.
 NWB_HD float nwb_div_fast(float a, float b) {
 #if defined(__CUDA_ARCH__)
-  return __fdividef(a, b);
+  // bare MUFU.RCP + FMUL: __fdividef wraps the same two instructions in a range check for |b| > 2^126 (one FSETP and
+  // two more FMULs per division); every denominator here is a squared length of at most a few m^2
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
+  return a * r;
 #else
   return a / b;
 #endif
@@ -226,6 +230,39 @@ NWB_HD T dot3(const T* a, T bx, T by, T bz) { return nwb_fma(a[2], bz, nwb_fma(a
 // ClosestPtSegmentSegment and leaves an interior optimum unchanged.  The tiny bias on the
 // denominator keeps parallel segments finite; whatever s they get is repaired by the two
 // refinement steps (any s is optimal along parallel lines).
+// `bias` is added to the result inside the last multiply-add chain: with bias = -(rA + rB)^2 the sign of the result is
+// the contact test and no separate compare (an ALU-pipe instruction, two dispatch cycles on sm_100) is needed per pair.
+template <class T>
+NWB_HD T seg_seg_dist2(const T* pa, const T* d1, T a, T inv_a, const T* pb, const T* d2, T e, T inv_e, T bias) {
+  T rx = pa[0] - pb[0], ry = pa[1] - pb[1], rz = pa[2] - pb[2];
+  T f = dot3(d2, rx, ry, rz);
+  T c = dot3(d1, rx, ry, rz);
+  T b = dot3(d1, d2[0], d2[1], d2[2]);
+  T denom = nwb_fma(-b, b, nwb_fma(a, e, T(1e-18f)));
+  T s = nwb_sat(nwb_div_fast(nwb_fma(b, f, -(c * e)), denom));
+  T t = nwb_mul_sat(nwb_fma(b, s, f), inv_e);
+  s = nwb_mul_sat(nwb_fma(b, t, -c), inv_a);
+  T vx = nwb_fma(-d2[0], t, nwb_fma(d1[0], s, rx));
+  T vy = nwb_fma(-d2[1], t, nwb_fma(d1[1], s, ry));
+  T vz = nwb_fma(-d2[2], t, nwb_fma(d1[2], s, rz));
+  return nwb_fma(vz, vz, nwb_fma(vy, vy, nwb_fma(vx, vx, bias)));
+}
+// segment A vs point pb
+template <class T>
+NWB_HD T seg_point_dist2(const T* pa, const T* d1, T inv_a, const T* pb, T bias) {
+  T rx = pa[0] - pb[0], ry = pa[1] - pb[1], rz = pa[2] - pb[2];
+  T c = dot3(d1, rx, ry, rz);
+  T s = nwb_mul_sat(-c, inv_a);
+  T vx = nwb_fma(d1[0], s, rx), vy = nwb_fma(d1[1], s, ry), vz = nwb_fma(d1[2], s, rz);
+  return nwb_fma(vz, vz, nwb_fma(vy, vy, nwb_fma(vx, vx, bias)));
+}
+template <class T>
+NWB_HD T point_point_dist2(const T* pa, const T* pb, T bias) {
+  T rx = pa[0] - pb[0], ry = pa[1] - pb[1], rz = pa[2] - pb[2];
+  return nwb_fma(rz, rz, nwb_fma(ry, ry, nwb_fma(rx, rx, bias)));
+}
+
+// unbiased forms (plain squared distances: table-driven pair lists, margins, planner kernels)
 template <class T>
 NWB_HD T seg_seg_dist2(const T* pa, const T* d1, T a, T inv_a, const T* pb, const T* d2, T e, T inv_e) {
   T rx = pa[0] - pb[0], ry = pa[1] - pb[1], rz = pa[2] - pb[2];
@@ -241,7 +278,6 @@ NWB_HD T seg_seg_dist2(const T* pa, const T* d1, T a, T inv_a, const T* pb, cons
   T vz = nwb_fma(-d2[2], t, nwb_fma(d1[2], s, rz));
   return nwb_fma(vz, vz, nwb_fma(vy, vy, vx * vx));
 }
-// segment A vs point pb
 template <class T>
 NWB_HD T seg_point_dist2(const T* pa, const T* d1, T inv_a, const T* pb) {
   T rx = pa[0] - pb[0], ry = pa[1] - pb[1], rz = pa[2] - pb[2];

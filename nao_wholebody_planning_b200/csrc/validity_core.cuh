@@ -172,9 +172,13 @@ NWB_HD ValidityResult<T> evaluate_config(const ValidityTables& tab, const T* q, 
     if constexpr (MARGINS) min_sep = nwb_min(min_sep, nwb_sqrt(d2) - rsum);
     else hit = nwb_or(hit, d2 < rsum * rsum);
   };
-  auto account2 = [&](T d2, T rsum, T rsum2) {   // (rA+rB)^2 known at compile time
-    if constexpr (MARGINS) min_sep = nwb_min(min_sep, nwb_sqrt(d2) - rsum);
-    else hit = nwb_or(hit, d2 < rsum2);
+  // compiled-in pair list: the pair's (rA+rB)^2 is an immediate, so the distance routine returns d^2 - (rA+rB)^2
+  // straight from its last multiply-add and contact = "the smallest of these is negative": one running minimum
+  // (the compiler fuses two updates into one 3-input FMNMX3) instead of one compare per pair
+  T worst = T(1e30f);
+  auto account2 = [&](T d2_biased, T rsum, T rsum2) {
+    if constexpr (MARGINS) min_sep = nwb_min(min_sep, nwb_sqrt(nwb_max(d2_biased + rsum2, T(0.f))) - rsum);
+    else worst = nwb_min(worst, d2_biased);
   };
   (void)account2;
   if constexpr (PAIRS == PAIRS_TABLE) {
@@ -233,20 +237,20 @@ NWB_HD ValidityResult<T> evaluate_config(const ValidityTables& tab, const T* q, 
       load3(st, SA, pa); load3(st, SA + 3, qa); load3(st, SB, pb); load3(st, SB + 3, qb);    \
       d1[0] = qa[0] - pa[0]; d1[1] = qa[1] - pa[1]; d1[2] = qa[2] - pa[2];                   \
       d2[0] = qb[0] - pb[0]; d2[1] = qb[1] - pb[1]; d2[2] = qb[2] - pb[2];                   \
-      account2(seg_seg_dist2(pa, d1, T(LA), T(ILA), pb, d2, T(LB), T(ILB)), T(RS), T(RS2)); \
+      account2(seg_seg_dist2(pa, d1, T(LA), T(ILA), pb, d2, T(LB), T(ILB), T(-(RS2))), T(RS), T(RS2)); \
     }
 #define NWB_X_CS(SA, LA, ILA, SB, LB, ILB, RS, RS2)                                        \
     {                                                                                        \
       T pa[3], qa[3], d1[3], pb[3];                                                          \
       load3(st, SA, pa); load3(st, SA + 3, qa); load3(st, SB, pb);                           \
       d1[0] = qa[0] - pa[0]; d1[1] = qa[1] - pa[1]; d1[2] = qa[2] - pa[2];                   \
-      account2(seg_point_dist2(pa, d1, T(ILA), pb), T(RS), T(RS2));                          \
+      account2(seg_point_dist2(pa, d1, T(ILA), pb, T(-(RS2))), T(RS), T(RS2));               \
     }
 #define NWB_X_SS(SA, LA, ILA, SB, LB, ILB, RS, RS2)                                        \
     {                                                                                        \
       T pa[3], pb[3];                                                                        \
       load3(st, SA, pa); load3(st, SB, pb);                                                  \
-      account2(point_point_dist2(pa, pb), T(RS), T(RS2));                                    \
+      account2(point_point_dist2(pa, pb, T(-(RS2))), T(RS), T(RS2));                         \
     }
     if constexpr (PAIRS == PAIRS_STATIC_GROUP) {
       NWB_PAIRS_CC_GROUP(NWB_X_CC)
@@ -260,6 +264,7 @@ NWB_HD ValidityResult<T> evaluate_config(const ValidityTables& tab, const T* q, 
 #undef NWB_X_CC
 #undef NWB_X_CS
 #undef NWB_X_SS
+    if constexpr (!MARGINS) hit = nwb_or(hit, worst < T(0.f));
   }
 
   // ---- environment: robot proxies against the scene boxes ---------------------------------------
