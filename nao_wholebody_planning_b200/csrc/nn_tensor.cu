@@ -26,6 +26,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 
 #include "tree_internal.h"
 
@@ -74,6 +75,28 @@ __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t
       "setp.ne.b32 p, %4, 0;\n"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kTcInstrDesc), "r"(accumulate)
+      : "memory");
+}
+// one lane of a fully converged warp (the others skip the guarded statement)
+__device__ __forceinline__ bool tc_elect_one() {
+  uint32_t is_elected;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n" : "=r"(is_elected));
+  return is_elected != 0;
+}
+// same MMA with N = 256: one instruction covers a PAIR of node tiles (consecutive tiles continue the 8-row group stride)
+constexpr uint32_t kTcInstrDesc256 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+__device__ __forceinline__ void tc_mma256(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kTcInstrDesc256), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -412,19 +435,314 @@ nn_tc_kernel(const unsigned char* __restrict__ tc, const double* __restrict__ ao
   if (tid == 0) tickets[blockIdx.y] = 0u;                    // ready for the next call
 }
 
+
+// =====================================================================================================================
+// Two-phase form (default).  The one-pass kernel above interleaves the filter with its exact candidates: a lane that
+// meets a new running minimum drags its warp - and, through the per-tile barrier, the CTA - into the candidate path,
+// which with 128 queries per CTA happened in nearly every tile (profiles/r02_nn_tc_onepass_*: 46 % of all warp time
+// waiting at that barrier).  Here the tensor-core pass does NOTHING but reduce:
+//
+//   phase A  nn_tc_min_kernel: a TMA thread, an MMA thread and 16 reduction warps, coupled only by mbarriers (stage
+//            landed / stage free / accumulator full / accumulator free) - no CTA-wide barrier in the loop.  A reduction
+//            thread reads 64 accumulator columns (one query x one half tile of 64 nodes), takes their minimum with a
+//            tree of FMNMX and stores that ONE float: chunk_min[half-tile row][query].  4 B per (query, 64 nodes).
+//   phase B  nn_tc_exact_kernel: per query, threshold = (smallest chunk minimum) + 2E; every chunk whose minimum is
+//            under it is evaluated exactly - 64 fp64 distances by one warp, the reference's rounding sequence - and
+//            folded lexicographically (distance, index).  The true nearest node n* has v(n*) <= v_min + 2E, so its chunk
+//            is always among them; so is every node that ties with it.  A flood of near ties only makes phase B longer.
+// =====================================================================================================================
+constexpr int TC2_EPI_WARPS = 16;
+constexpr int TC2_THREADS = (TC2_EPI_WARPS + 2) * 32;          // + TMA warp + MMA warp (one elected lane each)
+constexpr int TC2_DSTAGES = 3;                                 // ring of double stages: two consecutive node tiles (40 KB) each
+struct Tc2Smem {
+  static constexpr size_t kA = 0;
+  static constexpr size_t kB = kA + TC_TILE_BYTES;
+  static constexpr size_t kBars = kB + (size_t)TC2_DSTAGES * 2 * TC_TILE_BYTES;   // full[S] empty[S] done[2] accfree[2]
+  static constexpr size_t kMisc = kBars + 8 * (2 * TC2_DSTAGES + 4);
+  static constexpr size_t kBytes = kMisc + 16;
+};
+__device__ __forceinline__ void tc_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
+}
+
+// Node tiles are processed in PAIRS: one tcgen05.mma with N = 256 covers two consecutive tiles (their 8-row groups
+// continue at the same stride in shared memory), five K-steps per pair.  Two accumulator sets of 256 columns: the MMA
+// warp fills one while the 16 reduction warps read the other, so all 512 TMEM columns are in use.
+__global__ void __launch_bounds__(TC2_THREADS, 1)
+nn_tc_min_kernel(const unsigned char* __restrict__ tc, int64_t N, const double* __restrict__ q, int64_t nq, int64_t qp,
+                 float* __restrict__ chunk_min /*[tiles * 2][qp]: one row per half tile of 64 nodes*/, float* __restrict__ slice_min /*[slices * 4][qp]*/,
+                 float* __restrict__ debug_tile) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* a_tile = smem + Tc2Smem::kA;
+  unsigned char* b_ring = smem + Tc2Smem::kB;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Tc2Smem::kBars);
+  uint64_t* empty = full + TC2_DSTAGES;
+  uint64_t* done = empty + TC2_DSTAGES;
+  uint64_t* accfree = done + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Tc2Smem::kMisc);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int slice = blockIdx.x, n_slices = gridDim.x;
+  const int64_t q0 = (int64_t)blockIdx.y * TC_M;
+
+  if (tid == 0) {
+    for (int b = 0; b < TC2_DSTAGES; ++b) { tc_mbar_init(&full[b], 1); tc_mbar_init(&empty[b], 1); }
+    for (int b = 0; b < 2; ++b) { tc_mbar_init(&done[b], 1); tc_mbar_init(&accfree[b], TC2_EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // this slice's node tiles: a contiguous range of whole PAIRS (the copy holds one spare tile past the end of the tree)
+  const int64_t pairs_total = ((N + TC_N - 1) / TC_N + 1) / 2;
+  const int64_t per = (pairs_total + n_slices - 1) / n_slices;
+  const int64_t pair_lo = min(pairs_total, (int64_t)slice * per), pair_hi = min(pairs_total, pair_lo + per);
+  const int P = (int)(pair_hi - pair_lo);
+  if (tid < TC_M) {                                            // query row -> bf16 split (slot map: tree_internal.h)
+    const bool live = q0 + tid < nq;
+    __nv_bfloat16 row[TC_K];
+#pragma unroll
+    for (int j = 0; j < NWB_NJ; ++j) {
+      const float x = live ? (float)q[(q0 + tid) * NWB_NJ + j] : 0.f;
+      const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+      const __nv_bfloat16 mid = __float2bfloat16_rn(x - __bfloat162float(hi));
+      const __nv_bfloat16 hi2 = __float2bfloat16_rn(-2.f * __bfloat162float(hi));
+      const __nv_bfloat16 mid2 = __float2bfloat16_rn(-2.f * __bfloat162float(mid));
+      row[j] = hi2;
+      row[NWB_NJ + j] = hi2;
+      row[2 * NWB_NJ + j] = mid2;
+    }
+    row[63] = row[64] = row[65] = __float2bfloat16_rn(live ? 1.f : 0.f);
+#pragma unroll
+    for (int k = 66; k < TC_K; ++k) row[k] = __float2bfloat16_rn(0.f);
+    unsigned char* base = a_tile + (size_t)(tid >> 3) * (TC_KB * 128) + (size_t)(tid & 7) * 16;
+#pragma unroll
+    for (int kb = 0; kb < TC_KB; ++kb) *reinterpret_cast<uint4*>(base + kb * 128) = *reinterpret_cast<const uint4*>(&row[kb * 8]);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == TC2_EPI_WARPS) {                                 // ---- TMA thread: keeps the ring full --------------------
+    if (lane == 0)
+      for (int p = 0; p < P; ++p) {
+        const int stage = p % TC2_DSTAGES;
+        if (p >= TC2_DSTAGES) tc_mbar_wait(&empty[stage], (uint32_t)(((p / TC2_DSTAGES) - 1) & 1));
+        tc_mbar_expect_tx(&full[stage], 2 * TC_TILE_BYTES);
+        tc_bulk_g2s(b_ring + (size_t)stage * 2 * TC_TILE_BYTES, tc + (size_t)(pair_lo + p) * 2 * TC_TILE_BYTES, 2 * TC_TILE_BYTES,
+                    &full[stage]);
+      }
+  } else if (warp == TC2_EPI_WARPS + 1) {                      // ---- MMA warp ---------------------------------------------
+    // The whole warp runs the loop (waits included) and ONE elected lane issues: with warp-uniform control flow the
+    // descriptors live in uniform registers.  (Guarding the loop itself with lane == 0 made the compiler rebuild every
+    // operand through R2UR / ELECT sequences: ~160 cycles per issued MMA, four times the MMA itself.)
+    const uint64_t a_desc = tc_smem_desc(tc_smem_u32(a_tile));
+    for (int p = 0; p < P; ++p) {
+      const int stage = p % TC2_DSTAGES, set = p & 1;
+      tc_mbar_wait(&full[stage], (uint32_t)((p / TC2_DSTAGES) & 1));
+      if (p >= 2) tc_mbar_wait(&accfree[set], (uint32_t)(((p >> 1) - 1) & 1));
+      tc_fence_after();
+      const uint64_t b_desc = tc_smem_desc(tc_smem_u32(b_ring + (size_t)stage * 2 * TC_TILE_BYTES));
+      const uint32_t d0 = tmem_base + (uint32_t)(set * 2 * TC_N);
+      if (tc_elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < TC_K / 16; ++ks)                 // a K-step is 256 B further = 16 descriptor units
+          tc_mma256(d0, a_desc + ks * 16, b_desc + ks * 16, ks > 0 ? 1u : 0u);
+        tc_commit(&empty[stage]);                              // both arrive when the MMAs above have completed
+        tc_commit(&done[set]);
+      }
+      __syncwarp();
+    }
+  } else {                                                     // ---- 16 reduction warps ----------------------------------
+    // warp -> TMEM lane quadrant (its 32 queries) x one HALF TILE (64 accumulator columns = 64 nodes) of the pair;
+    // it stores ONE float per query and half tile: row (tile * 2 + half) of chunk_min
+    const int quad = warp & 3, part = warp >> 2, ql = quad * 32 + lane;      // part = tile-in-pair * 2 + half
+    float m_run = 3.0e38f;
+    float* out = chunk_min + ((size_t)pair_lo * 4 + part) * qp + q0 + ql;
+    for (int p = 0; p < P; ++p) {
+      const int set = p & 1;
+      tc_mbar_wait(&done[set], (uint32_t)((p >> 1) & 1));
+      tc_fence_after();
+      float v[2][32];
+      const uint32_t taddr = tmem_base + (uint32_t)(set * 2 * TC_N + part * 64) + ((uint32_t)(quad * 32) << 16);
+      tc_ld32(taddr, v[0]);
+      tc_ld32(taddr + 32, v[1]);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc_mbar_arrive(&accfree[set]);            // the accumulators may be overwritten: values are in registers
+      const int64_t n0 = (pair_lo + p) * 2 * TC_N + part * 64;
+      if (n0 + 64 > N) {                                       // tail of the tree: columns past the end never win
+#pragma unroll
+        for (int u = 0; u < 64; ++u)
+          if (n0 + u >= N) v[u >> 5][u & 31] = 3.0e38f;
+      }
+      if (debug_tile && slice == 0 && blockIdx.y == 0 && p == 0 && part < 2) {
+#pragma unroll
+        for (int u = 0; u < 64; ++u) debug_tile[ql * TC_N + part * 64 + u] = v[u >> 5][u & 31];
+      }
+      float r32[32];
+#pragma unroll
+      for (int u = 0; u < 32; ++u) r32[u] = fminf(v[0][u], v[1][u]);
+#pragma unroll
+      for (int u = 0; u < 16; ++u) r32[u] = fminf(r32[u], r32[u + 16]);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) r32[u] = fminf(r32[u], r32[u + 8]);
+      const float cm = fminf(fminf(fminf(r32[0], r32[1]), fminf(r32[2], r32[3])), fminf(fminf(r32[4], r32[5]), fminf(r32[6], r32[7])));
+      m_run = fminf(m_run, cm);
+      out[(size_t)p * 4 * qp] = cm;                            // 32 consecutive floats per warp: one 128-byte store
+    }
+    slice_min[((size_t)slice * 4 + part) * qp + q0 + ql] = m_run;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// Phase B.  One thread per query scans that query's chunk minima of a range of chunk rows, TC2_WINDOW rows at a time with
+// all loads of a window in flight (the scan is a 128 MB stream at 1024 x 10^6: memory-level parallelism is what it
+// needs); chunks under the threshold are listed, and between two windows the block evaluates the listed chunks
+// exactly, one warp per chunk.  The list holds a whole window (128 x TC2_WINDOW entries), so it cannot overflow.
+constexpr int TC2_WINDOW = 16;
+// threshold per query = smallest accumulator value over the whole tree + 2E (computed once, not once per block of phase B)
+__global__ void __launch_bounds__(TC_M)
+nn_tc_threshold_kernel(const float* __restrict__ slice_min, int n_slice_rows, int64_t qp, const unsigned* __restrict__ max_nn_bits,
+                       const double* __restrict__ q, int64_t nq, float* __restrict__ thr_out) {
+  const int64_t k = (int64_t)blockIdx.x * TC_M + threadIdx.x;
+  const bool live = k < nq;
+  float qnorm2 = 0.f;
+#pragma unroll
+  for (int j = 0; j < NWB_NJ; ++j) {
+    const float x = live ? (float)q[k * NWB_NJ + j] : 0.f;
+    qnorm2 = fmaf(x, x, qnorm2);
+  }
+  float vmin = 3.0e38f;
+#pragma unroll 8
+  for (int r = 0; r < n_slice_rows; ++r) vmin = fminf(vmin, slice_min[(size_t)r * qp + k]);
+  thr_out[k] = vmin + 2.f * tc_error_bound(sqrtf(qnorm2) * (1.f + 1e-6f), sqrtf(__uint_as_float(*max_nn_bits)));
+}
+
+__global__ void __launch_bounds__(TC_M)
+nn_tc_exact_kernel(const float* __restrict__ chunk_min, const float* __restrict__ thr_in, int n_slice_rows, int64_t chunk_rows,
+                   int64_t qp, const double* __restrict__ aos, const unsigned* __restrict__ max_nn_bits, int64_t N,
+                   const double* __restrict__ q, int64_t nq, double* __restrict__ part_d, int32_t* __restrict__ part_i,
+                   unsigned* __restrict__ tickets, int32_t* __restrict__ idx_out, double* __restrict__ dist_out) {
+  __shared__ unsigned long long best_key[TC_M], old_key[TC_M], cand_key[TC_M * TC2_WINDOW];
+  __shared__ int best_idx[TC_M], idx_tmp[TC_M], cand_idx[TC_M * TC2_WINDOW];
+  __shared__ int cand_row[TC_M * TC2_WINDOW];
+  __shared__ unsigned char cand_q[TC_M * TC2_WINDOW];
+  __shared__ int cand_n;
+  __shared__ bool last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int range = blockIdx.x, n_ranges = gridDim.x;
+  const int64_t q0 = (int64_t)blockIdx.y * TC_M;
+  const bool live = q0 + tid < nq;
+  const float thr = thr_in[q0 + tid];
+  (void)n_slice_rows;
+  (void)max_nn_bits;
+  best_key[tid] = 0x7FF0000000000000ull;
+  best_idx[tid] = -1;
+  if (tid == 0) cand_n = 0;
+  __syncthreads();
+  const int64_t per = (chunk_rows + n_ranges - 1) / n_ranges;
+  const int64_t r_lo = min(chunk_rows, (int64_t)range * per), r_hi = min(chunk_rows, r_lo + per);
+  const float* col = chunk_min + q0 + tid;
+  for (int64_t w0 = r_lo; w0 < r_hi; w0 += TC2_WINDOW) {
+    float v[TC2_WINDOW];
+#pragma unroll
+    for (int k = 0; k < TC2_WINDOW; ++k) v[k] = w0 + k < r_hi ? __ldcs(col + (size_t)(w0 + k) * qp) : 3.0e38f;   // streamed once
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < TC2_WINDOW; ++k)
+      if (v[k] <= thr && live) {
+        const int slot = atomicAdd(&cand_n, 1);
+        cand_row[slot] = (int)(w0 + k);
+        cand_q[slot] = (unsigned char)tid;
+        any = true;
+      }
+    if (!__syncthreads_or(any ? 1 : 0)) continue;              // nothing listed in this window (the common case)
+    const int n_c = cand_n;
+    old_key[tid] = best_key[tid];
+    idx_tmp[tid] = 0x7FFFFFFF;
+    __syncthreads();
+    for (int c = warp; c < n_c; c += TC_M / 32) {              // one warp per listed half tile: 64 exact distances
+      const int cq = cand_q[c];
+      unsigned long long key = 0x7FF0000000000000ull;
+      int idx = 0x7FFFFFFF;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int64_t node = (int64_t)cand_row[c] * 64 + h * 32 + lane;
+        if (node < N) {
+          const unsigned long long k = (unsigned long long)__double_as_longlong(tc_exact_dist(aos, q + (q0 + cq) * NWB_NJ, node));
+          if (k < key) { key = k; idx = (int)node; }           // ascending node order per lane: first minimum = lowest index
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {                       // lexicographic (distance, index) minimum of the warp
+        const unsigned long long k2 = __shfl_xor_sync(0xffffffffu, key, o);
+        const int i2 = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (k2 < key || (k2 == key && i2 < idx)) { key = k2; idx = i2; }
+      }
+      if (lane == 0) {
+        cand_key[c] = key;
+        cand_idx[c] = idx;
+        atomicMin(&best_key[cq], key);
+      }
+    }
+    __syncthreads();
+    for (int c = tid; c < n_c; c += TC_M)
+      if (cand_key[c] == best_key[cand_q[c]]) atomicMin(&idx_tmp[cand_q[c]], cand_idx[c]);
+    __syncthreads();
+    if (best_key[tid] < old_key[tid]) best_idx[tid] = idx_tmp[tid];
+    else if (idx_tmp[tid] != 0x7FFFFFFF && (best_idx[tid] < 0 || idx_tmp[tid] < best_idx[tid])) best_idx[tid] = idx_tmp[tid];
+    if (tid == 0) cand_n = 0;
+    __syncthreads();
+  }
+  if (live) {
+    part_d[(q0 + tid) * n_ranges + range] = __longlong_as_double((long long)best_key[tid]);
+    part_i[(q0 + tid) * n_ranges + range] = best_idx[tid];
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) last = atomicAdd(&tickets[blockIdx.y], 1u) == (unsigned)n_ranges - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  if (live) {
+    double d = 10000.0;                                        // RP:347: best_norm starts at 10000.0, strict <
+    int i = -1;
+    for (int s0 = 0; s0 < n_ranges; s0 += 8) {                 // 8 partials in flight: the fold is a chain of L2 round trips
+      double ds[8];
+      int is[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const bool in = s0 + k < n_ranges;
+        ds[k] = in ? part_d[(q0 + tid) * n_ranges + s0 + k] : 0.0;
+        is[k] = in ? part_i[(q0 + tid) * n_ranges + s0 + k] : -1;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (is[k] >= 0 && (ds[k] < d || (ds[k] == d && i >= 0 && is[k] < i))) { d = ds[k]; i = is[k]; }
+    }
+    idx_out[q0 + tid] = i;
+    if (dist_out) dist_out[q0 + tid] = d;
+  }
+  if (tid == 0) tickets[blockIdx.y] = 0u;
+}
+
 }  // namespace nwb
 
 using namespace nwb;
 
-cudaError_t nn_tc_launch(nwb_tree* t, const double* q_dev, int64_t nq, int32_t* idx_dev, double* dist_dev, float* debug_tile,
-                         int* n_launches) {
-  const int64_t groups = (nq + TC_M - 1) / TC_M;
-  const int64_t tiles = (t->size + TC_N - 1) / TC_N;
-  const int sm = std::max(1, t->ctx->sm_count);
-  // one CTA per SM (the shared-memory ring allows no more): slices x groups fills the machine once
-  int64_t slices = std::max<int64_t>(1, sm / std::min<int64_t>(groups, sm));
-  slices = std::max<int64_t>(1, std::min(slices, tiles));
-  const size_t need = (size_t)groups * TC_M * slices;
+static cudaError_t nn_tc_onepass_launch(nwb_tree* t, const double* q_dev, int64_t nq, int32_t* idx_dev, double* dist_dev,
+                                        float* debug_tile, int* n_launches);
+
+static cudaError_t tc_reserve_partials(nwb_tree* t, size_t need, size_t groups, cudaStream_t s) {
   cudaError_t e;
   if (need > t->part_cap) {
     if (t->part_d) cudaFree(t->part_d);
@@ -436,16 +754,83 @@ cudaError_t nn_tc_launch(nwb_tree* t, const double* q_dev, int64_t nq, int32_t* 
     if ((e = cudaMalloc(&t->part_i, sizeof(int32_t) * need)) != cudaSuccess) return e;
     t->part_cap = need;
   }
-  cudaStream_t s = t->ctx->stream;
-  if ((size_t)groups > t->ticket_cap) {
+  if (groups > t->ticket_cap) {
     if (t->tickets) cudaFree(t->tickets);
     t->tickets = nullptr;
     t->ticket_cap = 0;
-    const size_t cap = std::max<size_t>((size_t)groups, 1024);
+    const size_t cap = std::max<size_t>(groups, 1024);
     if ((e = cudaMalloc(&t->tickets, sizeof(unsigned) * cap)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(t->tickets, 0, sizeof(unsigned) * cap, s)) != cudaSuccess) return e;
     t->ticket_cap = cap;
   }
+  return cudaSuccess;
+}
+
+// Two-phase batched scan (see above).  Query groups are worked through in waves so that the chunk-minimum buffer
+// (4 B per query and 64 nodes) stays under 1 GiB whatever the batch.
+cudaError_t nn_tc_launch(nwb_tree* t, const double* q_dev, int64_t nq, int32_t* idx_dev, double* dist_dev, float* debug_tile,
+                         int* n_launches) {
+  static const bool onepass = getenv("NWB_NN_TC_ONEPASS") != nullptr;
+  if (onepass) return nn_tc_onepass_launch(t, q_dev, nq, idx_dev, dist_dev, debug_tile, n_launches);
+  const int64_t groups = (nq + TC_M - 1) / TC_M;
+  const int64_t pairs = std::max<int64_t>(1, ((t->size + TC_N - 1) / TC_N + 1) / 2);   // node tiles go through the MMA in pairs
+  const int64_t tiles = pairs;                                                            // (scheduling unit of phase A)
+  const int64_t chunk_rows = pairs * 4;                                                   // one row per half tile (64 nodes)
+  const int sm = std::max(1, t->ctx->sm_count);
+  const size_t bytes_per_group = (size_t)chunk_rows * TC_M * sizeof(float);
+  const int64_t wave = std::max<int64_t>(1, std::min<int64_t>(groups, (int64_t)(((size_t)1 << 30) / bytes_per_group)));
+  const int64_t wave_use = std::min<int64_t>(wave, 65535);
+  const int64_t slices = std::max<int64_t>(1, std::min<int64_t>(tiles, sm / std::min<int64_t>(wave_use, sm)));
+  const int64_t ranges = std::max<int64_t>(1, std::min<int64_t>((chunk_rows + TC2_WINDOW - 1) / TC2_WINDOW, (4 * sm + wave_use - 1) / wave_use));
+  const int64_t qp = wave_use * TC_M;
+  cudaStream_t s = t->ctx->stream;
+  cudaError_t e;
+  const size_t need_chunk = (size_t)chunk_rows * qp * sizeof(float), need_slice = (size_t)(slices * 4 + 1) * qp * sizeof(float);
+  if (need_chunk + need_slice > t->tc_scratch_bytes) {
+    if (t->tc_scratch) cudaFree(t->tc_scratch);
+    t->tc_scratch = nullptr;
+    t->tc_scratch_bytes = 0;
+    if ((e = cudaMalloc(&t->tc_scratch, need_chunk + need_slice)) != cudaSuccess) return e;
+    t->tc_scratch_bytes = need_chunk + need_slice;
+  }
+  float* chunk_min = reinterpret_cast<float*>(t->tc_scratch);
+  float* slice_min = reinterpret_cast<float*>(static_cast<char*>(t->tc_scratch) + need_chunk);
+  if ((e = tc_reserve_partials(t, (size_t)wave_use * TC_M * ranges, (size_t)wave_use, s)) != cudaSuccess) return e;
+  static std::atomic<bool> configured[64];
+  const int dev = t->ctx->device >= 0 && t->ctx->device < 64 ? t->ctx->device : 0;
+  if (!configured[dev].load(std::memory_order_relaxed)) {
+    if ((e = cudaFuncSetAttribute(nn_tc_min_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tc2Smem::kBytes)) != cudaSuccess) return e;
+    configured[dev].store(true, std::memory_order_relaxed);
+  }
+  int launches = 0;
+  for (int64_t g0 = 0; g0 < groups; g0 += wave_use) {
+    const int64_t ng = std::min<int64_t>(wave_use, groups - g0);
+    const int64_t qoff = g0 * TC_M;
+    nn_tc_min_kernel<<<dim3((unsigned)slices, (unsigned)ng), TC2_THREADS, Tc2Smem::kBytes, s>>>(
+        t->tc, t->size, q_dev + qoff * NWB_NJ, nq - qoff, qp, chunk_min, slice_min, debug_tile);
+    float* thr = slice_min + (size_t)slices * 4 * qp;
+    nn_tc_threshold_kernel<<<(unsigned)ng, TC_M, 0, s>>>(slice_min, (int)(slices * 4), qp, t->max_nn, q_dev + qoff * NWB_NJ, nq - qoff, thr);
+    nn_tc_exact_kernel<<<dim3((unsigned)ranges, (unsigned)ng), TC_M, 0, s>>>(
+        chunk_min, thr, (int)(slices * 4), (((t->size + TC_N - 1) / TC_N + 1) / 2) * 4, qp, t->aos, t->max_nn, t->size, q_dev + qoff * NWB_NJ, nq - qoff,
+        t->part_d, t->part_i, t->tickets, idx_dev + qoff, dist_dev ? dist_dev + qoff : nullptr);
+    launches += 3;
+    debug_tile = nullptr;
+  }
+  if (n_launches) *n_launches = launches;
+  return cudaGetLastError();
+}
+
+static cudaError_t nn_tc_onepass_launch(nwb_tree* t, const double* q_dev, int64_t nq, int32_t* idx_dev, double* dist_dev,
+                                        float* debug_tile, int* n_launches) {
+  const int64_t groups = (nq + TC_M - 1) / TC_M;
+  const int64_t tiles = (t->size + TC_N - 1) / TC_N;
+  const int sm = std::max(1, t->ctx->sm_count);
+  // one CTA per SM (the shared-memory ring allows no more): slices x groups fills the machine once
+  int64_t slices = std::max<int64_t>(1, sm / std::min<int64_t>(groups, sm));
+  slices = std::max<int64_t>(1, std::min(slices, tiles));
+  cudaStream_t s = t->ctx->stream;
+  cudaError_t e;
+  if ((e = tc_reserve_partials(t, (size_t)groups * TC_M * slices, (size_t)groups, s)) != cudaSuccess) return e;
   static std::atomic<bool> configured[64];
   const int dev = t->ctx->device >= 0 && t->ctx->device < 64 ? t->ctx->device : 0;
   if (!configured[dev].load(std::memory_order_relaxed)) {

@@ -716,7 +716,7 @@ int tree_reserve(nwb_tree* t, int64_t need) {
   double* aos = nullptr;
   int32_t* pred = nullptr;
   unsigned char* tc = nullptr;
-  const size_t tc_bytes = (size_t)(cap / TC_N) * TC_TILE_BYTES;
+  const size_t tc_bytes = (size_t)(cap / TC_N + 1) * TC_TILE_BYTES;   // + one spare tile: the scan reads tiles in pairs
   TREE_CUDA(t, cudaMalloc(&soa, sizeof(float) * NWB_NJ * cap));
   TREE_CUDA(t, cudaMalloc(&aos, sizeof(double) * NWB_NJ * cap));
   TREE_CUDA(t, cudaMalloc(&pred, sizeof(int32_t) * cap));
@@ -898,6 +898,7 @@ void nwb_tree_destroy(nwb_tree* t) {
   cudaFree(t->pred);
   cudaFree(t->tc);
   cudaFree(t->max_nn);
+  cudaFree(t->tc_scratch);
   cudaFree(t->part_d);
   cudaFree(t->part_i);
   cudaFree(t->tickets);

@@ -34,6 +34,8 @@ struct nwb_tree {
   int32_t* pred = nullptr;
   unsigned char* tc = nullptr;   // tensor-core scan copy: ceil(cap / 128) tiles of 20480 B (see above)
   unsigned* max_nn = nullptr;    // float bits of max |node|^2 over the tree (error bound of the tensor-core scan)
+  void* tc_scratch = nullptr;    // chunk minima + slice minima of the two-phase tensor-core scan (grow-only)
+  size_t tc_scratch_bytes = 0;
   // scratch
   double* part_d = nullptr;
   int32_t* part_i = nullptr;
