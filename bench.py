@@ -245,7 +245,7 @@ def run_sections(args, torch, dist, nwb, ctx, dev, rank, world, barrier, ffma_tf
         nodes_all, n_proj = BS.v1c_nodes(nwb, ctx, OL, 1_000_000)
         prep_s = time.perf_counter() - t0
         guarded("validity_scenes", lambda: BS.section_validity_scenes(torch, nwb, OL, orc, stream, dev, ffma_tflops, rf, cpu))
-        guarded("nn_scan", lambda: BS.section_nn_scan(torch, nwb, ctx, OL, orc, stream, dev, nodes_all, hbm, ffma_tflops, flush))
+        guarded("nn_scan", lambda: BS.section_nn_scan(torch, nwb, ctx, OL, orc, stream, dev, nodes_all, hbm, peaks.get("bf16_tflops") or 1650.7, flush))
         guarded("edge_check", lambda: BS.section_edge_check(torch, nwb, ctx, OL, orc, stream, dev, nodes_all, ffma_tflops,
                                                             rf.get("collision_only_S0_all_pairs_flops_per_config", 0)))
         ctx.set_stream(None)

@@ -100,7 +100,7 @@ def section_validity_scenes(torch, nwb, OL, orc, stream, dev, ffma_tflops, rf, c
     return out
 
 
-def section_nn_scan(torch, nwb, ctx, OL, orc, stream, dev, nodes_all, hbm_gbs, ffma_tflops, flush, quick=False):
+def section_nn_scan(torch, nwb, ctx, OL, orc, stream, dev, nodes_all, hbm_gbs, bf16_tflops, flush, quick=False):
     queries = db_queries(OL)
     with torch.cuda.stream(stream):
         q_dev = torch.from_numpy(queries).to(dev)
@@ -136,12 +136,18 @@ def section_nn_scan(torch, nwb, ctx, OL, orc, stream, dev, nodes_all, hbm_gbs, f
                 rec["roofline"] = {"bound": "hbm", "achieved": gbs, "peak": hbm_gbs, "unit": "GB/s", "frac": gbs / hbm_gbs,
                                    "bytes_per_launch": 84.0 * n, "note": "84 B/node (fp32 SoA scan copy), L2 flushed before every launch"}
             else:
-                # the distance matrix is a (Q x 21) . (21 x N) contraction: 2 flop per multiply-add, K = 21
+                # the distance matrix is a (Q x 21) . (21 x N) contraction (2 flop per multiply-add, K = 21) and runs on the
+                # tensor cores: tcgen05.mma over bf16 hi/mid splits, K padded to 80 slots (nn_tensor.cu)
                 tf = 2.0 * 21 * nq * n / (ms * 1e-3) / 1e12
-                rec["roofline"] = {"bound": "fp32", "achieved": 1.5 * tf, "peak": ffma_tflops, "unit": "TFLOP/s",
-                                   "frac": 1.5 * tf / ffma_tflops, "contraction_tflops": tf,
-                                   "note": "CUDA-core form: subtract + fma per (query, node, joint) = 3 flop; contraction_tflops "
-                                           "counts the 2 flop of the multiply-add only"}
+                rec["roofline"] = {"bound": "tensor", "achieved": tf, "peak": bf16_tflops, "unit": "TFLOP/s", "frac": tf / bf16_tflops,
+                                   "executed_tflops": tf * 80 / 21,
+                                   "peak_source": "MEASURED_PEAKS.json bf16_tflops (cuBLAS 8192^3, burst)",
+                                   "tmem_read_floor_ms": 4.0 * nq * n / (148 * 120.0 * 1.965e9) * 1e3,
+                                   "note": "algorithmic contraction flops 2*21*Q*N; the kernel executes K = 80 bf16 slots per pair "
+                                           "(three cross terms of the hi/mid split + |n|^2) = executed_tflops.  With K this short the "
+                                           "tensor pipe is not the binding resource: every accumulator element (4 B) has to be read "
+                                           "out of tensor memory once, and the 16 reduction warps drain ~120 B per clock and SM "
+                                           "(tmem_read_floor_ms); phase B (exact refinement) adds the rest"}
             out.append(rec)
         tree.close()
     return out

@@ -468,6 +468,13 @@ __device__ __forceinline__ void tc_mbar_arrive(uint64_t* bar) {
 // Node tiles are processed in PAIRS: one tcgen05.mma with N = 256 covers two consecutive tiles (their 8-row groups
 // continue at the same stride in shared memory), five K-steps per pair.  Two accumulator sets of 256 columns: the MMA
 // warp fills one while the 16 reduction warps read the other, so all 512 TMEM columns are in use.
+//
+// What bounds it (measured, profiles/r02_nn_tc_*): every accumulator element has to come out of tensor memory once -
+// 128 lanes x 256 columns x 4 B = 128 KB per pair - and the 16 warps drain it at ~120 B per clock and SM, i.e. ~1100
+// cycles per pair against 640 cycles of MMA (K = 80 is short).  A variant with TWO query groups per CTA (half the L2
+// stream per MMA) measured the same ~1200 cycles per 128 KB of accumulator and was dropped: the pass is TMEM-read bound,
+// 1024 x 10^6 = 4.2 GB of accumulator through 148 x ~120 B/clk = ~115 us.  (sm_103 has tcgen05.ld.red, a TMEM load with
+// a fused min; sm_100a does not.)
 __global__ void __launch_bounds__(TC2_THREADS, 1)
 nn_tc_min_kernel(const unsigned char* __restrict__ tc, int64_t N, const double* __restrict__ q, int64_t nq, int64_t qp,
                  float* __restrict__ chunk_min /*[tiles * 2][qp]: one row per half tile of 64 nodes*/, float* __restrict__ slice_min /*[slices * 4][qp]*/,
