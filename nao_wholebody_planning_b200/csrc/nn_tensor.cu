@@ -590,14 +590,17 @@ nn_tc_min_kernel(const unsigned char* __restrict__ tc, int64_t N, const double* 
 #pragma unroll
         for (int u = 0; u < 64; ++u) debug_tile[ql * TC_N + part * 64 + u] = v[u >> 5][u & 31];
       }
-      float r32[32];
+      // minimum of the 64 values as a tree of 3-input minima (FMNMX3: the min runs on the half-rate ALU pipe, which a
+      // 2-input tree kept 60 % busy - profiles/r02_nn_tc_min_metrics.txt): 64 -> 22 -> 8 -> 3 -> 1
+      float a[22];
 #pragma unroll
-      for (int u = 0; u < 32; ++u) r32[u] = fminf(v[0][u], v[1][u]);
+      for (int u = 0; u < 21; ++u) a[u] = fminf(fminf(v[0][u], v[1][u]), (u < 11 ? v[0][21 + u] : v[1][10 + u]));
+      a[21] = v[1][31];
+      float b8[8];
 #pragma unroll
-      for (int u = 0; u < 16; ++u) r32[u] = fminf(r32[u], r32[u + 16]);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) r32[u] = fminf(r32[u], r32[u + 8]);
-      const float cm = fminf(fminf(fminf(r32[0], r32[1]), fminf(r32[2], r32[3])), fminf(fminf(r32[4], r32[5]), fminf(r32[6], r32[7])));
+      for (int u = 0; u < 7; ++u) b8[u] = fminf(fminf(a[3 * u], a[3 * u + 1]), a[3 * u + 2]);
+      b8[7] = a[21];
+      const float cm = fminf(fminf(fminf(b8[0], b8[1]), b8[2]), fminf(fminf(b8[3], b8[4]), fminf(fminf(b8[5], b8[6]), b8[7])));
       m_run = fminf(m_run, cm);
       out[(size_t)p * 4 * qp] = cm;                            // 32 consecutive floats per warp: one 128-byte store
     }
