@@ -39,7 +39,7 @@ __global__ void tree_append_kernel(const double* __restrict__ src, const int32_t
   int j = (int)(e - i * NWB_NJ);
   double v = src[e];
   aos[(size + i) * NWB_NJ + j] = v;
-  soa[(int64_t)j * cap + size + i] = (float)v;
+  soa[soa_index(size + i, j)] = (float)v;
   if (j == 0) pred[size + i] = pred_src ? pred_src[i] : -1;
 }
 
@@ -170,13 +170,12 @@ nn_scan_kernel(const float* __restrict__ soa, const double* __restrict__ aos, in
   __syncthreads();
 
   const int64_t tiles = (N + TILE - 1) / TILE;
-  auto issue = [&](int64_t tile, int stage) {          // thread 0: 21 row copies of one tile
+  auto issue = [&](int64_t tile, int stage) {          // thread 0: the tile's blocks are consecutive: ONE bulk copy
     const int64_t n0 = tile * TILE;
-    const int64_t cnt = min((int64_t)TILE, ((N - n0) + 3) & ~(int64_t)3);   // rows are padded to 64 nodes
-    const uint32_t bytes = (uint32_t)(cnt * sizeof(float));
-    nn_mbar_expect_tx(&bars[stage], bytes * NWB_NJ);
-    float* dst = ring + (size_t)stage * NWB_NJ * TILE;
-    for (int j = 0; j < NWB_NJ; ++j) nn_bulk_g2s(dst + j * TILE, soa + (int64_t)j * cap + n0, bytes, &bars[stage]);
+    const int64_t blocks = min((int64_t)(TILE / SOA_BLK), (N - n0 + SOA_BLK - 1) / SOA_BLK);
+    const uint32_t bytes = (uint32_t)(blocks * SOA_BLK_FLOATS * sizeof(float));
+    nn_mbar_expect_tx(&bars[stage], bytes);
+    nn_bulk_g2s(ring + (size_t)stage * NWB_NJ * TILE, soa + (size_t)(n0 / SOA_BLK) * SOA_BLK_FLOATS, bytes, &bars[stage]);
   };
   if (tid == 0)
     for (int sg = 0; sg < STAGES; ++sg) {
@@ -211,12 +210,15 @@ nn_scan_kernel(const float* __restrict__ soa, const double* __restrict__ aos, in
 #pragma unroll
     for (int j = 0; j < NWB_NJ; ++j) {
       float2 x2[NPT / 2];
+      // shared-memory image of a tile = its blocks one after the other: [block][21][128]
+      constexpr int PER_BLK = SOA_BLK / NPT;             // threads per block of 128 nodes
+      const float* xb = x + ((tid / PER_BLK) * NWB_NJ + j) * SOA_BLK + (tid % PER_BLK) * NPT;
       if constexpr (NPT == 4) {
-        const float4 v = *reinterpret_cast<const float4*>(&x[j * TILE + 4 * tid]);
+        const float4 v = *reinterpret_cast<const float4*>(xb);
         x2[0] = make_float2(v.x, v.y);
         x2[1] = make_float2(v.z, v.w);
       } else {
-        x2[0] = *reinterpret_cast<const float2*>(&x[j * TILE + 2 * tid]);
+        x2[0] = *reinterpret_cast<const float2*>(xb);
       }
 #pragma unroll
       for (int k = 0; k < QT; ++k) {
@@ -347,7 +349,7 @@ nn_scan_kernel(const float* __restrict__ soa, const double* __restrict__ aos, in
         for (int k = 0; k < QT; ++k) {
           float sv = 0.f;
           for (int j = 0; j < NWB_NJ; ++j) {
-            float d = qf[k][j] - soa[(int64_t)j * cap + node];
+            float d = qf[k][j] - soa[soa_index(node, j)];
             sv = fmaf(d, d, sv);
           }
           if (sv <= nn_candidate_bound(__uint_as_float(run_min[k]))) {
@@ -548,9 +550,9 @@ nn_stream_kernel(const float* __restrict__ soa, const double* __restrict__ aos, 
   __shared__ int red_i[NN2_THREADS / 32];
   __shared__ bool last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // contiguous node range of this CTA, boundaries on multiples of 4 nodes (16-byte bulk copies)
-  const int64_t quads = (N + 3) >> 2;
-  const int64_t lo = (quads * blockIdx.x / gridDim.x) << 2, hi = min(N, (quads * (blockIdx.x + 1) / gridDim.x) << 2);
+  // contiguous node range of this CTA, boundaries on whole blocks of 128 nodes (the unit of the blocked copy)
+  const int64_t nblk = (N + SOA_BLK - 1) / SOA_BLK;
+  const int64_t lo = (nblk * blockIdx.x / gridDim.x) * SOA_BLK, hi = min(N, (nblk * (blockIdx.x + 1) / gridDim.x) * SOA_BLK);
   const int tiles = (int)((hi - lo + NN2_TILE - 1) / NN2_TILE);
   if (tid == 0) {
     for (int sg = 0; sg < NN2_STAGES; ++sg) nn_mbar_init(&bars[sg], 1);
@@ -559,14 +561,14 @@ nn_stream_kernel(const float* __restrict__ soa, const double* __restrict__ aos, 
     cand_n = 0;
   }
   __syncthreads();
-  auto issue = [&](int tile, int stage) {              // warp 0: lane j < 21 copies row j of the tile
+  auto issue = [&](int tile, int stage) {              // one bulk copy per tile: its blocks of 128 nodes are consecutive
     const int64_t t0 = lo + (int64_t)tile * NN2_TILE;
-    const int64_t cnt = min((int64_t)NN2_TILE, ((hi - t0) + 3) & ~(int64_t)3);   // rows are padded to 64 nodes
-    const uint32_t bytes = (uint32_t)(cnt * sizeof(float));
-    if (lane == 0) nn_mbar_expect_tx(&bars[stage], bytes * NWB_NJ);
-    __syncwarp();
-    if (lane < NWB_NJ)
-      nn_bulk_g2s(ring + ((size_t)stage * NWB_NJ + lane) * NN2_TILE, soa + (int64_t)lane * cap + t0, bytes, &bars[stage]);
+    const int64_t blocks = min((int64_t)(NN2_TILE / SOA_BLK), (hi - t0 + SOA_BLK - 1) / SOA_BLK);
+    const uint32_t bytes = (uint32_t)(blocks * SOA_BLK_FLOATS * sizeof(float));
+    if (lane == 0) {
+      nn_mbar_expect_tx(&bars[stage], bytes);
+      nn_bulk_g2s(ring + (size_t)stage * NWB_NJ * NN2_TILE, soa + (size_t)(t0 / SOA_BLK) * SOA_BLK_FLOATS, bytes, &bars[stage]);
+    }
   };
   if (warp == 0)
     for (int sg = 0; sg < NN2_STAGES && sg < tiles; ++sg) issue(sg, sg);
@@ -587,7 +589,7 @@ nn_stream_kernel(const float* __restrict__ soa, const double* __restrict__ aos, 
     float2 s2 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < NWB_NJ; ++j) {
-      const float2 d = __fadd2_rn(*reinterpret_cast<const float2*>(&x[j * NN2_TILE + 2 * tid]), qn2[j]);
+      const float2 d = __fadd2_rn(*reinterpret_cast<const float2*>(&x[((tid >> 6) * NWB_NJ + j) * SOA_BLK + 2 * (tid & 63)]), qn2[j]);
       s2 = __ffma2_rn(d, d, s2);
     }
     const int64_t node0 = t0 + 2 * tid;
@@ -650,7 +652,7 @@ nn_stream_kernel(const float* __restrict__ soa, const double* __restrict__ aos, 
     for (int64_t node = lo + tid; node < hi; node += NN2_THREADS) {
       float sv = 0.f;
       for (int j = 0; j < NWB_NJ; ++j) {
-        const float e = (float)qd[j] - soa[(int64_t)j * cap + node];
+        const float e = (float)qd[j] - soa[soa_index(node, j)];
         sv = fmaf(e, e, sv);
       }
       if (sv <= fbound) {
@@ -723,14 +725,15 @@ int tree_reserve(nwb_tree* t, int64_t need) {
   TREE_CUDA(t, cudaMalloc(&tc, tc_bytes));
   cudaStream_t s = t->ctx->stream;
   TREE_CUDA(t, cudaMemsetAsync(tc, 0, tc_bytes, s));    // rows past the end of the tree hold finite values
+  TREE_CUDA(t, cudaMemsetAsync(soa, 0, sizeof(float) * NWB_NJ * cap, s));
   if (!t->max_nn) {
     TREE_CUDA(t, cudaMalloc(&t->max_nn, sizeof(unsigned)));
     TREE_CUDA(t, cudaMemsetAsync(t->max_nn, 0, sizeof(unsigned), s));
   }
   if (t->size > 0) {
     TREE_CUDA(t, cudaMemcpyAsync(tc, t->tc, (size_t)((t->size + TC_N - 1) / TC_N) * TC_TILE_BYTES, cudaMemcpyDeviceToDevice, s));
-    TREE_CUDA(t, cudaMemcpy2DAsync(soa, sizeof(float) * cap, t->soa, sizeof(float) * t->cap, sizeof(float) * t->size, NWB_NJ,
-                                   cudaMemcpyDeviceToDevice, s));
+    TREE_CUDA(t, cudaMemcpyAsync(soa, t->soa, sizeof(float) * SOA_BLK_FLOATS * (size_t)((t->size + SOA_BLK - 1) / SOA_BLK),
+                                 cudaMemcpyDeviceToDevice, s));
     TREE_CUDA(t, cudaMemcpyAsync(aos, t->aos, sizeof(double) * NWB_NJ * t->size, cudaMemcpyDeviceToDevice, s));
     TREE_CUDA(t, cudaMemcpyAsync(pred, t->pred, sizeof(int32_t) * t->size, cudaMemcpyDeviceToDevice, s));
   }
@@ -969,10 +972,10 @@ int64_t nwb_nn_scan_owner(const nwb_tree* t, int64_t nq, int64_t node) {
   if (nq == 1) {
     if (t->size <= kNnSmallMax) return node;                              // exact kernel: one node per thread
     const int64_t blocks = std::max<int64_t>(1, std::min<int64_t>(t->ctx->sm_count, (t->size + NN2_TILE - 1) / NN2_TILE));
-    const int64_t quads = (t->size + 3) >> 2;
+    const int64_t nblk = (t->size + SOA_BLK - 1) / SOA_BLK;
     int64_t b = 0;                                                        // contiguous ranges (nn_stream_kernel)
-    while (b + 1 < blocks && ((quads * (b + 1) / blocks) << 2) <= node) ++b;
-    const int64_t lo = (quads * b / blocks) << 2;
+    while (b + 1 < blocks && (nblk * (b + 1) / blocks) * SOA_BLK <= node) ++b;
+    const int64_t lo = (nblk * b / blocks) * SOA_BLK;
     return b * NN2_THREADS + ((node - lo) % NN2_TILE) / 2;
   }
   if (nq >= 32) return (node % TC_N) / 32 * TC_M + 0;                     // tensor-core path: a thread per (query, 32-column chunk)
