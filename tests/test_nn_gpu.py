@@ -203,6 +203,35 @@ def test_tensor_core_path_ragged_query_counts(ctx, oracle, nq):
     t.close()
 
 
+def test_nn_randomised_stress_all_forms(ctx, oracle):
+    """Random tree sizes / query counts / data shapes through every form of the operator (exact small-tree kernel, fp32
+    stream, CUDA-core groups, tensor cores), trees grown in random pieces: always the oracle's answer."""
+    rng = np.random.default_rng(2026)
+    for case in range(28):
+        n = int(rng.choice([1, 5, 127, 128, 129, 255, 257, 1000, 4097, 20000, 70001, 131073]))
+        nq = int(rng.choice([1, 2, 9, 31, 32, 33, 127, 128, 129, 200, 257, 600]))
+        kind = case % 3
+        if kind == 0:
+            nodes = OL.uniform_configs(n, seed=3000 + case, lhyp_zero=True)
+            q = OL.uniform_configs(nq, seed=4000 + case)
+        elif kind == 1:
+            nodes = OL.noisy_db_configs(n, seed=3000 + case, sigma=0.03)
+            q = OL.noisy_db_configs(nq, seed=4000 + case, sigma=0.01)
+        else:                                    # heavy duplication: exact ties everywhere
+            base = OL.uniform_configs(max(1, n // 7), seed=3000 + case)
+            nodes = base[rng.integers(0, len(base), n)]
+            q = base[rng.integers(0, len(base), nq)] + (rng.random((nq, 1)) < 0.5) * 1e-7
+        t = nwb.Tree(ctx, 16)
+        cut = sorted(rng.integers(0, n + 1, 2))
+        for a, b in ((0, cut[0]), (cut[0], cut[1]), (cut[1], n)):
+            if b > a:
+                t.add(nodes[a:b])
+        idx, dist = t.findNearestNeighbour(q)
+        t.close()
+        o_idx, o_dist = oracle.nearest_neighbour(nodes, q, threads=oracle.threads)
+        assert (idx == o_idx).all() and np.abs(dist - o_dist).max() < 1e-12, (case, n, nq, kind)
+
+
 def test_nn_empty_tree_and_far_nodes(ctx):
     t = nwb.Tree(ctx)
     idx, dist = t.findNearestNeighbour(np.zeros((3, 21)))
