@@ -159,6 +159,187 @@ validity_kernel(const __grid_constant__ ValidityTables tab, const QT* __restrict
   }
 }
 
+// ---- large scenes: hierarchy walk per thread, exact tests through a CTA-wide work queue ----------
+// The per-thread walk above runs every (link, box) exact test of every leaf its robot bounding box reaches, and in a
+// warp of unrelated configurations a conservative per-link cull saves nothing: some lane always needs the test.  Here
+// the exact tests are COMPACTED instead.  Each round every thread advances its own walk to the next leaf whose bounds
+// its robot box reaches, culls that box against the bounding sphere of each tested link (mid point, half length +
+// radius + slack) and pushes the survivors as (owner, link, box) words onto a queue in shared memory; the CTA then
+// deals the queue over all its threads, so every lane runs an exact test that is actually needed, reading the owner's
+// link end points from the CTA's point table in shared memory.  The verdict is the same as the per-thread walk's:
+// the exact test is the same arithmetic and the cull only drops tests that cannot report contact.
+#ifndef NWB_SCENE_MINB
+#define NWB_SCENE_MINB 3
+#endif
+#ifndef NWB_SCENE_STAGED
+#define NWB_SCENE_STAGED 256
+#endif
+constexpr int kSceneStaged = NWB_SCENE_STAGED;                 // hierarchy nodes staged in shared memory by this kernel
+constexpr int kSceneQueueCap = NT * nwbm::kNumGeom;            // one leaf per thread and round: at most every link of every thread
+
+__device__ __forceinline__ bool scene_link_hits_box(const float* pts, const EnvLink& el, const SceneBox& bx) {
+  // exact capsule-box / sphere-box test: the arithmetic of evaluate_config's environment test
+  SmemStore st{const_cast<float*>(pts)};
+  const float H[3] = {bx.h[0], bx.h[1], bx.h[2]};
+  float pa[3], A[3];
+  load3(st, el.off, pa);
+  const float rx = pa[0] - bx.c[0], ry = pa[1] - bx.c[1], rz = pa[2] - bx.c[2];
+  A[0] = fmaf(bx.r[6], rz, fmaf(bx.r[3], ry, bx.r[0] * rx));
+  A[1] = fmaf(bx.r[7], rz, fmaf(bx.r[4], ry, bx.r[1] * rx));
+  A[2] = fmaf(bx.r[8], rz, fmaf(bx.r[5], ry, bx.r[2] * rx));
+  float d2;
+  if (el.is_sphere) {
+    const float ex = box_excess(A[0], H[0]), ey = box_excess(A[1], H[1]), ez = box_excess(A[2], H[2]);
+    d2 = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
+  } else {
+    float qa[3], D[3];
+    load3(st, el.off + 3, qa);
+    const float dx = qa[0] - pa[0], dy = qa[1] - pa[1], dz = qa[2] - pa[2];
+    D[0] = fmaf(bx.r[6], dz, fmaf(bx.r[3], dy, bx.r[0] * dx));
+    D[1] = fmaf(bx.r[7], dz, fmaf(bx.r[4], dy, bx.r[1] * dx));
+    D[2] = fmaf(bx.r[8], dz, fmaf(bx.r[5], dy, bx.r[2] * dx));
+    d2 = seg_box_dist2(A, D, H);
+  }
+  return d2 < el.radius * el.radius;
+}
+
+template <typename QT, bool COLLISION_ONLY, int PAIRS>
+__global__ void __launch_bounds__(NT, NWB_SCENE_MINB)
+validity_scene_kernel(const __grid_constant__ ValidityTables tab, const QT* __restrict__ q, int64_t n,
+                      uint8_t* __restrict__ valid, uint8_t* __restrict__ reason) {
+  extern __shared__ __align__(16) float smem[];
+  // layout: point table [kPointFloats][NT] | hierarchy head [kSceneStaged] | barrier | leaf of each thread | hit flags |
+  //         counter | test queue.  Three CTAs per SM (12 warps) fit: 72 KB each.
+  SceneNode* staged = reinterpret_cast<SceneNode*>(smem + kSmemFloats);
+  uint64_t* scene_bar = reinterpret_cast<uint64_t*>(staged + kSceneStaged);
+  int* cur_box = reinterpret_cast<int*>(scene_bar + 2);                 // [NT]: the leaf each thread handed in this round
+  int* hit_flag = cur_box + NT;                                         // [NT]
+  int* counts = hit_flag + NT;                                          // [1]: tests queued this round
+  uint16_t* testq = reinterpret_cast<uint16_t*>(counts + 2);            // (owner | link << 7)
+  const int tid = threadIdx.x;
+  const int64_t base = (int64_t)blockIdx.x * NT;
+  const int64_t i = base + tid;
+  const int nvalid = (int)min((int64_t)NT, n - base);
+  const int n_staged = min(tab.scene.n_nodes, kSceneStaged);
+  if (tid == 0) {
+    mbar_init(scene_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(scene_bar, (uint32_t)(n_staged * sizeof(SceneNode)));
+    bulk_g2s(staged, tab.scene.nodes, (uint32_t)(n_staged * sizeof(SceneNode)), scene_bar);
+    counts[0] = 0;
+    counts[1] = 0;
+  }
+  hit_flag[tid] = 0;
+  for (int e = tid; e < nvalid * NWB_NJ; e += NT) smem[e] = (float)q[base * NWB_NJ + e];
+  __syncthreads();
+  float qv[NWB_NJ];
+  const int row = tid < nvalid ? tid : 0;
+#pragma unroll
+  for (int j = 0; j < NWB_NJ; ++j) qv[j] = smem[row * NWB_NJ + j];
+  __syncthreads();                                                      // the staging area becomes the point table
+
+  // forward kinematics, stability and self collision; the scene has no inline boxes (tab.n_boxes == 0)
+  SmemStore st{smem + tid};
+  const ValidityResult<float> res = evaluate_config<float, SmemStore, false, COLLISION_ONLY, PAIRS>(tab, qv, st, nullptr, nullptr);
+  bool hit = res.hit;
+
+  // bounding box of the tested proxies of this configuration, radii and slack included
+  float rlo[3] = {1e30f, 1e30f, 1e30f}, rhi[3] = {-1e30f, -1e30f, -1e30f};
+  for (int l = 0; l < tab.n_env_links; ++l) {
+    const EnvLink& el = tab.env_links[l];
+    const float rr = el.radius + 1.0e-4f;
+    float p[3];
+    load3(st, el.off, p);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { rlo[k] = fminf(rlo[k], p[k] - rr); rhi[k] = fmaxf(rhi[k], p[k] + rr); }
+    if (!el.is_sphere) {
+      load3(st, el.off + 3, p);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { rlo[k] = fminf(rlo[k], p[k] - rr); rhi[k] = fmaxf(rhi[k], p[k] + rr); }
+    }
+  }
+  mbar_wait(scene_bar, 0);
+
+  int node = 0;
+  bool walking = !hit && i < n;
+  for (;;) {
+    // (1) walk to the next leaves whose bounds this configuration's box reaches; cull each tested link against the
+    //     leaf's box by its bounding sphere and queue the survivors
+    int found = 0;
+    if (walking) {
+      while (node < tab.scene.n_nodes) {
+        const SceneNode nd = node < n_staged ? staged[node] : tab.scene.nodes[node];
+        const bool apart = nd.lo[0] > rhi[0] || rlo[0] > nd.hi[0] || nd.lo[1] > rhi[1] || rlo[1] > nd.hi[1] ||
+                           nd.lo[2] > rhi[2] || rlo[2] > nd.hi[2];
+        if (apart) { node = nd.skip; continue; }
+        ++node;
+        if (nd.box < 0) continue;
+        const SceneBox& bx = tab.scene.boxes[nd.box];
+        const float c[3] = {bx.c[0], bx.c[1], bx.c[2]};
+        const float h[3] = {bx.h[0], bx.h[1], bx.h[2]};
+        float r[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) r[k] = bx.r[k];
+        int l = 0;
+        auto cull = [&](int off, bool is_sphere, float radius, float half_len) {
+          float pa[3];
+          load3(st, off, pa);
+          float mx = pa[0], my = pa[1], mz = pa[2];
+          if (!is_sphere) {
+            float qm[3];
+            load3(st, off + 3, qm);
+            mx = fmaf(0.5f, qm[0] - pa[0], pa[0]);
+            my = fmaf(0.5f, qm[1] - pa[1], pa[1]);
+            mz = fmaf(0.5f, qm[2] - pa[2], pa[2]);
+          }
+          mx -= c[0]; my -= c[1]; mz -= c[2];
+          const float c0 = fmaf(r[6], mz, fmaf(r[3], my, r[0] * mx));
+          const float c1 = fmaf(r[7], mz, fmaf(r[4], my, r[1] * mx));
+          const float c2 = fmaf(r[8], mz, fmaf(r[5], my, r[2] * mx));
+          const float e0 = box_excess(c0, h[0]), e1 = box_excess(c1, h[1]), e2 = box_excess(c2, h[2]);
+          const float dm2 = fmaf(e2, e2, fmaf(e1, e1, e0 * e0));
+          const float reach = half_len + radius + 1.0e-4f;              // slack for the fp32 evaluation of the exact test
+          if (dm2 <= reach * reach)
+            testq[atomicAdd(&counts[1], 1)] = (uint16_t)(tid | (l << 7));
+          ++l;
+        };
+        if constexpr (PAIRS == PAIRS_TABLE) {
+          for (int k = 0; k < tab.n_env_links; ++k)
+            cull(tab.env_links[k].off, tab.env_links[k].is_sphere != 0, tab.env_links[k].radius, tab.env_links[k].half_len);
+        } else {                                                         // same order as the table the exact tests index
+#define NWB_X_CULL(SLOT, SPHERE, R, HALF) cull(SLOT, SPHERE, R, HALF);
+          if constexpr (PAIRS == PAIRS_STATIC_GROUP) { NWB_ENV_LINKS_GROUP(NWB_X_CULL) }
+          else { NWB_ENV_LINKS_ALL(NWB_X_CULL) }
+#undef NWB_X_CULL
+        }
+        cur_box[tid] = nd.box;
+        found = 1;
+        break;
+      }
+      if (!found) walking = false;                                       // the walk ran off the end of the hierarchy
+    }
+    if (!__syncthreads_or(found > 0)) break;                             // publishes the test queue
+    // (2) exact tests, dealt over the CTA
+    const int n_test = counts[1];
+    for (int e = tid; e < n_test; e += NT) {
+      const uint32_t w = testq[e];
+      const int owner = (int)(w & 127u), l = (int)(w >> 7), b = cur_box[owner];
+      if (hit_flag[owner]) continue;                                     // benign race: a stale 0 only costs a redundant test
+      if (scene_link_hits_box(smem + owner, tab.env_links[l], tab.scene.boxes[b])) hit_flag[owner] = 1;
+    }
+    __syncthreads();
+    if (tid == 0) counts[1] = 0;                                         // ordered before the next pushes by the barrier below
+    if (hit_flag[tid]) { hit = true; walking = false; }
+    __syncthreads();
+  }
+
+  if (i < n) {
+    const unsigned rs = (hit ? NWB_REASON_COLLISION : 0u) | (res.stable ? 0u : NWB_REASON_UNSTABLE);
+    if (valid) valid[i] = COLLISION_ONLY ? (uint8_t)hit : (uint8_t)(rs == 0u);
+    if (reason) reason[i] = (uint8_t)rs;
+  }
+}
+
 // ---- persistent variant: one resident CTA per SM slot, input tiles streamed by TMA bulk copies --
 // The batch is cut into tiles of PT configurations (PT*21 contiguous elements).  One elected thread
 // issues cp.async.bulk (UBLKCP) for tile k+1 into the other half of a double buffer while all
@@ -392,6 +573,24 @@ static cudaError_t launch_one(const ValidityTables& tab, const void* q, int64_t 
   return cudaGetLastError();
 }
 
+template <typename QT, bool COLLISION_ONLY, int PAIRS>
+static cudaError_t launch_scene(const ValidityTables& tab, const void* q, int64_t n, uint8_t* valid, uint8_t* reason,
+                                cudaStream_t stream) {
+  auto kern = validity_scene_kernel<QT, COLLISION_ONLY, PAIRS>;
+  static std::atomic<bool> configured[kMaxDevices];
+  const size_t smem = kSmemFloats * sizeof(float) + (size_t)kSceneStaged * sizeof(SceneNode) + 16 +
+                      (2 * NT + 2) * sizeof(int) + (size_t)kSceneQueueCap * sizeof(uint16_t);
+  const int dev = current_device();
+  if (!configured[dev].load(std::memory_order_relaxed)) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured[dev].store(true, std::memory_order_relaxed);
+  }
+  const int64_t blocks = (n + NT - 1) / NT;
+  kern<<<(unsigned)blocks, NT, smem, stream>>>(tab, (const QT*)q, n, valid, reason);
+  return cudaGetLastError();
+}
+
 template <typename QT, bool COLLISION_ONLY>
 static cudaError_t launch_qt(const ValidityTables& tab, const void* q, int64_t n, uint8_t* valid, uint8_t* reason,
                              float* margins, bool static_pairs, cudaStream_t stream, const GatherPeers& gp) {
@@ -402,6 +601,10 @@ static cudaError_t launch_qt(const ValidityTables& tab, const void* q, int64_t n
 #endif
   if (tab.scene.n_nodes > 0) {                  // scene of more than kMaxBoxes boxes: the instantiations that walk the hierarchy
     if (gp.n > 0) return cudaErrorNotSupported; // the fused gather lives in the persistent kernel only
+    static const bool no_queue = getenv("NWB_SCENE_NO_QUEUE") != nullptr;
+    if (!margins && !no_queue)                  // verdicts only: exact tests compacted through the CTA queue
+      return static_pairs ? launch_scene<QT, COLLISION_ONLY, kStatic>(tab, q, n, valid, reason, stream)
+                          : launch_scene<QT, COLLISION_ONLY, PAIRS_TABLE>(tab, q, n, valid, reason, stream);
     if (static_pairs)
       return margins ? launch_one<QT, true, COLLISION_ONLY, kStatic, true>(tab, q, n, valid, reason, margins, stream)
                      : launch_one<QT, false, COLLISION_ONLY, kStatic, true>(tab, q, n, valid, reason, margins, stream);

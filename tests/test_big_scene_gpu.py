@@ -51,6 +51,47 @@ def test_generated_scene_validity_and_margins(oracle, n_boxes):
     assert added > 0 and o_valid.sum() > 0
 
 
+@pytest.mark.parametrize("n_boxes", [40, 300])
+def test_work_queue_kernel_every_instantiation(oracle, n_boxes):
+    """The verdict-only kernel of large scenes (hierarchy walk per thread, exact tests compacted through a CTA queue) in
+    each of its forms: float32 input, the table pair list (srdf_trim = 0), the whole-robot collision predicate, a ragged
+    last block, and against the per-thread walk that the margins path still uses."""
+    boxes = OL.generated_scene(n_boxes, seed=21)
+    q = configs(128 * 77 + 53, 900 + n_boxes)                   # ragged tail
+    o_valid, o_reason, o_marg = oracle.is_feasible(q, boxes=boxes, threads=oracle.threads)
+    band = (np.abs(o_marg) < BAND).any(1)
+    with nwb.Context() as c:
+        c.scene_add_boxes(boxes)
+        valid, reason, _ = c.isFeasible(q)
+        assert (((valid == o_valid) & (reason == o_reason)) | band).all()
+        valid_m, reason_m, _ = c.isFeasible(q, want_margins=True)   # per-thread walk
+        assert (valid == valid_m).all() and (reason == reason_m).all()
+        qf = np.ascontiguousarray(q.astype(np.float32))
+        vf, rf = np.empty(len(q), np.uint8), np.empty(len(q), np.uint8)
+        c.is_feasible_host_buffers_f32(qf.ctypes.data, len(q), vf.ctypes.data, rf.ctypes.data)
+        v64, r64, _ = c.isFeasible(qf.astype(np.float64))
+        assert (vf == v64).all() and (rf == r64).all()
+        col = c.is_state_colliding(q)[0]
+        o_col, o_sep = oracle.is_state_colliding(q, boxes=boxes, group_only=False)
+        assert ((col == o_col) | (np.abs(o_sep) < BAND)).all()
+        assert (col == c.is_state_colliding(q, want_separation=True)[0]).all()
+        # a single configuration and an empty batch
+        v1, r1, _ = c.isFeasible(q[:1])
+        assert v1[0] == valid[0] and r1[0] == reason[0]
+        assert len(c.isFeasible(q[:0])[0]) == 0
+    pn = OL.default_params(srdf_trim=0)
+    on_valid, on_reason, on_marg = oracle.is_feasible(q, params=pn, boxes=boxes, threads=oracle.threads)
+    bandn = (np.abs(on_marg) < BAND).any(1)
+    with nwb.Context(srdf_trim=0) as c:
+        c.scene_add_boxes(boxes)
+        valid, reason, _ = c.isFeasible(q)
+        assert (((valid == on_valid) & (reason == on_reason)) | bandn).all()
+        col = c.is_state_colliding(q)[0]
+        o_col, o_sep = oracle.is_state_colliding(q, params=pn, boxes=boxes, group_only=False)
+        assert ((col == o_col) | (np.abs(o_sep) < BAND)).all()
+    assert (on_reason != o_reason).any()                           # the two SRDF readings do differ on this batch
+
+
 def test_every_reference_scene_object_at_once(oracle):
     """initScene.cpp:120-158,172-176,569-573 + the clients' objects (SIM:322-356, EXE:376-377, PAR:465-485): 21 boxes."""
     boxes = OL.scene_boxes("ALL")
