@@ -40,11 +40,11 @@ int ensure(Ctx* ctx, void** buf, size_t* have, size_t need) {
 }  // namespace
 
 namespace nwb {
-// Scenes of more than kMaxBoxes boxes: hierarchy + boxes in one device block [nodes | boxes], rebuilt on every change
+// Scenes of kCulledMinBoxes boxes and more: hierarchy + boxes in one device block [nodes | boxes], rebuilt on every change
 // of the scene.  The stream is drained first: kernels in flight may still read the previous block.
 static void upload_scene(Ctx* ctx, SceneView& view) {
   view = SceneView{nullptr, nullptr, 0, 0};
-  if (ctx->boxes.size() <= (size_t)kMaxBoxes) return;
+  if (ctx->boxes.size() < (size_t)kCulledMinBoxes) return;
   build_scene_bvh(ctx->boxes, ctx->bvh);
   const size_t nb = sizeof(SceneNode) * ctx->bvh.size(), bb = sizeof(SceneBox) * ctx->boxes.size();
   cudaSetDevice(ctx->device);
@@ -72,10 +72,16 @@ static void upload_scene(Ctx* ctx, SceneView& view) {
 void build_tables(Ctx* ctx) {
   build_validity_tables(ctx->params, ctx->boxes, true, ctx->tab_group);
   build_validity_tables(ctx->params, ctx->boxes, false, ctx->tab_all);
-  upload_scene(ctx, ctx->tab_group.scene);
-  ctx->tab_all.scene = ctx->tab_group.scene;
+  SceneView view;
+  upload_scene(ctx, view);
+  const bool big = ctx->boxes.size() > (size_t)kMaxBoxes;    // small scenes keep their inline boxes for every other kernel
+  ctx->tab_group.scene = ctx->tab_all.scene = big ? view : SceneView{nullptr, nullptr, 0, 0};
+  ctx->tab_group.culled = ctx->tab_all.culled = view;
   ctx->scene_dirty = false;
-  if (getenv("NWB_ENV_NO_CULL")) ctx->tab_group.env_cull = ctx->tab_all.env_cull = 0;   // full evaluation (roofline runs)
+  if (getenv("NWB_ENV_NO_CULL")) {                           // full evaluation of every (link, box) pair (roofline runs)
+    ctx->tab_group.env_cull = ctx->tab_all.env_cull = 0;
+    if (!big) ctx->tab_group.culled = ctx->tab_all.culled = SceneView{nullptr, nullptr, 0, 0};
+  }
 }
 }  // namespace nwb
 

@@ -14,6 +14,7 @@ namespace nwb {
 constexpr int kMaxPairs = 112;
 constexpr int kMaxRuns = 48;
 constexpr int kMaxBoxes = 16;              // boxes that travel inline in the kernel parameters
+constexpr int kCulledMinBoxes = 2;        // below this the inline boxes of the kernel parameters are faster
 constexpr int kStagedNodes = 1024;         // hierarchy nodes a CTA of the batched validity kernel stages in shared memory
 constexpr int kSceneBoxLimit = 1 << 20;    // boxes of a scene held in global memory under the hierarchy
 
@@ -73,6 +74,8 @@ struct ValidityTables {
   SceneBox boxes[kMaxBoxes];            // inline scene (n_boxes <= kMaxBoxes), else n_boxes = 0 and `scene` holds it
   EnvLink env_links[nwbm::kNumGeom];
   SceneView scene;                      // large scene: BVH + boxes in global memory (owned by the context)
+  SceneView culled;                     // the same hierarchy for every scene of >= kCulledMinBoxes boxes: read by the
+                                        // verdict-only batch kernel, which culls and compacts the exact tests
 };
 
 // Fused result gather: besides its own verdict array, the validity kernel stores each verdict into

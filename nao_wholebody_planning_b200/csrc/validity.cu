@@ -47,6 +47,15 @@ struct RegStore {
   __device__ __forceinline__ float get(int slot) const { return v[slot]; }
 };
 
+// Both at once: reads come from registers (compile-time slots only), every write is mirrored into the block's shared
+// memory so that OTHER threads can read this configuration's points afterwards (the work-queue kernel of large scenes).
+struct MirrorStore {
+  float v[nwbm::kPointFloats];
+  float* base;   // shared memory, already offset by threadIdx.x
+  __device__ __forceinline__ void put(int slot, float x) { v[slot] = x; base[slot * NT] = x; }
+  __device__ __forceinline__ float get(int slot) const { return v[slot]; }
+};
+
 // Writes every frame and the full COM to global memory (nwb_fk_batch).
 struct FkVisitor {
   double* poses;   // [29][12] of this configuration, or nullptr
@@ -240,7 +249,14 @@ validity_scene_kernel(const __grid_constant__ ValidityTables tab, const QT* __re
 
   // forward kinematics, stability and self collision; the scene has no inline boxes (tab.n_boxes == 0)
   SmemStore st{smem + tid};
-  const ValidityResult<float> res = evaluate_config<float, SmemStore, false, COLLISION_ONLY, PAIRS>(tab, qv, st, nullptr, nullptr);
+  ValidityResult<float> res;
+  if constexpr (PAIRS == PAIRS_TABLE) {
+    res = evaluate_config<float, SmemStore, false, COLLISION_ONLY, PAIRS>(tab, qv, st, nullptr, nullptr);
+  } else {                                                              // compiled-in pairs: self collision out of registers
+    MirrorStore ms;
+    ms.base = smem + tid;
+    res = evaluate_config<float, MirrorStore, false, COLLISION_ONLY, PAIRS>(tab, qv, ms, nullptr, nullptr);
+  }
   bool hit = res.hit;
 
   // bounding box of the tested proxies of this configuration, radii and slack included
@@ -599,12 +615,18 @@ static cudaError_t launch_qt(const ValidityTables& tab, const void* q, int64_t n
   if (static_pairs && !margins && getenv("NWB_PACKED"))
     return launch_packed<QT, COLLISION_ONLY, kStatic>(tab, q, n, valid, reason, stream);
 #endif
+  static const bool no_queue = getenv("NWB_SCENE_NO_QUEUE") != nullptr;
+  if (tab.culled.n_nodes > 0 && !margins && gp.n == 0 && !no_queue) {
+    // verdicts only, any scene with a hierarchy: exact tests culled and compacted through the CTA queue.  The kernel
+    // reads the scene from the hierarchy alone, so the inline copy of a small scene is switched off for it.
+    ValidityTables t = tab;
+    t.n_boxes = 0;
+    t.scene = tab.culled;
+    return static_pairs ? launch_scene<QT, COLLISION_ONLY, kStatic>(t, q, n, valid, reason, stream)
+                        : launch_scene<QT, COLLISION_ONLY, PAIRS_TABLE>(t, q, n, valid, reason, stream);
+  }
   if (tab.scene.n_nodes > 0) {                  // scene of more than kMaxBoxes boxes: the instantiations that walk the hierarchy
     if (gp.n > 0) return cudaErrorNotSupported; // the fused gather lives in the persistent kernel only
-    static const bool no_queue = getenv("NWB_SCENE_NO_QUEUE") != nullptr;
-    if (!margins && !no_queue)                  // verdicts only: exact tests compacted through the CTA queue
-      return static_pairs ? launch_scene<QT, COLLISION_ONLY, kStatic>(tab, q, n, valid, reason, stream)
-                          : launch_scene<QT, COLLISION_ONLY, PAIRS_TABLE>(tab, q, n, valid, reason, stream);
     if (static_pairs)
       return margins ? launch_one<QT, true, COLLISION_ONLY, kStatic, true>(tab, q, n, valid, reason, margins, stream)
                      : launch_one<QT, false, COLLISION_ONLY, kStatic, true>(tab, q, n, valid, reason, margins, stream);

@@ -21,10 +21,12 @@ def main():
     q_dev = torch.from_numpy(q).to(dev)
     v = torch.empty(n, dtype=torch.uint8, device=dev)
     r = torch.empty(n, dtype=torch.uint8, device=dev)
-    sizes = [int(a) for a in sys.argv[1:]] or [17, 64, 256, 4096]
+    sizes = sys.argv[1:] or ["17", "64", "256", "4096"]
     for nb in sizes:
         c = nwb.Context()
-        c.scene_add_boxes(OL.generated_scene(nb))
+        boxes = OL.scene_boxes(nb) if nb.startswith("S") else OL.generated_scene(int(nb))
+        c.scene_add_boxes(boxes)
+        nb = len(boxes)
         ts = []
         for it in range(6):
             c.is_feasible_dev(q_dev.data_ptr(), nwb.F64, n, v.data_ptr(), r.data_ptr())
