@@ -241,6 +241,7 @@ def _declare(lib):
         "nwb_host_free": (None, [vp]),
         "nwb_ffma_peak": (C.c_int, [vp, C.c_int, pd, pd]),
         "nwb_last_kernel_ms": (C.c_int, [vp, pd, C.POINTER(i64)]),
+        "nwb_set_kernel_timing": (C.c_int, [vp, C.c_int]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)  # AttributeError here = header/library mismatch: fail loudly

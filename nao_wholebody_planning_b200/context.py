@@ -444,6 +444,10 @@ class Context:
         self._check(self.lib.nwb_ffma_peak(self.h, iters, C.byref(t), C.byref(ms)), "nwb_ffma_peak")
         return t.value, ms.value
 
+    def set_kernel_timing(self, enabled):
+        """Timing events around every operator's kernels (default on); off for pipelined back-to-back calls."""
+        self._check(self.lib.nwb_set_kernel_timing(self.h, int(bool(enabled))), "nwb_set_kernel_timing")
+
     def last_kernel_ms(self):
         ms, n = C.c_double(0), C.c_int64(0)
         self._check(self.lib.nwb_last_kernel_ms(self.h, C.byref(ms), C.byref(n)), "nwb_last_kernel_ms")

@@ -294,10 +294,10 @@ void nwb_host_free(void* p) {
 // ---- validity -----------------------------------------------------------------------------------
 static int feasible_dev(nwb_ctx* ctx, const ValidityTables& tab, const void* q, int dtype, int64_t n, uint8_t* valid,
                         uint8_t* reason, float* margins, bool collision_only) {
-  NWB_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  NWB_CUDA(ctx, ev_record(ctx, ctx->ev0, ctx->stream));
   const GatherPeers* gp = (!collision_only && ctx->gather.n > 0) ? &ctx->gather : nullptr;
   NWB_CUDA(ctx, launch_validity(tab, q, dtype, n, valid, reason, margins, collision_only, ctx->params.srdf_trim != 0 && !ctx->force_table_pairs, ctx->stream, gp));
-  NWB_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  NWB_CUDA(ctx, ev_record(ctx, ctx->ev1, ctx->stream));
   ctx->last_launches = n > 0 ? 1 : 0;
   ctx->last_ms = -1;   // resolved lazily by nwb_last_kernel_ms
   return NWB_OK;
@@ -476,8 +476,20 @@ int nwb_ffma_peak(nwb_ctx* ctx, int iters, double* tflops_out, double* ms_out) {
   return NWB_OK;
 }
 
+int nwb_set_kernel_timing(nwb_ctx* ctx, int enabled) {
+  if (!ctx) return NWB_E_INVALID;
+  ctx->timing = enabled != 0;
+  ctx->last_ms = 0;
+  return NWB_OK;
+}
+
 int nwb_last_kernel_ms(nwb_ctx* ctx, double* ms_out, int64_t* launches_out) {
   if (!ctx) return NWB_E_INVALID;
+  if (!ctx->timing) {                       // no events were recorded: only the launch count is known
+    if (ms_out) *ms_out = -1.0;
+    if (launches_out) *launches_out = ctx->last_launches;
+    return NWB_OK;
+  }
   if (ctx->last_ms < 0) {
     NWB_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
     float ms = 0;

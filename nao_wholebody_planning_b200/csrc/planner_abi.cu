@@ -60,10 +60,10 @@ int nwb_steer_project_batch_dev(nwb_ctx* ctx, const double* q_near, const double
     P_CUDA(ctx, cudaMalloc(&ctx->d_work, work_need));
     ctx->d_work_bytes = work_need;
   }
-  P_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  P_CUDA(ctx, ev_record(ctx, ctx->ev0, ctx->stream));
   P_CUDA(ctx, launch_steer_project(pc, q_near, q_target, n, q_out, status, ds_status, nullptr, n >= 4096 ? ctx->d_work : nullptr,
                                    ctx->stream));
-  P_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  P_CUDA(ctx, ev_record(ctx, ctx->ev1, ctx->stream));
   ctx->last_ms = -1;
   ctx->last_launches = n >= 4096 ? 2 : (n > 0);
   return NWB_OK;
@@ -112,10 +112,10 @@ int nwb_connect_batch(nwb_ctx* ctx, const double* q_start, const double* q_conne
   make_plan_const(ctx, weights, step, pc);
   P_CUDA(ctx, cudaMemcpyAsync(A.at<double>(o_s), q_start, qb, cudaMemcpyHostToDevice, s));
   P_CUDA(ctx, cudaMemcpyAsync(A.at<double>(o_c), q_connect, qb, cudaMemcpyHostToDevice, s));
-  P_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
+  P_CUDA(ctx, ev_record(ctx, ctx->ev0, s));
   P_CUDA(ctx, launch_connect(pc, ctx->tab_group, static_pairs(ctx), A.at<double>(o_s), A.at<double>(o_c), n_edges, max_steps,
                              A.at<double>(o_n), A.at<int32_t>(o_a), A.at<int32_t>(o_st), s));
-  P_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
+  P_CUDA(ctx, ev_record(ctx, ctx->ev1, s));
   ctx->last_ms = -1;
   P_CUDA(ctx, cudaMemcpyAsync(nodes_out, A.at<double>(o_n), nb, cudaMemcpyDeviceToHost, s));
   P_CUDA(ctx, cudaMemcpyAsync(n_added, A.at<int32_t>(o_a), ib, cudaMemcpyDeviceToHost, s));
@@ -130,9 +130,9 @@ int nwb_is_path_valid_batch_dev(nwb_ctx* ctx, const double* qa, const double* qb
   if (!ctx) return NWB_E_INVALID;
   if (n_edges < 0 || k < 0 || (n_edges > 0 && (!qa || !qb || !first_bad))) return bad(ctx, "nwb_is_path_valid_batch_dev: bad argument");
   P_CUDA(ctx, cudaSetDevice(ctx->device));
-  P_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  P_CUDA(ctx, ev_record(ctx, ctx->ev0, ctx->stream));
   P_CUDA(ctx, launch_edge_check(ctx->tab_all, static_pairs(ctx), qa, qb, n_edges, k, ok, first_bad, ctx->stream));
-  P_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  P_CUDA(ctx, ev_record(ctx, ctx->ev1, ctx->stream));
   ctx->last_ms = -1;
   ctx->last_launches = n_edges > 0 ? 2 : 0;
   return NWB_OK;
@@ -176,10 +176,10 @@ int nwb_sample_stable_configs_dev(nwb_ctx* ctx, uint64_t seed, uint64_t first, i
     P_CUDA(ctx, cudaMalloc(&ctx->d_work, work_need));
     ctx->d_work_bytes = work_need;
   }
-  P_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  P_CUDA(ctx, ev_record(ctx, ctx->ev0, ctx->stream));
   P_CUDA(ctx, launch_sample(pc, ctx->tab_group, static_pairs(ctx), seed, first, count, max_ik_iter, rows, index, cap, n_out, stage,
                             ctx->d_work, ctx->stream));
-  P_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  P_CUDA(ctx, ev_record(ctx, ctx->ev1, ctx->stream));
   ctx->last_ms = -1;
   ctx->last_launches = count > 0 ? 3 * (int)((count + ((int64_t)1 << 22) - 1) >> 22) : 0;
   return NWB_OK;

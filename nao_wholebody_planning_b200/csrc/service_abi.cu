@@ -673,12 +673,12 @@ int nwb_goal_sample_batch(nwb_ctx* ctx, uint64_t seed, uint64_t first, int64_t c
   S_CUDA(ctx, cudaMemsetAsync(A.at<char>(o_n), 0, 8, s));
   S_CUDA(ctx, cudaMemcpyAsync(A.at<double>(o_pose), hand_pose6, sizeof(double) * 6, cudaMemcpyHostToDevice, s));
   S_CUDA(ctx, cudaMemcpyAsync(A.at<uint64_t>(o_seed), &seed, 8, cudaMemcpyHostToDevice, s));
-  S_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
+  S_CUDA(ctx, ev_record(ctx, ctx->ev0, s));
   S_CUDA(ctx, launch_goal_sample(pc, ctx->tab_group, static_pairs(ctx), A.at<double>(o_pose), A.at<uint64_t>(o_seed), 1, first, count,
                                  max_ik_iter, A.at<double>(o_rows), A.at<uint64_t>(o_idx), A.at<double>(o_erg), 16,
                                  A.at<unsigned long long>(o_n), A.at<uint8_t>(o_st), ergonomics ? A.at<double>(o_ea) : nullptr,
                                  rows ? A.at<double>(o_ra) : nullptr, nullptr, s));
-  S_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
+  S_CUDA(ctx, ev_record(ctx, ctx->ev1, s));
   S_CUDA(ctx, cudaMemcpyAsync(stage, A.at<uint8_t>(o_st), count, cudaMemcpyDeviceToHost, s));
   if (ergonomics) S_CUDA(ctx, cudaMemcpyAsync(ergonomics, A.at<double>(o_ea), sizeof(double) * count, cudaMemcpyDeviceToHost, s));
   if (rows) S_CUDA(ctx, cudaMemcpyAsync(rows, A.at<double>(o_ra), sizeof(double) * NWB_NJ * count, cudaMemcpyDeviceToHost, s));

@@ -805,10 +805,10 @@ int nn_launch(nwb_tree* t, const double* q_dev, int64_t nq, int32_t* idx_dev, do
   // NWB_NN_NO_TC=1 keeps the CUDA-core scan for A/B measurements
   static const bool no_tc = getenv("NWB_NN_NO_TC") != nullptr;
   if (nq >= 32 && !no_tc) {
-    TREE_CUDA(t, cudaEventRecord(t->ctx->ev0, s));
+    TREE_CUDA(t, ev_record(t->ctx, t->ctx->ev0, s));
     int launches = 0;
     TREE_CUDA(t, nn_tc_launch(t, q_dev, nq, idx_dev, dist_dev, nullptr, &launches));
-    TREE_CUDA(t, cudaEventRecord(t->ctx->ev1, s));
+    TREE_CUDA(t, ev_record(t->ctx, t->ctx->ev1, s));
     t->ctx->last_ms = -1;
     t->ctx->last_launches = launches;
     t->ctx->last_nn_passes = (nq + TC_M - 1) / TC_M;
@@ -818,7 +818,7 @@ int nn_launch(nwb_tree* t, const double* q_dev, int64_t nq, int32_t* idx_dev, do
   // NWB_NN_OLD=1 keeps the round-1 tile-interleaved kernel for A/B measurements
   static const bool old_single = getenv("NWB_NN_OLD") != nullptr;
   if (nq == 1 && !old_single) {
-    TREE_CUDA(t, cudaEventRecord(t->ctx->ev0, s));
+    TREE_CUDA(t, ev_record(t->ctx, t->ctx->ev0, s));
     if (t->size <= kNnSmallMax) {
       const unsigned blocks = (unsigned)std::max<int64_t>(1, (t->size + NN1_THREADS - 1) / NN1_THREADS);
       if (t->size == 0) {
@@ -838,13 +838,13 @@ int nn_launch(nwb_tree* t, const double* q_dev, int64_t nq, int32_t* idx_dev, do
                                                            idx_dev, dist_dev);
     }
     TREE_CUDA(t, cudaGetLastError());
-    TREE_CUDA(t, cudaEventRecord(t->ctx->ev1, s));
+    TREE_CUDA(t, ev_record(t->ctx, t->ctx->ev1, s));
     t->ctx->last_ms = -1;
     t->ctx->last_launches = 1;
     t->ctx->last_nn_passes = 1;
     return NWB_OK;
   }
-  TREE_CUDA(t, cudaEventRecord(t->ctx->ev0, s));
+  TREE_CUDA(t, ev_record(t->ctx, t->ctx->ev0, s));
   // batches below 32 queries: 8 or 16 queries share each pass over the nodes on the FP32 pipe
   static const int qt_batch = getenv("NWB_NN_QT") ? atoi(getenv("NWB_NN_QT")) : 16;
   const int QT = nq == 1 ? 1 : (nq <= 8 || qt_batch == 8 ? 8 : 16);
@@ -866,7 +866,7 @@ int nn_launch(nwb_tree* t, const double* q_dev, int64_t nq, int32_t* idx_dev, do
                                                                              t->tickets + y0, idx_dev + qoff, dist_dev ? dist_dev + qoff : nullptr);
   }
   TREE_CUDA(t, cudaGetLastError());
-  TREE_CUDA(t, cudaEventRecord(t->ctx->ev1, s));
+  TREE_CUDA(t, ev_record(t->ctx, t->ctx->ev1, s));
   t->ctx->last_ms = -1;
   t->ctx->last_launches = (qtiles + 65534) / 65535;
   t->ctx->last_nn_passes = qtiles;

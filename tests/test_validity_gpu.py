@@ -159,6 +159,14 @@ def test_device_pointer_variant_f32_and_f64(ctx, oracle):
         assert ((v == o_valid) | band).all()
         ms, launches = ctx.last_kernel_ms()
         assert launches == 1 and ms > 0
+        # timing events off (pipelined callers): same verdicts, the duration is reported as unknown
+        ctx.set_kernel_timing(False)
+        valid2 = torch.empty_like(valid)
+        ctx.is_feasible_dev(qd.data_ptr(), code, len(q), valid2.data_ptr(), reason.data_ptr())
+        ctx.synchronize()
+        ms2, launches2 = ctx.last_kernel_ms()
+        ctx.set_kernel_timing(True)
+        assert ms2 == -1.0 and launches2 == 1 and bool((valid2 == valid).all())
 
 
 @pytest.mark.parametrize("scene", ["S1", "S2", "S3"])
