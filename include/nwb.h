@@ -225,7 +225,8 @@ NWB_API int nwb_steer_project_batch(nwb_ctx* ctx, const double* q_near, const do
 /* The connectTree walk (RP:926-1031) for n_edges independent edges: from q_start[e] step towards
  * q_connect[e] (steer -> project -> isConfigValid -> append, each step starting from the projected
  * previous node, RP:1004) until NWB_REACHED or NWB_TRAPPED.  nodes_out [n_edges][max_steps][21]
- * receives the appended nodes, n_added[e] their count; status[e] = -1 if max_steps ran out first. */
+ * receives the appended nodes, n_added[e] their count (rows past n_added[e] are not written: only the appended rows
+ * are copied back); status[e] = -1 if max_steps ran out first. */
 NWB_API int nwb_connect_batch(nwb_ctx* ctx, const double* q_start, const double* q_connect, int64_t n_edges,
                               const double* weights, double step, int32_t max_steps, double* nodes_out,
                               int32_t* n_added, int32_t* status);

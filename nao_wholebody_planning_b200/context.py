@@ -160,7 +160,7 @@ class Context:
         q_connect = np.ascontiguousarray(q_connect, dtype=np.float64).reshape(-1, NJ)
         n = len(q_start)
         w = self._weights(weights)
-        nodes = np.full((n, max_steps, NJ), np.nan)
+        nodes = np.zeros((n, max_steps, NJ))          # rows past n_added stay zero (only the appended rows are copied back)
         added = np.empty(n, np.int32)
         st = np.empty(n, np.int32)
         self._check(self.lib.nwb_connect_batch(self.h, _p(q_start), _p(q_connect), n, _p(w), float(step), int(max_steps),

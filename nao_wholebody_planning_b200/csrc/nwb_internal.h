@@ -184,6 +184,9 @@ cudaError_t launch_rrt_fused(const PlanConst& pc, const ValidityTables& tab, boo
 // scratch: 256 + 4 n bytes of device memory selects the two-launch form for n >= 4096 (nullptr: one launch)
 cudaError_t launch_steer_project(const PlanConst& pc, const double* q_near, const double* q_target, int64_t n, double* q_out,
                                  int32_t* status, int32_t* ds_status, int32_t* iters, void* scratch, cudaStream_t s);
+// rows [e][0 .. n_added[e]) of nodes [n_edges][max_steps][21] -> packed[offset[e] ..] (dense, edge order)
+cudaError_t launch_pack_rows(const double* nodes, const int32_t* n_added, const int64_t* offset, int64_t n_edges, int max_steps,
+                             double* packed, cudaStream_t s);
 cudaError_t launch_connect(const PlanConst& pc, const ValidityTables& tab, bool static_pairs, const double* q_start,
                            const double* q_connect, int64_t n_edges, int max_steps, double* nodes_out, int32_t* n_added,
                            int32_t* status, cudaStream_t s);

@@ -1068,6 +1068,22 @@ cudaError_t launch_connect(const PlanConst& pc, const ValidityTables& tab, bool 
   return cudaGetLastError();
 }
 
+__global__ void __launch_bounds__(128)
+pack_rows_kernel(const double* __restrict__ nodes, const int32_t* __restrict__ n_added, const int64_t* __restrict__ offset,
+                 int max_steps, double* __restrict__ packed) {
+  const int64_t e = blockIdx.x;
+  const int k = min(max(n_added[e], 0), max_steps);
+  const double* src = nodes + (size_t)e * max_steps * NWB_NJ;
+  double* dst = packed + (size_t)offset[e] * NWB_NJ;
+  for (int x = threadIdx.x; x < k * NWB_NJ; x += blockDim.x) dst[x] = src[x];
+}
+cudaError_t launch_pack_rows(const double* nodes, const int32_t* n_added, const int64_t* offset, int64_t n_edges, int max_steps,
+                             double* packed, cudaStream_t s) {
+  if (n_edges <= 0) return cudaSuccess;
+  pack_rows_kernel<<<(unsigned)n_edges, 128, 0, s>>>(nodes, n_added, offset, max_steps, packed);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_connect_forest(const PlanConst& pc, const ValidityTables& tab, bool static_pairs, ForestView F, RrtState S,
                                   int nq, const double* ma_pts, int n_pts, cudaStream_t s) {
   if (nq <= 0) return cudaSuccess;
