@@ -35,7 +35,12 @@ __device__ __forceinline__ ValidityResult<float> eval_one(const ValidityTables& 
   for (int j = 0; j < NWB_NJ; ++j) qf[j] = (float)q[j];
   LocalStore st;
   constexpr int P = STATIC ? (COLLISION_ONLY ? PAIRS_STATIC_ALL : PAIRS_STATIC_GROUP) : PAIRS_TABLE;
-  return evaluate_config<float, LocalStore, false, COLLISION_ONLY, P, /*ENV_CULL=*/true, /*BIG_SCENE=*/true>(tab, qf, st, nullptr, nullptr);
+  // Two instantiations behind a uniform branch: the hierarchy walk of large scenes raises the register pressure (robot
+  // bounding box, a second copy of the leaf test) enough to push the point table of the compiled-in pair list out of
+  // registers (edge check: 560 B of stack against 8 B), and the scenes the reference builds never need it.
+  if (tab.scene.n_nodes > 0)
+    return evaluate_config<float, LocalStore, false, COLLISION_ONLY, P, /*ENV_CULL=*/true, /*BIG_SCENE=*/true>(tab, qf, st, nullptr, nullptr);
+  return evaluate_config<float, LocalStore, false, COLLISION_ONLY, P, /*ENV_CULL=*/true, /*BIG_SCENE=*/false>(tab, qf, st, nullptr, nullptr);
 }
 
 // ---- steer + project ----------------------------------------------------------------------------

@@ -269,7 +269,7 @@ NWB_HD ValidityResult<T> evaluate_config(const ValidityTables& tab, const T* q, 
 
   // ---- environment: robot proxies against the scene boxes ---------------------------------------
   // One box against every tested link: exact capsule-box / sphere-box distance.
-  auto test_box = [&](const SceneBox& bx) {
+  auto test_box = [&](const SceneBox& bx) __attribute__((always_inline)) {
     const T H[3] = {T(bx.h[0]), T(bx.h[1]), T(bx.h[2])};
     auto env_link = [&](int off, bool is_sphere, T radius, float half_len) {
       T pa[3], A[3];
