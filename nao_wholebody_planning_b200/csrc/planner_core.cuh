@@ -235,23 +235,30 @@ static __device__ __noinline__ void pinv_solve(const double (*W_in)[5], const do
   }
 }
 
-// Exact rejection of left-sole targets the Newton-Raphson solve can never converge to.  Convergence needs a joint
-// vector whose sole frame is within eps of the target in every twist component: |dp| <= sqrt(3) eps =: t and a
-// rotation by at most t.  With c = (0, 0.05, 0) the hip joint centre, the chain is
+// Exact rejection of left-sole targets the Newton-Raphson solve can never converge to.  Convergence at iteration i
+// means that the frame of q_i differs from the target by a twist with EVERY component inside (-eps, eps)
+// (KDL::Equal(delta_twist, Zero, eps)): a translation dp with |dp_k| < eps and a base-frame rotation vector w with
+// |w_k| < eps; both have norm <= sqrt(3) eps =: t.  With c = (0, 0.05, 0) the hip joint centre, the chain is
 //   sole = c + Rx(q0) [ Ry(q1)(0,0,-0.1) + Ry(q1+q2)(0,0,-0.1029) ] + R (0,0,-0.04519),   R = Rx(q0) Ry(q1+q2+q3) Rx(q4),
 // so for EVERY joint vector (5 joints, 6 pose coordinates: one equality and two inequalities are left over)
 //   (1) |sole - c| <= L = 0.24809,
 //   (2) the ankle A = sole + 0.04519 R e_z satisfies |A - c| <= 0.2029,
-//   (3) n . (A - c) = 0 for n = Rx(q0) e_y, and n is also normal to e_x and to R e_x, i.e. n = +-u/|u|, u = e_x x R e_x.
-// Carrying the tolerances through: |d(R e_x)| <= t and |du| <= t, so for t < |u_t| the angle phi between n and n_t
-// obeys sin phi <= r = t / |u_t| and |n - n_t| = 2 sin(phi / 2) = r / sqrt((1 + sqrt(1 - r^2)) / 2) =: dn;  |dA| <= da =
-// 1.04519 t;  and n . (A - c) = 0 with |A - c| <= min(0.2029, |A_t - c| + da) =: arm.  A target that CAN be converged
-// to therefore obeys
-//   |sole_t - c| <= L + t,   |A_t - c| <= 0.2029 + da,   |n_t . (A_t - c)| <= da + dn * arm.
-// Anything else runs all `maxiter` iterations and fails: 87 % of the failing solves on uniform samples (oracle, 3 x
-// 10^5 samples: 43 % by (1), 3 % by (2), 41 % by (3); none of the 37 874 converging solves is rejected, they reach at
-// most 0.64 of the bound of (3)).  10 % slack on (3) and 1e-6 on the lengths cover rounding.  The CPU oracle runs
-// the full iteration for every target - the parity tests compare the verdicts.
+//   (3) F := u . (A - c) = 0 with u = e_x x R e_x: the leg plane's normal n = Rx(q0) e_y is normal to e_x and to R e_x,
+//       so n is parallel to u (or u = 0), and A - c lies in the leg plane.
+// A target that CAN be converged to is within the tolerance box of such a frame.  (1) and (2) with the norms carried
+// through: |sole_t - c| <= L + t, |A_t - c| <= 0.2029 + (1 + 0.04519) t.  (3) to first order over the box, with a
+// rigorous remainder: perturbing the target by (dp, w) changes F by
+//   -u . dp - w . g,   g = 0.04519 (z x u) + x x ((A - c) x e_x),   x = R e_x, z = R e_z,
+// whose largest magnitude over the box is eps (|u|_1 + |g|_1); what the expansion leaves out is bounded by
+//   R2 = t^2 (1 + f) + h (|A - c| + t (1 + f) + f h) + (|u| + t) f h,   f = 0.04519, h = 0.51 t^2
+// (a rotation by |w| <= t moves a unit vector by w x v up to |w|^2/2 + |w|^3/6 <= h).  F must vanish somewhere in the
+// box, so |F(target)| <= eps (|u|_1 + |g|_1) + R2 for every target the solve can converge to.
+// Anything else runs all `maxiter` iterations and fails.  On uniform samples (oracle, 3 x 10^5): 37 % rejected by (1),
+// 7 % by (2), 39 % by (3); 96 % of all failing solves; none of the 37 842 converging solves is rejected, they reach at
+// most 0.925 of the bound of (3) - the L1 bound is attained only at the corners of the box.  (Round 1 bounded (3) with
+// the Euclidean norms throughout, a bound 1.6 x wider: 87 % of the failing solves.)  1e-4 relative slack and 1e-6 on
+// the lengths cover rounding.  The CPU oracle runs the full iteration for every target - the parity tests compare the
+// verdicts, and tests/test_leg_rejection_rule_cpu.py restates the rule in numpy against the oracle on every CPU run.
 __device__ __forceinline__ bool left_leg_target_feasible(const DFrame& target, double eps) {
   const double t = 1.7320508075688772 * eps, foot = 0.04519, legs = 0.1 + 0.1029;
   const double dx = target.p.x, dy = target.p.y - 0.05, dz = target.p.z;
@@ -261,16 +268,17 @@ __device__ __forceinline__ bool left_leg_target_feasible(const DFrame& target, d
   const double da = (1.0 + foot) * t, ankle = legs + da + 1e-6;
   const double an2 = ax * ax + ay * ay + az * az;
   if (an2 > ankle * ankle) return false;
-  const double uy = -target.r[6], uz = target.r[3];         // u = e_x x (R e_x) = (0, -x_z, x_y)
-  const double un = sqrt(uy * uy + uz * uz);
-  if (un > t) {
-    const double r = t / un;
-    const double dn = r / sqrt(0.5 * (1.0 + sqrt(1.0 - r * r)));
-    const double arm = fmin(legs, sqrt(an2) + da);
-    const double g = fabs(uy * ay + uz * az);               // |u . (A - c)|, compared against bound * |u|
-    if (g > 1.1 * (un * (da + dn * arm)) + 1e-12) return false;
-  }
-  return true;
+  const double xx = target.r[0], xy = target.r[3], xz = target.r[6];   // x = R e_x
+  const double zx = target.r[2], zy = target.r[5], zz = target.r[8];   // z = R e_z
+  const double uy = -xz, uz = xy;                                       // u = e_x x x = (0, -x_z, x_y)
+  const double F0 = uy * ay + uz * az;
+  const double gx = foot * (zy * uz - zz * uy) - (xy * ay + xz * az);
+  const double gy = xx * ay - foot * (zx * uz);
+  const double gz = xx * az + foot * (zx * uy);
+  const double B1 = eps * (fabs(uy) + fabs(uz) + fabs(gx) + fabs(gy) + fabs(gz));
+  const double h = 0.51 * t * t;
+  const double R2 = t * t * (1.0 + foot) + h * (sqrt(an2) + da + foot * h) + (sqrt(uy * uy + uz * uz) + t) * foot * h;
+  return !(fabs(F0) > 1.0001 * (B1 + R2) + 1e-12);
 }
 
 // Iterations [i0, i1) of ChainIkSolverPos_NR::CartToJnt on the left-leg chain (base = hip frame).  The update is
