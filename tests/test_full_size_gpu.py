@@ -38,6 +38,26 @@ def inputs(ctx):
     return {"V1": v1, "V1b": v1b, "V1c": v1c, "V1d": v1d, "V1c_projected": int(ok.sum())}
 
 
+@pytest.mark.parametrize("tag", ["V1", "V1d"])
+def test_validity_full_batch_in_a_256_box_scene(oracle, inputs, tag):
+    """2^20 configurations against 256 generated boxes (bounding-volume hierarchy): the verdict-only work-queue kernel
+    against the oracle, which tests every box, and against the per-thread walk of the margins path."""
+    q = inputs[tag]
+    boxes = OL.generated_scene(256)
+    o_valid, o_reason, o_marg = oracle.is_feasible(q, boxes=boxes, threads=oracle.threads)
+    band = (np.abs(o_marg) < BAND).any(1)
+    with nwb.Context() as c:
+        c.scene_add_boxes(boxes)
+        valid, reason, _ = c.isFeasible(q)
+        valid_m, reason_m, marg = c.isFeasible(q, want_margins=True)
+    bad = ((valid != o_valid) | (reason != o_reason)) & ~band
+    print(f"\n{tag}/256 boxes: n={len(q)} valid={o_valid.mean():.5f} collision={(o_reason & 1).mean():.4f} "
+          f"in-band={int(band.sum())} mismatches-outside-band={int(bad.sum())}")
+    assert bad.sum() == 0
+    assert (valid == valid_m).all() and (reason == reason_m).all()
+    assert np.abs(marg - o_marg).max() < 3e-6
+
+
 @pytest.mark.parametrize("scene", ["S0", "S1"])
 @pytest.mark.parametrize("tag", ["V1", "V1b", "V1c", "V1d"])
 def test_validity_full_batch_against_oracle(oracle, inputs, tag, scene):
