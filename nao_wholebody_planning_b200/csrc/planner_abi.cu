@@ -161,7 +161,7 @@ int nwb_is_path_valid_batch_dev(nwb_ctx* ctx, const double* qa, const double* qb
   P_CUDA(ctx, launch_edge_check(ctx->tab_all, static_pairs(ctx), qa, qb, n_edges, k, ok, first_bad, ctx->stream));
   P_CUDA(ctx, ev_record(ctx, ctx->ev1, ctx->stream));
   ctx->last_ms = -1;
-  ctx->last_launches = n_edges > 0 ? 2 : 0;
+  ctx->last_launches = n_edges > 0 ? 1 : 0;
   return NWB_OK;
 }
 

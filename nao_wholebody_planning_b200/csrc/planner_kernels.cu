@@ -813,72 +813,61 @@ rrt_fused_kernel(const __grid_constant__ PlanConst pc, const __grid_constant__ V
 }
 
 // ---- edge check: (edge, way-point) -> collision-only validity ------------------------------------------
-// One way-point per thread, 256 consecutive (edge, way-point) slots per block.  The end points of the
-// few edges a block touches are staged in shared memory once (start + step width per joint, fp64 as
-// interpolateWaypoints computes them, RP:1758-1771); each thread then forms its way-point, evaluates
-// the whole-robot collision predicate in registers and posts the first colliding index per edge.
-constexpr int EC_THREADS = 256;
-constexpr int EC_MAX_EDGES = 8;     // edges a block can span when k + 2 >= 37 (a block of 256 slots covers <= 8 edges)
+// ONE launch.  A block owns whole edges (as many as fit its threads: 5 edges x 102 way-points in 512 threads), so the
+// first colliding way-point of an edge is a shared-memory minimum and the block writes ok / first_bad itself - no
+// memset before, no finishing kernel after, no global atomics.  The end points of the block's edges are staged in shared
+// memory once (start + step width per joint, fp64 as interpolateWaypoints computes them, RP:1758-1771); each thread
+// forms its way-point and evaluates the whole-robot collision predicate in registers.
+constexpr int EC_THREADS = 512;
+constexpr int EC_MAX_EDGES = 64;    // edges per block (reached only for k + 2 <= 8 way-points per edge)
 
 // EARLY_EXIT: a way-point whose edge already has an earlier colliding way-point on record is skipped;
-// the warp votes (ballot) and leaves together, so no lane idles through a full evaluation for an
+// the warp votes (ballot) and moves on together, so no lane idles through a full evaluation for an
 // edge that is already lost.  Results (ok, first_bad) are identical to the full evaluation.
 template <bool STATIC, bool EARLY_EXIT>
-__global__ void __launch_bounds__(EC_THREADS, 2)
+__global__ void __launch_bounds__(EC_THREADS, 1)
 edge_check_kernel(const __grid_constant__ ValidityTables tab, const double* __restrict__ qa, const double* __restrict__ qb,
-                  int64_t n_edges, int k, int32_t* __restrict__ first_bad) {
+                  int64_t n_edges, int k, int edges_per_block, uint8_t* __restrict__ ok, int32_t* __restrict__ first_bad) {
   __shared__ double s_a[EC_MAX_EDGES][NWB_NJ], s_sw[EC_MAX_EDGES][NWB_NJ];
+  __shared__ int s_bad[EC_MAX_EDGES];
   const int wp = k + 2;
-  const int64_t gid0 = (int64_t)blockIdx.x * EC_THREADS;
-  const int64_t e0 = gid0 / wp;
-  const bool staged = wp * EC_MAX_EDGES >= EC_THREADS + wp;          // the block's edges fit the staging area
-  if (staged) {
-    for (int t = threadIdx.x; t < EC_MAX_EDGES * NWB_NJ; t += EC_THREADS) {
-      const int le = t / NWB_NJ, j = t % NWB_NJ;
-      const int64_t e = e0 + le;
-      if (e < n_edges) {
-        const double a = qa[e * NWB_NJ + j], b = qb[e * NWB_NJ + j];
-        s_a[le][j] = a;
-        s_sw[le][j] = (b - a) / (k + 1);                    // RP:1758
-      }
+  const int64_t e0 = (int64_t)blockIdx.x * edges_per_block;
+  const int ne = (int)min((int64_t)edges_per_block, n_edges - e0);
+  for (int t = threadIdx.x; t < ne * NWB_NJ; t += blockDim.x) {
+    const int le = t / NWB_NJ, j = t - le * NWB_NJ;
+    const double a = qa[(e0 + le) * NWB_NJ + j], b = qb[(e0 + le) * NWB_NJ + j];
+    s_a[le][j] = a;
+    s_sw[le][j] = (b - a) / (k + 1);                        // RP:1758
+  }
+  if (threadIdx.x < ne) s_bad[threadIdx.x] = 0x7fffffff;
+  __syncthreads();
+  const int total = ne * wp;
+  for (int base = 0; base < total; base += blockDim.x) {  // one pass unless an edge alone has more way-points than the block threads
+    const int slot = base + threadIdx.x;
+    const bool active = slot < total;
+    if (__ballot_sync(0xffffffffu, active) == 0u) continue;
+    const int sl = active ? slot : 0;
+    const int le = sl / wp, n = sl - le * wp;
+    if constexpr (EARLY_EXIT) {
+      const bool needed = active && (*reinterpret_cast<volatile int*>(&s_bad[le]) > n);
+      if (__ballot_sync(0xffffffffu, needed) == 0u) continue;   // the whole warp is past a known collision
     }
-    __syncthreads();
-  }
-  int64_t gid = gid0 + threadIdx.x;
-  const bool active = gid < n_edges * wp;
-  if (!active) gid = gid0;
-  const int64_t e = gid / wp;
-  const int n = (int)(gid - e * wp);
-  if constexpr (EARLY_EXIT) {
-    const bool needed = active && (*reinterpret_cast<volatile int32_t*>(first_bad + e) > n);
-    if (__ballot_sync(0xffffffffu, needed) == 0u) return;        // the whole warp is past a known collision
-  }
-  double q[NWB_NJ];
-  if (staged) {
-    const int le = (int)(e - e0);
+    double q[NWB_NJ];
 #pragma unroll
     for (int j = 0; j < NWB_NJ; ++j) {
       const double a = s_a[le][j];
       q[j] = (n == 0) ? a : __dadd_rn(a, __dmul_rn(s_sw[le][j], (double)n));   // RP:1763, 1771
     }
-  } else {
-    for (int j = 0; j < NWB_NJ; ++j) {
-      const double a = qa[e * NWB_NJ + j], b = qb[e * NWB_NJ + j];
-      const double sw = (b - a) / (k + 1);
-      q[j] = (n == 0) ? a : __dadd_rn(a, __dmul_rn(sw, (double)n));
-    }
+    ValidityResult<float> r = eval_one<true, STATIC>(tab, q);
+    if (active && r.hit) atomicMin(&s_bad[le], n);
   }
-  ValidityResult<float> r = eval_one<true, STATIC>(tab, q);
-  if (active && r.hit) atomicMin(first_bad + e, n);
-}
-
-__global__ void edge_finish_kernel(int32_t* __restrict__ first_bad, int64_t n_edges, uint8_t* __restrict__ ok) {
-  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n_edges) return;
-  int fb = first_bad[e];
-  bool good = fb == 0x7f7f7f7f;                 // the memset pattern of launch_edge_check: no way-point collided
-  if (ok) ok[e] = good;
-  first_bad[e] = good ? -1 : fb;
+  __syncthreads();
+  if (threadIdx.x < ne) {
+    const int fb = s_bad[threadIdx.x];
+    const bool good = fb == 0x7fffffff;                    // no way-point collided
+    if (ok) ok[e0 + threadIdx.x] = good;
+    first_bad[e0 + threadIdx.x] = good ? -1 : fb;
+  }
 }
 
 // ---- stable-configuration sampler ------------------------------------------------------------------------
@@ -1121,19 +1110,18 @@ cudaError_t launch_rrt_fused(const PlanConst& pc, const ValidityTables& tab, boo
 cudaError_t launch_edge_check(const ValidityTables& tab, bool static_pairs, const double* qa, const double* qb, int64_t n_edges,
                               int k, uint8_t* ok, int32_t* first_bad, cudaStream_t s) {
   if (n_edges <= 0) return cudaSuccess;
-  cudaError_t e = cudaMemsetAsync(first_bad, 0x7f, sizeof(int32_t) * n_edges, s);   // 0x7f7f7f7f > any way-point index
-  if (e != cudaSuccess) return e;
-  const int64_t total = n_edges * (k + 2);
-  unsigned blocks = (unsigned)((total + EC_THREADS - 1) / EC_THREADS);
+  const int wp = k + 2;
+  const int epb = std::max(1, std::min(EC_MAX_EDGES, EC_THREADS / wp));      // whole edges per block
+  const int threads = std::max(32, std::min(EC_THREADS, (epb * wp + 31) / 32 * 32));
+  const unsigned blocks = (unsigned)((n_edges + epb - 1) / epb);
   static const bool full = getenv("NWB_EDGE_FULL") != nullptr;    // roofline runs: evaluate every way-point
   if (static_pairs) {
-    if (full) edge_check_kernel<true, false><<<blocks, EC_THREADS, 0, s>>>(tab, qa, qb, n_edges, k, first_bad);
-    else edge_check_kernel<true, true><<<blocks, EC_THREADS, 0, s>>>(tab, qa, qb, n_edges, k, first_bad);
+    if (full) edge_check_kernel<true, false><<<blocks, threads, 0, s>>>(tab, qa, qb, n_edges, k, epb, ok, first_bad);
+    else edge_check_kernel<true, true><<<blocks, threads, 0, s>>>(tab, qa, qb, n_edges, k, epb, ok, first_bad);
   } else {
-    if (full) edge_check_kernel<false, false><<<blocks, EC_THREADS, 0, s>>>(tab, qa, qb, n_edges, k, first_bad);
-    else edge_check_kernel<false, true><<<blocks, EC_THREADS, 0, s>>>(tab, qa, qb, n_edges, k, first_bad);
+    if (full) edge_check_kernel<false, false><<<blocks, threads, 0, s>>>(tab, qa, qb, n_edges, k, epb, ok, first_bad);
+    else edge_check_kernel<false, true><<<blocks, threads, 0, s>>>(tab, qa, qb, n_edges, k, epb, ok, first_bad);
   }
-  edge_finish_kernel<<<(unsigned)((n_edges + 127) / 128), 128, 0, s>>>(first_bad, n_edges, ok);
   return cudaGetLastError();
 }
 
