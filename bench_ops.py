@@ -228,8 +228,11 @@ def main():
     # ---- steer + project ------------------------------------------------------------------------------------
     n = 1 << 18
     wp = w.ctypes.data_as(C.c_void_p)
+    big = OL.uniform_configs(2 << 20, seed=20121009, lhyp_zero=True)
     for tag, near, target in (("db_rows", db[rng.integers(0, len(db), n)], db[rng.integers(0, len(db), n)]),
-                              ("uniform_configs", nodes_all[:n], nodes_all[n:2 * n])):
+                              ("uniform_configs", nodes_all[:n], nodes_all[n:2 * n]),
+                              ("uniform_configs_2^20", big[:1 << 20], big[1 << 20:])):
+        n = len(near)
         with torch.cuda.stream(stream):
             near_d, tgt_d = torch.from_numpy(np.ascontiguousarray(near)).to(dev), torch.from_numpy(np.ascontiguousarray(target)).to(dev)
             out_d = torch.empty_like(near_d)

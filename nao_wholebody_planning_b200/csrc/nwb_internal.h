@@ -182,6 +182,7 @@ cudaError_t launch_rrt_fused(const PlanConst& pc, const ValidityTables& tab, boo
                              unsigned long long* path_used, long long path_cap, const double* db, int n_db, int max_iter, int nq,
                              const double* ma_pts, int n_pts, int32_t* overflow_flag, cudaStream_t s);
 // scratch: 256 + 4 n bytes of device memory selects the two-launch form for n >= 4096 (nullptr: one launch)
+size_t steer_scratch_bytes(int64_t n);     // scratch of the phased form of launch_steer_project (n >= 4096)
 cudaError_t launch_steer_project(const PlanConst& pc, const double* q_near, const double* q_target, int64_t n, double* q_out,
                                  int32_t* status, int32_t* ds_status, int32_t* iters, void* scratch, cudaStream_t s);
 // rows [e][0 .. n_added[e]) of nodes [n_edges][max_steps][21] -> packed[offset[e] ..] (dense, edge order)

@@ -52,7 +52,7 @@ int nwb_steer_project_batch_dev(nwb_ctx* ctx, const double* q_near, const double
   P_CUDA(ctx, cudaSetDevice(ctx->device));
   PlanConst pc;
   make_plan_const(ctx, weights, step, pc);
-  const size_t work_need = 256 + sizeof(uint32_t) * (size_t)std::max<int64_t>(n, 0);
+  const size_t work_need = steer_scratch_bytes(n);
   if (n >= 4096 && ctx->d_work_bytes < work_need) {
     if (ctx->d_work) cudaFree(ctx->d_work);
     ctx->d_work = nullptr;
@@ -65,7 +65,7 @@ int nwb_steer_project_batch_dev(nwb_ctx* ctx, const double* q_near, const double
                                    ctx->stream));
   P_CUDA(ctx, ev_record(ctx, ctx->ev1, ctx->stream));
   ctx->last_ms = -1;
-  ctx->last_launches = n >= 4096 ? 2 : (n > 0);
+  ctx->last_launches = n >= 4096 ? 3 : (n > 0);
   return NWB_OK;
 }
 

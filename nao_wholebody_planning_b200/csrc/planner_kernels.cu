@@ -136,30 +136,16 @@ steer_filter_kernel(const __grid_constant__ PlanConst pc, const double* __restri
   const unsigned slot = steer_warp_append(need, counter);
   if (need) work[slot] = (uint32_t)i;
 }
-__global__ void __launch_bounds__(64, 2 * NWB_STEER_MIN_BLOCKS)   // 12 warps per SM, as the one-launch form
-steer_solve_kernel(const __grid_constant__ PlanConst pc, const double* __restrict__ q_near, const double* __restrict__ q_target,
-                   const uint32_t* __restrict__ work, const unsigned* __restrict__ counter, double* __restrict__ q_out,
-                   int32_t* __restrict__ status, int32_t* __restrict__ ds_status, int32_t* __restrict__ iters) {
-  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= (int64_t)*counter) return;
-  const int64_t i = work[w];
-  double a[NWB_NJ], b[NWB_NJ], q[NWB_NJ];
-  for (int j = 0; j < NWB_NJ; ++j) {
-    a[j] = q_near[i * NWB_NJ + j];
-    b[j] = q_target[i * NWB_NJ + j];
-  }
-  generate_q_new(a, b, pc, q);
-  double rl[5], ll[5], V[5][5];
-#pragma unroll
-  for (int m = 0; m < 5; ++m) {
-    rl[m] = -q[m];
-    ll[m] = q[16 + m];
-  }
-  DFrame hip, target;
-  right_leg_fk(rl, hip);
-  desired_left_leg_pose(hip, target);
-  nr_identity(V);
-  const int it = left_leg_ik_nr_span(target, ll, V, 0, pc.ik_maxiter, pc.ik_eps, pc.pinv_eps);
+// The solve is split once more, as in the database sampler: the head runs the first kSteerHead Newton-Raphson iterations
+// of every packed pair; a solve that is still running hands its state (5 joints + the 5x5 right singular vectors,
+// struct-of-arrays) to a second packed list and the tail kernel resumes it, again on full warps.  After the exact
+// rejection rule a quarter of the packed solves still fail the slow way (all `maxiter` iterations): without the split
+// every warp of 32 solves contains one and runs 100 iterations.  counters[0] = |work|, counters[1] = |tail|.
+constexpr int kSteerHead = 10;
+constexpr int kSteerTailState = 30;
+__device__ __forceinline__ void steer_finish(const PlanConst& pc, int64_t i, int it, double* q, const double* ll,
+                                             double* __restrict__ q_out, int32_t* __restrict__ status,
+                                             int32_t* __restrict__ ds_status, int32_t* __restrict__ iters) {
   const bool ok = it >= 0 && limits_ok(ll, pc.jmin + 16, pc.jmax + 16, 5);
   if (iters) iters[i] = it >= 0 ? it + 1 : pc.ik_maxiter;
   if (ds_status) ds_status[i] = ok ? NWB_ADVANCED : NWB_TRAPPED;
@@ -169,6 +155,85 @@ steer_solve_kernel(const __grid_constant__ PlanConst pc, const double* __restric
     for (int m = 0; m < 5; ++m) q[16 + m] = ll[m];
     for (int j = 0; j < NWB_NJ; ++j) q_out[i * NWB_NJ + j] = q[j];
   }
+}
+__global__ void __launch_bounds__(64, 2 * NWB_STEER_MIN_BLOCKS)   // 12 warps per SM, as the one-launch form
+steer_solve_kernel(const __grid_constant__ PlanConst pc, const double* __restrict__ q_near, const double* __restrict__ q_target,
+                   const uint32_t* __restrict__ work, unsigned* __restrict__ counters, uint32_t* __restrict__ tail_i,
+                   double* __restrict__ tail_state, unsigned tail_cap, double* __restrict__ q_out,
+                   int32_t* __restrict__ status, int32_t* __restrict__ ds_status, int32_t* __restrict__ iters) {
+  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = w < (int64_t)counters[0];
+  if (__ballot_sync(0xffffffffu, active) == 0u) return;
+  int64_t i = 0;
+  double q[NWB_NJ], ll[5], V[5][5];
+  DFrame target;
+  int it = -1;
+  const int head = pc.ik_maxiter < kSteerHead ? pc.ik_maxiter : kSteerHead;
+  if (active) {
+    i = work[w];
+    double a[NWB_NJ], b[NWB_NJ];
+    for (int j = 0; j < NWB_NJ; ++j) {
+      a[j] = q_near[i * NWB_NJ + j];
+      b[j] = q_target[i * NWB_NJ + j];
+    }
+    generate_q_new(a, b, pc, q);
+    double rl[5];
+#pragma unroll
+    for (int m = 0; m < 5; ++m) {
+      rl[m] = -q[m];
+      ll[m] = q[16 + m];
+    }
+    DFrame hip;
+    right_leg_fk(rl, hip);
+    desired_left_leg_pose(hip, target);
+    nr_identity(V);
+    it = left_leg_ik_nr_span(target, ll, V, 0, head, pc.ik_eps, pc.pinv_eps);
+  }
+  const bool more = active && it < 0 && head < pc.ik_maxiter;
+  const unsigned slot = steer_warp_append(more, counters + 1);
+  if (more) {
+    if (slot < tail_cap) {
+      tail_i[slot] = (uint32_t)i;
+#pragma unroll
+      for (int m = 0; m < 5; ++m) tail_state[(size_t)m * tail_cap + slot] = ll[m];
+#pragma unroll
+      for (int a = 0; a < 5; ++a)
+#pragma unroll
+        for (int b = 0; b < 5; ++b) tail_state[(size_t)(5 + 5 * a + b) * tail_cap + slot] = V[a][b];
+      return;
+    }
+    it = left_leg_ik_nr_span(target, ll, V, head, pc.ik_maxiter, pc.ik_eps, pc.pinv_eps);   // list full: finish in place
+  }
+  if (active) steer_finish(pc, i, it, q, ll, q_out, status, ds_status, iters);
+}
+__global__ void __launch_bounds__(64, 2 * NWB_STEER_MIN_BLOCKS)
+steer_tail_kernel(const __grid_constant__ PlanConst pc, const double* __restrict__ q_near, const double* __restrict__ q_target,
+                  const unsigned* __restrict__ counters, const uint32_t* __restrict__ tail_i, const double* __restrict__ tail_state,
+                  unsigned tail_cap, double* __restrict__ q_out, int32_t* __restrict__ status, int32_t* __restrict__ ds_status,
+                  int32_t* __restrict__ iters) {
+  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned queued = counters[1] < tail_cap ? counters[1] : tail_cap;
+  if (w >= (int64_t)queued) return;
+  const int64_t i = tail_i[w];
+  double a[NWB_NJ], b[NWB_NJ], q[NWB_NJ], rl[5], ll[5], V[5][5];
+  for (int j = 0; j < NWB_NJ; ++j) {
+    a[j] = q_near[i * NWB_NJ + j];
+    b[j] = q_target[i * NWB_NJ + j];
+  }
+  generate_q_new(a, b, pc, q);
+#pragma unroll
+  for (int m = 0; m < 5; ++m) rl[m] = -q[m];
+  DFrame hip, target;
+  right_leg_fk(rl, hip);
+  desired_left_leg_pose(hip, target);
+#pragma unroll
+  for (int m = 0; m < 5; ++m) ll[m] = tail_state[(size_t)m * tail_cap + w];
+#pragma unroll
+  for (int r = 0; r < 5; ++r)
+#pragma unroll
+    for (int c = 0; c < 5; ++c) V[r][c] = tail_state[(size_t)(5 + 5 * r + c) * tail_cap + w];
+  const int it = left_leg_ik_nr_span(target, ll, V, kSteerHead, pc.ik_maxiter, pc.ik_eps, pc.pinv_eps);
+  steer_finish(pc, i, it, q, ll, q_out, status, ds_status, iters);
 }
 
 // ---- connect: one thread walks one edge -------------------------------------------------------------
@@ -1036,6 +1101,11 @@ sample_tail_kernel(const __grid_constant__ PlanConst pc, const __grid_constant__
 }
 
 // ---- launchers -------------------------------------------------------------------------------------------------
+static unsigned steer_tail_cap(int64_t n) { return (unsigned)std::max<int64_t>(1024, n / 4); }
+size_t steer_scratch_bytes(int64_t n) {      // counters | tail state [30][cap] | tail index [cap] | work [n]
+  const size_t tc = steer_tail_cap(n);
+  return 256 + sizeof(double) * kSteerTailState * tc + sizeof(uint32_t) * tc + sizeof(uint32_t) * (size_t)std::max<int64_t>(n, 0);
+}
 cudaError_t launch_steer_project(const PlanConst& pc, const double* q_near, const double* q_target, int64_t n, double* q_out,
                                  int32_t* status, int32_t* ds_status, int32_t* iters, void* scratch, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
@@ -1043,12 +1113,18 @@ cudaError_t launch_steer_project(const PlanConst& pc, const double* q_near, cons
     steer_project_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(pc, q_near, q_target, n, q_out, status, ds_status, iters);
     return cudaGetLastError();
   }
-  unsigned* counter = static_cast<unsigned*>(scratch);         // scratch: 256 + 4 n bytes
-  uint32_t* work = reinterpret_cast<uint32_t*>(static_cast<char*>(scratch) + 256);
-  cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned), s);
+  const unsigned tc = steer_tail_cap(n);
+  unsigned* counters = static_cast<unsigned*>(scratch);        // scratch: steer_scratch_bytes(n)
+  double* tail_state = reinterpret_cast<double*>(static_cast<char*>(scratch) + 256);
+  uint32_t* tail_i = reinterpret_cast<uint32_t*>(tail_state + (size_t)kSteerTailState * tc);
+  uint32_t* work = tail_i + tc;
+  cudaError_t e = cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned), s);
   if (e != cudaSuccess) return e;
-  steer_filter_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(pc, q_near, q_target, n, q_out, status, ds_status, iters, work, counter);
-  steer_solve_kernel<<<(unsigned)((n + 63) / 64), 64, 0, s>>>(pc, q_near, q_target, work, counter, q_out, status, ds_status, iters);
+  steer_filter_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(pc, q_near, q_target, n, q_out, status, ds_status, iters, work, counters);
+  // the list sizes stay on the device: launch for the worst case, surplus blocks leave at once
+  steer_solve_kernel<<<(unsigned)((n + 63) / 64), 64, 0, s>>>(pc, q_near, q_target, work, counters, tail_i, tail_state, tc, q_out, status,
+                                                             ds_status, iters);
+  steer_tail_kernel<<<(tc + 63) / 64, 64, 0, s>>>(pc, q_near, q_target, counters, tail_i, tail_state, tc, q_out, status, ds_status, iters);
   return cudaGetLastError();
 }
 
