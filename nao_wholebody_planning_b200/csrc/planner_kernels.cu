@@ -878,19 +878,20 @@ rrt_fused_kernel(const __grid_constant__ PlanConst pc, const __grid_constant__ V
 }
 
 // ---- edge check: (edge, way-point) -> collision-only validity ------------------------------------------
-// ONE launch.  A block owns whole edges (as many as fit its threads: 5 edges x 102 way-points in 512 threads), so the
+// ONE launch.  A block owns whole edges (as many as fill two passes of its 256 threads: 5 edges x 102 way-points), so the
 // first colliding way-point of an edge is a shared-memory minimum and the block writes ok / first_bad itself - no
 // memset before, no finishing kernel after, no global atomics.  The end points of the block's edges are staged in shared
 // memory once (start + step width per joint, fp64 as interpolateWaypoints computes them, RP:1758-1771); each thread
 // forms its way-point and evaluates the whole-robot collision predicate in registers.
-constexpr int EC_THREADS = 512;
+constexpr int EC_THREADS = 256;     // two resident blocks per SM: one block's epilogue overlaps the other's evaluation
+constexpr int EC_SLOTS = 512;       // (edge, way-point) slots a block aims at: two passes of its threads
 constexpr int EC_MAX_EDGES = 64;    // edges per block (reached only for k + 2 <= 8 way-points per edge)
 
 // EARLY_EXIT: a way-point whose edge already has an earlier colliding way-point on record is skipped;
 // the warp votes (ballot) and moves on together, so no lane idles through a full evaluation for an
 // edge that is already lost.  Results (ok, first_bad) are identical to the full evaluation.
 template <bool STATIC, bool EARLY_EXIT>
-__global__ void __launch_bounds__(EC_THREADS, 1)
+__global__ void __launch_bounds__(EC_THREADS, 2)
 edge_check_kernel(const __grid_constant__ ValidityTables tab, const double* __restrict__ qa, const double* __restrict__ qb,
                   int64_t n_edges, int k, int edges_per_block, uint8_t* __restrict__ ok, int32_t* __restrict__ first_bad) {
   __shared__ double s_a[EC_MAX_EDGES][NWB_NJ], s_sw[EC_MAX_EDGES][NWB_NJ];
@@ -907,7 +908,7 @@ edge_check_kernel(const __grid_constant__ ValidityTables tab, const double* __re
   if (threadIdx.x < ne) s_bad[threadIdx.x] = 0x7fffffff;
   __syncthreads();
   const int total = ne * wp;
-  for (int base = 0; base < total; base += blockDim.x) {  // one pass unless an edge alone has more way-points than the block threads
+  for (int base = 0; base < total; base += blockDim.x) {  // two passes for 5 x 102 way-points; more when one edge alone is longer
     const int slot = base + threadIdx.x;
     const bool active = slot < total;
     if (__ballot_sync(0xffffffffu, active) == 0u) continue;
@@ -1187,7 +1188,7 @@ cudaError_t launch_edge_check(const ValidityTables& tab, bool static_pairs, cons
                               int k, uint8_t* ok, int32_t* first_bad, cudaStream_t s) {
   if (n_edges <= 0) return cudaSuccess;
   const int wp = k + 2;
-  const int epb = std::max(1, std::min(EC_MAX_EDGES, EC_THREADS / wp));      // whole edges per block
+  const int epb = std::max(1, std::min(EC_MAX_EDGES, EC_SLOTS / wp));        // whole edges per block
   const int threads = std::max(32, std::min(EC_THREADS, (epb * wp + 31) / 32 * 32));
   const unsigned blocks = (unsigned)((n_edges + epb - 1) / epb);
   static const bool full = getenv("NWB_EDGE_FULL") != nullptr;    // roofline runs: evaluate every way-point

@@ -20,7 +20,8 @@ q = torch.from_numpy(OL.golden_db()[:1].copy()).cuda()
 idx = torch.empty(1, dtype=torch.int32, device="cuda")
 dist = torch.empty(1, dtype=torch.float64, device="cuda")
 nodes = OL.uniform_configs(1_000_000, seed=20121001, lhyp_zero=True)
-for n in (0, 10_000, 100_000, 200_000, 300_000, 1_000_000):
+sizes = [int(a) for a in sys.argv[1:]] or [0, 10_000, 100_000, 200_000, 300_000, 1_000_000]
+for n in sizes:
     tree = nwb.Tree(ctx, max(n, 1))
     if n:
         tree.add(nodes[:n])
