@@ -368,8 +368,10 @@ def section_dbgen(torch, dist, nwb, sharding, ctx, orc, dev, rank, world, barrie
         n_acc = int(torch.as_tensor(_Raw(p_cnt, (1,), "<u8"), device=dev).cpu().numpy().view(np.uint64)[0])
         g_idx = torch.as_tensor(_Raw(p_idx, (min(n_acc, cap),), "<i8"), device=dev)
         g_rows = torch.as_tensor(_Raw(p_rows, (min(n_acc, cap), 21), "<f8"), device=dev)
-        # order-independent digest of the accepted set: must be equal at every GPU count
-        digest = [n_acc, int((g_idx % 1000003).sum().item()), float(g_rows.sum().item())]
+        # order-independent digest of the accepted set: must be equal at every GPU count.  The rows are summed as the
+        # int64 bit patterns of their doubles (wrap-around addition is exact and commutative); a floating-point sum
+        # would change in its last digit with the order in which the ranks' appends land.
+        digest = [n_acc, int((g_idx % 1000003).sum().item()), int(g_rows.view(torch.int64).sum().item())]
         res["strong_scaled"] = {"samples": total, "accepted": n_acc, "seconds": dt, "samples_per_s": total / dt, "n_gpus": world,
                                 "digest": digest, "overflowed": bool(n_acc > cap), "scaling": "strong", "timing": "CUDA events on the library stream, max over ranks",
                                 "gather": "fused: accepted rows appended into rank 0's arrays through peer-mapped memory inside the sampler kernel"}
