@@ -56,10 +56,8 @@ __device__ __forceinline__ void dframe_identity(DFrame& f) {
   f.r[0] = 1; f.r[1] = 0; f.r[2] = 0; f.r[3] = 0; f.r[4] = 1; f.r[5] = 0; f.r[6] = 0; f.r[7] = 0; f.r[8] = 1;
   f.p = d3(0, 0, 0);
 }
-// f.R <- f.R * RotX(a) / RotY(a)  (KDL::Rotation::RotX/RotY)
-__device__ __forceinline__ void drotx(DFrame& f, double a) {
-  double s, c;
-  sincos(a, &s, &c);
+// f.R <- f.R * RotX(a) / RotY(a)  (KDL::Rotation::RotX/RotY); the _sc forms take sin / cos of the angle
+__device__ __forceinline__ void drotx_sc(DFrame& f, double s, double c) {
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     double u = f.r[3 * k + 1], v = f.r[3 * k + 2];
@@ -67,15 +65,23 @@ __device__ __forceinline__ void drotx(DFrame& f, double a) {
     f.r[3 * k + 2] = c * v - s * u;
   }
 }
-__device__ __forceinline__ void droty(DFrame& f, double a) {
-  double s, c;
-  sincos(a, &s, &c);
+__device__ __forceinline__ void droty_sc(DFrame& f, double s, double c) {
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     double u = f.r[3 * k + 0], v = f.r[3 * k + 2];
     f.r[3 * k + 0] = c * u - s * v;
     f.r[3 * k + 2] = s * u + c * v;
   }
+}
+__device__ __forceinline__ void drotx(DFrame& f, double a) {
+  double s, c;
+  sincos(a, &s, &c);
+  drotx_sc(f, s, c);
+}
+__device__ __forceinline__ void droty(DFrame& f, double a) {
+  double s, c;
+  sincos(a, &s, &c);
+  droty_sc(f, s, c);
 }
 __device__ __forceinline__ void dtrans(DFrame& f, double x, double y, double z) { f.p = f.p + rmul(f.r, d3(x, y, z)); }
 
@@ -88,6 +94,24 @@ __device__ __forceinline__ void right_leg_fk(const double* legs5, DFrame& f) {
   droty(f, legs5[2]); dtrans(f, 0, 0, 0.1);
   droty(f, legs5[3]);
   drotx(f, legs5[4]); dtrans(f, 0, 0.05, 0);
+}
+// the same two chains with the sines / cosines of their five joint angles supplied (computed on five lanes of a warp)
+__device__ __forceinline__ void right_leg_fk_sc(const double* sn, const double* cs, DFrame& f) {
+  dframe_identity(f);
+  f.p = d3(0, 0, 0.04519);
+  drotx_sc(f, sn[0], cs[0]);
+  droty_sc(f, sn[1], cs[1]); dtrans(f, 0, 0, 0.1029);
+  droty_sc(f, sn[2], cs[2]); dtrans(f, 0, 0, 0.1);
+  droty_sc(f, sn[3], cs[3]);
+  drotx_sc(f, sn[4], cs[4]); dtrans(f, 0, 0.05, 0);
+}
+__device__ __forceinline__ void left_leg_fk_sc(const double* sn, const double* cs, DFrame& f) {
+  dtrans(f, 0, 0.05, 0);
+  drotx_sc(f, sn[0], cs[0]);
+  droty_sc(f, sn[1], cs[1]); dtrans(f, 0, 0, -0.1);
+  droty_sc(f, sn[2], cs[2]); dtrans(f, 0, 0, -0.1029);
+  droty_sc(f, sn[3], cs[3]);
+  drotx_sc(f, sn[4], cs[4]); dtrans(f, 0, 0, -0.04519);
 }
 
 // chain_left_leg_ (hip -> sole), local_planner.cpp:26-31, appended to `f`; optionally records the
@@ -416,6 +440,86 @@ __device__ __forceinline__ int enforce_ds_constraints(double* q, const PlanConst
 #pragma unroll
   for (int i = 0; i < 5; ++i) q[16 + i] = ll[i];
   return NWB_ADVANCED;
+}
+
+// ---- generate_q_new + enforce_DS_Constraints by one WARP for one pair (the RRT kernels) --------------------------
+// The arithmetic is that of the two functions above, operation for operation (the parity tests compare iteration counts
+// of whole searches); what changes is who does it.  Every lane forms the two serial sums itself (same order, same
+// roundings), lane j takes the division and the joint-limit test of joint j, lanes 0-9 the fp64 sincos of the ten leg
+// angles (~100 instructions each, the largest serial item of the walk), and lane 0 keeps the matrix chain, the foot
+// error and - where the foot is off target - the Newton-Raphson solve.
+struct WarpSteer {
+  double near[NWB_NJ];   // q_near (in)
+  double inc[NWB_NJ];    // scratch
+  double sn[10], cs[10]; // sines / cosines of (-q[0..4], q[16..20])
+};
+// tgt = q_rand / q_connect, q = result (both 21 doubles in shared memory).  Returns NWB_TRAPPED / ADVANCED / REACHED, uniform.
+__device__ __forceinline__ int warp_steer_project(const PlanConst& pc, WarpSteer& ws, const double* tgt, double* q, int lane) {
+  const unsigned FULL = 0xffffffffu;
+  double sum = 0;
+  for (int i = 0; i < NWB_NJ; ++i) {
+    const double di = tgt[i] - ws.near[i];
+    sum = __dadd_rn(sum, __dmul_rn(di, di));
+  }
+  const double norm = sqrt(sum);
+  if (lane < NWB_NJ) {
+    const double dir = (tgt[lane] - ws.near[lane]) / norm;
+    ws.inc[lane] = __dmul_rn(pc.step, __dmul_rn(dir, pc.weights[lane]));
+  }
+  __syncwarp();
+  double sum_inc = 0;
+  for (int j = 0; j < NWB_NJ; ++j) sum_inc = __dadd_rn(sum_inc, __dmul_rn(ws.inc[j], ws.inc[j]));
+  const double norm_inc = sqrt(sum_inc);
+  int st = norm_inc < norm ? NWB_ADVANCED : NWB_REACHED;
+  bool ok = true;
+  if (lane < NWB_NJ) {
+    const double v = st == NWB_ADVANCED ? ws.near[lane] + ws.inc[lane] : tgt[lane];
+    q[lane] = v;
+    const double mn = pc.jmin[lane], mx = pc.jmax[lane];
+    const double lo = fmin(mn, mx), hi = fmax(mn, mx);
+    if (mn != mx) ok = (v > lo) && (v < hi);
+  }
+  if (!__all_sync(FULL, ok)) return NWB_TRAPPED;
+  if (lane < 5 || (lane >= 16 && lane < NWB_NJ)) {        // right-leg chain runs on -q[0..4], left-leg chain on q[16..20]
+    const int slot = lane < 5 ? lane : 5 + lane - 16;
+    const double a = lane < 5 ? -q[lane] : q[lane];
+    sincos(a, &ws.sn[slot], &ws.cs[slot]);
+  }
+  __syncwarp();
+  int ds = NWB_REACHED;
+  if (lane == 0) {
+    DFrame hip;
+    right_leg_fk_sc(ws.sn, ws.cs, hip);
+    DFrame foot = hip;
+    left_leg_fk_sc(ws.sn + 5, ws.cs + 5, foot);
+    const double des[3] = {nwbm::kLeftSoleTarget[0], nwbm::kLeftSoleTarget[1], nwbm::kLeftSoleTarget[2]};
+    const double act[3] = {foot.p.x, foot.p.y, foot.p.z};
+    double max_err = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      double e = des[i] - act[i];
+      if (!(pc.quirks & NWB_QUIRK_SIGNED_FOOT_ERROR)) e = fabs(e);
+      if (e > max_err) max_err = e;
+    }
+    if (max_err > pc.ds_tolerance) {
+      double ll[5];
+#pragma unroll
+      for (int i = 0; i < 5; ++i) ll[i] = q[16 + i];
+      DFrame target;
+      desired_left_leg_pose(hip, target);
+      if (!left_leg_ik_nr(target, ll, pc.ik_maxiter, pc.ik_eps, pc.pinv_eps, nullptr) || !limits_ok(ll, pc.jmin + 16, pc.jmax + 16, 5)) {
+        ds = NWB_TRAPPED;
+      } else {
+        ds = NWB_ADVANCED;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) q[16 + i] = ll[i];
+      }
+    }
+  }
+  ds = __shfl_sync(FULL, ds, 0);
+  __syncwarp();
+  if (ds == NWB_TRAPPED) return NWB_TRAPPED;
+  return ds == NWB_ADVANCED ? NWB_ADVANCED : st;
 }
 
 // ---- Philox4x32-10 counter-based stream (DESIGN.md "random streams") ---------------------------

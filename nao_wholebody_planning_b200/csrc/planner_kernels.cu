@@ -574,8 +574,8 @@ struct RrtOutcome {
 template <bool STATIC>
 __device__ __forceinline__ RrtOutcome rrt_query_loop(const PlanConst& pc, const ValidityTables& tab, const ForestView& F, int k, int lane,
                                                      uint64_t seed, const double* __restrict__ db, int n_db, int max_iter,
-                                                     const MaView& ma, double* qd, float* qf, double* qv, int (&size)[2],
-                                                     int32_t* overflow_flag) {
+                                                     const MaView& ma, double* qd, float* qf, double* qv, WarpSteer& ws,
+                                                     int (&size)[2], int32_t* overflow_flag) {
   const unsigned FULL = 0xffffffffu;
   int swap = 0, done = 0, success = 0, connector = 0, bridge = 0, it = 0;
   for (; it < max_iter && !done; ++it) {
@@ -595,30 +595,20 @@ __device__ __forceinline__ RrtOutcome rrt_query_loop(const PlanConst& pc, const 
     const int idx_a = warp_nearest(F, ta, size[ta & 1], qd, qf, lane);
     const bool a_start = (ta & 1) == 0;
     int near_hand = 0, go = 0;
-    if (lane == 0) {
-      double near[NWB_NJ], tgt[NWB_NJ], q[NWB_NJ];
-      const double* nrow = F.aos + ((size_t)ta * F.cap + idx_a) * NWB_NJ;
-      for (int j = 0; j < NWB_NJ; ++j) {
-        near[j] = nrow[j];
-        tgt[j] = qd[j];
-      }
-      int st = generate_q_new(near, tgt, pc, q);
-      const int ds = enforce_ds_constraints(q, pc, nullptr);
-      if (ds == NWB_TRAPPED) st = NWB_TRAPPED;
-      else if (ds == NWB_ADVANCED) st = NWB_ADVANCED;
-      if (st != NWB_TRAPPED && ma.pts) {                  // enforce_MA_Constraints (RP:829-837)
+    if (lane < NWB_NJ) ws.near[lane] = F.aos[((size_t)ta * F.cap + idx_a) * NWB_NJ + lane];
+    __syncwarp();
+    int st = warp_steer_project(pc, ws, qd, qv, lane);    // generate_q_new + enforce_DS_Constraints: qv = the candidate node
+    if (st != NWB_TRAPPED && ma.pts) {                    // enforce_MA_Constraints (RP:829-837), lane 0
+      if (lane == 0) {
         near_hand = F.hand[(size_t)ta * F.cap + idx_a];
-        const int mas = enforce_ma_constraints(ma, a_start, near_hand, near, q, pc);
+        const int mas = enforce_ma_constraints(ma, a_start, near_hand, ws.near, qv, pc);
         if (mas == NWB_TRAPPED) st = NWB_TRAPPED;
         else if (mas == NWB_ADVANCED) st = NWB_ADVANCED;
       }
-      if (st != NWB_TRAPPED) {
-        go = 1;
-        for (int j = 0; j < NWB_NJ; ++j) qv[j] = q[j];
-      }
+      st = __shfl_sync(FULL, st, 0);
+      __syncwarp();
     }
-    __syncwarp();
-    go = __shfl_sync(FULL, go, 0);
+    go = st != NWB_TRAPPED;
     int walking = 0, connect_hand = 0;
     if (go) {
       const bool valid = config_valid<STATIC>(tab, qv, lane);         // isConfigValid (RP:846), all lanes
@@ -657,49 +647,32 @@ __device__ __forceinline__ RrtOutcome rrt_query_loop(const PlanConst& pc, const 
       int32_t* pred = F.pred + (size_t)tb * F.cap;
       int32_t* hand = ma.pts ? F.hand + (size_t)tb * F.cap : nullptr;
       int sz = size[tb & 1];
-      // lane 0's walk state
-      double cur[NWB_NJ], tgt[NWB_NJ];
+      // the walk's current node lives in ws.near (shared); its index / hand index on lane 0
       int cur_idx = idx_b, state = NWB_ADVANCED, cur_hand = 0;
-      if (lane == 0) {
-        for (int j = 0; j < NWB_NJ; ++j) {
-          cur[j] = aos[(size_t)idx_b * NWB_NJ + j];
-          tgt[j] = qd[j];
-        }
-        if (ma.pts) {
-          cur_hand = hand[cur_idx];
-          if ((b_start && cur_hand > connect_hand) || (!b_start && cur_hand < connect_hand)) state = NWB_TRAPPED;   // RP:917-922
-        }
+      if (lane < NWB_NJ) ws.near[lane] = aos[(size_t)idx_b * NWB_NJ + lane];
+      if (lane == 0 && ma.pts) {
+        cur_hand = hand[cur_idx];
+        if ((b_start && cur_hand > connect_hand) || (!b_start && cur_hand < connect_hand)) state = NWB_TRAPPED;   // RP:917-922
       }
       state = __shfl_sync(FULL, state, 0);
+      __syncwarp();
       while (state == NWB_ADVANCED) {
-        int need = 0;                                     // 1: a candidate node waits in qv for its validity test
-        if (lane == 0) {
-          double q[NWB_NJ];
-          state = generate_q_new(cur, tgt, pc, q);
-          const int ds = enforce_ds_constraints(q, pc, nullptr);
-          if (ds == NWB_TRAPPED) state = NWB_TRAPPED;
-          else {
-            if (ds == NWB_ADVANCED) state = NWB_ADVANCED;
+        state = warp_steer_project(pc, ws, qd, qv, lane);  // qd = q_connect; qv = the candidate node
+        if (state != NWB_TRAPPED && ma.pts) {             // RP:951-972, lane 0
+          if (lane == 0) {
             bool proceed = true;
-            if (ma.pts) {                                 // RP:951-972
-              const int mas = enforce_ma_constraints(ma, b_start, cur_hand, cur, q, pc);
-              if (mas == NWB_TRAPPED) proceed = false;
-              else {
-                if (mas == NWB_ADVANCED) state = NWB_ADVANCED;
-                if (cur_hand == connect_hand && state != NWB_REACHED) proceed = false;
-              }
+            const int mas = enforce_ma_constraints(ma, b_start, cur_hand, ws.near, qv, pc);
+            if (mas == NWB_TRAPPED) proceed = false;
+            else {
+              if (mas == NWB_ADVANCED) state = NWB_ADVANCED;
+              if (cur_hand == connect_hand && state != NWB_REACHED) proceed = false;
             }
             if (!proceed) state = NWB_TRAPPED;
-            else {
-              need = 1;
-              for (int j = 0; j < NWB_NJ; ++j) qv[j] = q[j];
-            }
           }
+          state = __shfl_sync(FULL, state, 0);            // ADVANCED / REACHED with a candidate in qv, TRAPPED otherwise
+          __syncwarp();
         }
-        __syncwarp();
-        need = __shfl_sync(FULL, need, 0);
-        state = __shfl_sync(FULL, state, 0);              // ADVANCED / REACHED when need, TRAPPED otherwise
-        if (!need) break;
+        if (state == NWB_TRAPPED) break;
         const bool valid = config_valid<STATIC>(tab, qv, lane);
         if (!valid) { state = NWB_TRAPPED; break; }
         if (sz >= F.cap) {
@@ -721,9 +694,9 @@ __device__ __forceinline__ RrtOutcome rrt_query_loop(const PlanConst& pc, const 
           } else {
             cur_idx = sz;                                 // RP:1004
             cur_hand = new_hand;
-            for (int j = 0; j < NWB_NJ; ++j) cur[j] = qv[j];
           }
         }
+        if (state != NWB_REACHED && lane < NWB_NJ) ws.near[lane] = qv[lane];   // RP:1004: the next step starts from the projected node
         ++sz;
         __syncwarp();
       }
@@ -756,9 +729,10 @@ rrt_persistent_kernel(const __grid_constant__ PlanConst pc, const __grid_constan
   __shared__ double qd[NWB_NJ];          // current query of the nearest-neighbour scan (q_rand, then q_connect)
   __shared__ float qf[NWB_NJ];
   __shared__ double qv[NWB_NJ];          // configuration under the warp-wide validity evaluation
+  __shared__ WarpSteer ws;               // scratch of the warp-cooperative steer + projection
   const MaView ma{ma_pts ? ma_pts + (size_t)k * n_pts * 6 : nullptr, n_pts};
   int size[2] = {F.size[2 * k], F.size[2 * k + 1]};      // kept in registers of every lane
-  const RrtOutcome o = rrt_query_loop<STATIC>(pc, tab, F, k, lane, seeds[k], db, n_db, max_iter, ma, qd, qf, qv, size, S.overflow);
+  const RrtOutcome o = rrt_query_loop<STATIC>(pc, tab, F, k, lane, seeds[k], db, n_db, max_iter, ma, qd, qf, qv, ws, size, S.overflow);
   if (lane == 0) {
     F.size[2 * k] = size[0];
     F.size[2 * k + 1] = size[1];
@@ -795,6 +769,7 @@ rrt_fused_kernel(const __grid_constant__ PlanConst pc, const __grid_constant__ V
   __shared__ double qd[NWB_NJ];
   __shared__ float qf[NWB_NJ];
   __shared__ double qv[NWB_NJ];
+  __shared__ WarpSteer ws;
   const MaView ma{ma_pts ? ma_pts + (size_t)k * n_pts * 6 : nullptr, n_pts};
   int32_t* res = io.res + (size_t)k * 12;
   const int ts = 2 * k, tg = 2 * k + 1;
@@ -828,7 +803,7 @@ rrt_fused_kernel(const __grid_constant__ PlanConst pc, const __grid_constant__ V
   __syncwarp();
   if (!ok) return;
   int size[2] = {1, 1};
-  const RrtOutcome o = rrt_query_loop<STATIC>(pc, tab, F, k, lane, io.seeds[k], db, n_db, max_iter, ma, qd, qf, qv, size, overflow_flag);
+  const RrtOutcome o = rrt_query_loop<STATIC>(pc, tab, F, k, lane, io.seeds[k], db, n_db, max_iter, ma, qd, qf, qv, ws, size, overflow_flag);
   // ---- results + raw path
   int ls = 0, lg = 0, idx_s = 0, idx_g = 0;
   long long off = -1;
