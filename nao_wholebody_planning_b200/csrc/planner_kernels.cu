@@ -368,14 +368,23 @@ __device__ __forceinline__ int warp_nearest(const ForestView& F, int t, int n, c
   double best = 10000.0;
   int besti = -1;
   float thr = 3.0e38f;
-  for (int node = lane; node < n; node += 32) {
-    float sf = 0.f;
+  for (int base = 0; base < n; base += 32) {
+    // The filter threshold is shared by the warp: whatever exact distance ANY lane has found bounds the answer, so every
+    // lane filters with the tightest one (positive floats order like their bit patterns: one REDUX per 32 nodes).  With
+    // lane-local thresholds some lane met a new local minimum in ~25 of the 31 steps of a 1000-node scan, and each such
+    // step stalls the warp behind one lane's exact fp64 distance; with the shared threshold it is ~5 steps.
+    thr = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(thr)));
+    const int node = base + lane;
+    float sf = 3.0e38f;
+    if (node < n) {
+      sf = 0.f;
 #pragma unroll
-    for (int j = 0; j < NWB_NJ; ++j) {
-      float d = qf[j] - soa[(size_t)j * F.cap + node];
-      sf = fmaf(d, d, sf);
+      for (int j = 0; j < NWB_NJ; ++j) {
+        float d = qf[j] - soa[(size_t)j * F.cap + node];
+        sf = fmaf(d, d, sf);
+      }
     }
-    if (sf <= thr) {
+    if (node < n && sf <= thr) {
       double sum = 0.0;
       const double* row = aos + (size_t)node * NWB_NJ;
       for (int j = 0; j < NWB_NJ; ++j) {
