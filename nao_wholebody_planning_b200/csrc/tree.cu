@@ -17,6 +17,7 @@
 // multiply and add, then sqrt, strict <) from the master copy.  Lexicographic (distance, index)
 // reductions (warp shuffle -> block -> last-block-done grid fold, one launch) then reproduce "first strict minimum wins".
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -31,8 +32,8 @@ namespace nwb {
 constexpr int NN_THREADS = 256;
 
 __global__ void tree_append_kernel(const double* __restrict__ src, const int32_t* __restrict__ pred_src, int64_t n,
-                                   float* __restrict__ soa, double* __restrict__ aos, int32_t* __restrict__ pred,
-                                   int64_t cap, int64_t size) {
+                                   float* __restrict__ soa, uint16_t* __restrict__ h16, double* __restrict__ aos,
+                                   int32_t* __restrict__ pred, int64_t cap, int64_t size) {
   int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n * NWB_NJ) return;
   int64_t i = e / NWB_NJ;
@@ -40,6 +41,7 @@ __global__ void tree_append_kernel(const double* __restrict__ src, const int32_t
   double v = src[e];
   aos[(size + i) * NWB_NJ + j] = v;
   soa[soa_index(size + i, j)] = (float)v;
+  h16[soa_index(size + i, j)] = __half_as_ushort(__double2half(v));     // one rounding: |error| <= half an fp16 ulp of |v|
   if (j == 0) pred[size + i] = pred_src ? pred_src[i] : -1;
 }
 
@@ -531,15 +533,33 @@ nn_small_kernel(const double* __restrict__ aos, int64_t N, const double* __restr
 constexpr int NN2_THREADS = 256;
 constexpr int NN2_TILE = 512;
 constexpr int NN2_STAGES = 4;
+constexpr int NN2_STAGES_H = 8;      // the fp16 ring holds twice the tiles in the same 172 KB
 constexpr int NN2_CAND = 1024;
 
+// HALF: the stream reads the fp16 filter copy (42 B/node instead of 84).  A node stored in fp16 is off by at most half
+// an fp16 ulp per joint, so its distance to the query moves by at most eps = sqrt(21) * (ulp16(max |node|) / 2)
+// (triangle inequality); the tree's max |node|^2 is tracked on the device.  With m the running minimum of the APPROXIMATE
+// distances, the exact nearest node w has d(w) <= m + eps, so every node that can be nearest or tie has an approximate
+// distance <= m + 2 eps: those are listed and re-evaluated in fp64 from the master copy, exactly as in the fp32 stream.
+// For joint angles (|q| < 4) eps = 4.5e-3; around the nearest of 10^6 nodes in 21 dimensions that shell holds a
+// handful of nodes.
+__device__ __forceinline__ float nn_candidate_bound16(float m2, float eps) {
+  const float m = sqrtf(m2) * (1.0f + 1e-5f) + 2.0f * eps;
+  return m * m * (1.0f + 1e-5f) + 1e-12f;
+}
+
+template <bool HALF>
 __global__ void __launch_bounds__(NN2_THREADS, 1)
-nn_stream_kernel(const float* __restrict__ soa, const double* __restrict__ aos, int64_t cap, int64_t N,
+nn_stream_kernel(const float* __restrict__ soa, const uint16_t* __restrict__ h16, const unsigned* __restrict__ max_nn,
+                 const double* __restrict__ aos, int64_t cap, int64_t N,
                  const double* __restrict__ q, double* __restrict__ part_d, int32_t* __restrict__ part_i,
                  unsigned* __restrict__ ticket, int32_t* __restrict__ idx_out, double* __restrict__ dist_out) {
+  constexpr int STAGES = HALF ? NN2_STAGES_H : NN2_STAGES;
+  constexpr size_t ELEM = HALF ? sizeof(uint16_t) : sizeof(float);
   extern __shared__ __align__(128) unsigned char nn_smem[];
-  float* ring = reinterpret_cast<float*>(nn_smem);                           // [STAGES][21][TILE]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(nn_smem + sizeof(float) * NN2_STAGES * NWB_NJ * NN2_TILE);
+  unsigned char* ring = nn_smem;                                             // [STAGES][21][TILE] floats or halves
+  uint64_t* bars = reinterpret_cast<uint64_t*>(nn_smem + ELEM * STAGES * NWB_NJ * NN2_TILE);
+  __shared__ float eps16;
   __shared__ double qd[NWB_NJ];
   __shared__ __align__(8) float2 qn2[NWB_NJ];
   __shared__ unsigned run_min;
@@ -555,23 +575,32 @@ nn_stream_kernel(const float* __restrict__ soa, const double* __restrict__ aos, 
   const int64_t lo = (nblk * blockIdx.x / gridDim.x) * SOA_BLK, hi = min(N, (nblk * (blockIdx.x + 1) / gridDim.x) * SOA_BLK);
   const int tiles = (int)((hi - lo + NN2_TILE - 1) / NN2_TILE);
   if (tid == 0) {
-    for (int sg = 0; sg < NN2_STAGES; ++sg) nn_mbar_init(&bars[sg], 1);
+    for (int sg = 0; sg < STAGES; ++sg) nn_mbar_init(&bars[sg], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     run_min = 0x7f7fffffu;
     cand_n = 0;
+    if constexpr (HALF) {
+      const float max_abs = sqrtf(__uint_as_float(*max_nn)) * (1.0f + 1e-6f);   // >= every |coordinate| of the tree
+      const int ex = max_abs > 6.1035156e-5f ? ilogbf(max_abs) : -14;           // below 2^-14 fp16 is subnormal: ulp 2^-24
+      const float half_ulp = max_abs < 6.0e4f ? ldexpf(1.0f, ex - 11) : 3.0e38f; // beyond the fp16 range: everything is a candidate
+      float qmax = 0.f;                                                          // the query is used in fp32: its own rounding
+      for (int j = 0; j < NWB_NJ; ++j) qmax = fmaxf(qmax, fabsf((float)q[j]));
+      eps16 = 4.5825757f * (half_ulp * 1.001f + qmax * 6.0e-8f) + 1e-12f;        // sqrt(21) x the per-joint errors
+    }
   }
   __syncthreads();
   auto issue = [&](int tile, int stage) {              // one bulk copy per tile: its blocks of 128 nodes are consecutive
     const int64_t t0 = lo + (int64_t)tile * NN2_TILE;
     const int64_t blocks = min((int64_t)(NN2_TILE / SOA_BLK), (hi - t0 + SOA_BLK - 1) / SOA_BLK);
-    const uint32_t bytes = (uint32_t)(blocks * SOA_BLK_FLOATS * sizeof(float));
+    const uint32_t bytes = (uint32_t)(blocks * SOA_BLK_FLOATS * ELEM);
     if (lane == 0) {
       nn_mbar_expect_tx(&bars[stage], bytes);
-      nn_bulk_g2s(ring + (size_t)stage * NWB_NJ * NN2_TILE, soa + (size_t)(t0 / SOA_BLK) * SOA_BLK_FLOATS, bytes, &bars[stage]);
+      const unsigned char* src = HALF ? reinterpret_cast<const unsigned char*>(h16) : reinterpret_cast<const unsigned char*>(soa);
+      nn_bulk_g2s(ring + (size_t)stage * NWB_NJ * NN2_TILE * ELEM, src + (size_t)(t0 / SOA_BLK) * SOA_BLK_FLOATS * ELEM, bytes, &bars[stage]);
     }
   };
   if (warp == 0)
-    for (int sg = 0; sg < NN2_STAGES && sg < tiles; ++sg) issue(sg, sg);
+    for (int sg = 0; sg < STAGES && sg < tiles; ++sg) issue(sg, sg);
   if (tid >= 32 && tid < 32 + NWB_NJ) {                // the query arrives while the first tiles are in flight
     const double v = q[tid - 32];
     qd[tid - 32] = v;
@@ -584,24 +613,34 @@ nn_stream_kernel(const float* __restrict__ soa, const double* __restrict__ aos, 
   bool flooded = false;
   for (int tile = 0; tile < tiles; ++tile) {
     nn_mbar_wait(&bars[stage], phase);
-    const float* x = ring + (size_t)stage * NWB_NJ * NN2_TILE;
     const int64_t t0 = lo + (int64_t)tile * NN2_TILE;
     float2 s2 = make_float2(0.f, 0.f);
+    if constexpr (HALF) {
+      const __half* x = reinterpret_cast<const __half*>(ring + (size_t)stage * NWB_NJ * NN2_TILE * ELEM);
 #pragma unroll
-    for (int j = 0; j < NWB_NJ; ++j) {
-      const float2 d = __fadd2_rn(*reinterpret_cast<const float2*>(&x[((tid >> 6) * NWB_NJ + j) * SOA_BLK + 2 * (tid & 63)]), qn2[j]);
-      s2 = __ffma2_rn(d, d, s2);
+      for (int j = 0; j < NWB_NJ; ++j) {
+        const float2 v = __half22float2(*reinterpret_cast<const __half2*>(&x[((tid >> 6) * NWB_NJ + j) * SOA_BLK + 2 * (tid & 63)]));
+        const float2 d = __fadd2_rn(v, qn2[j]);
+        s2 = __ffma2_rn(d, d, s2);
+      }
+    } else {
+      const float* x = reinterpret_cast<const float*>(ring + (size_t)stage * NWB_NJ * NN2_TILE * ELEM);
+#pragma unroll
+      for (int j = 0; j < NWB_NJ; ++j) {
+        const float2 d = __fadd2_rn(*reinterpret_cast<const float2*>(&x[((tid >> 6) * NWB_NJ + j) * SOA_BLK + 2 * (tid & 63)]), qn2[j]);
+        s2 = __ffma2_rn(d, d, s2);
+      }
     }
     const int64_t node0 = t0 + 2 * tid;
     const float sa = node0 < hi ? s2.x : 3.0e38f, sb = node0 + 1 < hi ? s2.y : 3.0e38f;
     const unsigned wmin = __reduce_min_sync(0xffffffffu, __float_as_uint(fminf(sa, sb)));
     if (lane == 0) atomicMin(&run_min, wmin);
     __syncthreads();                                    // the stage is consumed and run_min is current
-    if (warp == 0 && tile + NN2_STAGES < tiles) {
+    if (warp == 0 && tile + STAGES < tiles) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      issue(tile + NN2_STAGES, stage);
+      issue(tile + STAGES, stage);
     }
-    const float bound = nn_candidate_bound(__uint_as_float(run_min));
+    const float bound = HALF ? nn_candidate_bound16(__uint_as_float(run_min), eps16) : nn_candidate_bound(__uint_as_float(run_min));
     if (fminf(sa, sb) <= bound) {                       // rare
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
@@ -620,7 +659,7 @@ nn_stream_kernel(const float* __restrict__ soa, const double* __restrict__ aos, 
         }
       }
     }
-    if (++stage == NN2_STAGES) { stage = 0; phase ^= 1u; }
+    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
   }
   const int any_flood = __syncthreads_or(flooded ? 1 : 0);
 
@@ -639,7 +678,7 @@ nn_stream_kernel(const float* __restrict__ soa, const double* __restrict__ aos, 
   };
   double d = 10000.0;
   int i = -1;
-  const float fbound = nn_candidate_bound(__uint_as_float(run_min));
+  const float fbound = HALF ? nn_candidate_bound16(__uint_as_float(run_min), eps16) : nn_candidate_bound(__uint_as_float(run_min));
   if (!any_flood) {
     const int n_c = cand_n;
     for (int c = tid; c < n_c; c += NN2_THREADS)
@@ -648,14 +687,20 @@ nn_stream_kernel(const float* __restrict__ soa, const double* __restrict__ aos, 
         if (dn < 10000.0 && lex_less(dn, cand_node[c], d, i)) { d = dn; i = cand_node[c]; }
       }
   } else {
-    // a flood of near ties: exact rescan of this CTA's range from global memory
+    // a flood of near ties: exact rescan of this CTA's range from global memory (fp32 copy).  HALF: the exact nearest
+    // node is within sqrt(run_min) + eps of the query, which bounds the fp32 distances worth an exact look.
+    float fb32 = fbound;
+    if constexpr (HALF) {
+      const float m = sqrtf(__uint_as_float(run_min)) * (1.0f + 1e-5f) + eps16;
+      fb32 = nn_candidate_bound(m * m * (1.0f + 1e-5f));
+    }
     for (int64_t node = lo + tid; node < hi; node += NN2_THREADS) {
       float sv = 0.f;
       for (int j = 0; j < NWB_NJ; ++j) {
         const float e = (float)qd[j] - soa[soa_index(node, j)];
         sv = fmaf(e, e, sv);
       }
-      if (sv <= fbound) {
+      if (sv <= fb32) {
         const double dn = exact_dist(node);
         if (dn < 10000.0 && lex_less(dn, (int)node, d, i)) { d = dn; i = (int)node; }
       }
@@ -715,17 +760,20 @@ int tree_reserve(nwb_tree* t, int64_t need) {
   cap = (cap + 63) & ~(int64_t)63;
   cap = (cap + TC_N - 1) / TC_N * TC_N;                 // whole tiles of the tensor-core scan copy
   float* soa = nullptr;
+  uint16_t* h16 = nullptr;
   double* aos = nullptr;
   int32_t* pred = nullptr;
   unsigned char* tc = nullptr;
   const size_t tc_bytes = (size_t)(cap / TC_N + 1) * TC_TILE_BYTES;   // + one spare tile: the scan reads tiles in pairs
   TREE_CUDA(t, cudaMalloc(&soa, sizeof(float) * NWB_NJ * cap));
+  TREE_CUDA(t, cudaMalloc(&h16, sizeof(uint16_t) * NWB_NJ * cap));
   TREE_CUDA(t, cudaMalloc(&aos, sizeof(double) * NWB_NJ * cap));
   TREE_CUDA(t, cudaMalloc(&pred, sizeof(int32_t) * cap));
   TREE_CUDA(t, cudaMalloc(&tc, tc_bytes));
   cudaStream_t s = t->ctx->stream;
   TREE_CUDA(t, cudaMemsetAsync(tc, 0, tc_bytes, s));    // rows past the end of the tree hold finite values
   TREE_CUDA(t, cudaMemsetAsync(soa, 0, sizeof(float) * NWB_NJ * cap, s));
+  TREE_CUDA(t, cudaMemsetAsync(h16, 0, sizeof(uint16_t) * NWB_NJ * cap, s));
   if (!t->max_nn) {
     TREE_CUDA(t, cudaMalloc(&t->max_nn, sizeof(unsigned)));
     TREE_CUDA(t, cudaMemsetAsync(t->max_nn, 0, sizeof(unsigned), s));
@@ -734,15 +782,19 @@ int tree_reserve(nwb_tree* t, int64_t need) {
     TREE_CUDA(t, cudaMemcpyAsync(tc, t->tc, (size_t)((t->size + TC_N - 1) / TC_N) * TC_TILE_BYTES, cudaMemcpyDeviceToDevice, s));
     TREE_CUDA(t, cudaMemcpyAsync(soa, t->soa, sizeof(float) * SOA_BLK_FLOATS * (size_t)((t->size + SOA_BLK - 1) / SOA_BLK),
                                  cudaMemcpyDeviceToDevice, s));
+    TREE_CUDA(t, cudaMemcpyAsync(h16, t->h16, sizeof(uint16_t) * SOA_BLK_FLOATS * (size_t)((t->size + SOA_BLK - 1) / SOA_BLK),
+                                 cudaMemcpyDeviceToDevice, s));
     TREE_CUDA(t, cudaMemcpyAsync(aos, t->aos, sizeof(double) * NWB_NJ * t->size, cudaMemcpyDeviceToDevice, s));
     TREE_CUDA(t, cudaMemcpyAsync(pred, t->pred, sizeof(int32_t) * t->size, cudaMemcpyDeviceToDevice, s));
   }
   TREE_CUDA(t, cudaStreamSynchronize(s));
   cudaFree(t->soa);
+  cudaFree(t->h16);
   cudaFree(t->aos);
   cudaFree(t->pred);
   cudaFree(t->tc);
   t->soa = soa;
+  t->h16 = h16;
   t->aos = aos;
   t->pred = pred;
   t->tc = tc;
@@ -827,15 +879,22 @@ int nn_launch(nwb_tree* t, const double* q_dev, int64_t nq, int32_t* idx_dev, do
         nn_small_kernel<<<blocks, NN1_THREADS, 0, s>>>(t->aos, t->size, q_dev, t->part_d, t->part_i, t->tickets, idx_dev, dist_dev);
       }
     } else {
-      constexpr size_t kSmem2 = sizeof(float) * NN2_STAGES * NWB_NJ * NN2_TILE + 8 * NN2_STAGES;
+      constexpr size_t kSmem2 = sizeof(float) * NN2_STAGES * NWB_NJ * NN2_TILE + 8 * NN2_STAGES_H;
       static std::atomic<bool> cfg2[64];
       if (!cfg2[dev].load(std::memory_order_relaxed)) {
-        TREE_CUDA(t, cudaFuncSetAttribute(nn_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem2));
+        TREE_CUDA(t, cudaFuncSetAttribute(nn_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem2));
+        TREE_CUDA(t, cudaFuncSetAttribute(nn_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem2));
         cfg2[dev].store(true, std::memory_order_relaxed);
       }
       const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>(t->ctx->sm_count, (t->size + NN2_TILE - 1) / NN2_TILE));
-      nn_stream_kernel<<<blocks, NN2_THREADS, kSmem2, s>>>(t->soa, t->aos, t->cap, t->size, q_dev, t->part_d, t->part_i, t->tickets,
-                                                           idx_dev, dist_dev);
+      // the fp16 filter copy halves the stream (42 B/node); NWB_NN_NO_F16=1 keeps the fp32 stream for A/B measurements
+      static const bool no_f16 = getenv("NWB_NN_NO_F16") != nullptr;
+      if (no_f16)
+        nn_stream_kernel<false><<<blocks, NN2_THREADS, kSmem2, s>>>(t->soa, t->h16, t->max_nn, t->aos, t->cap, t->size, q_dev, t->part_d,
+                                                                    t->part_i, t->tickets, idx_dev, dist_dev);
+      else
+        nn_stream_kernel<true><<<blocks, NN2_THREADS, kSmem2, s>>>(t->soa, t->h16, t->max_nn, t->aos, t->cap, t->size, q_dev, t->part_d,
+                                                                   t->part_i, t->tickets, idx_dev, dist_dev);
     }
     TREE_CUDA(t, cudaGetLastError());
     TREE_CUDA(t, ev_record(t->ctx, t->ctx->ev1, s));
@@ -897,6 +956,7 @@ void nwb_tree_destroy(nwb_tree* t) {
   cudaSetDevice(t->ctx->device);
   cudaStreamSynchronize(t->ctx->stream);
   cudaFree(t->soa);
+  cudaFree(t->h16);
   cudaFree(t->aos);
   cudaFree(t->pred);
   cudaFree(t->tc);
@@ -928,8 +988,8 @@ int nwb_tree_add_dev(nwb_tree* t, const double* q_dev, const int32_t* pred_dev, 
   int rc = tree_reserve(t, t->size + n);
   if (rc != NWB_OK) return rc;
   const int64_t e = n * NWB_NJ;
-  tree_append_kernel<<<(unsigned)((e + 255) / 256), 256, 0, t->ctx->stream>>>(q_dev, pred_dev, n, t->soa, t->aos, t->pred, t->cap,
-                                                                               t->size);
+  tree_append_kernel<<<(unsigned)((e + 255) / 256), 256, 0, t->ctx->stream>>>(q_dev, pred_dev, n, t->soa, t->h16, t->aos, t->pred,
+                                                                               t->cap, t->size);
   tree_append_tc_kernel<<<(unsigned)((n + 127) / 128), 128, 0, t->ctx->stream>>>(q_dev, n, t->tc, t->size, t->max_nn);
   TREE_CUDA(t, cudaGetLastError());
   t->size += n;

@@ -37,6 +37,7 @@ struct nwb_tree {
   nwb_ctx* ctx = nullptr;
   int64_t size = 0, cap = 0;
   float* soa = nullptr;          // fp32 scan copy, blocked: soa_index(node, joint)
+  uint16_t* h16 = nullptr;       // fp16 filter copy of the single-query stream over large trees, same blocked order (42 B/node)
   double* aos = nullptr;
   int32_t* pred = nullptr;
   unsigned char* tc = nullptr;   // tensor-core scan copy: ceil(cap / 128) tiles of 20480 B (see above)

@@ -232,6 +232,42 @@ def test_nn_randomised_stress_all_forms(ctx, oracle):
         assert (idx == o_idx).all() and np.abs(dist - o_dist).max() < 1e-12, (case, n, nq, kind)
 
 
+@pytest.mark.parametrize("kind", ["shell", "ties", "scaled", "beyond_fp16"])
+def test_single_query_stream_over_the_fp16_filter_copy(ctx, oracle, kind):
+    """One query over a large tree streams the fp16 filter copy and re-evaluates the candidates in fp64: the answer is
+    the oracle's whatever the fp16 rounding does.  shell: thousands of nodes inside the fp16 error shell around the
+    nearest one (differences of 1e-6 ... 5e-3, far below an fp16 ulp); ties: exact duplicates of the nearest node at
+    higher and lower indices; scaled: coordinates up to 200 (the error bound follows the tree's largest |node|);
+    beyond_fp16: one coordinate of 1e5 is not representable - every node becomes a candidate and the exact rescan runs."""
+    rng = np.random.default_rng({"shell": 1, "ties": 2, "scaled": 3, "beyond_fp16": 4}[kind])
+    n = 150_000
+    nodes = OL.uniform_configs(n, seed=77, lhyp_zero=True)
+    q = OL.uniform_configs(6, seed=78)
+    if kind == "shell":
+        for k in range(6):                                     # 3000 nodes at distance 0.05 + (1e-6 ... 5e-3) from query k
+            u = rng.normal(size=(3000, 21))
+            u /= np.linalg.norm(u, axis=1, keepdims=True)
+            r = 0.05 + 10.0 ** rng.uniform(-6, -2.3, 3000)
+            nodes[rng.choice(n, 3000, replace=False)] = q[k] + u * r[:, None]
+    elif kind == "ties":
+        for k in range(6):
+            near = q[k] + 1e-3 * rng.normal(size=21)
+            nodes[rng.choice(n, 40, replace=False)] = near     # 40 exact copies: the lowest index must win
+    elif kind == "scaled":
+        nodes *= 60.0
+        q = q * 60.0
+    else:
+        nodes[12345, 3] = 1.0e5
+    t = nwb.Tree(ctx, 16)
+    t.add(nodes[:70_000])
+    t.add(nodes[70_000:])
+    o_idx, o_dist = oracle.nearest_neighbour(nodes, q, threads=oracle.threads)
+    for k in range(6):
+        idx, dist = t.findNearestNeighbour(q[k:k + 1])
+        assert idx[0] == o_idx[k] and abs(dist[0] - o_dist[k]) < 1e-12, (kind, k, idx[0], o_idx[k])
+    t.close()
+
+
 def test_nn_empty_tree_and_far_nodes(ctx):
     t = nwb.Tree(ctx)
     idx, dist = t.findNearestNeighbour(np.zeros((3, 21)))
