@@ -13,6 +13,31 @@ from . import _abi
 from ._abi import NJ, NFRAMES, NwbError, default_params, load_library
 
 
+_DTYPE_CACHE = {}
+
+
+def _struct_dtype(ct):
+    """numpy structured dtype with the layout of a ctypes Structure (pointers as uint64, nested structs recursively)."""
+    if ct in _DTYPE_CACHE:
+        return _DTYPE_CACHE[ct]
+    names, formats, offsets = [], [], []
+    for name, ftype in ct._fields_:
+        names.append(name)
+        offsets.append(getattr(ct, name).offset)
+        if isinstance(ftype, type) and issubclass(ftype, C.Structure):
+            formats.append(_struct_dtype(ftype))
+        elif isinstance(ftype, type) and issubclass(ftype, C._Pointer):
+            formats.append(np.dtype(np.uint64))
+        elif isinstance(ftype, type) and issubclass(ftype, C.Array):
+            formats.append(np.dtype((np.dtype(ftype._type_), (ftype._length_,))))
+        else:
+            formats.append(np.dtype(ftype))
+    dt = np.dtype({"names": names, "formats": formats, "offsets": offsets, "itemsize": C.sizeof(ct)})
+    _DTYPE_CACHE[ct] = dt
+    return dt
+
+
+
 def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
@@ -344,7 +369,9 @@ class Context:
                     time_from_start=tfs[:n].copy())
 
     def compute_motion_plan_batch(self, positions, directions, wb_start_configs, seeds, execute_trajectory=False, cap=2048):
-        """n compute_motion_plan requests in one call -> list of result dicts (as compute_motion_plan)."""
+        """n compute_motion_plan requests in one call -> list of result dicts (as compute_motion_plan).
+        The request / response arrays of the C ABI are filled and read through numpy views of the ctypes arrays (one
+        vector operation per field instead of a Python loop over 1681 structs)."""
         positions = np.ascontiguousarray(positions, dtype=np.float64).reshape(-1, 3)
         directions = np.ascontiguousarray(directions, dtype=np.float64).reshape(-1, 3)
         starts = np.ascontiguousarray(wb_start_configs, dtype=np.float64).reshape(-1, NJ)
@@ -354,18 +381,32 @@ class Context:
         resps = (_abi.MotionPlanResponse * n)()
         pos = np.empty((n, cap, NJ))                     # rows beyond n_points are never read
         tfs = np.empty((n, cap))
-        pd = C.POINTER(C.c_double)
-        for k in range(n):
-            reqs[k] = _abi.MotionPlanRequest(_abi.Point3(*positions[k]), _abi.Point3(*directions[k]),
-                                             starts[k].ctypes.data_as(pd), NJ, int(execute_trajectory))
-            resps[k].motion_plan = _abi.Trajectory(cap, 0, pos[k].ctypes.data_as(pd), tfs[k].ctypes.data_as(pd))
+        if n:
+            rq = np.frombuffer(reqs, dtype=_struct_dtype(_abi.MotionPlanRequest))
+            rs = np.frombuffer(resps, dtype=_struct_dtype(_abi.MotionPlanResponse))
+            k = np.arange(n, dtype=np.uint64)
+            for c, name in enumerate("xyz"):
+                rq["right_hand_position"][name] = positions[:, c]
+                rq["right_hand_direction"][name] = directions[:, c]
+            rq["wb_start_config"] = starts.ctypes.data + k * np.uint64(NJ * 8)
+            rq["wb_start_config_len"] = NJ
+            rq["execute_trajectory"] = int(execute_trajectory)
+            mp = rs["motion_plan"]
+            mp["capacity"] = cap
+            mp["n_points"] = 0
+            mp["positions"] = pos.ctypes.data + k * np.uint64(cap * NJ * 8)
+            mp["time_from_start"] = tfs.ctypes.data + k * np.uint64(cap * 8)
         self._check(self.lib.nwb_compute_motion_plan_batch(self.h, reqs, resps, n, _p(seeds)), "nwb_compute_motion_plan_batch")
         out = []
-        for k in range(n):
-            m = min(resps[k].motion_plan.n_points, cap)
-            out.append(dict(success=bool(resps[k].success), wb_goal_config=np.array(resps[k].wb_goal_config),
-                            time_goal_config=resps[k].time_goal_config, num_nodes_generated=resps[k].num_nodes_generated,
-                            search_time=resps[k].search_time, trajectory=pos[k, :m].copy(), time_from_start=tfs[k, :m].copy()))
+        if n:
+            m_all = np.minimum(rs["motion_plan"]["n_points"], cap)
+            ok, goal, tg = rs["success"].astype(bool), rs["wb_goal_config"].copy(), rs["time_goal_config"].copy()
+            nodes, st = rs["num_nodes_generated"].copy(), rs["search_time"].copy()
+            for i in range(n):
+                m = int(m_all[i])
+                out.append(dict(success=bool(ok[i]), wb_goal_config=goal[i], time_goal_config=float(tg[i]),
+                                num_nodes_generated=int(nodes[i]), search_time=float(st[i]), trajectory=pos[i, :m],
+                                time_from_start=tfs[i, :m]))       # views into the call's two output arrays
         return out
 
     def _manipulation_result(self, resp, pa, ta, pm, tm, cap):
