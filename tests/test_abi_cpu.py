@@ -62,3 +62,37 @@ def test_no_cpu_fallback_without_gpu():
 def test_missing_library_fails_loudly(tmp_path):
     with pytest.raises(nwb.NwbError, match="not found"):
         _abi.load_library(tmp_path / "libnwb.so")
+
+
+def test_numpy_views_of_the_service_structs_match_the_c_layout():
+    """context._struct_dtype: the batch wrappers fill nwb_motion_plan_request / read nwb_motion_plan_response arrays
+    through numpy views; the structured dtype must reproduce the ctypes (= C) layout field by field."""
+    import ctypes as C
+
+    import numpy as np
+
+    from nao_wholebody_planning_b200 import _abi
+    from nao_wholebody_planning_b200.context import _struct_dtype
+
+    for ct in (_abi.Point3, _abi.Trajectory, _abi.MotionPlanRequest, _abi.MotionPlanResponse, _abi.ManipulationPlanResponse):
+        dt = _struct_dtype(ct)
+        assert dt.itemsize == C.sizeof(ct)
+        for name, _ in ct._fields_:
+            assert dt.fields[name][1] == getattr(ct, name).offset, (ct.__name__, name)
+    n = 5
+    reqs = (_abi.MotionPlanRequest * n)()
+    rq = np.frombuffer(reqs, dtype=_struct_dtype(_abi.MotionPlanRequest))
+    rq["right_hand_direction"]["y"] = np.arange(n) + 0.5
+    rq["wb_start_config"] = np.arange(n, dtype=np.uint64) * 168 + 4096
+    rq["wb_start_config_len"] = 21
+    rq["execute_trajectory"] = 1
+    assert reqs[3].right_hand_direction.y == 3.5 and reqs[4].wb_start_config_len == 21 and reqs[0].execute_trajectory == 1
+    assert C.cast(reqs[2].wb_start_config, C.c_void_p).value == 4096 + 2 * 168
+    resps = (_abi.MotionPlanResponse * n)()
+    rs = np.frombuffer(resps, dtype=_struct_dtype(_abi.MotionPlanResponse))
+    resps[1].success = 1
+    resps[1].num_nodes_generated = 77
+    resps[1].wb_goal_config[20] = -0.25
+    resps[1].motion_plan.n_points = 9
+    assert rs["success"][1] == 1 and rs["num_nodes_generated"][1] == 77 and rs["wb_goal_config"][1, 20] == -0.25
+    assert rs["motion_plan"]["n_points"][1] == 9 and rs["success"][0] == 0
