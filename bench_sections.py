@@ -402,7 +402,8 @@ def section_grasp_queries(torch, dist, nwb, sharding, ctx, OL, orc, dev, rank, w
         mine = sharding.round_robin(n, rank, world)
 
         def plan():
-            res = ctx.compute_motion_plan_batch(pos[mine], dirs[mine], np.tile(CROUCH, (len(mine), 1)), seeds[mine], cap=2048)
+            res = ctx.compute_motion_plan_batch(pos[mine], dirs[mine], np.tile(CROUCH, (len(mine), 1)), seeds[mine], cap=2048,
+                                                reuse_buffers=True)   # the caller keeps its output buffers between calls
             rows, lengths = sharding.pack_trajectories([r["trajectory"] if r["success"] else None for r in res])
             meta = np.array([[int(r["success"]), int(r["num_nodes_generated"])] for r in res], dtype=np.int64).reshape(-1, 2)
             if world == 1:

@@ -368,10 +368,14 @@ class Context:
                     num_nodes_generated=resp.num_nodes_generated, search_time=resp.search_time, trajectory=pos[:n].copy(),
                     time_from_start=tfs[:n].copy())
 
-    def compute_motion_plan_batch(self, positions, directions, wb_start_configs, seeds, execute_trajectory=False, cap=2048):
+    def compute_motion_plan_batch(self, positions, directions, wb_start_configs, seeds, execute_trajectory=False, cap=2048,
+                                  reuse_buffers=False):
         """n compute_motion_plan requests in one call -> list of result dicts (as compute_motion_plan).
         The request / response arrays of the C ABI are filled and read through numpy views of the ctypes arrays (one
-        vector operation per field instead of a Python loop over 1681 structs)."""
+        vector operation per field instead of a Python loop over 1681 structs).  reuse_buffers: the trajectory output
+        arrays are kept on the context and handed to the next call of the same shape, as a C++ caller would keep its
+        buffers - the library then writes into resident pages instead of first-touching ~7 pages per request; the
+        returned trajectories are views that the NEXT such call overwrites."""
         positions = np.ascontiguousarray(positions, dtype=np.float64).reshape(-1, 3)
         directions = np.ascontiguousarray(directions, dtype=np.float64).reshape(-1, 3)
         starts = np.ascontiguousarray(wb_start_configs, dtype=np.float64).reshape(-1, NJ)
@@ -379,8 +383,14 @@ class Context:
         n = len(positions)
         reqs = (_abi.MotionPlanRequest * n)()
         resps = (_abi.MotionPlanResponse * n)()
-        pos = np.empty((n, cap, NJ))                     # rows beyond n_points are never read
-        tfs = np.empty((n, cap))
+        cached = getattr(self, "_mp_buffers", None)
+        if reuse_buffers and cached is not None and cached[0].shape == (n, cap, NJ):
+            pos, tfs = cached
+        else:
+            pos = np.empty((n, cap, NJ))                 # rows beyond n_points are never read
+            tfs = np.empty((n, cap))
+            if reuse_buffers:
+                self._mp_buffers = (pos, tfs)
         if n:
             rq = np.frombuffer(reqs, dtype=_struct_dtype(_abi.MotionPlanRequest))
             rs = np.frombuffer(resps, dtype=_struct_dtype(_abi.MotionPlanResponse))
